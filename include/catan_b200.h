@@ -1,0 +1,116 @@
+/*
+ * catan_b200.h — C ABI of the B200-native Catan self-play engine (libcatan_b200.so).
+ *
+ * This is the drop-in boundary for the reference's env-step + PPO-rollout hot path.  The reference
+ * has no FFI of its own (it is pure Python); the boundary there is the Python class
+ * env.wrapper.EnvWrapper (env/wrapper.py:11) and RL/ppo/process_batch.py's BatchProcessor.  Every
+ * entry point below names the reference interface it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  `*_dev` pointers are device memory owned by
+ *     the caller (e.g. tensor.data_ptr()); the library never allocates memory the caller sees.
+ *   - every call returns 0 on success, < 0 on failure; catan_last_error() gives the message
+ *     (thread-local).  Nothing throws across the ABI.  Illegal actions never abort a launch: they
+ *     are reported per env in the info row (CATAN_INFO_ERR) and OR-ed into a sticky flag word
+ *     (reference behaviour: RuntimeError from EnvWrapper.step, env/wrapper.py:38-41).
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  All launches are
+ *     asynchronous on it; only the *_host / export / import / read_* calls synchronise.
+ *   - a handle is bound to one device and is used from one host thread at a time.
+ *   - layouts: catan_layout.h.
+ */
+#ifndef CATAN_B200_H
+#define CATAN_B200_H
+
+#include "catan_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct catan_env catan_env_t;
+
+/* library / layout introspection (used by the host side to check it agrees with the binary) */
+int catan_abi_version(void);
+int catan_obs_stride(void);
+int catan_mask_stride(void);
+int catan_info_stride(void);
+int catan_action_words(void);
+int catan_state_words(void);
+int catan_record_bytes(void);          /* packed per-game record in HBM */
+const char* catan_last_error(void);
+
+/* reference defaults == EnvWrapper.__init__ kwargs (env/wrapper.py:12-28), auto_reset = 1 */
+void catan_default_config(catan_config_t* cfg);
+
+/* Replaces constructing n_envs EnvWrapper objects (RL/ppo/game_manager.py:16).  Games are numbered
+ * first_env_id .. first_env_id + n_envs - 1; game i draws from Philox key (seed, i), so results do not
+ * depend on how games are sharded over devices. */
+int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, const catan_config_t* cfg,
+                 catan_env_t** out);
+int catan_destroy(catan_env_t* env);
+int catan_num_envs(const catan_env_t* env);
+
+/* EnvWrapper attributes that callers mutate (RL/ppo/game_manager.py:164-166: reward_annealing_factor). */
+int catan_set_config(catan_env_t* env, const catan_config_t* cfg);
+
+/* Output buffers (device): obs uint8[n][CATAN_OBS_STRIDE], masks uint8[n][CATAN_MASK_STRIDE],
+ * reward float[n][4] (by player index), info uint8[n][CATAN_INFO_STRIDE].  16-byte aligned. */
+int catan_bind(catan_env_t* env, uint8_t* obs_dev, uint8_t* masks_dev, float* reward_dev, uint8_t* info_dev);
+
+/* EnvWrapper.reset (env/wrapper.py:30-34) for every env (reset_mask_dev == NULL) or for envs whose
+ * mask byte is non-zero; writes obs + masks (+ info actor). */
+int catan_reset(catan_env_t* env, const uint8_t* reset_mask_dev, void* stream);
+
+/* EnvWrapper.step + get_action_masks fused over all envs (env/wrapper.py:36-50, :168-290):
+ * actions int32[n][CATAN_ACTION_WORDS].  Writes obs, masks, reward, info.  With cfg.auto_reset a game
+ * that ends is reset inside the same launch (info RESET = 1; obs/masks describe the new game, reward /
+ * DONE / WINNER / FINAL_VP describe the finished one). */
+int catan_step(catan_env_t* env, const int32_t* actions_dev, void* stream);
+
+/* Random-legal policy used for the env-only benchmark: samples one composite action
+ * per env from the bound masks/obs into actions_out_dev. */
+int catan_sample_random(catan_env_t* env, int32_t* actions_out_dev, void* stream);
+
+/* catan_step followed by catan_sample_random in ONE launch: consumes actions_io_dev and overwrites it
+ * with the next random-legal action of every env. */
+int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream);
+
+/* Same as catan_step but with HOST buffers: copies the actions host->device, steps, copies
+ * obs/masks/reward/info device->host and synchronises.  Any output pointer may be NULL (not copied).
+ * This is the call an EnvWrapper-shaped Python adapter makes. */
+int catan_step_host(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host,
+                    float* reward_host, uint8_t* info_host, void* stream);
+int catan_reset_host(catan_env_t* env, uint8_t* obs_host, uint8_t* masks_host, uint8_t* info_host, void* stream);
+
+/* EnvWrapper.save_state / restore_state (env/wrapper.py:711-721; game/game.py:1013-1205) as the
+ * canonical int16 state (catan_state_t) of `count` envs starting at `first`.  Host buffers;
+ * synchronous.  import also re-encodes obs/masks of the touched envs. */
+int catan_export_state(catan_env_t* env, int first, int count, int16_t* states_host);
+int catan_import_state(catan_env_t* env, int first, int count, const int16_t* states_host);
+
+/* sticky per-env error flags (bit c set = CATAN_ERR_* code c was raised since the last clear). */
+int catan_read_err_flags(catan_env_t* env, uint32_t* flags_host, int clear);
+
+/* ---- PPO rollout path (RL/ppo/process_batch.py) -------------------------------------------------
+ * All arrays are device fp32, time-major [T(+1)][N] like the reference's [T+1, N, 1] tensors. */
+
+/* process_batch.py:134-140: GAE reverse scan.  rewards[T][N], values[T+1][N] (already denormalised),
+ * masks[T+1][N]; writes returns[T][N] and advantages[T][N] = returns - values[:-1] (un-normalised).
+ * Arithmetic is IEEE fp32 in the reference's evaluation order (no FMA contraction). */
+int catan_gae(const float* rewards_dev, const float* values_dev, const float* masks_dev, int T, int N,
+              double gamma, double gae_lambda, float* returns_dev, float* advantages_dev, void* stream);
+
+/* process_batch.py:141-142: advantages <- (A - mean(A)) / (std_unbiased(A) + eps) over all elements,
+ * in place.  stats_dev: double[3] = (count, sum, sum of squares).
+ *   catan_adv_stats : overwrites stats_dev with the statistics of this device's `count` advantages
+ *   catan_adv_apply : normalises with stats_dev.  When envs are sharded over GPUs the caller sum-all-reduces
+ *                     the three doubles between the two calls to get the reference's global statistics
+ *                     (SURVEY.md 8e); that 24-byte exchange is the only collective on this path. */
+int catan_adv_stats(const float* advantages_dev, long long count, double* stats_dev, void* stream);
+int catan_adv_apply(float* advantages_dev, long long count, const double* stats_dev, double eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATAN_B200_H */

@@ -1,0 +1,23 @@
+"""settlers_of_catan_rl_b200 — B200-native vectorised Catan self-play engine.
+
+Only the env-step + PPO-rollout hot path of henrycharlesworth/settlers_of_catan_RL lives here:
+``VecCatanEnv`` (vector env on CUDA tensors), ``EnvWrapper`` (single-env adapter with the reference's
+surface), and the rollout kernels (``gae``, ``normalise_advantages``).  The CUDA library is loaded
+lazily; there is no CPU implementation.
+"""
+from . import layout  # noqa: F401
+
+__all__ = ["layout", "VecCatanEnv", "EnvWrapper", "gae", "normalise_advantages", "RolloutStorage"]
+
+
+def __getattr__(name):
+    if name == "VecCatanEnv":
+        from .vec_env import VecCatanEnv
+        return VecCatanEnv
+    if name == "EnvWrapper":
+        from .env_wrapper import EnvWrapper
+        return EnvWrapper
+    if name in ("gae", "normalise_advantages", "RolloutStorage"):
+        from . import rollout
+        return getattr(rollout, name)
+    raise AttributeError(name)

@@ -1423,7 +1423,6 @@ CATAN_FN void sample_action(const uint8_t* m, const uint8_t* o, uint64_t seed, u
 // ------------------------------------------------------------------------------------------------
 // packed record <-> canonical state (host side of catan_export_state / catan_import_state)
 // ------------------------------------------------------------------------------------------------
-#if !defined(__CUDA_ARCH__)
 static inline void rec_to_state(const GameRec& g, catan_state_t& s) {
   memset(&s, 0, sizeof(s));
   for (int i = 0; i < 19; ++i) { s.tile_res[i] = g.tile_res[i]; s.tile_val[i] = g.tile_val[i]; }
@@ -1516,6 +1515,5 @@ static inline void state_to_rec(const catan_state_t& s, GameRec& g) {
   g.winner = static_cast<uint8_t>(s.winner);
   g.rng_ctr = static_cast<uint32_t>(static_cast<uint16_t>(s.rng_ctr_lo)) | (static_cast<uint32_t>(static_cast<uint16_t>(s.rng_ctr_hi)) << 16);
 }
-#endif
 
 }  // namespace catanb

@@ -1,0 +1,163 @@
+"""``VecCatanEnv`` — N four-player Catan games advanced in lock-step on one B200.
+
+The vector counterpart of the reference's ``EnvWrapper`` (env/wrapper.py:11-50): ``reset()`` /
+``step(actions)`` keep their meaning, but observations, legal-action masks, rewards and step info are
+written by the kernels straight into PyTorch-owned CUDA tensors (``obs`` uint8 [N, 1920], ``masks``
+uint8 [N, 336], ``reward`` fp32 [N, 4], ``info`` uint8 [N, 16]); nothing crosses PCIe inside a
+rollout.  PyTorch is only plumbing here (device memory + the current stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, layout as L
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class VecCatanEnv:
+    def __init__(self, n_envs: int, device="cuda:0", seed: int = 0, first_env_id: int = 0, **config):
+        if not torch.cuda.is_available():
+            raise _lib.CatanError("VecCatanEnv needs a CUDA device: there is no CPU implementation of the engine")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CatanError("VecCatanEnv runs on CUDA devices only")
+        self.n_envs = int(n_envs)
+        self.seed, self.first_env_id = int(seed), int(first_env_id)
+        self.config = _lib.make_config(**config)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._h = C.c_void_p()
+        _lib.check(self.lib.catan_create(self.n_envs, idx, self.seed, self.first_env_id, C.byref(self.config),
+                                         C.byref(self._h)))
+        dev = self.device
+        self.obs = torch.zeros((self.n_envs, L.OBS_STRIDE), dtype=torch.uint8, device=dev)
+        self.masks = torch.zeros((self.n_envs, L.MASK_STRIDE), dtype=torch.uint8, device=dev)
+        self.reward = torch.zeros((self.n_envs, 4), dtype=torch.float32, device=dev)
+        self.info = torch.zeros((self.n_envs, L.INFO_STRIDE), dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.catan_bind(self._h, _ptr(self.obs), _ptr(self.masks), _ptr(self.reward), _ptr(self.info)))
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.catan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ EnvWrapper surface, vectorised
+    def reset(self, reset_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """EnvWrapper.reset for all envs (or those with a non-zero byte in ``reset_mask``)."""
+        if reset_mask is not None:
+            assert reset_mask.dtype == torch.uint8 and reset_mask.is_cuda and reset_mask.numel() == self.n_envs
+        _lib.check(self.lib.catan_reset(self._h, _ptr(reset_mask), self._stream()))
+        self.kernel_launches += 1
+        return self.obs
+
+    def step(self, actions: torch.Tensor):
+        """EnvWrapper.step + get_action_masks for all envs.  ``actions``: int32 CUDA tensor [N, 20]."""
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous()
+        assert actions.shape == (self.n_envs, L.ACTION_WORDS)
+        _lib.check(self.lib.catan_step(self._h, _ptr(actions), self._stream()))
+        self.kernel_launches += 1
+        return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
+
+    def sample_random(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((self.n_envs, L.ACTION_WORDS), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.catan_sample_random(self._h, _ptr(out), self._stream()))
+        self.kernel_launches += 1
+        return out
+
+    def step_sample(self, actions_io: torch.Tensor):
+        """One launch: apply ``actions_io`` and overwrite it with the next random-legal actions."""
+        assert actions_io.dtype == torch.int32 and actions_io.is_cuda and actions_io.is_contiguous()
+        _lib.check(self.lib.catan_step_sample(self._h, _ptr(actions_io), self._stream()))
+        self.kernel_launches += 1
+        return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
+
+    def get_action_masks(self) -> torch.Tensor:
+        return self.masks
+
+    # ------------------------------------------------------------------ host-buffer path (the e2e call)
+    def step_host(self, actions: np.ndarray, obs: np.ndarray = None, masks: np.ndarray = None, reward: np.ndarray = None,
+                  info: np.ndarray = None) -> None:
+        def p(a):
+            return C.c_void_p(0 if a is None else a.ctypes.data)
+        assert actions.dtype == np.int32 and actions.flags.c_contiguous
+        _lib.check(self.lib.catan_step_host(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
+        self.kernel_launches += 1
+
+    def reset_host(self, obs: np.ndarray = None, masks: np.ndarray = None, info: np.ndarray = None) -> None:
+        def p(a):
+            return C.c_void_p(0 if a is None else a.ctypes.data)
+        _lib.check(self.lib.catan_reset_host(self._h, p(obs), p(masks), p(info), self._stream()))
+        self.kernel_launches += 1
+
+    # ------------------------------------------------------------------ state export / import (save_state / restore_state)
+    def export_state(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n_envs - first if count is None else count
+        out = np.zeros((count, L.STATE_WORDS), dtype=np.int16)
+        _lib.check(self.lib.catan_export_state(self._h, first, count, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def import_state(self, states: np.ndarray, first: int = 0) -> None:
+        states = np.ascontiguousarray(states, dtype=np.int16).reshape(-1, L.STATE_WORDS)
+        _lib.check(self.lib.catan_import_state(self._h, first, states.shape[0], C.c_void_p(states.ctypes.data)))
+        self.kernel_launches += 1
+
+    def err_flags(self, clear: bool = False) -> np.ndarray:
+        out = np.zeros(self.n_envs, dtype=np.uint32)
+        _lib.check(self.lib.catan_read_err_flags(self._h, C.c_void_p(out.ctypes.data), int(clear)))
+        return out
+
+    def set_reward_annealing_factor(self, factor: float) -> None:
+        """EnvWrapper.reward_annealing_factor (RL/ppo/game_manager.py:164-166)."""
+        self.config.reward_annealing_factor = float(factor)
+        _lib.check(self.lib.catan_set_config(self._h, C.byref(self.config)))
+
+    # ------------------------------------------------------------------ views for the policy
+    def obs_views(self) -> Dict[str, torch.Tensor]:
+        """Zero-copy uint8 views of the packed observation, keyed like the reference's obs dict."""
+        out = {}
+        for key, off, shape in L.OBS_NUMERIC:
+            n = int(np.prod(shape))
+            out[key] = self.obs[:, off:off + n].view(self.n_envs, *shape)
+        for key, li in L.OBS_LISTS:
+            a = L.OBS_DEV_LISTS + li * L.OBS_DEV_PAD
+            out[key] = self.obs[:, a:a + L.OBS_DEV_PAD]
+        out["player_id"] = self.obs[:, L.OBS_META]
+        return out
+
+    def obs_float(self, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+        """The observation as the float tensors ``policy.obs_to_torch`` would produce (RL/models/policy.py:168-183):
+        numeric blocks cast to ``dtype`` with the two ratio features rescaled; card lists as int64 [N, 25]."""
+        f = self.obs[:, :L.OBS_FEATURES].to(dtype)
+        for col, div in L.OBS_RATIO_COLUMNS:
+            f[:, col] *= 1.0 / div
+        out = {}
+        for key, off, shape in L.OBS_NUMERIC:
+            n = int(np.prod(shape))
+            out[key] = f[:, off:off + n].view(self.n_envs, *shape)
+        for key, li in L.OBS_LISTS:
+            a = L.OBS_DEV_LISTS + li * L.OBS_DEV_PAD
+            out[key] = self.obs[:, a:a + L.OBS_DEV_PAD].long()
+        return out
+
+    def mask_views(self):
+        """List of 12 uint8 views shaped like EnvWrapper.get_action_masks() with a leading env dim."""
+        return [self.masks[:, off:off + int(np.prod(shape))].view(self.n_envs, *shape) for off, shape in L.MASK_HEADS]
