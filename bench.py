@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Catan env-step hot path (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (CUDA kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference's algorithm on host cores
+
+Workload (config.workload): 65 536 parallel 4-player games per GPU, random-legal policy, one "step" = one
+lock-step tick of every game = ONE fused launch (apply action -> auto-reset -> legal-action masks ->
+packed observation -> next random-legal action).  metric = env steps per second, whole job.
+Prints ONE JSON line on rank 0.  See DESIGN.md §measurement for how every field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ENVS_PER_GPU = 65536
+METRIC = "env_steps_per_sec"
+UNIT = "env steps/s"
+# algorithmic bytes per env step with the int8 obs/mask layout =
+# obs 1867 + masks 325 + action 80 + state 640 read + 640 write
+ALGO_BYTES_PER_ENV_STEP = 3552
+WORKLOAD = "65536 parallel envs per GPU, random-legal policy, fused step+auto-reset+masks+obs+sample (BASELINE configs[1])"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU, help="games per GPU (default: the BASELINE config)")
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (C oracle port; the Python reference cannot travel)
+# ------------------------------------------------------------------------------------------------
+def cpu_rollout_rate(seconds: float, n_envs: int = 4096, chunk: int = 25, seed: int = 0):
+    """time the oracle's sample->step->masks->obs loop on all host threads for ~`seconds`; returns (steps/s, threads, sample)"""
+    from oracle import oracle_lib as O
+    v = O.OracleVec(n_envs, seed=seed, first_env_id=0)
+    v.run(chunk)                                   # reset + warm-up
+    done_steps, t0 = 0, time.perf_counter()
+    while True:
+        v.run(chunk)
+        done_steps += n_envs * chunk
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+    return done_steps / dt, v.threads_used, "%d envs x %d ticks, %.1f s, C port of game.py+wrapper.py on %d host threads" % (
+        n_envs, done_steps // n_envs, dt, v.threads_used)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle_lib as O
+    # calibrate the per-step sample so that (steps + warmup) ticks finish in about a minute
+    rate, threads, _ = cpu_rollout_rate(2.0, n_envs=2048, chunk=10, seed=args.seed)
+    total_ticks = max(1, args.steps + args.warmup)
+    n_envs = int(max(64, min(args.envs, rate * 60.0 / total_ticks)))
+    n_envs = max(64, (n_envs // 64) * 64)
+    v = O.OracleVec(n_envs, seed=args.seed, first_env_id=0)
+    v.run(0)
+    for _ in range(args.warmup):
+        v.run(1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v.run(1)
+    dt = time.perf_counter() - t0
+    value = n_envs * args.steps / dt
+    sample = "%d envs x %d ticks per timed run (one tick per step), all %d host threads" % (n_envs, args.steps, v.threads_used)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_step": n_envs,
+                   "note": "reference is pure Python and does not travel to the GPU box; this arm times the pinned C port of its "
+                           "algorithm (oracle/) on the host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": v.threads_used, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# this build
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L, gae, normalise_advantages
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.envs
+    # games are numbered globally: rank r owns [r*n, (r+1)*n) — no data-path collective
+    env = VecCatanEnv(n, device=dev, seed=args.seed, first_env_id=rank * n)
+    env.reset()
+    acts = env.sample_random()
+    for _ in range(max(3, args.warmup)):
+        env.step_sample(acts)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = env.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        env.step_sample(acts)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.kernel_launches - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    games_done = int(env.info[:, L.INFO_DONE].sum().item())  # touch the result
+    errs = int(env.err_flags().any())
+
+    # ---- e2e: the same tick through the host-buffer call (catan_step_host): pinned host actions in, obs/masks/reward/info out
+    e2e_steps = max(1, args.e2e_steps)
+    h_act = torch.empty((n, L.ACTION_WORDS), dtype=torch.int32).pin_memory()
+    h_obs = torch.empty((n, L.OBS_STRIDE), dtype=torch.uint8).pin_memory()
+    h_masks = torch.empty((n, L.MASK_STRIDE), dtype=torch.uint8).pin_memory()
+    h_rew = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    h_info = torch.empty((n, L.INFO_STRIDE), dtype=torch.uint8).pin_memory()
+    d_act = torch.empty((n, L.ACTION_WORDS), dtype=torch.int32, device=dev)
+
+    def e2e_tick():
+        env.sample_random(d_act)                       # the "policy" (on device), its actions brought to the host ...
+        h_act.copy_(d_act, non_blocking=False)
+        # ... and the reference-facing call: host actions in, host obs/masks/reward/info out
+        env.step_host(h_act.numpy(), h_obs.numpy(), h_masks.numpy(), h_rew.numpy(), h_info.numpy())
+
+    for _ in range(3):
+        e2e_tick()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_tick()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * e2e_steps / float(te.item())
+    h2d = n * L.ACTION_WORDS * 4
+    d2h = n * (L.OBS_STRIDE + L.MASK_STRIDE + 16 + L.INFO_STRIDE) + n * L.ACTION_WORDS * 4
+
+    # ---- PPO-side kernels at BASELINE config 4 size (T=200, N=131072), rank 0, reported as aux numbers
+    aux = {}
+    if rank == 0:
+        T, N = 200, 131072
+        r = torch.rand(T, N, device=dev)
+        val = torch.rand(T + 1, N, device=dev) * 300.0
+        m = (torch.rand(T + 1, N, device=dev) > 0.01).float()
+        ret, adv = torch.empty_like(r), torch.empty_like(r)
+        for _ in range(3):
+            gae(r, val, m, 0.999, 0.95, ret, adv)
+            normalise_advantages(adv)
+        torch.cuda.synchronize()
+        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        reps = 10
+        gae_ms = norm_ms = 0.0
+        for _ in range(reps):
+            a0.record()
+            gae(r, val, m, 0.999, 0.95, ret, adv)
+            a1.record()
+            normalise_advantages(adv)
+            a2.record()
+            torch.cuda.synchronize()
+            gae_ms += a0.elapsed_time(a1)
+            norm_ms += a1.elapsed_time(a2)
+        gae_ms /= reps
+        norm_ms /= reps
+        elems = T * N
+        aux = {"gae_T200_N131072": {"ms": gae_ms, "GB/s": elems * 20 / gae_ms / 1e6, "bytes_per_elem": 20},
+               "adv_norm_T200_N131072": {"ms": norm_ms, "GB/s": elems * 12 / norm_ms / 1e6, "bytes_per_elem": 12}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, threads, sample = cpu_rollout_rate(args.cpu_seconds, seed=args.seed)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        per_launch_ms = ms_max / args.steps
+        achieved = ALGO_BYTES_PER_ENV_STEP * n / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("env_kernel_step_sample_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        value = n * world * args.steps / (ms_max * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "seed": args.seed,
+                       "l2": "no explicit flush: one step streams %.0f MB (records+obs+masks+actions) > 126 MB L2" % (
+                           n * (2 * 832 + L.OBS_STRIDE + L.MASK_STRIDE + 160 + 32) / 1e6),
+                       "games_finished_in_last_step": games_done, "rejected_actions": errs},
+            "clocks": clock_info,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "call": "catan_step_host (pinned host actions in; obs+masks+reward+info out to pinned host)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "env_kernel<MODE_STEP, SAMPLE>",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n, "peak_source": peak_src},
+            "cpu_baseline": cpu_baseline,
+            "aux": aux,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
