@@ -10,7 +10,8 @@ import os
 
 from . import layout as L
 
-_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcatan_b200.so")
+# CATAN_B200_LIB lets profiles/phase_profile.py load the instrumented build of the SAME sources; never a fallback
+_SO = os.environ.get("CATAN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcatan_b200.so")
 
 
 class CatanConfig(C.Structure):

@@ -32,6 +32,18 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+PROF_SO = os.path.join(CSRC, "libcatan_b200_prof.so")
+
+
+def build_profiling_extension() -> str:
+    """instrumented twin (-DCATAN_PROFILE_PHASES): per-phase clock64 timers, used only by profiles/phase_profile.py"""
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-DCATAN_PROFILE_PHASES", "-o", PROF_SO] + list(SOURCES)
+    res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    return PROF_SO
+
+
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO

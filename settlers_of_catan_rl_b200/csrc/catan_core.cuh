@@ -24,11 +24,15 @@
 
 #if defined(__CUDACC__) && !defined(CATAN_HOST_EMU)
 #define CATAN_FN __device__ __forceinline__
+// phase-sized functions are emitted ONCE and called: the step kernel must stay small enough for the
+// instruction caches (profiles/r1_notes.md: 60% of stalls were stall_no_inst with everything inlined)
 #define CATAN_FN_NOINLINE __device__ __noinline__
+#define CATAN_NO_UNROLL _Pragma("unroll 1")
 #define CATAN_LANES 32
 #else
 #define CATAN_FN static inline
 #define CATAN_FN_NOINLINE static
+#define CATAN_NO_UNROLL
 #define CATAN_LANES 1
 #endif
 
@@ -148,7 +152,10 @@ struct alignas(16) WarpScratch {
   uint8_t err;
   uint8_t seat[5];           // seat of PlayerId (index 1..4)
   uint8_t acted_pid, act_type, roll_info, did_reset, done;
-  uint8_t pad_[2];
+  Act act;                   // translated action (wrapper.py:114-166), filled by step_begin
+  uint8_t lr_len, lr_shrunk;  // block-cooperative longest-road search: length of lr_pid, "holder's path shrank"
+  uint8_t lr_other[5];       // lengths of the other players (index PlayerId), only when lr_shrunk
+  uint8_t pad_[6];
 };
 static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must stay 16-byte granular");
 
@@ -156,12 +163,35 @@ struct Ctx {
   GameRec* g;
   const Topo* T;
   WarpScratch* ws;
-  uint8_t* obs;              // staging row, CATAN_OBS_STRIDE bytes (also DFS scratch)
+  uint8_t* obs;              // staging row, CATAN_OBS_STRIDE bytes
   uint8_t* mask;             // staging row, CATAN_MASK_STRIDE bytes
+  uint8_t* scratch;          // >= CATAN_LP_SCRATCH_BYTES, 16-byte aligned; may alias obs+mask (dead during the transition)
   const catan_config_t* cfg;
   uint64_t seed, env_id;
   int lane;
+#ifdef CATAN_PROFILE_PHASES
+  long long prof_t;
+  unsigned long long* prof;  // [phase][4] = {sum cycles, max cycles, count, -}
+#endif
 };
+
+// phase timers of the profiling build (profiles/phase_profile.py); compiled out of the product
+enum { PH_LOAD = 0, PH_SCALAR, PH_DICE, PH_EST, PH_LROAD, PH_FINISH, PH_MASKS, PH_OBS, PH_SAMPLE, PH_STORE, PH_COUNT };
+#ifdef CATAN_PROFILE_PHASES
+__device__ __forceinline__ void prof_mark(Ctx& cx, int ph) {
+  if (cx.lane == 0) {
+    const long long t = clock64();
+    const unsigned long long d = static_cast<unsigned long long>(t - cx.prof_t);
+    atomicAdd(&cx.prof[ph * 4 + 0], d);
+    atomicMax(&cx.prof[ph * 4 + 1], d);
+    atomicAdd(&cx.prof[ph * 4 + 2], 1ull);
+    cx.prof_t = clock64();
+  }
+}
+#define CATAN_PROF(cx, ph) prof_mark(cx, ph)
+#else
+#define CATAN_PROF(cx, ph) ((void)0)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // warp primitives
@@ -199,8 +229,8 @@ CATAN_FN uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 CATAN_FN uint32_t mulhi32(uint32_t a, uint32_t b) { return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32); }
 #endif
 
-CATAN_FN void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
-#pragma unroll
+CATAN_FN_NOINLINE void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  CATAN_NO_UNROLL
   for (int i = 0; i < 10; ++i) {
     uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -219,7 +249,7 @@ CATAN_FN uint32_t rng_next(Ctx& cx) {   // [L0] next word of the game stream
   return w[d & 3];
 }
 CATAN_FN int rng_bounded(Ctx& cx, int n) { return static_cast<int>(mulhi32(rng_next(cx), static_cast<uint32_t>(n))); }
-CATAN_FN void rng_shuffle(Ctx& cx, uint8_t* a, int n) {   // [L0]
+CATAN_FN_NOINLINE void rng_shuffle(Ctx& cx, uint8_t* a, int n) {   // [L0]
   for (int i = n - 1; i >= 1; --i) {
     int j = rng_bounded(cx, i + 1);
     uint8_t t = a[i]; a[i] = a[j]; a[j] = t;
@@ -249,6 +279,7 @@ CATAN_FN int best_exchange_rate(const GameRec& g, int pid, int r) {   // wrapper
 }
 CATAN_FN int count_cards(const uint8_t* list, int n, int card) {
   int k = 0;
+  CATAN_NO_UNROLL
   for (int i = 0; i < n; ++i) k += list[i] == card;
   return k;
 }
@@ -256,7 +287,7 @@ CATAN_FN int count_cards(const uint8_t* list, int n, int card) {
 // ------------------------------------------------------------------------------------------------
 // placement predicates (corner.py:24-39, edge.py:23-42)  [P]
 // ------------------------------------------------------------------------------------------------
-CATAN_FN bool can_place_settlement(const GameRec& g, const Topo& T, int c, int pid, bool initial) {
+CATAN_FN_NOINLINE bool can_place_settlement(const GameRec& g, const Topo& T, int c, int pid, bool initial) {
   if (g.corner[c]) return false;
   bool own_road = false;
 #pragma unroll
@@ -269,7 +300,7 @@ CATAN_FN bool can_place_settlement(const GameRec& g, const Topo& T, int c, int p
   return initial || own_road;
 }
 
-CATAN_FN bool can_place_road(const GameRec& g, const Topo& T, int e, int pid, bool after_second, int second_corner) {
+CATAN_FN_NOINLINE bool can_place_road(const GameRec& g, const Topo& T, int e, int pid, bool after_second, int second_corner) {
   if (g.edge[e]) return false;
   int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
   if (after_second) return c1 == second_corner || c2 == second_corner;
@@ -288,7 +319,7 @@ CATAN_FN bool can_place_road(const GameRec& g, const Topo& T, int e, int pid, bo
 // ------------------------------------------------------------------------------------------------
 // reset: Board.reset (board.py:67-167) + Game.reset (game.py:39-136) + EnvWrapper.reset (wrapper.py:30-34)  [L0]
 // ------------------------------------------------------------------------------------------------
-CATAN_FN bool number_order_ok(const Topo& T, const uint8_t* numbers, const uint8_t* terrain) {   // board.py:50-65
+CATAN_FN_NOINLINE bool number_order_ok(const Topo& T, const uint8_t* numbers, const uint8_t* terrain) {   // board.py:50-65
   uint8_t vals[19];
   int n = 0;
   for (int i = 0; i < 19; ++i) {
@@ -341,7 +372,7 @@ CATAN_FN_NOINLINE void reset_game(Ctx& cx) {   // [L0]
 // ------------------------------------------------------------------------------------------------
 // translate (wrapper.py:114-166, :414-486) and validate (game.py:264-525)  [L0]
 // ------------------------------------------------------------------------------------------------
-CATAN_FN int translate_action(const Ctx& cx, const int32_t* a, Act& t) {
+CATAN_FN_NOINLINE int translate_action(const Ctx& cx, const int32_t* a, Act& t) {
   const GameRec& g = *cx.g;
   memset(&t, 0, sizeof(Act));
   const int type = a[CATAN_A_TYPE], pg = g.players_go;
@@ -417,7 +448,7 @@ CATAN_FN int translate_action(const Ctx& cx, const int32_t* a, Act& t) {
   }
 }
 
-CATAN_FN int validate_action(const Ctx& cx, const Act& t) {
+CATAN_FN_NOINLINE int validate_action(const Ctx& cx, const Act& t) {
   const GameRec& g = *cx.g;
   const Topo& T = *cx.T;
   const int pid = g.players_go, p = pid - 1;
@@ -535,7 +566,7 @@ CATAN_FN void advance_seat(GameRec& g, bool left) {   // game.py:253-262
   g.players_go = g.player_order[g.player_order_id];
 }
 
-CATAN_FN void update_largest_army(GameRec& g) {   // game.py:817-841  [L0]
+CATAN_FN_NOINLINE void update_largest_army(GameRec& g) {   // game.py:817-841  [L0]
   const int order[4] = {BLUE, WHITE, RED, ORANGE};
   int max_count = 0, cp = 0;
   for (int i = 0; i < 4; ++i) {
@@ -554,10 +585,11 @@ CATAN_FN void update_largest_army(GameRec& g) {   // game.py:817-841  [L0]
   }
 }
 
-CATAN_FN_NOINLINE void apply_scalar(Ctx& cx, const Act& t) {   // [L0]
+CATAN_FN_NOINLINE void apply_scalar(Ctx& cx) {   // [L0]
   GameRec& g = *cx.g;
   const Topo& T = *cx.T;
   WarpScratch& ws = *cx.ws;
+  const Act& t = ws.act;
   const int pid = g.players_go, p = pid - 1;
   switch (t.type) {
     case CATAN_ACT_PLACE_SETTLEMENT: {                               // game.py:530-555, :195-212
@@ -799,7 +831,7 @@ CATAN_FN_NOINLINE void apply_scalar(Ctx& cx, const Act& t) {   // [L0]
 // ------------------------------------------------------------------------------------------------
 // dice payout (game.py:151-175)  [W]
 // ------------------------------------------------------------------------------------------------
-CATAN_FN void dice_payout(Ctx& cx) {
+CATAN_FN_NOINLINE void dice_payout(Ctx& cx) {
   GameRec& g = *cx.g;
   const Topo& T = *cx.T;
   WarpScratch& ws = *cx.ws;
@@ -842,7 +874,7 @@ CATAN_FN void dice_payout(Ctx& cx) {
 //   dice     : the 20 calls of one roll folded into one pass (game.py:170-175; Q4)
 //   monopoly : update_resource_estimates_monopoly (game.py:973-1010)
 // ------------------------------------------------------------------------------------------------
-CATAN_FN void est_apply(Ctx& cx) {
+CATAN_FN_NOINLINE void est_apply(Ctx& cx) {
   GameRec& g = *cx.g;
   WarpScratch& ws = *cx.ws;
   int16_t* emin = &g.est_min[0][0][0];
@@ -914,89 +946,171 @@ CATAN_FN void est_apply(Ctx& cx) {
 
 // ------------------------------------------------------------------------------------------------
 // longest road: node-simple longest path (game.py:843-862, utils.py:3-15; Q7)  [W]
-// Each lane runs an iterative DFS from its own start corners; the per-lane stack (<= 54 levels of
-// node | next-neighbour-index << 6) lives in the obs staging row, which is dead at this point.
+//
+// The reference enumerates every simple path of the player's road graph from every start corner.  Here
+// the graph is first reduced to one 64-bit adjacency mask per corner (a corner holding an opponent's
+// building keeps its incoming arcs but gets no outgoing ones, game.py:851-858).  The enumeration is
+// cut into 324 independent work items (start corner, 1st branch, 2nd branch) that the lanes claim from a
+// shared counter, and every lane runs the same branch-free push/pop state machine over its own path
+// stack, so the warp stays converged while the lanes sit at different depths of different subtrees.
+// Scratch (cx.scratch): adj[54] u64 | counter | path[54][LANES] bytes.
 // ------------------------------------------------------------------------------------------------
-CATAN_FN int longest_path(Ctx& cx, int pid) {
-  const GameRec& g = *cx.g;
-  const Topo& T = *cx.T;
-  uint8_t* stack = cx.obs;
-  int best = 0;
-  CATAN_LANE_LOOP(v0, 54) {
-    {
-      const uint8_t b0 = g.corner[v0];
-      if (b0 && (b0 >> 2) != pid) continue;                          // opponent building: no outgoing arcs (game.py:851-858)
-    }
-    uint64_t visited = 1ull << v0;
-    int depth = 0;
-    stack[cx.lane] = static_cast<uint8_t>(v0);
-    while (depth >= 0) {
-      const uint8_t sv = stack[depth * CATAN_LANES + cx.lane];
-      const int node = sv & 63;
-      int k = sv >> 6;
-      bool descended = false;
-      const uint8_t nb = g.corner[node];
-      if (!(nb && (nb >> 2) != pid)) {
-        while (k < 3) {
-          const int e = T.corner_neigh_edge[node][k], t = T.corner_neigh[node][k];
-          ++k;
-          if (e >= 0 && g.edge[e] == pid && !((visited >> t) & 1)) {
-            stack[depth * CATAN_LANES + cx.lane] = static_cast<uint8_t>(node | (k << 6));
-            ++depth;
-            stack[depth * CATAN_LANES + cx.lane] = static_cast<uint8_t>(t);
-            visited |= 1ull << t;
-            best = depth > best ? depth : best;
-            descended = true;
-            break;
-          }
-        }
+#define CATAN_LP_ADJ_BYTES 432
+#define CATAN_LP_PATH_OFF 448
+#define CATAN_LP_SCRATCH_BYTES (CATAN_LP_PATH_OFF + 54 * CATAN_LANES)
+#define CATAN_LP_ITEMS 324
+#if CATAN_LANES == 32
+CATAN_FN int ctz64(uint64_t x) { return __ffsll(static_cast<long long>(x)) - 1; }
+CATAN_FN int fetch_add_i32(int32_t* p) { return atomicAdd(p, 1); }
+CATAN_FN void smax_i32(int32_t* p, int v) { atomicMax(p, v); }
+#else
+CATAN_FN int ctz64(uint64_t x) { return __builtin_ctzll(x); }
+CATAN_FN int fetch_add_i32(int32_t* p) { return (*p)++; }
+CATAN_FN void smax_i32(int32_t* p, int v) { if (v > *p) *p = v; }
+#endif
+CATAN_FN int kth_bit(uint64_t m, int k) {   // index of the k-th (0-based) set bit, -1 if there is none
+  for (int j = 0; j < k; ++j) m &= m - 1;
+  return m ? ctz64(m) : -1;
+}
+
+// adjacency masks of PlayerId pid's road graph: adj[v] = corners reachable from v over one own road;
+// a corner holding an opponent's building has no outgoing arcs (game.py:851-858).  [W]; caller syncs.
+CATAN_FN void lp_build_adj(const GameRec& g, const Topo& T, int pid, uint64_t* adj, int lane) {
+  for (int v = lane; v < 54; v += CATAN_LANES) {
+    uint64_t a = 0;
+    const uint8_t b = g.corner[v];
+    if (!(b && (b >> 2) != pid)) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int e = T.corner_neigh_edge[v][k];
+        if (e >= 0 && g.edge[e] == pid) a |= 1ull << T.corner_neigh[v][k];
       }
-      if (!descended) { visited &= ~(1ull << node); --depth; }
+    }
+    adj[v] = a;
+  }
+}
+
+// Cooperative search over n_jobs graphs (adj[job][54]).  Every calling lane claims work items
+// (job, start corner, 1st branch, 2nd branch) from *counter until they run out and walks its subtree
+// with the push/pop state machine; the longest depth seen per job is max-ed into best[job].
+// path: byte stacks, element (depth, lane) at path[depth * path_stride + path_lane].
+// Any number of warps may call this concurrently on the same (adj, counter, best); the caller
+// synchronises before reading best[].
+CATAN_FN_NOINLINE void lp_search(const uint64_t* adj_all, int n_jobs, int32_t* counter, int32_t* best, uint8_t* path,
+                                 int path_stride, int path_lane) {
+  const int total = n_jobs * CATAN_LP_ITEMS;
+  const uint64_t* adj = adj_all;
+  int job = 0, lbest = 0, node = 0, depth = 0;
+  uint64_t visited = 0, above = ~0ull;
+  bool active = false, exhausted = false;
+  for (;;) {
+    if (!active && !exhausted) {                                     // claim the next non-empty work item
+      for (;;) {
+        const int i = fetch_add_i32(counter);
+        if (i >= total) { exhausted = true; break; }
+        const int nj = i / CATAN_LP_ITEMS, it = i - nj * CATAN_LP_ITEMS;
+        if (nj != job) { if (lbest) smax_i32(&best[job], lbest); job = nj; lbest = 0; adj = adj_all + nj * 54; }
+        const int v = it / 6, k1 = (it % 6) >> 1, k2 = it & 1;
+        const int t1 = kth_bit(adj[v], k1);
+        if (t1 < 0) continue;
+        const uint64_t c2 = adj[t1] & ~(1ull << v);
+        if (!c2) { if (k2 == 0 && lbest < 1) lbest = 1; continue; }
+        const int t2 = kth_bit(c2, k2);
+        if (t2 < 0) continue;
+        path[path_lane] = static_cast<uint8_t>(v);
+        path[path_stride + path_lane] = static_cast<uint8_t>(t1);
+        path[2 * path_stride + path_lane] = static_cast<uint8_t>(t2);
+        visited = (1ull << v) | (1ull << t1) | (1ull << t2);
+        depth = 2; node = t2; above = ~0ull; active = true;
+        if (lbest < 2) lbest = 2;
+        break;
+      }
+    }
+    if (!wany(active)) break;
+    if (active) {
+      const uint64_t cand = adj[node] & ~visited & above;
+      if (cand) {                                                    // push the lowest untried neighbour
+        const int t = ctz64(cand);
+        ++depth;
+        path[depth * path_stride + path_lane] = static_cast<uint8_t>(t);
+        visited |= 1ull << t;
+        node = t; above = ~0ull;
+        if (depth > lbest) lbest = depth;
+      } else if (depth == 2) {
+        active = false;                                              // subtree of this work item exhausted
+      } else {                                                       // pop; resume the parent above the popped child
+        visited &= ~(1ull << node);
+        above = ~((2ull << node) - 1ull);
+        --depth;
+        node = path[depth * path_stride + path_lane];
+      }
     }
   }
-  return wmax(best);
+  if (lbest) smax_i32(&best[job], lbest);
+}
+
+// warp-local longest path of one player (used by the host emulation and by callers without a block)  [W]
+CATAN_FN int longest_path(Ctx& cx, int pid) {
+  uint64_t* adj = reinterpret_cast<uint64_t*>(cx.scratch);
+  int32_t* counter = reinterpret_cast<int32_t*>(cx.scratch + CATAN_LP_ADJ_BYTES);
+  int32_t* best = counter + 1;
+  lp_build_adj(*cx.g, *cx.T, pid, adj, cx.lane);
+  if (cx.lane == 0) { *counter = 0; *best = 0; }
+  wsync();
+  lp_search(adj, 1, counter, best, cx.scratch + CATAN_LP_PATH_OFF, CATAN_LANES, cx.lane);
+  wsync();
+  const int r = *best;
+  wsync();
+  return r;
+}
+
+// game.py:880-881: the holder's own path got shorter -> the other three players must be re-measured
+CATAN_FN bool lr_is_shrunk(const GameRec& g, int pid, int len) { return g.lr_holder == pid && g.lr_count > len; }
+
+// game.py:864-919 given the measured lengths: len of `pid`, and (only when shrunk) other_len[PlayerId] of the rest  [L0]
+CATAN_FN_NOINLINE void lr_apply(GameRec& g, int pid, int len, bool shrunk, const uint8_t* other_len) {
+  const int holder = g.lr_holder, count = g.lr_count;
+  g.cur_longest_path[pid - 1] = static_cast<uint8_t>(len);
+  g.has_path_key[pid - 1] = 1;
+  if (!holder) {
+    if (len >= 5) { g.lr_holder = static_cast<uint8_t>(pid); g.lr_count = static_cast<uint8_t>(len); g.vp[pid - 1] += 2; }
+  } else if (holder == pid) {
+    if (shrunk) {
+      int max_len = len, player = pid;
+      bool tied = false;
+      for (int o = WHITE; o <= RED; ++o) {                           // game.py:886 order White,Blue,Orange,Red
+        if (o == pid) continue;
+        const int pl = other_len[o];
+        if (pl == max_len) tied = true;
+        else if (pl > max_len) { max_len = pl; tied = false; player = o; }
+      }
+      if (max_len >= 5) {
+        if (tied) {
+          if (player == pid) g.lr_count = static_cast<uint8_t>(len);
+          else { g.lr_holder = 0; g.lr_count = 0; g.vp[pid - 1] -= 2; }
+        } else {
+          g.lr_holder = static_cast<uint8_t>(player); g.lr_count = static_cast<uint8_t>(max_len);
+          g.vp[player - 1] += 2; g.vp[pid - 1] -= 2;
+        }
+      } else { g.lr_holder = 0; g.lr_count = 0; g.vp[pid - 1] -= 2; }
+    } else {
+      g.lr_count = static_cast<uint8_t>(len);
+    }
+  } else if (len > count) {
+    g.vp[holder - 1] -= 2; g.vp[pid - 1] += 2;
+    g.lr_holder = static_cast<uint8_t>(pid); g.lr_count = static_cast<uint8_t>(len);
+  }
 }
 
 CATAN_FN_NOINLINE void update_longest_road(Ctx& cx, int pid) {   // game.py:864-919  [W]
   GameRec& g = *cx.g;
   const int len = longest_path(cx, pid);
-  const int holder = g.lr_holder, count = g.lr_count;
-  int max_len = len, player = pid;
-  bool tied = false;
-  const bool shrunk = holder == pid && count > len;
-  if (shrunk) {                                                      // game.py:880-895 (order White,Blue,Orange,Red)
-    for (int o = WHITE; o <= RED; ++o) {
-      if (o == pid) continue;
-      const int pl = longest_path(cx, o);
-      if (pl == max_len) tied = true;
-      else if (pl > max_len) { max_len = pl; tied = false; player = o; }
-    }
+  const bool shrunk = lr_is_shrunk(g, pid, len);
+  uint8_t other_len[5] = {0, 0, 0, 0, 0};
+  if (shrunk) {
+    for (int o = WHITE; o <= RED; ++o) if (o != pid) other_len[o] = static_cast<uint8_t>(longest_path(cx, o));
   }
-  wsync();
-  if (cx.lane == 0) {
-    g.cur_longest_path[pid - 1] = static_cast<uint8_t>(len);
-    g.has_path_key[pid - 1] = 1;
-    if (!holder) {
-      if (len >= 5) { g.lr_holder = static_cast<uint8_t>(pid); g.lr_count = static_cast<uint8_t>(len); g.vp[pid - 1] += 2; }
-    } else if (holder == pid) {
-      if (shrunk) {
-        if (max_len >= 5) {
-          if (tied) {
-            if (player == pid) g.lr_count = static_cast<uint8_t>(len);
-            else { g.lr_holder = 0; g.lr_count = 0; g.vp[pid - 1] -= 2; }
-          } else {
-            g.lr_holder = static_cast<uint8_t>(player); g.lr_count = static_cast<uint8_t>(max_len);
-            g.vp[player - 1] += 2; g.vp[pid - 1] -= 2;
-          }
-        } else { g.lr_holder = 0; g.lr_count = 0; g.vp[pid - 1] -= 2; }
-      } else {
-        g.lr_count = static_cast<uint8_t>(len);
-      }
-    } else if (len > count) {
-      g.vp[holder - 1] -= 2; g.vp[pid - 1] += 2;
-      g.lr_holder = static_cast<uint8_t>(pid); g.lr_count = static_cast<uint8_t>(len);
-    }
-  }
+  if (cx.lane == 0) lr_apply(g, pid, len, shrunk, other_len);
   wsync();
 }
 
@@ -1005,74 +1119,97 @@ CATAN_FN_NOINLINE void update_longest_road(Ctx& cx, int pid) {   // game.py:864-
 //   ws.action must hold the composite action.  reward_out: float[4]; info_out: uint8[CATAN_INFO_STRIDE]
 //   (both written by lane 0; may point to global memory).  Returns the error code (uniform).
 // ------------------------------------------------------------------------------------------------
-CATAN_FN int step_game(Ctx& cx, float* reward_out, uint8_t* info_out) {
+// phase 1 [L0]: clear the scratch, translate (wrapper.py:114-166) and validate (game.py:264-525) -> ws.err, ws.act
+CATAN_FN_NOINLINE void step_begin(Ctx& cx) {
   GameRec& g = *cx.g;
   WarpScratch& ws = *cx.ws;
+  ws.n_est = 0; ws.est_special = EST_SPECIAL_NONE; ws.dice_roll = 0; ws.lr_pid = 0; ws.roll_info = 0;
+  ws.did_reset = 0; ws.done = 0;
+  compute_seats(cx);
+  ws.acted_pid = static_cast<uint8_t>(current_actor(g));
+  ws.act_type = static_cast<uint8_t>(ws.action[CATAN_A_TYPE]);
+  int err = translate_action(cx, ws.action, ws.act);
+  if (!err && cx.cfg->validate_actions) err = validate_action(cx, ws.act);
+  ws.err = static_cast<uint8_t>(err);
+}
+
+CATAN_FN_NOINLINE void step_finish(Ctx& cx, float* reward_out, uint8_t* info_out);
+
+CATAN_FN int step_game(Ctx& cx, float* reward_out, uint8_t* info_out) {
+  WarpScratch& ws = *cx.ws;
   if (cx.lane == 0) {
-    ws.n_est = 0; ws.est_special = EST_SPECIAL_NONE; ws.dice_roll = 0; ws.lr_pid = 0; ws.roll_info = 0;
-    ws.did_reset = 0; ws.done = 0;
-    compute_seats(cx);
-    ws.acted_pid = static_cast<uint8_t>(current_actor(g));
-    ws.act_type = static_cast<uint8_t>(ws.action[CATAN_A_TYPE]);
-    Act t;
-    int err = translate_action(cx, ws.action, t);
-    if (!err && cx.cfg->validate_actions) err = validate_action(cx, t);
-    ws.err = static_cast<uint8_t>(err);
-    if (!err) apply_scalar(cx, t);
+    step_begin(cx);
+    if (!ws.err) apply_scalar(cx);
   }
   wsync();
+  CATAN_PROF(cx, PH_SCALAR);
   const int err = ws.err;
   if (!err) {
-    if (ws.dice_roll) dice_payout(cx);
-    if (ws.n_est || ws.est_special) est_apply(cx);
-    if (ws.lr_pid) update_longest_road(cx, ws.lr_pid);
+    if (ws.dice_roll) { dice_payout(cx); CATAN_PROF(cx, PH_DICE); }
+    if (ws.n_est || ws.est_special) { est_apply(cx); CATAN_PROF(cx, PH_EST); }
+    if (ws.lr_pid) { update_longest_road(cx, ws.lr_pid); CATAN_PROF(cx, PH_LROAD); }
   }
-  if (cx.lane == 0) {                                                // wrapper.py:85-112
-    uint8_t info[CATAN_INFO_STRIDE];
-    for (int i = 0; i < CATAN_INFO_STRIDE; ++i) info[i] = 0;
-    float rew[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cx.lane == 0) step_finish(cx, reward_out, info_out);
+  wsync();
+  CATAN_PROF(cx, PH_FINISH);
+  return err;
+}
+
+// last phase [L0]: done / reward / info (wrapper.py:85-112) and the optional auto-reset
+CATAN_FN_NOINLINE void step_finish(Ctx& cx, float* reward_out, uint8_t* info_out) {
+  GameRec& g = *cx.g;
+  WarpScratch& ws = *cx.ws;
+  const int err = ws.err;
+  {
+    struct alignas(16) V16 { uint32_t w[4]; };
+    struct alignas(16) F4 { float v[4]; };
+    F4 rew = {{0.f, 0.f, 0.f, 0.f}};
     int done = 0;
     if (!err) {
       g.episode_steps += 1;
-      const int dict_order[4] = {BLUE, RED, ORANGE, WHITE};          // game.py:18-23: the last one >= 10 wins
-      for (int i = 0; i < 4; ++i) if (g.vp[dict_order[i] - 1] >= 10) { done = 1; g.winner = static_cast<uint8_t>(dict_order[i]); }
-      const int ty = ws.act_type;
-      for (int p = 0; p < 4; ++p) {
-        double r = 0.0;
-        if (cx.cfg->dense_reward) {                                  // wrapper.py:95-106
-          r += 5.0 * static_cast<double>(g.vp[p] - g.curr_vps[p]);
-          if (ty == CATAN_ACT_PLAY_DEV) r += 5.0;
-          if (ty == CATAN_ACT_MOVE_ROBBER) r += 1.0;
-          if (ty == CATAN_ACT_DISCARD) r -= 0.3;
-          if (ty == CATAN_ACT_UPGRADE_CITY) r += 2.5;
-          r *= static_cast<double>(cx.cfg->reward_annealing_factor);
+      // game.py:18-23: dict order Blue, Red, Orange, White; the LAST player with >= 10 VP becomes env.winner
+      if (g.vp[BLUE - 1] >= 10) { done = 1; g.winner = BLUE; }
+      if (g.vp[RED - 1] >= 10) { done = 1; g.winner = RED; }
+      if (g.vp[ORANGE - 1] >= 10) { done = 1; g.winner = ORANGE; }
+      if (g.vp[WHITE - 1] >= 10) { done = 1; g.winner = WHITE; }
+      if (cx.cfg->dense_reward) {                                    // wrapper.py:95-106
+        const int ty = ws.act_type;
+        const double bonus = (ty == CATAN_ACT_PLAY_DEV ? 5.0 : 0.0) + (ty == CATAN_ACT_MOVE_ROBBER ? 1.0 : 0.0) -
+                             (ty == CATAN_ACT_DISCARD ? 0.3 : 0.0) + (ty == CATAN_ACT_UPGRADE_CITY ? 2.5 : 0.0);
+        CATAN_NO_UNROLL
+        for (int p = 0; p < 4; ++p) {
+          // python: ((5*dvp + 5) + 1 - 0.3 + 2.5) * factor with at most one bonus non-zero => same double value
+          const double r = (5.0 * static_cast<double>(g.vp[p] - g.curr_vps[p]) + bonus) * static_cast<double>(cx.cfg->reward_annealing_factor);
+          rew.v[p] = static_cast<float>(r);
         }
-        g.curr_vps[p] = g.vp[p];
-        if (done && g.winner == p + 1) r += static_cast<double>(cx.cfg->win_reward);
-        rew[p] = static_cast<float>(r);
+      }
+      CATAN_NO_UNROLL
+      for (int p = 0; p < 4; ++p) g.curr_vps[p] = g.vp[p];
+      if (done) {
+        const int wp = g.winner - 1;
+        rew.v[wp] = static_cast<float>(static_cast<double>(rew.v[wp]) + static_cast<double>(cx.cfg->win_reward));
       }
     }
-    info[CATAN_INFO_DONE] = static_cast<uint8_t>(done);
-    info[CATAN_INFO_WINNER] = g.winner;
-    for (int p = 0; p < 4; ++p) info[CATAN_INFO_FINAL_VP + p] = static_cast<uint8_t>(g.vp[p]);
-    info[CATAN_INFO_ACTED] = ws.acted_pid;
-    info[CATAN_INFO_ACT_TYPE] = ws.act_type;
-    info[CATAN_INFO_ROLL] = ws.roll_info;
-    info[CATAN_INFO_ERR] = static_cast<uint8_t>(err);
-    if (done && cx.cfg->auto_reset) { reset_game(cx); info[CATAN_INFO_RESET] = 1; }
-    info[CATAN_INFO_ACTOR] = static_cast<uint8_t>(current_actor(g));
+    V16 info;
+    info.w[0] = static_cast<uint32_t>(done) | (static_cast<uint32_t>(g.winner) << 8) |
+                (static_cast<uint32_t>(static_cast<uint8_t>(g.vp[0])) << 16) | (static_cast<uint32_t>(static_cast<uint8_t>(g.vp[1])) << 24);
+    uint32_t reset_flag = 0;
+    const uint32_t vp23 = static_cast<uint32_t>(static_cast<uint8_t>(g.vp[2])) | (static_cast<uint32_t>(static_cast<uint8_t>(g.vp[3])) << 8);
+    if (done && cx.cfg->auto_reset) { reset_game(cx); reset_flag = 1; }
+    info.w[1] = vp23 | (static_cast<uint32_t>(current_actor(g)) << 16) | (static_cast<uint32_t>(ws.acted_pid) << 24);
+    info.w[2] = static_cast<uint32_t>(ws.act_type) | (static_cast<uint32_t>(ws.roll_info) << 8) |
+                (static_cast<uint32_t>(err) << 16) | (reset_flag << 24);
+    info.w[3] = 0;
     ws.done = static_cast<uint8_t>(done);
-    for (int p = 0; p < 4; ++p) reward_out[p] = rew[p];
-    for (int i = 0; i < CATAN_INFO_STRIDE; ++i) info_out[i] = info[i];
+    *reinterpret_cast<F4*>(reward_out) = rew;
+    *reinterpret_cast<V16*>(info_out) = info;
   }
-  wsync();
-  return err;
 }
 
 // ------------------------------------------------------------------------------------------------
 // legal-action masks (wrapper.py:168-412)  [W]
 // ------------------------------------------------------------------------------------------------
-CATAN_FN bool mask_play_dev(Ctx& cx, int pid) {   // wrapper.py:221-228 / :262-269 / :368-388; lane-0 writes
+CATAN_FN_NOINLINE bool mask_play_dev(Ctx& cx, int pid) {   // wrapper.py:221-228 / :262-269 / :368-388; lane-0 writes
   const GameRec& g = *cx.g;
   uint8_t* m = cx.mask;
   const int p = pid - 1;
@@ -1103,7 +1240,7 @@ CATAN_FN bool mask_play_dev(Ctx& cx, int pid) {   // wrapper.py:221-228 / :262-2
 
 // road head (wrapper.py:322-339).  mode 0: main phase (write only when something is placeable, returns that);
 // mode 1: initial phase (always write, dummy 0); mode 2: road building (always write, dummy iff nothing placeable)
-CATAN_FN bool mask_roads(Ctx& cx, int pid, int mode) {
+CATAN_FN_NOINLINE bool mask_roads(Ctx& cx, int pid, int mode) {
   const GameRec& g = *cx.g;
   const Topo& T = *cx.T;
   uint8_t* m = cx.mask + CATAN_MASK_EDGE;
@@ -1130,7 +1267,7 @@ CATAN_FN bool mask_roads(Ctx& cx, int pid, int mode) {
   return placed;
 }
 
-CATAN_FN void encode_masks(Ctx& cx) {
+CATAN_FN_NOINLINE void encode_masks(Ctx& cx) {
   const GameRec& g = *cx.g;
   const Topo& T = *cx.T;
   uint8_t* m = cx.mask;
@@ -1257,25 +1394,44 @@ CATAN_FN int bucket7(int n) { return n <= 2 ? n : (n <= 5 ? 3 : (n <= 7 ? 4 : (n
 // slot of resource index r in the obs order Wood,Brick,Wheat,Ore,Sheep (wrapper.py:550)
 CATAN_FN int obs_res_slot(int r) { return (0x24301 >> (4 * r)) & 7; }   // BRICK->1 WOOD->0 ORE->3 SHEEP->4 WHEAT->2
 
-CATAN_FN void encode_obs(Ctx& cx) {
+CATAN_FN_NOINLINE void encode_obs(Ctx& cx) {
   const GameRec& g = *cx.g;
   const Topo& T = *cx.T;
   uint8_t* o = cx.obs;
   {
-    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-    CATAN_LANE_LOOP(w, CATAN_OBS_STRIDE / 4) ow[w] = 0;
+    struct alignas(16) V16 { uint32_t a, b, c, d; };
+    V16* ov = reinterpret_cast<V16*>(o);
+    const V16 z = {0u, 0u, 0u, 0u};
+    CATAN_LANE_LOOP(w, CATAN_OBS_STRIDE / 16) ov[w] = z;
   }
-  wsync();
   const int actor = current_actor(g), ap = actor - 1;
-  const int aseat = cx.ws->seat[actor];
-  // block index of a player relative to the actor: 0 self, 1 next, 2 next_next, 3 next_next_next
-#define CATAN_REL(pid_) ((cx.ws->seat[(pid_)] - aseat + 4) & 3)
-  CATAN_LANE_LOOP(i, 114) {                                          // tile corners, wrapper.py:499-521
+  // relative seating in registers: REL(pid) = block of PlayerId pid seen from the actor (0 self, 1 next, ...),
+  // PID_AT(rel) = PlayerId sitting rel seats after the actor (player.py:13-19)
+  uint32_t relpack = 0, pidrel = 0;
+  {
+    const uint8_t* seat = cx.ws->seat;
+    const int aseat = seat[actor];
+#pragma unroll
+    for (int p = 1; p <= 4; ++p) relpack |= static_cast<uint32_t>((seat[p] - aseat + 4) & 3) << (2 * p);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) pidrel |= static_cast<uint32_t>(g.player_order[(aseat + r) & 3]) << (4 * r);
+  }
+#define CATAN_REL(pid_) ((relpack >> (2 * (pid_))) & 3u)
+#define CATAN_PID_AT(rel_) ((pidrel >> (4 * (rel_))) & 15u)
+#define CATAN_BLOCK(rel_) ((rel_) == 0 ? CATAN_OBS_CUR_MAIN : CATAN_OBS_OTHER_MAIN + ((rel_) - 1) * CATAN_OBS_OTHER_MAIN_DIM)
+  wsync();
+  CATAN_LANE_LOOP(i, 114) {                                          // (tile, corner) pairs: wrapper.py:499-521 and :595-610
     const int t = i / 6, k = i - 6 * t;
     const uint8_t b = g.corner[T.tile_corners[t][k]];
     uint8_t* cf = o + CATAN_OBS_TILES + t * CATAN_OBS_TILE_DIM + 18 + k * 7;
-    cf[b & 3] = 1;
-    if (b) cf[3 + CATAN_REL(b >> 2)] = 1;
+    cf[b & 3] = 1;                                                   // none / settlement / city
+    if (b) {
+      const int rel = CATAN_REL(b >> 2);
+      cf[3 + rel] = 1;                                               // owner relative to the actor
+      const int v = g.tile_val[t];
+      if (v != 7)                                                    // production table of the owner's block (+1 / +2)
+        sadd_u8(o + CATAN_BLOCK(rel) + (rel == 0 ? 50 : 90) + obs_res_slot(g.tile_res[t] - 1) * 10 + (v <= 6 ? v - 2 : v - 3), b & 3);
+    }
   }
   CATAN_LANE_LOOP(t, 19) {                                           // wrapper.py:494-498
     uint8_t* f = o + CATAN_OBS_TILES + t * CATAN_OBS_TILE_DIM;
@@ -1283,91 +1439,86 @@ CATAN_FN void encode_obs(Ctx& cx) {
     f[1 + g.tile_val[t] - 2] = 1;
     f[12 + g.tile_res[t]] = 1;
   }
-  CATAN_LANE_LOOP(c, 54) {                                           // production tables, wrapper.py:595-610
-    const uint8_t b = g.corner[c];
-    if (!b) continue;
-    const int rel = CATAN_REL(b >> 2);
-    uint8_t* prod = rel == 0 ? o + CATAN_OBS_CUR_MAIN + 50 : o + CATAN_OBS_OTHER_MAIN + (rel - 1) * CATAN_OBS_OTHER_MAIN_DIM + 90;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int t = T.corner_tiles[c][k];
-      if (t < 0) continue;
-      const int v = g.tile_val[t];
-      if (v == 7) continue;
-      sadd_u8(prod + obs_res_slot(g.tile_res[t] - 1) * 10 + (v <= 6 ? v - 2 : v - 3), b & 3);
-    }
-  }
-  CATAN_LANE_LOOP(i, 125) {                                          // development-card lists, wrapper.py:642-655
-    const int li = i / 25, j = i - 25 * li;
-    const int tp = li < 2 ? ap : pid_at_label(cx, actor, li - 2) - 1;
+  for (int li = 0; li < 5; ++li) {                                   // development-card lists, wrapper.py:642-655
+    const int tp = (li < 2 ? actor : static_cast<int>(CATAN_PID_AT(li - 1))) - 1;
     const uint8_t* list = li == 1 ? g.hidden[tp] : g.played[tp];
     const int n = li == 1 ? g.n_hidden[tp] : g.n_played[tp];
-    if (j < n) o[CATAN_OBS_DEV_LISTS + i] = static_cast<uint8_t>(list[j] + 1);
+    CATAN_LANE_LOOP(j, n) o[CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD + j] = static_cast<uint8_t>(list[j] + 1);
   }
-  CATAN_LANE_LOOP(rel, 4) {                                          // one lane per player block
-    const int target = rel == 0 ? actor : pid_at_label(cx, actor, rel - 1), tp = target - 1;
-    uint8_t* m = rel == 0 ? o + CATAN_OBS_CUR_MAIN : o + CATAN_OBS_OTHER_MAIN + (rel - 1) * CATAN_OBS_OTHER_MAIN_DIM;
-    uint8_t* c;                                                      // vp 10 | production 50 | road 2 | army 2 | harbours 6
-    if (rel == 0) {
-      for (int r = 0; r < 5; ++r) m[obs_res_slot(r) * 8 + bucket8(g.res[ap][r])] = 1;          // wrapper.py:550-562
-      c = m + 40;
-      uint8_t* bk = m + 110;
-      for (int r = 0; r < 5; ++r) bk[obs_res_slot(r) * 7 + bucket7(g.bank[r])] = 1;            // wrapper.py:657-672
-      bk[35 + bucket7(g.deck_n)] = 1;                                                          // wrapper.py:674-686
-    } else {
-      for (int r = 0; r < 5; ++r) {                                                            // wrapper.py:563-585
-        m[obs_res_slot(r) * 8 + bucket8(g.est_min[ap][rel - 1][r])] = 1;
-        m[40 + obs_res_slot(r) * 8 + bucket8(g.est_max[ap][rel - 1][r])] = 1;
+  wsync();   // word atomics of the production tables above share 32-bit words with the byte stores below
+  CATAN_LANE_LOOP(vl, 32) {                                          // player blocks: lane = (block rel, feature group sub)
+    const int rel = vl >> 3, sub = vl & 7;
+    const int target = CATAN_PID_AT(rel), tp = target - 1;
+    uint8_t* m = o + CATAN_BLOCK(rel);
+    uint8_t* c = m + (rel == 0 ? 40 : 80);                           // vp 10 | production 50 | road 2 | army 2 | harbours 6
+    if (sub < 5) {
+      const int r = sub, slot = obs_res_slot(r);
+      if (rel == 0) {
+        m[slot * 8 + bucket8(g.res[ap][r])] = 1;                     // wrapper.py:550-562
+        m[110 + slot * 7 + bucket7(g.bank[r])] = 1;                  // wrapper.py:657-672
+        o[CATAN_OBS_CURRENT_RES + 1 + r] = g.res[ap][r];             // wrapper.py:70-71
+      } else {
+        m[slot * 8 + bucket8(g.est_min[ap][rel - 1][r])] = 1;        // wrapper.py:563-585
+        m[40 + slot * 8 + bucket8(g.est_max[ap][rel - 1][r])] = 1;
       }
-      c = m + 80;
-      m[150 + rel - 1] = 1;                                                                    // wrapper.py:532-541
+    } else if (sub == 5) {
+      const int vps = g.vp[tp];
+      c[vps < 10 ? vps : 9] = 1;                                     // wrapper.py:587-593
+      if (g.lr_holder) {                                             // wrapper.py:613-620 (Q9)
+        if (g.lr_holder == target) { c[60] = 1; c[61] = g.lr_count; }
+        else if (g.has_path_key[tp]) c[61] = g.cur_longest_path[tp];
+      }
+    } else if (sub == 6) {
+      if (g.la_holder == target) c[62] = 1;                          // wrapper.py:623-627 (Q10)
+      c[63] = g.cur_army[tp];
+      const int hb = g.harbours[tp];
+#pragma unroll
+      for (int b = 0; b < 6; ++b) c[64 + b] = (hb >> b) & 1;         // wrapper.py:632-637
+    } else if (rel == 0) {
+      m[145 + bucket7(g.deck_n)] = 1;                                // wrapper.py:674-686
+      o[CATAN_OBS_META] = static_cast<uint8_t>(actor);
+      o[CATAN_OBS_META + 1] = g.n_played[ap];
+      o[CATAN_OBS_META + 2] = g.n_hidden[ap];
+      if (g.trade_proposer) {                                        // wrapper.py:65-69 (Q15)
+        for (int k = 0; k < g.n_give; ++k) o[CATAN_OBS_PROPOSED_TRADE + g.give[k]] = 1;
+        for (int k = 0; k < g.n_recv; ++k) o[CATAN_OBS_PROPOSED_TRADE + g.recv[k] + 5] = 1;
+      }
+    } else {
+      m[150 + rel - 1] = 1;                                          // wrapper.py:532-541
       const int nh = g.n_hidden[tp];
-      m[153 + (nh <= 4 ? nh : 5)] = 1;                                                         // wrapper.py:690-695
+      m[153 + (nh <= 4 ? nh : 5)] = 1;                               // wrapper.py:690-695
+      o[CATAN_OBS_META + 2 + rel] = g.n_played[tp];
     }
-    const int vps = g.vp[tp];
-    c[vps < 10 ? vps : 9] = 1;                                                                 // wrapper.py:587-593
-    if (g.lr_holder) {                                                                         // wrapper.py:613-620 (Q9)
-      if (g.lr_holder == target) { c[60] = 1; c[61] = g.lr_count; }
-      else if (g.has_path_key[tp]) c[61] = g.cur_longest_path[tp];
-    }
-    if (g.la_holder == target) c[62] = 1;                                                      // wrapper.py:623-627 (Q10)
-    c[63] = g.cur_army[tp];
-    for (int b = 0; b < 6; ++b) c[64 + b] = (g.harbours[tp] >> b) & 1;                         // wrapper.py:632-637
-    o[CATAN_OBS_META + (rel == 0 ? 1 : 2 + rel)] = g.n_played[tp];
-  }
-  if (cx.lane == 0) {
-    if (g.trade_proposer) {                                          // wrapper.py:65-69 (Q15)
-      for (int k = 0; k < g.n_give; ++k) o[CATAN_OBS_PROPOSED_TRADE + g.give[k]] = 1;
-      for (int k = 0; k < g.n_recv; ++k) o[CATAN_OBS_PROPOSED_TRADE + g.recv[k] + 5] = 1;
-    }
-    for (int r = 0; r < 5; ++r) o[CATAN_OBS_CURRENT_RES + 1 + r] = g.res[ap][r];   // wrapper.py:70-71
-    o[CATAN_OBS_META] = static_cast<uint8_t>(actor);
-    o[CATAN_OBS_META + 2] = g.n_hidden[ap];
   }
 #undef CATAN_REL
+#undef CATAN_PID_AT
+#undef CATAN_BLOCK
   wsync();
 }
 
 // ------------------------------------------------------------------------------------------------
 // pinned random-legal sampler (twin of oracle/ref_harness.py:sample_action)  [W]
-// m / o may point to shared or global memory.  Result in a[CATAN_ACTION_WORDS] of every lane's
+// m / hand may point to shared or global memory.  Result in a[CATAN_ACTION_WORDS] of every lane's
 // registers is NOT materialised; lane 0 writes the words to `out`.
 // ------------------------------------------------------------------------------------------------
 #if CATAN_LANES == 32
-CATAN_FN int pick(const uint8_t* bits, int n, uint32_t w, int lane) {   // n <= 96; index of the floor(w*k/2^32)-th set entry
-  const unsigned b0 = __ballot_sync(0xffffffffu, lane < n && bits[lane] != 0);
-  const unsigned b1 = __ballot_sync(0xffffffffu, lane + 32 < n && bits[lane + 32] != 0);
-  const unsigned b2 = __ballot_sync(0xffffffffu, lane + 64 < n && bits[lane + 64] != 0);
+CATAN_FN_NOINLINE int pick(const uint8_t* bits, int n, uint32_t w, int lane) {   // n <= 96; index of the floor(w*k/2^32)-th set entry
+  const bool s0 = lane < n && bits[lane] != 0, s1 = lane + 32 < n && bits[lane + 32] != 0, s2 = lane + 64 < n && bits[lane + 64] != 0;
+  const unsigned b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1), b2 = __ballot_sync(0xffffffffu, s2);
   const int k0 = __popc(b0), k1 = __popc(b1), k = k0 + k1 + __popc(b2);
   if (!k) return 0;
-  int j = static_cast<int>(__umulhi(w, static_cast<uint32_t>(k)));
-  if (j < k0) return __fns(b0, 0, j + 1);
-  j -= k0;
-  if (j < k1) return 32 + __fns(b1, 0, j + 1);
-  return 64 + __fns(b2, 0, j - k1 + 1);
+  const int j = static_cast<int>(__umulhi(w, static_cast<uint32_t>(k)));
+  const unsigned below = (1u << lane) - 1u;
+  // the lane whose set entry has rank j announces itself
+  const bool h0 = s0 && __popc(b0 & below) == j;
+  const bool h1 = s1 && k0 + __popc(b1 & below) == j;
+  const bool h2 = s2 && k0 + k1 + __popc(b2 & below) == j;
+  const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1), m2 = __ballot_sync(0xffffffffu, h2);
+  return m0 ? __ffs(m0) - 1 : (m1 ? 31 + __ffs(m1) : 63 + __ffs(m2));
 }
 #else
-CATAN_FN int pick(const uint8_t* bits, int n, uint32_t w, int) {
+CATAN_FN_NOINLINE int pick(const uint8_t* bits, int n, uint32_t w, int) {
   int k = 0;
   for (int i = 0; i < n; ++i) k += bits[i] != 0;
   if (!k) return 0;
@@ -1377,7 +1528,8 @@ CATAN_FN int pick(const uint8_t* bits, int n, uint32_t w, int) {
 }
 #endif
 
-CATAN_FN void sample_action(const uint8_t* m, const uint8_t* o, uint64_t seed, uint64_t env_id, uint32_t decision,
+// `hand`: the acting player's 5 resource counts (== obs current_resources[1..5], wrapper.py:70-71)
+CATAN_FN_NOINLINE void sample_action(const uint8_t* m, const uint8_t* hand, uint64_t seed, uint64_t env_id, uint32_t decision,
                             int lane, int32_t* out) {
   uint32_t w[4];
   philox4x32(decision, CATAN_STREAM_SAMPLER, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32),
@@ -1403,7 +1555,7 @@ CATAN_FN void sample_action(const uint8_t* m, const uint8_t* o, uint64_t seed, u
       break;
     case CATAN_ACT_PROPOSE_TRADE:
       player = pick(m + CATAN_MASK_PLAYER, 3, w[1], lane);
-      give = 1 + pick(o + CATAN_OBS_CURRENT_RES + 1, 5, w[2], lane);   // a resource the proposer holds
+      give = 1 + pick(hand, 5, w[2], lane);                            // a resource the proposer holds
       recv = 1 + static_cast<int>(mulhi32(w[3], 5u));
       break;
     case CATAN_ACT_RESPOND: accept = pick(m + CATAN_MASK_ACCEPT, 2, w[1], lane); break;
@@ -1411,12 +1563,27 @@ CATAN_FN void sample_action(const uint8_t* m, const uint8_t* o, uint64_t seed, u
     case CATAN_ACT_DISCARD: discard = pick(m + CATAN_MASK_DISCARD, 5, w[1], lane); break;
     default: break;
   }
-  if (lane == 0) {
-    for (int i = 0; i < CATAN_ACTION_WORDS; ++i) out[i] = 0;
-    out[CATAN_A_TYPE] = t; out[CATAN_A_CORNER] = corner; out[CATAN_A_EDGE] = edge; out[CATAN_A_TILE] = tile;
-    out[CATAN_A_CARD] = card; out[CATAN_A_ACCEPT] = accept; out[CATAN_A_PLAYER] = player;
-    out[CATAN_A_GIVE] = give; out[CATAN_A_RECV] = recv;
-    out[CATAN_A_RES_A] = res_a; out[CATAN_A_RES_B] = res_b; out[CATAN_A_DISCARD] = discard;
+  if (lane < CATAN_ACTION_WORDS * (CATAN_LANES == 32 ? 1 : CATAN_ACTION_WORDS)) {
+    CATAN_NO_UNROLL
+    for (int i = lane; i < CATAN_ACTION_WORDS; i += CATAN_LANES) {       // one coalesced 80-byte row
+      int v = 0;
+      switch (i) {
+        case CATAN_A_TYPE: v = t; break;
+        case CATAN_A_CORNER: v = corner; break;
+        case CATAN_A_EDGE: v = edge; break;
+        case CATAN_A_TILE: v = tile; break;
+        case CATAN_A_CARD: v = card; break;
+        case CATAN_A_ACCEPT: v = accept; break;
+        case CATAN_A_PLAYER: v = player; break;
+        case CATAN_A_GIVE: v = give; break;
+        case CATAN_A_RECV: v = recv; break;
+        case CATAN_A_RES_A: v = res_a; break;
+        case CATAN_A_RES_B: v = res_b; break;
+        case CATAN_A_DISCARD: v = discard; break;
+        default: break;
+      }
+      out[i] = v;
+    }
   }
 }
 

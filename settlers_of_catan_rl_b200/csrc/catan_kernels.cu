@@ -1,12 +1,15 @@
 // catan_kernels.cu — sm_100a kernels + C ABI of the vectorised Catan engine (see include/catan_b200.h).
 //
-// env_kernel: one warp per game.  Per game: coalesced 16-byte loads of the 832-byte packed record into
-// shared memory -> transition (catan_core.cuh) -> legal-action masks and the packed observation are
-// built in shared memory -> record, masks and observation leave through the TMA engine as 1-D bulk
-// async copies (cp.async.bulk.global.shared::cta) so the warp can move on to its next game while the
-// stores drain.  The 1 KB board topology is staged in shared memory once per block.
+// env_kernel: persistent, phase-major.  One 32-warp block per SM pulls a batch of 112 games: their
+// 832-byte packed records are copied (contiguous, coalesced) into shared memory and stay there while the
+// block walks through the phases of a step together -- translate/validate, scalar apply, dice payout,
+// belief updates, longest road, done/reward, masks(+sampler), observation -- one warp per game inside a
+// phase (catan_core.cuh).  Mask and observation rows are built in a per-warp staging row and leave
+// through the TMA engine as 1-D bulk async copies (cp.async.bulk.global.shared::cta).  The 1 KB board
+// topology is staged in shared memory once per block.
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <new>
 #include <string>
 #include <vector>
@@ -18,8 +21,20 @@ namespace catanb {
 
 __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 
-constexpr int kWarpsPerBlock = 4;
-constexpr int kThreads = kWarpsPerBlock * 32;
+// ---- launch shape -------------------------------------------------------------------------------
+// One persistent block of 32 warps per SM.  A block works on a BATCH of kBatch games whose packed
+// records stay in shared memory while the block walks through the phases of a step TOGETHER
+// (block barrier between phases).  At any time all 32 warps of an SM execute the same small phase
+// function, so the hot instruction footprint stays within the 32 KB instruction cache
+// (profiles/r1_notes.md: the fused warp-per-game pipeline spent 74% of its stall samples in
+// stall_no_inst).  Inside a phase each warp still owns one game at a time (lanes cooperate on it).
+constexpr int kWarps = 32;
+constexpr int kThreads = kWarps * 32;
+constexpr int kBatch = 112;                 // games per block iteration: 4 rounds of 148 blocks cover 65 536 games
+constexpr int kStageBytes = 2304;           // per-warp staging row: >= obs row, >= longest-road scratch
+constexpr int kSampleWarpsPerBlock = 4;     // stand-alone sampler kernel
+constexpr int kMaxJobs = 39;                // longest-road graphs searched per cooperative pass (13 games x 3 when re-measuring)
+static_assert(kStageBytes >= CATAN_OBS_STRIDE && kStageBytes >= CATAN_LP_SCRATCH_BYTES && kStageBytes % 16 == 0, "staging row too small");
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
@@ -36,20 +51,26 @@ struct EnvParams {
   uint8_t* info;
   uint32_t* err_flags;
   const uint8_t* reset_mask;   // MODE_RESET: nullptr = all envs
-  int refresh_first, refresh_count;   // MODE_REFRESH range
+  int range_first, range_count;   // env range this launch covers
+  unsigned long long* prof;    // profiling build only
 };
 
-struct alignas(16) WarpSmem {
-  GameRec g;
-  WarpScratch ws;
-  uint8_t obs[CATAN_OBS_STRIDE];
-  uint8_t mask[CATAN_MASK_STRIDE];
-};
-static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp shared slab must be 16-byte granular");
 struct alignas(16) BlockSmem {
   Topo topo;
-  WarpSmem w[kWarpsPerBlock];
+  GameRec recs[kBatch];
+  WarpScratch ws[kBatch];
+  uint8_t stage[kWarps][kStageBytes];
+  int32_t n_dice, n_est, n_lr, n_shrunk;
+  int32_t lp_counter, pad_[3];
+  int32_t lp_best[kMaxJobs];   // block-cooperative longest-road search: result per job
+  uint8_t dice_list[kBatch], est_list[kBatch], lr_list[kBatch], shrunk_list[kBatch];
+  uint8_t skip[kBatch];        // MODE_RESET with a mask: games left untouched
 };
+static_assert(kBatch <= 4 * kWarps, "scalar phases map the games of a batch onto lanes 0..3 of the 32 warps");
+// the longest-road search borrows the whole staging area: 1024 path stacks, then kMaxJobs adjacency tables
+constexpr int kLpPathBytes = 54 * kThreads;
+static_assert(kLpPathBytes + kMaxJobs * CATAN_LP_ADJ_BYTES <= kWarps * kStageBytes, "longest-road scratch does not fit the staging area");
+static_assert(sizeof(BlockSmem) <= 227 * 1024, "block shared memory exceeds the 227 KB a CTA can opt into");
 
 // ---- TMA 1-D bulk store helpers (SASS: UBLKCP) ---------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -61,89 +82,220 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// stage row (built by all lanes of the warp) -> global, through the TMA engine; the row may be reused
+// once bulk_wait_read_all() has returned
+__device__ __forceinline__ void stage_to_global(void* gdst, const void* ssrc, uint32_t bytes, int lane) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) { bulk_store(gdst, ssrc, bytes); bulk_commit(); }
+}
+__device__ __forceinline__ void stage_reuse_wait(int lane) {
+  if (lane == 0) bulk_wait_read_all();
+  __syncwarp();
+}
+
 template <int MODE, bool SAMPLE>
-__global__ void __launch_bounds__(kThreads) env_kernel(const __grid_constant__ EnvParams P) {
+__global__ void __launch_bounds__(kThreads, 1) env_kernel(const __grid_constant__ EnvParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BlockSmem& S = *reinterpret_cast<BlockSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     const int4* src = reinterpret_cast<const int4*>(&d_topo);
     int4* dst = reinterpret_cast<int4*>(&S.topo);
-    for (int i = threadIdx.x; i < static_cast<int>(sizeof(Topo) / 16); i += kThreads) dst[i] = src[i];
+    for (int i = tid; i < static_cast<int>(sizeof(Topo) / 16); i += kThreads) dst[i] = src[i];
   }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpSmem& W = S.w[warp];
   Ctx cx;
-  cx.g = &W.g; cx.T = &S.topo; cx.ws = &W.ws; cx.obs = W.obs; cx.mask = W.mask; cx.cfg = &P.cfg;
+  cx.T = &S.topo; cx.obs = S.stage[warp]; cx.mask = S.stage[warp]; cx.scratch = S.stage[warp]; cx.cfg = &P.cfg;
   cx.seed = P.seed; cx.lane = lane;
-  const int e0 = MODE == MODE_REFRESH ? P.refresh_first : 0;
-  const int e1 = MODE == MODE_REFRESH ? P.refresh_first + P.refresh_count : P.n_envs;
-  bool stores_in_flight = false;
-  for (int e = e0 + blockIdx.x * kWarpsPerBlock + warp; e < e1; e += gridDim.x * kWarpsPerBlock) {
-    if (MODE == MODE_RESET && P.reset_mask != nullptr && P.reset_mask[e] == 0) continue;
-    if (stores_in_flight) {                       // the TMA engine must be done READING this warp's slab
-      if (lane == 0) bulk_wait_read_all();
-      __syncwarp();
-    }
-    cx.env_id = P.first_env_id + static_cast<uint64_t>(e);
-    GameRec* grec = P.recs + e;
+  cx.g = nullptr; cx.ws = nullptr; cx.env_id = 0;
+#ifdef CATAN_PROFILE_PHASES
+  cx.prof = P.prof; cx.prof_t = clock64();
+#endif
+  bool stage_busy = false;
+  const int n_batches = (P.range_count + kBatch - 1) / kBatch;
+  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const int base = P.range_first + batch * kBatch;                 // first env of this batch
+    const int nb = min(kBatch, P.range_first + P.range_count - base);
+    if (stage_busy) { stage_reuse_wait(lane); stage_busy = false; }  // the longest-road scratch aliases the staging row
+    __syncthreads();                                                 // previous batch fully retired (records stored)
+    // ---- phase 0: records -> shared memory (one contiguous, fully coalesced copy), actions -> scratch
     {
-      const int4* src = reinterpret_cast<const int4*>(grec);
-      int4* dst = reinterpret_cast<int4*>(&W.g);
-#pragma unroll
-      for (int i = lane; i < static_cast<int>(sizeof(GameRec) / 16); i += 32) dst[i] = src[i];
+      const int4* src = reinterpret_cast<const int4*>(P.recs + base);
+      int4* dst = reinterpret_cast<int4*>(S.recs);
+      const int n16 = nb * static_cast<int>(sizeof(GameRec) / 16);
+      for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
+      if (MODE == MODE_STEP) {
+        const int32_t* a = P.actions + static_cast<size_t>(base) * CATAN_ACTION_WORDS;
+        for (int i = tid; i < nb * CATAN_ACTION_WORDS; i += kThreads) S.ws[i / CATAN_ACTION_WORDS].action[i % CATAN_ACTION_WORDS] = a[i];
+      }
+      if (MODE == MODE_RESET) for (int i = tid; i < nb; i += kThreads) S.skip[i] = P.reset_mask != nullptr && P.reset_mask[base + i] == 0;
+      if (tid == 0) { S.n_dice = 0; S.n_est = 0; S.n_lr = 0; S.n_shrunk = 0; }
     }
-    if (MODE == MODE_STEP && lane < CATAN_ACTION_WORDS) W.ws.action[lane] = P.actions[static_cast<size_t>(e) * CATAN_ACTION_WORDS + lane];
-    __syncwarp();
+    __syncthreads();
+    CATAN_PROF(cx, PH_LOAD);
+#define CATAN_BIND(gi) do { cx.g = &S.recs[(gi)]; cx.ws = &S.ws[(gi)]; cx.env_id = P.first_env_id + static_cast<uint64_t>(base + (gi)); } while (0)
     if (MODE == MODE_STEP) {
-      const int err = step_game(cx, P.reward + static_cast<size_t>(e) * 4, P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE);
-      if (err && lane == 0) P.err_flags[e] |= 1u << err;
+      // scalar phases: game gi of the batch is handled by lane (gi / 32) of warp (gi % 32), so all 32 warps
+      // are busy and each warp instruction serves up to four games
+      const int sgi = warp + kWarps * lane;
+      const bool scalar_owner = lane < 4 && sgi < nb;
+      // ---- phase 1: translate + validate
+      if (scalar_owner) { CATAN_BIND(sgi); step_begin(cx); }
+      __syncthreads();
+      // ---- phase 2: scalar part of apply_action; queue the lane-parallel follow-ups
+      if (scalar_owner) {
+        CATAN_BIND(sgi);
+        WarpScratch& ws = *cx.ws;
+        if (ws.err) {
+          P.err_flags[base + sgi] |= 1u << ws.err;
+        } else {
+          apply_scalar(cx);
+          if (ws.dice_roll) S.dice_list[atomicAdd(&S.n_dice, 1)] = static_cast<uint8_t>(sgi);
+          if (ws.dice_roll || ws.n_est || ws.est_special) S.est_list[atomicAdd(&S.n_est, 1)] = static_cast<uint8_t>(sgi);
+          if (ws.lr_pid) S.lr_list[atomicAdd(&S.n_lr, 1)] = static_cast<uint8_t>(sgi);
+        }
+      }
+      __syncthreads();
+      CATAN_PROF(cx, PH_SCALAR);
+      // ---- phase 3: dice payout (game.py:151-175), warp per queued game
+      for (int i = warp; i < S.n_dice; i += kWarps) { CATAN_BIND(S.dice_list[i]); dice_payout(cx); }
+      __syncthreads();
+      CATAN_PROF(cx, PH_DICE);
+      // ---- phase 4: belief updates
+      for (int i = warp; i < S.n_est; i += kWarps) { CATAN_BIND(S.est_list[i]); est_apply(cx); }
+      __syncthreads();
+      CATAN_PROF(cx, PH_EST);
+      // ---- phase 5: longest road (game.py:843-919), searched by the WHOLE block: the work items of every
+      // queued game go into one pool that all 1024 lanes drain, so one dense road network cannot stall the SM
+      {
+        uint8_t* lp_paths = &S.stage[0][0];
+        uint64_t* lp_adj = reinterpret_cast<uint64_t*>(&S.stage[0][0] + kLpPathBytes);
+        const int n_lr = S.n_lr;
+        for (int c0 = 0; c0 < n_lr; c0 += kMaxJobs) {                // pass A: the player whose road changed
+          const int nj = min(kMaxJobs, n_lr - c0);
+          for (int j = warp; j < nj; j += kWarps) {
+            const int gi = S.lr_list[c0 + j];
+            lp_build_adj(S.recs[gi], S.topo, S.ws[gi].lr_pid, lp_adj + j * 54, lane);
+          }
+          if (tid < nj) S.lp_best[tid] = 0;
+          if (tid == 0) S.lp_counter = 0;
+          __syncthreads();
+          lp_search(lp_adj, nj, &S.lp_counter, S.lp_best, lp_paths, kThreads, tid);
+          __syncthreads();
+          if (tid < nj) {
+            const int gi = S.lr_list[c0 + tid];
+            WarpScratch& ws = S.ws[gi];
+            const int len = S.lp_best[tid];
+            ws.lr_len = static_cast<uint8_t>(len);
+            ws.lr_shrunk = lr_is_shrunk(S.recs[gi], ws.lr_pid, len);
+            if (ws.lr_shrunk) S.shrunk_list[atomicAdd(&S.n_shrunk, 1)] = static_cast<uint8_t>(gi);
+          }
+          __syncthreads();
+        }
+        const int n_sh = S.n_shrunk;
+        for (int c0 = 0; c0 < n_sh; c0 += kMaxJobs / 3) {            // pass B (rare): holder's path shrank -> the other three
+          const int nj = 3 * min(kMaxJobs / 3, n_sh - c0);
+          for (int j = warp; j < nj; j += kWarps) {
+            const int gi = S.shrunk_list[c0 + j / 3], pid = S.ws[gi].lr_pid;
+            int o = j % 3 + 1;
+            if (o >= pid) ++o;
+            lp_build_adj(S.recs[gi], S.topo, o, lp_adj + j * 54, lane);
+          }
+          if (tid < nj) S.lp_best[tid] = 0;
+          if (tid == 0) S.lp_counter = 0;
+          __syncthreads();
+          lp_search(lp_adj, nj, &S.lp_counter, S.lp_best, lp_paths, kThreads, tid);
+          __syncthreads();
+          if (tid < nj) {
+            const int gi = S.shrunk_list[c0 + tid / 3], pid = S.ws[gi].lr_pid;
+            int o = tid % 3 + 1;
+            if (o >= pid) ++o;
+            S.ws[gi].lr_other[o] = static_cast<uint8_t>(S.lp_best[tid]);
+          }
+          __syncthreads();
+        }
+        if (tid < n_lr) {
+          const int gi = S.lr_list[tid];
+          const WarpScratch& ws = S.ws[gi];
+          lr_apply(S.recs[gi], ws.lr_pid, ws.lr_len, ws.lr_shrunk != 0, ws.lr_other);
+        }
+      }
+      __syncthreads();
+      CATAN_PROF(cx, PH_LROAD);
+      // ---- phase 6: done / reward / info (+ auto-reset)
+      if (scalar_owner) {
+        CATAN_BIND(sgi);
+        step_finish(cx, P.reward + static_cast<size_t>(base + sgi) * 4, P.info + static_cast<size_t>(base + sgi) * CATAN_INFO_STRIDE);
+      }
+      __syncthreads();
+      CATAN_PROF(cx, PH_FINISH);
     } else {
-      if (lane == 0) {
-        if (MODE == MODE_RESET) { reset_game(cx); W.g.episode_steps = 0; }
+      const int gi = warp + kWarps * lane;
+      if (lane < 4 && gi < nb && !(MODE == MODE_RESET && S.skip[gi])) {
+        CATAN_BIND(gi);
+        if (MODE == MODE_RESET) { reset_game(cx); cx.g->episode_steps = 0; }
         else compute_seats(cx);
-        uint8_t* info = P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE;
+        uint8_t* info = P.info + static_cast<size_t>(base + gi) * CATAN_INFO_STRIDE;
         for (int i = 0; i < CATAN_INFO_STRIDE; ++i) info[i] = 0;
-        info[CATAN_INFO_ACTOR] = static_cast<uint8_t>(current_actor(W.g));
-        info[CATAN_INFO_WINNER] = W.g.winner;
-        for (int p = 0; p < 4; ++p) info[CATAN_INFO_FINAL_VP + p] = static_cast<uint8_t>(W.g.vp[p]);
+        info[CATAN_INFO_ACTOR] = static_cast<uint8_t>(current_actor(*cx.g));
+        info[CATAN_INFO_WINNER] = cx.g->winner;
+        for (int p = 0; p < 4; ++p) info[CATAN_INFO_FINAL_VP + p] = static_cast<uint8_t>(cx.g->vp[p]);
         info[CATAN_INFO_RESET] = MODE == MODE_RESET;
       }
-      __syncwarp();
+      __syncthreads();
     }
-    encode_masks(cx);
-    encode_obs(cx);
-    if (SAMPLE) {
-      const uint32_t decision = W.g.decision_ctr;
-      __syncwarp();
-      sample_action(W.mask, W.obs, P.seed, cx.env_id, decision, lane,
-                    P.actions_out + static_cast<size_t>(e) * CATAN_ACTION_WORDS);
-      if (lane == 0) W.g.decision_ctr = decision + 1;
+    // ---- phase 7: legal-action masks (+ the next random-legal action), staged row -> TMA bulk store
+    for (int gi = warp; gi < nb; gi += kWarps) {
+      if (MODE == MODE_RESET && S.skip[gi]) continue;
+      CATAN_BIND(gi);
+      if (stage_busy) stage_reuse_wait(lane);
+      encode_masks(cx);
+      if (SAMPLE) {
+        const uint32_t decision = cx.g->decision_ctr;
+        __syncwarp();
+        sample_action(cx.mask, cx.g->res[current_actor(*cx.g) - 1], P.seed, cx.env_id, decision, lane,
+                      P.actions_out + static_cast<size_t>(base + gi) * CATAN_ACTION_WORDS);
+        if (lane == 0) cx.g->decision_ctr = decision + 1;
+      }
+      stage_to_global(P.masks + static_cast<size_t>(base + gi) * CATAN_MASK_STRIDE, cx.mask, CATAN_MASK_STRIDE, lane);
+      stage_busy = true;
     }
-    // generic-proxy writes to shared memory -> visible to the async proxy, then one lane issues the stores
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      bulk_store(grec, &W.g, sizeof(GameRec));
-      bulk_store(P.masks + static_cast<size_t>(e) * CATAN_MASK_STRIDE, W.mask, CATAN_MASK_STRIDE);
-      bulk_store(P.obs + static_cast<size_t>(e) * CATAN_OBS_STRIDE, W.obs, CATAN_OBS_STRIDE);
-      bulk_commit();
+    __syncthreads();
+    CATAN_PROF(cx, PH_MASKS);
+    // ---- phase 8: packed observation, staged row -> TMA bulk store
+    for (int gi = warp; gi < nb; gi += kWarps) {
+      if (MODE == MODE_RESET && S.skip[gi]) continue;
+      CATAN_BIND(gi);
+      if (stage_busy) stage_reuse_wait(lane);
+      encode_obs(cx);
+      stage_to_global(P.obs + static_cast<size_t>(base + gi) * CATAN_OBS_STRIDE, cx.obs, CATAN_OBS_STRIDE, lane);
+      stage_busy = true;
     }
-    stores_in_flight = true;
+    __syncthreads();
+    CATAN_PROF(cx, PH_OBS);
+    // ---- phase 9: records -> global (contiguous, coalesced)
+    {
+      int4* dst = reinterpret_cast<int4*>(P.recs + base);
+      const int4* src = reinterpret_cast<const int4*>(S.recs);
+      const int n16 = nb * static_cast<int>(sizeof(GameRec) / 16);
+      for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
+    }
+    CATAN_PROF(cx, PH_STORE);
+#undef CATAN_BIND
   }
-  if (stores_in_flight && lane == 0) bulk_wait_all();
+  if (stage_busy && lane == 0) bulk_wait_all();
 }
 
 // stand-alone sampler: one warp per env, reads the bound mask/obs rows from global memory
-__global__ void __launch_bounds__(kThreads) sample_kernel(GameRec* recs, int n_envs, uint64_t seed, uint64_t first_env_id,
+__global__ void __launch_bounds__(kSampleWarpsPerBlock * 32) sample_kernel(GameRec* recs, int n_envs, uint64_t seed, uint64_t first_env_id,
                                                           const uint8_t* masks, const uint8_t* obs, int32_t* actions_out) {
   const int lane = threadIdx.x & 31;
-  const int e = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int e = blockIdx.x * kSampleWarpsPerBlock + (threadIdx.x >> 5);
   if (e >= n_envs) return;
   uint32_t dec = 0;
   if (lane == 0) { dec = recs[e].decision_ctr; recs[e].decision_ctr = dec + 1; }
   dec = __shfl_sync(0xffffffffu, dec, 0);
-  sample_action(masks + static_cast<size_t>(e) * CATAN_MASK_STRIDE, obs + static_cast<size_t>(e) * CATAN_OBS_STRIDE, seed,
+  sample_action(masks + static_cast<size_t>(e) * CATAN_MASK_STRIDE, obs + static_cast<size_t>(e) * CATAN_OBS_STRIDE + CATAN_OBS_CURRENT_RES + 1, seed,
                 first_env_id + static_cast<uint64_t>(e), dec, lane, actions_out + static_cast<size_t>(e) * CATAN_ACTION_WORDS);
 }
 
@@ -182,19 +334,36 @@ static int device_guard(const catan_env* env) {
   return 0;
 }
 
+#ifdef CATAN_PROFILE_PHASES
+static unsigned long long* g_prof_dev = nullptr;
+extern "C" int catan_prof_read(unsigned long long* out_host, int clear) {   // profiling build only; not part of the ABI
+  if (!g_prof_dev) return -1;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out_host, g_prof_dev, sizeof(unsigned long long) * catanb::PH_COUNT * 4, cudaMemcpyDeviceToHost);
+  if (clear) cudaMemset(g_prof_dev, 0, sizeof(unsigned long long) * catanb::PH_COUNT * 4);
+  return 0;
+}
+#endif
+
 static EnvParams make_params(const catan_env* env) {
   EnvParams P{};
+#ifdef CATAN_PROFILE_PHASES
+  if (!g_prof_dev) { cudaMalloc(&g_prof_dev, sizeof(unsigned long long) * catanb::PH_COUNT * 4); cudaMemset(g_prof_dev, 0, sizeof(unsigned long long) * catanb::PH_COUNT * 4); }
+  P.prof = g_prof_dev;
+#endif
   P.recs = env->recs; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
   P.obs = env->obs; P.masks = env->masks; P.reward = env->reward; P.info = env->info; P.err_flags = env->err_flags;
   return P;
 }
 
 template <int MODE, bool SAMPLE>
-static int launch_env(const catan_env* env, const EnvParams& P, int n_items, cudaStream_t stream) {
+static int launch_env(const catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
   const size_t smem = sizeof(catanb::BlockSmem);
-  static_assert(sizeof(catanb::BlockSmem) <= 48 * 1024, "stays under the default dynamic shared memory limit");
-  int blocks = (n_items + catanb::kWarpsPerBlock - 1) / catanb::kWarpsPerBlock;
-  if (blocks > env->grid) blocks = env->grid;
+  // opt in to > 48 KB of dynamic shared memory (per kernel instantiation and device; cheap, so done every time)
+  CATAN_CUDA(cudaFuncSetAttribute(catanb::env_kernel<MODE, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  P.range_first = first; P.range_count = count;
+  int blocks = (count + catanb::kBatch - 1) / catanb::kBatch;
+  if (blocks > env->grid) blocks = env->grid;                       // persistent: one 1024-thread block per SM
   if (blocks < 1) blocks = 1;
   catanb::env_kernel<MODE, SAMPLE><<<blocks, catanb::kThreads, smem, stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
@@ -244,8 +413,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   cudaDeviceProp prop{};
   CATAN_CUDA(cudaGetDeviceProperties(&prop, device));
   env->sm_count = prop.multiProcessorCount;
-  // persistent-style grid: a whole number of waves of resident blocks (shared memory bound: ~14.4 KB/block)
-  env->grid = env->sm_count * 12;
+  env->grid = env->sm_count;   // one persistent 32-warp block per SM (shared-memory bound)
   e = cudaMalloc(&env->recs, sizeof(GameRec) * static_cast<size_t>(n_envs));
   if (e == cudaSuccess) e = cudaMemset(env->recs, 0, sizeof(GameRec) * static_cast<size_t>(n_envs));
   if (e == cudaSuccess) e = cudaMalloc(&env->err_flags, sizeof(uint32_t) * static_cast<size_t>(n_envs));
@@ -290,7 +458,7 @@ int catan_reset(catan_env_t* env, const uint8_t* reset_mask_dev, void* stream) {
   if (device_guard(env)) return -1;
   EnvParams P = make_params(env);
   P.reset_mask = reset_mask_dev;
-  return launch_env<catanb::MODE_RESET, false>(env, P, env->n, static_cast<cudaStream_t>(stream));
+  return launch_env<catanb::MODE_RESET, false>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
 }
 
 int catan_step(catan_env_t* env, const int32_t* actions_dev, void* stream) {
@@ -299,7 +467,7 @@ int catan_step(catan_env_t* env, const int32_t* actions_dev, void* stream) {
   if (device_guard(env)) return -1;
   EnvParams P = make_params(env);
   P.actions = actions_dev;
-  return launch_env<catanb::MODE_STEP, false>(env, P, env->n, static_cast<cudaStream_t>(stream));
+  return launch_env<catanb::MODE_STEP, false>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
 }
 
 int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream) {
@@ -309,15 +477,15 @@ int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream) {
   EnvParams P = make_params(env);
   P.actions = actions_io_dev;
   P.actions_out = actions_io_dev;
-  return launch_env<catanb::MODE_STEP, true>(env, P, env->n, static_cast<cudaStream_t>(stream));
+  return launch_env<catanb::MODE_STEP, true>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
 }
 
 int catan_sample_random(catan_env_t* env, int32_t* actions_out_dev, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_out_dev) return fail("actions_out_dev is null");
   if (device_guard(env)) return -1;
-  const int blocks = (env->n + catanb::kWarpsPerBlock - 1) / catanb::kWarpsPerBlock;
-  catanb::sample_kernel<<<blocks, catanb::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int blocks = (env->n + catanb::kSampleWarpsPerBlock - 1) / catanb::kSampleWarpsPerBlock;
+  catanb::sample_kernel<<<blocks, catanb::kSampleWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       env->recs, env->n, env->seed, env->first_env_id, env->masks, env->obs, actions_out_dev);
   CATAN_CUDA(cudaGetLastError());
   return 0;
@@ -375,8 +543,7 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
   for (int i = 0; i < count; ++i) catanb::state_to_rec(in[i], tmp[static_cast<size_t>(i)]);
   CATAN_CUDA(cudaMemcpy(env->recs + first, tmp.data(), sizeof(GameRec) * static_cast<size_t>(count), cudaMemcpyHostToDevice));
   EnvParams P = make_params(env);
-  P.refresh_first = first; P.refresh_count = count;
-  if (launch_env<catanb::MODE_REFRESH, false>(env, P, count, nullptr)) return -1;
+  if (launch_env<catanb::MODE_REFRESH, false>(env, P, first, count, nullptr)) return -1;
   CATAN_CUDA(cudaDeviceSynchronize());
   return 0;
 }

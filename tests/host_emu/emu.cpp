@@ -15,13 +15,14 @@ struct EmuEnv {
   WarpScratch ws;
   uint8_t obs[CATAN_OBS_STRIDE];
   uint8_t mask[CATAN_MASK_STRIDE];
+  alignas(16) uint8_t scratch[CATAN_LP_SCRATCH_BYTES + 16];
   catan_config_t cfg;
   uint64_t seed, env_id;
 };
 
 static Ctx make_ctx(EmuEnv* e) {
   Ctx cx;
-  cx.g = &e->g; cx.T = &h_topo; cx.ws = &e->ws; cx.obs = e->obs; cx.mask = e->mask; cx.cfg = &e->cfg;
+  cx.g = &e->g; cx.T = &h_topo; cx.ws = &e->ws; cx.obs = e->obs; cx.mask = e->mask; cx.scratch = e->scratch; cx.cfg = &e->cfg;
   cx.seed = e->seed; cx.env_id = e->env_id; cx.lane = 0;
   return cx;
 }
@@ -53,7 +54,7 @@ int emu_step(EmuEnv* e, const int32_t* action, float* reward, uint8_t* info) {
 }
 
 void emu_sample(EmuEnv* e, int32_t* action) {
-  sample_action(e->mask, e->obs, e->seed, e->env_id, e->g.decision_ctr++, 0, action);
+  sample_action(e->mask, e->obs + CATAN_OBS_CURRENT_RES + 1, e->seed, e->env_id, e->g.decision_ctr++, 0, action);
 }
 
 const uint8_t* emu_obs(EmuEnv* e) { return e->obs; }
