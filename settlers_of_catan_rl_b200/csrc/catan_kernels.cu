@@ -30,7 +30,8 @@ __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 // stall_no_inst).  Inside a phase each warp still owns one game at a time (lanes cooperate on it).
 constexpr int kWarps = 32;
 constexpr int kThreads = kWarps * 32;
-constexpr int kBatch = 112;                 // games per block iteration: 4 rounds of 148 blocks cover 65 536 games
+constexpr int kBlocksPerSM = 1;              // measured: 2 x 16 warps per SM is 8% slower (profiles/r1_notes.md)
+constexpr int kBatch = 112;                 // games per block iteration (3.5 per warp; 586 batches for 65 536 games)
 constexpr int kStageBytes = 2304;           // per-warp staging row: >= obs row, >= longest-road scratch
 constexpr int kSampleWarpsPerBlock = 4;     // stand-alone sampler kernel
 constexpr int kMaxJobs = 39;                // longest-road graphs searched per cooperative pass (13 games x 3 when re-measuring)
@@ -52,6 +53,8 @@ struct EnvParams {
   uint32_t* err_flags;
   const uint8_t* reset_mask;   // MODE_RESET: nullptr = all envs
   int range_first, range_count;   // env range this launch covers
+  unsigned int* ticket;           // device-wide batch ticket counter (never reset)
+  unsigned int ticket_base;       // value of *ticket when this launch starts
   unsigned long long* prof;    // profiling build only
 };
 
@@ -60,17 +63,17 @@ struct alignas(16) BlockSmem {
   GameRec recs[kBatch];
   WarpScratch ws[kBatch];
   uint8_t stage[kWarps][kStageBytes];
-  int32_t n_dice, n_est, n_lr, n_shrunk;
-  int32_t lp_counter, pad_[3];
+  int32_t n_est, n_lr, n_shrunk, pad0_;
+  int32_t lp_counter, batch, pad_[2];
   int32_t lp_best[kMaxJobs];   // block-cooperative longest-road search: result per job
-  uint8_t dice_list[kBatch], est_list[kBatch], lr_list[kBatch], shrunk_list[kBatch];
+  uint8_t est_list[kBatch], lr_list[kBatch], shrunk_list[kBatch];
   uint8_t skip[kBatch];        // MODE_RESET with a mask: games left untouched
 };
 static_assert(kBatch <= 4 * kWarps, "scalar phases map the games of a batch onto lanes 0..3 of the 32 warps");
 // the longest-road search borrows the whole staging area: 1024 path stacks, then kMaxJobs adjacency tables
 constexpr int kLpPathBytes = 54 * kThreads;
 static_assert(kLpPathBytes + kMaxJobs * CATAN_LP_ADJ_BYTES <= kWarps * kStageBytes, "longest-road scratch does not fit the staging area");
-static_assert(sizeof(BlockSmem) <= 227 * 1024, "block shared memory exceeds the 227 KB a CTA can opt into");
+static_assert(sizeof(BlockSmem) * kBlocksPerSM <= 227 * 1024, "block shared memory exceeds what kBlocksPerSM blocks can get on one SM");
 
 // ---- TMA 1-D bulk store helpers (SASS: UBLKCP) ---------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -95,7 +98,7 @@ __device__ __forceinline__ void stage_reuse_wait(int lane) {
 }
 
 template <int MODE, bool SAMPLE>
-__global__ void __launch_bounds__(kThreads, 1) env_kernel(const __grid_constant__ EnvParams P) {
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __grid_constant__ EnvParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BlockSmem& S = *reinterpret_cast<BlockSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,11 +116,18 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const __grid_constant_
 #endif
   bool stage_busy = false;
   const int n_batches = (P.range_count + kBatch - 1) / kBatch;
-  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+  for (;;) {
+    // blocks claim batches from a device-wide ticket counter: an SM that drew an expensive batch simply takes
+    // fewer of them.  The counter is never reset: every launch makes exactly n_batches + gridDim.x claims, so the
+    // host advances ticket_base by that amount (launch_env).
+    __syncthreads();                                                 // previous batch fully retired; S.batch reusable
+    if (tid == 0) S.batch = static_cast<int32_t>(atomicAdd(P.ticket, 1u) - P.ticket_base);
+    __syncthreads();
+    const int batch = S.batch;
+    if (batch >= n_batches) break;
     const int base = P.range_first + batch * kBatch;                 // first env of this batch
     const int nb = min(kBatch, P.range_first + P.range_count - base);
     if (stage_busy) { stage_reuse_wait(lane); stage_busy = false; }  // the longest-road scratch aliases the staging row
-    __syncthreads();                                                 // previous batch fully retired (records stored)
     // ---- phase 0: records -> shared memory (one contiguous, fully coalesced copy), actions -> scratch
     {
       const int4* src = reinterpret_cast<const int4*>(P.recs + base);
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const __grid_constant_
         for (int i = tid; i < nb * CATAN_ACTION_WORDS; i += kThreads) S.ws[i / CATAN_ACTION_WORDS].action[i % CATAN_ACTION_WORDS] = a[i];
       }
       if (MODE == MODE_RESET) for (int i = tid; i < nb; i += kThreads) S.skip[i] = P.reset_mask != nullptr && P.reset_mask[base + i] == 0;
-      if (tid == 0) { S.n_dice = 0; S.n_est = 0; S.n_lr = 0; S.n_shrunk = 0; }
+      if (tid == 0) { S.n_est = 0; S.n_lr = 0; S.n_shrunk = 0; }
     }
     __syncthreads();
     CATAN_PROF(cx, PH_LOAD);
@@ -140,29 +150,27 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const __grid_constant_
       const int sgi = warp + kWarps * lane;
       const bool scalar_owner = lane < 4 && sgi < nb;
       // ---- phase 1: translate + validate
-      if (scalar_owner) { CATAN_BIND(sgi); step_begin(cx); }
-      __syncthreads();
-      // ---- phase 2: scalar part of apply_action; queue the lane-parallel follow-ups
+      // ---- phase 2: scalar part of apply_action; queue the lane-parallel follow-ups (same owner thread: no barrier)
       if (scalar_owner) {
         CATAN_BIND(sgi);
+        step_begin(cx);
         WarpScratch& ws = *cx.ws;
         if (ws.err) {
           P.err_flags[base + sgi] |= 1u << ws.err;
         } else {
           apply_scalar(cx);
-          if (ws.dice_roll) S.dice_list[atomicAdd(&S.n_dice, 1)] = static_cast<uint8_t>(sgi);
           if (ws.dice_roll || ws.n_est || ws.est_special) S.est_list[atomicAdd(&S.n_est, 1)] = static_cast<uint8_t>(sgi);
           if (ws.lr_pid) S.lr_list[atomicAdd(&S.n_lr, 1)] = static_cast<uint8_t>(sgi);
         }
       }
       __syncthreads();
       CATAN_PROF(cx, PH_SCALAR);
-      // ---- phase 3: dice payout (game.py:151-175), warp per queued game
-      for (int i = warp; i < S.n_dice; i += kWarps) { CATAN_BIND(S.dice_list[i]); dice_payout(cx); }
-      __syncthreads();
-      CATAN_PROF(cx, PH_DICE);
-      // ---- phase 4: belief updates
-      for (int i = warp; i < S.n_est; i += kWarps) { CATAN_BIND(S.est_list[i]); est_apply(cx); }
+      // ---- phase 3+4: dice payout (game.py:151-175) and belief updates (game.py:921-1010), warp per queued game
+      for (int i = warp; i < S.n_est; i += kWarps) {
+        CATAN_BIND(S.est_list[i]);
+        if (cx.ws->dice_roll) dice_payout(cx);
+        est_apply(cx);
+      }
       __syncthreads();
       CATAN_PROF(cx, PH_EST);
       // ---- phase 5: longest road (game.py:843-919), searched by the WHOLE block: the work items of every
@@ -222,12 +230,13 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const __grid_constant_
       }
       __syncthreads();
       CATAN_PROF(cx, PH_LROAD);
-      // ---- phase 6: done / reward / info (+ auto-reset)
+      // ---- phase 6: done / reward / info (+ auto-reset).  Game gi is finished by lane gi/32 of warp gi%32, the
+      // warp that also encodes its masks and observation below, so a warp barrier is enough from here on.
       if (scalar_owner) {
         CATAN_BIND(sgi);
         step_finish(cx, P.reward + static_cast<size_t>(base + sgi) * 4, P.info + static_cast<size_t>(base + sgi) * CATAN_INFO_STRIDE);
       }
-      __syncthreads();
+      __syncwarp();
       CATAN_PROF(cx, PH_FINISH);
     } else {
       const int gi = warp + kWarps * lane;
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const __grid_constant_
         for (int p = 0; p < 4; ++p) info[CATAN_INFO_FINAL_VP + p] = static_cast<uint8_t>(cx.g->vp[p]);
         info[CATAN_INFO_RESET] = MODE == MODE_RESET;
       }
-      __syncthreads();
+      __syncwarp();
     }
     // ---- phase 7: legal-action masks (+ the next random-legal action), staged row -> TMA bulk store
     for (int gi = warp; gi < nb; gi += kWarps) {
@@ -260,7 +269,6 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const __grid_constant_
       stage_to_global(P.masks + static_cast<size_t>(base + gi) * CATAN_MASK_STRIDE, cx.mask, CATAN_MASK_STRIDE, lane);
       stage_busy = true;
     }
-    __syncthreads();
     CATAN_PROF(cx, PH_MASKS);
     // ---- phase 8: packed observation, staged row -> TMA bulk store
     for (int gi = warp; gi < nb; gi += kWarps) {
@@ -320,6 +328,8 @@ struct catan_env {
   GameRec* recs = nullptr;
   uint32_t* err_flags = nullptr;
   int32_t* actions_stage = nullptr;   // device staging for catan_step_host
+  unsigned int* ticket = nullptr;     // batch ticket counter of the persistent kernel
+  unsigned int ticket_base = 0;
   uint8_t* obs = nullptr;
   uint8_t* masks = nullptr;
   float* reward = nullptr;
@@ -357,7 +367,7 @@ static EnvParams make_params(const catan_env* env) {
 }
 
 template <int MODE, bool SAMPLE>
-static int launch_env(const catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
+static int launch_env(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
   const size_t smem = sizeof(catanb::BlockSmem);
   // opt in to > 48 KB of dynamic shared memory (per kernel instantiation and device; cheap, so done every time)
   CATAN_CUDA(cudaFuncSetAttribute(catanb::env_kernel<MODE, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -365,6 +375,9 @@ static int launch_env(const catan_env* env, EnvParams P, int first, int count, c
   int blocks = (count + catanb::kBatch - 1) / catanb::kBatch;
   if (blocks > env->grid) blocks = env->grid;                       // persistent: one 1024-thread block per SM
   if (blocks < 1) blocks = 1;
+  P.ticket = env->ticket;
+  P.ticket_base = env->ticket_base;
+  env->ticket_base += static_cast<unsigned int>((count + catanb::kBatch - 1) / catanb::kBatch + blocks);   // claims this launch makes
   catanb::env_kernel<MODE, SAMPLE><<<blocks, catanb::kThreads, smem, stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
   return 0;
@@ -413,14 +426,16 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   cudaDeviceProp prop{};
   CATAN_CUDA(cudaGetDeviceProperties(&prop, device));
   env->sm_count = prop.multiProcessorCount;
-  env->grid = env->sm_count;   // one persistent 32-warp block per SM (shared-memory bound)
+  env->grid = env->sm_count * catanb::kBlocksPerSM;   // persistent blocks (shared-memory bound)
   e = cudaMalloc(&env->recs, sizeof(GameRec) * static_cast<size_t>(n_envs));
   if (e == cudaSuccess) e = cudaMemset(env->recs, 0, sizeof(GameRec) * static_cast<size_t>(n_envs));
   if (e == cudaSuccess) e = cudaMalloc(&env->err_flags, sizeof(uint32_t) * static_cast<size_t>(n_envs));
   if (e == cudaSuccess) e = cudaMemset(env->err_flags, 0, sizeof(uint32_t) * static_cast<size_t>(n_envs));
   if (e == cudaSuccess) e = cudaMalloc(&env->actions_stage, sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(n_envs));
+  if (e == cudaSuccess) e = cudaMalloc(&env->ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(env->ticket, 0, sizeof(unsigned int));
   if (e != cudaSuccess) {
-    cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage);
+    cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage); cudaFree(env->ticket);
     delete env;
     return cuda_fail(e, "cudaMalloc(game records)");
   }
@@ -430,7 +445,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
 
 int catan_destroy(catan_env_t* env) {
   if (!env) return 0;
-  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage);
+  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage); cudaFree(env->ticket);
   delete env;
   return 0;
 }
