@@ -68,6 +68,11 @@ int catan_reset(catan_env_t* env, const uint8_t* reset_mask_dev, void* stream);
  * DONE / WINNER / FINAL_VP describe the finished one). */
 int catan_step(catan_env_t* env, const int32_t* actions_dev, void* stream);
 
+/* catan_step for the envs whose byte in step_mask_dev[n] is non-zero; the others are frozen (state and outputs
+ * untouched).  Used by the rollout collector: an env that has filled its quota of active-seat decisions waits for
+ * the rest (RL/ppo/game_manager.py:78).  step_mask_dev == NULL: all envs. */
+int catan_step_masked(catan_env_t* env, const int32_t* actions_dev, const uint8_t* step_mask_dev, void* stream);
+
 /* Random-legal policy used for the env-only benchmark: samples one composite action
  * per env from the bound masks/obs into actions_out_dev. */
 int catan_sample_random(catan_env_t* env, int32_t* actions_out_dev, void* stream);
@@ -109,6 +114,34 @@ int catan_gae(const float* rewards_dev, const float* values_dev, const float* ma
  *                     (SURVEY.md 8e); that 24-byte exchange is the only collective on this path. */
 int catan_adv_stats(const float* advantages_dev, long long count, double* stats_dev, void* stream);
 int catan_adv_apply(float* advantages_dev, long long count, const double* stats_dev, double eps, void* stream);
+
+/* ---- rollout collector (RL/ppo/game_manager.py:69-140 + RL/ppo/process_batch.py:37-104) -----------
+ * The reference records, per env, only the decisions of ONE "active" seat: an observation (+ masks) each time it
+ * becomes that seat's turn, the action / log-prob it takes, the sum of its rewards until its next decision, and a
+ * terminal mask that is 0 when the stored observation is the first of a new game.  Every env fills its own quota of
+ * T+1 observations; time-major device buffers, all caller-owned: */
+typedef struct catan_rollout {
+  uint8_t* obs;               /* [T+1][N][CATAN_OBS_STRIDE]                     process_batch.py:40-51 */
+  uint8_t* masks;             /* [T][N][CATAN_MASK_STRIDE]                      process_batch.py:77-91 */
+  int32_t* actions;           /* [T][N][CATAN_ACTION_WORDS]                     process_batch.py:67-75 */
+  float* logp;                /* [T][N]                                         process_batch.py:93-96 */
+  float* rewards;             /* [T][N]                                         process_batch.py:61-65 */
+  float* tmasks;              /* [T+1][N] terminal masks                        process_batch.py:98-103 */
+  int32_t* cursors;           /* [N][4]  lengths of the env's obs / action / reward / terminal-mask lists */
+  float* acc;                 /* [N][4]  running reward sums per player (game_manager.py:94-95) */
+  uint8_t* flags;             /* [N]     bit 0 = done_since_prev_turn (game_manager.py:77,134-136), bit 1 = last terminal mask */
+  const uint8_t* active_pid;  /* [N]     the recorded seat's PlayerId (game_manager.py:26-27) */
+  uint8_t* collecting;        /* [N] out (may be NULL): 1 while the env still needs observations -> catan_step_masked */
+  int32_t T, N;
+} catan_rollout_t;
+
+/* One call per tick AFTER catan_step[_masked] (begin = 0): consumes the env's bound obs / masks / reward / info rows plus
+ * the actions and log-probs of that tick; `stepped_dev` = the mask the step used (NULL = all).
+ * begin = 1 starts a rollout without a step: fresh = 1 right after catan_reset (GamesAndPoliciesManager.reset,
+ * game_manager.py:34-56), fresh = 0 carries the last observation / terminal mask over (_after_rollouts, :142-150). */
+int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t* env_obs_dev, const uint8_t* env_masks_dev,
+                        const float* env_reward_dev, const uint8_t* env_info_dev, const int32_t* actions_dev,
+                        const float* logp_dev, const uint8_t* stepped_dev, int begin, int fresh, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,7 @@ enum { CATAN_RES_BRICK = 0, CATAN_RES_WOOD = 1, CATAN_RES_ORE = 2, CATAN_RES_SHE
 #define CATAN_INFO_ROLL        9   /* die_1 + die_2 if this step rolled, else 0 */
 #define CATAN_INFO_ERR         10  /* non-zero: action rejected by validation this step (state unchanged) */
 #define CATAN_INFO_RESET       11  /* 1 if the env was auto-reset inside this step */
+#define CATAN_INFO_ACTOR_PRE   12  /* PlayerId that would act next in the state BEFORE any auto-reset (game_manager.py:99) */
 #define CATAN_INFO_STRIDE      16
 
 /* error codes stored in CATAN_INFO_ERR and OR-ed (1<<code) into the sticky err_flags */

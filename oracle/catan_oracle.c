@@ -843,6 +843,7 @@ int catan_oracle_step(S* s, const catan_config_t* cfg, const int32_t* action, ui
   if (err) {
     info[CATAN_INFO_ERR] = (uint8_t)err;
     info[CATAN_INFO_ACTOR] = (uint8_t)catan_oracle_actor(s);
+    info[CATAN_INFO_ACTOR_PRE] = info[CATAN_INFO_ACTOR];
     info[CATAN_INFO_WINNER] = (uint8_t)s->winner;
     for (int p = 0; p < 4; ++p) info[CATAN_INFO_FINAL_VP + p] = (uint8_t)s->vp[p];
     return err;
@@ -871,6 +872,7 @@ int catan_oracle_step(S* s, const catan_config_t* cfg, const int32_t* action, ui
   info[CATAN_INFO_WINNER] = (uint8_t)s->winner;
   for (int p = 0; p < 4; ++p) info[CATAN_INFO_FINAL_VP + p] = (uint8_t)s->vp[p];
   info[CATAN_INFO_ACTOR] = (uint8_t)catan_oracle_actor(s);
+  info[CATAN_INFO_ACTOR_PRE] = info[CATAN_INFO_ACTOR];
   return 0;
 }
 

@@ -28,6 +28,14 @@ class CatanConfig(C.Structure):
     ]
 
 
+class CatanRollout(C.Structure):
+    """``catan_rollout_t``: device pointers of the time-major rollout buffers."""
+
+    _fields_ = [("obs", C.c_void_p), ("masks", C.c_void_p), ("actions", C.c_void_p), ("logp", C.c_void_p), ("rewards", C.c_void_p),
+                ("tmasks", C.c_void_p), ("cursors", C.c_void_p), ("acc", C.c_void_p), ("flags", C.c_void_p),
+                ("active_pid", C.c_void_p), ("collecting", C.c_void_p), ("T", C.c_int32), ("N", C.c_int32)]
+
+
 class CatanError(RuntimeError):
     pass
 
@@ -52,6 +60,8 @@ ABI = {
     "catan_bind": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "catan_reset": (C.c_int, [_vp, _vp, _vp]),
     "catan_step": (C.c_int, [_vp, _vp, _vp]),
+    "catan_step_masked": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "catan_rollout_store": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "catan_sample_random": (C.c_int, [_vp, _vp, _vp]),
     "catan_step_sample": (C.c_int, [_vp, _vp, _vp]),
     "catan_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

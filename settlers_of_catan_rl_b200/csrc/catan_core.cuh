@@ -1194,12 +1194,13 @@ CATAN_FN_NOINLINE void step_finish(Ctx& cx, float* reward_out, uint8_t* info_out
     info.w[0] = static_cast<uint32_t>(done) | (static_cast<uint32_t>(g.winner) << 8) |
                 (static_cast<uint32_t>(static_cast<uint8_t>(g.vp[0])) << 16) | (static_cast<uint32_t>(static_cast<uint8_t>(g.vp[1])) << 24);
     uint32_t reset_flag = 0;
+    const uint32_t actor_before_reset = static_cast<uint32_t>(current_actor(g));   // game_manager.py:99 reads it before env.reset()
     const uint32_t vp23 = static_cast<uint32_t>(static_cast<uint8_t>(g.vp[2])) | (static_cast<uint32_t>(static_cast<uint8_t>(g.vp[3])) << 8);
     if (done && cx.cfg->auto_reset) { reset_game(cx); reset_flag = 1; }
     info.w[1] = vp23 | (static_cast<uint32_t>(current_actor(g)) << 16) | (static_cast<uint32_t>(ws.acted_pid) << 24);
     info.w[2] = static_cast<uint32_t>(ws.act_type) | (static_cast<uint32_t>(ws.roll_info) << 8) |
                 (static_cast<uint32_t>(err) << 16) | (reset_flag << 24);
-    info.w[3] = 0;
+    info.w[3] = actor_before_reset;
     ws.done = static_cast<uint8_t>(done);
     *reinterpret_cast<F4*>(reward_out) = rew;
     *reinterpret_cast<V16*>(info_out) = info;

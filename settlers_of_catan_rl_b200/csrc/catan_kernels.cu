@@ -51,7 +51,7 @@ struct EnvParams {
   float* reward;
   uint8_t* info;
   uint32_t* err_flags;
-  const uint8_t* reset_mask;   // MODE_RESET: nullptr = all envs
+  const uint8_t* reset_mask;   // MODE_RESET / MODE_STEP: envs whose byte is 0 are left untouched; nullptr = all envs
   int range_first, range_count;   // env range this launch covers
   unsigned int* ticket;           // device-wide batch ticket counter (never reset)
   unsigned int ticket_base;       // value of *ticket when this launch starts
@@ -67,7 +67,7 @@ struct alignas(16) BlockSmem {
   int32_t lp_counter, batch, pad_[2];
   int32_t lp_best[kMaxJobs];   // block-cooperative longest-road search: result per job
   uint8_t est_list[kBatch], lr_list[kBatch], shrunk_list[kBatch];
-  uint8_t skip[kBatch];        // MODE_RESET with a mask: games left untouched
+  uint8_t skip[kBatch];        // games of the batch the env mask excludes: left untouched
 };
 static_assert(kBatch <= 4 * kWarps, "scalar phases map the games of a batch onto lanes 0..3 of the 32 warps");
 // the longest-road search borrows the whole staging area: 1024 path stacks, then kMaxJobs adjacency tables
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
         const int32_t* a = P.actions + static_cast<size_t>(base) * CATAN_ACTION_WORDS;
         for (int i = tid; i < nb * CATAN_ACTION_WORDS; i += kThreads) S.ws[i / CATAN_ACTION_WORDS].action[i % CATAN_ACTION_WORDS] = a[i];
       }
-      if (MODE == MODE_RESET) for (int i = tid; i < nb; i += kThreads) S.skip[i] = P.reset_mask != nullptr && P.reset_mask[base + i] == 0;
+      for (int i = tid; i < nb; i += kThreads) S.skip[i] = MODE != MODE_REFRESH && P.reset_mask != nullptr && P.reset_mask[base + i] == 0;
       if (tid == 0) { S.n_est = 0; S.n_lr = 0; S.n_shrunk = 0; }
     }
     __syncthreads();
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
       // scalar phases: game gi of the batch is handled by lane (gi / 32) of warp (gi % 32), so all 32 warps
       // are busy and each warp instruction serves up to four games
       const int sgi = warp + kWarps * lane;
-      const bool scalar_owner = lane < 4 && sgi < nb;
+      const bool scalar_owner = lane < 4 && sgi < nb && !S.skip[sgi];
       // ---- phase 1: translate + validate
       // ---- phase 2: scalar part of apply_action; queue the lane-parallel follow-ups (same owner thread: no barrier)
       if (scalar_owner) {
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
       CATAN_PROF(cx, PH_FINISH);
     } else {
       const int gi = warp + kWarps * lane;
-      if (lane < 4 && gi < nb && !(MODE == MODE_RESET && S.skip[gi])) {
+      if (lane < 4 && gi < nb && !S.skip[gi]) {
         CATAN_BIND(gi);
         if (MODE == MODE_RESET) { reset_game(cx); cx.g->episode_steps = 0; }
         else compute_seats(cx);
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
     }
     // ---- phase 7: legal-action masks (+ the next random-legal action), staged row -> TMA bulk store
     for (int gi = warp; gi < nb; gi += kWarps) {
-      if (MODE == MODE_RESET && S.skip[gi]) continue;
+      if (S.skip[gi]) continue;
       CATAN_BIND(gi);
       if (stage_busy) stage_reuse_wait(lane);
       encode_masks(cx);
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
     CATAN_PROF(cx, PH_MASKS);
     // ---- phase 8: packed observation, staged row -> TMA bulk store
     for (int gi = warp; gi < nb; gi += kWarps) {
-      if (MODE == MODE_RESET && S.skip[gi]) continue;
+      if (S.skip[gi]) continue;
       CATAN_BIND(gi);
       if (stage_busy) stage_reuse_wait(lane);
       encode_obs(cx);
@@ -476,12 +476,15 @@ int catan_reset(catan_env_t* env, const uint8_t* reset_mask_dev, void* stream) {
   return launch_env<catanb::MODE_RESET, false>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
 }
 
-int catan_step(catan_env_t* env, const int32_t* actions_dev, void* stream) {
+int catan_step(catan_env_t* env, const int32_t* actions_dev, void* stream) { return catan_step_masked(env, actions_dev, nullptr, stream); }
+
+int catan_step_masked(catan_env_t* env, const int32_t* actions_dev, const uint8_t* step_mask_dev, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_dev) return fail("actions_dev is null");
   if (device_guard(env)) return -1;
   EnvParams P = make_params(env);
   P.actions = actions_dev;
+  P.reset_mask = step_mask_dev;
   return launch_env<catanb::MODE_STEP, false>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
 }
 

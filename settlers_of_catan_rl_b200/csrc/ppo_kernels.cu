@@ -139,3 +139,136 @@ static int ppo_fail(cudaError_t e, const char* what) {
   catan_set_last_error(m.c_str());
   return -1;
 }
+
+// =================================================================================================
+// rollout collector: the per-env state machine of GamesAndPoliciesManager.gather_rollouts
+// (RL/ppo/game_manager.py:69-140) and the buffer layout of BatchProcessor.process_rollouts
+// (RL/ppo/process_batch.py:37-104), one warp per env per tick.
+// =================================================================================================
+namespace catanb {
+
+struct RolloutArgs {
+  catan_rollout_t r;
+  const uint8_t* env_obs;      // [N][OBS_STRIDE]   post-step observation (the env's bound buffer)
+  const uint8_t* env_masks;    // [N][MASK_STRIDE]
+  const float* env_reward;     // [N][4]
+  const uint8_t* env_info;     // [N][INFO_STRIDE]
+  const int32_t* actions;      // [N][ACTION_WORDS] the actions applied this tick
+  const float* logp;           // [N]
+  const uint8_t* stepped;      // [N] envs that were stepped this tick (nullptr = all)
+  int begin;                   // 1: (re)start of a rollout (GamesAndPoliciesManager.reset / _after_rollouts), no step happened
+  int fresh;                   // with begin: 1 = after env.reset() (manager.reset), 0 = carry the last observation over
+};
+
+__device__ __forceinline__ void copy_row16(uint8_t* dst, const uint8_t* src, int bytes, int lane) {
+  const int4* s = reinterpret_cast<const int4*>(src);
+  int4* d = reinterpret_cast<int4*>(dst);
+  for (int i = lane; i < bytes / 16; i += 32) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(128) rollout_store_kernel(const RolloutArgs A) {
+  const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const catan_rollout_t& R = A.r;
+  if (e >= R.N) return;
+  const int T = R.T, N = R.N;
+  int32_t* cur = R.cursors + static_cast<size_t>(e) * 4;          // n_obs, n_act, n_rew, n_tm
+  float* acc = R.acc + static_cast<size_t>(e) * 4;
+  const int active = R.active_pid[e];
+  int n_obs = cur[0], n_act = cur[1], n_rew = cur[2], n_tm = cur[3];
+  int flags = R.flags[e];                                          // bit 0: done_since_prev_turn, bit 1: last terminal mask
+  const uint8_t* info = A.env_info + static_cast<size_t>(e) * CATAN_INFO_STRIDE;
+  __syncwarp();
+  bool store_obs = false;
+  if (A.begin) {
+    if (A.fresh) {                                                 // game_manager.py:34-56
+      n_obs = 0; n_act = 0; n_rew = 0; n_tm = 0;
+      if (lane == 0) R.tmasks[e] = 1.0f;
+      n_tm = 1; flags |= 2;
+      store_obs = info[CATAN_INFO_ACTOR] == active;
+    } else {                                                       // _after_rollouts, game_manager.py:142-150
+      if (n_obs > 0) copy_row16(R.obs + static_cast<size_t>(e) * CATAN_OBS_STRIDE,
+                                R.obs + (static_cast<size_t>(n_obs - 1) * N + e) * CATAN_OBS_STRIDE, CATAN_OBS_STRIDE, lane);
+      // the env has been frozen since that observation was stored, so its bound mask row is still the one that goes with it
+      if (n_obs > 0) copy_row16(R.masks + static_cast<size_t>(e) * CATAN_MASK_STRIDE, A.env_masks + static_cast<size_t>(e) * CATAN_MASK_STRIDE,
+                                CATAN_MASK_STRIDE, lane);
+      if (lane == 0 && n_tm > 0) R.tmasks[e] = (flags & 2) ? 1.0f : 0.0f;   // terminal_masks[-1], even when it lay beyond the buffer
+      n_obs = n_obs > 0 ? 1 : 0; n_tm = n_tm > 0 ? 1 : 0; n_act = 0; n_rew = 0;
+    }
+    if (lane < 4) acc[lane] = 0.0f;                                // game_manager.py:76-77: per-call locals
+    flags &= 2;                                                    // bit 1 = value of the last terminal mask, kept
+  } else if ((A.stepped == nullptr || A.stepped[e]) && n_obs < T + 1) {
+    const int pg = info[CATAN_INFO_ACTED], n_pg_pre = info[CATAN_INFO_ACTOR_PRE], n_pg = info[CATAN_INFO_ACTOR];
+    const bool done = info[CATAN_INFO_DONE] != 0;
+    float a_acc = acc[active - 1] + A.env_reward[static_cast<size_t>(e) * 4 + active - 1];     // :94-95
+    __syncwarp();
+    if (lane < 4) acc[lane] += A.env_reward[static_cast<size_t>(e) * 4 + lane];
+    bool reward_updated = false;
+    // The reference's lists may grow past what process_rollouts reads (T rows, T+1 for obs / terminal masks): e.g. the
+    // terminal-mask list leads by one when the first observation of a rollout was not the active seat's.  Entries
+    // beyond the buffers are counted in the cursors but not stored.
+    if (pg == active) {                                            // :102-105
+      if (n_act < T && lane < CATAN_ACTION_WORDS) R.actions[(static_cast<size_t>(n_act) * N + e) * CATAN_ACTION_WORDS + lane] =
+          A.actions[static_cast<size_t>(e) * CATAN_ACTION_WORDS + lane];
+      if (n_act < T && lane == 0) R.logp[static_cast<size_t>(n_act) * N + e] = A.logp[e];
+      n_act += 1;
+    }
+    if (n_pg_pre == active && n_act > 0 && !(flags & 1)) {         // :106-110
+      if (n_rew < T && lane == 0) R.rewards[static_cast<size_t>(n_rew) * N + e] = a_acc;
+      n_rew += 1; a_acc = 0.0f; reward_updated = true;
+      __syncwarp();
+      if (lane == 0) acc[active - 1] = 0.0f;
+    }
+    if (done) {                                                    // :112-124
+      if (n_tm <= T && lane == 0) R.tmasks[static_cast<size_t>(n_tm) * N + e] = 0.0f;
+      n_tm += 1;
+      flags &= ~3;
+      if (!reward_updated) {
+        if (n_rew < T && lane == 0) R.rewards[static_cast<size_t>(n_rew) * N + e] = a_acc;
+        n_rew += 1;
+      }
+      __syncwarp();
+      if (lane < 4) acc[lane] = 0.0f;
+    }
+    if (n_pg == active) {                                          // :128-133
+      if (!done && !(flags & 1)) {
+        if (n_tm <= T && lane == 0) R.tmasks[static_cast<size_t>(n_tm) * N + e] = 1.0f;
+        n_tm += 1; flags |= 2;
+      }
+      flags &= ~1;
+      store_obs = true;
+    } else if (done) {
+      flags |= 1;                                                  // :134-136
+    }
+  }
+  if (store_obs) {
+    copy_row16(R.obs + (static_cast<size_t>(n_obs) * N + e) * CATAN_OBS_STRIDE, A.env_obs + static_cast<size_t>(e) * CATAN_OBS_STRIDE,
+               CATAN_OBS_STRIDE, lane);
+    if (n_obs < T)   // the masks of the (T+1)-th observation are never used (game_manager.py:78: the loop ends first)
+      copy_row16(R.masks + (static_cast<size_t>(n_obs) * N + e) * CATAN_MASK_STRIDE, A.env_masks + static_cast<size_t>(e) * CATAN_MASK_STRIDE,
+                 CATAN_MASK_STRIDE, lane);
+    n_obs += 1;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    cur[0] = n_obs; cur[1] = n_act; cur[2] = n_rew; cur[3] = n_tm;
+    R.flags[e] = static_cast<uint8_t>(flags);
+    if (R.collecting) R.collecting[e] = n_obs < T + 1;             // step mask of the next tick
+  }
+}
+
+}  // namespace catanb
+
+extern "C" int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t* env_obs_dev, const uint8_t* env_masks_dev,
+                                   const float* env_reward_dev, const uint8_t* env_info_dev, const int32_t* actions_dev,
+                                   const float* logp_dev, const uint8_t* stepped_dev, int begin, int fresh, void* stream) {
+  if (!rollout || !env_obs_dev || !env_masks_dev || !env_info_dev || rollout->N <= 0 || rollout->T <= 0)
+    return ppo_fail(cudaErrorInvalidValue, "catan_rollout_store: bad argument");
+  if (!begin && (!env_reward_dev || !actions_dev || !logp_dev)) return ppo_fail(cudaErrorInvalidValue, "catan_rollout_store: bad argument");
+  catanb::RolloutArgs A;
+  A.r = *rollout;
+  A.env_obs = env_obs_dev; A.env_masks = env_masks_dev; A.env_reward = env_reward_dev; A.env_info = env_info_dev;
+  A.actions = actions_dev; A.logp = logp_dev; A.stepped = stepped_dev; A.begin = begin; A.fresh = fresh;
+  catanb::rollout_store_kernel<<<(rollout->N + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : ppo_fail(e, "catan_rollout_store launch");
+}

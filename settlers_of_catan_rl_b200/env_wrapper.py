@@ -87,7 +87,14 @@ class EnvWrapper(object):
         self._game = None
         self.winner = None
         self.curr_vps = {PlayerId.White: 0, PlayerId.Red: 0, PlayerId.Blue: 0, PlayerId.Orange: 0}
-        self.reset()
+        # The reference's constructor already holds a freshly reset Game (game.py:24).  Here the first game is dealt by
+        # the first reset() so that construction does not consume the (seed, env_id) stream; anything that needs a
+        # game before that triggers it.
+        self._started = False
+
+    def _ensure_started(self):
+        if not self._started:
+            self.reset()
 
     # ---- attributes the managers touch
     @property
@@ -100,12 +107,14 @@ class EnvWrapper(object):
 
     @property
     def game(self):
+        self._ensure_started()
         if self._game is None:
             self._game = _GameView(self._vec.export_state().view(L.STATE_DTYPE)[0, 0])
         return self._game
 
     # ---- EnvWrapper API
     def reset(self):
+        self._started = True
         self._vec.reset_host(self._obs, self._masks, self._info)
         self._game = None
         self.winner = None
@@ -113,6 +122,7 @@ class EnvWrapper(object):
         return self._obs_dict()
 
     def step(self, action):
+        self._ensure_started()
         a = self.pack_action(action)
         self._vec.step_host(a, self._obs, self._masks, self._reward, self._info)
         self._game = None
@@ -128,13 +138,16 @@ class EnvWrapper(object):
         return self._obs_dict(), reward, done, {"log": log}
 
     def get_action_masks(self):
+        self._ensure_started()
         row = self._masks[0]
         return [row[off:off + int(np.prod(shape))].reshape(shape).astype(np.float64) for off, shape in L.MASK_HEADS]
 
     def save_state(self):
+        self._ensure_started()
         return {"state": self._vec.export_state()[0].copy(), "vps": dict(self.curr_vps), "winner": self.winner}
 
     def restore_state(self, state):
+        self._started = True
         self._vec.import_state(state["state"][None, :])
         self._obs[:] = self._vec.obs.cpu().numpy()
         self._masks[:] = self._vec.masks.cpu().numpy()

@@ -83,7 +83,7 @@ MASK_STRIDE = 336
 
 # ---- per-step info row (uint8)
 INFO_DONE, INFO_WINNER, INFO_FINAL_VP, INFO_ACTOR, INFO_ACTED = 0, 1, 2, 6, 7
-INFO_ACT_TYPE, INFO_ROLL, INFO_ERR, INFO_RESET = 8, 9, 10, 11
+INFO_ACT_TYPE, INFO_ROLL, INFO_ERR, INFO_RESET, INFO_ACTOR_PRE = 8, 9, 10, 11, 12
 INFO_STRIDE = 16
 
 # ---- canonical state (int16 fields, C order) — mirrors ``catan_state_t``

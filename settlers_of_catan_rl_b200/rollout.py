@@ -66,3 +66,81 @@ def normalise_advantages(advantages: torch.Tensor, eps: float = 1e-5, group=None
             dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=None if group is True else group)
         _lib.check(lib.catan_adv_apply(_p(advantages), n, _p(stats), float(eps), _stream(advantages)))
     return advantages
+
+
+class RolloutStorage:
+    """Device-resident rollout buffer with the reference's record semantics.
+
+    Replaces the Python lists of ``GamesAndPoliciesManager`` (RL/ppo/game_manager.py:34-150) and their stacking
+    in ``BatchProcessor.process_rollouts`` (RL/ppo/process_batch.py:37-104): per env only the decisions of one
+    "active" seat are recorded; rewards are summed between that seat's decisions; ``tmasks[t] == 0`` marks an
+    observation that is the first of a new game.  Buffers are time-major ``[T(+1), N, ...]`` CUDA tensors written
+    by ``catan_rollout_store`` (one launch per tick), so they feed ``gae`` / the minibatch gather directly.
+    """
+
+    def __init__(self, env, num_steps: int, active_pid: Optional[torch.Tensor] = None):
+        from . import layout as L
+        self.env, self.T, self.N = env, int(num_steps), env.n_envs
+        dev = env.device
+        T, N = self.T, self.N
+        self.obs = torch.zeros((T + 1, N, L.OBS_STRIDE), dtype=torch.uint8, device=dev)
+        self.masks = torch.zeros((T, N, L.MASK_STRIDE), dtype=torch.uint8, device=dev)
+        self.actions = torch.zeros((T, N, L.ACTION_WORDS), dtype=torch.int32, device=dev)
+        self.logp = torch.zeros((T, N), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros((T, N), dtype=torch.float32, device=dev)
+        self.tmasks = torch.ones((T + 1, N), dtype=torch.float32, device=dev)
+        self.cursors = torch.zeros((N, 4), dtype=torch.int32, device=dev)
+        self.acc = torch.zeros((N, 4), dtype=torch.float32, device=dev)
+        self.flags = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.collecting = torch.ones(N, dtype=torch.uint8, device=dev)
+        if active_pid is None:   # game_manager.py:24-27: a random seat per env is the recorded one
+            active_pid = torch.randint(1, 5, (N,), device=dev, dtype=torch.uint8)
+        self.active_pid = active_pid.to(device=dev, dtype=torch.uint8).contiguous()
+        self._c = _lib.CatanRollout(
+            obs=self.obs.data_ptr(), masks=self.masks.data_ptr(), actions=self.actions.data_ptr(), logp=self.logp.data_ptr(),
+            rewards=self.rewards.data_ptr(), tmasks=self.tmasks.data_ptr(), cursors=self.cursors.data_ptr(),
+            acc=self.acc.data_ptr(), flags=self.flags.data_ptr(), active_pid=self.active_pid.data_ptr(),
+            collecting=self.collecting.data_ptr(), T=T, N=N)
+
+    def _call(self, actions, logp, stepped, begin, fresh):
+        e = self.env
+        z = C.c_void_p(0)
+        with torch.cuda.device(e.device):
+            _lib.check(_lib.load().catan_rollout_store(
+                C.byref(self._c), _p(e.obs), _p(e.masks), _p(e.reward), _p(e.info),
+                z if actions is None else _p(actions), z if logp is None else _p(logp), z if stepped is None else _p(stepped),
+                int(begin), int(fresh), _stream(e.obs)))
+
+    def begin(self, fresh: bool) -> None:
+        """fresh=True right after ``env.reset()`` (manager.reset); False between rollouts (_after_rollouts)."""
+        self._call(None, None, None, True, fresh)
+
+    def record(self, actions: torch.Tensor, logp: torch.Tensor, stepped: Optional[torch.Tensor] = None) -> None:
+        """call once per tick after ``env.step``; ``stepped`` = the step mask used for that tick (None = all)."""
+        assert actions.dtype == torch.int32 and logp.dtype == torch.float32 and actions.is_contiguous() and logp.is_contiguous()
+        self._call(actions, logp, stepped, False, False)
+
+    def finished(self) -> bool:
+        return not bool(self.collecting.any().item())
+
+    def collect(self, policy_fn, max_ticks: int = 1_000_000) -> int:
+        """Run ticks until every env holds T+1 observations.  ``policy_fn(env) -> (actions int32 [N,20], logp fp32 [N])``.
+        Envs that filled their quota are frozen with the step mask (game_manager.py:78).  Returns the tick count."""
+        ticks = 0
+        stepped = torch.empty_like(self.collecting)
+        while ticks < max_ticks:
+            if ticks % 8 == 0 and self.finished():
+                break
+            actions, logp = policy_fn(self.env)
+            stepped.copy_(self.collecting)
+            self.env.step(actions, step_mask=stepped)
+            self.record(actions, logp, stepped)
+            ticks += 1
+        return ticks
+
+    def compute_returns(self, values: torch.Tensor, gamma: float = 0.999, gae_lambda: float = 0.95, normalise: bool = True, group=None):
+        """values: [T+1, N] fp32 (denormalised).  Returns (returns, advantages) — process_batch.py:134-142."""
+        returns, adv = gae(self.rewards, values.contiguous(), self.tmasks, gamma, gae_lambda)
+        if normalise:
+            normalise_advantages(adv, group=group)
+        return returns, adv

@@ -68,11 +68,14 @@ class VecCatanEnv:
         self.kernel_launches += 1
         return self.obs
 
-    def step(self, actions: torch.Tensor):
-        """EnvWrapper.step + get_action_masks for all envs.  ``actions``: int32 CUDA tensor [N, 20]."""
+    def step(self, actions: torch.Tensor, step_mask: Optional[torch.Tensor] = None):
+        """EnvWrapper.step + get_action_masks for all envs.  ``actions``: int32 CUDA tensor [N, 20].
+        ``step_mask`` (uint8 [N], optional): envs with a zero byte are frozen (state and outputs untouched)."""
         assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous()
         assert actions.shape == (self.n_envs, L.ACTION_WORDS)
-        _lib.check(self.lib.catan_step(self._h, _ptr(actions), self._stream()))
+        if step_mask is not None:
+            assert step_mask.dtype == torch.uint8 and step_mask.is_cuda and step_mask.numel() == self.n_envs
+        _lib.check(self.lib.catan_step_masked(self._h, _ptr(actions), _ptr(step_mask), self._stream()))
         self.kernel_launches += 1
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
