@@ -990,43 +990,131 @@ CATAN_FN void lp_build_adj(const GameRec& g, const Topo& T, int pid, uint64_t* a
   }
 }
 
-// Cooperative search over n_jobs graphs (adj[job][54]).  Every calling lane claims work items
-// (job, start corner, 1st branch, 2nd branch) from *counter until they run out and walks its subtree
-// with the push/pop state machine; the longest depth seen per job is max-ed into best[job].
-// path: byte stacks, element (depth, lane) at path[depth * path_stride + path_lane].
-// Any number of warps may call this concurrently on the same (adj, counter, best); the caller
-// synchronises before reading best[].
-CATAN_FN_NOINLINE void lp_search(const uint64_t* adj_all, int n_jobs, int32_t* counter, int32_t* best, uint8_t* path,
-                                 int path_stride, int path_lane) {
-  const int total = n_jobs * CATAN_LP_ITEMS;
+// Cooperative search over n_jobs graphs (adj[job][54]), in ROUNDS of at most `budget` loop iterations.
+// A unit of work is a DFS state: in round 0 the 324 static prefixes (start corner, 1st branch, 2nd branch) per job
+// claimed from *counter, in later rounds the tasks queued in `ring`.  Every lane walks its unit with the push/pop
+// state machine; the deepest level seen per job is max-ed into best[job].  When the budget of a round is used up,
+// every lane that is still inside a subtree (a) donates the untried siblings of the shallowest open level of its
+// path as fresh tasks (the biggest pieces of what is left) and (b) parks the rest of its state as a RESUME task;
+// the next round hands all of these to whatever lanes are free.  Parallelism therefore grows geometrically round
+// by round and a dense road network (10^5 path visits) is spread over the whole block instead of pinning a lane.
+// path: byte stacks, element (depth, lane) at path[depth * path_stride + path_lane]; bit 7 of a stack byte marks a
+// level whose remaining siblings were donated.  ctl[0] = claim counter, ctl[1] = ring reservation cursor (absolute,
+// monotonic), ctl[2] = first absolute slot that is NOT valid this round, ctl[3] = absolute slot of this round's first task.
+// Any number of warps may call this concurrently on the same arguments; the caller synchronises between rounds.
+struct alignas(8) LpTask {
+  uint8_t job, depth, base, pad_[5];
+  uint64_t above;            // untried-candidate filter at the deepest level (resume tasks); ~0 for fresh tasks
+  uint8_t path[56];          // path[0..depth], flag bits included
+};
+static_assert(sizeof(LpTask) == 72, "LpTask layout");
+
+CATAN_FN_NOINLINE void lp_round(const uint64_t* adj_all, int n_jobs, bool first_round, int32_t* ctl, int32_t* best,
+                                uint8_t* path, int path_stride, int path_lane, LpTask* ring, int ring_cap, int n_in, int budget) {
+  const int total = first_round ? n_jobs * CATAN_LP_ITEMS : n_in;
+  const int round_base = ctl[3];
   const uint64_t* adj = adj_all;
-  int job = 0, lbest = 0, node = 0, depth = 0;
+  int job = 0, lbest = 0, node = 0, depth = 0, base = 0, iters = 0;
   uint64_t visited = 0, above = ~0ull;
   bool active = false, exhausted = false;
   for (;;) {
-    if (!active && !exhausted) {                                     // claim the next non-empty work item
+    if (!active && !exhausted) {                                     // claim the next non-empty unit
       for (;;) {
-        const int i = fetch_add_i32(counter);
+        const int i = fetch_add_i32(&ctl[0]);
         if (i >= total) { exhausted = true; break; }
-        const int nj = i / CATAN_LP_ITEMS, it = i - nj * CATAN_LP_ITEMS;
-        if (nj != job) { if (lbest) smax_i32(&best[job], lbest); job = nj; lbest = 0; adj = adj_all + nj * 54; }
-        const int v = it / 6, k1 = (it % 6) >> 1, k2 = it & 1;
-        const int t1 = kth_bit(adj[v], k1);
-        if (t1 < 0) continue;
-        const uint64_t c2 = adj[t1] & ~(1ull << v);
-        if (!c2) { if (k2 == 0 && lbest < 1) lbest = 1; continue; }
-        const int t2 = kth_bit(c2, k2);
-        if (t2 < 0) continue;
-        path[path_lane] = static_cast<uint8_t>(v);
-        path[path_stride + path_lane] = static_cast<uint8_t>(t1);
-        path[2 * path_stride + path_lane] = static_cast<uint8_t>(t2);
-        visited = (1ull << v) | (1ull << t1) | (1ull << t2);
-        depth = 2; node = t2; above = ~0ull; active = true;
-        if (lbest < 2) lbest = 2;
+        int nj;
+        if (first_round) {
+          nj = i / CATAN_LP_ITEMS;
+          const int it = i - nj * CATAN_LP_ITEMS;
+          if (nj != job) { if (lbest) smax_i32(&best[job], lbest); job = nj; lbest = 0; }
+          adj = adj_all + nj * 54;
+          const int v = it / 6, k1 = (it % 6) >> 1, k2 = it & 1;
+          const int t1 = kth_bit(adj[v], k1);
+          if (t1 < 0) continue;
+          const uint64_t c2 = adj[t1] & ~(1ull << v);
+          if (!c2) { if (k2 == 0 && lbest < 1) lbest = 1; continue; }
+          const int t2 = kth_bit(c2, k2);
+          if (t2 < 0) continue;
+          path[path_lane] = static_cast<uint8_t>(v);
+          path[path_stride + path_lane] = static_cast<uint8_t>(t1);
+          path[2 * path_stride + path_lane] = static_cast<uint8_t>(t2);
+          visited = (1ull << v) | (1ull << t1) | (1ull << t2);
+          depth = 2; base = 2; node = t2; above = ~0ull;
+        } else {
+          const LpTask& tk = ring[(round_base + i) % ring_cap];
+          nj = tk.job;
+          if (nj != job) { if (lbest) smax_i32(&best[job], lbest); job = nj; lbest = 0; }
+          adj = adj_all + nj * 54;
+          depth = tk.depth; base = tk.base; above = tk.above;
+          visited = 0;
+          for (int q = 0; q <= depth; ++q) {
+            const int raw = tk.path[q];
+            path[q * path_stride + path_lane] = static_cast<uint8_t>(raw);
+            visited |= 1ull << (raw & 63);
+          }
+          node = tk.path[depth] & 63;
+        }
+        active = true;
+        if (lbest < depth) lbest = depth;
         break;
       }
     }
     if (!wany(active)) break;
+    if (++iters >= budget) {                                         // (warp-uniform) budget used up: queue what is left
+      iters = 0;
+      if (active) {
+        // shallowest open level q in [base, depth] that still has untried siblings -> they become fresh tasks
+        int dq = -1;
+        uint64_t dc = 0, vis = 0;
+        for (int q = 0; q <= depth; ++q) {
+          const int raw = path[q * path_stride + path_lane], u = raw & 63;
+          vis |= 1ull << u;
+          if (q < base || (raw & 128)) continue;
+          uint64_t c = adj[u] & ~vis;
+          c &= q == depth ? above : ~((2ull << (path[(q + 1) * path_stride + path_lane] & 63)) - 1ull);
+          if (c) { dq = q; dc = c; break; }
+        }
+        int need = 1;                                                // the resume task
+        for (uint64_t t = dc; t; t &= t - 1) ++need;
+        // Reserve `need` consecutive ring slots.  A reservation that does not fit leaves a hole at the END of the
+        // round's list (every later reservation fails too); ctl[2] remembers where the valid part stops.
+#if CATAN_LANES == 32
+        const int slot = atomicAdd(&ctl[1], need);
+#else
+        const int slot = ctl[1]; ctl[1] += need;
+#endif
+        if (slot + need - round_base <= ring_cap) {
+          int w = slot;
+          for (uint64_t t = dc; t; t &= t - 1) {                     // fresh tasks: prefix path[0..dq] + one untried sibling
+            LpTask& tk = ring[w++ % ring_cap];
+            tk.job = static_cast<uint8_t>(job);
+            tk.depth = static_cast<uint8_t>(dq + 1);
+            tk.base = static_cast<uint8_t>(dq + 1);
+            tk.above = ~0ull;
+            for (int z = 0; z <= dq; ++z) tk.path[z] = path[z * path_stride + path_lane] & 63;
+            tk.path[dq + 1] = static_cast<uint8_t>(ctz64(t));
+          }
+          if (dq >= 0) {
+            path[dq * path_stride + path_lane] |= 128;              // those siblings are no longer this unit's business
+            if (dq == depth) above = 0;
+          }
+          LpTask& rk = ring[w % ring_cap];                           // resume task: the state machine's registers + stack
+          rk.job = static_cast<uint8_t>(job);
+          rk.depth = static_cast<uint8_t>(depth);
+          rk.base = static_cast<uint8_t>(base);
+          rk.above = above;
+          for (int z = 0; z <= depth; ++z) rk.path[z] = path[z * path_stride + path_lane];
+          active = false;
+        } else {
+#if CATAN_LANES == 32
+          atomicMin(&ctl[2], slot);                                  // ring full: keep the unit and carry on in this round
+#else
+          if (slot < ctl[2]) ctl[2] = slot;
+#endif
+        }
+      }
+      continue;
+    }
     if (active) {
       const uint64_t cand = adj[node] & ~visited & above;
       if (cand) {                                                    // push the lowest untried neighbour
@@ -1036,29 +1124,65 @@ CATAN_FN_NOINLINE void lp_search(const uint64_t* adj_all, int n_jobs, int32_t* c
         visited |= 1ull << t;
         node = t; above = ~0ull;
         if (depth > lbest) lbest = depth;
-      } else if (depth == 2) {
-        active = false;                                              // subtree of this work item exhausted
+      } else if (depth == base) {
+        active = false;                                              // unit exhausted
       } else {                                                       // pop; resume the parent above the popped child
         visited &= ~(1ull << node);
-        above = ~((2ull << node) - 1ull);
         --depth;
-        node = path[depth * path_stride + path_lane];
+        const int raw = path[depth * path_stride + path_lane];
+        above = (raw & 128) ? 0ull : ~((2ull << node) - 1ull);       // siblings of a donated level belong to other lanes
+        node = raw & 63;
       }
     }
   }
   if (lbest) smax_i32(&best[job], lbest);
 }
 
+// Round driver shared by the warp-local and the block-cooperative callers: `sync` is the barrier of the
+// participating threads, `leader` is true for exactly one of them.
+#define CATAN_LP_RUN(adj_, n_jobs_, ctl_, best_, path_, stride_, plane_, ring_, cap_, budget_, leader_, SYNC_, ROUNDS_)   \
+  do {                                                                                                                     \
+    int n_in_ = 0;                                                                                                         \
+    bool first_ = true;                                                                                                    \
+    SYNC_;                                                                                                                 \
+    if (leader_) { (ctl_)[1] = 0; (ctl_)[3] = 0; }                                                                         \
+    do {                                                                                                                   \
+      SYNC_;                                                                                                               \
+      if (leader_) { (ctl_)[0] = 0; (ctl_)[2] = 0x7fffffff; }                                                          \
+      SYNC_;                                                                                                               \
+      lp_round(adj_, n_jobs_, first_, ctl_, best_, path_, stride_, plane_, ring_, cap_, n_in_, budget_);                   \
+      SYNC_;                                                                                                               \
+      {                                                                                                                    \
+        const int base_ = (ctl_)[3] + n_in_;                          /* first task queued during this round */           \
+        const int end_ = (ctl_)[1] < (ctl_)[2] ? (ctl_)[1] : (ctl_)[2];                                                    \
+        n_in_ = end_ - base_;                                                                                              \
+        SYNC_;                                                                                                             \
+        if (leader_) { (ctl_)[3] = base_; (ctl_)[1] = end_; }                                                              \
+      }                                                                                                                    \
+      first_ = false;                                                                                                      \
+      ROUNDS_;                                                                                                             \
+    } while (n_in_ > 0);                                                                                                   \
+    SYNC_;                                                                                                                 \
+  } while (0)
+
 // warp-local longest path of one player (used by the host emulation and by callers without a block)  [W]
+// scratch: adj 432 | ctl[4] | path stacks | best | task ring of CATAN_LP_WARP_TASKS
+#define CATAN_LP_WARP_TASKS 96
+#undef CATAN_LP_SCRATCH_BYTES
+#define CATAN_LP_TASK_OFF ((CATAN_LP_PATH_OFF + 54 * CATAN_LANES + 8 + 7) & ~7)
+#define CATAN_LP_SCRATCH_BYTES (CATAN_LP_TASK_OFF + CATAN_LP_WARP_TASKS * 72)
+#ifndef CATAN_LP_BUDGET
+#define CATAN_LP_BUDGET 160
+#endif
 CATAN_FN int longest_path(Ctx& cx, int pid) {
   uint64_t* adj = reinterpret_cast<uint64_t*>(cx.scratch);
-  int32_t* counter = reinterpret_cast<int32_t*>(cx.scratch + CATAN_LP_ADJ_BYTES);
-  int32_t* best = counter + 1;
+  int32_t* ctl = reinterpret_cast<int32_t*>(cx.scratch + CATAN_LP_ADJ_BYTES);
+  int32_t* best = reinterpret_cast<int32_t*>(cx.scratch + CATAN_LP_TASK_OFF - 8);
+  LpTask* ring = reinterpret_cast<LpTask*>(cx.scratch + CATAN_LP_TASK_OFF);
   lp_build_adj(*cx.g, *cx.T, pid, adj, cx.lane);
-  if (cx.lane == 0) { *counter = 0; *best = 0; }
-  wsync();
-  lp_search(adj, 1, counter, best, cx.scratch + CATAN_LP_PATH_OFF, CATAN_LANES, cx.lane);
-  wsync();
+  if (cx.lane == 0) *best = 0;
+  CATAN_LP_RUN(adj, 1, ctl, best, cx.scratch + CATAN_LP_PATH_OFF, CATAN_LANES, cx.lane, ring, CATAN_LP_WARP_TASKS, CATAN_LP_BUDGET,
+               cx.lane == 0, wsync(), (void)0);
   const int r = *best;
   wsync();
   return r;

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -34,8 +35,10 @@ constexpr int kBlocksPerSM = 1;              // measured: 2 x 16 warps per SM is
 constexpr int kBatch = 112;                 // games per block iteration (3.5 per warp; 586 batches for 65 536 games)
 constexpr int kStageBytes = 2304;           // per-warp staging row: >= obs row, >= longest-road scratch
 constexpr int kSampleWarpsPerBlock = 4;     // stand-alone sampler kernel
+constexpr int kLpWarps = 32;                // warps that run the longest-road search (the rest wait at the phase barrier)
+constexpr int kLpBudget = 128;              // loop iterations per round before unfinished subtrees are re-queued
 constexpr int kMaxJobs = 39;                // longest-road graphs searched per cooperative pass (13 games x 3 when re-measuring)
-static_assert(kStageBytes >= CATAN_OBS_STRIDE && kStageBytes >= CATAN_LP_SCRATCH_BYTES && kStageBytes % 16 == 0, "staging row too small");
+static_assert(kStageBytes >= CATAN_OBS_STRIDE && kStageBytes % 16 == 0, "staging row too small");
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
@@ -53,9 +56,12 @@ struct EnvParams {
   uint32_t* err_flags;
   const uint8_t* reset_mask;   // MODE_RESET / MODE_STEP: envs whose byte is 0 are left untouched; nullptr = all envs
   int range_first, range_count;   // env range this launch covers
+  LpTask* lp_ring;                // [gridDim.x][kLpRingTasks] queue of re-split longest-road subtrees
   unsigned int* ticket;           // device-wide batch ticket counter (never reset)
   unsigned int ticket_base;       // value of *ticket when this launch starts
   unsigned long long* prof;    // profiling build only
+  int lp_budget;               // loop iterations per search round (default kLpBudget; CATAN_LP_BUDGET overrides for tuning)
+  int debug_flags;             // timing experiments only (CATAN_DEBUG_FLAGS): 1 = skip longest-road search, 2 = skip obs encode, 4 = skip masks
 };
 
 struct alignas(16) BlockSmem {
@@ -66,13 +72,20 @@ struct alignas(16) BlockSmem {
   int32_t n_est, n_lr, n_shrunk, pad0_;
   int32_t lp_counter, batch, pad_[2];
   int32_t lp_best[kMaxJobs];   // block-cooperative longest-road search: result per job
+  int32_t lp_ctl[4];           // lp_round control words: claim counter, ring cursor, ring limit, ring base
   uint8_t est_list[kBatch], lr_list[kBatch], shrunk_list[kBatch];
   uint8_t skip[kBatch];        // games of the batch the env mask excludes: left untouched
 };
 static_assert(kBatch <= 4 * kWarps, "scalar phases map the games of a batch onto lanes 0..3 of the 32 warps");
 // the longest-road search borrows the whole staging area: 1024 path stacks, then kMaxJobs adjacency tables
-constexpr int kLpPathBytes = 54 * kThreads;
-static_assert(kLpPathBytes + kMaxJobs * CATAN_LP_ADJ_BYTES <= kWarps * kStageBytes, "longest-road scratch does not fit the staging area");
+// the search borrows the staging area: path stacks of the kLpWarps searching warps | adjacency tables.  The queue of
+// re-split subtrees lives in a per-block ring in global memory (L2-resident, touched only when a unit is parked or
+// resumed): a shared-memory ring was too small -- once it filled up, lanes could not park and one dense network again
+// pinned a lane for milliseconds (profiles/r1_notes.md).
+constexpr int kLpPathBytes = 54 * kLpWarps * 32;
+constexpr int kLpAdjBytes = kMaxJobs * CATAN_LP_ADJ_BYTES;
+constexpr int kLpRingTasks = 2048;
+static_assert(kLpPathBytes % 8 == 0 && kLpPathBytes + kLpAdjBytes <= kWarps * kStageBytes, "longest-road scratch does not fit the staging area");
 static_assert(sizeof(BlockSmem) * kBlocksPerSM <= 227 * 1024, "block shared memory exceeds what kBlocksPerSM blocks can get on one SM");
 
 // ---- TMA 1-D bulk store helpers (SASS: UBLKCP) ---------------------------------------------------
@@ -173,12 +186,15 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
       }
       __syncthreads();
       CATAN_PROF(cx, PH_EST);
+      int lp_rounds_total = 0;
       // ---- phase 5: longest road (game.py:843-919), searched by the WHOLE block: the work items of every
-      // queued game go into one pool that all 1024 lanes drain, so one dense road network cannot stall the SM
+      // queued game go into one pool that the searching warps drain in rounds, so one dense road network cannot stall the SM
       {
         uint8_t* lp_paths = &S.stage[0][0];
         uint64_t* lp_adj = reinterpret_cast<uint64_t*>(&S.stage[0][0] + kLpPathBytes);
-        const int n_lr = S.n_lr;
+        LpTask* lp_ring = P.lp_ring + static_cast<size_t>(blockIdx.x) * kLpRingTasks;
+        const int n_lr = (P.debug_flags & 1) ? 0 : S.n_lr;
+        int lp_rounds = 0;
         for (int c0 = 0; c0 < n_lr; c0 += kMaxJobs) {                // pass A: the player whose road changed
           const int nj = min(kMaxJobs, n_lr - c0);
           for (int j = warp; j < nj; j += kWarps) {
@@ -186,10 +202,21 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
             lp_build_adj(S.recs[gi], S.topo, S.ws[gi].lr_pid, lp_adj + j * 54, lane);
           }
           if (tid < nj) S.lp_best[tid] = 0;
-          if (tid == 0) S.lp_counter = 0;
           __syncthreads();
-          lp_search(lp_adj, nj, &S.lp_counter, S.lp_best, lp_paths, kThreads, tid);
+#ifdef CATAN_PROFILE_PHASES
+          const long long t_search0 = clock64();
+#endif
+          if (warp < kLpWarps) {                                     // rounds: unfinished subtrees are re-queued and re-split
+            CATAN_LP_RUN(lp_adj, nj, S.lp_ctl, S.lp_best, lp_paths, kLpWarps * 32, tid, lp_ring, kLpRingTasks, P.lp_budget, tid == 0,
+                         asm volatile("bar.sync 1, %0;" :: "n"(kLpWarps * 32) : "memory"), ++lp_rounds);
+          }
           __syncthreads();
+#ifdef CATAN_PROFILE_PHASES
+          if (tid == 0) {   // pure search time per pass goes into the (otherwise unused) "dice" slot
+            const unsigned long long d = static_cast<unsigned long long>(clock64() - t_search0);
+            atomicAdd(&P.prof[PH_DICE * 4 + 0], d); atomicMax(&P.prof[PH_DICE * 4 + 1], d); atomicAdd(&P.prof[PH_DICE * 4 + 2], 1ull);
+          }
+#endif
           if (tid < nj) {
             const int gi = S.lr_list[c0 + tid];
             WarpScratch& ws = S.ws[gi];
@@ -210,10 +237,21 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
             lp_build_adj(S.recs[gi], S.topo, o, lp_adj + j * 54, lane);
           }
           if (tid < nj) S.lp_best[tid] = 0;
-          if (tid == 0) S.lp_counter = 0;
           __syncthreads();
-          lp_search(lp_adj, nj, &S.lp_counter, S.lp_best, lp_paths, kThreads, tid);
+#ifdef CATAN_PROFILE_PHASES
+          const long long t_search0 = clock64();
+#endif
+          if (warp < kLpWarps) {                                     // rounds: unfinished subtrees are re-queued and re-split
+            CATAN_LP_RUN(lp_adj, nj, S.lp_ctl, S.lp_best, lp_paths, kLpWarps * 32, tid, lp_ring, kLpRingTasks, P.lp_budget, tid == 0,
+                         asm volatile("bar.sync 1, %0;" :: "n"(kLpWarps * 32) : "memory"), ++lp_rounds);
+          }
           __syncthreads();
+#ifdef CATAN_PROFILE_PHASES
+          if (tid == 0) {   // pure search time per pass goes into the (otherwise unused) "dice" slot
+            const unsigned long long d = static_cast<unsigned long long>(clock64() - t_search0);
+            atomicAdd(&P.prof[PH_DICE * 4 + 0], d); atomicMax(&P.prof[PH_DICE * 4 + 1], d); atomicAdd(&P.prof[PH_DICE * 4 + 2], 1ull);
+          }
+#endif
           if (tid < nj) {
             const int gi = S.shrunk_list[c0 + tid / 3], pid = S.ws[gi].lr_pid;
             int o = tid % 3 + 1;
@@ -222,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
           }
           __syncthreads();
         }
+        lp_rounds_total = lp_rounds;
         if (tid < n_lr) {
           const int gi = S.lr_list[tid];
           const WarpScratch& ws = S.ws[gi];
@@ -229,6 +268,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
         }
       }
       __syncthreads();
+#ifdef CATAN_PROFILE_PHASES
+      if (tid == 0 && lp_rounds_total > 0) {   // search rounds per batch go into the (otherwise unused) "sample" slot
+        atomicAdd(&P.prof[PH_SAMPLE * 4 + 0], static_cast<unsigned long long>(lp_rounds_total));
+        atomicMax(&P.prof[PH_SAMPLE * 4 + 1], static_cast<unsigned long long>(lp_rounds_total));
+        atomicAdd(&P.prof[PH_SAMPLE * 4 + 2], 1ull);
+      }
+#endif
       CATAN_PROF(cx, PH_LROAD);
       // ---- phase 6: done / reward / info (+ auto-reset).  Game gi is finished by lane gi/32 of warp gi%32, the
       // warp that also encodes its masks and observation below, so a warp barrier is enough from here on.
@@ -258,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
       if (S.skip[gi]) continue;
       CATAN_BIND(gi);
       if (stage_busy) stage_reuse_wait(lane);
-      encode_masks(cx);
+      if (!(P.debug_flags & 4)) encode_masks(cx);
       if (SAMPLE) {
         const uint32_t decision = cx.g->decision_ctr;
         __syncwarp();
@@ -275,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
       if (S.skip[gi]) continue;
       CATAN_BIND(gi);
       if (stage_busy) stage_reuse_wait(lane);
-      encode_obs(cx);
+      if (!(P.debug_flags & 2)) encode_obs(cx);
       stage_to_global(P.obs + static_cast<size_t>(base + gi) * CATAN_OBS_STRIDE, cx.obs, CATAN_OBS_STRIDE, lane);
       stage_busy = true;
     }
@@ -328,6 +374,7 @@ struct catan_env {
   GameRec* recs = nullptr;
   uint32_t* err_flags = nullptr;
   int32_t* actions_stage = nullptr;   // device staging for catan_step_host
+  catanb::LpTask* lp_ring = nullptr;  // per-block task rings of the longest-road search
   unsigned int* ticket = nullptr;     // batch ticket counter of the persistent kernel
   unsigned int ticket_base = 0;
   uint8_t* obs = nullptr;
@@ -363,6 +410,8 @@ static EnvParams make_params(const catan_env* env) {
 #endif
   P.recs = env->recs; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
   P.obs = env->obs; P.masks = env->masks; P.reward = env->reward; P.info = env->info; P.err_flags = env->err_flags;
+  { const char* d = getenv("CATAN_DEBUG_FLAGS"); P.debug_flags = d ? atoi(d) : 0; }
+  { const char* d = getenv("CATAN_LP_BUDGET"); P.lp_budget = d && atoi(d) > 0 ? atoi(d) : catanb::kLpBudget; }
   return P;
 }
 
@@ -376,6 +425,7 @@ static int launch_env(catan_env* env, EnvParams P, int first, int count, cudaStr
   if (blocks > env->grid) blocks = env->grid;                       // persistent: one 1024-thread block per SM
   if (blocks < 1) blocks = 1;
   P.ticket = env->ticket;
+  P.lp_ring = env->lp_ring;
   P.ticket_base = env->ticket_base;
   env->ticket_base += static_cast<unsigned int>((count + catanb::kBatch - 1) / catanb::kBatch + blocks);   // claims this launch makes
   catanb::env_kernel<MODE, SAMPLE><<<blocks, catanb::kThreads, smem, stream>>>(P);
@@ -432,10 +482,11 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   if (e == cudaSuccess) e = cudaMalloc(&env->err_flags, sizeof(uint32_t) * static_cast<size_t>(n_envs));
   if (e == cudaSuccess) e = cudaMemset(env->err_flags, 0, sizeof(uint32_t) * static_cast<size_t>(n_envs));
   if (e == cudaSuccess) e = cudaMalloc(&env->actions_stage, sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(n_envs));
+  if (e == cudaSuccess) e = cudaMalloc(&env->lp_ring, sizeof(catanb::LpTask) * catanb::kLpRingTasks * static_cast<size_t>(env->grid));
   if (e == cudaSuccess) e = cudaMalloc(&env->ticket, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(env->ticket, 0, sizeof(unsigned int));
   if (e != cudaSuccess) {
-    cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage); cudaFree(env->ticket);
+    cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage); cudaFree(env->ticket); cudaFree(env->lp_ring);
     delete env;
     return cuda_fail(e, "cudaMalloc(game records)");
   }
@@ -445,7 +496,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
 
 int catan_destroy(catan_env_t* env) {
   if (!env) return 0;
-  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage); cudaFree(env->ticket);
+  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage); cudaFree(env->ticket); cudaFree(env->lp_ring);
   delete env;
   return 0;
 }

@@ -2,6 +2,9 @@
 // for the host with CATAN_LANES == 1 so the CPU test-suite can check the exact shipped logic against
 // the oracle and the golden fixtures without a GPU.  Never loaded by the product package.
 #define CATAN_HOST_EMU 1
+#ifndef CATAN_LP_BUDGET
+#define CATAN_LP_BUDGET 24   // tiny on purpose: the host emulation must exercise the subtree hand-off of lp_round
+#endif
 #include "../../settlers_of_catan_rl_b200/csrc/catan_core.cuh"
 
 #include <stdlib.h>
