@@ -956,7 +956,7 @@ CATAN_FN_NOINLINE void est_apply(Ctx& cx) {
 // Scratch (cx.scratch): adj[54] u64 | counter | path[54][LANES] bytes.
 // ------------------------------------------------------------------------------------------------
 #define CATAN_LP_ADJ_BYTES 432
-#define CATAN_LP_PATH_OFF 448
+#define CATAN_LP_PATH_OFF 464
 #define CATAN_LP_SCRATCH_BYTES (CATAN_LP_PATH_OFF + 54 * CATAN_LANES)
 #define CATAN_LP_ITEMS 324
 #if CATAN_LANES == 32
@@ -1138,35 +1138,34 @@ CATAN_FN_NOINLINE void lp_round(const uint64_t* adj_all, int n_jobs, bool first_
   if (lbest) smax_i32(&best[job], lbest);
 }
 
-// Round driver shared by the warp-local and the block-cooperative callers: `sync` is the barrier of the
-// participating threads, `leader` is true for exactly one of them.
+// Round driver shared by the warp-local and the block-cooperative callers: SYNC_ is the barrier of the participating
+// threads, leader_ is true for exactly one of them.  ctl_ holds TWO sets of four control words used by alternate
+// rounds, so that the leader can prepare the next round's set while the others still read this round's: two barriers
+// per round.  The caller must have made the adjacency tables and best_[] visible (one barrier) before entering.
 #define CATAN_LP_RUN(adj_, n_jobs_, ctl_, best_, path_, stride_, plane_, ring_, cap_, budget_, leader_, SYNC_, ROUNDS_)   \
   do {                                                                                                                     \
-    int n_in_ = 0;                                                                                                         \
+    int n_in_ = 0, set_ = 0;                                                                                               \
     bool first_ = true;                                                                                                    \
-    SYNC_;                                                                                                                 \
-    if (leader_) { (ctl_)[1] = 0; (ctl_)[3] = 0; }                                                                         \
+    if (leader_) { (ctl_)[0] = 0; (ctl_)[1] = 0; (ctl_)[2] = 0x7fffffff; (ctl_)[3] = 0; }                                  \
     do {                                                                                                                   \
       SYNC_;                                                                                                               \
-      if (leader_) { (ctl_)[0] = 0; (ctl_)[2] = 0x7fffffff; }                                                          \
-      SYNC_;                                                                                                               \
-      lp_round(adj_, n_jobs_, first_, ctl_, best_, path_, stride_, plane_, ring_, cap_, n_in_, budget_);                   \
+      int32_t* c_ = (ctl_) + 4 * set_;                                                                                     \
+      lp_round(adj_, n_jobs_, first_, c_, best_, path_, stride_, plane_, ring_, cap_, n_in_, budget_);                     \
       SYNC_;                                                                                                               \
       {                                                                                                                    \
-        const int base_ = (ctl_)[3] + n_in_;                          /* first task queued during this round */           \
-        const int end_ = (ctl_)[1] < (ctl_)[2] ? (ctl_)[1] : (ctl_)[2];                                                    \
+        const int base_ = c_[3] + n_in_;                              /* first task queued during this round */           \
+        const int end_ = c_[1] < c_[2] ? c_[1] : c_[2];                                                                    \
         n_in_ = end_ - base_;                                                                                              \
-        SYNC_;                                                                                                             \
-        if (leader_) { (ctl_)[3] = base_; (ctl_)[1] = end_; }                                                              \
+        set_ ^= 1;                                                                                                         \
+        if (leader_) { int32_t* d_ = (ctl_) + 4 * set_; d_[0] = 0; d_[1] = end_; d_[2] = 0x7fffffff; d_[3] = base_; }      \
       }                                                                                                                    \
       first_ = false;                                                                                                      \
       ROUNDS_;                                                                                                             \
     } while (n_in_ > 0);                                                                                                   \
-    SYNC_;                                                                                                                 \
   } while (0)
 
 // warp-local longest path of one player (used by the host emulation and by callers without a block)  [W]
-// scratch: adj 432 | ctl[4] | path stacks | best | task ring of CATAN_LP_WARP_TASKS
+// scratch: adj 432 | ctl[8] | path stacks | best | task ring of CATAN_LP_WARP_TASKS
 #define CATAN_LP_WARP_TASKS 96
 #undef CATAN_LP_SCRATCH_BYTES
 #define CATAN_LP_TASK_OFF ((CATAN_LP_PATH_OFF + 54 * CATAN_LANES + 8 + 7) & ~7)
@@ -1181,8 +1180,10 @@ CATAN_FN int longest_path(Ctx& cx, int pid) {
   LpTask* ring = reinterpret_cast<LpTask*>(cx.scratch + CATAN_LP_TASK_OFF);
   lp_build_adj(*cx.g, *cx.T, pid, adj, cx.lane);
   if (cx.lane == 0) *best = 0;
+  wsync();
   CATAN_LP_RUN(adj, 1, ctl, best, cx.scratch + CATAN_LP_PATH_OFF, CATAN_LANES, cx.lane, ring, CATAN_LP_WARP_TASKS, CATAN_LP_BUDGET,
                cx.lane == 0, wsync(), (void)0);
+  wsync();
   const int r = *best;
   wsync();
   return r;

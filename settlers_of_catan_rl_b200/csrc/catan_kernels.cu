@@ -32,7 +32,7 @@ __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 constexpr int kWarps = 32;
 constexpr int kThreads = kWarps * 32;
 constexpr int kBlocksPerSM = 1;              // measured: 2 x 16 warps per SM is 8% slower (profiles/r1_notes.md)
-constexpr int kBatch = 112;                 // games per block iteration (3.5 per warp; 586 batches for 65 536 games)
+constexpr int kBatch = 96;                  // games per block iteration: 3 per warp (measured: 64 / 96 / 112 / 128 within 3% of each other)
 constexpr int kStageBytes = 2304;           // per-warp staging row: >= obs row, >= longest-road scratch
 constexpr int kSampleWarpsPerBlock = 4;     // stand-alone sampler kernel
 constexpr int kLpWarps = 32;                // warps that run the longest-road search (the rest wait at the phase barrier)
@@ -72,7 +72,7 @@ struct alignas(16) BlockSmem {
   int32_t n_est, n_lr, n_shrunk, pad0_;
   int32_t lp_counter, batch, pad_[2];
   int32_t lp_best[kMaxJobs];   // block-cooperative longest-road search: result per job
-  int32_t lp_ctl[4];           // lp_round control words: claim counter, ring cursor, ring limit, ring base
+  int32_t lp_ctl[8];           // two sets of lp_round control words: claim counter, ring cursor, ring limit, ring base
   uint8_t est_list[kBatch], lr_list[kBatch], shrunk_list[kBatch];
   uint8_t skip[kBatch];        // games of the batch the env mask excludes: left untouched
 };
@@ -320,10 +320,17 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __gri
     for (int gi = warp; gi < nb; gi += kWarps) {
       if (S.skip[gi]) continue;
       CATAN_BIND(gi);
-      if (stage_busy) stage_reuse_wait(lane);
+      if (stage_busy) { stage_reuse_wait(lane); stage_busy = false; }
       if (!(P.debug_flags & 2)) encode_obs(cx);
-      stage_to_global(P.obs + static_cast<size_t>(base + gi) * CATAN_OBS_STRIDE, cx.obs, CATAN_OBS_STRIDE, lane);
-      stage_busy = true;
+      if (P.debug_flags & 8) {                                       // experiment: plain coalesced stores instead of the TMA engine
+        const int4* src = reinterpret_cast<const int4*>(cx.obs);
+        int4* dst = reinterpret_cast<int4*>(P.obs + static_cast<size_t>(base + gi) * CATAN_OBS_STRIDE);
+        for (int i = lane; i < CATAN_OBS_STRIDE / 16; i += 32) dst[i] = src[i];
+        __syncwarp();
+      } else {
+        stage_to_global(P.obs + static_cast<size_t>(base + gi) * CATAN_OBS_STRIDE, cx.obs, CATAN_OBS_STRIDE, lane);
+        stage_busy = true;
+      }
     }
     __syncthreads();
     CATAN_PROF(cx, PH_OBS);

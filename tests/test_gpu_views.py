@@ -1,0 +1,48 @@
+"""VecCatanEnv's policy-facing views: obs_views / obs_float / mask_views slice the packed rows into the reference's
+keys and shapes (env/wrapper.py:60-83, :172-185; RL/models/policy.py:168-190)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.common import load_golden
+from settlers_of_catan_rl_b200 import layout as L
+
+pytestmark = pytest.mark.gpu
+
+
+def test_views_match_reference_keys_shapes_and_values():
+    from settlers_of_catan_rl_b200 import VecCatanEnv
+    g = load_golden("default_s1")
+    n = 3
+    v = VecCatanEnv(n, seed=int(g["seed"]), first_env_id=int(g["env_id"]), auto_reset=0)
+    v.reset()
+    a = torch.zeros((n, L.ACTION_WORDS), dtype=torch.int32, device=v.device)
+    mask = torch.tensor([1, 0, 0], dtype=torch.uint8, device=v.device)        # only env 0 replays the golden game
+    for t in range(400):
+        a[0] = torch.from_numpy(g["actions"][t]).to(v.device)
+        v.step(a, step_mask=mask)
+    want = g["obs"][400]
+    views = v.obs_views()
+    fl = v.obs_float()
+    assert views["tile_representations"].shape == (n, 19, 60) and views["current_player_main"].shape == (n, 152)
+    assert views["next_next_next_player_main"].shape == (n, 159) and views["current_player_hidden_dev"].shape == (n, 25)
+    assert fl["tile_representations"].dtype == torch.float32 and fl["current_player_played_dev"].dtype == torch.int64
+    ratio = dict(L.OBS_RATIO_COLUMNS)
+    for key, off, shape in L.OBS_NUMERIC:
+        k = int(np.prod(shape))
+        assert np.array_equal(views[key][0].reshape(-1).cpu().numpy(), want[off:off + k]), key
+        ref = want[off:off + k].astype(np.float64)
+        for i in range(k):
+            ref[i] /= ratio.get(off + i, 1.0)
+        assert np.array_equal(fl[key][0].reshape(-1).double().cpu().numpy(), ref), key
+    for key, li in L.OBS_LISTS:
+        s = L.OBS_DEV_LISTS + li * L.OBS_DEV_PAD
+        assert np.array_equal(views[key][0].cpu().numpy(), want[s:s + L.OBS_DEV_PAD]), key
+    assert int(views["player_id"][0]) == int(want[L.OBS_META])
+    heads = v.mask_views()
+    assert [tuple(h.shape[1:]) for h in heads] == [tuple(s) for _, s in L.MASK_HEADS]
+    flat = torch.cat([h[0].reshape(-1) for h in heads]).cpu().numpy()
+    assert np.array_equal(flat, g["masks"][400][:L.MASK_ENTRIES])
+    # the frozen envs still show their reset situation
+    st = v.export_state()
+    assert st[1, L.STATE_DTYPE.fields["turn"][1] // 2] == 0
