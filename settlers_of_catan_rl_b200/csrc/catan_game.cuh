@@ -1,0 +1,1620 @@
+// catan_game.cuh — the Catan env-step engine, ONE THREAD PER GAME.
+//
+// Why thread-per-game (profiles/r2_notes.md): the first engine gave every game a warp.  Its lane-parallel loops are
+// 19/54/72/114 wide and its rule code is scalar, so a warp instruction did useful work for ~16 lanes of ONE game and the
+// kernel needed 2.9 k warp instructions per env step (issue-bound at 6 % of the HBM roofline).  Here a warp instruction
+// serves 32 games.  That only pays if the 32 lanes touch memory together, so the packed game records are stored
+// LANE-INTERLEAVED: 32 consecutive games form a chunk in which byte k of game l lives at chunk + 32*k + l (16- and 32-bit
+// fields interleave in units of their own size).  Every `g.field(i)` below is then one fully used 32-byte sector per
+// warp, and a per-game pointer chase costs no more than a coalesced load.
+//
+// The same source compiles two ways, like catan_core.cuh: nvcc (product, CATAN_W == 32) and g++ -DCATAN_HOST_EMU
+// (tests/host_emu only, CATAN_W == 1: a "chunk" is one plain GameRec), so the CPU test-suite runs exactly this logic
+// against the oracle and the golden fixtures.
+//
+// Reference behaviour reproduced here (file:line are in /root/reference): game/game.py (Game),
+// game/components/{board,corner,edge,player}.py, env/wrapper.py (EnvWrapper).  See SURVEY.md §8a.
+#pragma once
+
+#include <stddef.h>
+
+#include "catan_core.cuh"
+
+namespace catanb {
+
+#ifdef CATAN_DEVICE
+#define CATAN_W 32
+#define CATAN_MFN __device__ __forceinline__
+#else
+#define CATAN_W 1
+#define CATAN_MFN inline
+#endif
+#define CATAN_CHUNK_BYTES (sizeof(GameRec) * CATAN_W)
+
+// ------------------------------------------------------------------------------------------------
+// view of one game inside a lane-interleaved chunk.  Field names / meaning == GameRec (catan_core.cuh).
+// ------------------------------------------------------------------------------------------------
+struct GameView {
+  uint8_t* base;   // chunk base
+  int lane;        // game index inside the chunk
+  template <class T>
+  CATAN_MFN T& at(int off, int k) const {
+    return *reinterpret_cast<T*>(base + (static_cast<size_t>(off) + static_cast<size_t>(k) * sizeof(T)) * CATAN_W +
+                                 static_cast<size_t>(lane) * sizeof(T));
+  }
+#define CATAN_F0(T, name) CATAN_MFN T& name() const { return at<T>(offsetof(GameRec, name), 0); }
+#define CATAN_F1(T, name) CATAN_MFN T& name(int i) const { return at<T>(offsetof(GameRec, name), i); }
+#define CATAN_F2(T, name, B) CATAN_MFN T& name(int i, int j) const { return at<T>(offsetof(GameRec, name), i * (B) + j); }
+#define CATAN_F3(T, name, B, C_) CATAN_MFN T& name(int i, int j, int k) const { return at<T>(offsetof(GameRec, name), (i * (B) + j) * (C_) + k); }
+  CATAN_F3(int16_t, est_min, 3, 5) CATAN_F3(int16_t, est_max, 3, 5) CATAN_F2(int16_t, vis, 5)
+  CATAN_F0(uint32_t, rng_ctr) CATAN_F0(uint32_t, decision_ctr) CATAN_F0(uint32_t, episode_steps)
+  CATAN_F0(uint16_t, actions_this_turn) CATAN_F0(uint16_t, turn)
+  CATAN_F1(uint8_t, corner) CATAN_F1(uint8_t, edge) CATAN_F1(uint8_t, tile_res) CATAN_F1(uint8_t, tile_val)
+  CATAN_F1(uint8_t, harbour_perm) CATAN_F0(uint8_t, robber_tile) CATAN_F2(uint8_t, res, 5) CATAN_F1(int8_t, vp)
+  CATAN_F1(uint8_t, harbours) CATAN_F1(uint8_t, n_hidden) CATAN_F1(uint8_t, n_played) CATAN_F1(uint8_t, settlements_left)
+  CATAN_F1(uint8_t, cities_left) CATAN_F1(uint8_t, init_settlements) CATAN_F1(uint8_t, init_roads) CATAN_F1(int8_t, second_corner)
+  CATAN_F1(uint8_t, cur_longest_path) CATAN_F1(uint8_t, has_path_key) CATAN_F1(uint8_t, cur_army)
+  CATAN_F2(uint8_t, hidden, 25) CATAN_F2(uint8_t, played, 25) CATAN_F1(uint8_t, bank) CATAN_F0(uint8_t, deck_n) CATAN_F1(uint8_t, deck)
+  CATAN_F1(uint8_t, player_order) CATAN_F0(uint8_t, player_order_id) CATAN_F0(uint8_t, players_go)
+  CATAN_F0(uint8_t, lr_holder) CATAN_F0(uint8_t, lr_count) CATAN_F0(uint8_t, la_holder) CATAN_F0(uint8_t, la_count)
+  CATAN_F0(uint8_t, initial_phase) CATAN_F0(uint8_t, dice_rolled) CATAN_F0(uint8_t, played_dev) CATAN_F0(uint8_t, must_use_dev)
+  CATAN_F0(uint8_t, rb_active) CATAN_F0(uint8_t, rb_count) CATAN_F0(uint8_t, can_move_robber) CATAN_F0(uint8_t, just_moved_robber)
+  CATAN_F0(uint8_t, must_respond) CATAN_F0(uint8_t, need_discard) CATAN_F0(uint8_t, n_discard) CATAN_F1(uint8_t, discard_queue)
+  CATAN_F0(uint8_t, trade_proposer) CATAN_F0(uint8_t, trade_target) CATAN_F0(uint8_t, n_give) CATAN_F1(uint8_t, give)
+  CATAN_F0(uint8_t, n_recv) CATAN_F1(uint8_t, recv) CATAN_F0(uint8_t, die1) CATAN_F0(uint8_t, die2) CATAN_F0(uint8_t, trades_this_turn)
+  CATAN_F1(uint8_t, bought) CATAN_F1(int8_t, curr_vps) CATAN_F0(uint8_t, winner)
+#undef CATAN_F0
+#undef CATAN_F1
+#undef CATAN_F2
+#undef CATAN_F3
+};
+
+// view of game `i` of a record array stored as lane-interleaved chunks
+CATAN_FN GameView game_view(uint8_t* recs, size_t i) {
+  GameView g;
+  g.base = recs + (i / CATAN_W) * CATAN_CHUNK_BYTES;
+  g.lane = static_cast<int>(i % CATAN_W);
+  return g;
+}
+
+// host side: one game between a chunked buffer and a plain GameRec (catan_export_state / catan_import_state)
+static inline void chunk_get(const uint8_t* chunk, int lane, int W, GameRec& out) {
+  // 1-, 2- and 4-byte fields interleave in units of their own size; GameRec's layout: int16 [0,280), uint32 [280,292),
+  // uint16 [292,296), bytes from 296 on
+  uint8_t* o = reinterpret_cast<uint8_t*>(&out);
+  for (size_t off = 0; off < sizeof(GameRec);) {
+    const size_t sz = off < offsetof(GameRec, rng_ctr) ? 2 : (off < offsetof(GameRec, actions_this_turn) ? 4 : (off < offsetof(GameRec, corner) ? 2 : 1));
+    memcpy(o + off, chunk + off * W + static_cast<size_t>(lane) * sz, sz);
+    off += sz;
+  }
+}
+static inline void chunk_put(uint8_t* chunk, int lane, int W, const GameRec& in) {
+  const uint8_t* o = reinterpret_cast<const uint8_t*>(&in);
+  for (size_t off = 0; off < sizeof(GameRec);) {
+    const size_t sz = off < offsetof(GameRec, rng_ctr) ? 2 : (off < offsetof(GameRec, actions_this_turn) ? 4 : (off < offsetof(GameRec, corner) ? 2 : 1));
+    memcpy(chunk + off * W + static_cast<size_t>(lane) * sz, o + off, sz);
+    off += sz;
+  }
+}
+static_assert(offsetof(GameRec, est_min) == 0 && offsetof(GameRec, rng_ctr) == 280 && offsetof(GameRec, actions_this_turn) == 292 &&
+              offsetof(GameRec, corner) == 296, "chunk_get/chunk_put assume this field order");
+
+// ------------------------------------------------------------------------------------------------
+// bit tables derived from the topology (built once per block into shared memory)
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) TopoX {
+  uint64_t corner_nb[54];        // neighbouring corners of corner c
+  uint64_t corner_edges_lo[54];  // edges 0..63 incident to corner c
+  uint64_t tile_cmask[19];       // the six corners of tile t
+  uint32_t corner_edges_hi[54];  // edges 64..71 incident to corner c (bit e - 64)
+  uint32_t pad_[2];
+};
+CATAN_FN void build_topox(const Topo& T, TopoX& X, int tid, int nthreads) {
+  for (int c = tid; c < 54; c += nthreads) {
+    uint64_t nb = 0, lo = 0;
+    uint32_t hi = 0;
+    for (int k = 0; k < 3; ++k) {
+      if (T.corner_neigh[c][k] >= 0) nb |= 1ull << T.corner_neigh[c][k];
+      const int e = T.corner_neigh_edge[c][k];
+      if (e >= 64) hi |= 1u << (e - 64);
+      else if (e >= 0) lo |= 1ull << e;
+    }
+    X.corner_nb[c] = nb; X.corner_edges_lo[c] = lo; X.corner_edges_hi[c] = hi;
+  }
+  for (int t = tid; t < 19; t += nthreads) {
+    uint64_t m = 0;
+    for (int k = 0; k < 6; ++k) m |= 1ull << T.tile_corners[t][k];
+    X.tile_cmask[t] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// relative seating in registers (player.py:13-19): sp = seat of PlayerId p at bits [2p, 2p+2), op = PlayerId at seat s at
+// bits [4s, 4s+4)
+// ------------------------------------------------------------------------------------------------
+struct Seats { uint32_t sp, op; };
+CATAN_FN Seats load_seats(const GameView& g) {
+  Seats s = {0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t p = g.player_order(i);
+    s.op |= p << (4 * i);
+    s.sp |= static_cast<uint32_t>(i) << (2 * p);
+  }
+  return s;
+}
+CATAN_FN int seat_of(Seats s, int pid) { return (s.sp >> (2 * pid)) & 3; }
+CATAN_FN int pid_at_seat(Seats s, int seat) { return (s.op >> (4 * (seat & 3))) & 15; }
+// relative label of b seen from a: 0 next, 1 next_next, 2 next_next_next (player_lookup); -1 if a == b
+CATAN_FN int label_of(Seats s, int a, int b) { return ((seat_of(s, b) - seat_of(s, a) + 4) & 3) - 1; }
+CATAN_FN int pid_at_label(Seats s, int a, int label) { return pid_at_seat(s, seat_of(s, a) + 1 + label); }
+
+struct TCx {
+  GameView g;
+  const Topo* T;
+  const TopoX* X;
+  const catan_config_t* cfg;
+  uint64_t seed, env_id;
+  Seats s;
+};
+
+// what apply_action leaves for the follow-up passes of the same step
+struct StepTmp {
+  Act act;
+  EstReq est[2];
+  int16_t dice_T[4][5];      // clip bound of the (r, player) belief update of this roll
+  int16_t mono_T[4];
+  uint8_t alloc[5][4];       // dice payout [r][player index]      (game.py:153-167)
+  uint8_t mono_lost[4];
+  uint8_t n_est, est_special, granted, dice_roll;
+  uint8_t mono_pid, mono_res, lr_pid, err;
+  uint8_t acted_pid, act_type, roll_info, pad_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+CATAN_FN int t_hand_total(const GameView& g, int pid) {
+  const int p = pid - 1;
+  return g.res(p, 0) + g.res(p, 1) + g.res(p, 2) + g.res(p, 3) + g.res(p, 4);
+}
+CATAN_FN int t_current_actor(const GameView& g) {   // game_manager.py:152-159 / wrapper.py:53-58
+  return g.need_discard() ? g.discard_queue(0) : (g.must_respond() ? g.trade_target() : g.players_go());
+}
+CATAN_FN int t_best_exchange_rate(const GameView& g, int pid, int r) {   // wrapper.py:428-438
+  const int h = g.harbours(pid - 1);
+  return (h >> (r + 1)) & 1 ? 2 : ((h & 1) ? 3 : 4);
+}
+// number of cards of every kind in a player's hidden list, 6 bits per kind
+CATAN_FN uint32_t t_hidden_counts(const GameView& g, int p) {
+  uint32_t k = 0;
+  const int n = g.n_hidden(p);
+  CATAN_NO_UNROLL
+  for (int i = 0; i < n; ++i) k += 1u << (6 * g.hidden(p, i));
+  return k;
+}
+CATAN_FN int t_count_played(const GameView& g, int p, int card) {
+  int k = 0;
+  const int n = g.n_played(p);
+  CATAN_NO_UNROLL
+  for (int i = 0; i < n; ++i) k += g.played(p, i) == card;
+  return k;
+}
+
+CATAN_FN uint32_t t_rng_next(TCx& cx) {   // next word of the game stream
+  const uint32_t d = cx.g.rng_ctr();
+  cx.g.rng_ctr() = d + 1;
+  uint32_t w[4];
+  philox4x32(d >> 2, CATAN_STREAM_GAME, static_cast<uint32_t>(cx.env_id), static_cast<uint32_t>(cx.env_id >> 32),
+             static_cast<uint32_t>(cx.seed), static_cast<uint32_t>(cx.seed >> 32), w);
+  return w[d & 3];
+}
+CATAN_FN int t_rng_bounded(TCx& cx, int n) { return static_cast<int>(mulhi32(t_rng_next(cx), static_cast<uint32_t>(n))); }
+
+// ------------------------------------------------------------------------------------------------
+// placement predicates for ONE location (corner.py:24-39, edge.py:23-42); the mask encoder uses bit boards instead
+// ------------------------------------------------------------------------------------------------
+CATAN_FN_NOINLINE bool t_can_place_settlement(const GameView& g, const Topo& T, int c, int pid, bool initial) {
+  if (g.corner(c)) return false;
+  bool own_road = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int nb = T.corner_neigh[c][k];
+    if (nb < 0) continue;
+    if (g.corner(nb)) return false;
+    own_road |= g.edge(T.corner_neigh_edge[c][k]) == pid;
+  }
+  return initial || own_road;
+}
+
+CATAN_FN_NOINLINE bool t_can_place_road(const GameView& g, const Topo& T, int e, int pid, bool after_second, int second_corner) {
+  if (g.edge(e)) return false;
+  const int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
+  if (after_second) return c1 == second_corner || c2 == second_corner;
+  const uint8_t b1 = g.corner(c1), b2 = g.corner(c2);
+  if ((b1 && (b1 >> 2) == pid) || (b2 && (b2 >> 2) == pid)) return true;
+  bool ok = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int e1 = T.corner_neigh_edge[c1][k], e2 = T.corner_neigh_edge[c2][k];
+    ok |= (e1 >= 0 && !b1 && g.edge(e1) == pid);
+    ok |= (e2 >= 0 && !b2 && g.edge(e2) == pid);
+  }
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// translate (wrapper.py:114-166, :414-486) and validate (game.py:264-525)
+// ------------------------------------------------------------------------------------------------
+CATAN_FN_NOINLINE int t_translate_action(const TCx& cx, const int32_t* a, Act& t) {
+  const GameView& g = cx.g;
+  memset(&t, 0, sizeof(Act));
+  const int type = a[CATAN_A_TYPE], pg = g.players_go();
+  t.type = static_cast<int8_t>(type);
+  switch (type) {
+    case CATAN_ACT_PLACE_SETTLEMENT:
+    case CATAN_ACT_UPGRADE_CITY: {
+      const int v = a[CATAN_A_CORNER];
+      if (v < 0 || v >= 54) return CATAN_ERR_BAD_HEAD_VALUE;
+      t.corner = static_cast<int8_t>(v);
+      return 0;
+    }
+    case CATAN_ACT_PLACE_ROAD: {
+      const int v = a[CATAN_A_EDGE];
+      if (v < 0 || v > 72) return CATAN_ERR_BAD_HEAD_VALUE;
+      t.edge = static_cast<int8_t>(v == 72 ? -1 : v);
+      return 0;
+    }
+    case CATAN_ACT_MOVE_ROBBER: {
+      const int v = a[CATAN_A_TILE];
+      if (v < 0 || v >= 19) return CATAN_ERR_BAD_HEAD_VALUE;
+      t.tile = static_cast<int8_t>(v);
+      return 0;
+    }
+    case CATAN_ACT_STEAL:
+    case CATAN_ACT_PROPOSE_TRADE: {
+      const int pl = a[CATAN_A_PLAYER];
+      if (pl < 0 || pl > 2) return CATAN_ERR_BAD_HEAD_VALUE;
+      t.target_pid = static_cast<int8_t>(pid_at_label(cx.s, pg, pl));
+      if (type == CATAN_ACT_STEAL) return 0;
+      for (int k = 0; k < 4; ++k) {                                  // wrapper.py:451-466: 0 ends the list
+        const int v = a[CATAN_A_GIVE + k];
+        if (v == 0) break;
+        if (v < 0 || v > 5) return CATAN_ERR_BAD_HEAD_VALUE;
+        t.give[t.n_give++] = static_cast<int8_t>(v - 1);
+      }
+      for (int k = 0; k < 4; ++k) {
+        const int v = a[CATAN_A_RECV + k];
+        if (v == 0) break;
+        if (v < 0 || v > 5) return CATAN_ERR_BAD_HEAD_VALUE;
+        t.recv[t.n_recv++] = static_cast<int8_t>(v - 1);
+      }
+      return 0;
+    }
+    case CATAN_ACT_PLAY_DEV: {
+      const int card = a[CATAN_A_CARD];
+      if (card < 0 || card > 4) return CATAN_ERR_BAD_HEAD_VALUE;
+      t.card = static_cast<int8_t>(card);
+      if (card == CATAN_DEV_MONOPOLY || card == CATAN_DEV_YOP) {
+        const int v = a[CATAN_A_RES_A];
+        if (v < 0 || v > 4) return CATAN_ERR_BAD_HEAD_VALUE;
+        t.res_a = static_cast<int8_t>(v);
+      }
+      if (card == CATAN_DEV_YOP) {
+        const int v = a[CATAN_A_RES_B];
+        if (v < 0 || v > 4) return CATAN_ERR_BAD_HEAD_VALUE;
+        t.res_b = static_cast<int8_t>(v);
+      }
+      return 0;
+    }
+    case CATAN_ACT_EXCHANGE: {
+      const int va = a[CATAN_A_RES_A], vb = a[CATAN_A_RES_B];
+      if (va < 0 || va > 4 || vb < 0 || vb > 4) return CATAN_ERR_BAD_HEAD_VALUE;
+      t.res_a = static_cast<int8_t>(va);
+      t.res_b = static_cast<int8_t>(vb);
+      t.rate = static_cast<int8_t>(t_best_exchange_rate(g, pg, va));
+      return 0;
+    }
+    case CATAN_ACT_RESPOND: {
+      const int v = a[CATAN_A_ACCEPT];
+      if (v < 0 || v > 1) return CATAN_ERR_BAD_HEAD_VALUE;
+      t.accept = static_cast<int8_t>(v);
+      return 0;
+    }
+    case CATAN_ACT_DISCARD: {
+      const int v = a[CATAN_A_DISCARD];
+      if (v < 0 || v > 4) return CATAN_ERR_BAD_HEAD_VALUE;
+      t.discard = static_cast<int8_t>(v);
+      return 0;
+    }
+    case CATAN_ACT_BUY_DEV:
+    case CATAN_ACT_ROLL_DICE:
+    case CATAN_ACT_END_TURN:
+      return 0;
+    default:
+      return CATAN_ERR_BAD_TYPE;
+  }
+}
+
+CATAN_FN_NOINLINE int t_validate_action(const TCx& cx, const Act& t) {
+  const GameView& g = cx.g;
+  const Topo& T = *cx.T;
+  const int pid = g.players_go(), p = pid - 1;
+  if (g.need_discard()) {                                            // game.py:279-300
+    if (t.type != CATAN_ACT_DISCARD) return CATAN_ERR_PHASE;
+    const int d = g.discard_queue(0);
+    if (t_hand_total(g, d) <= 7) return CATAN_ERR_PHASE;
+    return g.res(d - 1, t.discard) > 0 ? 0 : CATAN_ERR_BAD_RESOURCE;
+  }
+  if (t.type == CATAN_ACT_DISCARD) return CATAN_ERR_PHASE;           // game.py:301-303
+  const bool must_respond = g.must_respond(), initial = g.initial_phase(), rolled = g.dice_rolled(), must_use = g.must_use_dev(),
+             just_moved = g.just_moved_robber();
+  // the common guard of most main-phase actions (must have rolled, nothing pending)
+  const bool blocked_main = must_respond || initial || !rolled || must_use || just_moved;
+  switch (t.type) {
+    case CATAN_ACT_PLACE_SETTLEMENT:                                 // game.py:305-323
+      if (must_respond || (!rolled && !initial) || must_use || just_moved) return CATAN_ERR_PHASE;
+      if (initial || (g.settlements_left(p) > 0 && g.res(p, WHEAT) && g.res(p, WOOD) && g.res(p, BRICK) && g.res(p, SHEEP))) {
+        if (t_can_place_settlement(g, T, t.corner, pid, initial)) {
+          if (!initial) return 0;
+          return (g.init_settlements(p) == 0 || (g.init_settlements(p) == 1 && g.init_roads(p) == 1)) ? 0 : CATAN_ERR_BAD_LOCATION;
+        }
+      }
+      return CATAN_ERR_CANNOT_AFFORD;
+    case CATAN_ACT_PLACE_ROAD:                                       // game.py:324-357
+      if (g.rb_active()) {
+        if (t.edge < 0) return 0;
+        return t_can_place_road(g, T, t.edge, pid, false, 0) ? 0 : CATAN_ERR_BAD_LOCATION;
+      }
+      if (must_respond || (!rolled && !initial) || must_use || just_moved) return CATAN_ERR_PHASE;
+      if (!(initial || (g.res(p, WOOD) && g.res(p, BRICK)))) return CATAN_ERR_CANNOT_AFFORD;
+      if (t.edge < 0) return CATAN_ERR_BAD_LOCATION;
+      if (!t_can_place_road(g, T, t.edge, pid, false, 0)) return CATAN_ERR_BAD_LOCATION;
+      if (!initial) return 0;
+      if (g.init_settlements(p) == 1 && g.init_roads(p) == 0) return 0;
+      if (g.init_settlements(p) == 2 && g.init_roads(p) == 1)
+        return t_can_place_road(g, T, t.edge, pid, true, g.second_corner(p)) ? 0 : CATAN_ERR_BAD_LOCATION;
+      return CATAN_ERR_BAD_LOCATION;
+    case CATAN_ACT_UPGRADE_CITY:                                     // game.py:358-376
+      if (blocked_main) return CATAN_ERR_PHASE;
+      if (g.cities_left(p) > 0 && g.res(p, WHEAT) > 1 && g.res(p, ORE) > 2) {
+        const uint8_t b = g.corner(t.corner);
+        if ((b & 3) != 1) return CATAN_ERR_BAD_LOCATION;
+        if ((b >> 2) == pid) return 0;
+      }
+      return CATAN_ERR_CANNOT_AFFORD;
+    case CATAN_ACT_BUY_DEV:                                          // game.py:377-393
+      if (blocked_main) return CATAN_ERR_PHASE;
+      if (g.res(p, WHEAT) && g.res(p, SHEEP) && g.res(p, ORE)) return g.deck_n() > 0 ? 0 : CATAN_ERR_BAD_CARD;
+      return CATAN_ERR_CANNOT_AFFORD;
+    case CATAN_ACT_PLAY_DEV: {                                       // game.py:394-415
+      if (must_respond || g.played_dev() || initial || just_moved) return CATAN_ERR_PHASE;
+      const int k = (t_hidden_counts(g, p) >> (6 * t.card)) & 63;
+      return (k > 0 && k != g.bought(t.card)) ? 0 : CATAN_ERR_BAD_CARD;
+    }
+    case CATAN_ACT_EXCHANGE:                                         // game.py:416-443
+      if (blocked_main) return CATAN_ERR_PHASE;
+      if (g.res(p, t.res_a) < t.rate) return CATAN_ERR_CANNOT_AFFORD;
+      return g.bank(t.res_b) > 0 ? 0 : CATAN_ERR_BAD_RESOURCE;
+    case CATAN_ACT_PROPOSE_TRADE: {                                  // game.py:444-466
+      if (blocked_main) return CATAN_ERR_PHASE;
+      uint32_t cnt = 0;                                              // 4 bits per resource
+      for (int k = 0; k < t.n_give; ++k) cnt += 1u << (4 * t.give[k]);
+      for (int r = 0; r < 5; ++r) if (g.res(p, r) < static_cast<int>((cnt >> (4 * r)) & 15)) return CATAN_ERR_CANNOT_AFFORD;
+      return 0;
+    }
+    case CATAN_ACT_RESPOND: {                                        // game.py:467-482
+      if (!must_respond) return CATAN_ERR_PHASE;
+      if (t.accept == 1) return 0;                                   // head value 1 == "reject" (wrapper.py:157-160)
+      uint32_t cnt = 0;
+      const int nr = g.n_recv(), tt = g.trade_target() - 1;
+      for (int k = 0; k < nr; ++k) cnt += 1u << (4 * (g.recv(k) - 1));
+      for (int r = 0; r < 5; ++r) if (g.res(tt, r) < static_cast<int>((cnt >> (4 * r)) & 15)) return CATAN_ERR_CANNOT_AFFORD;
+      return 0;
+    }
+    case CATAN_ACT_MOVE_ROBBER:                                      // game.py:483-490
+      return (must_respond || must_use || !g.can_move_robber()) ? CATAN_ERR_PHASE : 0;
+    case CATAN_ACT_ROLL_DICE:                                        // game.py:491-500
+      return (must_respond || initial || rolled || just_moved) ? CATAN_ERR_PHASE : 0;
+    case CATAN_ACT_END_TURN:                                         // game.py:501-512
+      return blocked_main ? CATAN_ERR_PHASE : 0;
+    case CATAN_ACT_STEAL: {                                          // game.py:513-525
+      if (must_respond || !just_moved) return CATAN_ERR_PHASE;
+      const int rt = g.robber_tile();
+      for (int k = 0; k < 6; ++k) {
+        const uint8_t b = g.corner(T.tile_corners[rt][k]);
+        if (b && (b >> 2) == t.target_pid) return 0;
+      }
+      return CATAN_ERR_BAD_TARGET;
+    }
+  }
+  return CATAN_ERR_BAD_TYPE;
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply_action, scalar part (game.py:527-815).  Belief updates, the dice payout and the longest-road search are posted
+// to `tmp` and executed afterwards.
+// ------------------------------------------------------------------------------------------------
+CATAN_FN void t_pay(const GameView& g, int p, int r, int n) {   // hand -n, visible floor 0, bank +n (game.py:197-208 etc.)
+  g.res(p, r) = static_cast<uint8_t>(g.res(p, r) - n);
+  const int v = g.vis(p, r) - n;
+  g.vis(p, r) = static_cast<int16_t>(v > 0 ? v : 0);
+  g.bank(r) = static_cast<uint8_t>(g.bank(r) + n);
+}
+
+CATAN_FN EstReq& t_post_est(TCx& cx, StepTmp& tmp, int owner, int thief) {
+  EstReq& q = tmp.est[tmp.n_est++];
+  memset(&q, 0, sizeof(EstReq));
+  q.owner = static_cast<uint8_t>(owner);
+  q.thief = static_cast<uint8_t>(thief);
+  q.T_o = static_cast<int16_t>(t_hand_total(cx.g, owner));
+  q.T_t = static_cast<int16_t>(thief ? t_hand_total(cx.g, thief) : 0);
+  return q;
+}
+
+CATAN_FN void t_advance_seat(const GameView& g, bool left) {   // game.py:253-262
+  const int id = (g.player_order_id() + (left ? 3 : 1)) & 3;
+  g.player_order_id() = static_cast<uint8_t>(id);
+  g.players_go() = g.player_order(id);
+}
+
+CATAN_FN_NOINLINE void t_update_largest_army(const GameView& g) {   // game.py:817-841
+  int max_count = 0, cp = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = (0x3412 >> (4 * i)) & 15;                    // order Blue, White, Red, Orange (game.py:820)
+    const int k = t_count_played(g, q - 1, CATAN_DEV_KNIGHT);
+    g.cur_army(q - 1) = static_cast<uint8_t>(k);
+    if (k >= 3 && k > max_count) { max_count = k; cp = q; }
+  }
+  if (!cp) return;
+  const int holder = g.la_holder();
+  if (!holder) { g.la_holder() = static_cast<uint8_t>(cp); g.la_count() = static_cast<uint8_t>(max_count); g.vp(cp - 1) += 2; }
+  else if (holder == cp) g.la_count() = static_cast<uint8_t>(max_count);
+  else if (max_count > g.la_count()) {
+    g.vp(holder - 1) -= 2;
+    g.la_holder() = static_cast<uint8_t>(cp); g.la_count() = static_cast<uint8_t>(max_count);
+    g.vp(cp - 1) += 2;
+  }
+}
+
+CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp) {
+  const GameView& g = cx.g;
+  const Topo& T = *cx.T;
+  const Act& t = tmp.act;
+  const int pid = g.players_go(), p = pid - 1;
+  switch (t.type) {
+    case CATAN_ACT_PLACE_SETTLEMENT: {                               // game.py:530-555, :195-212
+      const int c = t.corner;
+      const bool initial = g.initial_phase();
+      if (!initial) { t_pay(g, p, WHEAT, 1); t_pay(g, p, SHEEP, 1); t_pay(g, p, WOOD, 1); t_pay(g, p, BRICK, 1); }
+      g.corner(c) = static_cast<uint8_t>((pid << 2) | 1);
+      const int slot = T.corner_harbour_slot[c];                     // board.py:182-183
+      if (slot >= 0) {
+        const int hres = T.harbour_res[g.harbour_perm(slot)];
+        g.harbours(p) |= static_cast<uint8_t>(1u << hres);           // bit 0 = generic, bit Resource = 2:1
+      }
+      g.settlements_left(p) -= 1;
+      g.vp(p) += 1;
+      if (initial) {
+        const int ns = g.init_settlements(p) + 1;
+        g.init_settlements(p) = static_cast<uint8_t>(ns);
+        if (ns == 2) {
+          uint32_t gain = 0;                                         // 4 bits per resource
+          for (int k = 0; k < 3; ++k) {
+            const int tl = T.corner_tiles[c][k];
+            if (tl < 0) continue;
+            const int tr = g.tile_res(tl);
+            if (tr == 0) continue;
+            const int r = tr - 1;
+            g.res(p, r) += 1; g.vis(p, r) += 1; g.bank(r) -= 1; gain += 1u << (4 * r);
+          }
+          EstReq& q = t_post_est(cx, tmp, pid, 0);
+          for (int r = 0; r < 5; ++r) if ((gain >> (4 * r)) & 15) est_set(q, r, (gain >> (4 * r)) & 15);
+          g.second_corner(p) = static_cast<int8_t>(c);
+        }
+      } else {
+        EstReq& q = t_post_est(cx, tmp, pid, 0);
+        est_set(q, BRICK, -1); est_set(q, WOOD, -1); est_set(q, WHEAT, -1); est_set(q, SHEEP, -1);
+        if (g.lr_holder()) tmp.lr_pid = g.lr_holder();               // game.py:552-553
+      }
+      break;
+    }
+    case CATAN_ACT_PLACE_ROAD: {                                     // game.py:556-597, :222-232
+      bool final_init = false;
+      const bool initial = g.initial_phase(), rb = g.rb_active();
+      if (t.edge >= 0) {
+        if (!initial && !rb) { t_pay(g, p, WOOD, 1); t_pay(g, p, BRICK, 1); }
+        g.edge(t.edge) = static_cast<uint8_t>(pid);
+        if (initial) {
+          g.init_roads(p) += 1;
+          int first = 0, second = 0;
+          for (int q = 0; q < 4; ++q) { const int ns = g.init_settlements(q); first += ns >= 1; second += ns == 2; }
+          if (first < 4) t_advance_seat(g, false);
+          else if (second == 0) { /* last seat places twice in a row */ }
+          else if (second < 4) t_advance_seat(g, true);
+          else { g.initial_phase() = 0; final_init = true; }
+        }
+      }
+      tmp.lr_pid = static_cast<uint8_t>(pid);                        // game.py:585 (also for the dummy edge)
+      if (rb) {
+        const int n = g.rb_count() + 1;
+        if (n >= 2) { g.rb_active() = 0; g.rb_count() = 0; g.must_use_dev() = 0; }
+        else g.rb_count() = static_cast<uint8_t>(n);
+      } else if (!initial) {
+        EstReq& q = t_post_est(cx, tmp, pid, 0);
+        est_set(q, BRICK, -1); est_set(q, WOOD, -1);
+      }
+      break;
+    }
+    case CATAN_ACT_UPGRADE_CITY: {                                   // game.py:598-604, :240-251
+      t_pay(g, p, WHEAT, 2); t_pay(g, p, ORE, 3);
+      g.corner(t.corner) = static_cast<uint8_t>((pid << 2) | 2);
+      g.vp(p) += 1; g.cities_left(p) -= 1; g.settlements_left(p) += 1;
+      EstReq& q = t_post_est(cx, tmp, pid, 0);
+      est_set(q, ORE, -3); est_set(q, WHEAT, -2);
+      break;
+    }
+    case CATAN_ACT_ROLL_DICE: {                                      // game.py:605-611, :138-150
+      const int d1 = 1 + t_rng_bounded(cx, 6), d2 = 1 + t_rng_bounded(cx, 6);
+      g.die1() = static_cast<uint8_t>(d1);
+      g.die2() = static_cast<uint8_t>(d2);
+      const int roll = d1 + d2;
+      tmp.roll_info = static_cast<uint8_t>(roll);
+      g.dice_rolled() = 1;
+      if (roll == 7) {
+        g.can_move_robber() = 1;
+        int nd = g.n_discard();
+        for (int i = 0; i < 4; ++i) {
+          const int q = pid_at_seat(cx.s, i);
+          if (t_hand_total(g, q) > 7) { g.need_discard() = 1; g.discard_queue(nd++) = static_cast<uint8_t>(q); }
+        }
+        g.n_discard() = static_cast<uint8_t>(nd);
+      } else {
+        tmp.dice_roll = static_cast<uint8_t>(roll);                  // payout + beliefs: t_dice_payout()
+      }
+      break;
+    }
+    case CATAN_ACT_END_TURN:                                         // game.py:612-622
+      g.can_move_robber() = 0; g.dice_rolled() = 0; g.played_dev() = 0;
+      t_advance_seat(g, false);
+      g.turn() += 1;
+      for (int c = 0; c < 5; ++c) g.bought(c) = 0;
+      g.trades_this_turn() = 0; g.actions_this_turn() = 0;
+      break;
+    case CATAN_ACT_MOVE_ROBBER: {                                    // game.py:623-634
+      g.robber_tile() = static_cast<uint8_t>(t.tile);
+      g.can_move_robber() = 0;
+      bool jm = false;
+      for (int k = 0; k < 6; ++k) {
+        const uint8_t b = g.corner(T.tile_corners[t.tile][k]);
+        jm |= b && (b >> 2) != pid;
+      }
+      if (jm) g.just_moved_robber() = 1;
+      break;
+    }
+    case CATAN_ACT_STEAL: {                                          // game.py:635-652
+      const int v = t.target_pid;
+      const int n = t_hand_total(g, v);
+      if (n > 0) {
+        int idx = t_rng_bounded(cx, n), r = BRICK;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int ri = (0x23140 >> (4 * i)) & 15;            // Brick, Wheat, Wood, Sheep, Ore (game.py:638)
+          const int cnt = g.res(v - 1, ri);
+          if (idx >= 0 && idx < cnt) { r = ri; idx = -1; }
+          else if (idx >= 0) idx -= cnt;
+        }
+        g.res(p, r) += 1; g.res(v - 1, r) -= 1;
+        for (int q = 0; q < 5; ++q) if (g.vis(v - 1, q) > 0) g.vis(v - 1, q) -= 1;
+        EstReq& rq = t_post_est(cx, tmp, v, pid);
+        est_set(rq, r, -1);
+      }
+      g.just_moved_robber() = 0;
+      break;
+    }
+    case CATAN_ACT_PLAY_DEV: {                                       // game.py:653-693
+      const int n = g.n_hidden(p);
+      int at = 0;
+      while (at < n && g.hidden(p, at) != t.card) ++at;
+      if (at < n) {                                                  // (always true for a validated action)
+        for (int i = at; i + 1 < n; ++i) g.hidden(p, i) = g.hidden(p, i + 1);
+        g.hidden(p, n - 1) = 0;
+        g.n_hidden(p) = static_cast<uint8_t>(n - 1);
+      }
+      const int np = g.n_played(p);
+      if (np < 25) { g.played(p, np) = static_cast<uint8_t>(t.card); g.n_played(p) = static_cast<uint8_t>(np + 1); }
+      g.played_dev() = 1;
+      if (t.card == CATAN_DEV_VP) g.vp(p) += 1;
+      else if (t.card == CATAN_DEV_KNIGHT) { g.can_move_robber() = 1; t_update_largest_army(g); }
+      else if (t.card == CATAN_DEV_ROADBUILDING) { g.rb_active() = 1; g.rb_count() = 0; g.must_use_dev() = 1; }
+      else if (t.card == CATAN_DEV_MONOPOLY) {
+        const int r = t.res_a;
+        tmp.est_special = EST_SPECIAL_MONOPOLY;
+        tmp.mono_pid = static_cast<uint8_t>(pid); tmp.mono_res = static_cast<uint8_t>(r);
+        for (int o = 0; o < 4; ++o) {
+          tmp.mono_lost[o] = 0;
+          if (o == p) continue;
+          const int cnt = g.res(o, r);
+          g.res(o, r) = 0; g.vis(o, r) = 0;
+          g.res(p, r) = static_cast<uint8_t>(g.res(p, r) + cnt); g.vis(p, r) = static_cast<int16_t>(g.vis(p, r) + cnt);
+          tmp.mono_lost[o] = static_cast<uint8_t>(cnt);
+        }
+        for (int o = 0; o < 4; ++o) tmp.mono_T[o] = static_cast<int16_t>(t_hand_total(g, o + 1));
+      } else {                                                       // Year of Plenty
+        for (int i = 0; i < 2; ++i) {
+          const int r = i == 0 ? t.res_a : t.res_b;
+          if (g.bank(r) > 0) {
+            g.bank(r) -= 1; g.res(p, r) += 1; g.vis(p, r) += 1;
+            EstReq& q = t_post_est(cx, tmp, pid, 0);
+            est_set(q, r, 1);
+          }
+        }
+      }
+      break;
+    }
+    case CATAN_ACT_BUY_DEV: {                                        // game.py:694-710
+      t_pay(g, p, SHEEP, 1); t_pay(g, p, ORE, 1); t_pay(g, p, WHEAT, 1);
+      EstReq& q = t_post_est(cx, tmp, pid, 0);
+      est_set(q, SHEEP, -1); est_set(q, ORE, -1); est_set(q, WHEAT, -1);
+      const int dn = g.deck_n(), nh = g.n_hidden(p);
+      if (dn > 0 && nh < 25) {                                       // (always true for a validated action)
+        const int card = g.deck(dn - 1);                             // deque.pop(): right end
+        g.deck(dn - 1) = 0; g.deck_n() = static_cast<uint8_t>(dn - 1);
+        g.hidden(p, nh) = static_cast<uint8_t>(card); g.n_hidden(p) = static_cast<uint8_t>(nh + 1);
+        g.bought(card) += 1;
+      }
+      break;
+    }
+    case CATAN_ACT_EXCHANGE: {                                       // game.py:711-734
+      const int d = t.res_b, tr = t.res_a, rate = t.rate;
+      g.res(p, d) += 1; g.vis(p, d) += 1;
+      g.res(p, tr) = static_cast<uint8_t>(g.res(p, tr) - rate);
+      const int v = g.vis(p, tr) - rate;
+      g.vis(p, tr) = static_cast<int16_t>(v > 0 ? v : 0);
+      g.bank(tr) = static_cast<uint8_t>(g.bank(tr) + rate); g.bank(d) -= 1;
+      EstReq& q = t_post_est(cx, tmp, pid, 0);
+      if (d == tr) est_set(q, d, 1 - rate);
+      else { est_set(q, d, 1); est_set(q, tr, -rate); }
+      break;
+    }
+    case CATAN_ACT_PROPOSE_TRADE:                                    // game.py:735-750
+      g.must_respond() = 1;
+      g.trade_proposer() = static_cast<uint8_t>(pid); g.trade_target() = static_cast<uint8_t>(t.target_pid);
+      g.n_give() = static_cast<uint8_t>(t.n_give); g.n_recv() = static_cast<uint8_t>(t.n_recv);
+      for (int k = 0; k < 4; ++k) {
+        g.give(k) = static_cast<uint8_t>(k < t.n_give ? t.give[k] + 1 : 0);
+        g.recv(k) = static_cast<uint8_t>(k < t.n_recv ? t.recv[k] + 1 : 0);
+      }
+      g.trades_this_turn() += 1;
+      break;
+    case CATAN_ACT_RESPOND: {                                        // game.py:751-784
+      if (t.accept == 0) {
+        const int p1 = g.trade_proposer() - 1, p2 = g.trade_target() - 1;
+        const int ng = g.n_give(), nr = g.n_recv();
+        int8_t d1[5] = {0, 0, 0, 0, 0};
+        uint8_t touched = 0;
+        for (int k = 0; k < ng; ++k) {
+          const int r = g.give(k) - 1;
+          g.res(p1, r) -= 1; if (g.vis(p1, r) > 0) g.vis(p1, r) -= 1;
+          g.res(p2, r) += 1; g.vis(p2, r) += 1;
+          d1[r] -= 1; touched |= static_cast<uint8_t>(1u << r);
+        }
+        for (int k = 0; k < nr; ++k) {
+          const int r = g.recv(k) - 1;
+          g.res(p1, r) += 1; g.vis(p1, r) += 1;
+          g.res(p2, r) -= 1; if (g.vis(p2, r) > 0) g.vis(p2, r) -= 1;
+          d1[r] += 1; touched |= static_cast<uint8_t>(1u << r);
+        }
+        EstReq& q1 = t_post_est(cx, tmp, p1 + 1, 0);
+        EstReq& q2 = t_post_est(cx, tmp, p2 + 1, 0);
+        for (int r = 0; r < 5; ++r) { q1.delta[r] = d1[r]; q2.delta[r] = static_cast<int8_t>(-d1[r]); }
+        q1.touched = touched; q2.touched = touched;
+      }
+      g.must_respond() = 0;
+      g.trade_proposer() = 0; g.trade_target() = 0; g.n_give() = 0; g.n_recv() = 0;
+      for (int k = 0; k < 4; ++k) { g.give(k) = 0; g.recv(k) = 0; }
+      break;
+    }
+    case CATAN_ACT_DISCARD: {                                        // game.py:785-807
+      const int d = g.discard_queue(0), r = t.discard;
+      g.res(d - 1, r) -= 1; g.bank(r) += 1;
+      EstReq& q = t_post_est(cx, tmp, d, 0);
+      est_set(q, r, -1);
+      if (t_hand_total(g, d) <= 7) {
+        for (int i = 0; i < 3; ++i) g.discard_queue(i) = g.discard_queue(i + 1);
+        g.discard_queue(3) = 0;
+        const int nd = g.n_discard() - 1;
+        g.n_discard() = static_cast<uint8_t>(nd);
+        if (nd == 0) g.need_discard() = 0;
+      }
+      break;
+    }
+  }
+  if (t.type != CATAN_ACT_RESPOND && t.type != CATAN_ACT_END_TURN && t.type != CATAN_ACT_DISCARD)
+    g.actions_this_turn() += 1;                                      // game.py:809-810
+}
+
+// ------------------------------------------------------------------------------------------------
+// dice payout (game.py:151-175)
+// ------------------------------------------------------------------------------------------------
+CATAN_FN_NOINLINE void t_dice_payout(TCx& cx, StepTmp& tmp) {
+  const GameView& g = cx.g;
+  const Topo& T = *cx.T;
+  const int roll = tmp.dice_roll, robber = g.robber_tile();
+  for (int i = 0; i < 20; ++i) (&tmp.alloc[0][0])[i] = 0;
+  CATAN_NO_UNROLL
+  for (int t = 0; t < 19; ++t) {
+    if (g.tile_val(t) != roll || t == robber) continue;
+    const int r = g.tile_res(t) - 1;
+    for (int k = 0; k < 6; ++k) {
+      const uint8_t b = g.corner(T.tile_corners[t][k]);
+      if (b) tmp.alloc[r][(b >> 2) - 1] += b & 3;                    // settlement +1, city +2
+    }
+  }
+  int tot[4];
+  for (int p = 0; p < 4; ++p) tot[p] = t_hand_total(g, p + 1);
+  uint8_t granted = 0;
+#pragma unroll
+  for (int ri = 0; ri < 5; ++ri) {
+    const int r = (0x34021 >> (4 * ri)) & 15;                        // Wood, Ore, Brick, Wheat, Sheep (game.py:153-155)
+    const int total = tmp.alloc[r][0] + tmp.alloc[r][1] + tmp.alloc[r][2] + tmp.alloc[r][3];
+    if (total > g.bank(r)) continue;                                 // all-or-nothing per resource (game.py:171)
+    granted |= static_cast<uint8_t>(1u << r);
+    for (int p = 0; p < 4; ++p) {
+      const int a = tmp.alloc[r][p];
+      if (a) { g.res(p, r) = static_cast<uint8_t>(g.res(p, r) + a); g.bank(r) = static_cast<uint8_t>(g.bank(r) - a); }
+      tot[p] += a;
+      tmp.dice_T[p][r] = static_cast<int16_t>(tot[p]);               // owner's running total when (r, p) is re-clipped (Q4)
+    }
+  }
+  tmp.granted = granted;
+  tmp.est_special = EST_SPECIAL_DICE;
+}
+
+// ------------------------------------------------------------------------------------------------
+// belief updates
+//   generic  : update_player_resource_estimates (game.py:921-971)
+//   dice     : the 20 calls of one roll folded into one pass (game.py:170-175; Q4)
+//   monopoly : update_resource_estimates_monopoly (game.py:973-1010)
+// ------------------------------------------------------------------------------------------------
+CATAN_FN_NOINLINE void t_est_generic(TCx& cx, const EstReq& rq) {
+  const GameView& g = cx.g;
+  const int owner = rq.owner, thief = rq.thief, T_o = rq.T_o, T_t = rq.T_t;
+  CATAN_NO_UNROLL
+  for (int o = 0; o < 4; ++o) {
+    const int observer = o + 1;
+    if (!thief || observer == thief) {                               // game.py:936-954
+      if (observer == owner) continue;
+      const int l = label_of(cx.s, observer, owner);
+      for (int r = 0; r < 5; ++r) {
+        if (!((rq.touched >> r) & 1)) continue;
+        g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) + rq.delta[r], 0, T_o));
+        g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) + rq.delta[r], 0, T_o));
+      }
+    } else if (observer == owner) {                                  // victim knows what was taken (game.py:929-933)
+      const int l = label_of(cx.s, observer, thief);
+      for (int r = 0; r < 5; ++r) {
+        if (!((rq.touched >> r) & 1)) continue;
+        g.est_max(o, l, r) = static_cast<int16_t>(g.est_max(o, l, r) - rq.delta[r]);
+        g.est_min(o, l, r) = static_cast<int16_t>(g.est_min(o, l, r) - rq.delta[r]);
+      }
+    } else {                                                         // third party (game.py:955-971)
+      const int lo = label_of(cx.s, observer, owner), lt = label_of(cx.s, observer, thief);
+      for (int r = 0; r < 5; ++r) {
+        const int m0 = g.est_max(o, lo, r);                          // the victim entry BEFORE its clip
+        g.est_max(o, lo, r) = static_cast<int16_t>(clipi(m0, 0, T_o));
+        g.est_min(o, lo, r) = static_cast<int16_t>(clipi(g.est_min(o, lo, r) - 1, 0, T_o));
+        if (m0 > 0) {
+          g.est_max(o, lt, r) = static_cast<int16_t>(clipi(g.est_max(o, lt, r) + 1, 0, T_t));
+          g.est_min(o, lt, r) = static_cast<int16_t>(clipi(g.est_min(o, lt, r), 0, T_t));
+        }
+      }
+    }
+  }
+}
+
+CATAN_FN_NOINLINE void t_est_special(TCx& cx, const StepTmp& tmp) {
+  const GameView& g = cx.g;
+  if (tmp.est_special == EST_SPECIAL_DICE) {
+    CATAN_NO_UNROLL
+    for (int ol = 0; ol < 12; ++ol) {
+      const int o = ol / 3, l = ol - 3 * o;
+      const int tp = pid_at_label(cx.s, o + 1, l) - 1;
+      for (int r = 0; r < 5; ++r) {
+        if (!((tmp.granted >> r) & 1)) continue;
+        const int gain = tmp.alloc[r][tp], T = tmp.dice_T[tp][r];
+        g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) + gain, 0, T));
+        g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) + gain, 0, T));
+      }
+    }
+  } else if (tmp.est_special == EST_SPECIAL_MONOPOLY) {
+    const int tot = tmp.mono_lost[0] + tmp.mono_lost[1] + tmp.mono_lost[2] + tmp.mono_lost[3];
+    const int mr = tmp.mono_res;
+    CATAN_NO_UNROLL
+    for (int ol = 0; ol < 12; ++ol) {
+      const int o = ol / 3, l = ol - 3 * o;
+      const int target = pid_at_label(cx.s, o + 1, l);
+      if (target == tmp.mono_pid) {                                  // game.py:984-991, unclipped
+        g.est_min(o, l, mr) = static_cast<int16_t>(g.est_min(o, l, mr) + tot);
+        g.est_max(o, l, mr) = static_cast<int16_t>(g.est_max(o, l, mr) + tot);
+      } else {                                                       // game.py:993-1010
+        const int T = tmp.mono_T[target - 1];
+        for (int r = 0; r < 5; ++r) {
+          const int lost = r == mr ? tmp.mono_lost[target - 1] : 0;
+          g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) - lost, 0, T));
+          g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) - lost, 0, T));
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the transition of one env step up to (not including) the longest-road update (wrapper.py:36-50, game.py:527-815).
+// `a`: the env's composite action row.  Leaves tmp.err / tmp.lr_pid for the caller.
+// ------------------------------------------------------------------------------------------------
+CATAN_FN void t_step_transition(TCx& cx, const int32_t* a, StepTmp& tmp) {
+  tmp.n_est = 0; tmp.est_special = EST_SPECIAL_NONE; tmp.dice_roll = 0; tmp.lr_pid = 0; tmp.roll_info = 0;
+  tmp.acted_pid = static_cast<uint8_t>(t_current_actor(cx.g));
+  tmp.act_type = static_cast<uint8_t>(a[CATAN_A_TYPE]);
+  int err = t_translate_action(cx, a, tmp.act);
+  if (!err && cx.cfg->validate_actions) err = t_validate_action(cx, tmp.act);
+  tmp.err = static_cast<uint8_t>(err);
+  if (err) return;
+  t_apply_scalar(cx, tmp);
+  if (tmp.dice_roll) t_dice_payout(cx, tmp);
+  for (int qi = 0; qi < tmp.n_est; ++qi) t_est_generic(cx, tmp.est[qi]);
+  if (tmp.est_special) t_est_special(cx, tmp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// longest road (game.py:843-919): adjacency masks from a view; the search itself is catan_core.cuh's lp_round
+// ------------------------------------------------------------------------------------------------
+CATAN_FN void t_lp_build_adj(const GameView& g, const Topo& T, int pid, uint64_t* adj, int lane, int nlanes) {
+  for (int v = lane; v < 54; v += nlanes) {
+    uint64_t a = 0;
+    const uint8_t b = g.corner(v);
+    if (!(b && (b >> 2) != pid)) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int e = T.corner_neigh_edge[v][k];
+        if (e >= 0 && g.edge(e) == pid) a |= 1ull << T.corner_neigh[v][k];
+      }
+    }
+    adj[v] = a;
+  }
+}
+// longest path of one player searched by ONE group of lanes (host build: one lane) -- the block-cooperative caller
+// is slowpath_kernel.  scratch: CATAN_LP_SCRATCH_BYTES, 16-byte aligned.
+CATAN_FN int t_longest_path(const GameView& g, const Topo& T, int pid, uint8_t* scratch, int lane) {
+  uint64_t* adj = reinterpret_cast<uint64_t*>(scratch);
+  int32_t* ctl = reinterpret_cast<int32_t*>(scratch + CATAN_LP_ADJ_BYTES);
+  int32_t* best = reinterpret_cast<int32_t*>(scratch + CATAN_LP_TASK_OFF - 8);
+  LpTask* ring = reinterpret_cast<LpTask*>(scratch + CATAN_LP_TASK_OFF);
+  t_lp_build_adj(g, T, pid, adj, lane, CATAN_LANES);
+  if (lane == 0) *best = 0;
+  wsync();
+  CATAN_LP_RUN(adj, 1, ctl, best, scratch + CATAN_LP_PATH_OFF, CATAN_LANES, lane, ring, CATAN_LP_WARP_TASKS, CATAN_LP_BUDGET,
+               lane == 0, wsync(), (void)0);
+  wsync();
+  const int r = *best;
+  wsync();
+  return r;
+}
+CATAN_FN bool t_lr_is_shrunk(const GameView& g, int pid, int len) { return g.lr_holder() == pid && g.lr_count() > len; }
+
+// game.py:864-919 given the measured lengths: len of `pid`, and (only when shrunk) other_len[PlayerId] of the rest
+CATAN_FN_NOINLINE void t_lr_apply(const GameView& g, int pid, int len, bool shrunk, const uint8_t* other_len) {
+  const int holder = g.lr_holder(), count = g.lr_count();
+  g.cur_longest_path(pid - 1) = static_cast<uint8_t>(len);
+  g.has_path_key(pid - 1) = 1;
+  if (!holder) {
+    if (len >= 5) { g.lr_holder() = static_cast<uint8_t>(pid); g.lr_count() = static_cast<uint8_t>(len); g.vp(pid - 1) += 2; }
+  } else if (holder == pid) {
+    if (shrunk) {
+      int max_len = len, player = pid;
+      bool tied = false;
+      for (int o = WHITE; o <= RED; ++o) {                           // game.py:886 order White,Blue,Orange,Red
+        if (o == pid) continue;
+        const int pl = other_len[o];
+        if (pl == max_len) tied = true;
+        else if (pl > max_len) { max_len = pl; tied = false; player = o; }
+      }
+      if (max_len >= 5) {
+        if (tied) {
+          if (player == pid) g.lr_count() = static_cast<uint8_t>(len);
+          else { g.lr_holder() = 0; g.lr_count() = 0; g.vp(pid - 1) -= 2; }
+        } else {
+          g.lr_holder() = static_cast<uint8_t>(player); g.lr_count() = static_cast<uint8_t>(max_len);
+          g.vp(player - 1) += 2; g.vp(pid - 1) -= 2;
+        }
+      } else { g.lr_holder() = 0; g.lr_count() = 0; g.vp(pid - 1) -= 2; }
+    } else {
+      g.lr_count() = static_cast<uint8_t>(len);
+    }
+  } else if (len > count) {
+    g.vp(holder - 1) -= 2; g.vp(pid - 1) += 2;
+    g.lr_holder() = static_cast<uint8_t>(pid); g.lr_count() = static_cast<uint8_t>(len);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// done / reward / info (wrapper.py:85-112).  Returns true when the game ended and must be reset (cfg.auto_reset); the
+// reset itself is done by reset_game_group(), which then patches the two info bytes that describe the new game.
+// ------------------------------------------------------------------------------------------------
+CATAN_FN_NOINLINE bool t_step_finish(TCx& cx, const StepTmp& tmp, float* reward_out, uint8_t* info_out) {
+  const GameView& g = cx.g;
+  struct alignas(16) V16 { uint32_t w[4]; };
+  struct alignas(16) F4 { float v[4]; };
+  F4 rew = {{0.f, 0.f, 0.f, 0.f}};
+  const int err = tmp.err;
+  int done = 0, winner = g.winner();
+  int vp[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) vp[p] = g.vp(p);
+  if (!err) {
+    g.episode_steps() += 1;
+    // game.py:18-23: dict order Blue, Red, Orange, White; the LAST player with >= 10 VP becomes env.winner
+    if (vp[BLUE - 1] >= 10) { done = 1; winner = BLUE; }
+    if (vp[RED - 1] >= 10) { done = 1; winner = RED; }
+    if (vp[ORANGE - 1] >= 10) { done = 1; winner = ORANGE; }
+    if (vp[WHITE - 1] >= 10) { done = 1; winner = WHITE; }
+    if (done) g.winner() = static_cast<uint8_t>(winner);
+    if (cx.cfg->dense_reward) {                                      // wrapper.py:95-106
+      const int ty = tmp.act_type;
+      const double bonus = (ty == CATAN_ACT_PLAY_DEV ? 5.0 : 0.0) + (ty == CATAN_ACT_MOVE_ROBBER ? 1.0 : 0.0) -
+                           (ty == CATAN_ACT_DISCARD ? 0.3 : 0.0) + (ty == CATAN_ACT_UPGRADE_CITY ? 2.5 : 0.0);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        // python: ((5*dvp + 5) + 1 - 0.3 + 2.5) * factor with at most one bonus non-zero => same double value
+        const double r = (5.0 * static_cast<double>(vp[p] - g.curr_vps(p)) + bonus) * static_cast<double>(cx.cfg->reward_annealing_factor);
+        rew.v[p] = static_cast<float>(r);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) g.curr_vps(p) = static_cast<int8_t>(vp[p]);
+    if (done) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (p == winner - 1) rew.v[p] = static_cast<float>(static_cast<double>(rew.v[p]) + static_cast<double>(cx.cfg->win_reward));
+    }
+  }
+  const uint32_t actor = static_cast<uint32_t>(t_current_actor(g));   // game_manager.py:99 reads it before env.reset()
+  V16 info;
+  info.w[0] = static_cast<uint32_t>(done) | (static_cast<uint32_t>(winner) << 8) | (static_cast<uint32_t>(static_cast<uint8_t>(vp[0])) << 16) |
+              (static_cast<uint32_t>(static_cast<uint8_t>(vp[1])) << 24);
+  info.w[1] = static_cast<uint32_t>(static_cast<uint8_t>(vp[2])) | (static_cast<uint32_t>(static_cast<uint8_t>(vp[3])) << 8) | (actor << 16) |
+              (static_cast<uint32_t>(tmp.acted_pid) << 24);
+  info.w[2] = static_cast<uint32_t>(tmp.act_type) | (static_cast<uint32_t>(tmp.roll_info) << 8) | (static_cast<uint32_t>(err) << 16);
+  info.w[3] = actor;
+  *reinterpret_cast<F4*>(reward_out) = rew;
+  *reinterpret_cast<V16*>(info_out) = info;
+  return done && cx.cfg->auto_reset;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset: Board.reset (board.py:67-167) + Game.reset (game.py:39-136) + EnvWrapper.reset (wrapper.py:30-34), by a GROUP of
+// `nl` lanes (a warp on the device, one lane in the host build).  The game stream is counter based, so the lanes first
+// compute the next CATAN_RESET_WORDS draws in parallel; lane 0 then runs the (inherently serial) Fisher-Yates shuffles
+// over small arrays in `arr` and only falls back to computing single draws when the 6/8 rejection loop of board.py:80-81
+// needed more than that.  wbuf: CATAN_RESET_WORDS words, arr: 80 bytes, both private to the group (shared memory).
+// info_patch (may be null): info row of the step that ended the previous game; gets the new actor and RESET = 1.
+// ------------------------------------------------------------------------------------------------
+#define CATAN_RESET_WORDS 256
+struct ResetRng {
+  const uint32_t* wbuf;
+  uint32_t d_base, d;
+  uint64_t seed, env_id;
+};
+CATAN_FN uint32_t reset_rng_next(ResetRng& R) {
+  const uint32_t d = R.d++;
+  const uint32_t i = d - R.d_base;
+  if (i < CATAN_RESET_WORDS) return R.wbuf[i];
+  uint32_t w[4];
+  philox4x32(d >> 2, CATAN_STREAM_GAME, static_cast<uint32_t>(R.env_id), static_cast<uint32_t>(R.env_id >> 32),
+             static_cast<uint32_t>(R.seed), static_cast<uint32_t>(R.seed >> 32), w);
+  return w[d & 3];
+}
+CATAN_FN void reset_shuffle(ResetRng& R, uint8_t* a, int n) {
+  for (int i = n - 1; i >= 1; --i) {
+    const int j = static_cast<int>(mulhi32(reset_rng_next(R), static_cast<uint32_t>(i + 1)));
+    const uint8_t t = a[i]; a[i] = a[j]; a[j] = t;
+  }
+}
+#ifdef CATAN_DEVICE
+#define CATAN_GROUP_SYNC() __syncwarp()
+#else
+#define CATAN_GROUP_SYNC() ((void)0)
+#endif
+CATAN_FN_NOINLINE void reset_game_group(const GameView& g, const Topo& T, uint64_t seed, uint64_t env_id, uint32_t* wbuf, uint8_t* arr,
+                                        int lane, int nl, uint8_t* info_patch) {
+  const uint32_t rng = g.rng_ctr(), dec = g.decision_ctr();
+  CATAN_GROUP_SYNC();
+  // clear the record field-size wise (16- and 32-bit fields interleave in units of their own size); the two stream counters survive
+  for (int k = lane; k < static_cast<int>(offsetof(GameRec, rng_ctr) / 2); k += nl) g.at<int16_t>(0, k) = 0;
+  if (lane == 0) { g.episode_steps() = 0; g.actions_this_turn() = 0; g.turn() = 0; }
+  for (int k = static_cast<int>(offsetof(GameRec, corner)) + lane; k < static_cast<int>(sizeof(GameRec)); k += nl) g.at<uint8_t>(k, 0) = 0;
+  const uint32_t d_base = rng & ~3u;
+  for (int b = lane; b < CATAN_RESET_WORDS / 4; b += nl)
+    philox4x32((d_base >> 2) + b, CATAN_STREAM_GAME, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32),
+               static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), wbuf + 4 * b);
+  CATAN_GROUP_SYNC();
+  if (lane == 0) {
+    ResetRng R = {wbuf, d_base, rng, seed, env_id};
+    uint8_t* terrain = arr;            // 19
+    uint8_t* numbers = arr + 19;       // 18
+    uint8_t* harb = arr + 37;          // 9
+    uint8_t* order = arr + 46;         // 4
+    uint8_t* deck = arr + 50;          // 25
+    for (int i = 0; i < 19; ++i) terrain[i] = static_cast<uint8_t>(T.terrain_to_place[i]);
+    reset_shuffle(R, terrain, 19);                                   // board.py:71-72
+    for (int i = 0; i < 18; ++i) numbers[i] = static_cast<uint8_t>(T.default_number_order[i]);
+    reset_shuffle(R, numbers, 18);                                   // board.py:79
+    while (!number_order_ok(T, numbers, terrain)) reset_shuffle(R, numbers, 18);   // board.py:80-81
+    for (int i = 0; i < 9; ++i) harb[i] = static_cast<uint8_t>(i);
+    reset_shuffle(R, harb, 9);                                       // board.py:83-84
+    order[0] = WHITE; order[1] = BLUE; order[2] = ORANGE; order[3] = RED;
+    reset_shuffle(R, order, 4);                                      // game.py:41-42
+    for (int i = 0; i < 25; ++i) deck[i] = static_cast<uint8_t>(T.deck_init[i]);
+    reset_shuffle(R, deck, 25);                                      // game.py:75-78
+    g.rng_ctr() = R.d;
+    g.decision_ctr() = dec;
+    int n = 0;
+    for (int i = 0; i < 19; ++i) {                                   // board.py:88-100
+      const int t = T.number_placement[i];
+      g.tile_res(t) = terrain[t];
+      if (terrain[t] == 0) { g.tile_val(t) = 7; g.robber_tile() = static_cast<uint8_t>(t); }
+      else g.tile_val(t) = numbers[n++];
+    }
+    for (int i = 0; i < 9; ++i) g.harbour_perm(i) = harb[i];
+    for (int i = 0; i < 4; ++i) g.player_order(i) = order[i];
+    g.players_go() = order[0];
+    for (int r = 0; r < 5; ++r) g.bank(r) = 19;                      // game.py:48-54
+    for (int p = 0; p < 4; ++p) { g.settlements_left(p) = 5; g.cities_left(p) = 4; g.second_corner(p) = -1; }
+    for (int i = 0; i < 25; ++i) g.deck(i) = deck[i];
+    g.deck_n() = 25;
+    g.initial_phase() = 1;
+    if (info_patch) { info_patch[CATAN_INFO_ACTOR] = order[0]; info_patch[CATAN_INFO_RESET] = 1; }
+  }
+  CATAN_GROUP_SYNC();
+}
+
+// info row written by catan_reset / catan_import_state (no step happened)
+CATAN_FN void t_write_info_fresh(const GameView& g, uint8_t* info, bool was_reset) {
+  struct alignas(16) V16 { uint32_t w[4]; };
+  V16 v;
+  v.w[0] = (static_cast<uint32_t>(g.winner()) << 8) | (static_cast<uint32_t>(static_cast<uint8_t>(g.vp(0))) << 16) |
+           (static_cast<uint32_t>(static_cast<uint8_t>(g.vp(1))) << 24);
+  v.w[1] = static_cast<uint32_t>(static_cast<uint8_t>(g.vp(2))) | (static_cast<uint32_t>(static_cast<uint8_t>(g.vp(3))) << 8) |
+           (static_cast<uint32_t>(t_current_actor(g)) << 16);
+  v.w[2] = was_reset ? (1u << 24) : 0u;
+  v.w[3] = 0;
+  *reinterpret_cast<V16*>(info) = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// legal-action masks as BIT sets (wrapper.py:168-412): every head defaults to all ones except the
+// type head (wrapper.py:172-185)
+// ------------------------------------------------------------------------------------------------
+struct MaskBits {
+  uint64_t settle, city;     // rows 0 and 1 of the corner head (row 2 is never restricted)
+  uint64_t edge_lo;          // edges 0..63
+  uint32_t edge_hi;          // edges 64..71 and the dummy edge (bit 8)
+  uint32_t type, tile, dev, accept, player, res_a, res_b, discard;
+};
+#define CATAN_ALL54 ((1ull << 54) - 1ull)
+
+struct Boards {              // occupancy bit boards of one game seen by PlayerId pid
+  uint64_t bld, mine, mine_settle;
+  uint64_t e_any_lo, e_mine_lo;
+  uint32_t e_any_hi, e_mine_hi;
+};
+CATAN_FN_NOINLINE void t_load_boards(const GameView& g, int pid, Boards& B) {
+  uint64_t bld = 0, mine = 0, ms = 0;
+  CATAN_NO_UNROLL
+  for (int c0 = 0; c0 < 54; c0 += 6) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int c = c0 + j;
+      const uint32_t b = g.corner(c);
+      bld |= static_cast<uint64_t>(b != 0) << c;
+      mine |= static_cast<uint64_t>(b != 0 && (b >> 2) == static_cast<uint32_t>(pid)) << c;
+      ms |= static_cast<uint64_t>(b == static_cast<uint32_t>((pid << 2) | 1)) << c;
+    }
+  }
+  uint64_t ea = 0, em = 0;
+  CATAN_NO_UNROLL
+  for (int e0 = 0; e0 < 64; e0 += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = e0 + j;
+      const uint32_t b = g.edge(e);
+      ea |= static_cast<uint64_t>(b != 0) << e;
+      em |= static_cast<uint64_t>(b == static_cast<uint32_t>(pid)) << e;
+    }
+  }
+  uint32_t eah = 0, emh = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t b = g.edge(64 + j);
+    eah |= static_cast<uint32_t>(b != 0) << j;
+    emh |= static_cast<uint32_t>(b == static_cast<uint32_t>(pid)) << j;
+  }
+  B.bld = bld; B.mine = mine; B.mine_settle = ms; B.e_any_lo = ea; B.e_mine_lo = em; B.e_any_hi = eah; B.e_mine_hi = emh;
+}
+
+// corner.py:24-39 for all corners: settle_ok (without the "initial" waiver: needs an own road) and settle_free (distance
+// rule only); reach[c] = a road of pid may start from c (own building, or an own road at a corner without any building)
+CATAN_FN_NOINLINE void t_corner_scan(const TopoX& X, const Boards& B, uint64_t& settle_free, uint64_t& road_at, uint64_t& reach) {
+  uint64_t fre = 0, ra = 0;
+  CATAN_NO_UNROLL
+  for (int c = 0; c < 54; ++c) {
+    const bool blocked = ((X.corner_nb[c] | (1ull << c)) & B.bld) != 0;
+    const bool own_road = ((X.corner_edges_lo[c] & B.e_mine_lo) | static_cast<uint64_t>(X.corner_edges_hi[c] & B.e_mine_hi)) != 0;
+    fre |= static_cast<uint64_t>(!blocked) << c;
+    ra |= static_cast<uint64_t>(own_road) << c;
+  }
+  settle_free = fre; road_at = ra;
+  reach = B.mine | (~B.bld & ra);
+}
+
+// edge.py:23-42 for all edges; returns lo (edges 0..63) and hi (64..71)
+CATAN_FN_NOINLINE void t_road_scan(const Topo& T, const Boards& B, uint64_t reach, uint64_t& lo, uint32_t& hi) {
+  uint64_t l = 0;
+  uint32_t h = 0;
+  CATAN_NO_UNROLL
+  for (int e = 0; e < 64; ++e) {
+    const int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
+    l |= static_cast<uint64_t>(((reach >> c1) | (reach >> c2)) & 1ull) << e;
+  }
+#pragma unroll
+  for (int e = 64; e < 72; ++e) {
+    const int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
+    h |= static_cast<uint32_t>(((reach >> c1) | (reach >> c2)) & 1ull) << (e - 64);
+  }
+  lo = l & ~B.e_any_lo;
+  hi = h & ~B.e_any_hi & 0xffu;
+}
+
+CATAN_FN void t_mask_play_dev(const GameView& g, int p, MaskBits& m) {   // wrapper.py:221-228 / :262-269 / :368-388
+  if (g.n_hidden(p) == 0 || g.played_dev()) return;
+  const uint32_t counts = t_hidden_counts(g, p);
+  uint32_t bank_bits = 0;
+  int bank_total = 0;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) { const int b = g.bank(r); bank_total += b; bank_bits |= static_cast<uint32_t>(b > 0) << r; }
+  uint32_t valid = 0;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const int k = (counts >> (6 * c)) & 63;
+    if (k > 0 && g.bought(c) < k && (c != CATAN_DEV_YOP || bank_total > 0)) valid |= 1u << c;
+  }
+  if (!valid) return;
+  m.type |= 1u << CATAN_ACT_PLAY_DEV;
+  m.dev = valid;
+  if (valid & (1u << CATAN_DEV_YOP)) {                               // Q11: bank mask lands on row 2 of head 9 and on head 10
+    m.res_a = (m.res_a & ~(31u << 10)) | (bank_bits << 10);
+    m.res_b = bank_bits;
+  }
+}
+
+CATAN_FN_NOINLINE void t_build_masks(const TCx& cx, MaskBits& m) {
+  const GameView& g = cx.g;
+  const Topo& T = *cx.T;
+  m.type = 0; m.settle = CATAN_ALL54; m.city = CATAN_ALL54; m.edge_lo = ~0ull; m.edge_hi = 0x1ffu; m.tile = (1u << 19) - 1u;
+  m.dev = 31u; m.accept = 3u; m.player = 0x1ffu; m.res_a = 0xfffffu; m.res_b = 31u; m.discard = 31u;
+  const int pid = g.players_go(), p = pid - 1;
+  if (g.need_discard()) {                                            // wrapper.py:186-192
+    const int d = g.discard_queue(0);
+    m.type = 1u << CATAN_ACT_DISCARD;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) bits |= static_cast<uint32_t>(g.res(d - 1, r) != 0) << r;
+    m.discard = bits;
+    return;
+  }
+  const bool initial = g.initial_phase(), rb = g.rb_active();
+  if (!initial && !rb) {
+    if (g.just_moved_robber()) {                                     // wrapper.py:210-213, :341-351
+      m.type = 1u << CATAN_ACT_STEAL;
+      uint32_t row = 0;
+      const int rt = g.robber_tile();
+      for (int k = 0; k < 6; ++k) {
+        const uint8_t b = g.corner(T.tile_corners[rt][k]);
+        if (b && (b >> 2) != pid) row |= 1u << label_of(cx.s, pid, b >> 2);
+      }
+      m.player = (m.player & ~(7u << 3)) | (row << 3);
+      return;
+    }
+    if (g.must_respond()) {                                          // wrapper.py:214-218, :353-365
+      m.type = 1u << CATAN_ACT_RESPOND;
+      uint32_t cnt = 0;
+      const int nr = g.n_recv(), tt = g.trade_target() - 1;
+      for (int k = 0; k < nr; ++k) cnt += 1u << (4 * (g.recv(k) - 1));
+      bool ok = true;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) ok &= g.res(tt, r) >= static_cast<int>((cnt >> (4 * r)) & 15);
+      m.accept = 2u | static_cast<uint32_t>(ok);
+      return;
+    }
+    if (!g.dice_rolled()) {                                          // wrapper.py:219-229
+      m.type = 1u << CATAN_ACT_ROLL_DICE;
+      t_mask_play_dev(g, p, m);
+      return;
+    }
+  }
+  // the placement phases: initial (wrapper.py:195-204), road building (:206-209) and the main phase (:232-290)
+  int h[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) h[r] = g.res(p, r);
+  const bool capped = !initial && !rb && cx.cfg->max_actions_per_turn >= 0 && g.actions_this_turn() > cx.cfg->max_actions_per_turn;
+  const bool init_settle = initial && (g.init_settlements(p) == 0 || (g.init_settlements(p) == 1 && g.init_roads(p) == 1));
+  const bool want_settle = init_settle || (!initial && !rb && !capped && h[WHEAT] && h[SHEEP] && h[WOOD] && h[BRICK]);
+  const bool want_city = !initial && !rb && !capped && h[WHEAT] >= 2 && h[ORE] >= 3 && g.cities_left(p) > 0;
+  const bool want_road = (initial && !init_settle) || rb || (!initial && !capped && h[WOOD] && h[BRICK]);
+  if (!initial && !rb) m.type = 1u << CATAN_ACT_END_TURN;            // wrapper.py:232
+  if (want_settle || want_city || want_road) {
+    Boards B;
+    t_load_boards(g, pid, B);
+    uint64_t settle_free = 0, road_at = 0, reach = 0;
+    if (want_settle || want_road) t_corner_scan(*cx.X, B, settle_free, road_at, reach);
+    if (want_settle) {
+      if (init_settle) {
+        m.type = 1u << CATAN_ACT_PLACE_SETTLEMENT;
+        m.settle = settle_free;
+      } else {                                                       // wrapper.py:238-243
+        const uint64_t ok = settle_free & road_at;
+        if (ok && g.settlements_left(p) > 0) { m.type |= 1u << CATAN_ACT_PLACE_SETTLEMENT; m.settle = ok; }
+      }
+    }
+    if (want_city && B.mine_settle) { m.type |= 1u << CATAN_ACT_UPGRADE_CITY; m.city = B.mine_settle; }   // wrapper.py:245-250
+    if (want_road) {                                                 // wrapper.py:322-339
+      uint64_t lo;
+      uint32_t hi;
+      if (initial && g.init_settlements(p) == 2) {                   // the second road must touch the second settlement (edge.py:27-31)
+        const int sc = g.second_corner(p);
+        lo = cx.X->corner_edges_lo[sc] & ~B.e_any_lo;
+        hi = cx.X->corner_edges_hi[sc] & ~B.e_any_hi;
+      } else {
+        t_road_scan(T, B, reach, lo, hi);
+      }
+      const bool placed = (lo | hi) != 0;
+      if (initial) { m.type = 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi; }
+      else if (rb) { m.type = 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi | (placed ? 0u : 0x100u); }
+      else if (placed) { m.type |= 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi; }
+    }
+    if (initial || rb) return;
+    if (g.can_move_robber() && !capped) {                            // wrapper.py:278-281, :308-320 (Q1: any building)
+      uint32_t tl = 0;
+      CATAN_NO_UNROLL
+      for (int t = 0; t < 19; ++t) tl |= static_cast<uint32_t>((cx.X->tile_cmask[t] & B.bld) != 0) << t;
+      m.tile = tl;
+    }
+  } else if (g.can_move_robber() && !capped) {
+    uint32_t tl = 0;
+    CATAN_NO_UNROLL
+    for (int t = 0; t < 19; ++t) {
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) any |= g.corner(T.tile_corners[t][k]) != 0;
+      tl |= static_cast<uint32_t>(any) << t;
+    }
+    m.tile = tl;
+  }
+  if (capped) return;
+  if (h[WHEAT] && h[SHEEP] && h[ORE] && g.deck_n() > 0) m.type |= 1u << CATAN_ACT_BUY_DEV;
+  t_mask_play_dev(g, p, m);                                          // wrapper.py:262-269
+  {
+    uint32_t give = 0, get = 0;                                      // wrapper.py:271-276, :390-412 (Q13)
+    const int hb = g.harbours(p);
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int rate = (hb >> (r + 1)) & 1 ? 2 : ((hb & 1) ? 3 : 4);
+      give |= static_cast<uint32_t>(h[r] >= rate) << r;
+      get |= static_cast<uint32_t>(g.bank(r) > 0) << r;
+    }
+    if (give && get) {
+      m.type |= 1u << CATAN_ACT_EXCHANGE;
+      m.res_a = (m.res_a & ~31u) | give;
+      m.res_b = get;
+    }
+    if (h[0] + h[1] + h[2] + h[3] + h[4] > 0 &&                      // wrapper.py:283-289
+        (cx.cfg->max_proposed_trades_per_turn < 0 || g.trades_this_turn() < cx.cfg->max_proposed_trades_per_turn))
+      m.type |= 1u << CATAN_ACT_PROPOSE_TRADE;
+    if (g.can_move_robber()) m.type |= 1u << CATAN_ACT_MOVE_ROBBER;
+  }
+}
+
+// the 325 mask entries as one bit string (bit i = entry i of the packed row, catan_layout.h)
+struct MaskFlat { uint32_t w[11]; };
+template <int POS, int N>
+CATAN_FN void flat_put(MaskFlat& F, uint64_t v) {
+  constexpr int w0 = POS / 32, s = POS % 32;
+  F.w[w0] |= static_cast<uint32_t>(v << s);
+  if (s + N > 32) F.w[w0 + 1] |= static_cast<uint32_t>(v >> (32 - s));
+  if (s + N > 64) F.w[w0 + 2] |= static_cast<uint32_t>(v >> (64 - s));
+}
+CATAN_FN void t_flatten_masks(const MaskBits& m, MaskFlat& F) {
+#pragma unroll
+  for (int i = 0; i < 11; ++i) F.w[i] = 0;
+  flat_put<CATAN_MASK_TYPE, 13>(F, m.type);
+  flat_put<CATAN_MASK_CORNER, 54>(F, m.settle);
+  flat_put<CATAN_MASK_CORNER + 54, 54>(F, m.city);
+  flat_put<CATAN_MASK_CORNER + 108, 54>(F, CATAN_ALL54);
+  flat_put<CATAN_MASK_EDGE, 64>(F, m.edge_lo);
+  flat_put<CATAN_MASK_EDGE + 64, 9>(F, m.edge_hi);
+  flat_put<CATAN_MASK_TILE, 19>(F, m.tile);
+  flat_put<CATAN_MASK_DEV, 5>(F, m.dev);
+  flat_put<CATAN_MASK_ACCEPT, 2>(F, m.accept);
+  flat_put<CATAN_MASK_PLAYER, 9>(F, m.player);
+  flat_put<CATAN_MASK_GIVE, 12>(F, 0xfffu);
+  flat_put<CATAN_MASK_RES_A, 20>(F, m.res_a);
+  flat_put<CATAN_MASK_RES_B, 5>(F, m.res_b);
+  flat_put<CATAN_MASK_DISCARD, 5>(F, m.discard);
+}
+// bits -> one byte per entry: 4 bits -> the 4 bytes of a word
+CATAN_FN uint32_t spread4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
+CATAN_FN void t_store_mask_row(const MaskFlat& F, uint8_t* row) {   // row: CATAN_MASK_STRIDE bytes, 16-byte aligned
+  struct alignas(16) V16 { uint32_t a, b, c, d; };
+  V16* out = reinterpret_cast<V16*>(row);
+#pragma unroll
+  for (int j = 0; j < CATAN_MASK_STRIDE / 16; ++j) {
+    const uint32_t b = (F.w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+    V16 v = {spread4(b & 15u), spread4((b >> 4) & 15u), spread4((b >> 8) & 15u), spread4(b >> 12)};
+    out[j] = v;
+  }
+}
+// packed row -> bit sets (stand-alone sampler reading a mask row back)
+CATAN_FN void t_load_mask_row(const uint8_t* row, MaskBits& m) {
+  auto bits = [&](int pos, int n) {
+    uint64_t v = 0;
+    for (int i = 0; i < n; ++i) v |= static_cast<uint64_t>(row[pos + i] != 0) << i;
+    return v;
+  };
+  m.type = static_cast<uint32_t>(bits(CATAN_MASK_TYPE, 13));
+  m.settle = bits(CATAN_MASK_CORNER, 54); m.city = bits(CATAN_MASK_CORNER + 54, 54);
+  m.edge_lo = bits(CATAN_MASK_EDGE, 64); m.edge_hi = static_cast<uint32_t>(bits(CATAN_MASK_EDGE + 64, 9));
+  m.tile = static_cast<uint32_t>(bits(CATAN_MASK_TILE, 19)); m.dev = static_cast<uint32_t>(bits(CATAN_MASK_DEV, 5));
+  m.accept = static_cast<uint32_t>(bits(CATAN_MASK_ACCEPT, 2)); m.player = static_cast<uint32_t>(bits(CATAN_MASK_PLAYER, 9));
+  m.res_a = static_cast<uint32_t>(bits(CATAN_MASK_RES_A, 20)); m.res_b = static_cast<uint32_t>(bits(CATAN_MASK_RES_B, 5));
+  m.discard = static_cast<uint32_t>(bits(CATAN_MASK_DISCARD, 5));
+}
+
+// ------------------------------------------------------------------------------------------------
+// pinned random-legal sampler (twin of oracle/ref_harness.py:sample_action) on bit sets:
+// pick = index of the floor(w*k/2^32)-th set entry (k = number of set entries), 0 if none
+// ------------------------------------------------------------------------------------------------
+CATAN_FN int nth_set32(uint32_t m, int j) {
+#ifdef CATAN_DEVICE
+  return static_cast<int>(__fns(m, 0, j + 1));
+#else
+  for (int q = 0; q < j; ++q) m &= m - 1;
+  return __builtin_ctz(m);
+#endif
+}
+CATAN_FN int popc32(uint32_t m) {
+#ifdef CATAN_DEVICE
+  return __popc(m);
+#else
+  return __builtin_popcount(m);
+#endif
+}
+CATAN_FN int pick96(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t w) {
+  const int k0 = popc32(m0), k1 = popc32(m1), k = k0 + k1 + popc32(m2);
+  if (!k) return 0;
+  const int j = static_cast<int>(mulhi32(w, static_cast<uint32_t>(k)));
+  if (j < k0) return nth_set32(m0, j);
+  if (j < k0 + k1) return 32 + nth_set32(m1, j - k0);
+  return 64 + nth_set32(m2, j - k0 - k1);
+}
+CATAN_FN int pick32(uint32_t m, uint32_t w) { return pick96(m, 0u, 0u, w); }
+CATAN_FN int pick64(uint64_t m, uint32_t w) { return pick96(static_cast<uint32_t>(m), static_cast<uint32_t>(m >> 32), 0u, w); }
+
+// hand_bits: bit r set iff the acting player holds resource r (== obs current_resources[1..5] != 0, wrapper.py:70-71)
+CATAN_FN_NOINLINE void t_sample_action(const MaskBits& m, uint32_t hand_bits, uint64_t seed, uint64_t env_id, uint32_t decision, int32_t* out) {
+  uint32_t w[4];
+  philox4x32(decision, CATAN_STREAM_SAMPLER, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32),
+             static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), w);
+  const int t = pick32(m.type, w[0]);
+  int corner = 0, edge = 0, tile = 0, card = 0, accept = 0, player = 0, give = 0, recv = 0, res_a = 0, res_b = 0, discard = 0;
+  switch (t) {
+    case CATAN_ACT_PLACE_SETTLEMENT: corner = pick64(m.settle, w[1]); break;
+    case CATAN_ACT_UPGRADE_CITY: corner = pick64(m.city, w[1]); break;
+    case CATAN_ACT_PLACE_ROAD: edge = pick96(static_cast<uint32_t>(m.edge_lo), static_cast<uint32_t>(m.edge_lo >> 32), m.edge_hi, w[1]); break;
+    case CATAN_ACT_MOVE_ROBBER: tile = pick32(m.tile, w[1]); break;
+    case CATAN_ACT_PLAY_DEV:
+      card = pick32(m.dev, w[1]);
+      if (card == CATAN_DEV_MONOPOLY) res_a = pick32((m.res_a >> 10) & 31u, w[2]);
+      else if (card == CATAN_DEV_YOP) {
+        res_a = pick32((m.res_a >> 15) & 31u, w[2]);
+        res_b = pick32(m.res_b, w[3]);
+      }
+      break;
+    case CATAN_ACT_EXCHANGE:
+      res_a = pick32(m.res_a & 31u, w[1]);
+      res_b = pick32(m.res_b, w[2]);
+      break;
+    case CATAN_ACT_PROPOSE_TRADE:
+      player = pick32(m.player & 7u, w[1]);
+      give = 1 + pick32(hand_bits, w[2]);                            // a resource the proposer holds
+      recv = 1 + static_cast<int>(mulhi32(w[3], 5u));
+      break;
+    case CATAN_ACT_RESPOND: accept = pick32(m.accept, w[1]); break;
+    case CATAN_ACT_STEAL: player = pick32((m.player >> 3) & 7u, w[1]); break;
+    case CATAN_ACT_DISCARD: discard = pick32(m.discard, w[1]); break;
+    default: break;
+  }
+  struct alignas(16) I4 { int32_t a, b, c, d; };
+  I4* o = reinterpret_cast<I4*>(out);                                // 80-byte row, 16-byte aligned
+  const I4 r0 = {t, corner, edge, tile}, r1 = {card, accept, player, give}, r2 = {0, 0, 0, recv}, r3 = {0, 0, 0, res_a}, r4 = {res_b, discard, 0, 0};
+  o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4;
+}
+static_assert(CATAN_A_TYPE == 0 && CATAN_A_CORNER == 1 && CATAN_A_EDGE == 2 && CATAN_A_TILE == 3 && CATAN_A_CARD == 4 && CATAN_A_ACCEPT == 5 &&
+              CATAN_A_PLAYER == 6 && CATAN_A_GIVE == 7 && CATAN_A_RECV == 11 && CATAN_A_RES_A == 15 && CATAN_A_RES_B == 16 &&
+              CATAN_A_DISCARD == 17 && CATAN_ACTION_WORDS == 20, "t_sample_action packs the action row by hand");
+
+// ------------------------------------------------------------------------------------------------
+// observation (wrapper.py:52-83, :491-524, :526-709).
+//
+// A thread produces its row front to back through a small sliding window in shared memory (RowWriter): features are
+// scattered as bytes into the window, and every completed 16-byte piece leaves as one vector store.  The window of
+// thread t is word-interleaved with the other threads of the block (word w at ring[w * NT + t]), so every access of a
+// warp is bank-conflict free whatever the per-thread byte positions are.
+// ------------------------------------------------------------------------------------------------
+#define CATAN_RING_BYTES 128
+template <int NT>
+struct RowWriter {
+  uint32_t* ring;      // this thread's word 0
+  uint8_t* row;        // destination row (16-byte aligned)
+  int flushed;         // everything below this row offset (multiple of 16) has been written
+  CATAN_MFN uint8_t* byte_ptr(int p) const {
+    return reinterpret_cast<uint8_t*>(ring + ((p & (CATAN_RING_BYTES - 1)) >> 2) * NT) + (p & 3);
+  }
+  CATAN_MFN void init(uint32_t* r, uint8_t* dst) {
+    ring = r; row = dst; flushed = 0;
+#pragma unroll
+    for (int w = 0; w < CATAN_RING_BYTES / 4; ++w) ring[w * NT] = 0;
+  }
+  CATAN_MFN void put(int p, int v) const { *byte_ptr(p) = static_cast<uint8_t>(v); }
+  CATAN_MFN void add(int p, int v) const { uint8_t* q = byte_ptr(p); *q = static_cast<uint8_t>(*q + v); }
+  // write out (and clear) every complete 16-byte piece below `upto`; afterwards positions < upto + 112 are writable
+  CATAN_MFN void flush_to(int upto) {
+    struct alignas(16) V16 { uint32_t a, b, c, d; };
+    CATAN_NO_UNROLL
+    while (flushed + 16 <= upto) {
+      uint32_t* q = ring + ((flushed & (CATAN_RING_BYTES - 1)) >> 2) * NT;
+      const V16 v = {q[0], q[NT], q[2 * NT], q[3 * NT]};
+      *reinterpret_cast<V16*>(row + flushed) = v;
+      q[0] = 0; q[NT] = 0; q[2 * NT] = 0; q[3 * NT] = 0;
+      flushed += 16;
+    }
+  }
+};
+
+CATAN_FN int t_bucket8(int n) { return n < 5 ? n : (n < 8 ? 5 : (n < 11 ? 6 : 7)); }                        // wrapper.py:554-561
+CATAN_FN int t_bucket7(int n) { return n <= 2 ? n : (n <= 5 ? 3 : (n <= 7 ? 4 : (n <= 10 ? 5 : 6))); }       // wrapper.py:662-671
+
+template <int NT>
+CATAN_FN_NOINLINE void t_encode_obs(const TCx& cx, uint32_t* ring, uint8_t* row) {
+  const GameView& g = cx.g;
+  const Topo& T = *cx.T;
+  RowWriter<NT> W;
+  W.init(ring, row);
+  const int actor = t_current_actor(g), ap = actor - 1;
+  const int aseat = seat_of(cx.s, actor);
+  // REL(pid) = block of PlayerId pid seen from the actor (0 self, 1 next, ...), PID_AT(rel) = PlayerId rel seats after the actor
+  uint32_t relpack = 0;
+#pragma unroll
+  for (int p = 1; p <= 4; ++p) relpack |= static_cast<uint32_t>((seat_of(cx.s, p) - aseat + 4) & 3) << (2 * p);
+#define CATAN_REL(pid_) ((relpack >> (2 * (pid_))) & 3u)
+#define CATAN_PID_AT(rel_) pid_at_seat(cx.s, aseat + (rel_))
+  // ---- [0, 18): proposed trade (wrapper.py:61-69, Q15) and the actor's hand (wrapper.py:70-71)
+  if (g.trade_proposer()) {
+    const int ng = g.n_give(), nr = g.n_recv();
+    for (int k = 0; k < ng; ++k) W.put(CATAN_OBS_PROPOSED_TRADE + g.give(k), 1);
+    for (int k = 0; k < nr; ++k) W.put(CATAN_OBS_PROPOSED_TRADE + g.recv(k) + 5, 1);
+  }
+  int hand[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) { hand[r] = g.res(ap, r); W.put(CATAN_OBS_CURRENT_RES + 1 + r, hand[r]); }
+  // ---- tiles (wrapper.py:491-524); tinfo[t] keeps what the production tables need: slot (6 bits, 63 = desert) and the
+  // building weight (settlement 1, city 2) per relative owner, 4 bits each
+  uint32_t tinfo[19];
+  const int robber = g.robber_tile();
+  CATAN_NO_UNROLL
+  for (int t = 0; t < 19; ++t) {
+    const int base = CATAN_OBS_TILES + t * CATAN_OBS_TILE_DIM;
+    W.flush_to(base);
+    const int val = g.tile_val(t), tres = g.tile_res(t);
+    if (robber == t) W.put(base, 1);
+    W.put(base + 1 + val - 2, 1);
+    W.put(base + 12 + tres, 1);
+    // slot of resource index r in the obs order Wood,Brick,Wheat,Ore,Sheep (wrapper.py:550): BRICK->1 WOOD->0 ORE->3 SHEEP->4 WHEAT->2
+    uint32_t info = val == 7 ? 63u : static_cast<uint32_t>(((0x24301 >> (4 * (tres - 1))) & 7) * 10 + (val <= 6 ? val - 2 : val - 3));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const uint32_t b = g.corner(T.tile_corners[t][k]);
+      const int cf = base + 18 + k * 7;
+      W.put(cf + (b & 3), 1);                                        // none / settlement / city
+      if (b) {
+        const uint32_t rel = CATAN_REL(b >> 2);
+        W.put(cf + 3 + rel, 1);                                      // owner relative to the actor
+        info += (b & 3u) << (6 + 4 * rel);
+      }
+    }
+    tinfo[t] = info;
+  }
+  // ---- player blocks (wrapper.py:526-709)
+  const int lr_holder = g.lr_holder(), la_holder = g.la_holder();
+  CATAN_NO_UNROLL
+  for (int rel = 0; rel < 4; ++rel) {
+    const int target = CATAN_PID_AT(rel), tp = target - 1;
+    const int m = rel == 0 ? CATAN_OBS_CUR_MAIN : CATAN_OBS_OTHER_MAIN + (rel - 1) * CATAN_OBS_OTHER_MAIN_DIM;
+    const int c = m + (rel == 0 ? 40 : 80);                          // vp 10 | production 50 | road 2 | army 2 | harbours 6
+    W.flush_to(m);
+    if (rel == 0) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) W.put(m + ((0x24301 >> (4 * r)) & 7) * 8 + t_bucket8(hand[r]), 1);   // wrapper.py:550-562
+    } else {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {                                  // wrapper.py:563-585
+        const int slot = (0x24301 >> (4 * r)) & 7;
+        W.put(m + slot * 8 + t_bucket8(g.est_min(ap, rel - 1, r)), 1);
+        W.put(m + 40 + slot * 8 + t_bucket8(g.est_max(ap, rel - 1, r)), 1);
+      }
+      W.flush_to(c);
+    }
+    const int vps = g.vp(tp);
+    W.put(c + (vps < 10 ? vps : 9), 1);                              // wrapper.py:587-593
+    CATAN_NO_UNROLL
+    for (int t = 0; t < 19; ++t) {                                   // production table (wrapper.py:595-610)
+      const uint32_t info = tinfo[t];
+      const uint32_t cnt = (info >> (6 + 4 * rel)) & 15u;
+      if (cnt && (info & 63u) != 63u) W.add(c + 10 + (info & 63u), cnt);
+    }
+    if (rel == 0) W.flush_to(c + 60);
+    if (lr_holder) {                                                 // wrapper.py:613-620 (Q9)
+      if (lr_holder == target) { W.put(c + 60, 1); W.put(c + 61, g.lr_count()); }
+      else if (g.has_path_key(tp)) W.put(c + 61, g.cur_longest_path(tp));
+    }
+    if (la_holder == target) W.put(c + 62, 1);                       // wrapper.py:623-627 (Q10)
+    W.put(c + 63, g.cur_army(tp));
+    const int hb = g.harbours(tp);
+#pragma unroll
+    for (int b = 0; b < 6; ++b) W.put(c + 64 + b, (hb >> b) & 1);    // wrapper.py:632-637
+    if (rel == 0) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) W.put(m + 110 + ((0x24301 >> (4 * r)) & 7) * 7 + t_bucket7(g.bank(r)), 1);   // wrapper.py:657-672
+      W.put(m + 145 + t_bucket7(g.deck_n()), 1);                     // wrapper.py:674-686
+    } else {
+      W.put(m + 150 + rel - 1, 1);                                   // wrapper.py:532-541
+      const int nh = g.n_hidden(tp);
+      W.put(m + 153 + (nh <= 4 ? nh : 5), 1);                        // wrapper.py:690-695
+    }
+  }
+  // ---- development-card lists (wrapper.py:642-655) and the meta bytes
+  int n_list[5];
+  CATAN_NO_UNROLL
+  for (int li = 0; li < 5; ++li) {
+    const int lb = CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD;
+    W.flush_to(lb);
+    const int tp = (li < 2 ? actor : CATAN_PID_AT(li - 1)) - 1;
+    const int n = li == 1 ? g.n_hidden(tp) : g.n_played(tp);
+    n_list[li] = n;
+    if (li == 1) { for (int j = 0; j < n; ++j) W.put(lb + j, g.hidden(tp, j) + 1); }
+    else { for (int j = 0; j < n; ++j) W.put(lb + j, g.played(tp, j) + 1); }
+  }
+  W.flush_to(CATAN_OBS_META);
+  W.put(CATAN_OBS_META, actor);
+  W.put(CATAN_OBS_META + 1, n_list[0]);
+  W.put(CATAN_OBS_META + 2, n_list[1]);
+  W.put(CATAN_OBS_META + 3, n_list[2]);
+  W.put(CATAN_OBS_META + 4, n_list[3]);
+  W.put(CATAN_OBS_META + 5, n_list[4]);
+  W.flush_to(CATAN_OBS_STRIDE);
+#undef CATAN_REL
+#undef CATAN_PID_AT
+}
+
+}  // namespace catanb

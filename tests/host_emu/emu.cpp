@@ -1,39 +1,56 @@
-// TEST INFRASTRUCTURE — compiles the PRODUCT game core (settlers_of_catan_rl_b200/csrc/catan_core.cuh)
-// for the host with CATAN_LANES == 1 so the CPU test-suite can check the exact shipped logic against
-// the oracle and the golden fixtures without a GPU.  Never loaded by the product package.
+// TEST INFRASTRUCTURE — compiles the PRODUCT game core (settlers_of_catan_rl_b200/csrc/catan_game.cuh, the thread-per-game
+// engine) for the host with one game per "chunk" so the CPU test-suite can check the exact shipped logic against the
+// oracle and the golden fixtures without a GPU.  Never loaded by the product package.
 #define CATAN_HOST_EMU 1
 #ifndef CATAN_LP_BUDGET
 #define CATAN_LP_BUDGET 24   // tiny on purpose: the host emulation must exercise the subtree hand-off of lp_round
 #endif
-#include "../../settlers_of_catan_rl_b200/csrc/catan_core.cuh"
+#include "../../settlers_of_catan_rl_b200/csrc/catan_game.cuh"
 
 #include <stdlib.h>
 
 using namespace catanb;
 
 static const Topo h_topo = CATAN_TOPO_INITIALIZER;
+static TopoX h_topox;
+static bool h_topox_ready = false;
 
 struct EmuEnv {
   GameRec g;
-  WarpScratch ws;
-  uint8_t obs[CATAN_OBS_STRIDE];
-  uint8_t mask[CATAN_MASK_STRIDE];
+  alignas(16) uint8_t obs[CATAN_OBS_STRIDE];
+  alignas(16) uint8_t mask[CATAN_MASK_STRIDE];
   alignas(16) uint8_t scratch[CATAN_LP_SCRATCH_BYTES + 16];
+  uint32_t ring[CATAN_RING_BYTES / 4];
+  uint32_t wbuf[CATAN_RESET_WORDS];
+  uint8_t arr[96];
   catan_config_t cfg;
   uint64_t seed, env_id;
 };
 
-static Ctx make_ctx(EmuEnv* e) {
-  Ctx cx;
-  cx.g = &e->g; cx.T = &h_topo; cx.ws = &e->ws; cx.obs = e->obs; cx.mask = e->mask; cx.scratch = e->scratch; cx.cfg = &e->cfg;
-  cx.seed = e->seed; cx.env_id = e->env_id; cx.lane = 0;
+static TCx make_ctx(EmuEnv* e) {
+  if (!h_topox_ready) { build_topox(h_topo, h_topox, 0, 1); h_topox_ready = true; }
+  TCx cx;
+  cx.g.base = reinterpret_cast<uint8_t*>(&e->g); cx.g.lane = 0;
+  cx.T = &h_topo; cx.X = &h_topox; cx.cfg = &e->cfg; cx.seed = e->seed; cx.env_id = e->env_id;
+  cx.s = load_seats(cx.g);
   return cx;
+}
+
+static void encode(EmuEnv* e) {
+  TCx cx = make_ctx(e);
+  MaskBits m;
+  t_build_masks(cx, m);
+  MaskFlat F;
+  t_flatten_masks(m, F);
+  t_store_mask_row(F, e->mask);
+  t_encode_obs<1>(cx, e->ring, e->obs);
 }
 
 extern "C" {
 
 EmuEnv* emu_create(uint64_t seed, uint64_t env_id, const catan_config_t* cfg) {
-  EmuEnv* e = static_cast<EmuEnv*>(calloc(1, sizeof(EmuEnv)));
+  EmuEnv* e = static_cast<EmuEnv*>(aligned_alloc(64, (sizeof(EmuEnv) + 63) / 64 * 64));
+  memset(e, 0, sizeof(EmuEnv));
   e->seed = seed; e->env_id = env_id; e->cfg = *cfg;
   return e;
 }
@@ -41,36 +58,72 @@ void emu_destroy(EmuEnv* e) { free(e); }
 void emu_set_config(EmuEnv* e, const catan_config_t* cfg) { e->cfg = *cfg; }
 
 void emu_reset(EmuEnv* e) {
-  Ctx cx = make_ctx(e);
-  reset_game(cx);
-  encode_masks(cx);
-  encode_obs(cx);
+  TCx cx = make_ctx(e);
+  reset_game_group(cx.g, h_topo, e->seed, e->env_id, e->wbuf, e->arr, 0, 1, nullptr);
+  encode(e);
 }
 
 int emu_step(EmuEnv* e, const int32_t* action, float* reward, uint8_t* info) {
-  Ctx cx = make_ctx(e);
-  for (int i = 0; i < CATAN_ACTION_WORDS; ++i) e->ws.action[i] = action[i];
-  int err = step_game(cx, reward, info);
-  encode_masks(cx);
-  encode_obs(cx);
-  return err;
+  TCx cx = make_ctx(e);
+  StepTmp tmp;
+  t_step_transition(cx, action, tmp);
+  if (!tmp.err && tmp.lr_pid) {                                      // game.py:864-919
+    const int pid = tmp.lr_pid;
+    const int len = t_longest_path(cx.g, h_topo, pid, e->scratch, 0);
+    const bool shrunk = t_lr_is_shrunk(cx.g, pid, len);
+    uint8_t other_len[5] = {0, 0, 0, 0, 0};
+    if (shrunk) for (int o = WHITE; o <= RED; ++o) if (o != pid) other_len[o] = static_cast<uint8_t>(t_longest_path(cx.g, h_topo, o, e->scratch, 0));
+    t_lr_apply(cx.g, pid, len, shrunk, other_len);
+  }
+  alignas(16) float rew[4];
+  alignas(16) uint8_t inf[CATAN_INFO_STRIDE];
+  if (t_step_finish(cx, tmp, rew, inf)) reset_game_group(cx.g, h_topo, e->seed, e->env_id, e->wbuf, e->arr, 0, 1, inf);
+  memcpy(reward, rew, sizeof(rew));
+  memcpy(info, inf, sizeof(inf));
+  encode(e);
+  return tmp.err;
 }
 
 void emu_sample(EmuEnv* e, int32_t* action) {
-  sample_action(e->mask, e->obs + CATAN_OBS_CURRENT_RES + 1, e->seed, e->env_id, e->g.decision_ctr++, 0, action);
+  TCx cx = make_ctx(e);
+  MaskBits m;
+  t_load_mask_row(e->mask, m);                                       // the stand-alone sampler reads the packed row back
+  uint32_t hand = 0;
+  for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(e->obs[CATAN_OBS_CURRENT_RES + 1 + r] != 0) << r;
+  alignas(16) int32_t out[CATAN_ACTION_WORDS];
+  t_sample_action(m, hand, e->seed, e->env_id, e->g.decision_ctr++, out);
+  memcpy(action, out, sizeof(out));
 }
 
 const uint8_t* emu_obs(EmuEnv* e) { return e->obs; }
 const uint8_t* emu_masks(EmuEnv* e) { return e->mask; }
 void emu_export_state(EmuEnv* e, int16_t* out) { rec_to_state(e->g, *reinterpret_cast<catan_state_t*>(out)); }
 void emu_import_state(EmuEnv* e, const int16_t* in) {
-  Ctx cx = make_ctx(e);
   state_to_rec(*reinterpret_cast<const catan_state_t*>(in), e->g);
-  compute_seats(cx);
-  encode_masks(cx);
-  encode_obs(cx);
+  encode(e);
 }
-int emu_longest_path(EmuEnv* e, int pid) { Ctx cx = make_ctx(e); compute_seats(cx); return longest_path(cx, pid); }
+int emu_longest_path(EmuEnv* e, int pid) { TCx cx = make_ctx(e); return t_longest_path(cx.g, h_topo, pid, e->scratch, 0); }
 int emu_rec_bytes(void) { return static_cast<int>(sizeof(GameRec)); }
+
+// chunk <-> record round trip through a W-wide interleaved buffer (checks chunk_get / chunk_put, which the C ABI's
+// export / import use on the host)
+int emu_chunk_roundtrip(EmuEnv* e, int W, int lane) {
+  uint8_t* chunk = static_cast<uint8_t*>(calloc(sizeof(GameRec), static_cast<size_t>(W)));
+  GameRec back;
+  memset(&back, 0xee, sizeof(back));
+  chunk_put(chunk, lane, W, e->g);
+  chunk_get(chunk, lane, W, back);
+  int bad = memcmp(&back, &e->g, sizeof(GameRec)) != 0;
+  // no other lane's bytes may have been touched
+  GameRec other;
+  for (int l = 0; l < W && !bad; ++l) {
+    if (l == lane) continue;
+    chunk_get(chunk, l, W, other);
+    const uint8_t* o = reinterpret_cast<const uint8_t*>(&other);
+    for (size_t i = 0; i < sizeof(GameRec); ++i) bad |= o[i] != 0;
+  }
+  free(chunk);
+  return bad;
+}
 
 }  // extern "C"

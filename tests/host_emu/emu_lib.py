@@ -17,6 +17,7 @@ from oracle.oracle_lib import Config, make_config  # noqa: E402  (config struct 
 
 SO = os.path.join(_HERE, "libcatan_emu.so")
 _SRCS = [os.path.join(_HERE, "emu.cpp"), os.path.join(_ROOT, "settlers_of_catan_rl_b200", "csrc", "catan_core.cuh"),
+         os.path.join(_ROOT, "settlers_of_catan_rl_b200", "csrc", "catan_game.cuh"),
          os.path.join(_ROOT, "include", "catan_layout.h"), os.path.join(_ROOT, "include", "catan_topology.h")]
 
 
