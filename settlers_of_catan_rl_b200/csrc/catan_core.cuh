@@ -23,6 +23,7 @@
 #include "../../include/catan_topology.h"
 
 #if defined(__CUDACC__) && !defined(CATAN_HOST_EMU)
+#define CATAN_DEVICE 1
 #define CATAN_FN __device__ __forceinline__
 // phase-sized functions are emitted ONCE and called: the step kernel must stay small enough for the
 // instruction caches (profiles/r1_notes.md: 60% of stalls were stall_no_inst with everything inlined)

@@ -1,12 +1,19 @@
 // catan_kernels.cu — sm_100a kernels + C ABI of the vectorised Catan engine (see include/catan_b200.h).
 //
-// env_kernel: persistent, phase-major.  One 32-warp block per SM pulls a batch of 112 games: their
-// 832-byte packed records are copied (contiguous, coalesced) into shared memory and stay there while the
-// block walks through the phases of a step together -- translate/validate, scalar apply, dice payout,
-// belief updates, longest road, done/reward, masks(+sampler), observation -- one warp per game inside a
-// phase (catan_core.cuh).  Mask and observation rows are built in a per-warp staging row and leave
-// through the TMA engine as 1-D bulk async copies (cp.async.bulk.global.shared::cta).  The 1 KB board
-// topology is staged in shared memory once per block.
+// One env step is three launches on the caller's stream (catan_game.cuh holds the game logic):
+//
+//   transition_kernel   ONE THREAD PER GAME.  translate + validate + apply_action incl. dice payout and belief updates,
+//                       straight on the lane-interleaved game records in HBM/L2 (every field access of a warp is one
+//                       fully used 32-byte sector).  Games whose road network changed are appended to a device queue.
+//   longest_road_kernel the queued longest-road re-evaluations (game.py:843-919), searched block-cooperatively: the
+//                       node-simple path enumeration of all games of a batch is one pool of work units that 1024 lanes
+//                       drain in rounds (lp_round), so a dense road network cannot pin a lane -- or a warp of 32 games.
+//   encode_kernel       ONE THREAD PER GAME.  done / reward / info (+ auto-reset by the warp), legal-action masks as bit
+//                       sets, the fused random-legal sampler, and the packed observation row streamed out through a
+//                       128-byte sliding window per thread.
+//
+// Why not one fused kernel: the search is the only part of a step whose cost varies by four orders of magnitude between
+// games; inside a thread-per-game kernel it would stall 31 other games per unit of imbalance (profiles/r1_notes.md).
 #include <cuda_runtime.h>
 
 #include <cstddef>
@@ -16,348 +23,251 @@
 #include <vector>
 
 #include "../../include/catan_b200.h"
-#include "catan_core.cuh"
+#include "catan_game.cuh"
 
 namespace catanb {
 
 __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 
-// ---- launch shape -------------------------------------------------------------------------------
-// One persistent block of 32 warps per SM.  A block works on a BATCH of kBatch games whose packed
-// records stay in shared memory while the block walks through the phases of a step TOGETHER
-// (block barrier between phases).  At any time all 32 warps of an SM execute the same small phase
-// function, so the hot instruction footprint stays within the 32 KB instruction cache
-// (profiles/r1_notes.md: the fused warp-per-game pipeline spent 74% of its stall samples in
-// stall_no_inst).  Inside a phase each warp still owns one game at a time (lanes cooperate on it).
-constexpr int kWarps = 32;
-constexpr int kThreads = kWarps * 32;
-constexpr int kBlocksPerSM = 1;              // measured: 2 x 16 warps per SM is 8% slower (profiles/r1_notes.md)
-constexpr int kBatch = 96;                  // games per block iteration: 3 per warp (measured: 64 / 96 / 112 / 128 within 3% of each other)
-constexpr int kStageBytes = 2304;           // per-warp staging row: >= obs row, >= longest-road scratch
-constexpr int kSampleWarpsPerBlock = 4;     // stand-alone sampler kernel
-constexpr int kLpWarps = 32;                // warps that run the longest-road search (the rest wait at the phase barrier)
-constexpr int kLpBudget = 128;              // loop iterations per round before unfinished subtrees are re-queued
-constexpr int kMaxJobs = 39;                // longest-road graphs searched per cooperative pass (13 games x 3 when re-measuring)
-static_assert(kStageBytes >= CATAN_OBS_STRIDE && kStageBytes % 16 == 0, "staging row too small");
+// ---- launch shapes ------------------------------------------------------------------------------
+constexpr int kGameThreads = 64;            // transition / encode: threads (= games) per block; small blocks keep the
+                                            // 148 SMs evenly loaded at 65 536 games (1024 blocks ~ 7 per SM)
+constexpr int kLrThreads = 1024;            // longest_road_kernel: one persistent block per SM
+constexpr int kLrWarps = kLrThreads / 32;
+constexpr int kLpBudget = 128;              // loop iterations per search round before unfinished subtrees are re-queued
+constexpr int kMaxJobs = 39;                // road graphs searched per cooperative pass (13 games x 3 when re-measuring)
+constexpr int kLpRingTasks = 2048;          // per-block queue of re-split subtrees (global memory, L2 resident)
+constexpr int kSampleThreads = 128;         // stand-alone sampler kernel
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
+struct LrCtl { int32_t count, ticket; };    // queue length written by transition_kernel, batch ticket of longest_road_kernel
+
 struct EnvParams {
-  GameRec* recs;
+  uint8_t* recs;               // lane-interleaved chunks of 32 games (catan_game.cuh)
   int n_envs;
   uint64_t seed, first_env_id;
   catan_config_t cfg;
-  const int32_t* actions;      // MODE_STEP input
+  const int32_t* actions;      // transition input
   int32_t* actions_out;        // fused sampler output (may alias `actions`), or nullptr
   uint8_t* obs;
   uint8_t* masks;
   float* reward;
   uint8_t* info;
   uint32_t* err_flags;
-  const uint8_t* reset_mask;   // MODE_RESET / MODE_STEP: envs whose byte is 0 are left untouched; nullptr = all envs
+  const uint8_t* env_mask;     // envs whose byte is 0 are left untouched; nullptr = all envs
   int range_first, range_count;   // env range this launch covers
-  LpTask* lp_ring;                // [gridDim.x][kLpRingTasks] queue of re-split longest-road subtrees
-  unsigned int* ticket;           // device-wide batch ticket counter (never reset)
-  unsigned int ticket_base;       // value of *ticket when this launch starts
-  unsigned long long* prof;    // profiling build only
-  int lp_budget;               // loop iterations per search round (default kLpBudget; CATAN_LP_BUDGET overrides for tuning)
-  int debug_flags;             // timing experiments only (CATAN_DEBUG_FLAGS): 1 = skip longest-road search, 2 = skip obs encode, 4 = skip masks
+  uint32_t* side;              // [n] transition -> encode: err | acted_pid << 8 | act_type << 16 | roll << 24
+  uint32_t* lr_queue;          // [n] env index | PlayerId << 28
+  LrCtl* lr_ctl;
+  LpTask* lp_ring;             // [gridDim.x][kLpRingTasks]
+  int lp_budget;
 };
 
-struct alignas(16) BlockSmem {
+struct GameSmem {
   Topo topo;
-  GameRec recs[kBatch];
-  WarpScratch ws[kBatch];
-  uint8_t stage[kWarps][kStageBytes];
-  int32_t n_est, n_lr, n_shrunk, pad0_;
-  int32_t lp_counter, batch, pad_[2];
-  int32_t lp_best[kMaxJobs];   // block-cooperative longest-road search: result per job
-  int32_t lp_ctl[8];           // two sets of lp_round control words: claim counter, ring cursor, ring limit, ring base
-  uint8_t est_list[kBatch], lr_list[kBatch], shrunk_list[kBatch];
-  uint8_t skip[kBatch];        // games of the batch the env mask excludes: left untouched
+  TopoX topox;
 };
-static_assert(kBatch <= 4 * kWarps, "scalar phases map the games of a batch onto lanes 0..3 of the 32 warps");
-// the longest-road search borrows the whole staging area: 1024 path stacks, then kMaxJobs adjacency tables
-// the search borrows the staging area: path stacks of the kLpWarps searching warps | adjacency tables.  The queue of
-// re-split subtrees lives in a per-block ring in global memory (L2-resident, touched only when a unit is parked or
-// resumed): a shared-memory ring was too small -- once it filled up, lanes could not park and one dense network again
-// pinned a lane for milliseconds (profiles/r1_notes.md).
-constexpr int kLpPathBytes = 54 * kLpWarps * 32;
-constexpr int kLpAdjBytes = kMaxJobs * CATAN_LP_ADJ_BYTES;
-constexpr int kLpRingTasks = 2048;
-static_assert(kLpPathBytes % 8 == 0 && kLpPathBytes + kLpAdjBytes <= kWarps * kStageBytes, "longest-road scratch does not fit the staging area");
-static_assert(sizeof(BlockSmem) * kBlocksPerSM <= 227 * 1024, "block shared memory exceeds what kBlocksPerSM blocks can get on one SM");
 
-// ---- TMA 1-D bulk store helpers (SASS: UBLKCP) ---------------------------------------------------
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               :: "l"(gdst), "r"(static_cast<uint32_t>(__cvta_generic_to_shared(ssrc))), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// stage row (built by all lanes of the warp) -> global, through the TMA engine; the row may be reused
-// once bulk_wait_read_all() has returned
-__device__ __forceinline__ void stage_to_global(void* gdst, const void* ssrc, uint32_t bytes, int lane) {
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (lane == 0) { bulk_store(gdst, ssrc, bytes); bulk_commit(); }
-}
-__device__ __forceinline__ void stage_reuse_wait(int lane) {
-  if (lane == 0) bulk_wait_read_all();
-  __syncwarp();
+__device__ __forceinline__ void stage_topology(GameSmem& S, int tid, int nthreads) {
+  const int4* src = reinterpret_cast<const int4*>(&d_topo);
+  int4* dst = reinterpret_cast<int4*>(&S.topo);
+  for (int i = tid; i < static_cast<int>(sizeof(Topo) / 16); i += nthreads) dst[i] = src[i];
+  build_topox(d_topo, S.topox, tid, nthreads);
+  __syncthreads();
 }
 
-template <int MODE, bool SAMPLE>
-__global__ void __launch_bounds__(kThreads, kBlocksPerSM) env_kernel(const __grid_constant__ EnvParams P) {
+// ---- 1. transition ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGameThreads) transition_kernel(const __grid_constant__ EnvParams P) {
+  __shared__ __align__(16) GameSmem S;
+  stage_topology(S, threadIdx.x, kGameThreads);
+  const int i = (P.range_first & ~31) + blockIdx.x * kGameThreads + threadIdx.x;
+  if (i < P.range_first || i >= P.range_first + P.range_count) return;
+  if (P.env_mask != nullptr && P.env_mask[i] == 0) return;
+  TCx cx;
+  cx.g = game_view(P.recs, static_cast<size_t>(i));
+  cx.T = &S.topo; cx.X = &S.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
+  cx.s = load_seats(cx.g);
+  StepTmp tmp;
+  t_step_transition(cx, P.actions + static_cast<size_t>(i) * CATAN_ACTION_WORDS, tmp);
+  P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
+              (static_cast<uint32_t>(tmp.roll_info) << 24);
+  if (tmp.err) {
+    P.err_flags[i] |= 1u << tmp.err;
+  } else if (tmp.lr_pid) {
+    const int slot = atomicAdd(&P.lr_ctl->count, 1);
+    P.lr_queue[slot] = static_cast<uint32_t>(i) | (static_cast<uint32_t>(tmp.lr_pid) << 28);
+  }
+}
+
+// ---- 2. longest road ----------------------------------------------------------------------------
+struct alignas(16) LrSmem {
+  Topo topo;
+  uint64_t adj[kMaxJobs * 54];
+  uint8_t paths[54 * kLrThreads];
+  int32_t lp_best[kMaxJobs];
+  int32_t lp_ctl[8];
+  int32_t start, n_shrunk;
+  uint32_t entry[kMaxJobs];
+  uint8_t len[kMaxJobs], shrunk[kMaxJobs], shrunk_list[kMaxJobs];
+  uint8_t other[kMaxJobs][5];
+};
+
+__global__ void __launch_bounds__(kLrThreads, 1) longest_road_kernel(const __grid_constant__ EnvParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  BlockSmem& S = *reinterpret_cast<BlockSmem*>(smem_raw);
+  LrSmem& S = *reinterpret_cast<LrSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int count = P.lr_ctl->count;
+  if (count == 0) return;
   {
     const int4* src = reinterpret_cast<const int4*>(&d_topo);
     int4* dst = reinterpret_cast<int4*>(&S.topo);
-    for (int i = tid; i < static_cast<int>(sizeof(Topo) / 16); i += kThreads) dst[i] = src[i];
+    for (int i = tid; i < static_cast<int>(sizeof(Topo) / 16); i += kLrThreads) dst[i] = src[i];
   }
-  Ctx cx;
-  cx.T = &S.topo; cx.obs = S.stage[warp]; cx.mask = S.stage[warp]; cx.scratch = S.stage[warp]; cx.cfg = &P.cfg;
-  cx.seed = P.seed; cx.lane = lane;
-  cx.g = nullptr; cx.ws = nullptr; cx.env_id = 0;
-#ifdef CATAN_PROFILE_PHASES
-  cx.prof = P.prof; cx.prof_t = clock64();
-#endif
-  bool stage_busy = false;
-  const int n_batches = (P.range_count + kBatch - 1) / kBatch;
+  // jobs per claim: spread the queue over the blocks, at most kMaxJobs at a time
+  int per = (count + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  per = per < 1 ? 1 : (per > kMaxJobs ? kMaxJobs : per);
+  LpTask* ring = P.lp_ring + static_cast<size_t>(blockIdx.x) * kLpRingTasks;
   for (;;) {
-    // blocks claim batches from a device-wide ticket counter: an SM that drew an expensive batch simply takes
-    // fewer of them.  The counter is never reset: every launch makes exactly n_batches + gridDim.x claims, so the
-    // host advances ticket_base by that amount (launch_env).
-    __syncthreads();                                                 // previous batch fully retired; S.batch reusable
-    if (tid == 0) S.batch = static_cast<int32_t>(atomicAdd(P.ticket, 1u) - P.ticket_base);
+    __syncthreads();                                                 // previous batch retired; S.start reusable
+    if (tid == 0) { S.start = atomicAdd(&P.lr_ctl->ticket, per); S.n_shrunk = 0; }
     __syncthreads();
-    const int batch = S.batch;
-    if (batch >= n_batches) break;
-    const int base = P.range_first + batch * kBatch;                 // first env of this batch
-    const int nb = min(kBatch, P.range_first + P.range_count - base);
-    if (stage_busy) { stage_reuse_wait(lane); stage_busy = false; }  // the longest-road scratch aliases the staging row
-    // ---- phase 0: records -> shared memory (one contiguous, fully coalesced copy), actions -> scratch
-    {
-      const int4* src = reinterpret_cast<const int4*>(P.recs + base);
-      int4* dst = reinterpret_cast<int4*>(S.recs);
-      const int n16 = nb * static_cast<int>(sizeof(GameRec) / 16);
-      for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
-      if (MODE == MODE_STEP) {
-        const int32_t* a = P.actions + static_cast<size_t>(base) * CATAN_ACTION_WORDS;
-        for (int i = tid; i < nb * CATAN_ACTION_WORDS; i += kThreads) S.ws[i / CATAN_ACTION_WORDS].action[i % CATAN_ACTION_WORDS] = a[i];
-      }
-      for (int i = tid; i < nb; i += kThreads) S.skip[i] = MODE != MODE_REFRESH && P.reset_mask != nullptr && P.reset_mask[base + i] == 0;
-      if (tid == 0) { S.n_est = 0; S.n_lr = 0; S.n_shrunk = 0; }
+    const int start = S.start;
+    if (start >= count) break;
+    const int nj = min(per, count - start);
+    if (tid < nj) { S.entry[tid] = P.lr_queue[start + tid]; S.lp_best[tid] = 0; }
+    __syncthreads();
+    // pass A: the player whose road network changed
+    for (int j = warp; j < nj; j += kLrWarps) {
+      const uint32_t en = S.entry[j];
+      t_lp_build_adj(game_view(P.recs, en & 0x0fffffffu), S.topo, static_cast<int>(en >> 28), S.adj + j * 54, lane, 32);
     }
     __syncthreads();
-    CATAN_PROF(cx, PH_LOAD);
-#define CATAN_BIND(gi) do { cx.g = &S.recs[(gi)]; cx.ws = &S.ws[(gi)]; cx.env_id = P.first_env_id + static_cast<uint64_t>(base + (gi)); } while (0)
-    if (MODE == MODE_STEP) {
-      // scalar phases: game gi of the batch is handled by lane (gi / 32) of warp (gi % 32), so all 32 warps
-      // are busy and each warp instruction serves up to four games
-      const int sgi = warp + kWarps * lane;
-      const bool scalar_owner = lane < 4 && sgi < nb && !S.skip[sgi];
-      // ---- phase 1: translate + validate
-      // ---- phase 2: scalar part of apply_action; queue the lane-parallel follow-ups (same owner thread: no barrier)
-      if (scalar_owner) {
-        CATAN_BIND(sgi);
-        step_begin(cx);
-        WarpScratch& ws = *cx.ws;
-        if (ws.err) {
-          P.err_flags[base + sgi] |= 1u << ws.err;
-        } else {
-          apply_scalar(cx);
-          if (ws.dice_roll || ws.n_est || ws.est_special) S.est_list[atomicAdd(&S.n_est, 1)] = static_cast<uint8_t>(sgi);
-          if (ws.lr_pid) S.lr_list[atomicAdd(&S.n_lr, 1)] = static_cast<uint8_t>(sgi);
-        }
-      }
-      __syncthreads();
-      CATAN_PROF(cx, PH_SCALAR);
-      // ---- phase 3+4: dice payout (game.py:151-175) and belief updates (game.py:921-1010), warp per queued game
-      for (int i = warp; i < S.n_est; i += kWarps) {
-        CATAN_BIND(S.est_list[i]);
-        if (cx.ws->dice_roll) dice_payout(cx);
-        est_apply(cx);
-      }
-      __syncthreads();
-      CATAN_PROF(cx, PH_EST);
-      int lp_rounds_total = 0;
-      // ---- phase 5: longest road (game.py:843-919), searched by the WHOLE block: the work items of every
-      // queued game go into one pool that the searching warps drain in rounds, so one dense road network cannot stall the SM
-      {
-        uint8_t* lp_paths = &S.stage[0][0];
-        uint64_t* lp_adj = reinterpret_cast<uint64_t*>(&S.stage[0][0] + kLpPathBytes);
-        LpTask* lp_ring = P.lp_ring + static_cast<size_t>(blockIdx.x) * kLpRingTasks;
-        const int n_lr = (P.debug_flags & 1) ? 0 : S.n_lr;
-        int lp_rounds = 0;
-        for (int c0 = 0; c0 < n_lr; c0 += kMaxJobs) {                // pass A: the player whose road changed
-          const int nj = min(kMaxJobs, n_lr - c0);
-          for (int j = warp; j < nj; j += kWarps) {
-            const int gi = S.lr_list[c0 + j];
-            lp_build_adj(S.recs[gi], S.topo, S.ws[gi].lr_pid, lp_adj + j * 54, lane);
-          }
-          if (tid < nj) S.lp_best[tid] = 0;
-          __syncthreads();
-#ifdef CATAN_PROFILE_PHASES
-          const long long t_search0 = clock64();
-#endif
-          if (warp < kLpWarps) {                                     // rounds: unfinished subtrees are re-queued and re-split
-            CATAN_LP_RUN(lp_adj, nj, S.lp_ctl, S.lp_best, lp_paths, kLpWarps * 32, tid, lp_ring, kLpRingTasks, P.lp_budget, tid == 0,
-                         asm volatile("bar.sync 1, %0;" :: "n"(kLpWarps * 32) : "memory"), ++lp_rounds);
-          }
-          __syncthreads();
-#ifdef CATAN_PROFILE_PHASES
-          if (tid == 0) {   // pure search time per pass goes into the (otherwise unused) "dice" slot
-            const unsigned long long d = static_cast<unsigned long long>(clock64() - t_search0);
-            atomicAdd(&P.prof[PH_DICE * 4 + 0], d); atomicMax(&P.prof[PH_DICE * 4 + 1], d); atomicAdd(&P.prof[PH_DICE * 4 + 2], 1ull);
-          }
-#endif
-          if (tid < nj) {
-            const int gi = S.lr_list[c0 + tid];
-            WarpScratch& ws = S.ws[gi];
-            const int len = S.lp_best[tid];
-            ws.lr_len = static_cast<uint8_t>(len);
-            ws.lr_shrunk = lr_is_shrunk(S.recs[gi], ws.lr_pid, len);
-            if (ws.lr_shrunk) S.shrunk_list[atomicAdd(&S.n_shrunk, 1)] = static_cast<uint8_t>(gi);
-          }
-          __syncthreads();
-        }
-        const int n_sh = S.n_shrunk;
-        for (int c0 = 0; c0 < n_sh; c0 += kMaxJobs / 3) {            // pass B (rare): holder's path shrank -> the other three
-          const int nj = 3 * min(kMaxJobs / 3, n_sh - c0);
-          for (int j = warp; j < nj; j += kWarps) {
-            const int gi = S.shrunk_list[c0 + j / 3], pid = S.ws[gi].lr_pid;
-            int o = j % 3 + 1;
-            if (o >= pid) ++o;
-            lp_build_adj(S.recs[gi], S.topo, o, lp_adj + j * 54, lane);
-          }
-          if (tid < nj) S.lp_best[tid] = 0;
-          __syncthreads();
-#ifdef CATAN_PROFILE_PHASES
-          const long long t_search0 = clock64();
-#endif
-          if (warp < kLpWarps) {                                     // rounds: unfinished subtrees are re-queued and re-split
-            CATAN_LP_RUN(lp_adj, nj, S.lp_ctl, S.lp_best, lp_paths, kLpWarps * 32, tid, lp_ring, kLpRingTasks, P.lp_budget, tid == 0,
-                         asm volatile("bar.sync 1, %0;" :: "n"(kLpWarps * 32) : "memory"), ++lp_rounds);
-          }
-          __syncthreads();
-#ifdef CATAN_PROFILE_PHASES
-          if (tid == 0) {   // pure search time per pass goes into the (otherwise unused) "dice" slot
-            const unsigned long long d = static_cast<unsigned long long>(clock64() - t_search0);
-            atomicAdd(&P.prof[PH_DICE * 4 + 0], d); atomicMax(&P.prof[PH_DICE * 4 + 1], d); atomicAdd(&P.prof[PH_DICE * 4 + 2], 1ull);
-          }
-#endif
-          if (tid < nj) {
-            const int gi = S.shrunk_list[c0 + tid / 3], pid = S.ws[gi].lr_pid;
-            int o = tid % 3 + 1;
-            if (o >= pid) ++o;
-            S.ws[gi].lr_other[o] = static_cast<uint8_t>(S.lp_best[tid]);
-          }
-          __syncthreads();
-        }
-        lp_rounds_total = lp_rounds;
-        if (tid < n_lr) {
-          const int gi = S.lr_list[tid];
-          const WarpScratch& ws = S.ws[gi];
-          lr_apply(S.recs[gi], ws.lr_pid, ws.lr_len, ws.lr_shrunk != 0, ws.lr_other);
-        }
-      }
-      __syncthreads();
-#ifdef CATAN_PROFILE_PHASES
-      if (tid == 0 && lp_rounds_total > 0) {   // search rounds per batch go into the (otherwise unused) "sample" slot
-        atomicAdd(&P.prof[PH_SAMPLE * 4 + 0], static_cast<unsigned long long>(lp_rounds_total));
-        atomicMax(&P.prof[PH_SAMPLE * 4 + 1], static_cast<unsigned long long>(lp_rounds_total));
-        atomicAdd(&P.prof[PH_SAMPLE * 4 + 2], 1ull);
-      }
-#endif
-      CATAN_PROF(cx, PH_LROAD);
-      // ---- phase 6: done / reward / info (+ auto-reset).  Game gi is finished by lane gi/32 of warp gi%32, the
-      // warp that also encodes its masks and observation below, so a warp barrier is enough from here on.
-      if (scalar_owner) {
-        CATAN_BIND(sgi);
-        step_finish(cx, P.reward + static_cast<size_t>(base + sgi) * 4, P.info + static_cast<size_t>(base + sgi) * CATAN_INFO_STRIDE);
-      }
-      __syncwarp();
-      CATAN_PROF(cx, PH_FINISH);
-    } else {
-      const int gi = warp + kWarps * lane;
-      if (lane < 4 && gi < nb && !S.skip[gi]) {
-        CATAN_BIND(gi);
-        if (MODE == MODE_RESET) { reset_game(cx); cx.g->episode_steps = 0; }
-        else compute_seats(cx);
-        uint8_t* info = P.info + static_cast<size_t>(base + gi) * CATAN_INFO_STRIDE;
-        for (int i = 0; i < CATAN_INFO_STRIDE; ++i) info[i] = 0;
-        info[CATAN_INFO_ACTOR] = static_cast<uint8_t>(current_actor(*cx.g));
-        info[CATAN_INFO_WINNER] = cx.g->winner;
-        for (int p = 0; p < 4; ++p) info[CATAN_INFO_FINAL_VP + p] = static_cast<uint8_t>(cx.g->vp[p]);
-        info[CATAN_INFO_RESET] = MODE == MODE_RESET;
-      }
-      __syncwarp();
-    }
-    // ---- phase 7: legal-action masks (+ the next random-legal action), staged row -> TMA bulk store
-    for (int gi = warp; gi < nb; gi += kWarps) {
-      if (S.skip[gi]) continue;
-      CATAN_BIND(gi);
-      if (stage_busy) stage_reuse_wait(lane);
-      if (!(P.debug_flags & 4)) encode_masks(cx);
-      if (SAMPLE) {
-        const uint32_t decision = cx.g->decision_ctr;
-        __syncwarp();
-        sample_action(cx.mask, cx.g->res[current_actor(*cx.g) - 1], P.seed, cx.env_id, decision, lane,
-                      P.actions_out + static_cast<size_t>(base + gi) * CATAN_ACTION_WORDS);
-        if (lane == 0) cx.g->decision_ctr = decision + 1;
-      }
-      stage_to_global(P.masks + static_cast<size_t>(base + gi) * CATAN_MASK_STRIDE, cx.mask, CATAN_MASK_STRIDE, lane);
-      stage_busy = true;
-    }
-    CATAN_PROF(cx, PH_MASKS);
-    // ---- phase 8: packed observation, staged row -> TMA bulk store
-    for (int gi = warp; gi < nb; gi += kWarps) {
-      if (S.skip[gi]) continue;
-      CATAN_BIND(gi);
-      if (stage_busy) { stage_reuse_wait(lane); stage_busy = false; }
-      if (!(P.debug_flags & 2)) encode_obs(cx);
-      if (P.debug_flags & 8) {                                       // experiment: plain coalesced stores instead of the TMA engine
-        const int4* src = reinterpret_cast<const int4*>(cx.obs);
-        int4* dst = reinterpret_cast<int4*>(P.obs + static_cast<size_t>(base + gi) * CATAN_OBS_STRIDE);
-        for (int i = lane; i < CATAN_OBS_STRIDE / 16; i += 32) dst[i] = src[i];
-        __syncwarp();
-      } else {
-        stage_to_global(P.obs + static_cast<size_t>(base + gi) * CATAN_OBS_STRIDE, cx.obs, CATAN_OBS_STRIDE, lane);
-        stage_busy = true;
-      }
+    CATAN_LP_RUN(S.adj, nj, S.lp_ctl, S.lp_best, S.paths, kLrThreads, tid, ring, kLpRingTasks, P.lp_budget, tid == 0, __syncthreads(), (void)0);
+    __syncthreads();
+    if (tid < nj) {
+      const uint32_t en = S.entry[tid];
+      const int len = S.lp_best[tid];
+      const bool sh = t_lr_is_shrunk(game_view(P.recs, en & 0x0fffffffu), static_cast<int>(en >> 28), len);
+      S.len[tid] = static_cast<uint8_t>(len);
+      S.shrunk[tid] = sh;
+      if (sh) S.shrunk_list[atomicAdd(&S.n_shrunk, 1)] = static_cast<uint8_t>(tid);
     }
     __syncthreads();
-    CATAN_PROF(cx, PH_OBS);
-    // ---- phase 9: records -> global (contiguous, coalesced)
-    {
-      int4* dst = reinterpret_cast<int4*>(P.recs + base);
-      const int4* src = reinterpret_cast<const int4*>(S.recs);
-      const int n16 = nb * static_cast<int>(sizeof(GameRec) / 16);
-      for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
+    // pass B (rare, game.py:880-881): the holder's path shrank -> re-measure the other three players
+    const int n_sh = S.n_shrunk;
+    for (int c0 = 0; c0 < n_sh; c0 += kMaxJobs / 3) {
+      const int ng = min(kMaxJobs / 3, n_sh - c0), nb = 3 * ng;
+      for (int j = warp; j < nb; j += kLrWarps) {
+        const uint32_t en = S.entry[S.shrunk_list[c0 + j / 3]];
+        const int pid = static_cast<int>(en >> 28);
+        int o = j % 3 + 1;
+        if (o >= pid) ++o;
+        t_lp_build_adj(game_view(P.recs, en & 0x0fffffffu), S.topo, o, S.adj + j * 54, lane, 32);
+      }
+      if (tid < nb) S.lp_best[tid] = 0;
+      __syncthreads();
+      CATAN_LP_RUN(S.adj, nb, S.lp_ctl, S.lp_best, S.paths, kLrThreads, tid, ring, kLpRingTasks, P.lp_budget, tid == 0, __syncthreads(), (void)0);
+      __syncthreads();
+      if (tid < nb) {
+        const int job = S.shrunk_list[c0 + tid / 3];
+        const int pid = static_cast<int>(S.entry[job] >> 28);
+        int o = tid % 3 + 1;
+        if (o >= pid) ++o;
+        S.other[job][o] = static_cast<uint8_t>(S.lp_best[tid]);
+      }
+      __syncthreads();
     }
-    CATAN_PROF(cx, PH_STORE);
-#undef CATAN_BIND
+    if (tid < nj) {
+      const uint32_t en = S.entry[tid];
+      t_lr_apply(game_view(P.recs, en & 0x0fffffffu), static_cast<int>(en >> 28), S.len[tid], S.shrunk[tid] != 0, S.other[tid]);
+    }
   }
-  if (stage_busy && lane == 0) bulk_wait_all();
 }
 
-// stand-alone sampler: one warp per env, reads the bound mask/obs rows from global memory
-__global__ void __launch_bounds__(kSampleWarpsPerBlock * 32) sample_kernel(GameRec* recs, int n_envs, uint64_t seed, uint64_t first_env_id,
-                                                          const uint8_t* masks, const uint8_t* obs, int32_t* actions_out) {
-  const int lane = threadIdx.x & 31;
-  const int e = blockIdx.x * kSampleWarpsPerBlock + (threadIdx.x >> 5);
+// ---- 3. finish + masks + sampler + observation --------------------------------------------------
+struct alignas(16) EncSmem {
+  GameSmem topo;
+  uint32_t ring[(CATAN_RING_BYTES / 4) * kGameThreads];             // RowWriter windows, word-interleaved over the block
+  uint32_t wbuf[kGameThreads / 32][CATAN_RESET_WORDS];              // reset: pre-drawn Philox words, per warp
+  uint8_t arr[kGameThreads / 32][96];                               // reset: shuffle arrays, per warp
+};
+
+template <int MODE, bool SAMPLE>
+__global__ void __launch_bounds__(kGameThreads) encode_kernel(const __grid_constant__ EnvParams P) {
+  __shared__ EncSmem S;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  stage_topology(S.topo, tid, kGameThreads);
+  if (blockIdx.x == 0 && tid == 0) { P.lr_ctl->count = 0; P.lr_ctl->ticket = 0; }   // the queue of this step has been consumed
+  const int i = (P.range_first & ~31) + blockIdx.x * kGameThreads + tid;
+  const bool valid = i >= P.range_first && i < P.range_first + P.range_count && !(MODE != MODE_REFRESH && P.env_mask != nullptr && P.env_mask[i] == 0);
+  TCx cx;
+  cx.g = game_view(P.recs, static_cast<size_t>(valid ? i : P.range_first));
+  cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
+  uint8_t* info = P.info + static_cast<size_t>(i) * CATAN_INFO_STRIDE;
+  bool need_reset = false;
+  if (MODE == MODE_STEP) {
+    if (valid) {
+      cx.s = load_seats(cx.g);
+      const uint32_t sd = P.side[i];
+      StepTmp tmp;
+      tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
+      tmp.roll_info = static_cast<uint8_t>(sd >> 24);
+      need_reset = t_step_finish(cx, tmp, P.reward + static_cast<size_t>(i) * 4, info);
+    }
+  } else if (MODE == MODE_RESET) {
+    need_reset = valid;
+  }
+  if (MODE != MODE_REFRESH) {
+    // Board.reset + Game.reset are a handful of serial shuffles: the warp does them game by game (lanes pre-draw the
+    // Philox words in parallel).  Rare in a step (a game ends every ~1500 steps), everything in catan_reset.
+    unsigned rb = __ballot_sync(0xffffffffu, need_reset);
+    const int warp_first = i - lane;
+    while (rb) {
+      const int b = __ffs(static_cast<int>(rb)) - 1;
+      rb &= rb - 1;
+      const int e = warp_first + b;
+      reset_game_group(game_view(P.recs, static_cast<size_t>(e)), S.topo.topo, P.seed, P.first_env_id + static_cast<uint64_t>(e), S.wbuf[warp], S.arr[warp],
+                       lane, 32, MODE == MODE_STEP ? P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE : nullptr);
+    }
+  }
+  if (!valid) return;
+  if (MODE != MODE_STEP || need_reset) cx.s = load_seats(cx.g);
+  if (MODE != MODE_STEP) t_write_info_fresh(cx.g, info, MODE == MODE_RESET);
+  MaskBits m;
+  t_build_masks(cx, m);
+  {
+    MaskFlat F;
+    t_flatten_masks(m, F);
+    t_store_mask_row(F, P.masks + static_cast<size_t>(i) * CATAN_MASK_STRIDE);
+  }
+  if (SAMPLE) {
+    const int ap = t_current_actor(cx.g) - 1;
+    uint32_t hand = 0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(cx.g.res(ap, r) != 0) << r;
+    const uint32_t decision = cx.g.decision_ctr();
+    cx.g.decision_ctr() = decision + 1;
+    t_sample_action(m, hand, P.seed, cx.env_id, decision, P.actions_out + static_cast<size_t>(i) * CATAN_ACTION_WORDS);
+  }
+  t_encode_obs<kGameThreads>(cx, S.ring + tid, P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE);
+}
+
+// stand-alone sampler: one thread per env, reads the bound mask / obs rows back from global memory
+__global__ void __launch_bounds__(kSampleThreads) sample_kernel(uint8_t* recs, int n_envs, uint64_t seed, uint64_t first_env_id,
+                                                                const uint8_t* masks, const uint8_t* obs, int32_t* actions_out) {
+  const int e = blockIdx.x * kSampleThreads + threadIdx.x;
   if (e >= n_envs) return;
-  uint32_t dec = 0;
-  if (lane == 0) { dec = recs[e].decision_ctr; recs[e].decision_ctr = dec + 1; }
-  dec = __shfl_sync(0xffffffffu, dec, 0);
-  sample_action(masks + static_cast<size_t>(e) * CATAN_MASK_STRIDE, obs + static_cast<size_t>(e) * CATAN_OBS_STRIDE + CATAN_OBS_CURRENT_RES + 1, seed,
-                first_env_id + static_cast<uint64_t>(e), dec, lane, actions_out + static_cast<size_t>(e) * CATAN_ACTION_WORDS);
+  const GameView g = game_view(recs, static_cast<size_t>(e));
+  MaskBits m;
+  t_load_mask_row(masks + static_cast<size_t>(e) * CATAN_MASK_STRIDE, m);
+  const uint8_t* cur = obs + static_cast<size_t>(e) * CATAN_OBS_STRIDE + CATAN_OBS_CURRENT_RES + 1;
+  uint32_t hand = 0;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(cur[r] != 0) << r;
+  const uint32_t dec = g.decision_ctr();
+  g.decision_ctr() = dec + 1;
+  t_sample_action(m, hand, seed, first_env_id + static_cast<uint64_t>(e), dec, actions_out + static_cast<size_t>(e) * CATAN_ACTION_WORDS);
 }
 
 }  // namespace catanb
@@ -378,17 +288,20 @@ struct catan_env {
   int n = 0, device = 0, sm_count = 0;
   uint64_t seed = 0, first_env_id = 0;
   catan_config_t cfg{};
-  GameRec* recs = nullptr;
+  uint8_t* recs = nullptr;            // ceil(n / 32) lane-interleaved chunks
+  size_t rec_bytes = 0;
   uint32_t* err_flags = nullptr;
+  uint32_t* side = nullptr;
+  uint32_t* lr_queue = nullptr;
+  catanb::LrCtl* lr_ctl = nullptr;
   int32_t* actions_stage = nullptr;   // device staging for catan_step_host
   catanb::LpTask* lp_ring = nullptr;  // per-block task rings of the longest-road search
-  unsigned int* ticket = nullptr;     // batch ticket counter of the persistent kernel
-  unsigned int ticket_base = 0;
   uint8_t* obs = nullptr;
   uint8_t* masks = nullptr;
   float* reward = nullptr;
   uint8_t* info = nullptr;
-  int grid = 0;
+  int lr_grid = 0;
+  int lp_budget = catanb::kLpBudget;
 };
 
 static int device_guard(const catan_env* env) {
@@ -398,52 +311,48 @@ static int device_guard(const catan_env* env) {
   return 0;
 }
 
-#ifdef CATAN_PROFILE_PHASES
-static unsigned long long* g_prof_dev = nullptr;
-extern "C" int catan_prof_read(unsigned long long* out_host, int clear) {   // profiling build only; not part of the ABI
-  if (!g_prof_dev) return -1;
-  cudaDeviceSynchronize();
-  cudaMemcpy(out_host, g_prof_dev, sizeof(unsigned long long) * catanb::PH_COUNT * 4, cudaMemcpyDeviceToHost);
-  if (clear) cudaMemset(g_prof_dev, 0, sizeof(unsigned long long) * catanb::PH_COUNT * 4);
-  return 0;
-}
-#endif
-
 static EnvParams make_params(const catan_env* env) {
   EnvParams P{};
-#ifdef CATAN_PROFILE_PHASES
-  if (!g_prof_dev) { cudaMalloc(&g_prof_dev, sizeof(unsigned long long) * catanb::PH_COUNT * 4); cudaMemset(g_prof_dev, 0, sizeof(unsigned long long) * catanb::PH_COUNT * 4); }
-  P.prof = g_prof_dev;
-#endif
   P.recs = env->recs; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
   P.obs = env->obs; P.masks = env->masks; P.reward = env->reward; P.info = env->info; P.err_flags = env->err_flags;
-  { const char* d = getenv("CATAN_DEBUG_FLAGS"); P.debug_flags = d ? atoi(d) : 0; }
-  { const char* d = getenv("CATAN_LP_BUDGET"); P.lp_budget = d && atoi(d) > 0 ? atoi(d) : catanb::kLpBudget; }
+  P.side = env->side; P.lr_queue = env->lr_queue; P.lr_ctl = env->lr_ctl; P.lp_ring = env->lp_ring; P.lp_budget = env->lp_budget;
   return P;
 }
 
+static int game_blocks(int first, int count) {   // blocks of kGameThreads covering [first & ~31, first + count)
+  const int span = first + count - (first & ~31);
+  return (span + catanb::kGameThreads - 1) / catanb::kGameThreads;
+}
+
 template <int MODE, bool SAMPLE>
-static int launch_env(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
-  const size_t smem = sizeof(catanb::BlockSmem);
-  // opt in to > 48 KB of dynamic shared memory (per kernel instantiation and device; cheap, so done every time)
-  CATAN_CUDA(cudaFuncSetAttribute(catanb::env_kernel<MODE, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+static int launch_encode(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
   P.range_first = first; P.range_count = count;
-  int blocks = (count + catanb::kBatch - 1) / catanb::kBatch;
-  if (blocks > env->grid) blocks = env->grid;                       // persistent: one 1024-thread block per SM
-  if (blocks < 1) blocks = 1;
-  P.ticket = env->ticket;
-  P.lp_ring = env->lp_ring;
-  P.ticket_base = env->ticket_base;
-  env->ticket_base += static_cast<unsigned int>((count + catanb::kBatch - 1) / catanb::kBatch + blocks);   // claims this launch makes
-  catanb::env_kernel<MODE, SAMPLE><<<blocks, catanb::kThreads, smem, stream>>>(P);
+  if (count <= 0) return 0;
+  catanb::encode_kernel<MODE, SAMPLE><<<game_blocks(first, count), catanb::kGameThreads, 0, stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <bool SAMPLE>
+static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
+  P.range_first = 0; P.range_count = env->n;
+  catanb::transition_kernel<<<game_blocks(0, env->n), catanb::kGameThreads, 0, stream>>>(P);
+  CATAN_CUDA(cudaGetLastError());
+  catanb::longest_road_kernel<<<env->lr_grid, catanb::kLrThreads, sizeof(catanb::LrSmem), stream>>>(P);
+  CATAN_CUDA(cudaGetLastError());
+  return launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream);
 }
 
 static int check_bound(const catan_env* env) {
   if (!env) return fail("null handle");
   if (!env->obs || !env->masks || !env->reward || !env->info) return fail("catan_bind has not been called");
   return 0;
+}
+
+static void free_env(catan_env* env) {
+  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_queue); cudaFree(env->lr_ctl);
+  cudaFree(env->actions_stage); cudaFree(env->lp_ring);
+  delete env;
 }
 
 extern "C" {
@@ -471,6 +380,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   if (!out) return fail("out is null");
   *out = nullptr;
   if (n_envs <= 0) return fail("n_envs must be positive");
+  if (n_envs >= (1 << 28)) return fail("n_envs must be below 2^28");
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) return fail("no CUDA device available: this library has no CPU path");
@@ -483,19 +393,26 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   cudaDeviceProp prop{};
   CATAN_CUDA(cudaGetDeviceProperties(&prop, device));
   env->sm_count = prop.multiProcessorCount;
-  env->grid = env->sm_count * catanb::kBlocksPerSM;   // persistent blocks (shared-memory bound)
-  e = cudaMalloc(&env->recs, sizeof(GameRec) * static_cast<size_t>(n_envs));
-  if (e == cudaSuccess) e = cudaMemset(env->recs, 0, sizeof(GameRec) * static_cast<size_t>(n_envs));
-  if (e == cudaSuccess) e = cudaMalloc(&env->err_flags, sizeof(uint32_t) * static_cast<size_t>(n_envs));
-  if (e == cudaSuccess) e = cudaMemset(env->err_flags, 0, sizeof(uint32_t) * static_cast<size_t>(n_envs));
-  if (e == cudaSuccess) e = cudaMalloc(&env->actions_stage, sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(n_envs));
-  if (e == cudaSuccess) e = cudaMalloc(&env->lp_ring, sizeof(catanb::LpTask) * catanb::kLpRingTasks * static_cast<size_t>(env->grid));
-  if (e == cudaSuccess) e = cudaMalloc(&env->ticket, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(env->ticket, 0, sizeof(unsigned int));
+  env->lr_grid = env->sm_count;                        // persistent search blocks: one per SM
+  { const char* d = getenv("CATAN_LP_BUDGET"); if (d && atoi(d) > 0) env->lp_budget = atoi(d); }
+  env->rec_bytes = CATAN_CHUNK_BYTES * ((static_cast<size_t>(n_envs) + 31) / 32);
+  const size_t n = static_cast<size_t>(n_envs);
+  e = cudaMalloc(&env->recs, env->rec_bytes);
+  if (e == cudaSuccess) e = cudaMemset(env->recs, 0, env->rec_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&env->err_flags, sizeof(uint32_t) * n);
+  if (e == cudaSuccess) e = cudaMemset(env->err_flags, 0, sizeof(uint32_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&env->side, sizeof(uint32_t) * n);
+  if (e == cudaSuccess) e = cudaMemset(env->side, 0, sizeof(uint32_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&env->lr_queue, sizeof(uint32_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&env->lr_ctl, sizeof(catanb::LrCtl));
+  if (e == cudaSuccess) e = cudaMemset(env->lr_ctl, 0, sizeof(catanb::LrCtl));
+  if (e == cudaSuccess) e = cudaMalloc(&env->actions_stage, sizeof(int32_t) * CATAN_ACTION_WORDS * n);
+  if (e == cudaSuccess) e = cudaMalloc(&env->lp_ring, sizeof(catanb::LpTask) * catanb::kLpRingTasks * static_cast<size_t>(env->lr_grid));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::longest_road_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(sizeof(catanb::LrSmem)));
   if (e != cudaSuccess) {
-    cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage); cudaFree(env->ticket); cudaFree(env->lp_ring);
-    delete env;
-    return cuda_fail(e, "cudaMalloc(game records)");
+    free_env(env);
+    return cuda_fail(e, "catan_create");
   }
   *out = env;
   return 0;
@@ -503,8 +420,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
 
 int catan_destroy(catan_env_t* env) {
   if (!env) return 0;
-  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->actions_stage); cudaFree(env->ticket); cudaFree(env->lp_ring);
-  delete env;
+  free_env(env);
   return 0;
 }
 
@@ -530,8 +446,8 @@ int catan_reset(catan_env_t* env, const uint8_t* reset_mask_dev, void* stream) {
   if (check_bound(env)) return -1;
   if (device_guard(env)) return -1;
   EnvParams P = make_params(env);
-  P.reset_mask = reset_mask_dev;
-  return launch_env<catanb::MODE_RESET, false>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
+  P.env_mask = reset_mask_dev;
+  return launch_encode<catanb::MODE_RESET, false>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
 }
 
 int catan_step(catan_env_t* env, const int32_t* actions_dev, void* stream) { return catan_step_masked(env, actions_dev, nullptr, stream); }
@@ -542,8 +458,8 @@ int catan_step_masked(catan_env_t* env, const int32_t* actions_dev, const uint8_
   if (device_guard(env)) return -1;
   EnvParams P = make_params(env);
   P.actions = actions_dev;
-  P.reset_mask = step_mask_dev;
-  return launch_env<catanb::MODE_STEP, false>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
+  P.env_mask = step_mask_dev;
+  return launch_step<false>(env, P, static_cast<cudaStream_t>(stream));
 }
 
 int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream) {
@@ -553,15 +469,15 @@ int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream) {
   EnvParams P = make_params(env);
   P.actions = actions_io_dev;
   P.actions_out = actions_io_dev;
-  return launch_env<catanb::MODE_STEP, true>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
+  return launch_step<true>(env, P, static_cast<cudaStream_t>(stream));
 }
 
 int catan_sample_random(catan_env_t* env, int32_t* actions_out_dev, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_out_dev) return fail("actions_out_dev is null");
   if (device_guard(env)) return -1;
-  const int blocks = (env->n + catanb::kSampleWarpsPerBlock - 1) / catanb::kSampleWarpsPerBlock;
-  catanb::sample_kernel<<<blocks, catanb::kSampleWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int blocks = (env->n + catanb::kSampleThreads - 1) / catanb::kSampleThreads;
+  catanb::sample_kernel<<<blocks, catanb::kSampleThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       env->recs, env->n, env->seed, env->first_env_id, env->masks, env->obs, actions_out_dev);
   CATAN_CUDA(cudaGetLastError());
   return 0;
@@ -595,15 +511,32 @@ int catan_reset_host(catan_env_t* env, uint8_t* obs_host, uint8_t* masks_host, u
   return copy_outputs_to_host(env, obs_host, masks_host, nullptr, info_host, static_cast<cudaStream_t>(stream));
 }
 
+// the chunks [first / 32, (first + count - 1) / 32] of the record array <-> host
+static int chunk_range(const catan_env* env, int first, int count, size_t& off, size_t& bytes) {
+  const size_t c0 = static_cast<size_t>(first) / 32, c1 = static_cast<size_t>(first + count - 1) / 32;
+  off = c0 * CATAN_CHUNK_BYTES;
+  bytes = (c1 - c0 + 1) * CATAN_CHUNK_BYTES;
+  return off + bytes <= env->rec_bytes ? 0 : fail("env range out of bounds");
+}
+
 int catan_export_state(catan_env_t* env, int first, int count, int16_t* states_host) {
   if (!env || !states_host) return fail("null argument");
   if (first < 0 || count < 0 || first + count > env->n) return fail("env range out of bounds");
+  if (count == 0) return 0;
   if (device_guard(env)) return -1;
-  std::vector<GameRec> tmp(static_cast<size_t>(count));
+  size_t off, bytes;
+  if (chunk_range(env, first, count, off, bytes)) return -1;
+  std::vector<uint8_t> tmp(bytes);
   CATAN_CUDA(cudaDeviceSynchronize());
-  CATAN_CUDA(cudaMemcpy(tmp.data(), env->recs + first, sizeof(GameRec) * static_cast<size_t>(count), cudaMemcpyDeviceToHost));
+  CATAN_CUDA(cudaMemcpy(tmp.data(), env->recs + off, bytes, cudaMemcpyDeviceToHost));
   catan_state_t* out = reinterpret_cast<catan_state_t*>(states_host);
-  for (int i = 0; i < count; ++i) catanb::rec_to_state(tmp[static_cast<size_t>(i)], out[i]);
+  const int base = first & ~31;
+  for (int i = 0; i < count; ++i) {
+    const int e = first + i - base;
+    GameRec rec;
+    catanb::chunk_get(tmp.data() + static_cast<size_t>(e / 32) * CATAN_CHUNK_BYTES, e % 32, 32, rec);
+    catanb::rec_to_state(rec, out[i]);
+  }
   return 0;
 }
 
@@ -611,15 +544,26 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
   if (check_bound(env)) return -1;
   if (!states_host) return fail("null argument");
   if (first < 0 || count < 0 || first + count > env->n) return fail("env range out of bounds");
+  if (count == 0) return 0;
   if (device_guard(env)) return -1;
-  std::vector<GameRec> tmp(static_cast<size_t>(count));
+  size_t off, bytes;
+  if (chunk_range(env, first, count, off, bytes)) return -1;
+  std::vector<uint8_t> tmp(bytes);
   CATAN_CUDA(cudaDeviceSynchronize());
-  CATAN_CUDA(cudaMemcpy(tmp.data(), env->recs + first, sizeof(GameRec) * static_cast<size_t>(count), cudaMemcpyDeviceToHost));
+  CATAN_CUDA(cudaMemcpy(tmp.data(), env->recs + off, bytes, cudaMemcpyDeviceToHost));
   const catan_state_t* in = reinterpret_cast<const catan_state_t*>(states_host);
-  for (int i = 0; i < count; ++i) catanb::state_to_rec(in[i], tmp[static_cast<size_t>(i)]);
-  CATAN_CUDA(cudaMemcpy(env->recs + first, tmp.data(), sizeof(GameRec) * static_cast<size_t>(count), cudaMemcpyHostToDevice));
+  const int base = first & ~31;
+  for (int i = 0; i < count; ++i) {
+    const int e = first + i - base;
+    uint8_t* chunk = tmp.data() + static_cast<size_t>(e / 32) * CATAN_CHUNK_BYTES;
+    GameRec rec;
+    catanb::chunk_get(chunk, e % 32, 32, rec);   // keeps what the canonical state does not carry
+    catanb::state_to_rec(in[i], rec);
+    catanb::chunk_put(chunk, e % 32, 32, rec);
+  }
+  CATAN_CUDA(cudaMemcpy(env->recs + off, tmp.data(), bytes, cudaMemcpyHostToDevice));
   EnvParams P = make_params(env);
-  if (launch_env<catanb::MODE_REFRESH, false>(env, P, first, count, nullptr)) return -1;
+  if (launch_encode<catanb::MODE_REFRESH, false>(env, P, first, count, nullptr)) return -1;
   CATAN_CUDA(cudaDeviceSynchronize());
   return 0;
 }
