@@ -97,6 +97,12 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
 /* sticky per-env error flags (bit c set = CATAN_ERR_* code c was raised since the last clear). */
 int catan_read_err_flags(catan_env_t* env, uint32_t* flags_host, int clear);
 
+/* Diagnostics of the longest-road path (game/game.py:843-919): counters since catan_create,
+ * out_host[0] = updates triggered (road placed, or settlement placed while the card is held), out_host[1] = updates
+ * that needed a search over the road network by a whole block (the rest is settled incrementally by one thread),
+ * out_host[2..3] reserved.  Synchronous. */
+int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host);
+
 /* ---- PPO rollout path (RL/ppo/process_batch.py) -------------------------------------------------
  * All arrays are device fp32, time-major [T(+1)][N] like the reference's [T+1, N, 1] tensors. */
 

@@ -62,7 +62,7 @@ struct GameView {
   CATAN_F0(uint8_t, must_respond) CATAN_F0(uint8_t, need_discard) CATAN_F0(uint8_t, n_discard) CATAN_F1(uint8_t, discard_queue)
   CATAN_F0(uint8_t, trade_proposer) CATAN_F0(uint8_t, trade_target) CATAN_F0(uint8_t, n_give) CATAN_F1(uint8_t, give)
   CATAN_F0(uint8_t, n_recv) CATAN_F1(uint8_t, recv) CATAN_F0(uint8_t, die1) CATAN_F0(uint8_t, die2) CATAN_F0(uint8_t, trades_this_turn)
-  CATAN_F1(uint8_t, bought) CATAN_F1(int8_t, curr_vps) CATAN_F0(uint8_t, winner)
+  CATAN_F1(uint8_t, bought) CATAN_F1(int8_t, curr_vps) CATAN_F0(uint8_t, winner) CATAN_F1(uint8_t, lr_dirty)
 #undef CATAN_F0
 #undef CATAN_F1
 #undef CATAN_F2
@@ -98,6 +98,16 @@ static inline void chunk_put(uint8_t* chunk, int lane, int W, const GameRec& in)
 }
 static_assert(offsetof(GameRec, est_min) == 0 && offsetof(GameRec, rng_ctr) == 280 && offsetof(GameRec, actions_this_turn) == 292 &&
               offsetof(GameRec, corner) == 296, "chunk_get/chunk_put assume this field order");
+
+// OR over the lanes of a group (host build: one lane)
+#ifdef CATAN_DEVICE
+CATAN_FN uint32_t group_or32(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+#else
+CATAN_FN uint32_t group_or32(uint32_t v) { return v; }
+#endif
+CATAN_FN uint64_t group_or64(uint64_t v) {
+  return static_cast<uint64_t>(group_or32(static_cast<uint32_t>(v))) | (static_cast<uint64_t>(group_or32(static_cast<uint32_t>(v >> 32))) << 32);
+}
 
 // ------------------------------------------------------------------------------------------------
 // bit tables derived from the topology (built once per block into shared memory)
@@ -158,6 +168,7 @@ struct TCx {
   Seats s;
 };
 
+enum { CATAN_LR_ROAD = 0, CATAN_LR_SETTLE = 1 };
 // what apply_action leaves for the follow-up passes of the same step
 struct StepTmp {
   Act act;
@@ -168,7 +179,9 @@ struct StepTmp {
   uint8_t mono_lost[4];
   uint8_t n_est, est_special, granted, dice_roll;
   uint8_t mono_pid, mono_res, lr_pid, err;
-  uint8_t acted_pid, act_type, roll_info, pad_;
+  uint8_t acted_pid, act_type, roll_info, follow;   // follow: dice payout / belief updates are pending (t_followups_group)
+  uint8_t lr_kind, lr_loc;   // what triggered the longest-road update of lr_pid: CATAN_LR_ROAD + edge (0xff: none), CATAN_LR_SETTLE + corner
+  Seats s;                   // seating of the game (for the follow-up pass)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -489,6 +502,13 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp) {
       const bool initial = g.initial_phase();
       if (!initial) { t_pay(g, p, WHEAT, 1); t_pay(g, p, SHEEP, 1); t_pay(g, p, WOOD, 1); t_pay(g, p, BRICK, 1); }
       g.corner(c) = static_cast<uint8_t>((pid << 2) | 1);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {                                  // the corner now cuts the other players' roads through it
+        const int e = T.corner_neigh_edge[c][k];
+        if (e < 0) continue;
+        const int o = g.edge(e);
+        if (o && o != pid) g.lr_dirty(o - 1) = 1;
+      }
       const int slot = T.corner_harbour_slot[c];                     // board.py:182-183
       if (slot >= 0) {
         const int hres = T.harbour_res[g.harbour_perm(slot)];
@@ -516,7 +536,7 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp) {
       } else {
         EstReq& q = t_post_est(cx, tmp, pid, 0);
         est_set(q, BRICK, -1); est_set(q, WOOD, -1); est_set(q, WHEAT, -1); est_set(q, SHEEP, -1);
-        if (g.lr_holder()) tmp.lr_pid = g.lr_holder();               // game.py:552-553
+        if (g.lr_holder()) { tmp.lr_pid = g.lr_holder(); tmp.lr_kind = CATAN_LR_SETTLE; tmp.lr_loc = static_cast<uint8_t>(c); }   // game.py:552-553
       }
       break;
     }
@@ -537,6 +557,7 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp) {
         }
       }
       tmp.lr_pid = static_cast<uint8_t>(pid);                        // game.py:585 (also for the dummy edge)
+      tmp.lr_kind = CATAN_LR_ROAD; tmp.lr_loc = static_cast<uint8_t>(t.edge >= 0 ? t.edge : 0xff);
       if (rb) {
         const int n = g.rb_count() + 1;
         if (n >= 2) { g.rb_active() = 0; g.rb_count() = 0; g.must_use_dev() = 0; }
@@ -736,126 +757,137 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// dice payout (game.py:151-175)
-// ------------------------------------------------------------------------------------------------
-CATAN_FN_NOINLINE void t_dice_payout(TCx& cx, StepTmp& tmp) {
-  const GameView& g = cx.g;
-  const Topo& T = *cx.T;
-  const int roll = tmp.dice_roll, robber = g.robber_tile();
-  for (int i = 0; i < 20; ++i) (&tmp.alloc[0][0])[i] = 0;
-  CATAN_NO_UNROLL
-  for (int t = 0; t < 19; ++t) {
-    if (g.tile_val(t) != roll || t == robber) continue;
-    const int r = g.tile_res(t) - 1;
-    for (int k = 0; k < 6; ++k) {
-      const uint8_t b = g.corner(T.tile_corners[t][k]);
-      if (b) tmp.alloc[r][(b >> 2) - 1] += b & 3;                    // settlement +1, city +2
-    }
-  }
-  int tot[4];
-  for (int p = 0; p < 4; ++p) tot[p] = t_hand_total(g, p + 1);
-  uint8_t granted = 0;
-#pragma unroll
-  for (int ri = 0; ri < 5; ++ri) {
-    const int r = (0x34021 >> (4 * ri)) & 15;                        // Wood, Ore, Brick, Wheat, Sheep (game.py:153-155)
-    const int total = tmp.alloc[r][0] + tmp.alloc[r][1] + tmp.alloc[r][2] + tmp.alloc[r][3];
-    if (total > g.bank(r)) continue;                                 // all-or-nothing per resource (game.py:171)
-    granted |= static_cast<uint8_t>(1u << r);
-    for (int p = 0; p < 4; ++p) {
-      const int a = tmp.alloc[r][p];
-      if (a) { g.res(p, r) = static_cast<uint8_t>(g.res(p, r) + a); g.bank(r) = static_cast<uint8_t>(g.bank(r) - a); }
-      tot[p] += a;
-      tmp.dice_T[p][r] = static_cast<int16_t>(tot[p]);               // owner's running total when (r, p) is re-clipped (Q4)
-    }
-  }
-  tmp.granted = granted;
-  tmp.est_special = EST_SPECIAL_DICE;
-}
-
-// ------------------------------------------------------------------------------------------------
-// belief updates
+// Follow-ups of a transition, executed by a GROUP of `nl` lanes on ONE game (a warp on the device, one lane in the host
+// build): the dice payout (game.py:151-175) and the belief updates.  They are the data-parallel part of apply_action
+// (19 tiles x 6 corners, 60 belief entries), so the thread that ran the scalar part only posts them to `tmp`, which
+// lives in memory that the whole group sees (shared memory on the device).
 //   generic  : update_player_resource_estimates (game.py:921-971)
 //   dice     : the 20 calls of one roll folded into one pass (game.py:170-175; Q4)
 //   monopoly : update_resource_estimates_monopoly (game.py:973-1010)
 // ------------------------------------------------------------------------------------------------
-CATAN_FN_NOINLINE void t_est_generic(TCx& cx, const EstReq& rq) {
-  const GameView& g = cx.g;
+#ifdef CATAN_DEVICE
+#define CATAN_GROUP_SYNC() __syncwarp()
+#else
+#define CATAN_GROUP_SYNC() ((void)0)
+#endif
+
+CATAN_FN void t_dice_payout_group(const GameView& g, const Topo& T, StepTmp& tmp, int lane, int nl) {
+  const int roll = tmp.dice_roll, robber = g.robber_tile();
+  for (int i = lane; i < 20; i += nl) (&tmp.alloc[0][0])[i] = 0;
+  CATAN_GROUP_SYNC();
+  for (int t = lane; t < 19; t += nl) {
+    if (g.tile_val(t) != roll || t == robber) continue;
+    const int r = g.tile_res(t) - 1;
+    uint8_t b[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = g.corner(T.tile_corners[t][k]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (b[k]) sadd_u8(&tmp.alloc[r][(b[k] >> 2) - 1], b[k] & 3);   // settlement +1, city +2
+  }
+  CATAN_GROUP_SYNC();
+  if (lane == 0) {
+    int tot[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) tot[p] = t_hand_total(g, p + 1);
+    uint8_t granted = 0;
+#pragma unroll
+    for (int ri = 0; ri < 5; ++ri) {
+      const int r = (0x34021 >> (4 * ri)) & 15;                      // Wood, Ore, Brick, Wheat, Sheep (game.py:153-155)
+      const int total = tmp.alloc[r][0] + tmp.alloc[r][1] + tmp.alloc[r][2] + tmp.alloc[r][3];
+      if (total > g.bank(r)) continue;                               // all-or-nothing per resource (game.py:171)
+      granted |= static_cast<uint8_t>(1u << r);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int a = tmp.alloc[r][p];
+        if (a) { g.res(p, r) = static_cast<uint8_t>(g.res(p, r) + a); g.bank(r) = static_cast<uint8_t>(g.bank(r) - a); }
+        tot[p] += a;
+        tmp.dice_T[p][r] = static_cast<int16_t>(tot[p]);             // owner's running total when (r, p) is re-clipped (Q4)
+      }
+    }
+    tmp.granted = granted;
+  }
+  CATAN_GROUP_SYNC();
+}
+
+// one item = (observer o, resource r): the requests touch disjoint entries for different items
+CATAN_FN void t_est_generic_group(const GameView& g, Seats s, const EstReq& rq, int lane, int nl) {
   const int owner = rq.owner, thief = rq.thief, T_o = rq.T_o, T_t = rq.T_t;
-  CATAN_NO_UNROLL
-  for (int o = 0; o < 4; ++o) {
-    const int observer = o + 1;
+  for (int it = lane; it < 20; it += nl) {
+    const int o = it / 5, r = it - 5 * o, observer = o + 1;
+    const bool touched = (rq.touched >> r) & 1;
     if (!thief || observer == thief) {                               // game.py:936-954
-      if (observer == owner) continue;
-      const int l = label_of(cx.s, observer, owner);
-      for (int r = 0; r < 5; ++r) {
-        if (!((rq.touched >> r) & 1)) continue;
-        g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) + rq.delta[r], 0, T_o));
-        g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) + rq.delta[r], 0, T_o));
-      }
+      if (observer == owner || !touched) continue;
+      const int l = label_of(s, observer, owner);
+      g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) + rq.delta[r], 0, T_o));
+      g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) + rq.delta[r], 0, T_o));
     } else if (observer == owner) {                                  // victim knows what was taken (game.py:929-933)
-      const int l = label_of(cx.s, observer, thief);
-      for (int r = 0; r < 5; ++r) {
-        if (!((rq.touched >> r) & 1)) continue;
-        g.est_max(o, l, r) = static_cast<int16_t>(g.est_max(o, l, r) - rq.delta[r]);
-        g.est_min(o, l, r) = static_cast<int16_t>(g.est_min(o, l, r) - rq.delta[r]);
-      }
+      if (!touched) continue;
+      const int l = label_of(s, observer, thief);
+      g.est_max(o, l, r) = static_cast<int16_t>(g.est_max(o, l, r) - rq.delta[r]);
+      g.est_min(o, l, r) = static_cast<int16_t>(g.est_min(o, l, r) - rq.delta[r]);
     } else {                                                         // third party (game.py:955-971)
-      const int lo = label_of(cx.s, observer, owner), lt = label_of(cx.s, observer, thief);
-      for (int r = 0; r < 5; ++r) {
-        const int m0 = g.est_max(o, lo, r);                          // the victim entry BEFORE its clip
-        g.est_max(o, lo, r) = static_cast<int16_t>(clipi(m0, 0, T_o));
-        g.est_min(o, lo, r) = static_cast<int16_t>(clipi(g.est_min(o, lo, r) - 1, 0, T_o));
-        if (m0 > 0) {
-          g.est_max(o, lt, r) = static_cast<int16_t>(clipi(g.est_max(o, lt, r) + 1, 0, T_t));
-          g.est_min(o, lt, r) = static_cast<int16_t>(clipi(g.est_min(o, lt, r), 0, T_t));
-        }
+      const int lo = label_of(s, observer, owner), lt = label_of(s, observer, thief);
+      const int m0 = g.est_max(o, lo, r);                            // the victim entry BEFORE its clip
+      g.est_max(o, lo, r) = static_cast<int16_t>(clipi(m0, 0, T_o));
+      g.est_min(o, lo, r) = static_cast<int16_t>(clipi(g.est_min(o, lo, r) - 1, 0, T_o));
+      if (m0 > 0) {
+        g.est_max(o, lt, r) = static_cast<int16_t>(clipi(g.est_max(o, lt, r) + 1, 0, T_t));
+        g.est_min(o, lt, r) = static_cast<int16_t>(clipi(g.est_min(o, lt, r), 0, T_t));
       }
     }
   }
 }
 
-CATAN_FN_NOINLINE void t_est_special(TCx& cx, const StepTmp& tmp) {
-  const GameView& g = cx.g;
+// one item = (observer o, label l, resource r)
+CATAN_FN void t_est_special_group(const GameView& g, Seats s, const StepTmp& tmp, int lane, int nl) {
   if (tmp.est_special == EST_SPECIAL_DICE) {
-    CATAN_NO_UNROLL
-    for (int ol = 0; ol < 12; ++ol) {
-      const int o = ol / 3, l = ol - 3 * o;
-      const int tp = pid_at_label(cx.s, o + 1, l) - 1;
-      for (int r = 0; r < 5; ++r) {
-        if (!((tmp.granted >> r) & 1)) continue;
-        const int gain = tmp.alloc[r][tp], T = tmp.dice_T[tp][r];
-        g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) + gain, 0, T));
-        g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) + gain, 0, T));
-      }
+    for (int it = lane; it < 60; it += nl) {
+      const int ol = it / 5, r = it - 5 * ol, o = ol / 3, l = ol - 3 * o;
+      if (!((tmp.granted >> r) & 1)) continue;
+      const int tp = pid_at_label(s, o + 1, l) - 1;
+      const int gain = tmp.alloc[r][tp], T = tmp.dice_T[tp][r];
+      g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) + gain, 0, T));
+      g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) + gain, 0, T));
     }
   } else if (tmp.est_special == EST_SPECIAL_MONOPOLY) {
     const int tot = tmp.mono_lost[0] + tmp.mono_lost[1] + tmp.mono_lost[2] + tmp.mono_lost[3];
     const int mr = tmp.mono_res;
-    CATAN_NO_UNROLL
-    for (int ol = 0; ol < 12; ++ol) {
-      const int o = ol / 3, l = ol - 3 * o;
-      const int target = pid_at_label(cx.s, o + 1, l);
+    for (int it = lane; it < 60; it += nl) {
+      const int ol = it / 5, r = it - 5 * ol, o = ol / 3, l = ol - 3 * o;
+      const int target = pid_at_label(s, o + 1, l);
       if (target == tmp.mono_pid) {                                  // game.py:984-991, unclipped
+        if (r != mr) continue;
         g.est_min(o, l, mr) = static_cast<int16_t>(g.est_min(o, l, mr) + tot);
         g.est_max(o, l, mr) = static_cast<int16_t>(g.est_max(o, l, mr) + tot);
       } else {                                                       // game.py:993-1010
         const int T = tmp.mono_T[target - 1];
-        for (int r = 0; r < 5; ++r) {
-          const int lost = r == mr ? tmp.mono_lost[target - 1] : 0;
-          g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) - lost, 0, T));
-          g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) - lost, 0, T));
-        }
+        const int lost = r == mr ? tmp.mono_lost[target - 1] : 0;
+        g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) - lost, 0, T));
+        g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) - lost, 0, T));
       }
     }
   }
 }
 
+CATAN_FN_NOINLINE void t_followups_group(const GameView& g, const Topo& T, StepTmp& tmp, int lane, int nl) {
+  if (tmp.dice_roll) { t_dice_payout_group(g, T, tmp, lane, nl); tmp.est_special = EST_SPECIAL_DICE; }
+  for (int qi = 0; qi < tmp.n_est; ++qi) {
+    t_est_generic_group(g, tmp.s, tmp.est[qi], lane, nl);
+    CATAN_GROUP_SYNC();
+  }
+  if (tmp.est_special) t_est_special_group(g, tmp.s, tmp, lane, nl);
+  CATAN_GROUP_SYNC();
+}
+
 // ------------------------------------------------------------------------------------------------
-// the transition of one env step up to (not including) the longest-road update (wrapper.py:36-50, game.py:527-815).
-// `a`: the env's composite action row.  Leaves tmp.err / tmp.lr_pid for the caller.
+// the scalar part of one env step (wrapper.py:36-50, game.py:527-815), by the game's own thread.  `a`: the env's
+// composite action row.  Leaves tmp.err / tmp.lr_pid / tmp.follow for the caller: when tmp.follow is set,
+// t_followups_group() must run next, and the longest-road update (tmp.lr_pid) after that.
 // ------------------------------------------------------------------------------------------------
-CATAN_FN void t_step_transition(TCx& cx, const int32_t* a, StepTmp& tmp) {
-  tmp.n_est = 0; tmp.est_special = EST_SPECIAL_NONE; tmp.dice_roll = 0; tmp.lr_pid = 0; tmp.roll_info = 0;
+CATAN_FN void t_step_scalar(TCx& cx, const int32_t* a, StepTmp& tmp) {
+  tmp.n_est = 0; tmp.est_special = EST_SPECIAL_NONE; tmp.dice_roll = 0; tmp.lr_pid = 0; tmp.roll_info = 0; tmp.follow = 0;
+  tmp.s = cx.s;
   tmp.acted_pid = static_cast<uint8_t>(t_current_actor(cx.g));
   tmp.act_type = static_cast<uint8_t>(a[CATAN_A_TYPE]);
   int err = t_translate_action(cx, a, tmp.act);
@@ -863,9 +895,7 @@ CATAN_FN void t_step_transition(TCx& cx, const int32_t* a, StepTmp& tmp) {
   tmp.err = static_cast<uint8_t>(err);
   if (err) return;
   t_apply_scalar(cx, tmp);
-  if (tmp.dice_roll) t_dice_payout(cx, tmp);
-  for (int qi = 0; qi < tmp.n_est; ++qi) t_est_generic(cx, tmp.est[qi]);
-  if (tmp.est_special) t_est_special(cx, tmp);
+  tmp.follow = tmp.dice_roll || tmp.n_est || tmp.est_special;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -885,22 +915,70 @@ CATAN_FN void t_lp_build_adj(const GameView& g, const Topo& T, int pid, uint64_t
     adj[v] = a;
   }
 }
-// longest path of one player searched by ONE group of lanes (host build: one lane) -- the block-cooperative caller
-// is slowpath_kernel.  scratch: CATAN_LP_SCRATCH_BYTES, 16-byte aligned.
+// scratch of a group-local search (host emulation; the block-cooperative callers are in catan_kernels.cu):
+// adj 432 | adjb 432 | ctl | best | path stacks | task ring
+#define CATAN_LP_WARP_TASKS 256
+#define CATAN_LP_CTL_OFF (2 * CATAN_LP_ADJ_BYTES)
+#define CATAN_LP_BEST_OFF (CATAN_LP_CTL_OFF + 4 * CATAN_LP_CTL_WORDS)
+#define CATAN_LP_PATH_OFF (CATAN_LP_BEST_OFF + 16)
+#define CATAN_LP_TASK_OFF ((CATAN_LP_PATH_OFF + 54 * CATAN_LANES + 15) & ~15)
+#define CATAN_LP_SCRATCH_BYTES (CATAN_LP_TASK_OFF + CATAN_LP_WARP_TASKS * 16)
+// longest path of one player searched by ONE group of lanes.  scratch: CATAN_LP_SCRATCH_BYTES, 16-byte aligned.
 CATAN_FN int t_longest_path(const GameView& g, const Topo& T, int pid, uint8_t* scratch, int lane) {
   uint64_t* adj = reinterpret_cast<uint64_t*>(scratch);
-  int32_t* ctl = reinterpret_cast<int32_t*>(scratch + CATAN_LP_ADJ_BYTES);
-  int32_t* best = reinterpret_cast<int32_t*>(scratch + CATAN_LP_TASK_OFF - 8);
+  int32_t* ctl = reinterpret_cast<int32_t*>(scratch + CATAN_LP_CTL_OFF);
+  int32_t* best = reinterpret_cast<int32_t*>(scratch + CATAN_LP_BEST_OFF);
   LpTask* ring = reinterpret_cast<LpTask*>(scratch + CATAN_LP_TASK_OFF);
+  wsync();
   t_lp_build_adj(g, T, pid, adj, lane, CATAN_LANES);
   if (lane == 0) *best = 0;
   wsync();
-  CATAN_LP_RUN(adj, 1, ctl, best, scratch + CATAN_LP_PATH_OFF, CATAN_LANES, lane, ring, CATAN_LP_WARP_TASKS, CATAN_LP_BUDGET,
-               lane == 0, wsync(), (void)0);
+  CATAN_LP_RUN(adj, adj, -1, -1, ctl, best, scratch + CATAN_LP_PATH_OFF, CATAN_LANES, lane, ring, CATAN_LP_WARP_TASKS, lane == 0, wsync());
+  return *best;
+}
+// Tables of the THROUGH search for a new road a -> b (lp_round, through mode): adj = arcs out of a corner, adjb = arcs
+// into it plus the jump bit b.  Group of nl lanes; the caller synchronises afterwards.
+CATAN_FN void t_lp_build_adj2(const GameView& g, const Topo& T, int pid, uint64_t* adj, uint64_t* adjb, int b, int lane, int nl) {
+  uint64_t blk = 0;
+  for (int v = lane; v < 54; v += nl) {
+    uint64_t und = 0;
+    const uint8_t bd = g.corner(v);
+    if (bd && (bd >> 2) != pid) blk |= 1ull << v;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int e = T.corner_neigh_edge[v][k];
+      if (e >= 0 && g.edge(e) == pid) und |= 1ull << T.corner_neigh[v][k];
+    }
+    adjb[v] = und;
+  }
+  blk = group_or64(blk);
+  for (int v = lane; v < 54; v += nl) {
+    const uint64_t und = adjb[v];
+    adj[v] = (blk >> v) & 1ull ? 0ull : und;
+    adjb[v] = (und & ~blk) | (1ull << b);
+  }
+}
+// longest path of PlayerId pid that contains the road `edge`, same group, same scratch
+CATAN_FN int t_through_edge(const GameView& g, const Topo& T, int pid, int edge, uint8_t* scratch, int lane) {
+  uint64_t* adj = reinterpret_cast<uint64_t*>(scratch);
+  uint64_t* adjb = reinterpret_cast<uint64_t*>(scratch + CATAN_LP_ADJ_BYTES);
+  int32_t* ctl = reinterpret_cast<int32_t*>(scratch + CATAN_LP_CTL_OFF);
+  int32_t* best = reinterpret_cast<int32_t*>(scratch + CATAN_LP_BEST_OFF);
+  LpTask* ring = reinterpret_cast<LpTask*>(scratch + CATAN_LP_TASK_OFF);
+  int through = 0;
+  for (int dir = 0; dir < 2; ++dir) {
+    const int a = T.edge_corners[edge][dir], b = T.edge_corners[edge][dir ^ 1];
+    const uint8_t bd = g.corner(a);
+    if (bd && (bd >> 2) != pid) continue;                            // a is blocked: no arc a -> b
+    wsync();
+    t_lp_build_adj2(g, T, pid, adj, adjb, b, lane, CATAN_LANES);
+    if (lane == 0) *best = 0;
+    wsync();
+    CATAN_LP_RUN(adj, adjb, b, a, ctl, best, scratch + CATAN_LP_PATH_OFF, CATAN_LANES, lane, ring, CATAN_LP_WARP_TASKS, lane == 0, wsync());
+    if (*best > through) through = *best;
+  }
   wsync();
-  const int r = *best;
-  wsync();
-  return r;
+  return through;
 }
 CATAN_FN bool t_lr_is_shrunk(const GameView& g, int pid, int len) { return g.lr_holder() == pid && g.lr_count() > len; }
 
@@ -937,6 +1015,123 @@ CATAN_FN_NOINLINE void t_lr_apply(const GameView& g, int pid, int len, bool shru
     g.vp(holder - 1) -= 2; g.vp(pid - 1) += 2;
     g.lr_holder() = static_cast<uint8_t>(pid); g.lr_count() = static_cast<uint8_t>(len);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Incremental longest road, ONE THREAD per update.  The reference re-enumerates every simple path of the player's road
+// graph each time (game.py:843-862).  The result can be had from the stored length in most cases:
+//   * road placed (edge {u,v}): the new maximum is max(old, longest path THROUGH the new edge).  If the edge is a bridge
+//     of the player's road graph (96 % of the placements in random play), the part behind u and the part beyond v cannot
+//     share a corner, so that path is (longest path into u) + 1 + (longest path out of v) -- two small searches.  Known
+//     cheaply when one end had no road before; otherwise the sum is only an upper bound: good enough when it does not
+//     beat the stored length.
+//   * settlement placed while somebody holds the longest road: the holder's paths are untouched unless the corner lies on
+//     one of the holder's roads (and the holder is not the builder).
+// The stored length is exact unless an opponent built on the player's network since it was measured (lr_dirty).  All other
+// cases -- and searches that exceed CATAN_LR_FAST_ITERS -- are left to the full enumeration (return -1).
+// Arc semantics as lp_build_adj: a corner holding an opponent's building has no outgoing arcs (game.py:851-858).
+// ------------------------------------------------------------------------------------------------
+#ifndef CATAN_LR_FAST_ITERS
+#define CATAN_LR_FAST_ITERS 96
+#endif
+struct RoadBits { uint64_t em_lo, blk; uint32_t em_hi; };   // pid's roads (edge bit set), corners blocked for pid
+CATAN_FN RoadBits t_load_road_bits(const GameView& g, int pid) {
+  RoadBits R = {0ull, 0ull, 0u};
+  CATAN_NO_UNROLL
+  for (int e0 = 0; e0 < 72; e0 += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = e0 + j;
+      const uint32_t own = g.edge(e) == static_cast<uint32_t>(pid);
+      if (e0 < 64) R.em_lo |= static_cast<uint64_t>(own) << e; else R.em_hi |= own << (e - 64);
+    }
+  }
+  CATAN_NO_UNROLL
+  for (int c0 = 0; c0 < 54; c0 += 6) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const uint32_t b = g.corner(c0 + j);
+      R.blk |= static_cast<uint64_t>(b != 0 && (b >> 2) != static_cast<uint32_t>(pid)) << (c0 + j);
+    }
+  }
+  return R;
+}
+// new length of PlayerId pid's longest road, or -1 if the full enumeration is needed
+CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int kind, int loc, int placer) {
+  const int holder = g.lr_holder();
+  const int old = holder == pid ? g.lr_count() : (g.has_path_key(pid - 1) ? g.cur_longest_path(pid - 1) : 0);
+  if (kind == CATAN_LR_SETTLE) {                                     // pid == holder (game.py:552-553): its length is always current
+    if (placer == pid) return old;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int e = T.corner_neigh_edge[loc][k];
+      if (e >= 0 && g.edge(e) == pid) return -1;                     // the new building may cut the holder's road
+    }
+    return old;
+  }
+  if (g.lr_dirty(pid - 1)) return -1;
+  if (loc == 0xff) return old;                                       // dummy edge of road building (game.py:585): nothing changed
+  const RoadBits R = t_load_road_bits(g, pid);
+  uint64_t und[54];                                                  // neighbours over pid's roads (thread-private table)
+#pragma unroll
+  for (int c = 0; c < 54; ++c) und[c] = 0ull;
+  {
+    uint64_t lo = R.em_lo;
+    uint32_t hi = R.em_hi;
+    CATAN_NO_UNROLL
+    while (lo | hi) {
+      int e;
+      if (lo) { e = ctz64(lo); lo &= lo - 1; } else { e = 64 + ctz64(hi); hi &= hi - 1; }
+      const int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
+      und[c1] |= 1ull << c2;
+      und[c2] |= 1ull << c1;
+    }
+  }
+  const int u = T.edge_corners[loc][0], v = T.edge_corners[loc][1];
+  // one end had no road before: the new edge is certainly a bridge
+  const bool leaf = !(und[u] & ~(1ull << v)) || !(und[v] & ~(1ull << u));
+  // four searches in ONE loop (the lanes of a warp are in different searches of different games): into u, out of v, into
+  // v, out of u; arcs out of a corner blocked by an opponent's building do not exist
+  int through = 0, iters = CATAN_LR_FAST_ITERS, phase = 0, acc = 0;
+  int depth = 0, best = 0, node = 0;
+  uint64_t visited = 0, above = 0;
+  uint8_t st[54];
+  bool fresh = true;
+  CATAN_NO_UNROLL
+  for (;;) {
+    if (fresh) {
+      if (phase >= 4) break;
+      const int a = phase < 2 ? u : v, b = phase < 2 ? v : u;
+      if ((R.blk >> a) & 1ull) { phase += 2; continue; }             // no arc a -> b
+      node = (phase & 1) ? b : a;
+      depth = 0; best = 0; visited = (1ull << a) | (1ull << b); above = ~0ull;
+      st[0] = static_cast<uint8_t>(node);
+      fresh = false;
+    }
+    if (--iters < 0) return -1;
+    const bool fwd = phase & 1;
+    uint64_t nb = und[node];
+    nb = fwd ? (((R.blk >> node) & 1ull) ? 0ull : nb) : (nb & ~R.blk);
+    const uint64_t cand = nb & ~visited & above;
+    if (cand) {
+      const int t = ctz64(cand);
+      st[++depth] = static_cast<uint8_t>(t);
+      visited |= 1ull << t;
+      node = t; above = ~0ull;
+      if (depth > best) best = depth;
+    } else if (depth == 0) {
+      if (!fwd) acc = best;
+      else if (acc + 1 + best > through) through = acc + 1 + best;
+      ++phase;
+      fresh = true;
+    } else {
+      visited &= ~(1ull << node);
+      above = ~((2ull << node) - 1ull);
+      node = st[--depth];
+    }
+  }
+  if (leaf) return through > old ? through : old;
+  return through <= old ? old : -1;                                  // the sum is only an upper bound on a cycle
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1022,11 +1217,6 @@ CATAN_FN void reset_shuffle(ResetRng& R, uint8_t* a, int n) {
     const uint8_t t = a[i]; a[i] = a[j]; a[j] = t;
   }
 }
-#ifdef CATAN_DEVICE
-#define CATAN_GROUP_SYNC() __syncwarp()
-#else
-#define CATAN_GROUP_SYNC() ((void)0)
-#endif
 CATAN_FN_NOINLINE void reset_game_group(const GameView& g, const Topo& T, uint64_t seed, uint64_t env_id, uint32_t* wbuf, uint8_t* arr,
                                         int lane, int nl, uint8_t* info_patch) {
   const uint32_t rng = g.rng_ctr(), dec = g.decision_ctr();
@@ -1105,76 +1295,58 @@ struct MaskBits {
 };
 #define CATAN_ALL54 ((1ull << 54) - 1ull)
 
-struct Boards {              // occupancy bit boards of one game seen by PlayerId pid
-  uint64_t bld, mine, mine_settle;
-  uint64_t e_any_lo, e_mine_lo;
-  uint32_t e_any_hi, e_mine_hi;
+// Placement scan of ONE game by a GROUP of `nl` lanes (a warp on the device), one lane per corner / edge / tile: the
+// occupancy bit boards seen by PlayerId pid, corner.py:24-39 for all corners and edge.py:23-42 for all edges.  Every lane
+// returns the complete result.
+struct Scan {
+  uint64_t settle_free;      // distance rule only (corner.py:28-33)
+  uint64_t road_at;          // an own road touches the corner
+  uint64_t mine_settle;      // own settlements
+  uint64_t road_lo;          // edges 0..63 where pid may build (edge.py:33-42)
+  uint64_t e_any_lo;         // occupied edges 0..63
+  uint32_t road_hi, e_any_hi;   // edges 64..71
+  uint32_t tile_bld;         // tiles with any building on a corner (wrapper.py:308-320, Q1)
 };
-CATAN_FN_NOINLINE void t_load_boards(const GameView& g, int pid, Boards& B) {
+CATAN_FN_NOINLINE Scan t_scan_group(const GameView& g, const Topo& T, const TopoX& X, int pid, int lane, int nl) {
   uint64_t bld = 0, mine = 0, ms = 0;
-  CATAN_NO_UNROLL
-  for (int c0 = 0; c0 < 54; c0 += 6) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int c = c0 + j;
-      const uint32_t b = g.corner(c);
-      bld |= static_cast<uint64_t>(b != 0) << c;
-      mine |= static_cast<uint64_t>(b != 0 && (b >> 2) == static_cast<uint32_t>(pid)) << c;
-      ms |= static_cast<uint64_t>(b == static_cast<uint32_t>((pid << 2) | 1)) << c;
-    }
+  for (int c = lane; c < 54; c += nl) {
+    const uint32_t b = g.corner(c);
+    bld |= static_cast<uint64_t>(b != 0) << c;
+    mine |= static_cast<uint64_t>(b != 0 && (b >> 2) == static_cast<uint32_t>(pid)) << c;
+    ms |= static_cast<uint64_t>(b == static_cast<uint32_t>((pid << 2) | 1)) << c;
   }
   uint64_t ea = 0, em = 0;
-  CATAN_NO_UNROLL
-  for (int e0 = 0; e0 < 64; e0 += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e = e0 + j;
-      const uint32_t b = g.edge(e);
-      ea |= static_cast<uint64_t>(b != 0) << e;
-      em |= static_cast<uint64_t>(b == static_cast<uint32_t>(pid)) << e;
-    }
-  }
   uint32_t eah = 0, emh = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint32_t b = g.edge(64 + j);
-    eah |= static_cast<uint32_t>(b != 0) << j;
-    emh |= static_cast<uint32_t>(b == static_cast<uint32_t>(pid)) << j;
+  for (int e = lane; e < 72; e += nl) {
+    const uint32_t b = g.edge(e);
+    if (e < 64) { ea |= static_cast<uint64_t>(b != 0) << e; em |= static_cast<uint64_t>(b == static_cast<uint32_t>(pid)) << e; }
+    else { eah |= static_cast<uint32_t>(b != 0) << (e - 64); emh |= static_cast<uint32_t>(b == static_cast<uint32_t>(pid)) << (e - 64); }
   }
-  B.bld = bld; B.mine = mine; B.mine_settle = ms; B.e_any_lo = ea; B.e_mine_lo = em; B.e_any_hi = eah; B.e_mine_hi = emh;
-}
-
-// corner.py:24-39 for all corners: settle_ok (without the "initial" waiver: needs an own road) and settle_free (distance
-// rule only); reach[c] = a road of pid may start from c (own building, or an own road at a corner without any building)
-CATAN_FN_NOINLINE void t_corner_scan(const TopoX& X, const Boards& B, uint64_t& settle_free, uint64_t& road_at, uint64_t& reach) {
+  bld = group_or64(bld); mine = group_or64(mine); ms = group_or64(ms);
+  ea = group_or64(ea); em = group_or64(em); eah = group_or32(eah); emh = group_or32(emh);
   uint64_t fre = 0, ra = 0;
-  CATAN_NO_UNROLL
-  for (int c = 0; c < 54; ++c) {
-    const bool blocked = ((X.corner_nb[c] | (1ull << c)) & B.bld) != 0;
-    const bool own_road = ((X.corner_edges_lo[c] & B.e_mine_lo) | static_cast<uint64_t>(X.corner_edges_hi[c] & B.e_mine_hi)) != 0;
+  for (int c = lane; c < 54; c += nl) {
+    const bool blocked = ((X.corner_nb[c] | (1ull << c)) & bld) != 0;
+    const bool own_road = ((X.corner_edges_lo[c] & em) | static_cast<uint64_t>(X.corner_edges_hi[c] & emh)) != 0;
     fre |= static_cast<uint64_t>(!blocked) << c;
     ra |= static_cast<uint64_t>(own_road) << c;
   }
-  settle_free = fre; road_at = ra;
-  reach = B.mine | (~B.bld & ra);
-}
-
-// edge.py:23-42 for all edges; returns lo (edges 0..63) and hi (64..71)
-CATAN_FN_NOINLINE void t_road_scan(const Topo& T, const Boards& B, uint64_t reach, uint64_t& lo, uint32_t& hi) {
-  uint64_t l = 0;
-  uint32_t h = 0;
-  CATAN_NO_UNROLL
-  for (int e = 0; e < 64; ++e) {
+  fre = group_or64(fre); ra = group_or64(ra);
+  const uint64_t reach = mine | (~bld & ra);                         // a road of pid may start here
+  uint64_t lo = 0;
+  uint32_t hi = 0, tl = 0;
+  for (int e = lane; e < 72; e += nl) {
     const int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
-    l |= static_cast<uint64_t>(((reach >> c1) | (reach >> c2)) & 1ull) << e;
+    const uint64_t ok = ((reach >> c1) | (reach >> c2)) & 1ull;
+    if (e < 64) lo |= ok << e; else hi |= static_cast<uint32_t>(ok) << (e - 64);
   }
-#pragma unroll
-  for (int e = 64; e < 72; ++e) {
-    const int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
-    h |= static_cast<uint32_t>(((reach >> c1) | (reach >> c2)) & 1ull) << (e - 64);
-  }
-  lo = l & ~B.e_any_lo;
-  hi = h & ~B.e_any_hi & 0xffu;
+  for (int t = lane; t < 19; t += nl) tl |= static_cast<uint32_t>((X.tile_cmask[t] & bld) != 0) << t;
+  Scan sc;
+  sc.settle_free = fre; sc.road_at = ra; sc.mine_settle = ms;
+  sc.road_lo = group_or64(lo) & ~ea; sc.road_hi = group_or32(hi) & ~eah & 0xffu;
+  sc.e_any_lo = ea; sc.e_any_hi = eah;
+  sc.tile_bld = group_or32(tl);
+  return sc;
 }
 
 CATAN_FN void t_mask_play_dev(const GameView& g, int p, MaskBits& m) {   // wrapper.py:221-228 / :262-269 / :368-388
@@ -1199,11 +1371,15 @@ CATAN_FN void t_mask_play_dev(const GameView& g, int p, MaskBits& m) {   // wrap
   }
 }
 
-CATAN_FN_NOINLINE void t_build_masks(const TCx& cx, MaskBits& m) {
+// The masks of one game in two halves around the placement scan: t_masks_pre() handles the phases that need no board
+// scan and returns true when t_scan_group() must run for this game (PlayerId = players_go) before t_masks_post().
+struct MaskPlan { uint8_t post, initial, rb, capped, init_settle, want_settle, want_city, want_road, want_tiles; };   // post: t_masks_post() must run
+CATAN_FN_NOINLINE bool t_masks_pre(const TCx& cx, MaskBits& m, MaskPlan& pl) {
   const GameView& g = cx.g;
   const Topo& T = *cx.T;
   m.type = 0; m.settle = CATAN_ALL54; m.city = CATAN_ALL54; m.edge_lo = ~0ull; m.edge_hi = 0x1ffu; m.tile = (1u << 19) - 1u;
   m.dev = 31u; m.accept = 3u; m.player = 0x1ffu; m.res_a = 0xfffffu; m.res_b = 31u; m.discard = 31u;
+  pl.post = 0; pl.initial = 0; pl.rb = 0; pl.capped = 0; pl.init_settle = 0; pl.want_settle = 0; pl.want_city = 0; pl.want_road = 0; pl.want_tiles = 0;
   const int pid = g.players_go(), p = pid - 1;
   if (g.need_discard()) {                                            // wrapper.py:186-192
     const int d = g.discard_queue(0);
@@ -1212,7 +1388,7 @@ CATAN_FN_NOINLINE void t_build_masks(const TCx& cx, MaskBits& m) {
 #pragma unroll
     for (int r = 0; r < 5; ++r) bits |= static_cast<uint32_t>(g.res(d - 1, r) != 0) << r;
     m.discard = bits;
-    return;
+    return false;
   }
   const bool initial = g.initial_phase(), rb = g.rb_active();
   if (!initial && !rb) {
@@ -1225,7 +1401,7 @@ CATAN_FN_NOINLINE void t_build_masks(const TCx& cx, MaskBits& m) {
         if (b && (b >> 2) != pid) row |= 1u << label_of(cx.s, pid, b >> 2);
       }
       m.player = (m.player & ~(7u << 3)) | (row << 3);
-      return;
+      return false;
     }
     if (g.must_respond()) {                                          // wrapper.py:214-218, :353-365
       m.type = 1u << CATAN_ACT_RESPOND;
@@ -1236,12 +1412,12 @@ CATAN_FN_NOINLINE void t_build_masks(const TCx& cx, MaskBits& m) {
 #pragma unroll
       for (int r = 0; r < 5; ++r) ok &= g.res(tt, r) >= static_cast<int>((cnt >> (4 * r)) & 15);
       m.accept = 2u | static_cast<uint32_t>(ok);
-      return;
+      return false;
     }
     if (!g.dice_rolled()) {                                          // wrapper.py:219-229
       m.type = 1u << CATAN_ACT_ROLL_DICE;
       t_mask_play_dev(g, p, m);
-      return;
+      return false;
     }
   }
   // the placement phases: initial (wrapper.py:195-204), road building (:206-209) and the main phase (:232-290)
@@ -1253,56 +1429,46 @@ CATAN_FN_NOINLINE void t_build_masks(const TCx& cx, MaskBits& m) {
   const bool want_settle = init_settle || (!initial && !rb && !capped && h[WHEAT] && h[SHEEP] && h[WOOD] && h[BRICK]);
   const bool want_city = !initial && !rb && !capped && h[WHEAT] >= 2 && h[ORE] >= 3 && g.cities_left(p) > 0;
   const bool want_road = (initial && !init_settle) || rb || (!initial && !capped && h[WOOD] && h[BRICK]);
+  const bool want_tiles = !initial && !rb && !capped && g.can_move_robber();
   if (!initial && !rb) m.type = 1u << CATAN_ACT_END_TURN;            // wrapper.py:232
-  if (want_settle || want_city || want_road) {
-    Boards B;
-    t_load_boards(g, pid, B);
-    uint64_t settle_free = 0, road_at = 0, reach = 0;
-    if (want_settle || want_road) t_corner_scan(*cx.X, B, settle_free, road_at, reach);
-    if (want_settle) {
-      if (init_settle) {
-        m.type = 1u << CATAN_ACT_PLACE_SETTLEMENT;
-        m.settle = settle_free;
-      } else {                                                       // wrapper.py:238-243
-        const uint64_t ok = settle_free & road_at;
-        if (ok && g.settlements_left(p) > 0) { m.type |= 1u << CATAN_ACT_PLACE_SETTLEMENT; m.settle = ok; }
-      }
+  pl.post = 1; pl.initial = initial; pl.rb = rb; pl.capped = capped; pl.init_settle = init_settle;
+  pl.want_settle = want_settle; pl.want_city = want_city; pl.want_road = want_road; pl.want_tiles = want_tiles;
+  return want_settle || want_city || want_road || want_tiles;
+}
+
+CATAN_FN_NOINLINE void t_masks_post(const TCx& cx, MaskBits& m, const MaskPlan& pl, const Scan& sc) {
+  const GameView& g = cx.g;
+  const int pid = g.players_go(), p = pid - 1;
+  const bool initial = pl.initial, rb = pl.rb;
+  if (pl.want_settle) {
+    if (pl.init_settle) {
+      m.type = 1u << CATAN_ACT_PLACE_SETTLEMENT;
+      m.settle = sc.settle_free;
+    } else {                                                         // wrapper.py:238-243
+      const uint64_t ok = sc.settle_free & sc.road_at;
+      if (ok && g.settlements_left(p) > 0) { m.type |= 1u << CATAN_ACT_PLACE_SETTLEMENT; m.settle = ok; }
     }
-    if (want_city && B.mine_settle) { m.type |= 1u << CATAN_ACT_UPGRADE_CITY; m.city = B.mine_settle; }   // wrapper.py:245-250
-    if (want_road) {                                                 // wrapper.py:322-339
-      uint64_t lo;
-      uint32_t hi;
-      if (initial && g.init_settlements(p) == 2) {                   // the second road must touch the second settlement (edge.py:27-31)
-        const int sc = g.second_corner(p);
-        lo = cx.X->corner_edges_lo[sc] & ~B.e_any_lo;
-        hi = cx.X->corner_edges_hi[sc] & ~B.e_any_hi;
-      } else {
-        t_road_scan(T, B, reach, lo, hi);
-      }
-      const bool placed = (lo | hi) != 0;
-      if (initial) { m.type = 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi; }
-      else if (rb) { m.type = 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi | (placed ? 0u : 0x100u); }
-      else if (placed) { m.type |= 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi; }
-    }
-    if (initial || rb) return;
-    if (g.can_move_robber() && !capped) {                            // wrapper.py:278-281, :308-320 (Q1: any building)
-      uint32_t tl = 0;
-      CATAN_NO_UNROLL
-      for (int t = 0; t < 19; ++t) tl |= static_cast<uint32_t>((cx.X->tile_cmask[t] & B.bld) != 0) << t;
-      m.tile = tl;
-    }
-  } else if (g.can_move_robber() && !capped) {
-    uint32_t tl = 0;
-    CATAN_NO_UNROLL
-    for (int t = 0; t < 19; ++t) {
-      bool any = false;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) any |= g.corner(T.tile_corners[t][k]) != 0;
-      tl |= static_cast<uint32_t>(any) << t;
-    }
-    m.tile = tl;
   }
-  if (capped) return;
+  if (pl.want_city && sc.mine_settle) { m.type |= 1u << CATAN_ACT_UPGRADE_CITY; m.city = sc.mine_settle; }   // wrapper.py:245-250
+  if (pl.want_road) {                                                // wrapper.py:322-339
+    uint64_t lo = sc.road_lo;
+    uint32_t hi = sc.road_hi;
+    if (initial && g.init_settlements(p) == 2) {                     // the second road must touch the second settlement (edge.py:27-31)
+      const int c2 = g.second_corner(p);
+      lo = cx.X->corner_edges_lo[c2] & ~sc.e_any_lo;
+      hi = cx.X->corner_edges_hi[c2] & ~sc.e_any_hi;
+    }
+    const bool placed = (lo | hi) != 0;
+    if (initial) { m.type = 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi; }
+    else if (rb) { m.type = 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi | (placed ? 0u : 0x100u); }
+    else if (placed) { m.type |= 1u << CATAN_ACT_PLACE_ROAD; m.edge_lo = lo; m.edge_hi = hi; }
+  }
+  if (initial || rb) return;
+  if (pl.want_tiles) m.tile = sc.tile_bld;                           // wrapper.py:278-281, :308-320 (Q1: any building)
+  if (pl.capped) return;
+  int h[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) h[r] = g.res(p, r);
   if (h[WHEAT] && h[SHEEP] && h[ORE] && g.deck_n() > 0) m.type |= 1u << CATAN_ACT_BUY_DEV;
   t_mask_play_dev(g, p, m);                                          // wrapper.py:262-269
   {
@@ -1332,8 +1498,8 @@ template <int POS, int N>
 CATAN_FN void flat_put(MaskFlat& F, uint64_t v) {
   constexpr int w0 = POS / 32, s = POS % 32;
   F.w[w0] |= static_cast<uint32_t>(v << s);
-  if (s + N > 32) F.w[w0 + 1] |= static_cast<uint32_t>(v >> (32 - s));
-  if (s + N > 64) F.w[w0 + 2] |= static_cast<uint32_t>(v >> (64 - s));
+  if constexpr (s + N > 32) F.w[w0 + 1] |= static_cast<uint32_t>(v >> (32 - s));
+  if constexpr (s + N > 64) F.w[w0 + 2] |= static_cast<uint32_t>(v >> (64 - s));
 }
 CATAN_FN void t_flatten_masks(const MaskBits& m, MaskFlat& F) {
 #pragma unroll
@@ -1385,20 +1551,21 @@ CATAN_FN void t_load_mask_row(const uint8_t* row, MaskBits& m) {
 // pinned random-legal sampler (twin of oracle/ref_harness.py:sample_action) on bit sets:
 // pick = index of the floor(w*k/2^32)-th set entry (k = number of set entries), 0 if none
 // ------------------------------------------------------------------------------------------------
-CATAN_FN int nth_set32(uint32_t m, int j) {
-#ifdef CATAN_DEVICE
-  return static_cast<int>(__fns(m, 0, j + 1));
-#else
-  for (int q = 0; q < j; ++q) m &= m - 1;
-  return __builtin_ctz(m);
-#endif
-}
 CATAN_FN int popc32(uint32_t m) {
 #ifdef CATAN_DEVICE
   return __popc(m);
 #else
   return __builtin_popcount(m);
 #endif
+}
+CATAN_FN int nth_set32(uint32_t m, int j) {   // index of the j-th (0-based) set bit of m; popcount descent (__fns is a slow loop)
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const int c = popc32((m >> pos) & ((1u << w) - 1u));
+    if (j >= c) { j -= c; pos += w; }
+  }
+  return pos;
 }
 CATAN_FN int pick96(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t w) {
   const int k0 = popc32(m0), k1 = popc32(m1), k = k0 + k1 + popc32(m2);
@@ -1463,29 +1630,39 @@ static_assert(CATAN_A_TYPE == 0 && CATAN_A_CORNER == 1 && CATAN_A_EDGE == 2 && C
 // warp is bank-conflict free whatever the per-thread byte positions are.
 // ------------------------------------------------------------------------------------------------
 #define CATAN_RING_BYTES 128
+// A row can be produced by several threads: each owns a 16-byte aligned range [lo, hi) of it, walks the features that
+// intersect its range and drops the bytes outside (a feature straddling a cut is evaluated on both sides).
 template <int NT>
 struct RowWriter {
   uint32_t* ring;      // this thread's word 0
   uint8_t* row;        // destination row (16-byte aligned)
-  int flushed;         // everything below this row offset (multiple of 16) has been written
+  int flushed;         // everything in [lo, flushed) has been written (multiple of 16)
+  int lo, hi;          // range of the row this writer owns (multiples of 16)
   CATAN_MFN uint8_t* byte_ptr(int p) const {
     return reinterpret_cast<uint8_t*>(ring + ((p & (CATAN_RING_BYTES - 1)) >> 2) * NT) + (p & 3);
   }
-  CATAN_MFN void init(uint32_t* r, uint8_t* dst) {
-    ring = r; row = dst; flushed = 0;
+  CATAN_MFN void init(uint32_t* r, uint8_t* dst, int lo_, int hi_) {
+    ring = r; row = dst; flushed = lo_; lo = lo_; hi = hi_;
 #pragma unroll
     for (int w = 0; w < CATAN_RING_BYTES / 4; ++w) ring[w * NT] = 0;
   }
-  CATAN_MFN void put(int p, int v) const { *byte_ptr(p) = static_cast<uint8_t>(v); }
-  CATAN_MFN void add(int p, int v) const { uint8_t* q = byte_ptr(p); *q = static_cast<uint8_t>(*q + v); }
+  CATAN_MFN bool owns(int p) const { return p >= lo && p < hi; }
+  CATAN_MFN bool overlaps(int a, int b) const { return a < hi && b > lo; }   // [a, b) intersects [lo, hi)
+  CATAN_MFN void put(int p, int v) const { if (owns(p)) *byte_ptr(p) = static_cast<uint8_t>(v); }
+  CATAN_MFN void add(int p, int v) const { if (owns(p)) { uint8_t* q = byte_ptr(p); *q = static_cast<uint8_t>(*q + v); } }
   // write out (and clear) every complete 16-byte piece below `upto`; afterwards positions < upto + 112 are writable
   CATAN_MFN void flush_to(int upto) {
     struct alignas(16) V16 { uint32_t a, b, c, d; };
+    if (upto > hi) upto = hi;
     CATAN_NO_UNROLL
     while (flushed + 16 <= upto) {
       uint32_t* q = ring + ((flushed & (CATAN_RING_BYTES - 1)) >> 2) * NT;
       const V16 v = {q[0], q[NT], q[2 * NT], q[3 * NT]};
+#ifdef CATAN_DEVICE
+      __stcs(reinterpret_cast<uint4*>(row + flushed), make_uint4(v.a, v.b, v.c, v.d));   // streamed: rows are not re-read here
+#else
       *reinterpret_cast<V16*>(row + flushed) = v;
+#endif
       q[0] = 0; q[NT] = 0; q[2 * NT] = 0; q[3 * NT] = 0;
       flushed += 16;
     }
@@ -1495,12 +1672,13 @@ struct RowWriter {
 CATAN_FN int t_bucket8(int n) { return n < 5 ? n : (n < 8 ? 5 : (n < 11 ? 6 : 7)); }                        // wrapper.py:554-561
 CATAN_FN int t_bucket7(int n) { return n <= 2 ? n : (n <= 5 ? 3 : (n <= 7 ? 4 : (n <= 10 ? 5 : 6))); }       // wrapper.py:662-671
 
+// bytes [lo, hi) of the observation row of one game (lo, hi multiples of 16); the whole row is [0, CATAN_OBS_STRIDE)
 template <int NT>
-CATAN_FN_NOINLINE void t_encode_obs(const TCx& cx, uint32_t* ring, uint8_t* row) {
+CATAN_FN_NOINLINE void t_encode_obs(const TCx& cx, uint32_t* ring, uint8_t* row, int lo, int hi) {
   const GameView& g = cx.g;
   const Topo& T = *cx.T;
   RowWriter<NT> W;
-  W.init(ring, row);
+  W.init(ring, row, lo, hi);
   const int actor = t_current_actor(g), ap = actor - 1;
   const int aseat = seat_of(cx.s, actor);
   // REL(pid) = block of PlayerId pid seen from the actor (0 self, 1 next, ...), PID_AT(rel) = PlayerId rel seats after the actor
@@ -1510,111 +1688,219 @@ CATAN_FN_NOINLINE void t_encode_obs(const TCx& cx, uint32_t* ring, uint8_t* row)
 #define CATAN_REL(pid_) ((relpack >> (2 * (pid_))) & 3u)
 #define CATAN_PID_AT(rel_) pid_at_seat(cx.s, aseat + (rel_))
   // ---- [0, 18): proposed trade (wrapper.py:61-69, Q15) and the actor's hand (wrapper.py:70-71)
-  if (g.trade_proposer()) {
-    const int ng = g.n_give(), nr = g.n_recv();
-    for (int k = 0; k < ng; ++k) W.put(CATAN_OBS_PROPOSED_TRADE + g.give(k), 1);
-    for (int k = 0; k < nr; ++k) W.put(CATAN_OBS_PROPOSED_TRADE + g.recv(k) + 5, 1);
+  if (W.overlaps(0, CATAN_OBS_TILES)) {
+    if (g.trade_proposer()) {
+      const int ng = g.n_give(), nr = g.n_recv();
+      for (int k = 0; k < ng; ++k) W.put(CATAN_OBS_PROPOSED_TRADE + g.give(k), 1);
+      for (int k = 0; k < nr; ++k) W.put(CATAN_OBS_PROPOSED_TRADE + g.recv(k) + 5, 1);
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) W.put(CATAN_OBS_CURRENT_RES + 1 + r, g.res(ap, r));
   }
-  int hand[5];
+  // ---- tiles (wrapper.py:491-524)
+  if (W.overlaps(CATAN_OBS_TILES, CATAN_OBS_CUR_MAIN)) {
+    const int robber = g.robber_tile();
+    CATAN_NO_UNROLL
+    for (int t = 0; t < 19; ++t) {
+      const int base = CATAN_OBS_TILES + t * CATAN_OBS_TILE_DIM;
+      if (!W.overlaps(base, base + CATAN_OBS_TILE_DIM)) continue;
+      uint32_t b[6];
 #pragma unroll
-  for (int r = 0; r < 5; ++r) { hand[r] = g.res(ap, r); W.put(CATAN_OBS_CURRENT_RES + 1 + r, hand[r]); }
-  // ---- tiles (wrapper.py:491-524); tinfo[t] keeps what the production tables need: slot (6 bits, 63 = desert) and the
-  // building weight (settlement 1, city 2) per relative owner, 4 bits each
-  uint32_t tinfo[19];
-  const int robber = g.robber_tile();
-  CATAN_NO_UNROLL
-  for (int t = 0; t < 19; ++t) {
-    const int base = CATAN_OBS_TILES + t * CATAN_OBS_TILE_DIM;
-    W.flush_to(base);
-    const int val = g.tile_val(t), tres = g.tile_res(t);
-    if (robber == t) W.put(base, 1);
-    W.put(base + 1 + val - 2, 1);
-    W.put(base + 12 + tres, 1);
-    // slot of resource index r in the obs order Wood,Brick,Wheat,Ore,Sheep (wrapper.py:550): BRICK->1 WOOD->0 ORE->3 SHEEP->4 WHEAT->2
-    uint32_t info = val == 7 ? 63u : static_cast<uint32_t>(((0x24301 >> (4 * (tres - 1))) & 7) * 10 + (val <= 6 ? val - 2 : val - 3));
+      for (int k = 0; k < 6; ++k) b[k] = g.corner(T.tile_corners[t][k]);   // loads first, scatter afterwards
+      const int val = g.tile_val(t), tres = g.tile_res(t);
+      W.flush_to(base);
+      if (robber == t) W.put(base, 1);
+      W.put(base + 1 + val - 2, 1);
+      W.put(base + 12 + tres, 1);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const uint32_t b = g.corner(T.tile_corners[t][k]);
-      const int cf = base + 18 + k * 7;
-      W.put(cf + (b & 3), 1);                                        // none / settlement / city
-      if (b) {
-        const uint32_t rel = CATAN_REL(b >> 2);
-        W.put(cf + 3 + rel, 1);                                      // owner relative to the actor
-        info += (b & 3u) << (6 + 4 * rel);
+      for (int k = 0; k < 6; ++k) {
+        const int cf = base + 18 + k * 7;
+        W.put(cf + (b[k] & 3), 1);                                   // none / settlement / city
+        if (b[k]) W.put(cf + 3 + CATAN_REL(b[k] >> 2), 1);           // owner relative to the actor
       }
     }
-    tinfo[t] = info;
   }
   // ---- player blocks (wrapper.py:526-709)
-  const int lr_holder = g.lr_holder(), la_holder = g.la_holder();
-  CATAN_NO_UNROLL
-  for (int rel = 0; rel < 4; ++rel) {
-    const int target = CATAN_PID_AT(rel), tp = target - 1;
-    const int m = rel == 0 ? CATAN_OBS_CUR_MAIN : CATAN_OBS_OTHER_MAIN + (rel - 1) * CATAN_OBS_OTHER_MAIN_DIM;
-    const int c = m + (rel == 0 ? 40 : 80);                          // vp 10 | production 50 | road 2 | army 2 | harbours 6
-    W.flush_to(m);
-    if (rel == 0) {
-#pragma unroll
-      for (int r = 0; r < 5; ++r) W.put(m + ((0x24301 >> (4 * r)) & 7) * 8 + t_bucket8(hand[r]), 1);   // wrapper.py:550-562
-    } else {
-#pragma unroll
-      for (int r = 0; r < 5; ++r) {                                  // wrapper.py:563-585
-        const int slot = (0x24301 >> (4 * r)) & 7;
-        W.put(m + slot * 8 + t_bucket8(g.est_min(ap, rel - 1, r)), 1);
-        W.put(m + 40 + slot * 8 + t_bucket8(g.est_max(ap, rel - 1, r)), 1);
-      }
-      W.flush_to(c);
-    }
-    const int vps = g.vp(tp);
-    W.put(c + (vps < 10 ? vps : 9), 1);                              // wrapper.py:587-593
+  if (W.overlaps(CATAN_OBS_CUR_MAIN, CATAN_OBS_DEV_LISTS)) {
+    // tinfo[t] keeps what the production tables need: slot (6 bits, 63 = desert) and the building weight (settlement 1,
+    // city 2) per relative owner, 4 bits each
+    uint32_t tinfo[19];
     CATAN_NO_UNROLL
-    for (int t = 0; t < 19; ++t) {                                   // production table (wrapper.py:595-610)
-      const uint32_t info = tinfo[t];
-      const uint32_t cnt = (info >> (6 + 4 * rel)) & 15u;
-      if (cnt && (info & 63u) != 63u) W.add(c + 10 + (info & 63u), cnt);
-    }
-    if (rel == 0) W.flush_to(c + 60);
-    if (lr_holder) {                                                 // wrapper.py:613-620 (Q9)
-      if (lr_holder == target) { W.put(c + 60, 1); W.put(c + 61, g.lr_count()); }
-      else if (g.has_path_key(tp)) W.put(c + 61, g.cur_longest_path(tp));
-    }
-    if (la_holder == target) W.put(c + 62, 1);                       // wrapper.py:623-627 (Q10)
-    W.put(c + 63, g.cur_army(tp));
-    const int hb = g.harbours(tp);
+    for (int t = 0; t < 19; ++t) {
+      uint32_t b[6];
 #pragma unroll
-    for (int b = 0; b < 6; ++b) W.put(c + 64 + b, (hb >> b) & 1);    // wrapper.py:632-637
-    if (rel == 0) {
+      for (int k = 0; k < 6; ++k) b[k] = g.corner(T.tile_corners[t][k]);
+      const int val = g.tile_val(t), tres = g.tile_res(t);
+      // slot of resource index r in the obs order Wood,Brick,Wheat,Ore,Sheep (wrapper.py:550): BRICK->1 WOOD->0 ORE->3 SHEEP->4 WHEAT->2
+      uint32_t info = val == 7 ? 63u : static_cast<uint32_t>(((0x24301 >> (4 * (tres - 1))) & 7) * 10 + (val <= 6 ? val - 2 : val - 3));
 #pragma unroll
-      for (int r = 0; r < 5; ++r) W.put(m + 110 + ((0x24301 >> (4 * r)) & 7) * 7 + t_bucket7(g.bank(r)), 1);   // wrapper.py:657-672
-      W.put(m + 145 + t_bucket7(g.deck_n()), 1);                     // wrapper.py:674-686
-    } else {
-      W.put(m + 150 + rel - 1, 1);                                   // wrapper.py:532-541
-      const int nh = g.n_hidden(tp);
-      W.put(m + 153 + (nh <= 4 ? nh : 5), 1);                        // wrapper.py:690-695
+      for (int k = 0; k < 6; ++k)
+        if (b[k]) info += (b[k] & 3u) << (6 + 4 * CATAN_REL(b[k] >> 2));
+      tinfo[t] = info;
+    }
+    const int lr_holder = g.lr_holder(), la_holder = g.la_holder();
+    CATAN_NO_UNROLL
+    for (int rel = 0; rel < 4; ++rel) {
+      const int m = rel == 0 ? CATAN_OBS_CUR_MAIN : CATAN_OBS_OTHER_MAIN + (rel - 1) * CATAN_OBS_OTHER_MAIN_DIM;
+      if (!W.overlaps(m, m + (rel == 0 ? CATAN_OBS_CUR_MAIN_DIM : CATAN_OBS_OTHER_MAIN_DIM))) continue;
+      const int target = CATAN_PID_AT(rel), tp = target - 1;
+      const int c = m + (rel == 0 ? 40 : 80);                        // vp 10 | production 50 | road 2 | army 2 | harbours 6
+      W.flush_to(m);
+      if (rel == 0) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) W.put(m + ((0x24301 >> (4 * r)) & 7) * 8 + t_bucket8(g.res(ap, r)), 1);   // wrapper.py:550-562
+      } else {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {                                // wrapper.py:563-585
+          const int slot = (0x24301 >> (4 * r)) & 7;
+          W.put(m + slot * 8 + t_bucket8(g.est_min(ap, rel - 1, r)), 1);
+          W.put(m + 40 + slot * 8 + t_bucket8(g.est_max(ap, rel - 1, r)), 1);
+        }
+        W.flush_to(c);
+      }
+      const int vps = g.vp(tp);
+      W.put(c + (vps < 10 ? vps : 9), 1);                            // wrapper.py:587-593
+      CATAN_NO_UNROLL
+      for (int t = 0; t < 19; ++t) {                                 // production table (wrapper.py:595-610)
+        const uint32_t info = tinfo[t];
+        const uint32_t cnt = (info >> (6 + 4 * rel)) & 15u;
+        if (cnt && (info & 63u) != 63u) W.add(c + 10 + (info & 63u), cnt);
+      }
+      if (rel == 0) W.flush_to(c + 60);
+      if (lr_holder) {                                               // wrapper.py:613-620 (Q9)
+        if (lr_holder == target) { W.put(c + 60, 1); W.put(c + 61, g.lr_count()); }
+        else if (g.has_path_key(tp)) W.put(c + 61, g.cur_longest_path(tp));
+      }
+      if (la_holder == target) W.put(c + 62, 1);                     // wrapper.py:623-627 (Q10)
+      W.put(c + 63, g.cur_army(tp));
+      const int hb = g.harbours(tp);
+#pragma unroll
+      for (int b = 0; b < 6; ++b) W.put(c + 64 + b, (hb >> b) & 1);  // wrapper.py:632-637
+      if (rel == 0) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) W.put(m + 110 + ((0x24301 >> (4 * r)) & 7) * 7 + t_bucket7(g.bank(r)), 1);   // wrapper.py:657-672
+        W.put(m + 145 + t_bucket7(g.deck_n()), 1);                   // wrapper.py:674-686
+      } else {
+        W.put(m + 150 + rel - 1, 1);                                 // wrapper.py:532-541
+        const int nh = g.n_hidden(tp);
+        W.put(m + 153 + (nh <= 4 ? nh : 5), 1);                      // wrapper.py:690-695
+      }
     }
   }
   // ---- development-card lists (wrapper.py:642-655) and the meta bytes
-  int n_list[5];
-  CATAN_NO_UNROLL
-  for (int li = 0; li < 5; ++li) {
-    const int lb = CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD;
-    W.flush_to(lb);
-    const int tp = (li < 2 ? actor : CATAN_PID_AT(li - 1)) - 1;
-    const int n = li == 1 ? g.n_hidden(tp) : g.n_played(tp);
-    n_list[li] = n;
-    if (li == 1) { for (int j = 0; j < n; ++j) W.put(lb + j, g.hidden(tp, j) + 1); }
-    else { for (int j = 0; j < n; ++j) W.put(lb + j, g.played(tp, j) + 1); }
+  if (W.overlaps(CATAN_OBS_DEV_LISTS, CATAN_OBS_STRIDE)) {
+    int n_list[5];
+    CATAN_NO_UNROLL
+    for (int li = 0; li < 5; ++li) {
+      const int lb = CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD;
+      W.flush_to(lb);
+      const int tp = (li < 2 ? actor : CATAN_PID_AT(li - 1)) - 1;
+      const int n = li == 1 ? g.n_hidden(tp) : g.n_played(tp);
+      n_list[li] = n;
+      if (li == 1) { for (int j = 0; j < n; ++j) W.put(lb + j, g.hidden(tp, j) + 1); }
+      else { for (int j = 0; j < n; ++j) W.put(lb + j, g.played(tp, j) + 1); }
+    }
+    W.flush_to(CATAN_OBS_META);
+    W.put(CATAN_OBS_META, actor);
+    W.put(CATAN_OBS_META + 1, n_list[0]);
+    W.put(CATAN_OBS_META + 2, n_list[1]);
+    W.put(CATAN_OBS_META + 3, n_list[2]);
+    W.put(CATAN_OBS_META + 4, n_list[3]);
+    W.put(CATAN_OBS_META + 5, n_list[4]);
   }
-  W.flush_to(CATAN_OBS_META);
-  W.put(CATAN_OBS_META, actor);
-  W.put(CATAN_OBS_META + 1, n_list[0]);
-  W.put(CATAN_OBS_META + 2, n_list[1]);
-  W.put(CATAN_OBS_META + 3, n_list[2]);
-  W.put(CATAN_OBS_META + 4, n_list[3]);
-  W.put(CATAN_OBS_META + 5, n_list[4]);
-  W.flush_to(CATAN_OBS_STRIDE);
+  W.flush_to(hi);
 #undef CATAN_REL
 #undef CATAN_PID_AT
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bytes [lo, hi) of the row inside the header + tile region [0, 1152) -- 60 % of the row -- without the window: all of
+// these features are 0/1 bytes, so a tile is first built as a 60-bit set in registers (bit j = byte j of the tile's
+// block) and the stream of bits is then expanded 16 bits -> 16 bytes per vector store.  The five hand counts of the
+// header are patched into the two pieces they fall in.
+// ------------------------------------------------------------------------------------------------
+CATAN_FN uint64_t t_tile_bits(const GameView& g, const Topo& T, int t, int robber, uint32_t relpack) {
+  uint32_t b[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) b[k] = g.corner(T.tile_corners[t][k]);
+  const int val = g.tile_val(t), tres = g.tile_res(t);
+  uint32_t w0 = static_cast<uint32_t>(robber == t) | (1u << (val - 1)) | (1u << (12 + tres)), w1 = 0;   // wrapper.py:497-509
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {                                      // wrapper.py:510-523: none/settlement/city, owner relative to the actor
+    const uint32_t rel = (relpack >> (2 * (b[k] >> 2))) & 3u;
+    const uint32_t f = (1u << (b[k] & 3u)) | (static_cast<uint32_t>(b[k] != 0) << (3 + rel));   // the corner's 7 bytes
+    if (k < 2) w0 |= f << (18 + 7 * k); else w1 |= f << (7 * (k - 2));
+  }
+  return static_cast<uint64_t>(w0) | (static_cast<uint64_t>(w1) << 32);
+}
+
+CATAN_FN_NOINLINE void t_encode_obs_tiles(const TCx& cx, uint8_t* row, int lo, int hi) {
+  const GameView& g = cx.g;
+  const Topo& T = *cx.T;
+  const int actor = t_current_actor(g), ap = actor - 1, aseat = seat_of(cx.s, actor), robber = g.robber_tile();
+  uint32_t relpack = 0;
+#pragma unroll
+  for (int p = 1; p <= 4; ++p) relpack |= static_cast<uint32_t>((seat_of(cx.s, p) - aseat + 4) & 3) << (2 * p);
+  uint64_t acc_lo = 0, acc_hi = 0;       // pending bits: bit i = byte pos + i of the row
+  int fill = 0, pos = lo, t = 0;
+  uint32_t hand012 = 0, hand34 = 0;
+  if (lo == 0) {                                                     // [0, 18): proposed trade (wrapper.py:61-69, Q15), hand (:70-71)
+    uint32_t tr = 0;
+    if (g.trade_proposer()) {
+      const int ng = g.n_give(), nr = g.n_recv();
+      for (int k = 0; k < ng; ++k) tr |= 1u << (CATAN_OBS_PROPOSED_TRADE + g.give(k));
+      for (int k = 0; k < nr; ++k) tr |= 1u << (CATAN_OBS_PROPOSED_TRADE + g.recv(k) + 5);
+    }
+    acc_lo = tr; fill = CATAN_OBS_TILES;
+    hand012 = (static_cast<uint32_t>(g.res(ap, 0)) << 8) | (static_cast<uint32_t>(g.res(ap, 1)) << 16) | (static_cast<uint32_t>(g.res(ap, 2)) << 24);
+    hand34 = static_cast<uint32_t>(g.res(ap, 3)) | (static_cast<uint32_t>(g.res(ap, 4)) << 8);
+  } else {                                                           // start inside tile t: drop its bytes below lo
+    t = (lo - CATAN_OBS_TILES) / CATAN_OBS_TILE_DIM;
+    const int skip = lo - (CATAN_OBS_TILES + t * CATAN_OBS_TILE_DIM);
+    acc_lo = t_tile_bits(g, T, t, robber, relpack) >> skip;
+    fill = CATAN_OBS_TILE_DIM - skip;
+    ++t;
+  }
+  struct alignas(16) V16 { uint32_t a, b, c, d; };
+  CATAN_NO_UNROLL
+  while (pos < hi) {
+    if (fill < 16) {                                                 // (t < 19 here: the region ends inside tile 18)
+      const uint64_t m = t_tile_bits(g, T, t, robber, relpack);
+      ++t;
+      acc_lo |= m << fill;
+      acc_hi = fill > 4 ? m >> (64 - fill) : 0ull;
+      fill += CATAN_OBS_TILE_DIM;
+    }
+    const uint32_t b16 = static_cast<uint32_t>(acc_lo) & 0xffffu;
+    V16 v = {spread4(b16 & 15u), spread4((b16 >> 4) & 15u), spread4((b16 >> 8) & 15u), spread4(b16 >> 12)};
+    if (pos == 0) v.d |= hand012;                                    // bytes 13..15 = CATAN_OBS_CURRENT_RES + 1 + r
+    if (pos == 16) v.a |= hand34;                                    // bytes 16, 17
+#ifdef CATAN_DEVICE
+    __stcs(reinterpret_cast<uint4*>(row + pos), make_uint4(v.a, v.b, v.c, v.d));
+#else
+    *reinterpret_cast<V16*>(row + pos) = v;
+#endif
+    acc_lo = (acc_lo >> 16) | (acc_hi << 48);
+    acc_hi >>= 16;
+    fill -= 16;
+    pos += 16;
+  }
+}
+static_assert(CATAN_OBS_PROPOSED_TRADE == 0 && CATAN_OBS_CURRENT_RES == 12 && CATAN_OBS_TILES == 18 && CATAN_OBS_TILE_DIM == 60,
+              "t_encode_obs_tiles packs the header by hand");
+
+// The cuts used by the device encoder: CATAN_OBS_PARTS threads share one row.  Parts 0 .. CATAN_OBS_TILE_PARTS-1 lie in
+// the header + tile region (t_encode_obs_tiles), the others go through the window (t_encode_obs).
+#define CATAN_OBS_PARTS 5
+#define CATAN_OBS_TILE_PARTS 2
+#define CATAN_OBS_TILE_END 1152
+CATAN_FN int t_obs_part_lo(int part) {
+  return part == 0 ? 0 : part == 1 ? 592 : part == 2 ? CATAN_OBS_TILE_END : part == 3 ? 1472 : part == 4 ? 1792 : CATAN_OBS_STRIDE;
+}
+template <int NT>
+CATAN_FN void t_encode_obs_part(const TCx& cx, uint32_t* ring, uint8_t* row, int part) {
+  if (part < CATAN_OBS_TILE_PARTS) t_encode_obs_tiles(cx, row, t_obs_part_lo(part), t_obs_part_lo(part + 1));
+  else t_encode_obs<NT>(cx, ring, row, t_obs_part_lo(part), t_obs_part_lo(part + 1));
 }
 
 }  // namespace catanb

@@ -2,15 +2,16 @@
 //
 // One env step is three launches on the caller's stream (catan_game.cuh holds the game logic):
 //
-//   transition_kernel   ONE THREAD PER GAME.  translate + validate + apply_action incl. dice payout and belief updates,
-//                       straight on the lane-interleaved game records in HBM/L2 (every field access of a warp is one
-//                       fully used 32-byte sector).  Games whose road network changed are appended to a device queue.
-//   longest_road_kernel the queued longest-road re-evaluations (game.py:843-919), searched block-cooperatively: the
-//                       node-simple path enumeration of all games of a batch is one pool of work units that 1024 lanes
-//                       drain in rounds (lp_round), so a dense road network cannot pin a lane -- or a warp of 32 games.
-//   encode_kernel       ONE THREAD PER GAME.  done / reward / info (+ auto-reset by the warp), legal-action masks as bit
-//                       sets, the fused random-legal sampler, and the packed observation row streamed out through a
-//                       128-byte sliding window per thread.
+//   transition_kernel   ONE THREAD PER GAME for translate + validate + the scalar part of apply_action, straight on the
+//                       lane-interleaved game records in HBM/L2 (every field access of a warp is one fully used 32-byte
+//                       sector); the data-parallel follow-ups (dice payout, belief updates) one warp per game.  Games
+//                       whose road network changed are appended to a device queue.
+//   lr_fast_kernel      the queued longest-road updates (game.py:843-919), one thread each: an incremental rule settles
+//   lr_slow_kernel      ~95 % of them with two tiny searches; the rest gets the reference's full enumeration, one block
+//                       per update, cut into work units that 256 lanes claim and re-split in rounds (lp_round).
+//   encode_kernel       One block per chunk of 32 games, one game per lane: warp 0 does done / reward / info (+ auto-reset),
+//                       the legal-action masks as bit sets and the fused random-legal sampler; seven more warps stream
+//                       out one piece of the packed observation row each through a 128-byte sliding window per thread.
 //
 // Why not one fused kernel: the search is the only part of a step whose cost varies by four orders of magnitude between
 // games; inside a thread-per-game kernel it would stall 31 other games per unit of imbalance (profiles/r1_notes.md).
@@ -30,18 +31,18 @@ namespace catanb {
 __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 
 // ---- launch shapes ------------------------------------------------------------------------------
-constexpr int kGameThreads = 64;            // transition / encode: threads (= games) per block; small blocks keep the
-                                            // 148 SMs evenly loaded at 65 536 games (1024 blocks ~ 7 per SM)
-constexpr int kLrThreads = 1024;            // longest_road_kernel: one persistent block per SM
-constexpr int kLrWarps = kLrThreads / 32;
-constexpr int kLpBudget = 128;              // loop iterations per search round before unfinished subtrees are re-queued
-constexpr int kMaxJobs = 39;                // road graphs searched per cooperative pass (13 games x 3 when re-measuring)
-constexpr int kLpRingTasks = 2048;          // per-block queue of re-split subtrees (global memory, L2 resident)
+constexpr int kTransWarps = 4;              // transition_kernel: warps per chunk of 32 games
+constexpr int kTransThreads = kTransWarps * 32;
+constexpr int kEncWarps = 1 + CATAN_OBS_PARTS;   // encode_kernel: finish/masks/sampler warp + one warp per piece of the obs row
+constexpr int kEncThreads = kEncWarps * 32;
+constexpr int kLrFastThreads = 64;          // lr_fast_kernel: one thread per queued update
+constexpr int kLrSlowThreads = 256;         // lr_slow_kernel: one block per update that needs the full enumeration
+constexpr int kLrSlowBlocksPerSM = 4;
 constexpr int kSampleThreads = 128;         // stand-alone sampler kernel
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
-struct LrCtl { int32_t count, ticket; };    // queue length written by transition_kernel, batch ticket of longest_road_kernel
+struct LrCtl { int32_t count, slow_count; unsigned long long total, slow_total, dbg[6]; };   // dbg: job cycles sum/max, rounds sum/max, full-search jobs, -   // queue lengths: written by transition_kernel / lr_fast_kernel, cleared by encode_kernel
 
 struct EnvParams {
   uint8_t* recs;               // lane-interleaved chunks of 32 games (catan_game.cuh)
@@ -58,10 +59,9 @@ struct EnvParams {
   const uint8_t* env_mask;     // envs whose byte is 0 are left untouched; nullptr = all envs
   int range_first, range_count;   // env range this launch covers
   uint32_t* side;              // [n] transition -> encode: err | acted_pid << 8 | act_type << 16 | roll << 24
-  uint32_t* lr_queue;          // [n] env index | PlayerId << 28
+  uint64_t* lr_queue;          // [n] env index | PlayerId << 32 | edge or corner << 40 | CATAN_LR_* << 48 | acting PlayerId << 56
+  uint64_t* lr_slow_queue;     // [n] the entries lr_fast_kernel could not settle
   LrCtl* lr_ctl;
-  LpTask* lp_ring;             // [gridDim.x][kLpRingTasks]
-  int lp_budget;
 };
 
 struct GameSmem {
@@ -77,148 +77,222 @@ __device__ __forceinline__ void stage_topology(GameSmem& S, int tid, int nthread
   __syncthreads();
 }
 
+// all lines of the chunk -> L2, issued before anything depends on them: a game's fields are spread over the whole chunk,
+// and the dependent loads of the rule code would otherwise walk to DRAM one miss at a time
+__device__ __forceinline__ void prefetch_chunk(const uint8_t* recs, int first_game, int tid, int nthreads) {
+  const uint8_t* chunk = recs + static_cast<size_t>(first_game >> 5) * CATAN_CHUNK_BYTES;
+  for (int o = tid * 128; o < static_cast<int>(CATAN_CHUNK_BYTES); o += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(chunk + o));
+}
+
 // ---- 1. transition ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGameThreads) transition_kernel(const __grid_constant__ EnvParams P) {
-  __shared__ __align__(16) GameSmem S;
-  stage_topology(S, threadIdx.x, kGameThreads);
-  const int i = (P.range_first & ~31) + blockIdx.x * kGameThreads + threadIdx.x;
-  if (i < P.range_first || i >= P.range_first + P.range_count) return;
-  if (P.env_mask != nullptr && P.env_mask[i] == 0) return;
-  TCx cx;
-  cx.g = game_view(P.recs, static_cast<size_t>(i));
-  cx.T = &S.topo; cx.X = &S.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
-  cx.s = load_seats(cx.g);
-  StepTmp tmp;
-  t_step_transition(cx, P.actions + static_cast<size_t>(i) * CATAN_ACTION_WORDS, tmp);
-  P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
-              (static_cast<uint32_t>(tmp.roll_info) << 24);
-  if (tmp.err) {
-    P.err_flags[i] |= 1u << tmp.err;
-  } else if (tmp.lr_pid) {
-    const int slot = atomicAdd(&P.lr_ctl->count, 1);
-    P.lr_queue[slot] = static_cast<uint32_t>(i) | (static_cast<uint32_t>(tmp.lr_pid) << 28);
+// One block per chunk of 32 games.  Warp 0 runs the scalar part of apply_action, one game per lane; the data-parallel
+// follow-ups it posts (dice payout over 19 tiles x 6 corners, belief updates over 60 entries) are then executed by all
+// warps of the block, one warp per game and one lane per item.
+struct alignas(16) TransSmem {
+  GameSmem topo;
+  StepTmp tmp[32];
+  int32_t n_follow;
+  uint8_t follow_list[32];
+};
+
+__global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_constant__ EnvParams P) {
+  __shared__ TransSmem S;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int base = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32;
+  prefetch_chunk(P.recs, base, tid, kTransThreads);
+  stage_topology(S.topo, tid, kTransThreads);
+  if (warp == 0) {
+    const int i = base + lane;
+    const bool valid = i >= P.range_first && i < P.range_first + P.range_count && !(P.env_mask != nullptr && P.env_mask[i] == 0);
+    bool follow = false;
+    if (valid) {
+      TCx cx;
+      cx.g = game_view(P.recs, static_cast<size_t>(i));
+      cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
+      cx.s = load_seats(cx.g);
+      StepTmp& tmp = S.tmp[lane];
+      t_step_scalar(cx, P.actions + static_cast<size_t>(i) * CATAN_ACTION_WORDS, tmp);
+      P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
+                  (static_cast<uint32_t>(tmp.roll_info) << 24);
+      if (tmp.err) {
+        P.err_flags[i] |= 1u << tmp.err;
+      } else if (tmp.lr_pid) {
+        const int slot = atomicAdd(&P.lr_ctl->count, 1);
+        P.lr_queue[slot] = static_cast<uint64_t>(static_cast<uint32_t>(i)) | (static_cast<uint64_t>(tmp.lr_pid) << 32) | (static_cast<uint64_t>(tmp.lr_loc) << 40) |
+                           (static_cast<uint64_t>(tmp.lr_kind) << 48) | (static_cast<uint64_t>(tmp.acted_pid) << 56);
+      }
+      follow = tmp.follow != 0;
+    }
+    const unsigned fb = __ballot_sync(0xffffffffu, follow);
+    if (follow) S.follow_list[__popc(fb & ((1u << lane) - 1u))] = static_cast<uint8_t>(lane);
+    if (lane == 0) S.n_follow = __popc(fb);
+  }
+  __syncthreads();
+  const int nf = S.n_follow;
+  for (int j = warp; j < nf; j += kTransWarps) {
+    const int gi = S.follow_list[j];
+    t_followups_group(game_view(P.recs, static_cast<size_t>(base + gi)), S.topo.topo, S.tmp[gi], lane, 32);
   }
 }
 
 // ---- 2. longest road ----------------------------------------------------------------------------
+// Measured on random play at ticks 1000-1600 (oracle, 21 k updates): 3.5 % of the steps trigger an update; the reference's
+// full enumeration visits 205 corners on average and 13 k at most.
+//   lr_fast_kernel  one THREAD per queued update: the incremental rule of t_lr_fast() settles ~95 % of them with two
+//                   searches of ~10 visits; the rest goes to a second queue.
+//   lr_slow_kernel  one BLOCK per remaining update: the enumeration of the paths through the new road -- or, when the
+//                   stored length cannot be trusted, the reference's full enumeration -- as a pool of 16-byte subtree
+//                   tasks that 256 lanes drain and re-split in rounds (lp_round).
+constexpr int kLrRing = 2048;               // task ring of the pool (shared memory; a power of two >= 4 x lanes + 64)
 struct alignas(16) LrSmem {
   Topo topo;
-  uint64_t adj[kMaxJobs * 54];
-  uint8_t paths[54 * kLrThreads];
-  int32_t lp_best[kMaxJobs];
-  int32_t lp_ctl[8];
-  int32_t start, n_shrunk;
-  uint32_t entry[kMaxJobs];
-  uint8_t len[kMaxJobs], shrunk[kMaxJobs], shrunk_list[kMaxJobs];
-  uint8_t other[kMaxJobs][5];
+  uint64_t adj[54], adjb[54];
+  LpTask ring[kLrRing];
+  uint8_t paths[54 * kLrSlowThreads];
+  int32_t best[4];
+  int32_t ctl[CATAN_LP_CTL_WORDS];
+  int32_t rounds, tasks;     // diagnostics: walk steps and tasks of the current update
 };
 
-__global__ void __launch_bounds__(kLrThreads, 1) longest_road_kernel(const __grid_constant__ EnvParams P) {
+__global__ void __launch_bounds__(kLrFastThreads) lr_fast_kernel(const __grid_constant__ EnvParams P) {
+  __shared__ __align__(16) Topo sT;
+  const int count = P.lr_ctl->count;
+  if (static_cast<int>(blockIdx.x) >= count) return;
+  {
+    const int4* src = reinterpret_cast<const int4*>(&d_topo);
+    int4* dst = reinterpret_cast<int4*>(&sT);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(Topo) / 16); i += kLrFastThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  // update j goes to thread j / gridDim of block j % gridDim: a short queue is spread over all SMs, and a warp waits for
+  // the slowest of fewer searches
+  for (int j = static_cast<int>(threadIdx.x * gridDim.x + blockIdx.x); j < count; j += static_cast<int>(gridDim.x) * kLrFastThreads) {
+    const uint64_t en = P.lr_queue[j];
+    const GameView g = game_view(P.recs, static_cast<uint32_t>(en));
+    const int pid = static_cast<int>((en >> 32) & 0xff), loc = static_cast<int>((en >> 40) & 0xff), kind = static_cast<int>((en >> 48) & 0xff),
+              placer = static_cast<int>(en >> 56);
+    const int len = t_lr_fast(g, sT, pid, kind, loc, placer);
+    if (len >= 0) t_lr_apply(g, pid, len, false, nullptr);
+    else P.lr_slow_queue[atomicAdd(&P.lr_ctl->slow_count, 1)] = en;
+  }
+}
+
+__device__ __forceinline__ int block_longest_path(LrSmem& S, const GameView& g, int pid, int tid) {
+  if (tid < 32) t_lp_build_adj(g, S.topo, pid, S.adj, tid, 32);
+  if (tid == 0) S.best[0] = 0;
+  __syncthreads();
+  CATAN_LP_RUN(S.adj, S.adj, -1, -1, S.ctl, S.best, S.paths, kLrSlowThreads, tid, S.ring, kLrRing, tid == 0, __syncthreads());
+  if (tid == 0) { S.rounds += S.ctl[3]; S.tasks += S.ctl[1]; }
+  const int r = S.best[0];
+  __syncthreads();
+  return r;
+}
+// longest path that contains the new road `edge` (block-cooperative twin of t_through_edge)
+__device__ __forceinline__ int block_through_edge(LrSmem& S, const GameView& g, int pid, int edge, int tid) {
+  int through = 0;
+  for (int dir = 0; dir < 2; ++dir) {
+    const int a = S.topo.edge_corners[edge][dir], b = S.topo.edge_corners[edge][dir ^ 1];
+    const uint8_t bd = g.corner(a);
+    if (bd && (bd >> 2) != pid) continue;                            // (block-uniform) a is blocked: no arc a -> b
+    if (tid < 32) t_lp_build_adj2(g, S.topo, pid, S.adj, S.adjb, b, tid, 32);
+    if (tid == 0) S.best[0] = 0;
+    __syncthreads();
+    CATAN_LP_RUN(S.adj, S.adjb, b, a, S.ctl, S.best, S.paths, kLrSlowThreads, tid, S.ring, kLrRing, tid == 0, __syncthreads());
+    if (tid == 0) { S.rounds += S.ctl[3]; S.tasks += S.ctl[1]; }
+    through = max(through, S.best[0]);
+    __syncthreads();
+  }
+  return through;
+}
+
+__global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_constant__ EnvParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   LrSmem& S = *reinterpret_cast<LrSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int count = P.lr_ctl->count;
-  if (count == 0) return;
+  const int tid = threadIdx.x;
+  const int count = P.lr_ctl->slow_count;
+  if (static_cast<int>(blockIdx.x) >= count) return;
   {
     const int4* src = reinterpret_cast<const int4*>(&d_topo);
     int4* dst = reinterpret_cast<int4*>(&S.topo);
-    for (int i = tid; i < static_cast<int>(sizeof(Topo) / 16); i += kLrThreads) dst[i] = src[i];
+    for (int i = tid; i < static_cast<int>(sizeof(Topo) / 16); i += kLrSlowThreads) dst[i] = src[i];
   }
-  // jobs per claim: spread the queue over the blocks, at most kMaxJobs at a time
-  int per = (count + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  per = per < 1 ? 1 : (per > kMaxJobs ? kMaxJobs : per);
-  LpTask* ring = P.lp_ring + static_cast<size_t>(blockIdx.x) * kLpRingTasks;
-  for (;;) {
-    __syncthreads();                                                 // previous batch retired; S.start reusable
-    if (tid == 0) { S.start = atomicAdd(&P.lr_ctl->ticket, per); S.n_shrunk = 0; }
-    __syncthreads();
-    const int start = S.start;
-    if (start >= count) break;
-    const int nj = min(per, count - start);
-    if (tid < nj) { S.entry[tid] = P.lr_queue[start + tid]; S.lp_best[tid] = 0; }
-    __syncthreads();
-    // pass A: the player whose road network changed
-    for (int j = warp; j < nj; j += kLrWarps) {
-      const uint32_t en = S.entry[j];
-      t_lp_build_adj(game_view(P.recs, en & 0x0fffffffu), S.topo, static_cast<int>(en >> 28), S.adj + j * 54, lane, 32);
+  __syncthreads();
+  for (int j = static_cast<int>(blockIdx.x); j < count; j += static_cast<int>(gridDim.x)) {
+    const uint64_t en = P.lr_slow_queue[j];
+    const GameView g = game_view(P.recs, static_cast<uint32_t>(en));
+    const int pid = static_cast<int>((en >> 32) & 0xff), loc = static_cast<int>((en >> 40) & 0xff), kind = static_cast<int>((en >> 48) & 0xff);
+    const long long t_start = clock64();
+    bool was_full = true;
+    if (tid == 0) { S.rounds = 0; S.tasks = 0; }
+    if (kind == CATAN_LR_ROAD && loc != 0xff && !g.lr_dirty(pid - 1)) {
+      was_full = false;
+      // the stored length is exact: only the paths through the new road can beat it
+      const int old = g.lr_holder() == pid ? g.lr_count() : (g.has_path_key(pid - 1) ? g.cur_longest_path(pid - 1) : 0);
+      const int through = block_through_edge(S, g, pid, loc, tid);
+      if (tid == 0) t_lr_apply(g, pid, max(through, old), false, nullptr);
+    } else {
+      const int len = block_longest_path(S, g, pid, tid);
+      const bool shrunk = t_lr_is_shrunk(g, pid, len);               // game.py:880-881: re-measure the other three players
+      uint8_t other[5] = {0, 0, 0, 0, 0};
+      if (shrunk)
+        for (int o = WHITE; o <= RED; ++o)
+          if (o != pid) other[o] = static_cast<uint8_t>(block_longest_path(S, g, o, tid));
+      if (tid == 0) { t_lr_apply(g, pid, len, shrunk, other); g.lr_dirty(pid - 1) = 0; }
     }
-    __syncthreads();
-    CATAN_LP_RUN(S.adj, nj, S.lp_ctl, S.lp_best, S.paths, kLrThreads, tid, ring, kLpRingTasks, P.lp_budget, tid == 0, __syncthreads(), (void)0);
-    __syncthreads();
-    if (tid < nj) {
-      const uint32_t en = S.entry[tid];
-      const int len = S.lp_best[tid];
-      const bool sh = t_lr_is_shrunk(game_view(P.recs, en & 0x0fffffffu), static_cast<int>(en >> 28), len);
-      S.len[tid] = static_cast<uint8_t>(len);
-      S.shrunk[tid] = sh;
-      if (sh) S.shrunk_list[atomicAdd(&S.n_shrunk, 1)] = static_cast<uint8_t>(tid);
-    }
-    __syncthreads();
-    // pass B (rare, game.py:880-881): the holder's path shrank -> re-measure the other three players
-    const int n_sh = S.n_shrunk;
-    for (int c0 = 0; c0 < n_sh; c0 += kMaxJobs / 3) {
-      const int ng = min(kMaxJobs / 3, n_sh - c0), nb = 3 * ng;
-      for (int j = warp; j < nb; j += kLrWarps) {
-        const uint32_t en = S.entry[S.shrunk_list[c0 + j / 3]];
-        const int pid = static_cast<int>(en >> 28);
-        int o = j % 3 + 1;
-        if (o >= pid) ++o;
-        t_lp_build_adj(game_view(P.recs, en & 0x0fffffffu), S.topo, o, S.adj + j * 54, lane, 32);
-      }
-      if (tid < nb) S.lp_best[tid] = 0;
-      __syncthreads();
-      CATAN_LP_RUN(S.adj, nb, S.lp_ctl, S.lp_best, S.paths, kLrThreads, tid, ring, kLpRingTasks, P.lp_budget, tid == 0, __syncthreads(), (void)0);
-      __syncthreads();
-      if (tid < nb) {
-        const int job = S.shrunk_list[c0 + tid / 3];
-        const int pid = static_cast<int>(S.entry[job] >> 28);
-        int o = tid % 3 + 1;
-        if (o >= pid) ++o;
-        S.other[job][o] = static_cast<uint8_t>(S.lp_best[tid]);
-      }
-      __syncthreads();
-    }
-    if (tid < nj) {
-      const uint32_t en = S.entry[tid];
-      t_lr_apply(game_view(P.recs, en & 0x0fffffffu), static_cast<int>(en >> 28), S.len[tid], S.shrunk[tid] != 0, S.other[tid]);
+    __syncthreads();                                                 // everybody has read the game before its next update
+    if (tid == 0) {
+      const unsigned long long dt = static_cast<unsigned long long>(clock64() - t_start);
+      atomicAdd(&P.lr_ctl->dbg[0], dt); atomicMax(&P.lr_ctl->dbg[1], dt);
+      atomicAdd(&P.lr_ctl->dbg[2], static_cast<unsigned long long>(S.rounds)); atomicMax(&P.lr_ctl->dbg[3], static_cast<unsigned long long>(S.rounds));
+      if (was_full) atomicAdd(&P.lr_ctl->dbg[4], 1ull);
+      atomicAdd(&P.lr_ctl->dbg[5], static_cast<unsigned long long>(S.tasks));
     }
   }
 }
 
 // ---- 3. finish + masks + sampler + observation --------------------------------------------------
+// One block per chunk of 32 games, one game per lane in every warp.  Warp 0: done / reward / info (+ auto-reset), then
+// the legal-action masks and the fused sampler.  Warps 1..CATAN_OBS_PARTS: one 16-byte aligned piece of the observation
+// row each (t_obs_part_lo): the header + tile pieces as bit sets expanded in registers, the player blocks and card
+// lists through a 128-byte window per thread.
+constexpr int kObsRingThreads = (CATAN_OBS_PARTS - CATAN_OBS_TILE_PARTS) * 32;   // the tile parts build their pieces in registers
 struct alignas(16) EncSmem {
   GameSmem topo;
-  uint32_t ring[(CATAN_RING_BYTES / 4) * kGameThreads];             // RowWriter windows, word-interleaved over the block
-  uint32_t wbuf[kGameThreads / 32][CATAN_RESET_WORDS];              // reset: pre-drawn Philox words, per warp
-  uint8_t arr[kGameThreads / 32][96];                               // reset: shuffle arrays, per warp
+  uint32_t ring[(CATAN_RING_BYTES / 4) * kObsRingThreads];          // RowWriter windows, word-interleaved over those threads
+  uint32_t wbuf[CATAN_RESET_WORDS];                                 // reset: pre-drawn Philox words (warp 0)
+  uint8_t arr[96];                                                  // reset: shuffle arrays (warp 0)
 };
 
 template <int MODE, bool SAMPLE>
-__global__ void __launch_bounds__(kGameThreads) encode_kernel(const __grid_constant__ EnvParams P) {
+__global__ void __launch_bounds__(kEncThreads) encode_kernel(const __grid_constant__ EnvParams P) {
   __shared__ EncSmem S;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  stage_topology(S.topo, tid, kGameThreads);
-  if (blockIdx.x == 0 && tid == 0) { P.lr_ctl->count = 0; P.lr_ctl->ticket = 0; }   // the queue of this step has been consumed
-  const int i = (P.range_first & ~31) + blockIdx.x * kGameThreads + tid;
+  prefetch_chunk(P.recs, (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32, tid, kEncThreads);
+  stage_topology(S.topo, tid, kEncThreads);
+  if (blockIdx.x == 0 && tid == 0) {
+    P.lr_ctl->total += static_cast<unsigned long long>(P.lr_ctl->count); P.lr_ctl->slow_total += static_cast<unsigned long long>(P.lr_ctl->slow_count);
+    P.lr_ctl->count = 0; P.lr_ctl->slow_count = 0;
+  }   // the queue of this step has been consumed
+  const int i = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32 + lane;
   const bool valid = i >= P.range_first && i < P.range_first + P.range_count && !(MODE != MODE_REFRESH && P.env_mask != nullptr && P.env_mask[i] == 0);
   TCx cx;
   cx.g = game_view(P.recs, static_cast<size_t>(valid ? i : P.range_first));
   cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
   uint8_t* info = P.info + static_cast<size_t>(i) * CATAN_INFO_STRIDE;
-  bool need_reset = false;
-  if (MODE == MODE_STEP) {
-    if (valid) {
-      cx.s = load_seats(cx.g);
-      const uint32_t sd = P.side[i];
-      StepTmp tmp;
-      tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
-      tmp.roll_info = static_cast<uint8_t>(sd >> 24);
-      need_reset = t_step_finish(cx, tmp, P.reward + static_cast<size_t>(i) * 4, info);
+  if (warp == 0 && MODE != MODE_REFRESH) {
+    bool need_reset = false;
+    if (MODE == MODE_STEP) {
+      if (valid) {
+        cx.s = load_seats(cx.g);
+        const uint32_t sd = P.side[i];
+        StepTmp tmp;
+        tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
+        tmp.roll_info = static_cast<uint8_t>(sd >> 24);
+        need_reset = t_step_finish(cx, tmp, P.reward + static_cast<size_t>(i) * 4, info);
+      }
+    } else {
+      need_reset = valid;
     }
-  } else if (MODE == MODE_RESET) {
-    need_reset = valid;
-  }
-  if (MODE != MODE_REFRESH) {
     // Board.reset + Game.reset are a handful of serial shuffles: the warp does them game by game (lanes pre-draw the
     // Philox words in parallel).  Rare in a step (a game ends every ~1500 steps), everything in catan_reset.
     unsigned rb = __ballot_sync(0xffffffffu, need_reset);
@@ -227,30 +301,48 @@ __global__ void __launch_bounds__(kGameThreads) encode_kernel(const __grid_const
       const int b = __ffs(static_cast<int>(rb)) - 1;
       rb &= rb - 1;
       const int e = warp_first + b;
-      reset_game_group(game_view(P.recs, static_cast<size_t>(e)), S.topo.topo, P.seed, P.first_env_id + static_cast<uint64_t>(e), S.wbuf[warp], S.arr[warp],
+      reset_game_group(game_view(P.recs, static_cast<size_t>(e)), S.topo.topo, P.seed, P.first_env_id + static_cast<uint64_t>(e), S.wbuf, S.arr,
                        lane, 32, MODE == MODE_STEP ? P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE : nullptr);
     }
   }
-  if (!valid) return;
-  if (MODE != MODE_STEP || need_reset) cx.s = load_seats(cx.g);
-  if (MODE != MODE_STEP) t_write_info_fresh(cx.g, info, MODE == MODE_RESET);
-  MaskBits m;
-  t_build_masks(cx, m);
-  {
-    MaskFlat F;
-    t_flatten_masks(m, F);
-    t_store_mask_row(F, P.masks + static_cast<size_t>(i) * CATAN_MASK_STRIDE);
-  }
-  if (SAMPLE) {
-    const int ap = t_current_actor(cx.g) - 1;
-    uint32_t hand = 0;
+  __syncthreads();                                                   // the games are final: every warp may read them now
+  if (valid) cx.s = load_seats(cx.g);
+  if (warp == 0) {                                                   // (all 32 lanes stay: the scan below is a warp collective)
+    if (MODE != MODE_STEP && valid) t_write_info_fresh(cx.g, info, MODE == MODE_RESET);
+    MaskBits m;
+    MaskPlan pl;
+    pl.post = 0;
+    Scan sc = {};
+    // the board scan (54 corners, 72 edges, 19 tiles) of the few games that are in a placement phase: by the whole warp,
+    // one game at a time and one lane per corner / edge
+    unsigned nb = __ballot_sync(0xffffffffu, valid && t_masks_pre(cx, m, pl));
+    const int scan_pid = cx.g.players_go();
+    while (nb) {
+      const int b = __ffs(static_cast<int>(nb)) - 1;
+      nb &= nb - 1;
+      const Scan r = t_scan_group(game_view(P.recs, static_cast<size_t>(i - lane + b)), S.topo.topo, S.topo.topox,
+                                  __shfl_sync(0xffffffffu, scan_pid, b), lane, 32);
+      if (lane == b) sc = r;
+    }
+    if (!valid) return;
+    if (pl.post) t_masks_post(cx, m, pl, sc);
+    {
+      MaskFlat F;
+      t_flatten_masks(m, F);
+      t_store_mask_row(F, P.masks + static_cast<size_t>(i) * CATAN_MASK_STRIDE);
+    }
+    if (SAMPLE) {
+      const int ap = t_current_actor(cx.g) - 1;
+      uint32_t hand = 0;
 #pragma unroll
-    for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(cx.g.res(ap, r) != 0) << r;
-    const uint32_t decision = cx.g.decision_ctr();
-    cx.g.decision_ctr() = decision + 1;
-    t_sample_action(m, hand, P.seed, cx.env_id, decision, P.actions_out + static_cast<size_t>(i) * CATAN_ACTION_WORDS);
+      for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(cx.g.res(ap, r) != 0) << r;
+      const uint32_t decision = cx.g.decision_ctr();
+      cx.g.decision_ctr() = decision + 1;
+      t_sample_action(m, hand, P.seed, cx.env_id, decision, P.actions_out + static_cast<size_t>(i) * CATAN_ACTION_WORDS);
+    }
+  } else if (valid) {
+    t_encode_obs_part<kObsRingThreads>(cx, S.ring + (tid - 32 * (1 + CATAN_OBS_TILE_PARTS)), P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE, warp - 1);
   }
-  t_encode_obs<kGameThreads>(cx, S.ring + tid, P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE);
 }
 
 // stand-alone sampler: one thread per env, reads the bound mask / obs rows back from global memory
@@ -292,16 +384,15 @@ struct catan_env {
   size_t rec_bytes = 0;
   uint32_t* err_flags = nullptr;
   uint32_t* side = nullptr;
-  uint32_t* lr_queue = nullptr;
+  uint64_t* lr_queue = nullptr;
+  uint64_t* lr_slow_queue = nullptr;
   catanb::LrCtl* lr_ctl = nullptr;
   int32_t* actions_stage = nullptr;   // device staging for catan_step_host
-  catanb::LpTask* lp_ring = nullptr;  // per-block task rings of the longest-road search
   uint8_t* obs = nullptr;
   uint8_t* masks = nullptr;
   float* reward = nullptr;
   uint8_t* info = nullptr;
   int lr_grid = 0;
-  int lp_budget = catanb::kLpBudget;
 };
 
 static int device_guard(const catan_env* env) {
@@ -315,20 +406,19 @@ static EnvParams make_params(const catan_env* env) {
   EnvParams P{};
   P.recs = env->recs; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
   P.obs = env->obs; P.masks = env->masks; P.reward = env->reward; P.info = env->info; P.err_flags = env->err_flags;
-  P.side = env->side; P.lr_queue = env->lr_queue; P.lr_ctl = env->lr_ctl; P.lp_ring = env->lp_ring; P.lp_budget = env->lp_budget;
+  P.side = env->side; P.lr_queue = env->lr_queue; P.lr_slow_queue = env->lr_slow_queue; P.lr_ctl = env->lr_ctl;
   return P;
 }
 
-static int game_blocks(int first, int count) {   // blocks of kGameThreads covering [first & ~31, first + count)
-  const int span = first + count - (first & ~31);
-  return (span + catanb::kGameThreads - 1) / catanb::kGameThreads;
+static int game_blocks(int first, int count) {   // chunks of 32 games touched by [first, first + count): one block each
+  return ((first + count - 1) >> 5) - (first >> 5) + 1;
 }
 
 template <int MODE, bool SAMPLE>
 static int launch_encode(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
   P.range_first = first; P.range_count = count;
   if (count <= 0) return 0;
-  catanb::encode_kernel<MODE, SAMPLE><<<game_blocks(first, count), catanb::kGameThreads, 0, stream>>>(P);
+  catanb::encode_kernel<MODE, SAMPLE><<<game_blocks(first, count), catanb::kEncThreads, 0, stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -336,9 +426,11 @@ static int launch_encode(catan_env* env, EnvParams P, int first, int count, cuda
 template <bool SAMPLE>
 static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   P.range_first = 0; P.range_count = env->n;
-  catanb::transition_kernel<<<game_blocks(0, env->n), catanb::kGameThreads, 0, stream>>>(P);
+  catanb::transition_kernel<<<game_blocks(0, env->n), catanb::kTransThreads, 0, stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
-  catanb::longest_road_kernel<<<env->lr_grid, catanb::kLrThreads, sizeof(catanb::LrSmem), stream>>>(P);
+  catanb::lr_fast_kernel<<<env->sm_count * 2, catanb::kLrFastThreads, 0, stream>>>(P);
+  CATAN_CUDA(cudaGetLastError());
+  catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
   return launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream);
 }
@@ -350,8 +442,8 @@ static int check_bound(const catan_env* env) {
 }
 
 static void free_env(catan_env* env) {
-  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_queue); cudaFree(env->lr_ctl);
-  cudaFree(env->actions_stage); cudaFree(env->lp_ring);
+  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_queue); cudaFree(env->lr_slow_queue); cudaFree(env->lr_ctl);
+  cudaFree(env->actions_stage);
   delete env;
 }
 
@@ -393,8 +485,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   cudaDeviceProp prop{};
   CATAN_CUDA(cudaGetDeviceProperties(&prop, device));
   env->sm_count = prop.multiProcessorCount;
-  env->lr_grid = env->sm_count;                        // persistent search blocks: one per SM
-  { const char* d = getenv("CATAN_LP_BUDGET"); if (d && atoi(d) > 0) env->lp_budget = atoi(d); }
+  env->lr_grid = env->sm_count * catanb::kLrSlowBlocksPerSM;   // search blocks stride over the queue; idle blocks exit at once
   env->rec_bytes = CATAN_CHUNK_BYTES * ((static_cast<size_t>(n_envs) + 31) / 32);
   const size_t n = static_cast<size_t>(n_envs);
   e = cudaMalloc(&env->recs, env->rec_bytes);
@@ -403,13 +494,12 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   if (e == cudaSuccess) e = cudaMemset(env->err_flags, 0, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->side, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMemset(env->side, 0, sizeof(uint32_t) * n);
-  if (e == cudaSuccess) e = cudaMalloc(&env->lr_queue, sizeof(uint32_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&env->lr_queue, sizeof(uint64_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&env->lr_slow_queue, sizeof(uint64_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->lr_ctl, sizeof(catanb::LrCtl));
   if (e == cudaSuccess) e = cudaMemset(env->lr_ctl, 0, sizeof(catanb::LrCtl));
   if (e == cudaSuccess) e = cudaMalloc(&env->actions_stage, sizeof(int32_t) * CATAN_ACTION_WORDS * n);
-  if (e == cudaSuccess) e = cudaMalloc(&env->lp_ring, sizeof(catanb::LpTask) * catanb::kLpRingTasks * static_cast<size_t>(env->lr_grid));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::longest_road_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(sizeof(catanb::LrSmem)));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::lr_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::LrSmem)));
   if (e != cudaSuccess) {
     free_env(env);
     return cuda_fail(e, "catan_create");
@@ -565,6 +655,17 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
   EnvParams P = make_params(env);
   if (launch_encode<catanb::MODE_REFRESH, false>(env, P, first, count, nullptr)) return -1;
   CATAN_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
+  if (!env || !out_host) return fail("null argument");
+  if (device_guard(env)) return -1;
+  catanb::LrCtl c;
+  CATAN_CUDA(cudaDeviceSynchronize());
+  CATAN_CUDA(cudaMemcpy(&c, env->lr_ctl, sizeof(c), cudaMemcpyDeviceToHost));
+  out_host[0] = c.total; out_host[1] = c.slow_total; out_host[2] = c.dbg[4]; out_host[3] = c.dbg[5];
+  for (int i = 0; i < 4; ++i) out_host[4 + i] = c.dbg[i];
   return 0;
 }
 

@@ -2,9 +2,6 @@
 // engine) for the host with one game per "chunk" so the CPU test-suite can check the exact shipped logic against the
 // oracle and the golden fixtures without a GPU.  Never loaded by the product package.
 #define CATAN_HOST_EMU 1
-#ifndef CATAN_LP_BUDGET
-#define CATAN_LP_BUDGET 24   // tiny on purpose: the host emulation must exercise the subtree hand-off of lp_round
-#endif
 #include "../../settlers_of_catan_rl_b200/csrc/catan_game.cuh"
 
 #include <stdlib.h>
@@ -39,11 +36,16 @@ static TCx make_ctx(EmuEnv* e) {
 static void encode(EmuEnv* e) {
   TCx cx = make_ctx(e);
   MaskBits m;
-  t_build_masks(cx, m);
+  MaskPlan pl;
+  Scan sc;
+  memset(&sc, 0, sizeof(sc));
+  if (t_masks_pre(cx, m, pl)) sc = t_scan_group(cx.g, h_topo, h_topox, cx.g.players_go(), 0, 1);
+  if (pl.post) t_masks_post(cx, m, pl, sc);
   MaskFlat F;
   t_flatten_masks(m, F);
   t_store_mask_row(F, e->mask);
-  t_encode_obs<1>(cx, e->ring, e->obs);
+  // the row is produced in the same pieces as on the device (one thread per piece there)
+  for (int part = 0; part < CATAN_OBS_PARTS; ++part) t_encode_obs_part<1>(cx, e->ring, e->obs, part);
 }
 
 extern "C" {
@@ -66,14 +68,26 @@ void emu_reset(EmuEnv* e) {
 int emu_step(EmuEnv* e, const int32_t* action, float* reward, uint8_t* info) {
   TCx cx = make_ctx(e);
   StepTmp tmp;
-  t_step_transition(cx, action, tmp);
+  t_step_scalar(cx, action, tmp);
+  if (tmp.follow) t_followups_group(cx.g, h_topo, tmp, 0, 1);
   if (!tmp.err && tmp.lr_pid) {                                      // game.py:864-919
     const int pid = tmp.lr_pid;
-    const int len = t_longest_path(cx.g, h_topo, pid, e->scratch, 0);
-    const bool shrunk = t_lr_is_shrunk(cx.g, pid, len);
-    uint8_t other_len[5] = {0, 0, 0, 0, 0};
-    if (shrunk) for (int o = WHITE; o <= RED; ++o) if (o != pid) other_len[o] = static_cast<uint8_t>(t_longest_path(cx.g, h_topo, o, e->scratch, 0));
-    t_lr_apply(cx.g, pid, len, shrunk, other_len);
+    int len = t_lr_fast(cx.g, h_topo, pid, tmp.lr_kind, tmp.lr_loc, tmp.acted_pid);
+    if (len >= 0) {
+      t_lr_apply(cx.g, pid, len, false, nullptr);
+    } else if (tmp.lr_kind == CATAN_LR_ROAD && tmp.lr_loc != 0xff && !cx.g.lr_dirty(pid - 1)) {
+      // the stored length is exact: only the paths through the new road can beat it
+      const int old = cx.g.lr_holder() == pid ? cx.g.lr_count() : (cx.g.has_path_key(pid - 1) ? cx.g.cur_longest_path(pid - 1) : 0);
+      const int through = t_through_edge(cx.g, h_topo, pid, tmp.lr_loc, e->scratch, 0);
+      t_lr_apply(cx.g, pid, through > old ? through : old, false, nullptr);
+    } else {
+      len = t_longest_path(cx.g, h_topo, pid, e->scratch, 0);
+      const bool shrunk = t_lr_is_shrunk(cx.g, pid, len);
+      uint8_t other_len[5] = {0, 0, 0, 0, 0};
+      if (shrunk) for (int o = WHITE; o <= RED; ++o) if (o != pid) other_len[o] = static_cast<uint8_t>(t_longest_path(cx.g, h_topo, o, e->scratch, 0));
+      t_lr_apply(cx.g, pid, len, shrunk, other_len);
+      cx.g.lr_dirty(pid - 1) = 0;
+    }
   }
   alignas(16) float rew[4];
   alignas(16) uint8_t inf[CATAN_INFO_STRIDE];
