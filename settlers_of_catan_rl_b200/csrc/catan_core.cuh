@@ -230,6 +230,7 @@ CATAN_FN_NOINLINE bool number_order_ok(const Topo& T, const uint8_t* numbers, co
 // ------------------------------------------------------------------------------------------------
 #define CATAN_LP_ADJ_BYTES 432
 #define CATAN_LP_CTL_WORDS 4
+#define CATAN_LP_BURST 8
 struct alignas(16) LpTask {
   uint64_t visited;
   uint8_t node, depth, pad_[2];
@@ -253,7 +254,7 @@ CATAN_FN void group_idle() {}
 CATAN_FN_NOINLINE void lp_pool(const uint64_t* adj, const uint64_t* adjb, int sw, int32_t* ctl, int32_t* best,
                                uint8_t* path, int path_stride, int path_lane, LpTask* ring, int ring_mask, int low_water) {
 #define CATAN_LP_CAND(u_, vis_) ((sw >= 0 && !(((vis_) >> sw) & 1ull)) ? adjb[(u_)] : adj[(u_)])
-  int lbest = 0, node = 0, depth = 0, base = 0, my = -1, it = 0, steps = 0;
+  int lbest = 0, node = 0, depth = 0, base = 0, my = -1, steps = 0;
   uint64_t visited = 0, vbase = 0, above = ~0ull;
   bool active = false;
   for (;;) {
@@ -266,14 +267,14 @@ CATAN_FN_NOINLINE void lp_pool(const uint64_t* adj, const uint64_t* adjb, int sw
           visited = vbase = tk.visited; node = tk.node; depth = base = tk.depth; above = ~0ull;
           path[base * path_stride + path_lane] = static_cast<uint8_t>(node);
           if (lbest < depth) lbest = depth;
-          active = true; my = -1; it = 0;
+          active = true; my = -1;
         }
       }
     }
     if (!wany(active || vload_i32(&ctl[2]) > 0)) break;             // nobody in this warp works and the pool is dead
     if (!wany(active)) group_idle();                                 // a warp without work must not take issue slots from the others
     if (!active) continue;
-    if ((++it & 7) == 0 && vload_i32(&ctl[1]) - vload_i32(&ctl[0]) < low_water) {
+    if (vload_i32(&ctl[1]) - vload_i32(&ctl[0]) < low_water) {
       // the pool runs low: give the untried siblings of the shallowest open level away
       uint64_t vis = vbase;
       for (int q = base; q <= depth; ++q) {
@@ -299,24 +300,27 @@ CATAN_FN_NOINLINE void lp_pool(const uint64_t* adj, const uint64_t* adjb, int sw
         break;
       }
     }
-    ++steps;
-    const uint64_t cand = CATAN_LP_CAND(node, visited) & ~visited & above;
-    if (cand) {                                                      // push the lowest untried neighbour
-      const int t = ctz64(cand);
-      ++depth;
-      path[depth * path_stride + path_lane] = static_cast<uint8_t>(t);
-      visited |= 1ull << t;
-      node = t; above = ~0ull;
-      if (depth > lbest) lbest = depth;
-    } else if (depth == base) {
-      active = false;                                                // task exhausted
-      fetch_add_i32(&ctl[2], -1);
-    } else {                                                         // pop; resume the parent above the popped child
-      visited &= ~(1ull << node);
-      --depth;
-      const int raw = path[depth * path_stride + path_lane];
-      above = (raw & 128) ? 0ull : ~((2ull << node) - 1ull);         // the siblings of a level that was given away are not ours
-      node = raw & 63;
+    CATAN_NO_UNROLL
+    for (int k = 0; k < CATAN_LP_BURST && active; ++k) {             // a burst of walk steps between two looks at the pool
+      ++steps;
+      const uint64_t cand = CATAN_LP_CAND(node, visited) & ~visited & above;
+      if (cand) {                                                    // push the lowest untried neighbour
+        const int t = ctz64(cand);
+        ++depth;
+        path[depth * path_stride + path_lane] = static_cast<uint8_t>(t);
+        visited |= 1ull << t;
+        node = t; above = ~0ull;
+        if (depth > lbest) lbest = depth;
+      } else if (depth == base) {
+        active = false;                                              // task exhausted
+        fetch_add_i32(&ctl[2], -1);
+      } else {                                                       // pop; resume the parent above the popped child
+        visited &= ~(1ull << node);
+        --depth;
+        const int raw = path[depth * path_stride + path_lane];
+        above = (raw & 128) ? 0ull : ~((2ull << node) - 1ull);       // the siblings of a level that was given away are not ours
+        node = raw & 63;
+      }
     }
   }
   if (lbest) smax_i32(best, lbest);

@@ -1193,10 +1193,11 @@ CATAN_FN_NOINLINE bool t_step_finish(TCx& cx, const StepTmp& tmp, float* reward_
 // `nl` lanes (a warp on the device, one lane in the host build).  The game stream is counter based, so the lanes first
 // compute the next CATAN_RESET_WORDS draws in parallel; lane 0 then runs the (inherently serial) Fisher-Yates shuffles
 // over small arrays in `arr` and only falls back to computing single draws when the 6/8 rejection loop of board.py:80-81
-// needed more than that.  wbuf: CATAN_RESET_WORDS words, arr: 80 bytes, both private to the group (shared memory).
+// needed more than that.  wbuf: CATAN_RESET_WORDS words, arr: 96 bytes, both private to the group (shared memory).
 // info_patch (may be null): info row of the step that ended the previous game; gets the new actor and RESET = 1.
 // ------------------------------------------------------------------------------------------------
 #define CATAN_RESET_WORDS 256
+#define CATAN_PER_GROUP19 ((19 + CATAN_W - 1) / CATAN_W)   // tiles per lane of a group
 struct ResetRng {
   const uint32_t* wbuf;
   uint32_t d_base, d;
@@ -1230,18 +1231,47 @@ CATAN_FN_NOINLINE void reset_game_group(const GameView& g, const Topo& T, uint64
     philox4x32((d_base >> 2) + b, CATAN_STREAM_GAME, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32),
                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), wbuf + 4 * b);
   CATAN_GROUP_SYNC();
+  uint8_t* terrain = arr;            // 19
+  uint8_t* numbers = arr + 19;       // 18
+  uint8_t* harb = arr + 37;          // 9
+  uint8_t* order = arr + 46;         // 4
+  uint8_t* deck = arr + 50;          // 25
+  uint8_t* vals = arr + 75;          // 19: number token of every tile under the current number order
+  ResetRng R = {wbuf, d_base, rng, seed, env_id};                    // (only lane 0 draws)
   if (lane == 0) {
-    ResetRng R = {wbuf, d_base, rng, seed, env_id};
-    uint8_t* terrain = arr;            // 19
-    uint8_t* numbers = arr + 19;       // 18
-    uint8_t* harb = arr + 37;          // 9
-    uint8_t* order = arr + 46;         // 4
-    uint8_t* deck = arr + 50;          // 25
     for (int i = 0; i < 19; ++i) terrain[i] = static_cast<uint8_t>(T.terrain_to_place[i]);
     reset_shuffle(R, terrain, 19);                                   // board.py:71-72
     for (int i = 0; i < 18; ++i) numbers[i] = static_cast<uint8_t>(T.default_number_order[i]);
     reset_shuffle(R, numbers, 18);                                   // board.py:79
-    while (!number_order_ok(T, numbers, terrain)) reset_shuffle(R, numbers, 18);   // board.py:80-81
+  }
+  CATAN_GROUP_SYNC();
+  // board.py:80-81: reshuffle until no 6 / 8 touch (board.py:50-65).  The check is one lane per tile; tile t takes the
+  // token at its rank in the placement order, not counting the desert (board.py:88-100).
+  int my_rank[CATAN_PER_GROUP19], desert_rank = 0;
+  for (int i = 0; i < 19; ++i) if (terrain[T.number_placement[i]] == 0) desert_rank = i;
+  for (int q = 0, t = lane; t < 19; t += nl, ++q) {
+    int r = 0;
+    for (int i = 0; i < 19; ++i) if (T.number_placement[i] == t) r = i;
+    my_rank[q] = r;
+  }
+  for (;;) {
+    for (int q = 0, t = lane; t < 19; t += nl, ++q)
+      vals[t] = my_rank[q] == desert_rank ? 7 : numbers[my_rank[q] - (desert_rank < my_rank[q] ? 1 : 0)];
+    CATAN_GROUP_SYNC();
+    uint32_t bad = 0;
+    for (int t = lane; t < 19; t += nl) {
+      if (vals[t] != 6 && vals[t] != 8) continue;
+      for (int k = 0; k < 6; ++k) {
+        const int nb = T.tile_neigh[t][k];
+        if (nb >= 0 && (vals[nb] == 6 || vals[nb] == 8)) bad = 1;
+      }
+    }
+    bad = group_or32(bad);
+    if (!bad) break;
+    if (lane == 0) reset_shuffle(R, numbers, 18);
+    CATAN_GROUP_SYNC();
+  }
+  if (lane == 0) {
     for (int i = 0; i < 9; ++i) harb[i] = static_cast<uint8_t>(i);
     reset_shuffle(R, harb, 9);                                       // board.py:83-84
     order[0] = WHITE; order[1] = BLUE; order[2] = ORANGE; order[3] = RED;
@@ -1250,19 +1280,20 @@ CATAN_FN_NOINLINE void reset_game_group(const GameView& g, const Topo& T, uint64
     reset_shuffle(R, deck, 25);                                      // game.py:75-78
     g.rng_ctr() = R.d;
     g.decision_ctr() = dec;
-    int n = 0;
-    for (int i = 0; i < 19; ++i) {                                   // board.py:88-100
-      const int t = T.number_placement[i];
-      g.tile_res(t) = terrain[t];
-      if (terrain[t] == 0) { g.tile_val(t) = 7; g.robber_tile() = static_cast<uint8_t>(t); }
-      else g.tile_val(t) = numbers[n++];
-    }
-    for (int i = 0; i < 9; ++i) g.harbour_perm(i) = harb[i];
+  }
+  CATAN_GROUP_SYNC();
+  for (int t = lane; t < 19; t += nl) {                              // board.py:88-100
+    g.tile_res(t) = terrain[t];
+    g.tile_val(t) = vals[t];
+    if (terrain[t] == 0) g.robber_tile() = static_cast<uint8_t>(t);
+  }
+  for (int i = lane; i < 25; i += nl) g.deck(i) = deck[i];
+  for (int i = lane; i < 9; i += nl) g.harbour_perm(i) = harb[i];
+  if (lane == 0) {
     for (int i = 0; i < 4; ++i) g.player_order(i) = order[i];
     g.players_go() = order[0];
     for (int r = 0; r < 5; ++r) g.bank(r) = 19;                      // game.py:48-54
     for (int p = 0; p < 4; ++p) { g.settlements_left(p) = 5; g.cities_left(p) = 4; g.second_corner(p) = -1; }
-    for (int i = 0; i < 25; ++i) g.deck(i) = deck[i];
     g.deck_n() = 25;
     g.initial_phase() = 1;
     if (info_patch) { info_patch[CATAN_INFO_ACTOR] = order[0]; info_patch[CATAN_INFO_RESET] = 1; }
@@ -1297,7 +1328,8 @@ struct MaskBits {
 
 // Placement scan of ONE game by a GROUP of `nl` lanes (a warp on the device), one lane per corner / edge / tile: the
 // occupancy bit boards seen by PlayerId pid, corner.py:24-39 for all corners and edge.py:23-42 for all edges.  Every lane
-// returns the complete result.
+// returns the complete result.  solo (with lane 0, nl 1): the calling thread scans its own game alone -- cheaper for a
+// warp when most of its 32 games need a scan.
 struct Scan {
   uint64_t settle_free;      // distance rule only (corner.py:28-33)
   uint64_t road_at;          // an own road touches the corner
@@ -1307,7 +1339,7 @@ struct Scan {
   uint32_t road_hi, e_any_hi;   // edges 64..71
   uint32_t tile_bld;         // tiles with any building on a corner (wrapper.py:308-320, Q1)
 };
-CATAN_FN_NOINLINE Scan t_scan_group(const GameView& g, const Topo& T, const TopoX& X, int pid, int lane, int nl) {
+CATAN_FN_NOINLINE Scan t_scan_group(const GameView& g, const Topo& T, const TopoX& X, int pid, int lane, int nl, bool solo = false) {
   uint64_t bld = 0, mine = 0, ms = 0;
   for (int c = lane; c < 54; c += nl) {
     const uint32_t b = g.corner(c);
@@ -1322,8 +1354,10 @@ CATAN_FN_NOINLINE Scan t_scan_group(const GameView& g, const Topo& T, const Topo
     if (e < 64) { ea |= static_cast<uint64_t>(b != 0) << e; em |= static_cast<uint64_t>(b == static_cast<uint32_t>(pid)) << e; }
     else { eah |= static_cast<uint32_t>(b != 0) << (e - 64); emh |= static_cast<uint32_t>(b == static_cast<uint32_t>(pid)) << (e - 64); }
   }
-  bld = group_or64(bld); mine = group_or64(mine); ms = group_or64(ms);
-  ea = group_or64(ea); em = group_or64(em); eah = group_or32(eah); emh = group_or32(emh);
+  if (!solo) {
+    bld = group_or64(bld); mine = group_or64(mine); ms = group_or64(ms);
+    ea = group_or64(ea); em = group_or64(em); eah = group_or32(eah); emh = group_or32(emh);
+  }
   uint64_t fre = 0, ra = 0;
   for (int c = lane; c < 54; c += nl) {
     const bool blocked = ((X.corner_nb[c] | (1ull << c)) & bld) != 0;
@@ -1331,7 +1365,7 @@ CATAN_FN_NOINLINE Scan t_scan_group(const GameView& g, const Topo& T, const Topo
     fre |= static_cast<uint64_t>(!blocked) << c;
     ra |= static_cast<uint64_t>(own_road) << c;
   }
-  fre = group_or64(fre); ra = group_or64(ra);
+  if (!solo) { fre = group_or64(fre); ra = group_or64(ra); }
   const uint64_t reach = mine | (~bld & ra);                         // a road of pid may start here
   uint64_t lo = 0;
   uint32_t hi = 0, tl = 0;
@@ -1343,9 +1377,10 @@ CATAN_FN_NOINLINE Scan t_scan_group(const GameView& g, const Topo& T, const Topo
   for (int t = lane; t < 19; t += nl) tl |= static_cast<uint32_t>((X.tile_cmask[t] & bld) != 0) << t;
   Scan sc;
   sc.settle_free = fre; sc.road_at = ra; sc.mine_settle = ms;
-  sc.road_lo = group_or64(lo) & ~ea; sc.road_hi = group_or32(hi) & ~eah & 0xffu;
+  if (!solo) { lo = group_or64(lo); hi = group_or32(hi); tl = group_or32(tl); }
+  sc.road_lo = lo & ~ea; sc.road_hi = hi & ~eah & 0xffu;
   sc.e_any_lo = ea; sc.e_any_hi = eah;
-  sc.tile_bld = group_or32(tl);
+  sc.tile_bld = tl;
   return sc;
 }
 
@@ -1722,22 +1757,6 @@ CATAN_FN_NOINLINE void t_encode_obs(const TCx& cx, uint32_t* ring, uint8_t* row,
   }
   // ---- player blocks (wrapper.py:526-709)
   if (W.overlaps(CATAN_OBS_CUR_MAIN, CATAN_OBS_DEV_LISTS)) {
-    // tinfo[t] keeps what the production tables need: slot (6 bits, 63 = desert) and the building weight (settlement 1,
-    // city 2) per relative owner, 4 bits each
-    uint32_t tinfo[19];
-    CATAN_NO_UNROLL
-    for (int t = 0; t < 19; ++t) {
-      uint32_t b[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) b[k] = g.corner(T.tile_corners[t][k]);
-      const int val = g.tile_val(t), tres = g.tile_res(t);
-      // slot of resource index r in the obs order Wood,Brick,Wheat,Ore,Sheep (wrapper.py:550): BRICK->1 WOOD->0 ORE->3 SHEEP->4 WHEAT->2
-      uint32_t info = val == 7 ? 63u : static_cast<uint32_t>(((0x24301 >> (4 * (tres - 1))) & 7) * 10 + (val <= 6 ? val - 2 : val - 3));
-#pragma unroll
-      for (int k = 0; k < 6; ++k)
-        if (b[k]) info += (b[k] & 3u) << (6 + 4 * CATAN_REL(b[k] >> 2));
-      tinfo[t] = info;
-    }
     const int lr_holder = g.lr_holder(), la_holder = g.la_holder();
     CATAN_NO_UNROLL
     for (int rel = 0; rel < 4; ++rel) {
@@ -1760,11 +1779,19 @@ CATAN_FN_NOINLINE void t_encode_obs(const TCx& cx, uint32_t* ring, uint8_t* row,
       }
       const int vps = g.vp(tp);
       W.put(c + (vps < 10 ? vps : 9), 1);                            // wrapper.py:587-593
-      CATAN_NO_UNROLL
-      for (int t = 0; t < 19; ++t) {                                 // production table (wrapper.py:595-610)
-        const uint32_t info = tinfo[t];
-        const uint32_t cnt = (info >> (6 + 4 * rel)) & 15u;
-        if (cnt && (info & 63u) != 63u) W.add(c + 10 + (info & 63u), cnt);
+      if (W.overlaps(c + 10, c + 60)) {                              // production table (wrapper.py:595-610)
+        CATAN_NO_UNROLL
+        for (int t = 0; t < 19; ++t) {
+          uint32_t b[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) b[k] = g.corner(T.tile_corners[t][k]);
+          const int val = g.tile_val(t), tres = g.tile_res(t);
+          uint32_t cnt = 0;                                          // settlement 1, city 2 for every building of `target`
+#pragma unroll
+          for (int k = 0; k < 6; ++k) cnt += (b[k] >> 2) == static_cast<uint32_t>(target) ? (b[k] & 3u) : 0u;
+          // slot of resource index r in the obs order Wood,Brick,Wheat,Ore,Sheep (wrapper.py:550): BRICK->1 WOOD->0 ORE->3 SHEEP->4 WHEAT->2
+          if (cnt && val != 7) W.add(c + 10 + ((0x24301 >> (4 * (tres - 1))) & 7) * 10 + (val <= 6 ? val - 2 : val - 3), cnt);
+        }
       }
       if (rel == 0) W.flush_to(c + 60);
       if (lr_holder) {                                               // wrapper.py:613-620 (Q9)
@@ -1891,11 +1918,12 @@ static_assert(CATAN_OBS_PROPOSED_TRADE == 0 && CATAN_OBS_CURRENT_RES == 12 && CA
 
 // The cuts used by the device encoder: CATAN_OBS_PARTS threads share one row.  Parts 0 .. CATAN_OBS_TILE_PARTS-1 lie in
 // the header + tile region (t_encode_obs_tiles), the others go through the window (t_encode_obs).
-#define CATAN_OBS_PARTS 5
-#define CATAN_OBS_TILE_PARTS 2
+#define CATAN_OBS_PARTS 9
+#define CATAN_OBS_TILE_PARTS 4
 #define CATAN_OBS_TILE_END 1152
-CATAN_FN int t_obs_part_lo(int part) {
-  return part == 0 ? 0 : part == 1 ? 592 : part == 2 ? CATAN_OBS_TILE_END : part == 3 ? 1472 : part == 4 ? 1792 : CATAN_OBS_STRIDE;
+CATAN_FN int t_obs_part_lo(int part) {   // four tile parts, one part per player block (cut at the nearest 16-byte piece), lists + meta
+  return part == 0 ? 0 : part == 1 ? 304 : part == 2 ? 592 : part == 3 ? 880 : part == 4 ? CATAN_OBS_TILE_END : part == 5 ? 1312 :
+         part == 6 ? 1472 : part == 7 ? 1632 : part == 8 ? 1792 : CATAN_OBS_STRIDE;
 }
 template <int NT>
 CATAN_FN void t_encode_obs_part(const TCx& cx, uint32_t* ring, uint8_t* row, int part) {

@@ -35,17 +35,19 @@ constexpr int kTransWarps = 4;              // transition_kernel: warps per chun
 constexpr int kTransThreads = kTransWarps * 32;
 constexpr int kEncWarps = 1 + CATAN_OBS_PARTS;   // encode_kernel: finish/masks/sampler warp + one warp per piece of the obs row
 constexpr int kEncThreads = kEncWarps * 32;
-constexpr int kLrFastThreads = 64;          // lr_fast_kernel: one thread per queued update
-constexpr int kLrSlowThreads = 256;         // lr_slow_kernel: one block per update that needs the full enumeration
-constexpr int kLrSlowBlocksPerSM = 4;
+constexpr int kCopyThreads = 128;           // lr_copy_kernel: one warp per game
+constexpr int kLrFastThreads = 32;          // lr_fast_kernel: one thread per queued update
+constexpr int kLrSlowThreads = 1024;        // lr_slow_kernel: one block per update that needs the full enumeration
+constexpr int kLrSlowBlocksPerSM = 1;
 constexpr int kSampleThreads = 128;         // stand-alone sampler kernel
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
-struct LrCtl { int32_t count, slow_count; unsigned long long total, slow_total, dbg[6]; };   // dbg: job cycles sum/max, rounds sum/max, full-search jobs, -   // queue lengths: written by transition_kernel / lr_fast_kernel, cleared by encode_kernel
+struct LrCtl { int32_t count, slow_count; unsigned long long total, slow_total, dbg[6], enc[12]; };   // enc: max cycles of finish, warp 0, obs parts 0..8, block   // dbg: search cycles sum/max, walk steps sum/max, full searches, tasks   // queue lengths: written by transition_kernel / lr_fast_kernel, cleared by encode_kernel
 
 struct EnvParams {
   uint8_t* recs;               // lane-interleaved chunks of 32 games (catan_game.cuh)
+  uint8_t* stage;              // same layout: compact copy of the games with a pending longest-road update, in queue order
   int n_envs;
   uint64_t seed, first_env_id;
   catan_config_t cfg;
@@ -58,10 +60,11 @@ struct EnvParams {
   uint32_t* err_flags;
   const uint8_t* env_mask;     // envs whose byte is 0 are left untouched; nullptr = all envs
   int range_first, range_count;   // env range this launch covers
-  uint32_t* side;              // [n] transition -> encode: err | acted_pid << 8 | act_type << 16 | roll << 24
+  uint32_t* side;              // [n] transition -> encode: err | acted_pid << 8 | act_type << 16 | roll << 24 | longest-road update pending << 31
   uint64_t* lr_queue;          // [n] env index | PlayerId << 32 | edge or corner << 40 | CATAN_LR_* << 48 | acting PlayerId << 56
   uint64_t* lr_slow_queue;     // [n] the entries lr_fast_kernel could not settle
-  LrCtl* lr_ctl;
+  LrCtl* lr_ctl;               // queue lengths of THIS step
+  LrCtl* lr_ctl_next;          // the other buffer: cleared by this step's transition for the next step
 };
 
 struct GameSmem {
@@ -77,11 +80,18 @@ __device__ __forceinline__ void stage_topology(GameSmem& S, int tid, int nthread
   __syncthreads();
 }
 
-// all lines of the chunk -> L2, issued before anything depends on them: a game's fields are spread over the whole chunk,
-// and the dependent loads of the rule code would otherwise walk to DRAM one miss at a time
-__device__ __forceinline__ void prefetch_chunk(const uint8_t* recs, int first_game, int tid, int nthreads) {
-  const uint8_t* chunk = recs + static_cast<size_t>(first_game >> 5) * CATAN_CHUNK_BYTES;
-  for (int o = tid * 128; o < static_cast<int>(CATAN_CHUNK_BYTES); o += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(chunk + o));
+// The chunk of 32 games a block works on is staged in shared memory: a game's fields are spread over the whole 26 KB
+// chunk, and the rule code reads them through long chains of dependent loads -- from HBM/L2 one miss (0.3-1 us) at a
+// time, a block needed ~100 us for a few thousand instructions.  The copy is one burst of independent 16-byte loads.
+__device__ __forceinline__ void chunk_to_shared(uint8_t* dst, const uint8_t* chunk, int tid, int nthreads) {
+  const int4* src = reinterpret_cast<const int4*>(chunk);
+  int4* d = reinterpret_cast<int4*>(dst);
+  for (int o = tid; o < static_cast<int>(CATAN_CHUNK_BYTES / 16); o += nthreads) d[o] = __ldcg(src + o);
+}
+__device__ __forceinline__ void chunk_to_global(uint8_t* chunk, const uint8_t* src, int tid, int nthreads) {
+  const int4* sp = reinterpret_cast<const int4*>(src);
+  int4* d = reinterpret_cast<int4*>(chunk);
+  for (int o = tid; o < static_cast<int>(CATAN_CHUNK_BYTES / 16); o += nthreads) d[o] = sp[o];
 }
 
 // ---- 1. transition ------------------------------------------------------------------------------
@@ -89,6 +99,7 @@ __device__ __forceinline__ void prefetch_chunk(const uint8_t* recs, int first_ga
 // follow-ups it posts (dice payout over 19 tiles x 6 corners, belief updates over 60 entries) are then executed by all
 // warps of the block, one warp per game and one lane per item.
 struct alignas(16) TransSmem {
+  uint8_t chunk[CATAN_CHUNK_BYTES];
   GameSmem topo;
   StepTmp tmp[32];
   int32_t n_follow;
@@ -99,7 +110,16 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   __shared__ TransSmem S;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int base = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32;
-  prefetch_chunk(P.recs, base, tid, kTransThreads);
+  uint8_t* const home = P.recs + static_cast<size_t>(base >> 5) * CATAN_CHUNK_BYTES;
+  chunk_to_shared(S.chunk, home, tid, kTransThreads);
+  if (blockIdx.x == 0 && tid == 0) {                                 // the other queue buffer belongs to the step before: bank its counts, clear it
+    LrCtl& o = *P.lr_ctl_next;
+    P.lr_ctl->total = o.total + static_cast<unsigned long long>(o.count); P.lr_ctl->slow_total = o.slow_total + static_cast<unsigned long long>(o.slow_count);
+    for (int k = 0; k < 6; ++k) P.lr_ctl->dbg[k] = (k == 1 || k == 3) ? max(o.dbg[k], P.lr_ctl->dbg[k]) : o.dbg[k] + P.lr_ctl->dbg[k];
+    o.count = 0; o.slow_count = 0; o.total = 0; o.slow_total = 0;
+    for (int k = 0; k < 6; ++k) o.dbg[k] = 0;
+    for (int k = 0; k < 12; ++k) { P.lr_ctl->enc[k] = k == 0 ? max(o.enc[k], P.lr_ctl->enc[k]) : o.enc[k] + P.lr_ctl->enc[k]; o.enc[k] = 0; }
+  }
   stage_topology(S.topo, tid, kTransThreads);
   if (warp == 0) {
     const int i = base + lane;
@@ -107,13 +127,13 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     bool follow = false;
     if (valid) {
       TCx cx;
-      cx.g = game_view(P.recs, static_cast<size_t>(i));
+      cx.g.base = S.chunk; cx.g.lane = lane;
       cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
       cx.s = load_seats(cx.g);
       StepTmp& tmp = S.tmp[lane];
       t_step_scalar(cx, P.actions + static_cast<size_t>(i) * CATAN_ACTION_WORDS, tmp);
       P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
-                  (static_cast<uint32_t>(tmp.roll_info) << 24);
+                  (static_cast<uint32_t>(tmp.roll_info) << 24) | ((!tmp.err && tmp.lr_pid) ? 0x80000000u : 0u);
       if (tmp.err) {
         P.err_flags[i] |= 1u << tmp.err;
       } else if (tmp.lr_pid) {
@@ -130,9 +150,12 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   __syncthreads();
   const int nf = S.n_follow;
   for (int j = warp; j < nf; j += kTransWarps) {
-    const int gi = S.follow_list[j];
-    t_followups_group(game_view(P.recs, static_cast<size_t>(base + gi)), S.topo.topo, S.tmp[gi], lane, 32);
+    GameView g;
+    g.base = S.chunk; g.lane = S.follow_list[j];
+    t_followups_group(g, S.topo.topo, S.tmp[g.lane], lane, 32);
   }
+  __syncthreads();
+  chunk_to_global(home, S.chunk, tid, kTransThreads);               // (frozen games go back unchanged)
 }
 
 // ---- 2. longest road ----------------------------------------------------------------------------
@@ -143,7 +166,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
 //   lr_slow_kernel  one BLOCK per remaining update: the enumeration of the paths through the new road -- or, when the
 //                   stored length cannot be trusted, the reference's full enumeration -- as a pool of 16-byte subtree
 //                   tasks that 256 lanes drain and re-split in rounds (lp_round).
-constexpr int kLrRing = 2048;               // task ring of the pool (shared memory; a power of two >= 4 x lanes + 64)
+constexpr int kLrRing = 8192;               // task ring of the pool (shared memory; a power of two >= 4 x lanes + 64)
 struct alignas(16) LrSmem {
   Topo topo;
   uint64_t adj[54], adjb[54];
@@ -154,26 +177,44 @@ struct alignas(16) LrSmem {
   int32_t rounds, tasks;     // diagnostics: walk steps and tasks of the current update
 };
 
+// The games of the update queue are scattered over the chunks: every field access of a warp that works on 32 of them
+// would touch 32 sectors.  They are therefore copied (one warp per game, all fields in flight at once) into staging
+// chunks in queue order, updated and encoded there with the ordinary coalesced code, and copied back.
+__device__ __forceinline__ void copy_game(const GameView& src, const GameView& dst, int lane) {
+  for (int k = lane; k < static_cast<int>(offsetof(GameRec, rng_ctr) / 2); k += 32) dst.at<int16_t>(0, k) = src.at<int16_t>(0, k);
+  if (lane < 3) dst.at<uint32_t>(offsetof(GameRec, rng_ctr), lane) = src.at<uint32_t>(offsetof(GameRec, rng_ctr), lane);
+  if (lane < 2) dst.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane) = src.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane);
+  for (int k = static_cast<int>(offsetof(GameRec, corner)) + lane; k < static_cast<int>(sizeof(GameRec)); k += 32) dst.at<uint8_t>(k, 0) = src.at<uint8_t>(k, 0);
+}
+template <bool TO_STAGE>
+__global__ void __launch_bounds__(kCopyThreads) lr_copy_kernel(const __grid_constant__ EnvParams P) {
+  const int count = P.lr_ctl->count;
+  const int lane = threadIdx.x & 31, warps = static_cast<int>(gridDim.x) * (kCopyThreads / 32);
+  for (int j = static_cast<int>(blockIdx.x) * (kCopyThreads / 32) + (threadIdx.x >> 5); j < count; j += warps) {
+    const GameView home = game_view(P.recs, static_cast<uint32_t>(P.lr_queue[j])), st = game_view(P.stage, static_cast<size_t>(j));
+    if (TO_STAGE) copy_game(home, st, lane); else copy_game(st, home, lane);
+  }
+}
+
 __global__ void __launch_bounds__(kLrFastThreads) lr_fast_kernel(const __grid_constant__ EnvParams P) {
   __shared__ __align__(16) Topo sT;
   const int count = P.lr_ctl->count;
-  if (static_cast<int>(blockIdx.x) >= count) return;
+  if (static_cast<int>(blockIdx.x) * kLrFastThreads >= count) return;
   {
     const int4* src = reinterpret_cast<const int4*>(&d_topo);
     int4* dst = reinterpret_cast<int4*>(&sT);
     for (int i = threadIdx.x; i < static_cast<int>(sizeof(Topo) / 16); i += kLrFastThreads) dst[i] = src[i];
   }
   __syncthreads();
-  // update j goes to thread j / gridDim of block j % gridDim: a short queue is spread over all SMs, and a warp waits for
-  // the slowest of fewer searches
-  for (int j = static_cast<int>(threadIdx.x * gridDim.x + blockIdx.x); j < count; j += static_cast<int>(gridDim.x) * kLrFastThreads) {
+  // consecutive lanes take consecutive staging games (coalesced); one warp per block spreads a short queue over the SMs
+  for (int j = static_cast<int>(blockIdx.x) * kLrFastThreads + threadIdx.x; j < count; j += static_cast<int>(gridDim.x) * kLrFastThreads) {
     const uint64_t en = P.lr_queue[j];
-    const GameView g = game_view(P.recs, static_cast<uint32_t>(en));
+    const GameView g = game_view(P.stage, static_cast<size_t>(j));
     const int pid = static_cast<int>((en >> 32) & 0xff), loc = static_cast<int>((en >> 40) & 0xff), kind = static_cast<int>((en >> 48) & 0xff),
               placer = static_cast<int>(en >> 56);
     const int len = t_lr_fast(g, sT, pid, kind, loc, placer);
     if (len >= 0) t_lr_apply(g, pid, len, false, nullptr);
-    else P.lr_slow_queue[atomicAdd(&P.lr_ctl->slow_count, 1)] = en;
+    else P.lr_slow_queue[atomicAdd(&P.lr_ctl->slow_count, 1)] = (en & ~0xffffffffull) | static_cast<uint64_t>(j);   // staging slot instead of the env
   }
 }
 
@@ -219,7 +260,7 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
   __syncthreads();
   for (int j = static_cast<int>(blockIdx.x); j < count; j += static_cast<int>(gridDim.x)) {
     const uint64_t en = P.lr_slow_queue[j];
-    const GameView g = game_view(P.recs, static_cast<uint32_t>(en));
+    const GameView g = game_view(P.stage, static_cast<uint32_t>(en));
     const int pid = static_cast<int>((en >> 32) & 0xff), loc = static_cast<int>((en >> 40) & 0xff), kind = static_cast<int>((en >> 48) & 0xff);
     const long long t_start = clock64();
     bool was_full = true;
@@ -254,94 +295,125 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
 // One block per chunk of 32 games, one game per lane in every warp.  Warp 0: done / reward / info (+ auto-reset), then
 // the legal-action masks and the fused sampler.  Warps 1..CATAN_OBS_PARTS: one 16-byte aligned piece of the observation
 // row each (t_obs_part_lo): the header + tile pieces as bit sets expanded in registers, the player blocks and card
-// lists through a 128-byte window per thread.
+// lists through a 128-byte window per thread.  A block's latency is what bounds the kernel (a warp issues one instruction
+// every ~40 cycles), hence the many narrow parts.
 constexpr int kObsRingThreads = (CATAN_OBS_PARTS - CATAN_OBS_TILE_PARTS) * 32;   // the tile parts build their pieces in registers
 struct alignas(16) EncSmem {
   GameSmem topo;
   uint32_t ring[(CATAN_RING_BYTES / 4) * kObsRingThreads];          // RowWriter windows, word-interleaved over those threads
   uint32_t wbuf[CATAN_RESET_WORDS];                                 // reset: pre-drawn Philox words (warp 0)
   uint8_t arr[96];                                                  // reset: shuffle arrays (warp 0)
+  Scan scan[32];                                                    // board scan of game b (valid where scan_need has bit b)
+  uint32_t scan_need;
+  uint8_t scan_pid[32];
 };
 
-template <int MODE, bool SAMPLE>
-__global__ void __launch_bounds__(kEncThreads) encode_kernel(const __grid_constant__ EnvParams P) {
+// LISTED = false: block b takes chunk b of the env range; in a step, games whose longest-road update is still pending
+// (side bit 31) are left out.  LISTED = true: those games, 32 per block iteration in queue order, on their staging
+// copies once the searches have finished (second stream, see launch_step).
+template <int MODE, bool SAMPLE, bool LISTED>
+__global__ void __launch_bounds__(kEncThreads, 5) encode_kernel(const __grid_constant__ EnvParams P) {
   __shared__ EncSmem S;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  prefetch_chunk(P.recs, (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32, tid, kEncThreads);
+  const int list_count = LISTED ? P.lr_ctl->count : 0;
+  if (LISTED && static_cast<int>(blockIdx.x) * 32 >= list_count) return;
   stage_topology(S.topo, tid, kEncThreads);
-  if (blockIdx.x == 0 && tid == 0) {
-    P.lr_ctl->total += static_cast<unsigned long long>(P.lr_ctl->count); P.lr_ctl->slow_total += static_cast<unsigned long long>(P.lr_ctl->slow_count);
-    P.lr_ctl->count = 0; P.lr_ctl->slow_count = 0;
-  }   // the queue of this step has been consumed
-  const int i = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32 + lane;
-  const bool valid = i >= P.range_first && i < P.range_first + P.range_count && !(MODE != MODE_REFRESH && P.env_mask != nullptr && P.env_mask[i] == 0);
-  TCx cx;
-  cx.g = game_view(P.recs, static_cast<size_t>(valid ? i : P.range_first));
-  cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
-  uint8_t* info = P.info + static_cast<size_t>(i) * CATAN_INFO_STRIDE;
-  if (warp == 0 && MODE != MODE_REFRESH) {
-    bool need_reset = false;
-    if (MODE == MODE_STEP) {
-      if (valid) {
-        cx.s = load_seats(cx.g);
-        const uint32_t sd = P.side[i];
-        StepTmp tmp;
-        tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
-        tmp.roll_info = static_cast<uint8_t>(sd >> 24);
-        need_reset = t_step_finish(cx, tmp, P.reward + static_cast<size_t>(i) * 4, info);
-      }
+  const long long t_enc0 = clock64();
+  for (int l0 = static_cast<int>(blockIdx.x) * 32; LISTED ? l0 < list_count : l0 == static_cast<int>(blockIdx.x) * 32; l0 += static_cast<int>(gridDim.x) * 32) {
+    int i;
+    bool valid;
+    if (LISTED) {
+      valid = l0 + lane < list_count;
+      i = valid ? static_cast<int>(static_cast<uint32_t>(P.lr_queue[l0 + lane])) : 0;
     } else {
-      need_reset = valid;
+      i = (P.range_first & ~31) + l0 + lane;
+      valid = i >= P.range_first && i < P.range_first + P.range_count && !(MODE != MODE_REFRESH && P.env_mask != nullptr && P.env_mask[i] == 0);
+      if (MODE == MODE_STEP && valid) valid = !(P.side[i] >> 31);
     }
-    // Board.reset + Game.reset are a handful of serial shuffles: the warp does them game by game (lanes pre-draw the
-    // Philox words in parallel).  Rare in a step (a game ends every ~1500 steps), everything in catan_reset.
-    unsigned rb = __ballot_sync(0xffffffffu, need_reset);
-    const int warp_first = i - lane;
-    while (rb) {
-      const int b = __ffs(static_cast<int>(rb)) - 1;
-      rb &= rb - 1;
-      const int e = warp_first + b;
-      reset_game_group(game_view(P.recs, static_cast<size_t>(e)), S.topo.topo, P.seed, P.first_env_id + static_cast<uint64_t>(e), S.wbuf, S.arr,
-                       lane, 32, MODE == MODE_STEP ? P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE : nullptr);
+    // the chunk of these 32 games (home records, or the staging copies); lane b of every warp works on game b of it
+    uint8_t* const home = (LISTED ? P.stage : P.recs) + static_cast<size_t>((LISTED ? l0 : (P.range_first & ~31) + l0) >> 5) * CATAN_CHUNK_BYTES;
+#define CATAN_VIEW_OF(b_) GameView{home, (b_)}
+    TCx cx;
+    cx.g = CATAN_VIEW_OF(lane);
+    cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
+    uint8_t* info = P.info + static_cast<size_t>(i) * CATAN_INFO_STRIDE;
+    if (warp == 0 && MODE != MODE_REFRESH) {
+      bool need_reset = false;
+      if (MODE == MODE_STEP) {
+        if (valid) {
+          cx.s = load_seats(cx.g);
+          const uint32_t sd = P.side[i];
+          StepTmp tmp;
+          tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
+          tmp.roll_info = static_cast<uint8_t>((sd >> 24) & 0x7f);
+          need_reset = t_step_finish(cx, tmp, P.reward + static_cast<size_t>(i) * 4, info);
+        }
+      } else {
+        need_reset = valid;
+      }
+      // Board.reset + Game.reset are a handful of serial shuffles: the warp does them game by game (lanes pre-draw the
+      // Philox words in parallel).  Rare in a step (a game ends every ~1500 steps), everything in catan_reset.
+      unsigned rb = __ballot_sync(0xffffffffu, need_reset);
+      if (MODE == MODE_STEP && lane == 0 && rb) atomicAdd(&P.lr_ctl->enc[7], static_cast<unsigned long long>(__popc(rb)));
+      while (rb) {
+        const int b = __ffs(static_cast<int>(rb)) - 1;
+        rb &= rb - 1;
+        const int e = __shfl_sync(0xffffffffu, i, b);
+        reset_game_group(CATAN_VIEW_OF(b), S.topo.topo, P.seed, P.first_env_id + static_cast<uint64_t>(e), S.wbuf, S.arr,
+                         lane, 32, MODE == MODE_STEP ? P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE : nullptr);
+      }
     }
-  }
-  __syncthreads();                                                   // the games are final: every warp may read them now
-  if (valid) cx.s = load_seats(cx.g);
-  if (warp == 0) {                                                   // (all 32 lanes stay: the scan below is a warp collective)
-    if (MODE != MODE_STEP && valid) t_write_info_fresh(cx.g, info, MODE == MODE_RESET);
+    if (MODE == MODE_STEP && tid == 0) { const unsigned long long d = static_cast<unsigned long long>(clock64() - t_enc0); atomicMax(&P.lr_ctl->enc[0], d); atomicAdd(&P.lr_ctl->enc[1], d); atomicAdd(&P.lr_ctl->enc[2], 1ull); }
+    __syncthreads();                                                 // the games are final: every warp may read them now
+    if (valid) cx.s = load_seats(cx.g);
     MaskBits m;
     MaskPlan pl;
     pl.post = 0;
-    Scan sc = {};
-    // the board scan (54 corners, 72 edges, 19 tiles) of the few games that are in a placement phase: by the whole warp,
-    // one game at a time and one lane per corner / edge
-    unsigned nb = __ballot_sync(0xffffffffu, valid && t_masks_pre(cx, m, pl));
-    const int scan_pid = cx.g.players_go();
-    while (nb) {
-      const int b = __ffs(static_cast<int>(nb)) - 1;
-      nb &= nb - 1;
-      const Scan r = t_scan_group(game_view(P.recs, static_cast<size_t>(i - lane + b)), S.topo.topo, S.topo.topox,
-                                  __shfl_sync(0xffffffffu, scan_pid, b), lane, 32);
-      if (lane == b) sc = r;
+    if (warp == 0) {
+      if (MODE != MODE_STEP && valid) t_write_info_fresh(cx.g, info, MODE == MODE_RESET);
+      const bool need_scan = valid && t_masks_pre(cx, m, pl);
+      const unsigned nb = __ballot_sync(0xffffffffu, need_scan);
+      S.scan_pid[lane] = static_cast<uint8_t>(cx.g.players_go());
+      if (lane == 0) S.scan_need = nb;
     }
-    if (!valid) return;
-    if (pl.post) t_masks_post(cx, m, pl, sc);
+    __syncthreads();
+    // the board scans (54 corners, 72 edges, 19 tiles) of the games that are in a placement phase: one WARP per game, one
+    // lane per corner / edge, all warps of the block take their share
     {
-      MaskFlat F;
-      t_flatten_masks(m, F);
-      t_store_mask_row(F, P.masks + static_cast<size_t>(i) * CATAN_MASK_STRIDE);
+      unsigned nb = S.scan_need;
+      for (int k = 0; nb; ++k) {
+        const int b = __ffs(static_cast<int>(nb)) - 1;
+        nb &= nb - 1;
+        if (k % kEncWarps != warp) continue;
+        const Scan r = t_scan_group(CATAN_VIEW_OF(b), S.topo.topo, S.topo.topox, S.scan_pid[b], lane, 32);
+        if (lane == 0) S.scan[b] = r;
+      }
     }
-    if (SAMPLE) {
-      const int ap = t_current_actor(cx.g) - 1;
-      uint32_t hand = 0;
+    __syncthreads();
+    if (warp == 0) {
+      if (valid) {
+        if (pl.post) t_masks_post(cx, m, pl, S.scan[lane]);
+        {
+          MaskFlat F;
+          t_flatten_masks(m, F);
+          t_store_mask_row(F, P.masks + static_cast<size_t>(i) * CATAN_MASK_STRIDE);
+        }
+        if (SAMPLE) {
+          const int ap = t_current_actor(cx.g) - 1;
+          uint32_t hand = 0;
 #pragma unroll
-      for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(cx.g.res(ap, r) != 0) << r;
-      const uint32_t decision = cx.g.decision_ctr();
-      cx.g.decision_ctr() = decision + 1;
-      t_sample_action(m, hand, P.seed, cx.env_id, decision, P.actions_out + static_cast<size_t>(i) * CATAN_ACTION_WORDS);
+          for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(cx.g.res(ap, r) != 0) << r;
+          const uint32_t decision = cx.g.decision_ctr();
+          cx.g.decision_ctr() = decision + 1;
+          t_sample_action(m, hand, P.seed, cx.env_id, decision, P.actions_out + static_cast<size_t>(i) * CATAN_ACTION_WORDS);
+        }
+      }
+    } else if (valid) {
+      t_encode_obs_part<kObsRingThreads>(cx, S.ring + (tid - 32 * (1 + CATAN_OBS_TILE_PARTS)), P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE, warp - 1);
     }
-  } else if (valid) {
-    t_encode_obs_part<kObsRingThreads>(cx, S.ring + (tid - 32 * (1 + CATAN_OBS_TILE_PARTS)), P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE, warp - 1);
+    if (MODE == MODE_STEP && lane == 0 && (warp == 0 || warp == 1 || warp == 5 || warp == 9)) atomicAdd(&P.lr_ctl->enc[warp == 0 ? 3 : warp == 1 ? 4 : warp == 5 ? 5 : 6], static_cast<unsigned long long>(clock64() - t_enc0));
+    if (LISTED) __syncthreads();                                     // warp 0's reset scratch is reused by the next 32 games
+#undef CATAN_VIEW_OF
   }
 }
 
@@ -381,6 +453,7 @@ struct catan_env {
   uint64_t seed = 0, first_env_id = 0;
   catan_config_t cfg{};
   uint8_t* recs = nullptr;            // ceil(n / 32) lane-interleaved chunks
+  uint8_t* stage = nullptr;           // staging chunks of the games with a pending longest-road update
   size_t rec_bytes = 0;
   uint32_t* err_flags = nullptr;
   uint32_t* side = nullptr;
@@ -393,6 +466,9 @@ struct catan_env {
   float* reward = nullptr;
   uint8_t* info = nullptr;
   int lr_grid = 0;
+  cudaStream_t lr_stream = nullptr;   // high-priority stream of the longest-road updates (overlaps the encode kernel)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  unsigned long long ticks = 0;        // steps launched: selects the queue-counter buffer
 };
 
 static int device_guard(const catan_env* env) {
@@ -404,9 +480,9 @@ static int device_guard(const catan_env* env) {
 
 static EnvParams make_params(const catan_env* env) {
   EnvParams P{};
-  P.recs = env->recs; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
+  P.recs = env->recs; P.stage = env->stage; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
   P.obs = env->obs; P.masks = env->masks; P.reward = env->reward; P.info = env->info; P.err_flags = env->err_flags;
-  P.side = env->side; P.lr_queue = env->lr_queue; P.lr_slow_queue = env->lr_slow_queue; P.lr_ctl = env->lr_ctl;
+  P.side = env->side; P.lr_queue = env->lr_queue; P.lr_slow_queue = env->lr_slow_queue; P.lr_ctl = env->lr_ctl + (env->ticks & 1); P.lr_ctl_next = env->lr_ctl + ((env->ticks & 1) ^ 1);
   return P;
 }
 
@@ -418,21 +494,37 @@ template <int MODE, bool SAMPLE>
 static int launch_encode(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
   P.range_first = first; P.range_count = count;
   if (count <= 0) return 0;
-  catanb::encode_kernel<MODE, SAMPLE><<<game_blocks(first, count), catanb::kEncThreads, 0, stream>>>(P);
+  catanb::encode_kernel<MODE, SAMPLE, false><<<game_blocks(first, count), catanb::kEncThreads, 0, stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
   return 0;
 }
 
+// One step.  On the caller's stream: transition, then the encode of every game whose longest road is settled (96 %).
+// On the library's high-priority stream, forked after the transition and joined at the end: the queued longest-road
+// updates and the encode of exactly those games.  The searches are latency-bound (a few hundred dependent walk steps
+// per update) and would otherwise sit between the two big kernels with the machine idle.
 template <bool SAMPLE>
 static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   P.range_first = 0; P.range_count = env->n;
   catanb::transition_kernel<<<game_blocks(0, env->n), catanb::kTransThreads, 0, stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
-  catanb::lr_fast_kernel<<<env->sm_count * 2, catanb::kLrFastThreads, 0, stream>>>(P);
+  env->ticks += 1;
+  CATAN_CUDA(cudaEventRecord(env->ev_fork, stream));
+  CATAN_CUDA(cudaStreamWaitEvent(env->lr_stream, env->ev_fork, 0));
+  catanb::lr_copy_kernel<true><<<env->sm_count * 8, catanb::kCopyThreads, 0, env->lr_stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
-  catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), stream>>>(P);
+  catanb::lr_fast_kernel<<<env->sm_count * 4, catanb::kLrFastThreads, 0, env->lr_stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
-  return launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream);
+  catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), env->lr_stream>>>(P);
+  CATAN_CUDA(cudaGetLastError());
+  catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count, catanb::kEncThreads, 0, env->lr_stream>>>(P);
+  CATAN_CUDA(cudaGetLastError());
+  catanb::lr_copy_kernel<false><<<env->sm_count * 8, catanb::kCopyThreads, 0, env->lr_stream>>>(P);
+  CATAN_CUDA(cudaGetLastError());
+  CATAN_CUDA(cudaEventRecord(env->ev_join, env->lr_stream));
+  if (launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream)) return -1;
+  CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join, 0));
+  return 0;
 }
 
 static int check_bound(const catan_env* env) {
@@ -442,7 +534,10 @@ static int check_bound(const catan_env* env) {
 }
 
 static void free_env(catan_env* env) {
-  cudaFree(env->recs); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_queue); cudaFree(env->lr_slow_queue); cudaFree(env->lr_ctl);
+  if (env->lr_stream) cudaStreamDestroy(env->lr_stream);
+  if (env->ev_fork) cudaEventDestroy(env->ev_fork);
+  if (env->ev_join) cudaEventDestroy(env->ev_join);
+  cudaFree(env->recs); cudaFree(env->stage); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_queue); cudaFree(env->lr_slow_queue); cudaFree(env->lr_ctl);
   cudaFree(env->actions_stage);
   delete env;
 }
@@ -490,15 +585,24 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   const size_t n = static_cast<size_t>(n_envs);
   e = cudaMalloc(&env->recs, env->rec_bytes);
   if (e == cudaSuccess) e = cudaMemset(env->recs, 0, env->rec_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&env->stage, env->rec_bytes);
+  if (e == cudaSuccess) e = cudaMemset(env->stage, 0, env->rec_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&env->err_flags, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMemset(env->err_flags, 0, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->side, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMemset(env->side, 0, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->lr_queue, sizeof(uint64_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->lr_slow_queue, sizeof(uint64_t) * n);
-  if (e == cudaSuccess) e = cudaMalloc(&env->lr_ctl, sizeof(catanb::LrCtl));
-  if (e == cudaSuccess) e = cudaMemset(env->lr_ctl, 0, sizeof(catanb::LrCtl));
+  if (e == cudaSuccess) e = cudaMalloc(&env->lr_ctl, 2 * sizeof(catanb::LrCtl));
+  if (e == cudaSuccess) e = cudaMemset(env->lr_ctl, 0, 2 * sizeof(catanb::LrCtl));
   if (e == cudaSuccess) e = cudaMalloc(&env->actions_stage, sizeof(int32_t) * CATAN_ACTION_WORDS * n);
+  if (e == cudaSuccess) {
+    int lo = 0, hi = 0;                                  // (greatest priority is the numerically lowest value)
+    e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&env->lr_stream, cudaStreamNonBlocking, hi);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::lr_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::LrSmem)));
   if (e != cudaSuccess) {
     free_env(env);
@@ -661,11 +765,16 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
 int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
   if (!env || !out_host) return fail("null argument");
   if (device_guard(env)) return -1;
-  catanb::LrCtl c;
+  catanb::LrCtl c[2];
   CATAN_CUDA(cudaDeviceSynchronize());
-  CATAN_CUDA(cudaMemcpy(&c, env->lr_ctl, sizeof(c), cudaMemcpyDeviceToHost));
-  out_host[0] = c.total; out_host[1] = c.slow_total; out_host[2] = c.dbg[4]; out_host[3] = c.dbg[5];
-  for (int i = 0; i < 4; ++i) out_host[4 + i] = c.dbg[i];
+  CATAN_CUDA(cudaMemcpy(c, env->lr_ctl, sizeof(c), cudaMemcpyDeviceToHost));
+  // every step banks the totals of the step before into its own buffer; what it queued itself is still in count / slow_count
+  const catanb::LrCtl& last = c[(env->ticks & 1) ^ 1];
+  out_host[0] = last.total + static_cast<unsigned long long>(last.count);
+  out_host[1] = last.slow_total + static_cast<unsigned long long>(last.slow_count);
+  out_host[2] = last.dbg[4]; out_host[3] = last.dbg[5];
+  for (int i = 0; i < 4; ++i) out_host[4 + i] = last.dbg[i];
+  for (int i = 0; i < 12; ++i) out_host[8 + i] = last.enc[i];
   return 0;
 }
 

@@ -76,7 +76,7 @@ class VecCatanEnv:
         if step_mask is not None:
             assert step_mask.dtype == torch.uint8 and step_mask.is_cuda and step_mask.numel() == self.n_envs
         _lib.check(self.lib.catan_step_masked(self._h, _ptr(actions), _ptr(step_mask), self._stream()))
-        self.kernel_launches += 4                      # transition_kernel, lr_fast_kernel, lr_slow_kernel, encode_kernel
+        self.kernel_launches += 7                      # transition, encode | copy-in, lr_fast, lr_slow, encode (listed), copy-out
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
     def sample_random(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -87,10 +87,10 @@ class VecCatanEnv:
         return out
 
     def step_sample(self, actions_io: torch.Tensor):
-        """One call (four launches, the sampler fused into the last): apply ``actions_io`` and overwrite it with the next random-legal actions."""
+        """One call (seven launches on two streams, the sampler fused into the last): apply ``actions_io`` and overwrite it with the next random-legal actions."""
         assert actions_io.dtype == torch.int32 and actions_io.is_cuda and actions_io.is_contiguous()
         _lib.check(self.lib.catan_step_sample(self._h, _ptr(actions_io), self._stream()))
-        self.kernel_launches += 4
+        self.kernel_launches += 7
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
     def get_action_masks(self) -> torch.Tensor:
@@ -103,7 +103,7 @@ class VecCatanEnv:
             return C.c_void_p(0 if a is None else a.ctypes.data)
         assert actions.dtype == np.int32 and actions.flags.c_contiguous
         _lib.check(self.lib.catan_step_host(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
-        self.kernel_launches += 4
+        self.kernel_launches += 7
 
     def reset_host(self, obs: np.ndarray = None, masks: np.ndarray = None, info: np.ndarray = None) -> None:
         def p(a):
@@ -125,7 +125,7 @@ class VecCatanEnv:
 
     def lr_stats(self) -> np.ndarray:
         """(longest-road updates triggered, updates that needed a block-wide search, 0, 0) since construction"""
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(20, dtype=np.uint64)
         _lib.check(self.lib.catan_read_lr_stats(self._h, C.c_void_p(out.ctypes.data)))
         return out
 
