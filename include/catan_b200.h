@@ -97,11 +97,18 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
 /* sticky per-env error flags (bit c set = CATAN_ERR_* code c was raised since the last clear). */
 int catan_read_err_flags(catan_env_t* env, uint32_t* flags_host, int clear);
 
-/* Diagnostics of the longest-road path (game/game.py:843-919): counters since catan_create,
- * out_host[0] = updates triggered (road placed, or settlement placed while the card is held), out_host[1] = updates
- * that needed a search over the road network by a whole block (the rest is settled incrementally by one thread),
- * out_host[2..3] reserved.  Synchronous. */
+/* Diagnostics of the longest-road path (game/game.py:843-919): eight counters since catan_create.
+ * out_host[0] = updates triggered (road placed, or settlement placed while the card is held); [1] = updates that needed a
+ * search over the road network by a whole block (the rest is settled incrementally by one thread); [2] = of those, full
+ * enumerations (stored length not trusted); [3] = search tasks created; [4], [5] = GPU cycles per search, sum and max;
+ * [6], [7] = walk steps per search, sum and max.  Synchronous. */
 int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host);
+
+/* Device-side timing of a step's two kernels on the caller's stream (CUDA events recorded by catan_step*): enable,
+ * step, then read out_host[0] = steps timed, [1] = summed ms of transition_kernel, [2] = summed ms of encode_kernel
+ * (with the longest-road stream running beside it, as in production).  bench.py's roofline uses it.  Synchronous. */
+int catan_set_timing(catan_env_t* env, int enable);
+int catan_read_timing(catan_env_t* env, double* out_host);
 
 /* ---- PPO rollout path (RL/ppo/process_batch.py) -------------------------------------------------
  * All arrays are device fp32, time-major [T(+1)][N] like the reference's [T+1, N, 1] tensors. */

@@ -41,6 +41,4 @@ torch.cuda.synchronize()
 st = env.lr_stats()
 print("longest-road updates per tick: %.1f, needing a block-wide search: %.1f" % (st[0] / (a.skip + a.ticks + 200), st[1] / (a.skip + a.ticks + 200)))
 print("slow jobs: full-search %d of %d; cycles/job avg %.0f max %d; walk steps/job avg %.1f max %d; tasks/job avg %.1f" % (st[2], st[1], st[4] / max(1, st[1]), st[5], st[6] / max(1, st[1]), st[7], st[3] / max(1, st[1])))
-nb = max(1, int(st[10]))
-print("encode blocks %d, resets %d: finish phase avg %.0f max %d cycles; end of warp0 avg %.0f, tile part 0 avg %.0f, player part avg %.0f, lists part avg %.0f" % (nb, st[15], st[9] / nb, st[8], st[11] / nb, st[12] / nb, st[13] / nb, st[14] / nb))
 print("ms/tick after the profiled range (unprofiled launches): %.4f" % (ev0.elapsed_time(ev1) / 200))

@@ -1,20 +1,31 @@
 // catan_kernels.cu — sm_100a kernels + C ABI of the vectorised Catan engine (see include/catan_b200.h).
 //
-// One env step is three launches on the caller's stream (catan_game.cuh holds the game logic):
+// One env step is five launches on two streams (catan_game.cuh holds the game logic; records are lane-interleaved
+// chunks of 32 games, and every kernel below works on whole chunks with one game per lane):
 //
-//   transition_kernel   ONE THREAD PER GAME for translate + validate + the scalar part of apply_action, straight on the
-//                       lane-interleaved game records in HBM/L2 (every field access of a warp is one fully used 32-byte
-//                       sector); the data-parallel follow-ups (dice payout, belief updates) one warp per game.  Games
-//                       whose road network changed are appended to a device queue.
-//   lr_fast_kernel      the queued longest-road updates (game.py:843-919), one thread each: an incremental rule settles
-//   lr_slow_kernel      ~95 % of them with two tiny searches; the rest gets the reference's full enumeration, one block
-//                       per update, cut into work units that 256 lanes claim and re-split in rounds (lp_round).
-//   encode_kernel       One block per chunk of 32 games, one game per lane: warp 0 does done / reward / info (+ auto-reset),
-//                       the legal-action masks as bit sets and the fused random-legal sampler; seven more warps stream
-//                       out one piece of the packed observation row each through a 128-byte sliding window per thread.
+//   caller's stream
+//   transition_kernel    one block per chunk, staged in shared memory.  Warp 0: ONE THREAD PER GAME for translate +
+//                        validate + the scalar part of apply_action, then the incremental longest-road update of the
+//                        games that placed a road / settlement (t_lr_fast: ~93 % are settled by two tiny walks).  The
+//                        other warps: the data-parallel follow-ups (dice payout, belief updates), one warp per game and
+//                        one lane per item.  A game whose longest road needs a real search is queued and copied into a
+//                        staging chunk.
+//   encode_kernel        one block per chunk: warp 0 does done / reward / info (+ auto-reset), the legal-action masks as
+//                        bit sets and the fused random-legal sampler; nine more warps produce one piece of the packed
+//                        observation row each (tile pieces as bit sets expanded in registers, player blocks and card
+//                        lists through a 128-byte window per thread).  The board scans behind the placement masks are
+//                        shared by all ten warps, one warp per game that needs one.  Queued games are left out.
 //
-// Why not one fused kernel: the search is the only part of a step whose cost varies by four orders of magnitude between
-// games; inside a thread-per-game kernel it would stall 31 other games per unit of imbalance (profiles/r1_notes.md).
+//   library's high-priority stream (forked after the transition, joined at the end of the step)
+//   lr_slow_kernel       one 1024-thread block per queued update: the paths through the new road -- or, when the stored
+//                        length cannot be trusted, the reference's full enumeration (game.py:843-862) -- as a pool of
+//                        16-byte subtree tasks that the lanes drain and re-split without barriers (lp_pool).
+//   encode_kernel<LISTED> the same encode for the queued games, on their staging chunks
+//   lr_copy_back_kernel  staging -> home records
+//
+// Why the search is not inside a thread-per-game kernel: its cost varies by four orders of magnitude between games and
+// would stall 31 other games per unit of imbalance; why it runs on a second stream: it is latency-bound (a few hundred
+// dependent walk steps) and touches 0.3 % of the games, so it hides completely behind the encode of the others.
 #include <cuda_runtime.h>
 
 #include <cstddef>
@@ -35,15 +46,18 @@ constexpr int kTransWarps = 4;              // transition_kernel: warps per chun
 constexpr int kTransThreads = kTransWarps * 32;
 constexpr int kEncWarps = 1 + CATAN_OBS_PARTS;   // encode_kernel: finish/masks/sampler warp + one warp per piece of the obs row
 constexpr int kEncThreads = kEncWarps * 32;
-constexpr int kCopyThreads = 128;           // lr_copy_kernel: one warp per game
-constexpr int kLrFastThreads = 32;          // lr_fast_kernel: one thread per queued update
-constexpr int kLrSlowThreads = 1024;        // lr_slow_kernel: one block per update that needs the full enumeration
+constexpr int kCopyThreads = 128;           // lr_copy_back_kernel: one warp per game
+constexpr int kLrSlowThreads = 1024;        // lr_slow_kernel: one block per update that needs a search
 constexpr int kLrSlowBlocksPerSM = 1;
 constexpr int kSampleThreads = 128;         // stand-alone sampler kernel
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
-struct LrCtl { int32_t count, slow_count; unsigned long long total, slow_total, dbg[6], enc[12]; };   // enc: max cycles of finish, warp 0, obs parts 0..8, block   // dbg: search cycles sum/max, walk steps sum/max, full searches, tasks   // queue lengths: written by transition_kernel / lr_fast_kernel, cleared by encode_kernel
+struct LrCtl {                // double-buffered by step parity: the transition of a step clears the other buffer
+  int32_t count, slow_count;  // longest-road updates of this step; those that went to lr_slow_kernel (= length of its queue)
+  unsigned long long total, slow_total;   // the same, summed over all earlier steps
+  unsigned long long dbg[6];  // lr_slow_kernel diagnostics: cycles sum / max, walk steps sum / max per search; full enumerations; tasks
+};
 
 struct EnvParams {
   uint8_t* recs;               // lane-interleaved chunks of 32 games (catan_game.cuh)
@@ -61,8 +75,7 @@ struct EnvParams {
   const uint8_t* env_mask;     // envs whose byte is 0 are left untouched; nullptr = all envs
   int range_first, range_count;   // env range this launch covers
   uint32_t* side;              // [n] transition -> encode: err | acted_pid << 8 | act_type << 16 | roll << 24 | longest-road update pending << 31
-  uint64_t* lr_queue;          // [n] env index | PlayerId << 32 | edge or corner << 40 | CATAN_LR_* << 48 | acting PlayerId << 56
-  uint64_t* lr_slow_queue;     // [n] the entries lr_fast_kernel could not settle
+  uint64_t* lr_slow_queue;     // [n] updates that need a search: env index | PlayerId << 32 | edge or corner << 40 | CATAN_LR_* << 48 | acting PlayerId << 56
   LrCtl* lr_ctl;               // queue lengths of THIS step
   LrCtl* lr_ctl_next;          // the other buffer: cleared by this step's transition for the next step
 };
@@ -94,6 +107,33 @@ __device__ __forceinline__ void chunk_to_global(uint8_t* chunk, const uint8_t* s
   for (int o = tid; o < static_cast<int>(CATAN_CHUNK_BYTES / 16); o += nthreads) d[o] = sp[o];
 }
 
+// The games that need a search are scattered over the chunks: every field access of a warp that works on 32 of them
+// would touch 32 sectors.  The transition therefore copies them (one warp per game) into staging chunks in queue order;
+// they are searched and encoded there with the ordinary coalesced code and copied back.
+__device__ __forceinline__ void copy_game(const GameView& src, const GameView& dst, int lane) {
+  constexpr int n16 = static_cast<int>(offsetof(GameRec, rng_ctr) / 2), b0 = static_cast<int>(offsetof(GameRec, corner)), nb = static_cast<int>(sizeof(GameRec)) - b0;
+  int16_t h[(n16 + 31) / 32];
+  uint8_t c[(nb + 31) / 32];
+#pragma unroll
+  for (int q = 0; q < (n16 + 31) / 32; ++q) if (lane + 32 * q < n16) h[q] = src.at<int16_t>(0, lane + 32 * q);    // all loads first
+#pragma unroll
+  for (int q = 0; q < (nb + 31) / 32; ++q) if (lane + 32 * q < nb) c[q] = src.at<uint8_t>(b0 + lane + 32 * q, 0);
+  const uint32_t w = lane < 3 ? src.at<uint32_t>(offsetof(GameRec, rng_ctr), lane) : 0u;
+  const uint16_t v = lane < 2 ? src.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane) : 0;
+#pragma unroll
+  for (int q = 0; q < (n16 + 31) / 32; ++q) if (lane + 32 * q < n16) dst.at<int16_t>(0, lane + 32 * q) = h[q];
+#pragma unroll
+  for (int q = 0; q < (nb + 31) / 32; ++q) if (lane + 32 * q < nb) dst.at<uint8_t>(b0 + lane + 32 * q, 0) = c[q];
+  if (lane < 3) dst.at<uint32_t>(offsetof(GameRec, rng_ctr), lane) = w;
+  if (lane < 2) dst.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane) = v;
+}
+__global__ void __launch_bounds__(kCopyThreads) lr_copy_back_kernel(const __grid_constant__ EnvParams P) {
+  const int count = P.lr_ctl->slow_count;
+  const int lane = threadIdx.x & 31, warps = static_cast<int>(gridDim.x) * (kCopyThreads / 32);
+  for (int j = static_cast<int>(blockIdx.x) * (kCopyThreads / 32) + (threadIdx.x >> 5); j < count; j += warps)
+    copy_game(game_view(P.stage, static_cast<size_t>(j)), game_view(P.recs, static_cast<uint32_t>(P.lr_slow_queue[j])), lane);
+}
+
 // ---- 1. transition ------------------------------------------------------------------------------
 // One block per chunk of 32 games.  Warp 0 runs the scalar part of apply_action, one game per lane; the data-parallel
 // follow-ups it posts (dice payout over 19 tiles x 6 corners, belief updates over 60 entries) are then executed by all
@@ -103,6 +143,7 @@ struct alignas(16) TransSmem {
   GameSmem topo;
   StepTmp tmp[32];
   int32_t n_follow;
+  int32_t slot[32];          // staging slot of a game that goes to lr_slow_kernel, else -1
   uint8_t follow_list[32];
 };
 
@@ -118,54 +159,73 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     for (int k = 0; k < 6; ++k) P.lr_ctl->dbg[k] = (k == 1 || k == 3) ? max(o.dbg[k], P.lr_ctl->dbg[k]) : o.dbg[k] + P.lr_ctl->dbg[k];
     o.count = 0; o.slow_count = 0; o.total = 0; o.slow_total = 0;
     for (int k = 0; k < 6; ++k) o.dbg[k] = 0;
-    for (int k = 0; k < 12; ++k) { P.lr_ctl->enc[k] = k == 0 ? max(o.enc[k], P.lr_ctl->enc[k]) : o.enc[k] + P.lr_ctl->enc[k]; o.enc[k] = 0; }
   }
   stage_topology(S.topo, tid, kTransThreads);
+  const int i = base + lane;
+  TCx cx;
+  cx.g.base = S.chunk; cx.g.lane = lane;
+  cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
+  bool lr = false;
   if (warp == 0) {
-    const int i = base + lane;
     const bool valid = i >= P.range_first && i < P.range_first + P.range_count && !(P.env_mask != nullptr && P.env_mask[i] == 0);
     bool follow = false;
     if (valid) {
-      TCx cx;
-      cx.g.base = S.chunk; cx.g.lane = lane;
-      cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
       cx.s = load_seats(cx.g);
       StepTmp& tmp = S.tmp[lane];
       t_step_scalar(cx, P.actions + static_cast<size_t>(i) * CATAN_ACTION_WORDS, tmp);
-      P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
-                  (static_cast<uint32_t>(tmp.roll_info) << 24) | ((!tmp.err && tmp.lr_pid) ? 0x80000000u : 0u);
-      if (tmp.err) {
-        P.err_flags[i] |= 1u << tmp.err;
-      } else if (tmp.lr_pid) {
-        const int slot = atomicAdd(&P.lr_ctl->count, 1);
-        P.lr_queue[slot] = static_cast<uint64_t>(static_cast<uint32_t>(i)) | (static_cast<uint64_t>(tmp.lr_pid) << 32) | (static_cast<uint64_t>(tmp.lr_loc) << 40) |
-                           (static_cast<uint64_t>(tmp.lr_kind) << 48) | (static_cast<uint64_t>(tmp.acted_pid) << 56);
-      }
+      if (tmp.err) P.err_flags[i] |= 1u << tmp.err;
+      lr = !tmp.err && tmp.lr_pid;
       follow = tmp.follow != 0;
     }
     const unsigned fb = __ballot_sync(0xffffffffu, follow);
     if (follow) S.follow_list[__popc(fb & ((1u << lane) - 1u))] = static_cast<uint8_t>(lane);
     if (lane == 0) S.n_follow = __popc(fb);
+    S.slot[lane] = -1;
   }
   __syncthreads();
-  const int nf = S.n_follow;
-  for (int j = warp; j < nf; j += kTransWarps) {
-    GameView g;
-    g.base = S.chunk; g.lane = S.follow_list[j];
-    t_followups_group(g, S.topo.topo, S.tmp[g.lane], lane, 32);
+  if (warp == 0) {
+    // longest road (game.py:843-919), one thread per update: the incremental rule settles ~93 % of them on the spot; a
+    // game that needs a search goes to the queue of lr_slow_kernel.  (Independent of the follow-ups: those touch hands,
+    // bank and beliefs only.)
+    const StepTmp& tmp = S.tmp[lane];
+    bool slow = false;
+    if (lr) {
+      const int len = t_lr_fast(cx.g, S.topo.topo, tmp.lr_pid, tmp.lr_kind, tmp.lr_loc, tmp.acted_pid);
+      if (len >= 0) t_lr_apply(cx.g, tmp.lr_pid, len, false, nullptr);
+      else slow = true;
+    }
+    if (slow) {
+      const int slot = atomicAdd(&P.lr_ctl->slow_count, 1);
+      P.lr_slow_queue[slot] = static_cast<uint64_t>(static_cast<uint32_t>(i)) | (static_cast<uint64_t>(tmp.lr_pid) << 32) | (static_cast<uint64_t>(tmp.lr_loc) << 40) |
+                              (static_cast<uint64_t>(tmp.lr_kind) << 48) | (static_cast<uint64_t>(tmp.acted_pid) << 56);
+      S.slot[lane] = slot;
+    }
+    const unsigned lb = __ballot_sync(0xffffffffu, lr);
+    if (lane == 0 && lb) atomicAdd(&P.lr_ctl->count, __popc(lb));
+    if (i >= P.range_first && i < P.range_first + P.range_count && !(P.env_mask != nullptr && P.env_mask[i] == 0))
+      P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
+                  (static_cast<uint32_t>(tmp.roll_info) << 24) | (slow ? 0x80000000u : 0u);
+  } else {
+    const int nf = S.n_follow;
+    for (int j = warp - 1; j < nf; j += kTransWarps - 1) {
+      GameView g;
+      g.base = S.chunk; g.lane = S.follow_list[j];
+      t_followups_group(g, S.topo.topo, S.tmp[g.lane], lane, 32);
+    }
   }
   __syncthreads();
   chunk_to_global(home, S.chunk, tid, kTransThreads);               // (frozen games go back unchanged)
+  for (int b = warp; b < 32; b += kTransWarps) {                     // games that wait for a search: also into their staging slot
+    const int slot = S.slot[b];
+    if (slot >= 0) copy_game(GameView{S.chunk, b}, game_view(P.stage, static_cast<size_t>(slot)), lane);
+  }
 }
 
 // ---- 2. longest road ----------------------------------------------------------------------------
-// Measured on random play at ticks 1000-1600 (oracle, 21 k updates): 3.5 % of the steps trigger an update; the reference's
-// full enumeration visits 205 corners on average and 13 k at most.
-//   lr_fast_kernel  one THREAD per queued update: the incremental rule of t_lr_fast() settles ~95 % of them with two
-//                   searches of ~10 visits; the rest goes to a second queue.
-//   lr_slow_kernel  one BLOCK per remaining update: the enumeration of the paths through the new road -- or, when the
-//                   stored length cannot be trusted, the reference's full enumeration -- as a pool of 16-byte subtree
-//                   tasks that 256 lanes drain and re-split in rounds (lp_round).
+// Measured on random play at ticks 1000-1600 (oracle, 38 k road placements): 3.5 % of the steps trigger an update; the
+// reference's full enumeration visits 205 corners on average and 29 k at most.  96 % of the new roads are bridges of the
+// player's road graph, where the incremental rule of t_lr_fast() (inside transition_kernel) is exact with two walks of
+// ~10 visits; 166 updates per step (65 536 games) come here: one BLOCK per update, see lp_pool in catan_core.cuh.
 constexpr int kLrRing = 8192;               // task ring of the pool (shared memory; a power of two >= 4 x lanes + 64)
 struct alignas(16) LrSmem {
   Topo topo;
@@ -176,47 +236,6 @@ struct alignas(16) LrSmem {
   int32_t ctl[CATAN_LP_CTL_WORDS];
   int32_t rounds, tasks;     // diagnostics: walk steps and tasks of the current update
 };
-
-// The games of the update queue are scattered over the chunks: every field access of a warp that works on 32 of them
-// would touch 32 sectors.  They are therefore copied (one warp per game, all fields in flight at once) into staging
-// chunks in queue order, updated and encoded there with the ordinary coalesced code, and copied back.
-__device__ __forceinline__ void copy_game(const GameView& src, const GameView& dst, int lane) {
-  for (int k = lane; k < static_cast<int>(offsetof(GameRec, rng_ctr) / 2); k += 32) dst.at<int16_t>(0, k) = src.at<int16_t>(0, k);
-  if (lane < 3) dst.at<uint32_t>(offsetof(GameRec, rng_ctr), lane) = src.at<uint32_t>(offsetof(GameRec, rng_ctr), lane);
-  if (lane < 2) dst.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane) = src.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane);
-  for (int k = static_cast<int>(offsetof(GameRec, corner)) + lane; k < static_cast<int>(sizeof(GameRec)); k += 32) dst.at<uint8_t>(k, 0) = src.at<uint8_t>(k, 0);
-}
-template <bool TO_STAGE>
-__global__ void __launch_bounds__(kCopyThreads) lr_copy_kernel(const __grid_constant__ EnvParams P) {
-  const int count = P.lr_ctl->count;
-  const int lane = threadIdx.x & 31, warps = static_cast<int>(gridDim.x) * (kCopyThreads / 32);
-  for (int j = static_cast<int>(blockIdx.x) * (kCopyThreads / 32) + (threadIdx.x >> 5); j < count; j += warps) {
-    const GameView home = game_view(P.recs, static_cast<uint32_t>(P.lr_queue[j])), st = game_view(P.stage, static_cast<size_t>(j));
-    if (TO_STAGE) copy_game(home, st, lane); else copy_game(st, home, lane);
-  }
-}
-
-__global__ void __launch_bounds__(kLrFastThreads) lr_fast_kernel(const __grid_constant__ EnvParams P) {
-  __shared__ __align__(16) Topo sT;
-  const int count = P.lr_ctl->count;
-  if (static_cast<int>(blockIdx.x) * kLrFastThreads >= count) return;
-  {
-    const int4* src = reinterpret_cast<const int4*>(&d_topo);
-    int4* dst = reinterpret_cast<int4*>(&sT);
-    for (int i = threadIdx.x; i < static_cast<int>(sizeof(Topo) / 16); i += kLrFastThreads) dst[i] = src[i];
-  }
-  __syncthreads();
-  // consecutive lanes take consecutive staging games (coalesced); one warp per block spreads a short queue over the SMs
-  for (int j = static_cast<int>(blockIdx.x) * kLrFastThreads + threadIdx.x; j < count; j += static_cast<int>(gridDim.x) * kLrFastThreads) {
-    const uint64_t en = P.lr_queue[j];
-    const GameView g = game_view(P.stage, static_cast<size_t>(j));
-    const int pid = static_cast<int>((en >> 32) & 0xff), loc = static_cast<int>((en >> 40) & 0xff), kind = static_cast<int>((en >> 48) & 0xff),
-              placer = static_cast<int>(en >> 56);
-    const int len = t_lr_fast(g, sT, pid, kind, loc, placer);
-    if (len >= 0) t_lr_apply(g, pid, len, false, nullptr);
-    else P.lr_slow_queue[atomicAdd(&P.lr_ctl->slow_count, 1)] = (en & ~0xffffffffull) | static_cast<uint64_t>(j);   // staging slot instead of the env
-  }
-}
 
 __device__ __forceinline__ int block_longest_path(LrSmem& S, const GameView& g, int pid, int tid) {
   if (tid < 32) t_lp_build_adj(g, S.topo, pid, S.adj, tid, 32);
@@ -260,7 +279,7 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
   __syncthreads();
   for (int j = static_cast<int>(blockIdx.x); j < count; j += static_cast<int>(gridDim.x)) {
     const uint64_t en = P.lr_slow_queue[j];
-    const GameView g = game_view(P.stage, static_cast<uint32_t>(en));
+    const GameView g = game_view(P.stage, static_cast<size_t>(j));
     const int pid = static_cast<int>((en >> 32) & 0xff), loc = static_cast<int>((en >> 40) & 0xff), kind = static_cast<int>((en >> 48) & 0xff);
     const long long t_start = clock64();
     bool was_full = true;
@@ -299,6 +318,7 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
 // every ~40 cycles), hence the many narrow parts.
 constexpr int kObsRingThreads = (CATAN_OBS_PARTS - CATAN_OBS_TILE_PARTS) * 32;   // the tile parts build their pieces in registers
 struct alignas(16) EncSmem {
+  uint8_t chunk[CATAN_CHUNK_BYTES];                                 // the 32 games of this block (see chunk_to_shared)
   GameSmem topo;
   uint32_t ring[(CATAN_RING_BYTES / 4) * kObsRingThreads];          // RowWriter windows, word-interleaved over those threads
   uint32_t wbuf[CATAN_RESET_WORDS];                                 // reset: pre-drawn Philox words (warp 0)
@@ -312,27 +332,31 @@ struct alignas(16) EncSmem {
 // (side bit 31) are left out.  LISTED = true: those games, 32 per block iteration in queue order, on their staging
 // copies once the searches have finished (second stream, see launch_step).
 template <int MODE, bool SAMPLE, bool LISTED>
-__global__ void __launch_bounds__(kEncThreads, 5) encode_kernel(const __grid_constant__ EnvParams P) {
-  __shared__ EncSmem S;
+__global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_constant__ EnvParams P) {
+  extern __shared__ __align__(16) uint8_t enc_smem_raw[];
+  EncSmem& S = *reinterpret_cast<EncSmem*>(enc_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int list_count = LISTED ? P.lr_ctl->count : 0;
+  const int list_count = LISTED ? P.lr_ctl->slow_count : 0;
   if (LISTED && static_cast<int>(blockIdx.x) * 32 >= list_count) return;
   stage_topology(S.topo, tid, kEncThreads);
-  const long long t_enc0 = clock64();
   for (int l0 = static_cast<int>(blockIdx.x) * 32; LISTED ? l0 < list_count : l0 == static_cast<int>(blockIdx.x) * 32; l0 += static_cast<int>(gridDim.x) * 32) {
     int i;
     bool valid;
     if (LISTED) {
       valid = l0 + lane < list_count;
-      i = valid ? static_cast<int>(static_cast<uint32_t>(P.lr_queue[l0 + lane])) : 0;
+      i = valid ? static_cast<int>(static_cast<uint32_t>(P.lr_slow_queue[l0 + lane])) : 0;
     } else {
       i = (P.range_first & ~31) + l0 + lane;
       valid = i >= P.range_first && i < P.range_first + P.range_count && !(MODE != MODE_REFRESH && P.env_mask != nullptr && P.env_mask[i] == 0);
       if (MODE == MODE_STEP && valid) valid = !(P.side[i] >> 31);
     }
-    // the chunk of these 32 games (home records, or the staging copies); lane b of every warp works on game b of it
+    // the chunk of these 32 games (home records, or the staging copies) -> shared memory; lane b of every warp works on
+    // game b of it.  What the block changes goes home explicitly: the games of the other stream must not be touched.
     uint8_t* const home = (LISTED ? P.stage : P.recs) + static_cast<size_t>((LISTED ? l0 : (P.range_first & ~31) + l0) >> 5) * CATAN_CHUNK_BYTES;
-#define CATAN_VIEW_OF(b_) GameView{home, (b_)}
+    chunk_to_shared(S.chunk, home, tid, kEncThreads);
+    __syncthreads();
+    const GameView hv = GameView{home, lane};
+#define CATAN_VIEW_OF(b_) GameView{S.chunk, (b_)}
     TCx cx;
     cx.g = CATAN_VIEW_OF(lane);
     cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
@@ -354,16 +378,20 @@ __global__ void __launch_bounds__(kEncThreads, 5) encode_kernel(const __grid_con
       // Board.reset + Game.reset are a handful of serial shuffles: the warp does them game by game (lanes pre-draw the
       // Philox words in parallel).  Rare in a step (a game ends every ~1500 steps), everything in catan_reset.
       unsigned rb = __ballot_sync(0xffffffffu, need_reset);
-      if (MODE == MODE_STEP && lane == 0 && rb) atomicAdd(&P.lr_ctl->enc[7], static_cast<unsigned long long>(__popc(rb)));
       while (rb) {
         const int b = __ffs(static_cast<int>(rb)) - 1;
         rb &= rb - 1;
         const int e = __shfl_sync(0xffffffffu, i, b);
         reset_game_group(CATAN_VIEW_OF(b), S.topo.topo, P.seed, P.first_env_id + static_cast<uint64_t>(e), S.wbuf, S.arr,
                          lane, 32, MODE == MODE_STEP ? P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE : nullptr);
+        copy_game(CATAN_VIEW_OF(b), GameView{home, b}, lane);        // the whole new game goes home
+      }
+      if (MODE == MODE_STEP && valid) {                              // what done / reward changed (wrapper.py:85-112)
+        hv.episode_steps() = cx.g.episode_steps(); hv.winner() = cx.g.winner();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) hv.curr_vps(p) = cx.g.curr_vps(p);
       }
     }
-    if (MODE == MODE_STEP && tid == 0) { const unsigned long long d = static_cast<unsigned long long>(clock64() - t_enc0); atomicMax(&P.lr_ctl->enc[0], d); atomicAdd(&P.lr_ctl->enc[1], d); atomicAdd(&P.lr_ctl->enc[2], 1ull); }
     __syncthreads();                                                 // the games are final: every warp may read them now
     if (valid) cx.s = load_seats(cx.g);
     MaskBits m;
@@ -404,14 +432,13 @@ __global__ void __launch_bounds__(kEncThreads, 5) encode_kernel(const __grid_con
 #pragma unroll
           for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(cx.g.res(ap, r) != 0) << r;
           const uint32_t decision = cx.g.decision_ctr();
-          cx.g.decision_ctr() = decision + 1;
+          hv.decision_ctr() = decision + 1;
           t_sample_action(m, hand, P.seed, cx.env_id, decision, P.actions_out + static_cast<size_t>(i) * CATAN_ACTION_WORDS);
         }
       }
     } else if (valid) {
       t_encode_obs_part<kObsRingThreads>(cx, S.ring + (tid - 32 * (1 + CATAN_OBS_TILE_PARTS)), P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE, warp - 1);
     }
-    if (MODE == MODE_STEP && lane == 0 && (warp == 0 || warp == 1 || warp == 5 || warp == 9)) atomicAdd(&P.lr_ctl->enc[warp == 0 ? 3 : warp == 1 ? 4 : warp == 5 ? 5 : 6], static_cast<unsigned long long>(clock64() - t_enc0));
     if (LISTED) __syncthreads();                                     // warp 0's reset scratch is reused by the next 32 games
 #undef CATAN_VIEW_OF
   }
@@ -457,7 +484,6 @@ struct catan_env {
   size_t rec_bytes = 0;
   uint32_t* err_flags = nullptr;
   uint32_t* side = nullptr;
-  uint64_t* lr_queue = nullptr;
   uint64_t* lr_slow_queue = nullptr;
   catanb::LrCtl* lr_ctl = nullptr;
   int32_t* actions_stage = nullptr;   // device staging for catan_step_host
@@ -469,6 +495,12 @@ struct catan_env {
   cudaStream_t lr_stream = nullptr;   // high-priority stream of the longest-road updates (overlaps the encode kernel)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   unsigned long long ticks = 0;        // steps launched: selects the queue-counter buffer
+  // catan_set_timing: CUDA events around the two kernels on the caller's stream, a ring of kTimedSteps steps
+  bool timing = false;
+  cudaEvent_t tev[32][3] = {};
+  unsigned long long timed = 0;        // steps recorded since timing was switched on
+  double t_ms[2] = {0.0, 0.0};         // transition, encode: summed over the steps already retired from the ring
+  unsigned long long t_n = 0;
 };
 
 static int device_guard(const catan_env* env) {
@@ -482,7 +514,7 @@ static EnvParams make_params(const catan_env* env) {
   EnvParams P{};
   P.recs = env->recs; P.stage = env->stage; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
   P.obs = env->obs; P.masks = env->masks; P.reward = env->reward; P.info = env->info; P.err_flags = env->err_flags;
-  P.side = env->side; P.lr_queue = env->lr_queue; P.lr_slow_queue = env->lr_slow_queue; P.lr_ctl = env->lr_ctl + (env->ticks & 1); P.lr_ctl_next = env->lr_ctl + ((env->ticks & 1) ^ 1);
+  P.side = env->side; P.lr_slow_queue = env->lr_slow_queue; P.lr_ctl = env->lr_ctl + (env->ticks & 1); P.lr_ctl_next = env->lr_ctl + ((env->ticks & 1) ^ 1);
   return P;
 }
 
@@ -494,7 +526,7 @@ template <int MODE, bool SAMPLE>
 static int launch_encode(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
   P.range_first = first; P.range_count = count;
   if (count <= 0) return 0;
-  catanb::encode_kernel<MODE, SAMPLE, false><<<game_blocks(first, count), catanb::kEncThreads, 0, stream>>>(P);
+  catanb::encode_kernel<MODE, SAMPLE, false><<<game_blocks(first, count), catanb::kEncThreads, sizeof(catanb::EncSmem), stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -503,26 +535,40 @@ static int launch_encode(catan_env* env, EnvParams P, int first, int count, cuda
 // On the library's high-priority stream, forked after the transition and joined at the end: the queued longest-road
 // updates and the encode of exactly those games.  The searches are latency-bound (a few hundred dependent walk steps
 // per update) and would otherwise sit between the two big kernels with the machine idle.
+static int retire_timed_step(catan_env* env, cudaEvent_t* ev) {     // one ring slot -> the sums (waits for that step)
+  float a = 0.f, b = 0.f;
+  CATAN_CUDA(cudaEventSynchronize(ev[2]));
+  CATAN_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+  CATAN_CUDA(cudaEventElapsedTime(&b, ev[1], ev[2]));
+  env->t_ms[0] += a; env->t_ms[1] += b; env->t_n += 1;
+  return 0;
+}
+
 template <bool SAMPLE>
 static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   P.range_first = 0; P.range_count = env->n;
+  cudaEvent_t* tev = nullptr;
+  if (env->timing) {
+    tev = env->tev[env->timed % 32];
+    if (env->timed >= 32 && retire_timed_step(env, tev)) return -1;
+    env->timed += 1;
+    CATAN_CUDA(cudaEventRecord(tev[0], stream));
+  }
   catanb::transition_kernel<<<game_blocks(0, env->n), catanb::kTransThreads, 0, stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
+  if (tev) CATAN_CUDA(cudaEventRecord(tev[1], stream));
   env->ticks += 1;
   CATAN_CUDA(cudaEventRecord(env->ev_fork, stream));
   CATAN_CUDA(cudaStreamWaitEvent(env->lr_stream, env->ev_fork, 0));
-  catanb::lr_copy_kernel<true><<<env->sm_count * 8, catanb::kCopyThreads, 0, env->lr_stream>>>(P);
-  CATAN_CUDA(cudaGetLastError());
-  catanb::lr_fast_kernel<<<env->sm_count * 4, catanb::kLrFastThreads, 0, env->lr_stream>>>(P);
-  CATAN_CUDA(cudaGetLastError());
   catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), env->lr_stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
-  catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count, catanb::kEncThreads, 0, env->lr_stream>>>(P);
+  catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count / 2, catanb::kEncThreads, sizeof(catanb::EncSmem), env->lr_stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
-  catanb::lr_copy_kernel<false><<<env->sm_count * 8, catanb::kCopyThreads, 0, env->lr_stream>>>(P);
+  catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->lr_stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
   CATAN_CUDA(cudaEventRecord(env->ev_join, env->lr_stream));
   if (launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream)) return -1;
+  if (tev) CATAN_CUDA(cudaEventRecord(tev[2], stream));
   CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join, 0));
   return 0;
 }
@@ -537,7 +583,8 @@ static void free_env(catan_env* env) {
   if (env->lr_stream) cudaStreamDestroy(env->lr_stream);
   if (env->ev_fork) cudaEventDestroy(env->ev_fork);
   if (env->ev_join) cudaEventDestroy(env->ev_join);
-  cudaFree(env->recs); cudaFree(env->stage); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_queue); cudaFree(env->lr_slow_queue); cudaFree(env->lr_ctl);
+  for (auto& slot : env->tev) for (cudaEvent_t ev : slot) if (ev) cudaEventDestroy(ev);
+  cudaFree(env->recs); cudaFree(env->stage); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_slow_queue); cudaFree(env->lr_ctl);
   cudaFree(env->actions_stage);
   delete env;
 }
@@ -591,7 +638,6 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   if (e == cudaSuccess) e = cudaMemset(env->err_flags, 0, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->side, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMemset(env->side, 0, sizeof(uint32_t) * n);
-  if (e == cudaSuccess) e = cudaMalloc(&env->lr_queue, sizeof(uint64_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->lr_slow_queue, sizeof(uint64_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->lr_ctl, 2 * sizeof(catanb::LrCtl));
   if (e == cudaSuccess) e = cudaMemset(env->lr_ctl, 0, 2 * sizeof(catanb::LrCtl));
@@ -603,6 +649,15 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming);
+  {
+    const int enc_bytes = static_cast<int>(sizeof(catanb::EncSmem));   // > 48 KB: opt in, per instantiation
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_RESET, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_REFRESH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
+  }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::lr_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::LrSmem)));
   if (e != cudaSuccess) {
     free_env(env);
@@ -774,7 +829,26 @@ int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
   out_host[1] = last.slow_total + static_cast<unsigned long long>(last.slow_count);
   out_host[2] = last.dbg[4]; out_host[3] = last.dbg[5];
   for (int i = 0; i < 4; ++i) out_host[4 + i] = last.dbg[i];
-  for (int i = 0; i < 12; ++i) out_host[8 + i] = last.enc[i];
+  return 0;
+}
+
+int catan_set_timing(catan_env_t* env, int enable) {
+  if (!env) return fail("null handle");
+  if (device_guard(env)) return -1;
+  CATAN_CUDA(cudaDeviceSynchronize());
+  if (enable)
+    for (auto& slot : env->tev) for (cudaEvent_t& ev : slot) if (!ev) CATAN_CUDA(cudaEventCreate(&ev));
+  env->timing = enable != 0; env->timed = 0; env->t_ms[0] = env->t_ms[1] = 0.0; env->t_n = 0;
+  return 0;
+}
+
+int catan_read_timing(catan_env_t* env, double* out_host) {
+  if (!env || !out_host) return fail("null argument");
+  if (device_guard(env)) return -1;
+  const unsigned long long pending = env->timed < 32 ? env->timed : 32;
+  for (unsigned long long k = env->timed - pending; k < env->timed; ++k) if (retire_timed_step(env, env->tev[k % 32])) return -1;
+  env->timed = 0;                                                    // (the ring is empty again)
+  out_host[0] = static_cast<double>(env->t_n); out_host[1] = env->t_ms[0]; out_host[2] = env->t_ms[1];
   return 0;
 }
 

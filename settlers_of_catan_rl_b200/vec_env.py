@@ -76,7 +76,7 @@ class VecCatanEnv:
         if step_mask is not None:
             assert step_mask.dtype == torch.uint8 and step_mask.is_cuda and step_mask.numel() == self.n_envs
         _lib.check(self.lib.catan_step_masked(self._h, _ptr(actions), _ptr(step_mask), self._stream()))
-        self.kernel_launches += 7                      # transition, encode | copy-in, lr_fast, lr_slow, encode (listed), copy-out
+        self.kernel_launches += 5                      # transition, encode | lr_slow, encode (listed), copy-back
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
     def sample_random(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -87,10 +87,10 @@ class VecCatanEnv:
         return out
 
     def step_sample(self, actions_io: torch.Tensor):
-        """One call (seven launches on two streams, the sampler fused into the last): apply ``actions_io`` and overwrite it with the next random-legal actions."""
+        """One call (five launches on two streams, the sampler fused into the last): apply ``actions_io`` and overwrite it with the next random-legal actions."""
         assert actions_io.dtype == torch.int32 and actions_io.is_cuda and actions_io.is_contiguous()
         _lib.check(self.lib.catan_step_sample(self._h, _ptr(actions_io), self._stream()))
-        self.kernel_launches += 7
+        self.kernel_launches += 5
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
     def get_action_masks(self) -> torch.Tensor:
@@ -103,7 +103,7 @@ class VecCatanEnv:
             return C.c_void_p(0 if a is None else a.ctypes.data)
         assert actions.dtype == np.int32 and actions.flags.c_contiguous
         _lib.check(self.lib.catan_step_host(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
-        self.kernel_launches += 7
+        self.kernel_launches += 5
 
     def reset_host(self, obs: np.ndarray = None, masks: np.ndarray = None, info: np.ndarray = None) -> None:
         def p(a):
@@ -124,10 +124,22 @@ class VecCatanEnv:
         self.kernel_launches += 1
 
     def lr_stats(self) -> np.ndarray:
-        """(longest-road updates triggered, updates that needed a block-wide search, 0, 0) since construction"""
-        out = np.zeros(20, dtype=np.uint64)
+        """catan_read_lr_stats: [updates, searched by a block, full enumerations, search tasks, search cycles sum, max,
+        walk steps sum, max] since construction"""
+        out = np.zeros(8, dtype=np.uint64)
         _lib.check(self.lib.catan_read_lr_stats(self._h, C.c_void_p(out.ctypes.data)))
         return out
+
+    def set_timing(self, enable: bool) -> None:
+        """CUDA events around the transition and encode kernels of every following step (catan_set_timing)"""
+        _lib.check(self.lib.catan_set_timing(self._h, int(enable)))
+
+    def read_timing(self):
+        """(steps timed, average ms of transition_kernel, average ms of encode_kernel) since set_timing(True)"""
+        out = np.zeros(3, dtype=np.float64)
+        _lib.check(self.lib.catan_read_timing(self._h, C.c_void_p(out.ctypes.data)))
+        n = max(1.0, out[0])
+        return int(out[0]), out[1] / n, out[2] / n
 
     def err_flags(self, clear: bool = False) -> np.ndarray:
         out = np.zeros(self.n_envs, dtype=np.uint32)

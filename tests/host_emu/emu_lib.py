@@ -21,22 +21,26 @@ _SRCS = [os.path.join(_HERE, "emu.cpp"), os.path.join(_ROOT, "settlers_of_catan_
          os.path.join(_ROOT, "include", "catan_layout.h"), os.path.join(_ROOT, "include", "catan_topology.h")]
 
 
-def build(force=False):
-    stale = force or not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in _SRCS)
+# "search": the incremental longest-road rule gives up at once (CATAN_LR_FAST_ITERS=1), so every road placement goes through
+# the pooled search of the paths through the new road -- the code lr_slow_kernel runs for ~7 % of the updates on the device
+SO_SEARCH = os.path.join(_HERE, "libcatan_emu_search.so")
+
+
+def build(force=False, flavor="default"):
+    so, extra = (SO, []) if flavor == "default" else (SO_SEARCH, ["-DCATAN_LR_FAST_ITERS=1"])
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in _SRCS)
     if stale:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-shared", "-o", SO,
-                               _SRCS[0]])
-    return SO
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
+                               "-Wno-unused-but-set-variable", "-shared"] + extra + ["-o", so, _SRCS[0]])
+    return so
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        l = C.CDLL(SO)
+def lib(flavor="default"):
+    if flavor not in _libs:
+        l = C.CDLL(build(flavor=flavor))
         l.emu_create.restype = C.c_void_p
         l.emu_create.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(Config)]
         l.emu_destroy.argtypes = [C.c_void_p]
@@ -53,13 +57,13 @@ def lib():
         l.emu_import_state.argtypes = [C.c_void_p, C.POINTER(C.c_int16)]
         l.emu_longest_path.argtypes = [C.c_void_p, C.c_int]
         l.emu_longest_path.restype = C.c_int
-        _lib = l
-    return _lib
+        _libs[flavor] = l
+    return _libs[flavor]
 
 
 class EmuEnv:
-    def __init__(self, seed=0, env_id=0, **cfg):
-        self.l = lib()
+    def __init__(self, seed=0, env_id=0, flavor="default", **cfg):
+        self.l = lib(flavor)
         self.cfg = make_config(**cfg)
         self.h = self.l.emu_create(seed, env_id, C.byref(self.cfg))
 

@@ -71,6 +71,29 @@ def test_core_matches_oracle_on_random_games(seed, cfg):
     assert games >= 1
 
 
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_search_through_the_new_road_matches_oracle(seed):
+    """every road placement settled by the pooled search of the paths through the new road (the device's lr_slow_kernel
+    path) instead of the one-thread incremental rule: states (cur_longest_path, holder, VP) stay bit-equal to the oracle"""
+    o = O.OracleEnv(seed, 700 + seed)
+    e = EmuEnv(seed, 700 + seed, flavor="search")
+    o.reset()
+    e.reset()
+    games = 0
+    for t in range(5000):
+        om, oo = o.masks(), o.obs()
+        assert not state_diff(o.state, e.state(), ignore=()), (t, state_diff(o.state, e.state(), ignore=())[:5])
+        a = o.sample(om, oo, t)
+        err, r, info = o.step(a)
+        err2, r2, info2 = e.step(a)
+        assert err == 0 and err2 == 0 and np.array_equal(r, r2)
+        if info[0]:
+            games += 1
+            o.reset()
+            e.reset()
+    assert games >= 1
+
+
 def test_core_rejects_illegal_actions_like_the_reference():
     """wrapper.py:38-41: an invalid action raises; here: error code, state untouched."""
     e = EmuEnv(1, 1)

@@ -125,6 +125,34 @@ def test_cuda_matches_oracle_at_scale(n_envs, steps, chunk, cfg):
         assert ov.games_done.sum() > 0
 
 
+def test_cuda_imported_games_take_the_full_longest_road_search():
+    """catan_import_state cannot know how cur_longest_path relates to the imported board, so the first road of every
+    player re-enumerates all paths (game.py:843-862 as written) instead of the incremental rule; both must agree."""
+    from settlers_of_catan_rl_b200 import VecCatanEnv
+    n = 2048
+    a = VecCatanEnv(n, seed=11, first_env_id=500)
+    a.reset()
+    acts = a.sample_random()
+    for _ in range(700):
+        a.step_sample(acts)
+    b = VecCatanEnv(n, seed=11, first_env_id=500)
+    b.reset()
+    b.import_state(a.export_state())
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.masks, b.masks)
+    full0 = int(b.lr_stats()[2])
+    for t in range(400):
+        cur = acts.clone()                             # the actions `a` is about to apply
+        a.step_sample(acts)
+        b.step(cur)
+        if t % 50 == 49:
+            assert np.array_equal(a.export_state(), b.export_state()), t
+            assert torch.equal(a.obs, b.obs) and torch.equal(a.masks, b.masks) and torch.equal(a.reward, b.reward), t
+    sa, sb = a.lr_stats(), b.lr_stats()
+    assert sb[2] - full0 > 100, "the imported games never took the full enumeration"
+    assert sa[0] > 0 and sa[1] <= sa[0] and sa[2] <= sa[1]
+    assert not a.err_flags().any() and not b.err_flags().any()
+
+
 def test_cuda_split_sample_then_step_equals_fused():
     from settlers_of_catan_rl_b200 import VecCatanEnv
     a = VecCatanEnv(512, seed=3, first_env_id=99)
