@@ -96,15 +96,33 @@ __device__ __forceinline__ void stage_topology(GameSmem& S, int tid, int nthread
 // The chunk of 32 games a block works on is staged in shared memory: a game's fields are spread over the whole 26 KB
 // chunk, and the rule code reads them through long chains of dependent loads -- from HBM/L2 one miss (0.3-1 us) at a
 // time, a block needed ~100 us for a few thousand instructions.  The copy is one burst of independent 16-byte loads.
-__device__ __forceinline__ void chunk_to_shared(uint8_t* dst, const uint8_t* chunk, int tid, int nthreads) {
-  const int4* src = reinterpret_cast<const int4*>(chunk);
-  int4* d = reinterpret_cast<int4*>(dst);
-  for (int o = tid; o < static_cast<int>(CATAN_CHUNK_BYTES / 16); o += nthreads) d[o] = __ldcg(src + o);
+// Both directions go through the TMA engine as ONE 1-D bulk copy issued by one thread (cp.async.bulk, SASS UBLKCP):
+// with ordinary 16-byte loads / stores the two copies were 36 % of the transition kernel's stall samples.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar) {           // by one thread; make it visible with a block barrier
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void chunk_to_global(uint8_t* chunk, const uint8_t* src, int tid, int nthreads) {
-  const int4* sp = reinterpret_cast<const int4*>(src);
-  int4* d = reinterpret_cast<int4*>(chunk);
-  for (int o = tid; o < static_cast<int>(CATAN_CHUNK_BYTES / 16); o += nthreads) d[o] = sp[o];
+// by one thread: start the copy of a chunk into shared memory; everybody then waits with chunk_wait(bar, phase)
+__device__ __forceinline__ void chunk_to_shared(uint8_t* dst, const uint8_t* chunk, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(static_cast<uint32_t>(CATAN_CHUNK_BYTES)) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(chunk), "r"(static_cast<uint32_t>(CATAN_CHUNK_BYTES)), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void chunk_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  } while (!ok);
+}
+// every thread that wrote to the staged chunk: chunk_written(), then a block barrier; then ONE thread: chunk_to_global()
+__device__ __forceinline__ void chunk_written() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void chunk_to_global(uint8_t* chunk, const uint8_t* src) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(chunk), "r"(smem_u32(src)), "r"(static_cast<uint32_t>(CATAN_CHUNK_BYTES)) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the block may exit (and its shared memory go) after this
 }
 
 // The games that need a search are scattered over the chunks: every field access of a warp that works on 32 of them
@@ -138,8 +156,9 @@ __global__ void __launch_bounds__(kCopyThreads) lr_copy_back_kernel(const __grid
 // One block per chunk of 32 games.  Warp 0 runs the scalar part of apply_action, one game per lane; the data-parallel
 // follow-ups it posts (dice payout over 19 tiles x 6 corners, belief updates over 60 entries) are then executed by all
 // warps of the block, one warp per game and one lane per item.
-struct alignas(16) TransSmem {
+struct alignas(128) TransSmem {
   uint8_t chunk[CATAN_CHUNK_BYTES];
+  uint64_t mbar;
   GameSmem topo;
   StepTmp tmp[32];
   int32_t n_follow;
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int base = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32;
   uint8_t* const home = P.recs + static_cast<size_t>(base >> 5) * CATAN_CHUNK_BYTES;
-  chunk_to_shared(S.chunk, home, tid, kTransThreads);
+  if (tid == 0) mbar_init(&S.mbar);
   if (blockIdx.x == 0 && tid == 0) {                                 // the other queue buffer belongs to the step before: bank its counts, clear it
     LrCtl& o = *P.lr_ctl_next;
     P.lr_ctl->total = o.total + static_cast<unsigned long long>(o.count); P.lr_ctl->slow_total = o.slow_total + static_cast<unsigned long long>(o.slow_count);
@@ -160,7 +179,10 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     o.count = 0; o.slow_count = 0; o.total = 0; o.slow_total = 0;
     for (int k = 0; k < 6; ++k) o.dbg[k] = 0;
   }
+  __syncthreads();
+  if (tid == 0) chunk_to_shared(S.chunk, home, &S.mbar);
   stage_topology(S.topo, tid, kTransThreads);
+  chunk_wait(&S.mbar, 0);
   const int i = base + lane;
   TCx cx;
   cx.g.base = S.chunk; cx.g.lane = lane;
@@ -213,12 +235,13 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
       t_followups_group(g, S.topo.topo, S.tmp[g.lane], lane, 32);
     }
   }
+  chunk_written();
   __syncthreads();
-  chunk_to_global(home, S.chunk, tid, kTransThreads);               // (frozen games go back unchanged)
   for (int b = warp; b < 32; b += kTransWarps) {                     // games that wait for a search: also into their staging slot
     const int slot = S.slot[b];
     if (slot >= 0) copy_game(GameView{S.chunk, b}, game_view(P.stage, static_cast<size_t>(slot)), lane);
   }
+  if (tid == 0) chunk_to_global(home, S.chunk);                      // (frozen games go back unchanged)
 }
 
 // ---- 2. longest road ----------------------------------------------------------------------------
@@ -317,8 +340,9 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
 // lists through a 128-byte window per thread.  A block's latency is what bounds the kernel (a warp issues one instruction
 // every ~40 cycles), hence the many narrow parts.
 constexpr int kObsRingThreads = (CATAN_OBS_PARTS - CATAN_OBS_TILE_PARTS) * 32;   // the tile parts build their pieces in registers
-struct alignas(16) EncSmem {
+struct alignas(128) EncSmem {
   uint8_t chunk[CATAN_CHUNK_BYTES];                                 // the 32 games of this block (see chunk_to_shared)
+  uint64_t mbar;
   GameSmem topo;
   uint32_t ring[(CATAN_RING_BYTES / 4) * kObsRingThreads];          // RowWriter windows, word-interleaved over those threads
   uint32_t wbuf[CATAN_RESET_WORDS];                                 // reset: pre-drawn Philox words (warp 0)
@@ -333,12 +357,14 @@ struct alignas(16) EncSmem {
 // copies once the searches have finished (second stream, see launch_step).
 template <int MODE, bool SAMPLE, bool LISTED>
 __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_constant__ EnvParams P) {
-  extern __shared__ __align__(16) uint8_t enc_smem_raw[];
+  extern __shared__ __align__(128) uint8_t enc_smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(enc_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int list_count = LISTED ? P.lr_ctl->slow_count : 0;
   if (LISTED && static_cast<int>(blockIdx.x) * 32 >= list_count) return;
+  if (tid == 0) mbar_init(&S.mbar);
   stage_topology(S.topo, tid, kEncThreads);
+  uint32_t phase = 0;
   for (int l0 = static_cast<int>(blockIdx.x) * 32; LISTED ? l0 < list_count : l0 == static_cast<int>(blockIdx.x) * 32; l0 += static_cast<int>(gridDim.x) * 32) {
     int i;
     bool valid;
@@ -353,8 +379,9 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
     // the chunk of these 32 games (home records, or the staging copies) -> shared memory; lane b of every warp works on
     // game b of it.  What the block changes goes home explicitly: the games of the other stream must not be touched.
     uint8_t* const home = (LISTED ? P.stage : P.recs) + static_cast<size_t>((LISTED ? l0 : (P.range_first & ~31) + l0) >> 5) * CATAN_CHUNK_BYTES;
-    chunk_to_shared(S.chunk, home, tid, kEncThreads);
-    __syncthreads();
+    if (tid == 0) chunk_to_shared(S.chunk, home, &S.mbar);
+    chunk_wait(&S.mbar, phase);
+    phase ^= 1;
     const GameView hv = GameView{home, lane};
 #define CATAN_VIEW_OF(b_) GameView{S.chunk, (b_)}
     TCx cx;
