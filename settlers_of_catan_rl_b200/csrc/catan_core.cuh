@@ -230,7 +230,7 @@ CATAN_FN_NOINLINE bool number_order_ok(const Topo& T, const uint8_t* numbers, co
 // ------------------------------------------------------------------------------------------------
 #define CATAN_LP_ADJ_BYTES 432
 #define CATAN_LP_CTL_WORDS 4
-#define CATAN_LP_BURST 8
+#define CATAN_LP_BURST 4
 struct alignas(16) LpTask {
   uint64_t visited;
   uint8_t node, depth, pad_[2];
@@ -242,7 +242,7 @@ CATAN_FN int32_t vload_i32(const int32_t* p) { return *reinterpret_cast<const vo
 CATAN_FN uint32_t vload_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 CATAN_FN void vstore_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 CATAN_FN void group_fence() { __threadfence_block(); }
-CATAN_FN void group_idle() { __nanosleep(400); }
+CATAN_FN void group_idle() { __nanosleep(200); }
 #else
 CATAN_FN int32_t vload_i32(const int32_t* p) { return *p; }
 CATAN_FN uint32_t vload_u32(const uint32_t* p) { return *p; }

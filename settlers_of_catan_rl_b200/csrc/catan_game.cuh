@@ -170,12 +170,11 @@ struct TCx {
 
 enum { CATAN_LR_ROAD = 0, CATAN_LR_SETTLE = 1 };
 // what apply_action leaves for the follow-up passes of the same step
-struct StepTmp {
-  Act act;
+struct StepTmp {             // (kept small: 32 of them sit next to the staged chunk in the transition kernel's shared memory)
   EstReq est[2];
-  int16_t dice_T[4][5];      // clip bound of the (r, player) belief update of this roll
-  int16_t mono_T[4];
+  uint8_t dice_T[4][5];      // clip bound of the (r, player) belief update of this roll (a hand total)
   uint8_t alloc[5][4];       // dice payout [r][player index]      (game.py:153-167)
+  uint8_t mono_T[4];
   uint8_t mono_lost[4];
   uint8_t n_est, est_special, granted, dice_roll;
   uint8_t mono_pid, mono_res, lr_pid, err;
@@ -491,10 +490,9 @@ CATAN_FN_NOINLINE void t_update_largest_army(const GameView& g) {   // game.py:8
   }
 }
 
-CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp) {
+CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp, const Act& t) {
   const GameView& g = cx.g;
   const Topo& T = *cx.T;
-  const Act& t = tmp.act;
   const int pid = g.players_go(), p = pid - 1;
   switch (t.type) {
     case CATAN_ACT_PLACE_SETTLEMENT: {                               // game.py:530-555, :195-212
@@ -661,7 +659,7 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp) {
           g.res(p, r) = static_cast<uint8_t>(g.res(p, r) + cnt); g.vis(p, r) = static_cast<int16_t>(g.vis(p, r) + cnt);
           tmp.mono_lost[o] = static_cast<uint8_t>(cnt);
         }
-        for (int o = 0; o < 4; ++o) tmp.mono_T[o] = static_cast<int16_t>(t_hand_total(g, o + 1));
+        for (int o = 0; o < 4; ++o) tmp.mono_T[o] = static_cast<uint8_t>(t_hand_total(g, o + 1));
       } else {                                                       // Year of Plenty
         for (int i = 0; i < 2; ++i) {
           const int r = i == 0 ? t.res_a : t.res_b;
@@ -802,7 +800,7 @@ CATAN_FN void t_dice_payout_group(const GameView& g, const Topo& T, StepTmp& tmp
         const int a = tmp.alloc[r][p];
         if (a) { g.res(p, r) = static_cast<uint8_t>(g.res(p, r) + a); g.bank(r) = static_cast<uint8_t>(g.bank(r) - a); }
         tot[p] += a;
-        tmp.dice_T[p][r] = static_cast<int16_t>(tot[p]);             // owner's running total when (r, p) is re-clipped (Q4)
+        tmp.dice_T[p][r] = static_cast<uint8_t>(tot[p]);             // owner's running total when (r, p) is re-clipped (Q4)
       }
     }
     tmp.granted = granted;
@@ -890,11 +888,12 @@ CATAN_FN void t_step_scalar(TCx& cx, const int32_t* a, StepTmp& tmp) {
   tmp.s = cx.s;
   tmp.acted_pid = static_cast<uint8_t>(t_current_actor(cx.g));
   tmp.act_type = static_cast<uint8_t>(a[CATAN_A_TYPE]);
-  int err = t_translate_action(cx, a, tmp.act);
-  if (!err && cx.cfg->validate_actions) err = t_validate_action(cx, tmp.act);
+  Act act;
+  int err = t_translate_action(cx, a, act);
+  if (!err && cx.cfg->validate_actions) err = t_validate_action(cx, act);
   tmp.err = static_cast<uint8_t>(err);
   if (err) return;
-  t_apply_scalar(cx, tmp);
+  t_apply_scalar(cx, tmp, act);
   tmp.follow = tmp.dice_roll || tmp.n_est || tmp.est_special;
 }
 
@@ -1057,7 +1056,21 @@ CATAN_FN RoadBits t_load_road_bits(const GameView& g, int pid) {
   return R;
 }
 // new length of PlayerId pid's longest road, or -1 if the full enumeration is needed
-CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int kind, int loc, int placer) {
+// neighbours of corner x over pid's roads (ignoring buildings)
+CATAN_FN uint64_t t_road_nb(const Topo& T, const RoadBits& R, int x) {
+  uint64_t nb = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int e = T.corner_neigh_edge[x][k];
+    if (e < 0) continue;
+    const bool own = e < 64 ? (R.em_lo >> e) & 1ull : (R.em_hi >> (e - 64)) & 1u;
+    if (own) nb |= 1ull << T.corner_neigh[x][k];
+  }
+  return nb;
+}
+// pre (may be null): the player's RoadBits, when the caller has already gathered them (the transition kernel does, one
+// lane per corner / edge)
+CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int kind, int loc, int placer, const RoadBits* pre = nullptr) {
   const int holder = g.lr_holder();
   const int old = holder == pid ? g.lr_count() : (g.has_path_key(pid - 1) ? g.cur_longest_path(pid - 1) : 0);
   if (kind == CATAN_LR_SETTLE) {                                     // pid == holder (game.py:552-553): its length is always current
@@ -1071,25 +1084,10 @@ CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int k
   }
   if (g.lr_dirty(pid - 1)) return -1;
   if (loc == 0xff) return old;                                       // dummy edge of road building (game.py:585): nothing changed
-  const RoadBits R = t_load_road_bits(g, pid);
-  uint64_t und[54];                                                  // neighbours over pid's roads (thread-private table)
-#pragma unroll
-  for (int c = 0; c < 54; ++c) und[c] = 0ull;
-  {
-    uint64_t lo = R.em_lo;
-    uint32_t hi = R.em_hi;
-    CATAN_NO_UNROLL
-    while (lo | hi) {
-      int e;
-      if (lo) { e = ctz64(lo); lo &= lo - 1; } else { e = 64 + ctz64(hi); hi &= hi - 1; }
-      const int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
-      und[c1] |= 1ull << c2;
-      und[c2] |= 1ull << c1;
-    }
-  }
+  const RoadBits R = pre ? *pre : t_load_road_bits(g, pid);
   const int u = T.edge_corners[loc][0], v = T.edge_corners[loc][1];
   // one end had no road before: the new edge is certainly a bridge
-  const bool leaf = !(und[u] & ~(1ull << v)) || !(und[v] & ~(1ull << u));
+  const bool leaf = !(t_road_nb(T, R, u) & ~(1ull << v)) || !(t_road_nb(T, R, v) & ~(1ull << u));
   // four searches in ONE loop (the lanes of a warp are in different searches of different games): into u, out of v, into
   // v, out of u; arcs out of a corner blocked by an opponent's building do not exist
   int through = 0, iters = CATAN_LR_FAST_ITERS, phase = 0, acc = 0;
@@ -1110,7 +1108,7 @@ CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int k
     }
     if (--iters < 0) return -1;
     const bool fwd = phase & 1;
-    uint64_t nb = und[node];
+    uint64_t nb = t_road_nb(T, R, node);
     nb = fwd ? (((R.blk >> node) & 1ull) ? 0ull : nb) : (nb & ~R.blk);
     const uint64_t cand = nb & ~visited & above;
     if (cand) {

@@ -47,8 +47,8 @@ constexpr int kTransThreads = kTransWarps * 32;
 constexpr int kEncWarps = 1 + CATAN_OBS_PARTS;   // encode_kernel: finish/masks/sampler warp + one warp per piece of the obs row
 constexpr int kEncThreads = kEncWarps * 32;
 constexpr int kCopyThreads = 128;           // lr_copy_back_kernel: one warp per game
-constexpr int kLrSlowThreads = 1024;        // lr_slow_kernel: one block per update that needs a search
-constexpr int kLrSlowBlocksPerSM = 1;
+constexpr int kLrSlowThreads = 512;         // lr_slow_kernel: one block per update that needs a search
+constexpr int kLrSlowBlocksPerSM = 2;
 constexpr int kSampleThreads = 128;         // stand-alone sampler kernel
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
@@ -156,10 +156,10 @@ __global__ void __launch_bounds__(kCopyThreads) lr_copy_back_kernel(const __grid
 // One block per chunk of 32 games.  Warp 0 runs the scalar part of apply_action, one game per lane; the data-parallel
 // follow-ups it posts (dice payout over 19 tiles x 6 corners, belief updates over 60 entries) are then executed by all
 // warps of the block, one warp per game and one lane per item.
-struct alignas(128) TransSmem {
+struct alignas(128) TransSmem {      // <= 31.4 KB so that 7 blocks fit an SM: 2048 chunks are then two waves instead of three
   uint8_t chunk[CATAN_CHUNK_BYTES];
   uint64_t mbar;
-  GameSmem topo;
+  alignas(16) Topo topo;
   StepTmp tmp[32];
   int32_t n_follow;
   int32_t slot[32];          // staging slot of a game that goes to lr_slow_kernel, else -1
@@ -181,12 +181,17 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   }
   __syncthreads();
   if (tid == 0) chunk_to_shared(S.chunk, home, &S.mbar);
-  stage_topology(S.topo, tid, kTransThreads);
+  {
+    const int4* src = reinterpret_cast<const int4*>(&d_topo);
+    int4* dst = reinterpret_cast<int4*>(&S.topo);
+    for (int k = tid; k < static_cast<int>(sizeof(Topo) / 16); k += kTransThreads) dst[k] = src[k];
+  }
+  __syncthreads();
   chunk_wait(&S.mbar, 0);
   const int i = base + lane;
   TCx cx;
   cx.g.base = S.chunk; cx.g.lane = lane;
-  cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
+  cx.T = &S.topo; cx.X = nullptr; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);   // (X: masks only)
   bool lr = false;
   if (warp == 0) {
     const bool valid = i >= P.range_first && i < P.range_first + P.range_count && !(P.env_mask != nullptr && P.env_mask[i] == 0);
@@ -210,9 +215,22 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     // game that needs a search goes to the queue of lr_slow_kernel.  (Independent of the follow-ups: those touch hands,
     // bank and beliefs only.)
     const StepTmp& tmp = S.tmp[lane];
+    const unsigned lb = __ballot_sync(0xffffffffu, lr);
+    // the road / blocked-corner bit sets of every game with an update: one lane per corner / edge
+    RoadBits rb = {0ull, 0ull, 0u};
+    for (unsigned mm = lb; mm; mm &= mm - 1) {
+      const int b = __ffs(static_cast<int>(mm)) - 1;
+      const uint32_t pid = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp.lr_pid), b);
+      const GameView gb = GameView{S.chunk, b};
+      const uint32_t c0 = gb.corner(lane), c1 = lane + 32 < 54 ? gb.corner(lane + 32) : 0u;
+      const uint32_t k0 = __ballot_sync(0xffffffffu, c0 != 0 && (c0 >> 2) != pid), k1 = __ballot_sync(0xffffffffu, c1 != 0 && (c1 >> 2) != pid);
+      const uint32_t e0 = __ballot_sync(0xffffffffu, gb.edge(lane) == pid), e1 = __ballot_sync(0xffffffffu, gb.edge(lane + 32) == pid);
+      const uint32_t e2 = __ballot_sync(0xffffffffu, lane + 64 < 72 && gb.edge(lane + 64 < 72 ? lane + 64 : 0) == pid);
+      if (lane == b) { rb.blk = k0 | (static_cast<uint64_t>(k1) << 32); rb.em_lo = e0 | (static_cast<uint64_t>(e1) << 32); rb.em_hi = e2; }
+    }
     bool slow = false;
     if (lr) {
-      const int len = t_lr_fast(cx.g, S.topo.topo, tmp.lr_pid, tmp.lr_kind, tmp.lr_loc, tmp.acted_pid);
+      const int len = t_lr_fast(cx.g, S.topo, tmp.lr_pid, tmp.lr_kind, tmp.lr_loc, tmp.acted_pid, &rb);
       if (len >= 0) t_lr_apply(cx.g, tmp.lr_pid, len, false, nullptr);
       else slow = true;
     }
@@ -222,7 +240,6 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
                               (static_cast<uint64_t>(tmp.lr_kind) << 48) | (static_cast<uint64_t>(tmp.acted_pid) << 56);
       S.slot[lane] = slot;
     }
-    const unsigned lb = __ballot_sync(0xffffffffu, lr);
     if (lane == 0 && lb) atomicAdd(&P.lr_ctl->count, __popc(lb));
     if (i >= P.range_first && i < P.range_first + P.range_count && !(P.env_mask != nullptr && P.env_mask[i] == 0))
       P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
@@ -232,7 +249,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     for (int j = warp - 1; j < nf; j += kTransWarps - 1) {
       GameView g;
       g.base = S.chunk; g.lane = S.follow_list[j];
-      t_followups_group(g, S.topo.topo, S.tmp[g.lane], lane, 32);
+      t_followups_group(g, S.topo, S.tmp[g.lane], lane, 32);
     }
   }
   chunk_written();
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
 // reference's full enumeration visits 205 corners on average and 29 k at most.  96 % of the new roads are bridges of the
 // player's road graph, where the incremental rule of t_lr_fast() (inside transition_kernel) is exact with two walks of
 // ~10 visits; 166 updates per step (65 536 games) come here: one BLOCK per update, see lp_pool in catan_core.cuh.
-constexpr int kLrRing = 8192;               // task ring of the pool (shared memory; a power of two >= 4 x lanes + 64)
+constexpr int kLrRing = 2048;               // task ring of the pool (shared memory; a power of two >= 4 x lanes + 64)
 struct alignas(16) LrSmem {
   Topo topo;
   uint64_t adj[54], adjb[54];
@@ -685,6 +702,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
     if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_RESET, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_REFRESH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
   }
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::transition_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::lr_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::LrSmem)));
   if (e != cudaSuccess) {
     free_env(env);
