@@ -17,7 +17,7 @@
 //                        shared by all ten warps, one warp per game that needs one.  Queued games are left out.
 //
 //   library's high-priority stream (forked after the transition, joined at the end of the step)
-//   lr_slow_kernel       one 1024-thread block per queued update: the paths through the new road -- or, when the stored
+//   lr_slow_kernel       one 512-thread block per queued update: the paths through the new road -- or, when the stored
 //                        length cannot be trusted, the reference's full enumeration (game.py:843-862) -- as a pool of
 //                        16-byte subtree tasks that the lanes drain and re-split without barriers (lp_pool).
 //   encode_kernel<LISTED> the same encode for the queued games, on their staging chunks
@@ -274,7 +274,7 @@ struct alignas(16) LrSmem {
   uint8_t paths[54 * kLrSlowThreads];
   int32_t best[4];
   int32_t ctl[CATAN_LP_CTL_WORDS];
-  int32_t rounds, tasks;     // diagnostics: walk steps and tasks of the current update
+  int32_t steps, tasks;      // diagnostics: walk steps and tasks of the current update
 };
 
 __device__ __forceinline__ int block_longest_path(LrSmem& S, const GameView& g, int pid, int tid) {
@@ -282,7 +282,7 @@ __device__ __forceinline__ int block_longest_path(LrSmem& S, const GameView& g, 
   if (tid == 0) S.best[0] = 0;
   __syncthreads();
   CATAN_LP_RUN(S.adj, S.adj, -1, -1, S.ctl, S.best, S.paths, kLrSlowThreads, tid, S.ring, kLrRing, tid == 0, __syncthreads());
-  if (tid == 0) { S.rounds += S.ctl[3]; S.tasks += S.ctl[1]; }
+  if (tid == 0) { S.steps += S.ctl[3]; S.tasks += S.ctl[1]; }
   const int r = S.best[0];
   __syncthreads();
   return r;
@@ -298,7 +298,7 @@ __device__ __forceinline__ int block_through_edge(LrSmem& S, const GameView& g, 
     if (tid == 0) S.best[0] = 0;
     __syncthreads();
     CATAN_LP_RUN(S.adj, S.adjb, b, a, S.ctl, S.best, S.paths, kLrSlowThreads, tid, S.ring, kLrRing, tid == 0, __syncthreads());
-    if (tid == 0) { S.rounds += S.ctl[3]; S.tasks += S.ctl[1]; }
+    if (tid == 0) { S.steps += S.ctl[3]; S.tasks += S.ctl[1]; }
     through = max(through, S.best[0]);
     __syncthreads();
   }
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
     const int pid = static_cast<int>((en >> 32) & 0xff), loc = static_cast<int>((en >> 40) & 0xff), kind = static_cast<int>((en >> 48) & 0xff);
     const long long t_start = clock64();
     bool was_full = true;
-    if (tid == 0) { S.rounds = 0; S.tasks = 0; }
+    if (tid == 0) { S.steps = 0; S.tasks = 0; }
     if (kind == CATAN_LR_ROAD && loc != 0xff && !g.lr_dirty(pid - 1)) {
       was_full = false;
       // the stored length is exact: only the paths through the new road can beat it
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
     if (tid == 0) {
       const unsigned long long dt = static_cast<unsigned long long>(clock64() - t_start);
       atomicAdd(&P.lr_ctl->dbg[0], dt); atomicMax(&P.lr_ctl->dbg[1], dt);
-      atomicAdd(&P.lr_ctl->dbg[2], static_cast<unsigned long long>(S.rounds)); atomicMax(&P.lr_ctl->dbg[3], static_cast<unsigned long long>(S.rounds));
+      atomicAdd(&P.lr_ctl->dbg[2], static_cast<unsigned long long>(S.steps)); atomicMax(&P.lr_ctl->dbg[3], static_cast<unsigned long long>(S.steps));
       if (was_full) atomicAdd(&P.lr_ctl->dbg[4], 1ull);
       atomicAdd(&P.lr_ctl->dbg[5], static_cast<unsigned long long>(S.tasks));
     }
