@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int base = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32;
   uint8_t* const home = P.recs + static_cast<size_t>(base >> 5) * CATAN_CHUNK_BYTES;
-  if (tid == 0) mbar_init(&S.mbar);
+  if (tid == 0) { mbar_init(&S.mbar); chunk_to_shared(S.chunk, home, &S.mbar); }   // in flight while the topology is staged
   if (blockIdx.x == 0 && tid == 0) {                                 // the other queue buffer belongs to the step before: bank its counts, clear it
     LrCtl& o = *P.lr_ctl_next;
     P.lr_ctl->total = o.total + static_cast<unsigned long long>(o.count); P.lr_ctl->slow_total = o.slow_total + static_cast<unsigned long long>(o.slow_count);
@@ -179,8 +179,6 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     o.count = 0; o.slow_count = 0; o.total = 0; o.slow_total = 0;
     for (int k = 0; k < 6; ++k) o.dbg[k] = 0;
   }
-  __syncthreads();
-  if (tid == 0) chunk_to_shared(S.chunk, home, &S.mbar);
   {
     const int4* src = reinterpret_cast<const int4*>(&d_topo);
     int4* dst = reinterpret_cast<int4*>(&S.topo);
@@ -379,7 +377,11 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int list_count = LISTED ? P.lr_ctl->slow_count : 0;
   if (LISTED && static_cast<int>(blockIdx.x) * 32 >= list_count) return;
-  if (tid == 0) mbar_init(&S.mbar);
+#define CATAN_ENC_HOME(l0_) ((LISTED ? P.stage : P.recs) + static_cast<size_t>((LISTED ? (l0_) : (P.range_first & ~31) + (l0_)) >> 5) * CATAN_CHUNK_BYTES)
+  if (tid == 0) {                                                    // the first chunk is on its way while the topology is staged
+    mbar_init(&S.mbar);
+    chunk_to_shared(S.chunk, CATAN_ENC_HOME(static_cast<int>(blockIdx.x) * 32), &S.mbar);
+  }
   stage_topology(S.topo, tid, kEncThreads);
   uint32_t phase = 0;
   for (int l0 = static_cast<int>(blockIdx.x) * 32; LISTED ? l0 < list_count : l0 == static_cast<int>(blockIdx.x) * 32; l0 += static_cast<int>(gridDim.x) * 32) {
@@ -395,8 +397,8 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
     }
     // the chunk of these 32 games (home records, or the staging copies) -> shared memory; lane b of every warp works on
     // game b of it.  What the block changes goes home explicitly: the games of the other stream must not be touched.
-    uint8_t* const home = (LISTED ? P.stage : P.recs) + static_cast<size_t>((LISTED ? l0 : (P.range_first & ~31) + l0) >> 5) * CATAN_CHUNK_BYTES;
-    if (tid == 0) chunk_to_shared(S.chunk, home, &S.mbar);
+    uint8_t* const home = CATAN_ENC_HOME(l0);
+    if (tid == 0 && l0 != static_cast<int>(blockIdx.x) * 32) chunk_to_shared(S.chunk, home, &S.mbar);
     chunk_wait(&S.mbar, phase);
     phase ^= 1;
     const GameView hv = GameView{home, lane};
@@ -486,6 +488,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
     if (LISTED) __syncthreads();                                     // warp 0's reset scratch is reused by the next 32 games
 #undef CATAN_VIEW_OF
   }
+#undef CATAN_ENC_HOME
 }
 
 // stand-alone sampler: one thread per env, reads the bound mask / obs rows back from global memory
