@@ -42,7 +42,8 @@ namespace catanb {
 __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 
 // ---- launch shapes ------------------------------------------------------------------------------
-constexpr int kTransWarps = 4;              // transition_kernel: warps per chunk of 32 games
+constexpr int kTransWarps = 4;              // transition_kernel: warps per chunk of 32 games ...
+constexpr int kRuleWarps = 1;               // ... of which this many run the rules; the others the follow-ups (2 x 16 games measured: +5 % time)
 constexpr int kTransThreads = kTransWarps * 32;
 constexpr int kEncWarps = 1 + CATAN_OBS_PARTS;   // encode_kernel: finish/masks/sampler warp + one warp per piece of the obs row
 constexpr int kEncThreads = kEncWarps * 32;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int base = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32;
   uint8_t* const home = P.recs + static_cast<size_t>(base >> 5) * CATAN_CHUNK_BYTES;
-  if (tid == 0) { mbar_init(&S.mbar); chunk_to_shared(S.chunk, home, &S.mbar); }   // in flight while the topology is staged
+  if (tid == 0) { mbar_init(&S.mbar); chunk_to_shared(S.chunk, home, &S.mbar); S.n_follow = 0; }   // in flight while the topology is staged
   if (blockIdx.x == 0 && tid == 0) {                                 // the other queue buffer belongs to the step before: bank its counts, clear it
     LrCtl& o = *P.lr_ctl_next;
     P.lr_ctl->total = o.total + static_cast<unsigned long long>(o.count); P.lr_ctl->slow_total = o.slow_total + static_cast<unsigned long long>(o.slow_count);
@@ -186,40 +187,47 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   }
   __syncthreads();
   chunk_wait(&S.mbar, 0);
-  const int i = base + lane;
+  // kRuleWarps warps share the 32 games (game gl = warp * 32 / kRuleWarps + lane, lanes above that idle): the rule code is
+  // one big switch over 13 action types, and a warp pays for every type that occurs among ITS games
+  constexpr int kPerWarp = 32 / kRuleWarps;
+  const int gl = warp * kPerWarp + (lane & (kPerWarp - 1));          // game of this thread inside the chunk (rule warps)
+  const int i = base + gl;
+  const bool mine = warp < kRuleWarps && lane < kPerWarp && i >= P.range_first && i < P.range_first + P.range_count &&
+                    !(P.env_mask != nullptr && P.env_mask[i] == 0);
   TCx cx;
-  cx.g.base = S.chunk; cx.g.lane = lane;
+  cx.g.base = S.chunk; cx.g.lane = gl;
   cx.T = &S.topo; cx.X = nullptr; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);   // (X: masks only)
   bool lr = false;
-  if (warp == 0) {
-    const bool valid = i >= P.range_first && i < P.range_first + P.range_count && !(P.env_mask != nullptr && P.env_mask[i] == 0);
+  if (warp < kRuleWarps) {
     bool follow = false;
-    if (valid) {
+    if (mine) {
       cx.s = load_seats(cx.g);
-      StepTmp& tmp = S.tmp[lane];
+      StepTmp& tmp = S.tmp[gl];
       t_step_scalar(cx, P.actions + static_cast<size_t>(i) * CATAN_ACTION_WORDS, tmp);
       if (tmp.err) P.err_flags[i] |= 1u << tmp.err;
       lr = !tmp.err && tmp.lr_pid;
       follow = tmp.follow != 0;
     }
     const unsigned fb = __ballot_sync(0xffffffffu, follow);
-    if (follow) S.follow_list[__popc(fb & ((1u << lane) - 1u))] = static_cast<uint8_t>(lane);
-    if (lane == 0) S.n_follow = __popc(fb);
-    S.slot[lane] = -1;
+    int pos = 0;
+    if (lane == 0 && fb) pos = atomicAdd(&S.n_follow, __popc(fb));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (follow) S.follow_list[pos + __popc(fb & ((1u << lane) - 1u))] = static_cast<uint8_t>(gl);
+    if (lane < kPerWarp) S.slot[gl] = -1;
   }
   __syncthreads();
-  if (warp == 0) {
+  if (warp < kRuleWarps) {
     // longest road (game.py:843-919), one thread per update: the incremental rule settles ~93 % of them on the spot; a
     // game that needs a search goes to the queue of lr_slow_kernel.  (Independent of the follow-ups: those touch hands,
     // bank and beliefs only.)
-    const StepTmp& tmp = S.tmp[lane];
+    const StepTmp& tmp = S.tmp[gl];
     const unsigned lb = __ballot_sync(0xffffffffu, lr);
     // the road / blocked-corner bit sets of every game with an update: one lane per corner / edge
     RoadBits rb = {0ull, 0ull, 0u};
     for (unsigned mm = lb; mm; mm &= mm - 1) {
       const int b = __ffs(static_cast<int>(mm)) - 1;
       const uint32_t pid = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp.lr_pid), b);
-      const GameView gb = GameView{S.chunk, b};
+      const GameView gb = GameView{S.chunk, warp * kPerWarp + b};
       const uint32_t c0 = gb.corner(lane), c1 = lane + 32 < 54 ? gb.corner(lane + 32) : 0u;
       const uint32_t k0 = __ballot_sync(0xffffffffu, c0 != 0 && (c0 >> 2) != pid), k1 = __ballot_sync(0xffffffffu, c1 != 0 && (c1 >> 2) != pid);
       const uint32_t e0 = __ballot_sync(0xffffffffu, gb.edge(lane) == pid), e1 = __ballot_sync(0xffffffffu, gb.edge(lane + 32) == pid);
@@ -236,15 +244,15 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
       const int slot = atomicAdd(&P.lr_ctl->slow_count, 1);
       P.lr_slow_queue[slot] = static_cast<uint64_t>(static_cast<uint32_t>(i)) | (static_cast<uint64_t>(tmp.lr_pid) << 32) | (static_cast<uint64_t>(tmp.lr_loc) << 40) |
                               (static_cast<uint64_t>(tmp.lr_kind) << 48) | (static_cast<uint64_t>(tmp.acted_pid) << 56);
-      S.slot[lane] = slot;
+      S.slot[gl] = slot;
     }
     if (lane == 0 && lb) atomicAdd(&P.lr_ctl->count, __popc(lb));
-    if (i >= P.range_first && i < P.range_first + P.range_count && !(P.env_mask != nullptr && P.env_mask[i] == 0))
+    if (mine)
       P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
                   (static_cast<uint32_t>(tmp.roll_info) << 24) | (slow ? 0x80000000u : 0u);
   } else {
     const int nf = S.n_follow;
-    for (int j = warp - 1; j < nf; j += kTransWarps - 1) {
+    for (int j = warp - kRuleWarps; j < nf; j += kTransWarps - kRuleWarps) {
       GameView g;
       g.base = S.chunk; g.lane = S.follow_list[j];
       t_followups_group(g, S.topo, S.tmp[g.lane], lane, 32);
