@@ -838,8 +838,8 @@ CATAN_FN void t_est_generic_group(const GameView& g, Seats s, const EstReq& rq, 
 }
 
 // one item = (observer o, label l, resource r)
-CATAN_FN void t_est_special_group(const GameView& g, Seats s, const StepTmp& tmp, int lane, int nl) {
-  if (tmp.est_special == EST_SPECIAL_DICE) {
+CATAN_FN void t_est_special_group(const GameView& g, Seats s, const StepTmp& tmp, int special, int lane, int nl) {
+  if (special == EST_SPECIAL_DICE) {
     for (int it = lane; it < 60; it += nl) {
       const int ol = it / 5, r = it - 5 * ol, o = ol / 3, l = ol - 3 * o;
       if (!((tmp.granted >> r) & 1)) continue;
@@ -848,7 +848,7 @@ CATAN_FN void t_est_special_group(const GameView& g, Seats s, const StepTmp& tmp
       g.est_max(o, l, r) = static_cast<int16_t>(clipi(g.est_max(o, l, r) + gain, 0, T));
       g.est_min(o, l, r) = static_cast<int16_t>(clipi(g.est_min(o, l, r) + gain, 0, T));
     }
-  } else if (tmp.est_special == EST_SPECIAL_MONOPOLY) {
+  } else if (special == EST_SPECIAL_MONOPOLY) {
     const int tot = tmp.mono_lost[0] + tmp.mono_lost[1] + tmp.mono_lost[2] + tmp.mono_lost[3];
     const int mr = tmp.mono_res;
     for (int it = lane; it < 60; it += nl) {
@@ -869,12 +869,13 @@ CATAN_FN void t_est_special_group(const GameView& g, Seats s, const StepTmp& tmp
 }
 
 CATAN_FN_NOINLINE void t_followups_group(const GameView& g, const Topo& T, StepTmp& tmp, int lane, int nl) {
-  if (tmp.dice_roll) { t_dice_payout_group(g, T, tmp, lane, nl); tmp.est_special = EST_SPECIAL_DICE; }
+  const int special = tmp.dice_roll ? EST_SPECIAL_DICE : tmp.est_special;   // (nobody writes tmp's flags here: the lanes only read them)
+  if (tmp.dice_roll) t_dice_payout_group(g, T, tmp, lane, nl);
   for (int qi = 0; qi < tmp.n_est; ++qi) {
     t_est_generic_group(g, tmp.s, tmp.est[qi], lane, nl);
     CATAN_GROUP_SYNC();
   }
-  if (tmp.est_special) t_est_special_group(g, tmp.s, tmp, lane, nl);
+  if (special) t_est_special_group(g, tmp.s, tmp, special, lane, nl);
   CATAN_GROUP_SYNC();
 }
 
