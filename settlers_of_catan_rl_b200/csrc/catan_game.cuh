@@ -1070,8 +1070,9 @@ CATAN_FN uint64_t t_road_nb(const Topo& T, const RoadBits& R, int x) {
   return nb;
 }
 // pre (may be null): the player's RoadBits, when the caller has already gathered them (the transition kernel does, one
-// lane per corner / edge)
-CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int kind, int loc, int placer, const RoadBits* pre = nullptr) {
+// lane per corner / edge); und (may be null): likewise the table of t_road_nb() for all 54 corners
+CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int kind, int loc, int placer, const RoadBits* pre = nullptr,
+                                const uint64_t* und = nullptr) {
   const int holder = g.lr_holder();
   const int old = holder == pid ? g.lr_count() : (g.has_path_key(pid - 1) ? g.cur_longest_path(pid - 1) : 0);
   if (kind == CATAN_LR_SETTLE) {                                     // pid == holder (game.py:552-553): its length is always current
@@ -1088,7 +1089,7 @@ CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int k
   const RoadBits R = pre ? *pre : t_load_road_bits(g, pid);
   const int u = T.edge_corners[loc][0], v = T.edge_corners[loc][1];
   // one end had no road before: the new edge is certainly a bridge
-  const bool leaf = !(t_road_nb(T, R, u) & ~(1ull << v)) || !(t_road_nb(T, R, v) & ~(1ull << u));
+  const bool leaf = !((und ? und[u] : t_road_nb(T, R, u)) & ~(1ull << v)) || !((und ? und[v] : t_road_nb(T, R, v)) & ~(1ull << u));
   // four searches in ONE loop (the lanes of a warp are in different searches of different games): into u, out of v, into
   // v, out of u; arcs out of a corner blocked by an opponent's building do not exist
   int through = 0, iters = CATAN_LR_FAST_ITERS, phase = 0, acc = 0;
@@ -1109,7 +1110,7 @@ CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int k
     }
     if (--iters < 0) return -1;
     const bool fwd = phase & 1;
-    uint64_t nb = t_road_nb(T, R, node);
+    uint64_t nb = und ? und[node] : t_road_nb(T, R, node);
     nb = fwd ? (((R.blk >> node) & 1ull) ? 0ull : nb) : (nb & ~R.blk);
     const uint64_t cand = nb & ~visited & above;
     if (cand) {

@@ -43,6 +43,7 @@ __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 
 // ---- launch shapes ------------------------------------------------------------------------------
 constexpr int kTransWarps = 4;              // transition_kernel: warps per chunk of 32 games ...
+constexpr int kLrBatch = 2;                 // incremental longest road: games walked at a time per rule warp
 constexpr int kRuleWarps = 1;               // ... of which this many run the rules; the others the follow-ups (2 x 16 games measured: +5 % time)
 constexpr int kTransThreads = kTransWarps * 32;
 constexpr int kEncWarps = 1 + CATAN_OBS_PARTS;   // encode_kernel: finish/masks/sampler warp + one warp per piece of the obs row
@@ -164,6 +165,7 @@ struct alignas(128) TransSmem {      // <= 31.4 KB so that 7 blocks fit an SM: 2
   StepTmp tmp[32];
   int32_t n_follow;
   int32_t slot[32];          // staging slot of a game that goes to lr_slow_kernel, else -1
+  uint64_t und[kLrBatch][54];   // incremental longest road: neighbour tables of the games being walked
   uint8_t follow_list[32];
 };
 
@@ -222,23 +224,35 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     // bank and beliefs only.)
     const StepTmp& tmp = S.tmp[gl];
     const unsigned lb = __ballot_sync(0xffffffffu, lr);
-    // the road / blocked-corner bit sets of every game with an update: one lane per corner / edge
-    RoadBits rb = {0ull, 0ull, 0u};
-    for (unsigned mm = lb; mm; mm &= mm - 1) {
-      const int b = __ffs(static_cast<int>(mm)) - 1;
-      const uint32_t pid = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp.lr_pid), b);
-      const GameView gb = GameView{S.chunk, warp * kPerWarp + b};
-      const uint32_t c0 = gb.corner(lane), c1 = lane + 32 < 54 ? gb.corner(lane + 32) : 0u;
-      const uint32_t k0 = __ballot_sync(0xffffffffu, c0 != 0 && (c0 >> 2) != pid), k1 = __ballot_sync(0xffffffffu, c1 != 0 && (c1 >> 2) != pid);
-      const uint32_t e0 = __ballot_sync(0xffffffffu, gb.edge(lane) == pid), e1 = __ballot_sync(0xffffffffu, gb.edge(lane + 32) == pid);
-      const uint32_t e2 = __ballot_sync(0xffffffffu, lane + 64 < 72 && gb.edge(lane + 64 < 72 ? lane + 64 : 0) == pid);
-      if (lane == b) { rb.blk = k0 | (static_cast<uint64_t>(k1) << 32); rb.em_lo = e0 | (static_cast<uint64_t>(e1) << 32); rb.em_hi = e2; }
-    }
+    // Two games at a time: the warp gathers the road / blocked-corner bit sets (one lane per corner / edge) and the
+    // neighbour table of the player's road graph (one lane per corner) into shared memory, then the two owning lanes walk.
     bool slow = false;
-    if (lr) {
-      const int len = t_lr_fast(cx.g, S.topo, tmp.lr_pid, tmp.lr_kind, tmp.lr_loc, tmp.acted_pid, &rb);
-      if (len >= 0) t_lr_apply(cx.g, tmp.lr_pid, len, false, nullptr);
-      else slow = true;
+    for (unsigned mm = lb; mm;) {
+      int mine_k = -1;
+      RoadBits rb = {0ull, 0ull, 0u};
+#pragma unroll
+      for (int k = 0; k < kLrBatch; ++k) {
+        if (!mm) break;
+        const int b = __ffs(static_cast<int>(mm)) - 1;
+        mm &= mm - 1;
+        const uint32_t pid = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp.lr_pid), b);
+        const GameView gb = GameView{S.chunk, warp * kPerWarp + b};
+        const uint32_t c0 = gb.corner(lane), c1 = lane + 32 < 54 ? gb.corner(lane + 32) : 0u;
+        const uint32_t k0 = __ballot_sync(0xffffffffu, c0 != 0 && (c0 >> 2) != pid), k1 = __ballot_sync(0xffffffffu, c1 != 0 && (c1 >> 2) != pid);
+        const uint32_t e0 = __ballot_sync(0xffffffffu, gb.edge(lane) == pid), e1 = __ballot_sync(0xffffffffu, gb.edge(lane + 32) == pid);
+        const uint32_t e2 = __ballot_sync(0xffffffffu, lane + 64 < 72 && gb.edge(lane + 64 < 72 ? lane + 64 : 0) == pid);
+        const RoadBits r = {e0 | (static_cast<uint64_t>(e1) << 32), k0 | (static_cast<uint64_t>(k1) << 32), e2};
+        S.und[k][lane] = t_road_nb(S.topo, r, lane);
+        if (lane + 32 < 54) S.und[k][lane + 32] = t_road_nb(S.topo, r, lane + 32);
+        if (lane == b) { rb = r; mine_k = k; }
+      }
+      __syncwarp();
+      if (mine_k >= 0) {
+        const int len = t_lr_fast(cx.g, S.topo, tmp.lr_pid, tmp.lr_kind, tmp.lr_loc, tmp.acted_pid, &rb, S.und[mine_k]);
+        if (len >= 0) t_lr_apply(cx.g, tmp.lr_pid, len, false, nullptr);
+        else slow = true;
+      }
+      __syncwarp();
     }
     if (slow) {
       const int slot = atomicAdd(&P.lr_ctl->slow_count, 1);
