@@ -46,3 +46,25 @@ def test_views_match_reference_keys_shapes_and_values():
     # the frozen envs still show their reset situation
     st = v.export_state()
     assert st[1, L.STATE_DTYPE.fields["turn"][1] // 2] == 0
+
+
+def test_step_timing_hooks():
+    """catan_set_timing / catan_read_timing: device time of the two kernels on the caller's stream, and that timing does
+    not change what a step computes"""
+    import numpy as np
+    from settlers_of_catan_rl_b200 import VecCatanEnv
+    a = VecCatanEnv(2048, seed=2)
+    b = VecCatanEnv(2048, seed=2)
+    for v in (a, b):
+        v.reset()
+    acts_a, acts_b = a.sample_random(), b.sample_random()
+    a.set_timing(True)
+    for _ in range(100):                      # more than the ring of 32 timed steps
+        a.step_sample(acts_a)
+        b.step_sample(acts_b)
+    n, t_ms, e_ms = a.read_timing()
+    a.set_timing(False)
+    assert n == 100 and 0.0 < t_ms < 5.0 and 0.0 < e_ms < 5.0
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.masks, b.masks)
+    assert np.array_equal(a.export_state(), b.export_state())
+    assert a.read_timing()[0] == 0
