@@ -551,6 +551,7 @@ struct catan_env {
   uint8_t* recs = nullptr;            // ceil(n / 32) lane-interleaved chunks
   uint8_t* stage = nullptr;           // staging chunks of the games with a pending longest-road update
   size_t rec_bytes = 0;
+  size_t window_bytes = 0;            // L2 access-policy window on the records (0: not available)
   uint32_t* err_flags = nullptr;
   uint32_t* side = nullptr;
   uint64_t* lr_slow_queue = nullptr;
@@ -591,12 +592,34 @@ static int game_blocks(int first, int count) {   // chunks of 32 games touched b
   return ((first + count - 1) >> 5) - (first >> 5) + 1;
 }
 
+// With CATAN_L2_WINDOW set in the environment the two big kernels are launched with an L2 access-policy window on the game
+// records (persisting on hit, streaming on miss): the 54 MB of records then survive in the 126 MB L2 from the transition to
+// the encode and to the next step, while the 150 MB of observation / mask rows written per step stream through
+// (st.global.cs).  Measured: -1 % step time; off by default because the persisting set-aside is taken from every other
+// user of the device's L2 (the policy network).
+template <class Kernel>
+static cudaError_t launch_with_record_window(const catan_env* env, Kernel kernel, int blocks, int threads, size_t smem, cudaStream_t stream,
+                                             const EnvParams& P) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(blocks)); cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+  attr[0].val.accessPolicyWindow.base_ptr = env->recs;
+  attr[0].val.accessPolicyWindow.num_bytes = env->window_bytes;
+  attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+  attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cfg.attrs = attr; cfg.numAttrs = env->window_bytes ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, P);
+}
+
 template <int MODE, bool SAMPLE>
 static int launch_encode(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
   P.range_first = first; P.range_count = count;
   if (count <= 0) return 0;
-  catanb::encode_kernel<MODE, SAMPLE, false><<<game_blocks(first, count), catanb::kEncThreads, sizeof(catanb::EncSmem), stream>>>(P);
-  CATAN_CUDA(cudaGetLastError());
+  CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<MODE, SAMPLE, false>, game_blocks(first, count), catanb::kEncThreads,
+                                       sizeof(catanb::EncSmem), stream, P));
   return 0;
 }
 
@@ -623,8 +646,7 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
     env->timed += 1;
     CATAN_CUDA(cudaEventRecord(tev[0], stream));
   }
-  catanb::transition_kernel<<<game_blocks(0, env->n), catanb::kTransThreads, 0, stream>>>(P);
-  CATAN_CUDA(cudaGetLastError());
+  CATAN_CUDA(launch_with_record_window(env, catanb::transition_kernel, game_blocks(0, env->n), catanb::kTransThreads, 0, stream, P));
   if (tev) CATAN_CUDA(cudaEventRecord(tev[1], stream));
   env->ticks += 1;
   CATAN_CUDA(cudaEventRecord(env->ev_fork, stream));
@@ -696,7 +718,14 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   cudaDeviceProp prop{};
   CATAN_CUDA(cudaGetDeviceProperties(&prop, device));
   env->sm_count = prop.multiProcessorCount;
-  env->lr_grid = env->sm_count * catanb::kLrSlowBlocksPerSM;   // search blocks stride over the queue; idle blocks exit at once
+  env->lr_grid = env->sm_count * catanb::kLrSlowBlocksPerSM;
+  if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0 && getenv("CATAN_L2_WINDOW")) {   // opt-in: the set-aside is device-wide
+    const size_t rec = CATAN_CHUNK_BYTES * ((static_cast<size_t>(n_envs) + 31) / 32);
+    const size_t keep = rec < static_cast<size_t>(prop.persistingL2CacheMaxSize) ? rec : static_cast<size_t>(prop.persistingL2CacheMaxSize);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, keep) == cudaSuccess)
+      env->window_bytes = rec < static_cast<size_t>(prop.accessPolicyMaxWindowSize) ? rec : static_cast<size_t>(prop.accessPolicyMaxWindowSize);
+    else cudaGetLastError();
+  }   // search blocks stride over the queue; idle blocks exit at once
   env->rec_bytes = CATAN_CHUNK_BYTES * ((static_cast<size_t>(n_envs) + 31) / 32);
   const size_t n = static_cast<size_t>(n_envs);
   e = cudaMalloc(&env->recs, env->rec_bytes);
