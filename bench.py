@@ -291,6 +291,28 @@ def run_b200_arm(args):
         elems = T * N
         aux = {"gae_T200_N131072": {"ms": gae_ms, "GB/s": elems * 20 / gae_ms / 1e6, "bytes_per_elem": 20},
                "adv_norm_T200_N131072": {"ms": norm_ms, "GB/s": elems * 12 / norm_ms / 1e6, "bytes_per_elem": 12}}
+        del r, val, m, ret, adv
+        # minibatch gather (process_batch.py:169-200) on a rollout buffer that is larger than L2: T=16, N=16384 (0.6 GB)
+        from settlers_of_catan_rl_b200 import RolloutStorage
+        Tg, Ng = 16, 16384
+        genv = VecCatanEnv(Ng, device=dev, seed=args.seed)
+        st = RolloutStorage(genv, Tg)
+        gv = torch.rand(Tg + 1, Ng, device=dev)
+        gr, ga = torch.rand(Tg, Ng, device=dev), torch.rand(Tg, Ng, device=dev)
+        perm = torch.randperm(Tg * Ng, device=dev).to(torch.int32)
+        out = st.gather(perm, gv, gr, ga)
+        for _ in range(3):
+            st.gather(perm, gv, gr, ga, out=out)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(10):
+            st.gather(perm, gv, gr, ga, out=out)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1) / 10
+        aux["minibatch_gather_T16_N16384"] = {"ms": gather_ms, "GB/s": Tg * Ng * 4712 / gather_ms / 1e6, "bytes_per_row": 4712,
+                                              "rows": Tg * Ng}
+        del st, genv, out
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -156,6 +156,26 @@ int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t* env_obs_d
                         const float* env_reward_dev, const uint8_t* env_info_dev, const int32_t* actions_dev,
                         const float* logp_dev, const uint8_t* stepped_dev, int begin, int fresh, void* stream);
 
+/* ---- minibatch generator (RL/ppo/process_batch.py:169-200, generator_standard) --------------------
+ * The reference draws a random permutation of the T*N (time, env) pairs, cuts it into num_mini_batch index lists and, for
+ * each, indexes every CPU buffer key by key and copies the pieces to the device.  Here the rollout buffers are already in
+ * HBM: one launch gathers the B rows `indices_dev[b] = t * N + n` (t < T) of all arrays into contiguous minibatch buffers
+ * (caller-owned, row buffers 16-byte aligned).  values [T+1][N], returns / advantages [T][N] as produced by catan_gae. */
+typedef struct catan_minibatch {
+  uint8_t* obs;               /* [B][CATAN_OBS_STRIDE]      obs_dict[key][:-1].view(-1, ...)[indices]   process_batch.py:179-181 */
+  uint8_t* masks;             /* [B][CATAN_MASK_STRIDE]     action_masks[i]...[indices]                 :187-192 */
+  int32_t* actions;           /* [B][CATAN_ACTION_WORDS]    actions[i].view(-1, ...)[indices]           :193 */
+  float* logp;                /* [B]  old_action_log_probs_batch                                           :198 */
+  float* values;              /* [B]  value_preds_batch = values[:-1]                                      :195 */
+  float* returns;             /* [B]  returns_batch                                                        :196 */
+  float* tmasks;              /* [B]  masks_batch = masks[:-1]                                             :197 */
+  float* advantages;          /* [B]  adv_targets                                                          :199 */
+} catan_minibatch_t;
+
+int catan_minibatch_gather(const catan_rollout_t* rollout, const float* values_dev, const float* returns_dev,
+                           const float* advantages_dev, const int32_t* indices_dev, int B, const catan_minibatch_t* out,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,11 @@ class CatanError(RuntimeError):
     pass
 
 
+class CatanMinibatch(C.Structure):
+    """catan_minibatch_t"""
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "masks", "actions", "logp", "values", "returns", "tmasks", "advantages")]
+
+
 #: every symbol include/catan_b200.h declares: name -> (restype, argtypes)
 _u8p, _i32p, _f32p, _i16p, _u32p, _f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_int32, C.c_float, C.c_int16, C.c_uint32, C.c_double))
 _vp = C.c_void_p
@@ -75,6 +80,7 @@ ABI = {
     "catan_gae": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp]),
     "catan_adv_stats": (C.c_int, [_vp, C.c_longlong, _vp, _vp]),
     "catan_adv_apply": (C.c_int, [_vp, C.c_longlong, _vp, C.c_double, _vp]),
+    "catan_minibatch_gather": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
 }
 
 _lib = None

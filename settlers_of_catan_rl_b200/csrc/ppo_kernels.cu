@@ -256,6 +256,49 @@ __global__ void __launch_bounds__(128) rollout_store_kernel(const RolloutArgs A)
   }
 }
 
+// ---- minibatch gather (RL/ppo/process_batch.py:169-200, generator_standard) ------------------------
+// One minibatch = B rows picked by a random permutation of the T*N (time, env) pairs of the rollout buffers.  The
+// reference indexes its CPU tensors key by key and ships every piece to the device; here the buffers already live in HBM
+// and one launch copies the B rows of all eight arrays into contiguous minibatch tensors: one warp per row, 16-byte
+// vectors (120 for the observation, 21 for the masks, 5 for the action), the six scalars by lanes 0..5.
+// Algorithmic bytes per row: 2 x (1920 + 336 + 80 + 5 x 4) = 4712.
+struct GatherArgs {
+  catan_rollout_t r;
+  const float* values;        // [T+1][N]
+  const float* returns;       // [T][N]
+  const float* advantages;    // [T][N]
+  const int32_t* indices;     // [B] flat t * N + n, t < T
+  catan_minibatch_t out;
+  int B;
+};
+
+__global__ void __launch_bounds__(256) minibatch_gather_kernel(const __grid_constant__ GatherArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int row = static_cast<int>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= A.B) return;
+  const size_t src = static_cast<size_t>(A.indices[row]);          // (t, n) flattened: the same offset in every [T(+1)][N] array
+  {
+    const uint4* s = reinterpret_cast<const uint4*>(A.r.obs + src * CATAN_OBS_STRIDE);
+    uint4* d = reinterpret_cast<uint4*>(A.out.obs + static_cast<size_t>(row) * CATAN_OBS_STRIDE);
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (lane + 32 * k < CATAN_OBS_STRIDE / 16) v[k] = __ldcs(s + lane + 32 * k);   // read once, written once
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (lane + 32 * k < CATAN_OBS_STRIDE / 16) __stcs(d + lane + 32 * k, v[k]);
+  }
+  if (lane < CATAN_MASK_STRIDE / 16)
+    __stcs(reinterpret_cast<uint4*>(A.out.masks + static_cast<size_t>(row) * CATAN_MASK_STRIDE) + lane,
+           __ldcs(reinterpret_cast<const uint4*>(A.r.masks + src * CATAN_MASK_STRIDE) + lane));
+  if (lane < CATAN_ACTION_WORDS / 4)
+    __stcs(reinterpret_cast<uint4*>(A.out.actions + static_cast<size_t>(row) * CATAN_ACTION_WORDS) + lane,
+           __ldcs(reinterpret_cast<const uint4*>(A.r.actions + src * CATAN_ACTION_WORDS) + lane));
+  if (lane < 5) {
+    const float* sp = lane == 0 ? A.r.logp : lane == 1 ? A.values : lane == 2 ? A.returns : lane == 3 ? A.r.tmasks : A.advantages;
+    float* dp = lane == 0 ? A.out.logp : lane == 1 ? A.out.values : lane == 2 ? A.out.returns : lane == 3 ? A.out.tmasks : A.out.advantages;
+    dp[row] = sp[src];                                               // values[:-1], masks[:-1]: t < T, so the flat offset is the same
+  }
+}
+
 }  // namespace catanb
 
 extern "C" int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t* env_obs_dev, const uint8_t* env_masks_dev,
@@ -271,4 +314,21 @@ extern "C" int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t
   catanb::rollout_store_kernel<<<(rollout->N + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(A);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : ppo_fail(e, "catan_rollout_store launch");
+}
+
+extern "C" int catan_minibatch_gather(const catan_rollout_t* rollout, const float* values_dev, const float* returns_dev,
+                                      const float* advantages_dev, const int32_t* indices_dev, int B, const catan_minibatch_t* out,
+                                      void* stream) {
+  if (B == 0) return 0;                                              // (an empty batch has null pointers)
+  if (!rollout || !values_dev || !returns_dev || !advantages_dev || !indices_dev || !out || B < 0 || rollout->N <= 0 || rollout->T <= 0)
+    return ppo_fail(cudaErrorInvalidValue, "catan_minibatch_gather: bad argument");
+  if (!out->obs || !out->masks || !out->actions || !out->logp || !out->values || !out->returns || !out->tmasks || !out->advantages)
+    return ppo_fail(cudaErrorInvalidValue, "catan_minibatch_gather: null output buffer");
+  if ((reinterpret_cast<uintptr_t>(out->obs) | reinterpret_cast<uintptr_t>(out->masks) | reinterpret_cast<uintptr_t>(out->actions)) & 15)
+    return ppo_fail(cudaErrorInvalidValue, "catan_minibatch_gather: row buffers must be 16-byte aligned");
+  catanb::GatherArgs A;
+  A.r = *rollout; A.values = values_dev; A.returns = returns_dev; A.advantages = advantages_dev; A.indices = indices_dev; A.out = *out; A.B = B;
+  catanb::minibatch_gather_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : ppo_fail(e, "catan_minibatch_gather launch");
 }

@@ -138,6 +138,42 @@ class RolloutStorage:
             ticks += 1
         return ticks
 
+    def gather(self, indices: torch.Tensor, values: torch.Tensor, returns: torch.Tensor, advantages: torch.Tensor, out: Optional[dict] = None) -> dict:
+        """One minibatch (process_batch.py:177-200): rows ``indices`` (int32 CUDA, flat ``t * N + n`` with t < T) of every
+        rollout array, gathered by ONE launch into contiguous tensors.  ``values`` [T+1,N], ``returns`` / ``advantages``
+        [T,N] fp32.  Keys: obs uint8 [B,1920], masks uint8 [B,336], actions int32 [B,20], logp, values, returns, tmasks,
+        advantages fp32 [B]  (slice obs / masks into the policy's keys with ``VecCatanEnv.obs_views`` / ``mask_views``)."""
+        from . import layout as L
+        _check_f32_cuda(values, returns, advantages)
+        if not (indices.is_cuda and indices.dtype == torch.int32 and indices.is_contiguous()):
+            raise _lib.CatanError("indices must be a contiguous int32 CUDA tensor")
+        if values.numel() != (self.T + 1) * self.N or returns.numel() != self.T * self.N or advantages.numel() != self.T * self.N:
+            raise ValueError("values must be [T+1, N], returns and advantages [T, N]")
+        B, dev = indices.numel(), self.env.device
+        if out is None:
+            out = {"obs": torch.empty((B, L.OBS_STRIDE), dtype=torch.uint8, device=dev),
+                   "masks": torch.empty((B, L.MASK_STRIDE), dtype=torch.uint8, device=dev),
+                   "actions": torch.empty((B, L.ACTION_WORDS), dtype=torch.int32, device=dev)}
+            for k in ("logp", "values", "returns", "tmasks", "advantages"):
+                out[k] = torch.empty(B, dtype=torch.float32, device=dev)
+        mb = _lib.CatanMinibatch(**{k: out[k].data_ptr() for k in ("obs", "masks", "actions", "logp", "values", "returns", "tmasks", "advantages")})
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().catan_minibatch_gather(C.byref(self._c), _p(values), _p(returns), _p(advantages), _p(indices), B,
+                                                          C.byref(mb), _stream(self.obs)))
+        return out
+
+    def minibatches(self, num_mini_batch: int, values: torch.Tensor, returns: torch.Tensor, advantages: torch.Tensor, generator=None,
+                    perm: Optional[torch.Tensor] = None):
+        """generator_standard (process_batch.py:169-200): a random permutation of the T*N rows cut into ``num_mini_batch``
+        index lists of ``T*N // num_mini_batch`` rows (BatchSampler(SubsetRandomSampler(...), drop_last=True))."""
+        batch = self.T * self.N
+        size = batch // num_mini_batch
+        if perm is None:
+            perm = torch.randperm(batch, device=self.env.device, generator=generator)
+        perm = perm.to(device=self.env.device, dtype=torch.int32)
+        for k in range(num_mini_batch):
+            yield self.gather(perm[k * size:(k + 1) * size].contiguous(), values, returns, advantages)
+
     def compute_returns(self, values: torch.Tensor, gamma: float = 0.999, gae_lambda: float = 0.95, normalise: bool = True, group=None):
         """values: [T+1, N] fp32 (denormalised).  Returns (returns, advantages) — process_batch.py:134-142."""
         returns, adv = gae(self.rewards, values.contiguous(), self.tmasks, gamma, gae_lambda)

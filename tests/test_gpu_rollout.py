@@ -81,3 +81,41 @@ def test_rollout_store_matches_reference_collector():
     values = torch.rand(T + 1, N, device=env.device) * 300
     ret, adv = store.compute_returns(values)
     assert ret.shape == (T, N) and torch.isfinite(adv).all()
+
+
+def test_minibatch_gather_matches_the_reference_indexing():
+    """generator_standard (process_batch.py:169-200): view(-1, ...)[indices] of every buffer, for a drop_last permutation"""
+    from settlers_of_catan_rl_b200 import VecCatanEnv, RolloutStorage, layout as L
+    T, N = 12, 96
+    env = VecCatanEnv(N, seed=4)
+    env.reset()
+    st = RolloutStorage(env, T)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    st.obs.copy_(torch.randint(0, 255, st.obs.shape, device="cuda", dtype=torch.uint8, generator=g))
+    st.masks.copy_(torch.randint(0, 2, st.masks.shape, device="cuda", dtype=torch.uint8, generator=g))
+    st.actions.copy_(torch.randint(0, 54, st.actions.shape, device="cuda", dtype=torch.int32, generator=g))
+    st.logp.copy_(torch.randn(st.logp.shape, device="cuda", generator=g))
+    st.tmasks.copy_((torch.rand(st.tmasks.shape, device="cuda", generator=g) > 0.1).float())
+    values = torch.randn(T + 1, N, device="cuda", generator=g)
+    returns = torch.randn(T, N, device="cuda", generator=g)
+    adv = torch.randn(T, N, device="cuda", generator=g)
+    perm = torch.randperm(T * N, device="cuda", generator=g)
+    seen = list(st.minibatches(5, values, returns, adv, perm=perm))   # 1152 rows -> 5 x 230, 2 dropped
+    assert len(seen) == 5 and seen[0]["obs"].shape == (T * N // 5, L.OBS_STRIDE)
+    assert len(list(st.minibatches(4, values, returns, adv))) == 4    # (its own permutation)
+    # against torch indexing of the flattened buffers (the reference's own lines)
+    size = T * N // 5
+    for k, mb in enumerate(seen):
+        idx = perm[k * size:(k + 1) * size]
+        assert torch.equal(mb["obs"], st.obs[:-1].reshape(-1, L.OBS_STRIDE)[idx])
+        assert torch.equal(mb["masks"], st.masks.reshape(-1, L.MASK_STRIDE)[idx])
+        assert torch.equal(mb["actions"], st.actions.reshape(-1, L.ACTION_WORDS)[idx])
+        assert torch.equal(mb["logp"], st.logp.reshape(-1)[idx])
+        assert torch.equal(mb["values"], values[:-1].reshape(-1)[idx])
+        assert torch.equal(mb["returns"], returns.reshape(-1)[idx])
+        assert torch.equal(mb["tmasks"], st.tmasks[:-1].reshape(-1)[idx])
+        assert torch.equal(mb["advantages"], adv.reshape(-1)[idx])
+    # empty and single-row batches
+    one = st.gather(torch.tensor([T * N - 1], device="cuda", dtype=torch.int32), values, returns, adv)
+    assert torch.equal(one["obs"][0], st.obs[T - 1, N - 1]) and float(one["values"][0]) == float(values[T - 1, N - 1])
+    assert st.gather(torch.empty(0, device="cuda", dtype=torch.int32), values, returns, adv)["obs"].shape[0] == 0
