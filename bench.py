@@ -362,8 +362,8 @@ def run_b200_arm(args):
                                                "achieved": TRANSITION_BYTES_PER_ENV_STEP * n / (transition_ms * 1e-3) / 1e9},
                          "whole_step": {"ms": per_launch_ms, "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * n,
                                         "achieved": step_achieved, "frac": step_achieved / peak,
-                                        "note": "5 launches on 2 streams: transition, encode | longest-road search, encode of "
-                                                "the searched games, copy-back"}},
+                                        "note": "6 launches on 2 streams: transition, encode | longest-road search, encode of "
+                                                "the searched games, copy-back, counter bookkeeping"}},
             "cpu_baseline": cpu_baseline,
             "aux": aux,
         }

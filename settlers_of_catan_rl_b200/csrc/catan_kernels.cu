@@ -1,6 +1,6 @@
 // catan_kernels.cu — sm_100a kernels + C ABI of the vectorised Catan engine (see include/catan_b200.h).
 //
-// One env step is five launches on two streams (catan_game.cuh holds the game logic; records are lane-interleaved
+// One env step is six launches on two streams (catan_game.cuh holds the game logic; records are lane-interleaved
 // chunks of 32 games, and every kernel below works on whole chunks with one game per lane):
 //
 //   caller's stream
@@ -21,7 +21,7 @@
 //                        length cannot be trusted, the reference's full enumeration (game.py:843-862) -- as a pool of
 //                        16-byte subtree tasks that the lanes drain and re-split without barriers (lp_pool).
 //   encode_kernel<LISTED> the same encode for the queued games, on their staging chunks
-//   lr_copy_back_kernel  staging -> home records
+//   lr_copy_back_kernel  staging -> home records (+ lr_finish_kernel: one thread banks and clears the queue counters)
 //
 // Why the search is not inside a thread-per-game kernel: its cost varies by four orders of magnitude between games and
 // would stall 31 other games per unit of imbalance; why it runs on a second stream: it is latency-bound (a few hundred
@@ -55,7 +55,7 @@ constexpr int kSampleThreads = 128;         // stand-alone sampler kernel
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
-struct LrCtl {                // double-buffered by step parity: the transition of a step clears the other buffer
+struct LrCtl {                // per-step queue counters; lr_finish_kernel banks them into the totals and clears them
   int32_t count, slow_count;  // longest-road updates of this step; those that went to lr_slow_kernel (= length of its queue)
   unsigned long long total, slow_total;   // the same, summed over all earlier steps
   unsigned long long dbg[6];  // lr_slow_kernel diagnostics: cycles sum / max, walk steps sum / max per search; full enumerations; tasks
@@ -78,8 +78,7 @@ struct EnvParams {
   int range_first, range_count;   // env range this launch covers
   uint32_t* side;              // [n] transition -> encode: err | acted_pid << 8 | act_type << 16 | roll << 24 | longest-road update pending << 31
   uint64_t* lr_slow_queue;     // [n] updates that need a search: env index | PlayerId << 32 | edge or corner << 40 | CATAN_LR_* << 48 | acting PlayerId << 56
-  LrCtl* lr_ctl;               // queue lengths of THIS step
-  LrCtl* lr_ctl_next;          // the other buffer: cleared by this step's transition for the next step
+  LrCtl* lr_ctl;               // queue lengths of this step
 };
 
 struct GameSmem {
@@ -175,13 +174,6 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   const int base = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32;
   uint8_t* const home = P.recs + static_cast<size_t>(base >> 5) * CATAN_CHUNK_BYTES;
   if (tid == 0) { mbar_init(&S.mbar); chunk_to_shared(S.chunk, home, &S.mbar); S.n_follow = 0; }   // in flight while the topology is staged
-  if (blockIdx.x == 0 && tid == 0) {                                 // the other queue buffer belongs to the step before: bank its counts, clear it
-    LrCtl& o = *P.lr_ctl_next;
-    P.lr_ctl->total = o.total + static_cast<unsigned long long>(o.count); P.lr_ctl->slow_total = o.slow_total + static_cast<unsigned long long>(o.slow_count);
-    for (int k = 0; k < 6; ++k) P.lr_ctl->dbg[k] = (k == 1 || k == 3) ? max(o.dbg[k], P.lr_ctl->dbg[k]) : o.dbg[k] + P.lr_ctl->dbg[k];
-    o.count = 0; o.slow_count = 0; o.total = 0; o.slow_total = 0;
-    for (int k = 0; k < 6; ++k) o.dbg[k] = 0;
-  }
   {
     const int4* src = reinterpret_cast<const int4*>(&d_topo);
     int4* dst = reinterpret_cast<int4*>(&S.topo);
@@ -368,6 +360,12 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
       atomicAdd(&P.lr_ctl->dbg[5], static_cast<unsigned long long>(S.tasks));
     }
   }
+}
+
+// last launch of a step on the library's stream: every consumer of the queue counters has run
+__global__ void lr_finish_kernel(LrCtl* c) {
+  c->total += static_cast<unsigned long long>(c->count); c->slow_total += static_cast<unsigned long long>(c->slow_count);
+  c->count = 0; c->slow_count = 0;
 }
 
 // ---- 3. finish + masks + sampler + observation --------------------------------------------------
@@ -564,7 +562,6 @@ struct catan_env {
   int lr_grid = 0;
   cudaStream_t lr_stream = nullptr;   // high-priority stream of the longest-road updates (overlaps the encode kernel)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  unsigned long long ticks = 0;        // steps launched: selects the queue-counter buffer
   // catan_set_timing: CUDA events around the two kernels on the caller's stream, a ring of kTimedSteps steps
   bool timing = false;
   cudaEvent_t tev[32][3] = {};
@@ -584,7 +581,7 @@ static EnvParams make_params(const catan_env* env) {
   EnvParams P{};
   P.recs = env->recs; P.stage = env->stage; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
   P.obs = env->obs; P.masks = env->masks; P.reward = env->reward; P.info = env->info; P.err_flags = env->err_flags;
-  P.side = env->side; P.lr_slow_queue = env->lr_slow_queue; P.lr_ctl = env->lr_ctl + (env->ticks & 1); P.lr_ctl_next = env->lr_ctl + ((env->ticks & 1) ^ 1);
+  P.side = env->side; P.lr_slow_queue = env->lr_slow_queue; P.lr_ctl = env->lr_ctl;
   return P;
 }
 
@@ -648,7 +645,6 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   }
   CATAN_CUDA(launch_with_record_window(env, catanb::transition_kernel, game_blocks(0, env->n), catanb::kTransThreads, 0, stream, P));
   if (tev) CATAN_CUDA(cudaEventRecord(tev[1], stream));
-  env->ticks += 1;
   CATAN_CUDA(cudaEventRecord(env->ev_fork, stream));
   CATAN_CUDA(cudaStreamWaitEvent(env->lr_stream, env->ev_fork, 0));
   catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), env->lr_stream>>>(P);
@@ -656,6 +652,8 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count / 2, catanb::kEncThreads, sizeof(catanb::EncSmem), env->lr_stream>>>(P);
   CATAN_CUDA(cudaGetLastError());
   catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->lr_stream>>>(P);
+  CATAN_CUDA(cudaGetLastError());
+  catanb::lr_finish_kernel<<<1, 1, 0, env->lr_stream>>>(env->lr_ctl);
   CATAN_CUDA(cudaGetLastError());
   CATAN_CUDA(cudaEventRecord(env->ev_join, env->lr_stream));
   if (launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream)) return -1;
@@ -737,8 +735,8 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   if (e == cudaSuccess) e = cudaMalloc(&env->side, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMemset(env->side, 0, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->lr_slow_queue, sizeof(uint64_t) * n);
-  if (e == cudaSuccess) e = cudaMalloc(&env->lr_ctl, 2 * sizeof(catanb::LrCtl));
-  if (e == cudaSuccess) e = cudaMemset(env->lr_ctl, 0, 2 * sizeof(catanb::LrCtl));
+  if (e == cudaSuccess) e = cudaMalloc(&env->lr_ctl, sizeof(catanb::LrCtl));
+  if (e == cudaSuccess) e = cudaMemset(env->lr_ctl, 0, sizeof(catanb::LrCtl));
   if (e == cudaSuccess) e = cudaMalloc(&env->actions_stage, sizeof(int32_t) * CATAN_ACTION_WORDS * n);
   if (e == cudaSuccess) {
     int lo = 0, hi = 0;                                  // (greatest priority is the numerically lowest value)
@@ -919,13 +917,10 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
 int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
   if (!env || !out_host) return fail("null argument");
   if (device_guard(env)) return -1;
-  catanb::LrCtl c[2];
+  catanb::LrCtl last;
   CATAN_CUDA(cudaDeviceSynchronize());
-  CATAN_CUDA(cudaMemcpy(c, env->lr_ctl, sizeof(c), cudaMemcpyDeviceToHost));
-  // every step banks the totals of the step before into its own buffer; what it queued itself is still in count / slow_count
-  const catanb::LrCtl& last = c[(env->ticks & 1) ^ 1];
-  out_host[0] = last.total + static_cast<unsigned long long>(last.count);
-  out_host[1] = last.slow_total + static_cast<unsigned long long>(last.slow_count);
+  CATAN_CUDA(cudaMemcpy(&last, env->lr_ctl, sizeof(last), cudaMemcpyDeviceToHost));
+  out_host[0] = last.total; out_host[1] = last.slow_total;
   out_host[2] = last.dbg[4]; out_host[3] = last.dbg[5];
   for (int i = 0; i < 4; ++i) out_host[4 + i] = last.dbg[i];
   return 0;

@@ -76,7 +76,7 @@ class VecCatanEnv:
         if step_mask is not None:
             assert step_mask.dtype == torch.uint8 and step_mask.is_cuda and step_mask.numel() == self.n_envs
         _lib.check(self.lib.catan_step_masked(self._h, _ptr(actions), _ptr(step_mask), self._stream()))
-        self.kernel_launches += 5                      # transition, encode | lr_slow, encode (listed), copy-back
+        self.kernel_launches += 6                      # transition, encode | lr_slow, encode (listed), copy-back, lr_finish
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
     def sample_random(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -87,10 +87,10 @@ class VecCatanEnv:
         return out
 
     def step_sample(self, actions_io: torch.Tensor):
-        """One call (five launches on two streams, the sampler fused into the last): apply ``actions_io`` and overwrite it with the next random-legal actions."""
+        """One call (six launches on two streams, the sampler fused into the last): apply ``actions_io`` and overwrite it with the next random-legal actions."""
         assert actions_io.dtype == torch.int32 and actions_io.is_cuda and actions_io.is_contiguous()
         _lib.check(self.lib.catan_step_sample(self._h, _ptr(actions_io), self._stream()))
-        self.kernel_launches += 5
+        self.kernel_launches += 6
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
     def get_action_masks(self) -> torch.Tensor:
@@ -103,7 +103,7 @@ class VecCatanEnv:
             return C.c_void_p(0 if a is None else a.ctypes.data)
         assert actions.dtype == np.int32 and actions.flags.c_contiguous
         _lib.check(self.lib.catan_step_host(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
-        self.kernel_launches += 5
+        self.kernel_launches += 6
 
     def reset_host(self, obs: np.ndarray = None, masks: np.ndarray = None, info: np.ndarray = None) -> None:
         def p(a):

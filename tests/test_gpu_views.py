@@ -68,3 +68,29 @@ def test_step_timing_hooks():
     assert torch.equal(a.obs, b.obs) and torch.equal(a.masks, b.masks)
     assert np.array_equal(a.export_state(), b.export_state())
     assert a.read_timing()[0] == 0
+
+
+def test_a_step_can_be_captured_in_a_cuda_graph():
+    """the six launches of a step (two streams, forked and joined with events) are capturable: replaying the graph advances
+    the games exactly like direct calls"""
+    import numpy as np
+    from settlers_of_catan_rl_b200 import VecCatanEnv
+    a = VecCatanEnv(1024, seed=9)
+    b = VecCatanEnv(1024, seed=9)
+    for v in (a, b):
+        v.reset()
+    acts_a, acts_b = a.sample_random(), b.sample_random()
+    for _ in range(3):
+        a.step_sample(acts_a)
+        b.step_sample(acts_b)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        a.step_sample(acts_a)
+    for _ in range(300):
+        g.replay()
+        b.step_sample(acts_b)
+    torch.cuda.synchronize()
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.masks, b.masks) and torch.equal(acts_a, acts_b)
+    assert np.array_equal(a.export_state(), b.export_state())
+    assert int(a.lr_stats()[0]) == int(b.lr_stats()[0]) > 0
