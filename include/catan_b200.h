@@ -156,6 +156,14 @@ int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t* env_obs_d
                         const float* env_reward_dev, const uint8_t* env_info_dev, const int32_t* actions_dev,
                         const float* logp_dev, const uint8_t* stepped_dev, int begin, int fresh, void* stream);
 
+/* ---- per-seat policy routing (RL/ppo/game_manager.py:21-31 policy_maps, :82-93 the per-env policy call) --------------
+ * policy_map_dev uint8[N][4]: index (< n_policies) of the policy that plays PlayerId p + 1 in env n.  For every policy k:
+ * lists_dev[k][0 .. counts_dev[k]) = ascending indices of the envs whose NEXT decision (info CATAN_INFO_ACTOR) is taken by
+ * policy k, so that each policy runs one batched forward per tick.  active_dev uint8[N] or NULL: envs with a zero byte are
+ * left out (those frozen by catan_step_masked).  counts_dev int32[n_policies], lists_dev int32[n_policies][N]. */
+int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t* policy_map_dev, const uint8_t* active_dev, int N,
+                          int n_policies, int32_t* counts_dev, int32_t* lists_dev, void* stream);
+
 /* ---- minibatch generator (RL/ppo/process_batch.py:169-200, generator_standard) --------------------
  * The reference draws a random permutation of the T*N (time, env) pairs, cuts it into num_mini_batch index lists and, for
  * each, indexes every CPU buffer key by key and copies the pieces to the device.  Here the rollout buffers are already in

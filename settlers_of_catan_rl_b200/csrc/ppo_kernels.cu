@@ -299,6 +299,47 @@ __global__ void __launch_bounds__(256) minibatch_gather_kernel(const __grid_cons
   }
 }
 
+// ---- per-seat policy routing (RL/ppo/game_manager.py:21-31, :82-93) -----------------------------------
+// The reference keeps a PlayerId -> policy map per env (four policies: the learner and three earlier snapshots) and, env by
+// env, lets the policy of the player whose decision it is act.  Vectorised, a tick needs, per policy, the list of envs it
+// acts for: block k compacts the env indices n with policy_map[n][actor(n) - 1] == k, in ascending order (ballot + scan),
+// so that every policy runs ONE batched forward over its own envs.
+struct RouteArgs {
+  const uint8_t* info;        // [N][CATAN_INFO_STRIDE]: CATAN_INFO_ACTOR = PlayerId that takes the next decision
+  const uint8_t* policy_map;  // [N][4]: policy index of PlayerId p + 1
+  const uint8_t* active;      // [N] or null: envs with a zero byte are left out (frozen by catan_step_masked)
+  int32_t* counts;            // [K]
+  int32_t* lists;             // [K][N]
+  int N;
+};
+
+__global__ void __launch_bounds__(1024) route_kernel(const __grid_constant__ RouteArgs A) {
+  __shared__ int warp_count[32];
+  __shared__ int base;
+  const int k = static_cast<int>(blockIdx.x), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  int32_t* out = A.lists + static_cast<size_t>(k) * A.N;
+  for (int n0 = 0; n0 < A.N; n0 += 1024) {
+    const int n = n0 + tid;
+    bool hit = false;
+    if (n < A.N && (A.active == nullptr || A.active[n] != 0)) {
+      const int actor = A.info[static_cast<size_t>(n) * CATAN_INFO_STRIDE + CATAN_INFO_ACTOR];
+      hit = actor >= 1 && actor <= 4 && A.policy_map[static_cast<size_t>(n) * 4 + actor - 1] == k;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_count[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const int c = warp_count[w]; before += w < warp ? c : 0; total += c; }
+    if (hit) out[base + before + __popc(bal & ((1u << lane) - 1u))] = n;
+    __syncthreads();
+    if (tid == 0) base += total;
+  }
+  __syncthreads();
+  if (tid == 0) A.counts[k] = base;
+}
+
 }  // namespace catanb
 
 extern "C" int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t* env_obs_dev, const uint8_t* env_masks_dev,
@@ -331,4 +372,15 @@ extern "C" int catan_minibatch_gather(const catan_rollout_t* rollout, const floa
   catanb::minibatch_gather_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : ppo_fail(e, "catan_minibatch_gather launch");
+}
+
+extern "C" int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t* policy_map_dev, const uint8_t* active_dev, int N,
+                                     int n_policies, int32_t* counts_dev, int32_t* lists_dev, void* stream) {
+  if (!env_info_dev || !policy_map_dev || !counts_dev || !lists_dev || N <= 0 || n_policies <= 0 || n_policies > 255)
+    return ppo_fail(cudaErrorInvalidValue, "catan_route_by_policy: bad argument");
+  catanb::RouteArgs A;
+  A.info = env_info_dev; A.policy_map = policy_map_dev; A.active = active_dev; A.counts = counts_dev; A.lists = lists_dev; A.N = N;
+  catanb::route_kernel<<<n_policies, 1024, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : ppo_fail(e, "catan_route_by_policy launch");
 }

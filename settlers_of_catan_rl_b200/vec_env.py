@@ -123,6 +123,19 @@ class VecCatanEnv:
         _lib.check(self.lib.catan_import_state(self._h, first, states.shape[0], C.c_void_p(states.ctypes.data)))
         self.kernel_launches += 1
 
+    def route_by_policy(self, policy_map: torch.Tensor, n_policies: int, active: Optional[torch.Tensor] = None):
+        """game_manager.py:21-31 / :82-93 vectorised: ``policy_map`` uint8 [N,4] = policy index playing PlayerId p+1 in env n.
+        Returns (counts int32 [K], lists int32 [K,N]): ``lists[k, :counts[k]]`` are the envs (ascending) whose next decision
+        belongs to policy k; ``active`` (uint8 [N], optional) leaves frozen envs out."""
+        assert policy_map.dtype == torch.uint8 and policy_map.is_cuda and policy_map.is_contiguous() and policy_map.shape == (self.n_envs, 4)
+        if active is not None:
+            assert active.dtype == torch.uint8 and active.is_cuda and active.numel() == self.n_envs
+        counts = torch.empty(n_policies, dtype=torch.int32, device=self.device)
+        lists = torch.empty((n_policies, self.n_envs), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.catan_route_by_policy(_ptr(self.info), _ptr(policy_map), _ptr(active), self.n_envs, int(n_policies),
+                                                  _ptr(counts), _ptr(lists), self._stream()))
+        return counts, lists
+
     def lr_stats(self) -> np.ndarray:
         """catan_read_lr_stats: [updates, searched by a block, full enumerations, search tasks, search cycles sum, max,
         walk steps sum, max] since construction"""

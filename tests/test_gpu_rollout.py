@@ -119,3 +119,32 @@ def test_minibatch_gather_matches_the_reference_indexing():
     one = st.gather(torch.tensor([T * N - 1], device="cuda", dtype=torch.int32), values, returns, adv)
     assert torch.equal(one["obs"][0], st.obs[T - 1, N - 1]) and float(one["values"][0]) == float(values[T - 1, N - 1])
     assert st.gather(torch.empty(0, device="cuda", dtype=torch.int32), values, returns, adv)["obs"].shape[0] == 0
+
+
+def test_policy_routing_lists_match_the_reference_maps():
+    """game_manager.py:21-31, :82-93: env n is played by policy_map[n][players turn]; here as per-policy env lists"""
+    from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
+    n, K = 3000, 4
+    env = VecCatanEnv(n, seed=6)
+    env.reset()
+    acts = env.sample_random()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    # a random seat -> policy assignment per env, like random.shuffle(order) in initialise()
+    pmap = torch.stack([torch.randperm(K, device="cuda", generator=g) for _ in range(n)]).to(torch.uint8).contiguous()
+    active = (torch.rand(n, device="cuda", generator=g) > 0.2).to(torch.uint8)
+    for tick in range(40):
+        env.step_sample(acts)
+        for act in (None, active):
+            counts, lists = env.route_by_policy(pmap, K, act)
+            actor = env.info[:, L.INFO_ACTOR].long()
+            pol = pmap.long().gather(1, (actor - 1).view(-1, 1)).view(-1)
+            total = 0
+            for k in range(K):
+                sel = pol == k
+                if act is not None:
+                    sel = sel & (act != 0)
+                want = torch.nonzero(sel).view(-1).to(torch.int32)
+                c = int(counts[k])
+                assert c == want.numel() and torch.equal(lists[k, :c], want), (tick, k)
+                total += c
+            assert total == (n if act is None else int(active.sum()))
