@@ -313,6 +313,21 @@ def run_b200_arm(args):
         aux["minibatch_gather_T16_N16384"] = {"ms": gather_ms, "GB/s": Tg * Ng * 4712 / gather_ms / 1e6, "bytes_per_row": 4712,
                                               "rows": Tg * Ng}
         del st, genv, out
+        # policy inputs (policy.py:168-190 batched): the env's own 65 536 packed rows -> fp32 / bf16 policy tensors, one launch
+        from settlers_of_catan_rl_b200.policy_io import PolicyInputs
+        for pdt, pname, pbytes in ((torch.float32, "f32", 2256 + 1792 * 4 + 1000 + 325 * 4), (torch.bfloat16, "bf16", 2256 + 1792 * 2 + 1000 + 325 * 2)):
+            pin = PolicyInputs(n, dev, pdt)
+            for _ in range(3):
+                pin(env.obs, env.masks)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(10):
+                pin(env.obs, env.masks)
+            g1.record()
+            torch.cuda.synchronize()
+            pms = g0.elapsed_time(g1) / 10
+            aux["policy_inputs_%s_N%d" % (pname, n)] = {"ms": pms, "GB/s": n * pbytes / pms / 1e6, "bytes_per_row": pbytes}
+            del pin
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -164,6 +164,22 @@ int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t* env_obs_d
 int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t* policy_map_dev, const uint8_t* active_dev, int N,
                           int n_policies, int32_t* counts_dev, int32_t* lists_dev, void* stream);
 
+/* ---- policy inputs (RL/models/policy.py:168-190 obs_to_torch / act_masks_to_torch; batched form process_batch.py:43-51,
+ * :80-84; consumer RL/models/observation_module.py, action_heads_module.py:62-80) ------------------------------------------
+ * Expands B packed rows (the env's own obs / mask buffers, a routed subset copied out of them, or a gathered minibatch) into
+ * the tensors the reference's policy network reads, in one launch:
+ *   features_dev   [B][CATAN_POLICY_FEATURE_STRIDE] of dtype: columns 0..1786 = the numeric features in catan_layout.h order
+ *                  (ratio features rescaled to len/8 and knights/4), columns 1787..1791 = 0;
+ *   lists_dev      int64 [5][B][CATAN_OBS_DEV_PAD]: padded development-card lists (card + 1, 0 = pad), list order as in the row;
+ *   head_masks_dev dtype [CATAN_MASK_ENTRIES * B]: head h starts at element CATAN_MASK_<h> * B and is [B][dim], except the
+ *                  type-conditional heads 1 (corner), 6 (player), 9 (resource A), which are [types][B][dim].
+ * mask_rows_dev and head_masks_dev may both be NULL (value-only pass, policy.py:108-110 get_value). */
+#define CATAN_POLICY_FEATURE_STRIDE 1792
+#define CATAN_DTYPE_F32 0
+#define CATAN_DTYPE_BF16 1
+int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_dev, int B, int dtype, void* features_dev,
+                        int64_t* lists_dev, void* head_masks_dev, void* stream);
+
 /* ---- minibatch generator (RL/ppo/process_batch.py:169-200, generator_standard) --------------------
  * The reference draws a random permutation of the T*N (time, env) pairs, cuts it into num_mini_batch index lists and, for
  * each, indexes every CPU buffer key by key and copies the pieces to the device.  Here the rollout buffers are already in

@@ -1,6 +1,7 @@
 // ppo_kernels.cu — rollout-side PPO kernels (RL/ppo/process_batch.py:134-142): GAE reverse scan and
 // advantage normalisation.  HBM-bound streaming kernels; arithmetic is plain IEEE fp32 with explicit
 // round-to-nearest intrinsics so that no FMA contraction changes the reference's results.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <string>
@@ -80,6 +81,98 @@ __global__ void __launch_bounds__(256) adv_apply_kernel(float* __restrict__ a, l
     a4[i] = v;
   }
   for (long long i = (n4 << 2) + tid; i < count; i += stride) a[i] = __fdiv_rn(__fsub_rn(a[i], mean), denom);
+}
+
+
+// ---- policy inputs (RL/models/policy.py:168-190 obs_to_torch / act_masks_to_torch, process_batch.py:43-51, :80-84) -----
+// The reference converts every observation dict and mask list to fp32 tensors on the host, env by env, and stacks them.  Here
+// the packed uint8 rows are already in HBM and ONE launch expands a batch of them into the tensors the policy network reads:
+//   features [B][1792] (fp32 or bf16): the 1787 numeric features in the reference's order (the two ratio features rescaled:
+//            len / 8, knights / 4 — exact), 5 zero columns so that every row starts on a 16-byte boundary;
+//   lists    [5][B][25] int64: the padded development-card lists (card + 1, 0 = pad; player_modules.py:49-53 tensor form);
+//   head masks, one flat buffer: head h at element CATAN_MASK_<h> * B, shaped [B][dim], or [types][B][dim] for the
+//            type-conditional heads 1, 6 and 9 (policy.py:188-189 transposes them that way).
+// HBM-bound streaming: per row 1920 + 336 B read, 1792 * 4 + 125 * 8 + 325 * 4 = 9 468 B written (fp32).
+struct PolicyInArgs {
+  const uint8_t* obs;         // [B][CATAN_OBS_STRIDE]
+  const uint8_t* masks;       // [B][CATAN_MASK_STRIDE] or null
+  void* features;             // [B][CATAN_POLICY_FEATURE_STRIDE]
+  long long* lists;           // [5][B][CATAN_OBS_DEV_PAD]
+  void* head_masks;           // [CATAN_MASK_ENTRIES * B] or null
+  int B;
+};
+
+__constant__ int c_head_off[13] = {CATAN_MASK_TYPE, CATAN_MASK_CORNER, CATAN_MASK_EDGE, CATAN_MASK_TILE, CATAN_MASK_DEV,
+                                   CATAN_MASK_ACCEPT, CATAN_MASK_PLAYER, CATAN_MASK_GIVE, CATAN_MASK_RECV, CATAN_MASK_RES_A,
+                                   CATAN_MASK_RES_B, CATAN_MASK_DISCARD, CATAN_MASK_ENTRIES};
+__constant__ int c_head_dim[12] = {13, 54, 73, 19, 5, 2, 3, 6, 6, 5, 5, 5};   // last dimension; types = (off[h+1] - off[h]) / dim
+
+__device__ __forceinline__ float ratio_scale(int col) {
+  if (col < CATAN_OBS_CUR_MAIN) return 1.0f;
+  const int r = col < CATAN_OBS_OTHER_MAIN ? col - CATAN_OBS_CUR_MAIN - CATAN_OBS_CUR_LR_LEN
+                                           : (col - CATAN_OBS_OTHER_MAIN) % CATAN_OBS_OTHER_MAIN_DIM - CATAN_OBS_OTH_LR_LEN;
+  return r == 0 ? 0.125f : r == 2 ? 0.25f : 1.0f;                  // wrapper.py:613-627: len / 8.0, knights / 4.0
+}
+
+__device__ __forceinline__ void store4(float* p, size_t i4, float a, float b, float c, float d) {
+  __stcs(reinterpret_cast<float4*>(p) + i4, make_float4(a, b, c, d));
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, size_t i4, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<const unsigned*>(&lo);
+  v.y = *reinterpret_cast<const unsigned*>(&hi);
+  __stcs(reinterpret_cast<uint2*>(p) + i4, v);
+}
+__device__ __forceinline__ void store1(float* p, size_t i, float a) { __stcs(p + i, a); }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, size_t i, float a) { p[i] = __float2bfloat16_rn(a); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constant__ PolicyInArgs A) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t B = static_cast<size_t>(A.B);
+  {  // numeric features: one 4-byte load -> one 16-byte (fp32) / 8-byte (bf16) store
+    constexpr int G = CATAN_POLICY_FEATURE_STRIDE / 4;
+    const unsigned* src = reinterpret_cast<const unsigned*>(A.obs);
+    T* dst = static_cast<T*>(A.features);
+    for (size_t g = tid; g < B * G; g += stride) {
+      const size_t row = g / G;
+      const int c4 = static_cast<int>(g - row * G), col = c4 * 4;
+      const unsigned w = __ldcs(src + row * (CATAN_OBS_STRIDE / 4) + c4);
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = col + k < CATAN_OBS_FEATURES ? static_cast<float>((w >> (8 * k)) & 0xffu) : 0.0f;
+      if (col >= CATAN_OBS_CUR_MAIN) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] *= ratio_scale(col + k);
+      }
+      store4(dst, g, v[0], v[1], v[2], v[3]);
+    }
+  }
+  {  // development-card lists: byte -> int64
+    constexpr int L = 5 * CATAN_OBS_DEV_PAD;
+    for (size_t i = tid; i < B * L; i += stride) {
+      const size_t li = i / (B * CATAN_OBS_DEV_PAD), rem = i - li * B * CATAN_OBS_DEV_PAD;
+      const size_t b = rem / CATAN_OBS_DEV_PAD, j = rem - b * CATAN_OBS_DEV_PAD;
+      __stcs(A.lists + i, static_cast<long long>(A.obs[b * CATAN_OBS_STRIDE + CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD + j]));
+    }
+  }
+  if (A.masks != nullptr && A.head_masks != nullptr) {  // masks: head-major, type-conditional heads as [types][B][dim]
+    T* dst = static_cast<T*>(A.head_masks);
+    for (size_t o = tid; o < B * CATAN_MASK_ENTRIES; o += stride) {
+      const int col = static_cast<int>(o / B);                     // head h owns elements [off[h] * B, off[h + 1] * B)
+      int h = 0;
+#pragma unroll
+      for (int k = 1; k < 12; ++k) h += col >= c_head_off[k];
+      const int off = c_head_off[h], dim = c_head_dim[h];
+      const size_t r = o - static_cast<size_t>(off) * B;           // = (t * B + b) * dim + j
+      const size_t tb = r / dim;
+      const int j = static_cast<int>(r - tb * dim);
+      const size_t t = tb / B, b = tb - t * B;
+      store1(dst, o, static_cast<float>(A.masks[b * CATAN_MASK_STRIDE + off + t * dim + j]));
+    }
+  }
 }
 
 }  // namespace catanb
@@ -383,4 +476,20 @@ extern "C" int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t*
   catanb::route_kernel<<<n_policies, 1024, 0, static_cast<cudaStream_t>(stream)>>>(A);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : ppo_fail(e, "catan_route_by_policy launch");
+}
+
+extern "C" int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_dev, int B, int dtype, void* features_dev,
+                                   int64_t* lists_dev, void* head_masks_dev, void* stream) {
+  if (!obs_rows_dev || !features_dev || !lists_dev || B <= 0 || (dtype != CATAN_DTYPE_F32 && dtype != CATAN_DTYPE_BF16) ||
+      (mask_rows_dev == nullptr) != (head_masks_dev == nullptr))
+    return ppo_fail(cudaErrorInvalidValue, "catan_policy_inputs: bad argument");
+  catanb::PolicyInArgs A;
+  A.obs = obs_rows_dev; A.masks = mask_rows_dev; A.features = features_dev; A.lists = reinterpret_cast<long long*>(lists_dev);
+  A.head_masks = head_masks_dev; A.B = B;
+  const long long groups = static_cast<long long>(B) * (CATAN_POLICY_FEATURE_STRIDE / 4);
+  const int blocks = static_cast<int>(groups + 255 < 256LL * 148 * 8 ? (groups + 255) / 256 : 148 * 8);   // grid-stride, 8 blocks per SM
+  if (dtype == CATAN_DTYPE_F32) catanb::policy_inputs_kernel<float><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  else catanb::policy_inputs_kernel<__nv_bfloat16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : ppo_fail(e, "catan_policy_inputs launch");
 }

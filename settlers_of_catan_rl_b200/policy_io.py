@@ -1,0 +1,94 @@
+"""Hand-off between the packed env rows and the reference's policy network.
+
+The reference converts every observation dict and mask list to torch tensors on the host, env by env
+(``SettlersAgentPolicy.obs_to_torch`` / ``act_masks_to_torch``, RL/models/policy.py:168-190), stacks them per key
+(RL/ppo/process_batch.py:43-51, :80-84) and turns the sampled heads back into numpy for ``env.step``
+(``torch_act_to_np``, policy.py:192-199).  Here one kernel launch (``catan_policy_inputs``) expands a batch of packed
+uint8 rows — the env's own buffers, a routed subset, or a gathered minibatch — into exactly the tensors
+``SettlersAgentPolicy.act / evaluate_actions / get_value`` take, and the sampled heads go back into the int32 [B, 20]
+action rows that ``VecCatanEnv.step`` reads, without leaving the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, layout as L
+
+FEATURE_STRIDE = 1792           # CATAN_POLICY_FEATURE_STRIDE
+TYPE_CONDITIONAL_HEADS = (1, 6, 9)   # policy.py:188-189
+_DTYPES = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class PolicyInputs:
+    """Pre-allocated device buffers for batches of up to ``capacity`` rows; ``__call__`` fills them with one launch and returns
+    ``(obs_dict, action_masks)`` as views: ``obs_dict[key]`` is ``[B, ...]`` of ``dtype`` for the numeric keys and int64
+    ``[B, 25]`` for the five card lists (the padded-tensor form of player_modules.py:49-53); ``action_masks`` is the list of 12
+    with heads 1 / 6 / 9 as ``[types, B, dim]``."""
+
+    def __init__(self, capacity: int, device="cuda:0", dtype: torch.dtype = torch.float32):
+        if dtype not in _DTYPES:
+            raise ValueError("policy inputs are produced in float32 or bfloat16")
+        self.lib = _lib.load()
+        self.capacity, self.dtype, self.device = int(capacity), dtype, torch.device(device)
+        self.features = torch.empty((self.capacity, FEATURE_STRIDE), dtype=dtype, device=self.device)
+        self.lists = torch.empty(5 * self.capacity * L.OBS_DEV_PAD, dtype=torch.int64, device=self.device)
+        self.head_masks = torch.empty(L.MASK_ENTRIES * self.capacity, dtype=dtype, device=self.device)
+        self.kernel_launches = 0
+
+    def __call__(self, obs_rows: torch.Tensor, mask_rows: Optional[torch.Tensor] = None) -> Tuple[Dict[str, torch.Tensor], Optional[List[torch.Tensor]]]:
+        B = obs_rows.shape[0]
+        assert obs_rows.dtype == torch.uint8 and obs_rows.is_cuda and obs_rows.is_contiguous() and obs_rows.shape == (B, L.OBS_STRIDE)
+        assert 0 < B <= self.capacity
+        if mask_rows is not None:
+            assert mask_rows.dtype == torch.uint8 and mask_rows.is_cuda and mask_rows.is_contiguous() and mask_rows.shape == (B, L.MASK_STRIDE)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.catan_policy_inputs(_p(obs_rows), _p(mask_rows), B, _DTYPES[self.dtype], _p(self.features), _p(self.lists),
+                                                _p(self.head_masks) if mask_rows is not None else C.c_void_p(0), stream))
+        self.kernel_launches += 1
+        f = self.features[:B]
+        obs = {}
+        for key, off, shape in L.OBS_NUMERIC:
+            obs[key] = f[:, off:off + int(np.prod(shape))].view(B, *shape)
+        lists = self.lists[:5 * B * L.OBS_DEV_PAD].view(5, B, L.OBS_DEV_PAD)
+        for key, li in L.OBS_LISTS:
+            obs[key] = lists[li]
+        if mask_rows is None:
+            return obs, None
+        masks = []
+        for h, (off, shape) in enumerate(L.MASK_HEADS):
+            flat = self.head_masks[off * B:(off + int(np.prod(shape))) * B]
+            masks.append(flat.view(shape[0], B, shape[1]) if h in TYPE_CONDITIONAL_HEADS else flat.view(B, shape[0]))
+        return obs, masks
+
+
+def actions_to_rows(actions: Sequence, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The 12 sampled heads of ``policy.act`` (``[B, 1]`` long tensors; heads 7 / 8 a list of four of them, or ``[B, 4]``) ->
+    int32 ``[B, 20]`` action rows (catan_layout.h; policy.py:192-199 + wrapper.py:114-166 read them in this order)."""
+    cols = []
+    for h in range(12):
+        a = actions[h]
+        if isinstance(a, (list, tuple)):
+            a = torch.cat([x.reshape(-1, 1) for x in a], dim=1)
+        cols.append(a.reshape(a.shape[0], -1))
+    assert [c.shape[1] for c in cols] == [1] * 7 + [4, 4] + [1] * 3
+    B = cols[0].shape[0]
+    if out is None:
+        out = torch.zeros((B, L.ACTION_WORDS), dtype=torch.int32, device=cols[0].device)
+    out[:, :18] = torch.cat(cols, dim=1)
+    return out
+
+
+def rows_to_actions(action_rows: torch.Tensor) -> List[torch.Tensor]:
+    """int32 ``[B, 20]`` action rows -> the list of 12 long tensors ``evaluate_actions`` takes (``[B, 1]``; heads 7 / 8
+    ``[B, 4]``: process_batch.py:67-75)."""
+    a = action_rows.long()
+    return [a[:, h:h + 1] for h in range(7)] + [a[:, L.A_GIVE:L.A_GIVE + 4], a[:, L.A_RECV:L.A_RECV + 4]] + \
+           [a[:, L.A_RES_A:L.A_RES_A + 1], a[:, L.A_RES_B:L.A_RES_B + 1], a[:, L.A_DISCARD:L.A_DISCARD + 1]]
