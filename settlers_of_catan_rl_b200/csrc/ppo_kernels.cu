@@ -99,13 +99,24 @@ struct PolicyInArgs {
   void* features;             // [B][CATAN_POLICY_FEATURE_STRIDE]
   long long* lists;           // [5][B][CATAN_OBS_DEV_PAD]
   void* head_masks;           // [CATAN_MASK_ENTRIES * B] or null
-  int B;
+  unsigned B;
+  unsigned long long magic_B; // 2^64 / B + 1: n / B = umul64hi(n, magic_B) for every 32-bit n (B > 1)
 };
 
+#define CATAN_DIV_MAGIC(d) (0xFFFFFFFFFFFFFFFFull / (d) + 1ull)
 __constant__ int c_head_off[13] = {CATAN_MASK_TYPE, CATAN_MASK_CORNER, CATAN_MASK_EDGE, CATAN_MASK_TILE, CATAN_MASK_DEV,
                                    CATAN_MASK_ACCEPT, CATAN_MASK_PLAYER, CATAN_MASK_GIVE, CATAN_MASK_RECV, CATAN_MASK_RES_A,
                                    CATAN_MASK_RES_B, CATAN_MASK_DISCARD, CATAN_MASK_ENTRIES};
-__constant__ int c_head_dim[12] = {13, 54, 73, 19, 5, 2, 3, 6, 6, 5, 5, 5};   // last dimension; types = (off[h+1] - off[h]) / dim
+// last dimension of every head; types = (off[h + 1] - off[h]) / dim (3 for the corner and player heads, 4 for resource A)
+__constant__ int c_head_dim[13] = {13, 54, 73, 19, 5, 2, 3, 6, 6, 5, 5, 5, 1};
+__constant__ unsigned long long c_head_magic[13] = {
+    CATAN_DIV_MAGIC(13), CATAN_DIV_MAGIC(54), CATAN_DIV_MAGIC(73), CATAN_DIV_MAGIC(19), CATAN_DIV_MAGIC(5), CATAN_DIV_MAGIC(2),
+    CATAN_DIV_MAGIC(3),  CATAN_DIV_MAGIC(6),  CATAN_DIV_MAGIC(6),  CATAN_DIV_MAGIC(5),  CATAN_DIV_MAGIC(5), CATAN_DIV_MAGIC(5), 0};
+
+__device__ __forceinline__ unsigned div_magic(unsigned n, unsigned long long magic) {
+  return static_cast<unsigned>(__umul64hi(static_cast<unsigned long long>(n), magic));
+}
+__device__ __forceinline__ unsigned div_B(unsigned n, const PolicyInArgs& A) { return A.B == 1 ? n : div_magic(n, A.magic_B); }
 
 __device__ __forceinline__ float ratio_scale(int col) {
   if (col < CATAN_OBS_CUR_MAIN) return 1.0f;
@@ -114,63 +125,107 @@ __device__ __forceinline__ float ratio_scale(int col) {
   return r == 0 ? 0.125f : r == 2 ? 0.25f : 1.0f;                  // wrapper.py:613-627: len / 8.0, knights / 4.0
 }
 
-__device__ __forceinline__ void store4(float* p, size_t i4, float a, float b, float c, float d) {
-  __stcs(reinterpret_cast<float4*>(p) + i4, make_float4(a, b, c, d));
+__device__ __forceinline__ void store4(float* p, size_t i4, const float* v) {
+  __stcs(reinterpret_cast<float4*>(p) + i4, make_float4(v[0], v[1], v[2], v[3]));
 }
-__device__ __forceinline__ void store4(__nv_bfloat16* p, size_t i4, float a, float b, float c, float d) {
-  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-  uint2 v;
-  v.x = *reinterpret_cast<const unsigned*>(&lo);
-  v.y = *reinterpret_cast<const unsigned*>(&hi);
-  __stcs(reinterpret_cast<uint2*>(p) + i4, v);
+__device__ __forceinline__ void store4(__nv_bfloat16* p, size_t i4, const float* v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<const unsigned*>(&lo);
+  u.y = *reinterpret_cast<const unsigned*>(&hi);
+  __stcs(reinterpret_cast<uint2*>(p) + i4, u);
 }
-__device__ __forceinline__ void store1(float* p, size_t i, float a) { __stcs(p + i, a); }
+__device__ __forceinline__ void store1(float* p, size_t i, float a) { p[i] = a; }
 __device__ __forceinline__ void store1(__nv_bfloat16* p, size_t i, float a) { p[i] = __float2bfloat16_rn(a); }
 
+// Every thread keeps four independent loads in flight per loop trip (the kernel is a pure stream: without that it is bound
+// by one DRAM latency per trip), all index arithmetic is 32-bit with multiply-high divisions, every store is a 16-byte
+// (8-byte for bf16 quads) vector that the warp writes contiguously.
 template <typename T>
 __global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constant__ PolicyInArgs A) {
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t B = static_cast<size_t>(A.B);
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned B = A.B;
   {  // numeric features: one 4-byte load -> one 16-byte (fp32) / 8-byte (bf16) store
-    constexpr int G = CATAN_POLICY_FEATURE_STRIDE / 4;
+    constexpr unsigned G = CATAN_POLICY_FEATURE_STRIDE / 4;
     const unsigned* src = reinterpret_cast<const unsigned*>(A.obs);
     T* dst = static_cast<T*>(A.features);
-    for (size_t g = tid; g < B * G; g += stride) {
-      const size_t row = g / G;
-      const int c4 = static_cast<int>(g - row * G), col = c4 * 4;
-      const unsigned w = __ldcs(src + row * (CATAN_OBS_STRIDE / 4) + c4);
-      float v[4];
+    const unsigned total = B * G;
+    for (unsigned g0 = tid; g0 < total; g0 += 4 * stride) {
+      unsigned w[4], col[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = col + k < CATAN_OBS_FEATURES ? static_cast<float>((w >> (8 * k)) & 0xffu) : 0.0f;
-      if (col >= CATAN_OBS_CUR_MAIN) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] *= ratio_scale(col + k);
+      for (int u = 0; u < 4; ++u) {
+        const unsigned g = g0 + u * stride;
+        if (g < total) {
+          const unsigned row = g / G, c4 = g - row * G;
+          col[u] = c4 * 4;
+          w[u] = __ldcs(src + static_cast<size_t>(row) * (CATAN_OBS_STRIDE / 4) + c4);
+        }
       }
-      store4(dst, g, v[0], v[1], v[2], v[3]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned g = g0 + u * stride;
+        if (g < total) {
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            v[k] = col[u] + k < CATAN_OBS_FEATURES ? static_cast<float>((w[u] >> (8 * k)) & 0xffu) : 0.0f;
+          if (col[u] + 3 >= CATAN_OBS_CUR_MAIN) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] *= ratio_scale(static_cast<int>(col[u]) + k);
+          }
+          store4(dst, g, v);
+        }
+      }
     }
   }
-  {  // development-card lists: byte -> int64
-    constexpr int L = 5 * CATAN_OBS_DEV_PAD;
-    for (size_t i = tid; i < B * L; i += stride) {
-      const size_t li = i / (B * CATAN_OBS_DEV_PAD), rem = i - li * B * CATAN_OBS_DEV_PAD;
-      const size_t b = rem / CATAN_OBS_DEV_PAD, j = rem - b * CATAN_OBS_DEV_PAD;
-      __stcs(A.lists + i, static_cast<long long>(A.obs[b * CATAN_OBS_STRIDE + CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD + j]));
+  {  // development-card lists: four bytes -> four int64 (two 16-byte stores); flat index i = (li * B + b) * 25 + j
+    const unsigned total = 5 * CATAN_OBS_DEV_PAD * B;
+    for (unsigned i0 = tid * 4; i0 < total; i0 += stride * 4) {
+      const unsigned q = i0 / CATAN_OBS_DEV_PAD;
+      unsigned j = i0 - q * CATAN_OBS_DEV_PAD, li = div_B(q, A), b = q - li * B;
+      long long v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i0 + k < total) v[k] = A.obs[static_cast<size_t>(b) * CATAN_OBS_STRIDE + CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD + j];
+        if (++j == CATAN_OBS_DEV_PAD) { j = 0; if (++b == B) { b = 0; ++li; } }
+      }
+      if (i0 + 3 < total) {
+        __stcs(reinterpret_cast<longlong2*>(A.lists + i0), make_longlong2(v[0], v[1]));
+        __stcs(reinterpret_cast<longlong2*>(A.lists + i0) + 1, make_longlong2(v[2], v[3]));
+      } else {
+        for (int k = 0; k < 4; ++k) if (i0 + k < total) A.lists[i0 + k] = v[k];
+      }
     }
   }
-  if (A.masks != nullptr && A.head_masks != nullptr) {  // masks: head-major, type-conditional heads as [types][B][dim]
+  if (A.masks != nullptr && A.head_masks != nullptr) {
+    // masks, head-major: head h owns output elements [off[h] * B, off[h + 1] * B), element (t * B + b) * dim + j of it is
+    // mask byte off[h] + t * dim + j of row b.  A thread decomposes its first element and walks on from there.
     T* dst = static_cast<T*>(A.head_masks);
-    for (size_t o = tid; o < B * CATAN_MASK_ENTRIES; o += stride) {
-      const int col = static_cast<int>(o / B);                     // head h owns elements [off[h] * B, off[h + 1] * B)
+    const unsigned total = CATAN_MASK_ENTRIES * B;
+    for (unsigned o0 = tid * 4; o0 < total; o0 += stride * 4) {
+      const unsigned c = div_B(o0, A);
       int h = 0;
 #pragma unroll
-      for (int k = 1; k < 12; ++k) h += col >= c_head_off[k];
-      const int off = c_head_off[h], dim = c_head_dim[h];
-      const size_t r = o - static_cast<size_t>(off) * B;           // = (t * B + b) * dim + j
-      const size_t tb = r / dim;
-      const int j = static_cast<int>(r - tb * dim);
-      const size_t t = tb / B, b = tb - t * B;
-      store1(dst, o, static_cast<float>(A.masks[b * CATAN_MASK_STRIDE + off + t * dim + j]));
+      for (int k = 1; k < 12; ++k) h += c >= static_cast<unsigned>(c_head_off[k]);
+      unsigned off = c_head_off[h], dim = c_head_dim[h];
+      const unsigned r = o0 - off * B, tb = div_magic(r, c_head_magic[h]);
+      unsigned j = r - tb * dim, t = div_B(tb, A), b = tb - t * B;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (o0 + k >= total) continue;
+        v[k] = static_cast<float>(A.masks[static_cast<size_t>(b) * CATAN_MASK_STRIDE + off + t * dim + j]);
+        if (++j == dim) {
+          j = 0;
+          if (++b == B) {
+            b = 0; ++t;
+            if (off + t * dim >= static_cast<unsigned>(c_head_off[h + 1])) { ++h; off = c_head_off[h]; dim = c_head_dim[h]; t = 0; }
+          }
+        }
+      }
+      if (o0 + 3 < total) store4(dst, o0 >> 2, v);
+      else for (int k = 0; k < 4; ++k) if (o0 + k < total) store1(dst, o0 + k, v[k]);
     }
   }
 }
@@ -480,12 +535,13 @@ extern "C" int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t*
 
 extern "C" int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_dev, int B, int dtype, void* features_dev,
                                    int64_t* lists_dev, void* head_masks_dev, void* stream) {
-  if (!obs_rows_dev || !features_dev || !lists_dev || B <= 0 || (dtype != CATAN_DTYPE_F32 && dtype != CATAN_DTYPE_BF16) ||
+  if (!obs_rows_dev || !features_dev || !lists_dev || B <= 0 || B > (1 << 22) || (dtype != CATAN_DTYPE_F32 && dtype != CATAN_DTYPE_BF16) ||
       (mask_rows_dev == nullptr) != (head_masks_dev == nullptr))
     return ppo_fail(cudaErrorInvalidValue, "catan_policy_inputs: bad argument");
   catanb::PolicyInArgs A;
   A.obs = obs_rows_dev; A.masks = mask_rows_dev; A.features = features_dev; A.lists = reinterpret_cast<long long*>(lists_dev);
-  A.head_masks = head_masks_dev; A.B = B;
+  A.head_masks = head_masks_dev; A.B = static_cast<unsigned>(B);
+  A.magic_B = 0xFFFFFFFFFFFFFFFFull / static_cast<unsigned>(B) + 1ull;
   const long long groups = static_cast<long long>(B) * (CATAN_POLICY_FEATURE_STRIDE / 4);
   const int blocks = static_cast<int>(groups + 255 < 256LL * 148 * 8 ? (groups + 255) / 256 : 148 * 8);   // grid-stride, 8 blocks per SM
   if (dtype == CATAN_DTYPE_F32) catanb::policy_inputs_kernel<float><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);

@@ -42,6 +42,7 @@ class PolicyInputs:
         self.lists = torch.empty(5 * self.capacity * L.OBS_DEV_PAD, dtype=torch.int64, device=self.device)
         self.head_masks = torch.empty(L.MASK_ENTRIES * self.capacity, dtype=dtype, device=self.device)
         self.kernel_launches = 0
+        self._view_cache = {}
 
     def __call__(self, obs_rows: torch.Tensor, mask_rows: Optional[torch.Tensor] = None) -> Tuple[Dict[str, torch.Tensor], Optional[List[torch.Tensor]]]:
         B = obs_rows.shape[0]
@@ -53,6 +54,13 @@ class PolicyInputs:
         _lib.check(self.lib.catan_policy_inputs(_p(obs_rows), _p(mask_rows), B, _DTYPES[self.dtype], _p(self.features), _p(self.lists),
                                                 _p(self.head_masks) if mask_rows is not None else C.c_void_p(0), stream))
         self.kernel_launches += 1
+        return self._views(B, mask_rows is not None)
+
+    def _views(self, B: int, with_masks: bool):
+        """the views of a batch size are built once: a call costs one launch, not two dozen tensor constructions"""
+        hit = self._view_cache.get((B, with_masks))
+        if hit is not None:
+            return hit
         f = self.features[:B]
         obs = {}
         for key, off, shape in L.OBS_NUMERIC:
@@ -60,12 +68,14 @@ class PolicyInputs:
         lists = self.lists[:5 * B * L.OBS_DEV_PAD].view(5, B, L.OBS_DEV_PAD)
         for key, li in L.OBS_LISTS:
             obs[key] = lists[li]
-        if mask_rows is None:
-            return obs, None
-        masks = []
-        for h, (off, shape) in enumerate(L.MASK_HEADS):
-            flat = self.head_masks[off * B:(off + int(np.prod(shape))) * B]
-            masks.append(flat.view(shape[0], B, shape[1]) if h in TYPE_CONDITIONAL_HEADS else flat.view(B, shape[0]))
+        masks = None
+        if with_masks:
+            masks = []
+            for h, (off, shape) in enumerate(L.MASK_HEADS):
+                flat = self.head_masks[off * B:(off + int(np.prod(shape))) * B]
+                masks.append(flat.view(shape[0], B, shape[1]) if h in TYPE_CONDITIONAL_HEADS else flat.view(B, shape[0]))
+        if len(self._view_cache) < 64:
+            self._view_cache[(B, with_masks)] = (obs, masks)
         return obs, masks
 
 
