@@ -173,11 +173,13 @@ int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t* policy_map
  *   lists_dev      int64 [5][B][CATAN_OBS_DEV_PAD]: padded development-card lists (card + 1, 0 = pad), list order as in the row;
  *   head_masks_dev dtype [CATAN_MASK_ENTRIES * B]: head h starts at element CATAN_MASK_<h> * B and is [B][dim], except the
  *                  type-conditional heads 1 (corner), 6 (player), 9 (resource A), which are [types][B][dim].
- * mask_rows_dev and head_masks_dev may both be NULL (value-only pass, policy.py:108-110 get_value). */
+ * mask_rows_dev and head_masks_dev may both be NULL (value-only pass, policy.py:108-110 get_value).  row_index_dev int32[B] or
+ * NULL: batch row b is read from row row_index_dev[b] of the two row buffers — one policy's env list from
+ * catan_route_by_policy, so that the per-seat policies of game_manager.py:82-93 each get their batch without a gather pass. */
 #define CATAN_POLICY_FEATURE_STRIDE 1792
 #define CATAN_DTYPE_F32 0
 #define CATAN_DTYPE_BF16 1
-int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_dev, int B, int dtype, void* features_dev,
+int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_dev, const int32_t* row_index_dev, int B, int dtype, void* features_dev,
                         int64_t* lists_dev, void* head_masks_dev, void* stream);
 
 /* ---- minibatch generator (RL/ppo/process_batch.py:169-200, generator_standard) --------------------

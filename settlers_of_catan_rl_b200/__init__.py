@@ -7,7 +7,7 @@ lazily; there is no CPU implementation.
 """
 from . import layout  # noqa: F401
 
-__all__ = ["layout", "VecCatanEnv", "EnvWrapper", "gae", "normalise_advantages", "RolloutStorage"]
+__all__ = ["layout", "VecCatanEnv", "EnvWrapper", "gae", "normalise_advantages", "RolloutStorage", "PolicyInputs", "SeatPolicies"]
 
 
 def __getattr__(name):
@@ -20,4 +20,10 @@ def __getattr__(name):
     if name in ("gae", "normalise_advantages", "RolloutStorage"):
         from . import rollout
         return getattr(rollout, name)
+    if name == "PolicyInputs":
+        from .policy_io import PolicyInputs
+        return PolicyInputs
+    if name == "SeatPolicies":
+        from .self_play import SeatPolicies
+        return SeatPolicies
     raise AttributeError(name)

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) adv_apply_kernel(float* __restrict__ a, l
 struct PolicyInArgs {
   const uint8_t* obs;         // [B][CATAN_OBS_STRIDE]
   const uint8_t* masks;       // [B][CATAN_MASK_STRIDE] or null
+  const int32_t* index;       // [B] or null: batch row b is row index[b] of obs / masks (the env list of one policy)
   void* features;             // [B][CATAN_POLICY_FEATURE_STRIDE]
   long long* lists;           // [5][B][CATAN_OBS_DEV_PAD]
   void* head_masks;           // [CATAN_MASK_ENTRIES * B] or null
@@ -117,6 +118,7 @@ __device__ __forceinline__ unsigned div_magic(unsigned n, unsigned long long mag
   return static_cast<unsigned>(__umul64hi(static_cast<unsigned long long>(n), magic));
 }
 __device__ __forceinline__ unsigned div_B(unsigned n, const PolicyInArgs& A) { return A.B == 1 ? n : div_magic(n, A.magic_B); }
+__device__ __forceinline__ size_t src_row(unsigned b, const PolicyInArgs& A) { return A.index == nullptr ? b : static_cast<size_t>(__ldg(A.index + b)); }
 
 __device__ __forceinline__ float ratio_scale(int col) {
   if (col < CATAN_OBS_CUR_MAIN) return 1.0f;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constan
         if (g < total) {
           const unsigned row = g / G, c4 = g - row * G;
           col[u] = c4 * 4;
-          w[u] = __ldcs(src + static_cast<size_t>(row) * (CATAN_OBS_STRIDE / 4) + c4);
+          w[u] = __ldcs(src + src_row(row, A) * (CATAN_OBS_STRIDE / 4) + c4);
         }
       }
 #pragma unroll
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constan
       long long v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (i0 + k < total) v[k] = A.obs[static_cast<size_t>(b) * CATAN_OBS_STRIDE + CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD + j];
+        if (i0 + k < total) v[k] = A.obs[src_row(b, A) * CATAN_OBS_STRIDE + CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD + j];
         if (++j == CATAN_OBS_DEV_PAD) { j = 0; if (++b == B) { b = 0; ++li; } }
       }
       if (i0 + 3 < total) {
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constan
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (o0 + k >= total) continue;
-        v[k] = static_cast<float>(A.masks[static_cast<size_t>(b) * CATAN_MASK_STRIDE + off + t * dim + j]);
+        v[k] = static_cast<float>(A.masks[src_row(b, A) * CATAN_MASK_STRIDE + off + t * dim + j]);
         if (++j == dim) {
           j = 0;
           if (++b == B) {
@@ -533,13 +535,13 @@ extern "C" int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t*
   return e == cudaSuccess ? 0 : ppo_fail(e, "catan_route_by_policy launch");
 }
 
-extern "C" int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_dev, int B, int dtype, void* features_dev,
+extern "C" int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_dev, const int32_t* row_index_dev, int B, int dtype, void* features_dev,
                                    int64_t* lists_dev, void* head_masks_dev, void* stream) {
   if (!obs_rows_dev || !features_dev || !lists_dev || B <= 0 || B > (1 << 22) || (dtype != CATAN_DTYPE_F32 && dtype != CATAN_DTYPE_BF16) ||
       (mask_rows_dev == nullptr) != (head_masks_dev == nullptr))
     return ppo_fail(cudaErrorInvalidValue, "catan_policy_inputs: bad argument");
   catanb::PolicyInArgs A;
-  A.obs = obs_rows_dev; A.masks = mask_rows_dev; A.features = features_dev; A.lists = reinterpret_cast<long long*>(lists_dev);
+  A.obs = obs_rows_dev; A.masks = mask_rows_dev; A.index = row_index_dev; A.features = features_dev; A.lists = reinterpret_cast<long long*>(lists_dev);
   A.head_masks = head_masks_dev; A.B = static_cast<unsigned>(B);
   A.magic_B = 0xFFFFFFFFFFFFFFFFull / static_cast<unsigned>(B) + 1ull;
   const long long groups = static_cast<long long>(B) * (CATAN_POLICY_FEATURE_STRIDE / 4);

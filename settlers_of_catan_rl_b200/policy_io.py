@@ -44,14 +44,21 @@ class PolicyInputs:
         self.kernel_launches = 0
         self._view_cache = {}
 
-    def __call__(self, obs_rows: torch.Tensor, mask_rows: Optional[torch.Tensor] = None) -> Tuple[Dict[str, torch.Tensor], Optional[List[torch.Tensor]]]:
-        B = obs_rows.shape[0]
-        assert obs_rows.dtype == torch.uint8 and obs_rows.is_cuda and obs_rows.is_contiguous() and obs_rows.shape == (B, L.OBS_STRIDE)
-        assert 0 < B <= self.capacity
+    def __call__(self, obs_rows: torch.Tensor, mask_rows: Optional[torch.Tensor] = None,
+                 index: Optional[torch.Tensor] = None) -> Tuple[Dict[str, torch.Tensor], Optional[List[torch.Tensor]]]:
+        """``index`` (int32 [B], optional): batch row b is row ``index[b]`` of ``obs_rows`` / ``mask_rows`` (one policy's env
+        list from ``VecCatanEnv.route_by_policy``); without it the batch is all the rows."""
+        R = obs_rows.shape[0]
+        assert obs_rows.dtype == torch.uint8 and obs_rows.is_cuda and obs_rows.is_contiguous() and obs_rows.shape == (R, L.OBS_STRIDE)
         if mask_rows is not None:
-            assert mask_rows.dtype == torch.uint8 and mask_rows.is_cuda and mask_rows.is_contiguous() and mask_rows.shape == (B, L.MASK_STRIDE)
+            assert mask_rows.dtype == torch.uint8 and mask_rows.is_cuda and mask_rows.is_contiguous() and mask_rows.shape == (R, L.MASK_STRIDE)
+        B = R
+        if index is not None:
+            assert index.dtype == torch.int32 and index.is_cuda and index.is_contiguous() and index.dim() == 1
+            B = index.shape[0]
+        assert 0 < B <= self.capacity
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(self.lib.catan_policy_inputs(_p(obs_rows), _p(mask_rows), B, _DTYPES[self.dtype], _p(self.features), _p(self.lists),
+        _lib.check(self.lib.catan_policy_inputs(_p(obs_rows), _p(mask_rows), _p(index), B, _DTYPES[self.dtype], _p(self.features), _p(self.lists),
                                                 _p(self.head_masks) if mask_rows is not None else C.c_void_p(0), stream))
         self.kernel_launches += 1
         return self._views(B, mask_rows is not None)
