@@ -258,6 +258,59 @@ def run_b200_arm(args):
 
     e2e_value = time_e2e(False, e2e_steps * 10)
     e2e_full = time_e2e(True, e2e_steps)
+
+    # ---- e2e, double-buffered: the same per-step traffic (actions H2D from pinned memory, reward + done/info rows and the
+    # sampler's actions D2H to pinned memory, every step, for every game), with the games split over TWO handles on two
+    # streams (catan_step_host_async): while the host waits for one half's result, the other half's kernels and copies run.
+    # This is how a host-side policy loop drives the library (the reference's sub-process manager also keeps several env
+    # groups in flight, RL/ppo/vec_gather_experience.py); each half's step still depends on that half's previous result.
+    def time_e2e_pipelined(steps, warm_ticks):
+        half = n // 2
+        groups = []
+        for gi in range(2):
+            e = VecCatanEnv(half, device=dev, seed=args.seed, first_env_id=rank * n + gi * half)
+            e.reset()
+            a = e.sample_random()
+            for _ in range(warm_ticks):
+                e.step_sample(a)
+            g = {"env": e, "stream": torch.cuda.Stream(device=dev), "d_act": a,
+                 "h_act": torch.empty((half, L.ACTION_WORDS), dtype=torch.int32).pin_memory(),
+                 "h_rew": torch.empty((half, 4), dtype=torch.float32).pin_memory(),
+                 "h_info": torch.empty((half, L.INFO_STRIDE), dtype=torch.uint8).pin_memory()}
+            g["np"] = (g["h_act"].numpy(), g["h_rew"].numpy(), g["h_info"].numpy())
+            groups.append(g)
+        torch.cuda.synchronize()
+
+        def issue(g, step):
+            with torch.cuda.stream(g["stream"]):
+                if step:
+                    g["env"].step_host_async(g["np"][0], None, None, g["np"][1], g["np"][2])
+                g["env"].sample_random(g["d_act"])                 # stand-in for the policy, as in e2e_tick
+                g["h_act"].copy_(g["d_act"], non_blocking=True)
+
+        for g in groups:
+            issue(g, False)
+        done_rows = 0
+        t0 = 0.0
+        for it in range(3 + steps):
+            if it == 3:
+                barrier()
+                t0 = time.perf_counter()
+            for g in groups:
+                g["stream"].synchronize()                          # this half's result (and next actions) are on the host
+                done_rows += int(g["np"][2][0, L.INFO_DONE])       # touch the result
+                issue(g, True)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        launches_e2e = sum(g["env"].kernel_launches for g in groups)
+        errs_e2e = int(sum(int(g["env"].err_flags().any()) for g in groups))
+        for g in groups:
+            g["env"].close()
+        return 2 * half * world * steps / float(te.item()), errs_e2e
+
+    e2e_pipe, e2e_pipe_errs = time_e2e_pipelined(e2e_steps * 10, min(1000, max(3, args.warmup) + args.steps))
     h2d = n * L.ACTION_WORDS * 4
     d2h = n * (16 + L.INFO_STRIDE) + n * L.ACTION_WORDS * 4
     d2h_full = d2h + n * (L.OBS_STRIDE + L.MASK_STRIDE)
@@ -334,6 +387,15 @@ def run_b200_arm(args):
         rate, threads, sample = cpu_rollout_rate(args.cpu_seconds, seed=args.seed)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
+    e2e_sync = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
+                "call": "VecCatanEnv.step_host -> catan_step_host, one handle: pinned host actions in, reward+done/info rows out to "
+                        "pinned host, synchronous; obs/masks stay in HBM for the GPU policy (d2h also counts the sampler's actions)"}
+    e2e_db = {"value": e2e_pipe, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
+              "rejected_actions": e2e_pipe_errs,
+              "call": "VecCatanEnv.step_host_async -> catan_step_host_async, double-buffered: the games split over two handles on two "
+                      "streams, every step of every game still takes its actions from pinned host memory and returns reward+done/info "
+                      "rows (and the sampler's next actions) to pinned host memory; the host waits for one half while the other runs"}
+    e2e_best, e2e_other = (e2e_db, e2e_sync) if e2e_pipe >= e2e_value else (e2e_sync, e2e_db)
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -361,10 +423,8 @@ def run_b200_arm(args):
                            n * (2 * 832 + L.OBS_STRIDE + L.MASK_STRIDE + 160 + 32) / 1e6),
                        "games_finished_in_last_step": games_done, "rejected_actions": errs},
             "clocks": clock_info,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps * 10,
-                    "call": "VecCatanEnv.step_host -> catan_step_host: pinned host actions in, reward+done/info rows out to pinned "
-                            "host, synchronous; obs/masks stay in HBM for the GPU policy (d2h also counts the sampler's actions)"},
+            "e2e": e2e_best,
+            "e2e_other": e2e_other,
             "e2e_full_obs_to_host": {"value": e2e_full, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
                                      "steps": e2e_steps, "call": "same call with obs+masks rows also copied to pinned host (PCIe-bound)"},
             "gpu_launches": launches,

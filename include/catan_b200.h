@@ -86,6 +86,12 @@ int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream);
  * This is the call an EnvWrapper-shaped Python adapter makes. */
 int catan_step_host(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host,
                     float* reward_host, uint8_t* info_host, void* stream);
+/* The same call without the final synchronisation (the copies are enqueued on `stream`; the host buffers must be pinned and
+ * hold the step's result once the caller has synchronised the stream).  With the games split over two handles on two streams
+ * (the double-buffered env groups of a sub-process manager, RL/ppo/vec_gather_experience.py), one half's PCIe copies overlap
+ * the other half's kernels. */
+int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host,
+                          float* reward_host, uint8_t* info_host, void* stream);
 int catan_reset_host(catan_env_t* env, uint8_t* obs_host, uint8_t* masks_host, uint8_t* info_host, void* stream);
 
 /* EnvWrapper.save_state / restore_state (env/wrapper.py:711-721; game/game.py:1013-1205) as the

@@ -9,7 +9,8 @@ from settlers_of_catan_rl_b200 import layout as L  # noqa: E402
 from settlers_of_catan_rl_b200.policy_io import PolicyInputs  # noqa: E402
 
 out = {}
-for n in (16384, 65536, 131072):
+sizes = tuple(int(a) for a in sys.argv[1:]) or (16384, 65536, 131072)
+for n in sizes:
     obs = torch.randint(0, 12, (n, L.OBS_STRIDE), dtype=torch.uint8, device="cuda")
     masks = torch.randint(0, 2, (n, L.MASK_STRIDE), dtype=torch.uint8, device="cuda")
     for dt, name, nbytes in ((torch.float32, "f32", 2256 + 1792 * 4 + 1000 + 325 * 4), (torch.bfloat16, "bf16", 2256 + 1792 * 2 + 1000 + 325 * 2)):

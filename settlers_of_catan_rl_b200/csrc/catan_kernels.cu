@@ -830,14 +830,29 @@ int catan_sample_random(catan_env_t* env, int32_t* actions_out_dev, void* stream
 }
 
 static int copy_outputs_to_host(catan_env_t* env, uint8_t* obs_host, uint8_t* masks_host, float* reward_host, uint8_t* info_host,
-                                cudaStream_t s) {
+                                cudaStream_t s, bool sync = true) {
   const size_t n = static_cast<size_t>(env->n);
   if (obs_host) CATAN_CUDA(cudaMemcpyAsync(obs_host, env->obs, n * CATAN_OBS_STRIDE, cudaMemcpyDeviceToHost, s));
   if (masks_host) CATAN_CUDA(cudaMemcpyAsync(masks_host, env->masks, n * CATAN_MASK_STRIDE, cudaMemcpyDeviceToHost, s));
   if (reward_host) CATAN_CUDA(cudaMemcpyAsync(reward_host, env->reward, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (info_host) CATAN_CUDA(cudaMemcpyAsync(info_host, env->info, n * CATAN_INFO_STRIDE, cudaMemcpyDeviceToHost, s));
-  CATAN_CUDA(cudaStreamSynchronize(s));
+  if (sync) CATAN_CUDA(cudaStreamSynchronize(s));
   return 0;
+}
+
+// The same call without the final synchronisation: the host buffers (pinned, or the copies serialise) hold the step's result
+// once `stream` has been synchronised.  Two handles on two streams, each owning half of the games, overlap one half's PCIe
+// copies with the other half's kernels.
+int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host, float* reward_host,
+                          uint8_t* info_host, void* stream) {
+  if (check_bound(env)) return -1;
+  if (!actions_host) return fail("actions_host is null");
+  if (device_guard(env)) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_host, sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(env->n),
+                             cudaMemcpyHostToDevice, s));
+  if (catan_step(env, env->actions_stage, stream)) return -1;
+  return copy_outputs_to_host(env, obs_host, masks_host, reward_host, info_host, s, false);
 }
 
 int catan_step_host(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host, float* reward_host,

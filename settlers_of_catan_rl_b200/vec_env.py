@@ -105,6 +105,16 @@ class VecCatanEnv:
         _lib.check(self.lib.catan_step_host(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
         self.kernel_launches += 6
 
+    def step_host_async(self, actions: np.ndarray, obs: np.ndarray = None, masks: np.ndarray = None, reward: np.ndarray = None,
+                        info: np.ndarray = None) -> None:
+        """``step_host`` without the final synchronisation: every buffer must be pinned; the results are in place once the
+        current stream has been synchronised.  Two envs on two streams overlap one's copies with the other's kernels."""
+        def p(a):
+            return C.c_void_p(0 if a is None else a.ctypes.data)
+        assert actions.dtype == np.int32 and actions.flags.c_contiguous
+        _lib.check(self.lib.catan_step_host_async(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
+        self.kernel_launches += 6
+
     def reset_host(self, obs: np.ndarray = None, masks: np.ndarray = None, info: np.ndarray = None) -> None:
         def p(a):
             return C.c_void_p(0 if a is None else a.ctypes.data)

@@ -94,3 +94,27 @@ def test_a_step_can_be_captured_in_a_cuda_graph():
     assert torch.equal(a.obs, b.obs) and torch.equal(a.masks, b.masks) and torch.equal(acts_a, acts_b)
     assert np.array_equal(a.export_state(), b.export_state())
     assert int(a.lr_stats()[0]) == int(b.lr_stats()[0]) > 0
+
+
+def test_async_host_step_equals_the_synchronous_one():
+    """catan_step_host_async on a side stream + a stream synchronise == catan_step_host (same games, same host buffers)"""
+    from settlers_of_catan_rl_b200 import VecCatanEnv
+    n = 700
+    a, b = VecCatanEnv(n, seed=31), VecCatanEnv(n, seed=31)
+    a.reset(); b.reset()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    bufs = [{"act": pin((n, L.ACTION_WORDS), torch.int32), "obs": pin((n, L.OBS_STRIDE), torch.uint8), "masks": pin((n, L.MASK_STRIDE), torch.uint8),
+             "rew": pin((n, 4), torch.float32), "info": pin((n, L.INFO_STRIDE), torch.uint8)} for _ in range(2)]
+    side = torch.cuda.Stream()
+    for tick in range(120):
+        acts = a.sample_random()
+        torch.cuda.synchronize()
+        for k in range(2):
+            bufs[k]["act"].copy_(acts)
+        a.step_host(*(bufs[0][k].numpy() for k in ("act", "obs", "masks", "rew", "info")))
+        with torch.cuda.stream(side):
+            b.step_host_async(*(bufs[1][k].numpy() for k in ("act", "obs", "masks", "rew", "info")))
+        side.synchronize()
+        for k in ("obs", "masks", "rew", "info"):
+            assert torch.equal(bufs[0][k], bufs[1][k]), (tick, k)
+    assert np.array_equal(a.export_state(), b.export_state())
