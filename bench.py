@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU, help="games per GPU (default: the BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--e2e-groups", type=int, default=6, help="handles (env groups) kept in flight by the double-buffered e2e loop")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
@@ -162,6 +163,58 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # this build
 # ------------------------------------------------------------------------------------------------
+def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_groups=2, barrier=None):
+    import torch
+    from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
+    sizes = [n // n_groups + (1 if gi < n % n_groups else 0) for gi in range(n_groups)]     # sum = n
+    groups = []
+    for gi in range(n_groups):
+        half = sizes[gi]
+        e = VecCatanEnv(half, device=dev, seed=seed, first_env_id=rank * n + sum(sizes[:gi]))
+        e.reset()
+        a = e.sample_random()
+        for _ in range(warm_ticks):
+            e.step_sample(a)
+        g = {"env": e, "stream": torch.cuda.Stream(device=dev), "d_act": a,
+             "h_act": torch.empty((half, L.ACTION_WORDS), dtype=torch.int32).pin_memory(),
+             "h_rew": torch.empty((half, 4), dtype=torch.float32).pin_memory(),
+             "h_info": torch.empty((half, L.INFO_STRIDE), dtype=torch.uint8).pin_memory()}
+        g["np"] = (g["h_act"].numpy(), g["h_rew"].numpy(), g["h_info"].numpy())
+        groups.append(g)
+    torch.cuda.synchronize()
+
+    def issue(g, step):
+        with torch.cuda.stream(g["stream"]):
+            if step:
+                g["env"].step_host_async(g["np"][0], None, None, g["np"][1], g["np"][2])
+            g["env"].sample_random(g["d_act"])                 # stand-in for the policy, as in e2e_tick
+            g["h_act"].copy_(g["d_act"], non_blocking=True)
+
+    for g in groups:
+        issue(g, False)
+    done_rows = 0
+    t0 = 0.0
+    for it in range(3 + steps):
+        if it == 3:
+            if barrier is not None:
+                barrier()
+            t0 = time.perf_counter()
+        for g in groups:
+            g["stream"].synchronize()                          # this half's result (and next actions) are on the host
+            done_rows += int(g["np"][2][0, L.INFO_DONE])       # touch the result
+            issue(g, True)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    launches_e2e = sum(g["env"].kernel_launches for g in groups)
+    errs_e2e = int(sum(int(g["env"].err_flags().any()) for g in groups))
+    for g in groups:
+        g["env"].close()
+    return n * world * steps / float(te.item()), errs_e2e
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -264,53 +317,8 @@ def run_b200_arm(args):
     # streams (catan_step_host_async): while the host waits for one half's result, the other half's kernels and copies run.
     # This is how a host-side policy loop drives the library (the reference's sub-process manager also keeps several env
     # groups in flight, RL/ppo/vec_gather_experience.py); each half's step still depends on that half's previous result.
-    def time_e2e_pipelined(steps, warm_ticks):
-        half = n // 2
-        groups = []
-        for gi in range(2):
-            e = VecCatanEnv(half, device=dev, seed=args.seed, first_env_id=rank * n + gi * half)
-            e.reset()
-            a = e.sample_random()
-            for _ in range(warm_ticks):
-                e.step_sample(a)
-            g = {"env": e, "stream": torch.cuda.Stream(device=dev), "d_act": a,
-                 "h_act": torch.empty((half, L.ACTION_WORDS), dtype=torch.int32).pin_memory(),
-                 "h_rew": torch.empty((half, 4), dtype=torch.float32).pin_memory(),
-                 "h_info": torch.empty((half, L.INFO_STRIDE), dtype=torch.uint8).pin_memory()}
-            g["np"] = (g["h_act"].numpy(), g["h_rew"].numpy(), g["h_info"].numpy())
-            groups.append(g)
-        torch.cuda.synchronize()
-
-        def issue(g, step):
-            with torch.cuda.stream(g["stream"]):
-                if step:
-                    g["env"].step_host_async(g["np"][0], None, None, g["np"][1], g["np"][2])
-                g["env"].sample_random(g["d_act"])                 # stand-in for the policy, as in e2e_tick
-                g["h_act"].copy_(g["d_act"], non_blocking=True)
-
-        for g in groups:
-            issue(g, False)
-        done_rows = 0
-        t0 = 0.0
-        for it in range(3 + steps):
-            if it == 3:
-                barrier()
-                t0 = time.perf_counter()
-            for g in groups:
-                g["stream"].synchronize()                          # this half's result (and next actions) are on the host
-                done_rows += int(g["np"][2][0, L.INFO_DONE])       # touch the result
-                issue(g, True)
-        torch.cuda.synchronize()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        launches_e2e = sum(g["env"].kernel_launches for g in groups)
-        errs_e2e = int(sum(int(g["env"].err_flags().any()) for g in groups))
-        for g in groups:
-            g["env"].close()
-        return 2 * half * world * steps / float(te.item()), errs_e2e
-
-    e2e_pipe, e2e_pipe_errs = time_e2e_pipelined(e2e_steps * 10, min(1000, max(3, args.warmup) + args.steps))
+    e2e_pipe, e2e_pipe_errs = e2e_double_buffered(n, e2e_steps * 10, min(1000, max(3, args.warmup) + args.steps), dev, args.seed, rank, world,
+                                                  args.e2e_groups, barrier)
     h2d = n * L.ACTION_WORDS * 4
     d2h = n * (16 + L.INFO_STRIDE) + n * L.ACTION_WORDS * 4
     d2h_full = d2h + n * (L.OBS_STRIDE + L.MASK_STRIDE)
@@ -392,9 +400,9 @@ def run_b200_arm(args):
                         "pinned host, synchronous; obs/masks stay in HBM for the GPU policy (d2h also counts the sampler's actions)"}
     e2e_db = {"value": e2e_pipe, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
               "rejected_actions": e2e_pipe_errs,
-              "call": "VecCatanEnv.step_host_async -> catan_step_host_async, double-buffered: the games split over two handles on two "
+              "call": "VecCatanEnv.step_host_async -> catan_step_host_async, double-buffered: the games split over %d handles on their own "
                       "streams, every step of every game still takes its actions from pinned host memory and returns reward+done/info "
-                      "rows (and the sampler's next actions) to pinned host memory; the host waits for one half while the other runs"}
+                      "rows (and the sampler's next actions) to pinned host memory; the host waits for one group while the others run" % args.e2e_groups}
     e2e_best, e2e_other = (e2e_db, e2e_sync) if e2e_pipe >= e2e_value else (e2e_sync, e2e_db)
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

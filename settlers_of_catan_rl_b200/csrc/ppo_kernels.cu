@@ -148,35 +148,31 @@ __global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constan
   const unsigned stride = gridDim.x * blockDim.x;
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned B = A.B;
-  {  // numeric features: one 4-byte load -> one 16-byte (fp32) / 8-byte (bf16) store
+  {  // numeric features: one 4-byte load -> one 16-byte (fp32) / 8-byte (bf16) store.  The grid is a multiple of 7 blocks, so
+     // the grid stride is a multiple of the 448 groups of a row: a thread keeps ITS four columns for the whole kernel and
+     // their scale factors (1, 1/8, 1/4, or 0 for the pad columns) are computed once.
     constexpr unsigned G = CATAN_POLICY_FEATURE_STRIDE / 4;
     const unsigned* src = reinterpret_cast<const unsigned*>(A.obs);
     T* dst = static_cast<T*>(A.features);
-    const unsigned total = B * G;
-    for (unsigned g0 = tid; g0 < total; g0 += 4 * stride) {
-      unsigned w[4], col[4];
+    const unsigned row0 = tid / G, c4 = tid - row0 * G, row_step = stride / G;
+    float scale[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) scale[k] = c4 * 4 + k < CATAN_OBS_FEATURES ? ratio_scale(static_cast<int>(c4 * 4) + k) : 0.0f;
+    for (unsigned r0 = row0; r0 < B; r0 += 4 * row_step) {
+      unsigned w[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const unsigned g = g0 + u * stride;
-        if (g < total) {
-          const unsigned row = g / G, c4 = g - row * G;
-          col[u] = c4 * 4;
-          w[u] = __ldcs(src + src_row(row, A) * (CATAN_OBS_STRIDE / 4) + c4);
-        }
+        const unsigned row = r0 + u * row_step;
+        if (row < B) w[u] = __ldcs(src + src_row(row, A) * (CATAN_OBS_STRIDE / 4) + c4);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const unsigned g = g0 + u * stride;
-        if (g < total) {
+        const unsigned row = r0 + u * row_step;
+        if (row < B) {
           float v[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            v[k] = col[u] + k < CATAN_OBS_FEATURES ? static_cast<float>((w[u] >> (8 * k)) & 0xffu) : 0.0f;
-          if (col[u] + 3 >= CATAN_OBS_CUR_MAIN) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] *= ratio_scale(static_cast<int>(col[u]) + k);
-          }
-          store4(dst, g, v);
+          for (int k = 0; k < 4; ++k) v[k] = static_cast<float>((w[u] >> (8 * k)) & 0xffu) * scale[k];
+          store4(dst, static_cast<size_t>(row) * G + c4, v);
         }
       }
     }
@@ -545,7 +541,8 @@ extern "C" int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* m
   A.head_masks = head_masks_dev; A.B = static_cast<unsigned>(B);
   A.magic_B = 0xFFFFFFFFFFFFFFFFull / static_cast<unsigned>(B) + 1ull;
   const long long groups = static_cast<long long>(B) * (CATAN_POLICY_FEATURE_STRIDE / 4);
-  const int blocks = static_cast<int>(groups + 255 < 256LL * 148 * 8 ? (groups + 255) / 256 : 148 * 8);   // grid-stride, 8 blocks per SM
+  // grid-stride, 8 blocks of 256 threads per SM; a multiple of 7 blocks (7 * 256 = 4 * 448) keeps every thread on its columns
+  const int blocks = static_cast<int>(groups + 255 < 256LL * 1183 ? ((groups + 255) / 256 + 6) / 7 * 7 : 1183);
   if (dtype == CATAN_DTYPE_F32) catanb::policy_inputs_kernel<float><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   else catanb::policy_inputs_kernel<__nv_bfloat16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   cudaError_t e = cudaGetLastError();
