@@ -188,6 +188,18 @@ int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t* policy_map
 int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_dev, const int32_t* row_index_dev, int B, int dtype, void* features_dev,
                         int64_t* lists_dev, void* head_masks_dev, void* stream);
 
+/* ---- masked categorical head (RL/distributions.py:11-40: Categorical.forward builds FixedCategorical(logits = x + log(mask));
+ * the head module then calls sample() / mode(), log_probs() and entropy(), RL/models/action_heads_module.py:84-160) ----------
+ * One launch for B rows of D logits (fp32, contiguous): mask_dev fp32 [B][D] (0 = illegal) or NULL.  The action is
+ *   given_actions_dev[b]                      when given_actions_dev != NULL (evaluate_actions; actions_dev is not written),
+ *   inverse CDF of uniforms_dev[b] in [0, 1)   when uniforms_dev != NULL (sample; never an illegal entry),
+ *   the first maximum                          otherwise (mode, deterministic=True).
+ * logp_dev[b] = log p(action), entropy_dev[b] (may be NULL) = -sum p log p over p > 0.  Forward only: the PPO update, which
+ * differentiates through log_probs and entropy, keeps the reference's torch distribution. */
+int catan_masked_categorical(const float* logits_dev, const float* mask_dev, const int64_t* given_actions_dev,
+                             const float* uniforms_dev, int B, int D, int64_t* actions_dev, float* logp_dev,
+                             float* entropy_dev, void* stream);
+
 /* ---- minibatch generator (RL/ppo/process_batch.py:169-200, generator_standard) --------------------
  * The reference draws a random permutation of the T*N (time, env) pairs, cuts it into num_mini_batch index lists and, for
  * each, indexes every CPU buffer key by key and copies the pieces to the device.  Here the rollout buffers are already in

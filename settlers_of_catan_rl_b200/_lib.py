@@ -83,6 +83,7 @@ ABI = {
     "catan_adv_apply": (C.c_int, [_vp, C.c_longlong, _vp, C.c_double, _vp]),
     "catan_route_by_policy": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "catan_policy_inputs": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "catan_masked_categorical": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "catan_minibatch_gather": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
 }
 

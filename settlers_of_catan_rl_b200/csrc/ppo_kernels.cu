@@ -228,6 +228,95 @@ __global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constan
   }
 }
 
+
+// ---- masked categorical head (RL/distributions.py:11-40 FixedCategorical / Categorical.forward) ----------------------
+// The tail of every action head in the reference: logits + log(mask) -> Categorical -> sample / mode, log_probs, entropy,
+// ~10 small torch launches per head and 12 heads per decision.  One warp per row does all of it in one launch:
+//   l_i = x_i (mask_i != 0) or -inf;  m = max l;  S = sum exp(l_i - m);  log p_i = l_i - m - log S;
+//   entropy = -sum p_i log p_i over p_i > 0 (distributions.py:18-20) = log S - sum e_i (l_i - m) / S;
+//   action: given (evaluate), argmax p (mode, first maximum), or inverse CDF of a caller-supplied uniform (sample).
+// expf / logf are the IEEE-accurate library versions; results agree with torch to ~1e-6.
+struct CategoricalArgs {
+  const float* logits;        // [B][D]
+  const float* mask;          // [B][D] or null (no mask)
+  const long long* given;     // [B] or null
+  const float* uniform;       // [B] or null
+  long long* action;          // [B]
+  float* logp;                // [B]
+  float* entropy;             // [B] or null
+  int B, D;
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) masked_categorical_kernel(const __grid_constant__ CategoricalArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int row = static_cast<int>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= A.B) return;
+  const int D = A.D;
+  const float* x = A.logits + static_cast<size_t>(row) * D;
+  const float* mk = A.mask == nullptr ? nullptr : A.mask + static_cast<size_t>(row) * D;
+  const float NEG_INF = __int_as_float(0xff800000);
+  auto logit = [&](int i) { return (mk == nullptr || mk[i] != 0.0f) ? x[i] : NEG_INF; };
+  float m = NEG_INF;
+  int arg = 0x7fffffff;
+  for (int i = lane; i < D; i += 32) { const float l = logit(i); if (l > m) { m = l; arg = i; } }   // first maximum of this lane
+  const float mx = warp_max(m);
+  {  // mode: the first index holding the maximum
+    int cand = (m == mx && arg != 0x7fffffff) ? arg : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    arg = cand == 0x7fffffff ? 0 : cand;
+  }
+  float s = 0.0f, sl = 0.0f;
+  for (int i = lane; i < D; i += 32) {
+    const float l = logit(i);
+    if (l != NEG_INF) { const float d = l - mx, e = expf(d); s += e; sl += e * d; }
+  }
+  const float S = warp_sum(s), SL = warp_sum(sl), logS = logf(S);
+  long long a;
+  if (A.given != nullptr) {
+    a = A.given[row];
+  } else if (A.uniform != nullptr) {
+    // inverse CDF in index order: the first i with e_0 + ... + e_i > u * S; masked entries add nothing and are never picked
+    const float target = A.uniform[row] * S;
+    float run = 0.0f;
+    int pick = -1, last = -1;
+    for (int base = 0; base < D && pick < 0; base += 32) {
+      const int i = base + lane;
+      const float l = i < D ? logit(i) : NEG_INF;
+      const float e = l != NEG_INF ? expf(l - mx) : 0.0f;
+      float c = e;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, c, o); if (lane >= o) c += t; }
+      const unsigned hit = __ballot_sync(0xffffffffu, e > 0.0f && run + c > target);
+      const unsigned legal = __ballot_sync(0xffffffffu, e > 0.0f);
+      if (legal) last = base + 31 - __clz(legal);
+      if (hit) pick = base + __ffs(hit) - 1;
+      run += __shfl_sync(0xffffffffu, c, 31);
+    }
+    a = pick >= 0 ? pick : (last >= 0 ? last : arg);               // rounding at the top of the CDF: the last legal entry
+  } else {
+    a = arg;
+  }
+  if (lane == 0) {
+    const int ai = static_cast<int>(a);
+    const float la = (ai >= 0 && ai < D) ? logit(ai) : NEG_INF;
+    if (A.given == nullptr) A.action[row] = a;
+    A.logp[row] = (la - mx) - logS;
+    if (A.entropy != nullptr) A.entropy[row] = logS - SL / S;
+  }
+}
+
 }  // namespace catanb
 
 static thread_local std::string g_ppo_error;
@@ -547,4 +636,17 @@ extern "C" int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* m
   else catanb::policy_inputs_kernel<__nv_bfloat16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : ppo_fail(e, "catan_policy_inputs launch");
+}
+
+extern "C" int catan_masked_categorical(const float* logits_dev, const float* mask_dev, const int64_t* given_actions_dev,
+                                        const float* uniforms_dev, int B, int D, int64_t* actions_dev, float* logp_dev,
+                                        float* entropy_dev, void* stream) {
+  if (!logits_dev || !logp_dev || B <= 0 || D <= 0 || (given_actions_dev == nullptr && actions_dev == nullptr))
+    return ppo_fail(cudaErrorInvalidValue, "catan_masked_categorical: bad argument");
+  catanb::CategoricalArgs A;
+  A.logits = logits_dev; A.mask = mask_dev; A.given = reinterpret_cast<const long long*>(given_actions_dev); A.uniform = uniforms_dev;
+  A.action = reinterpret_cast<long long*>(actions_dev); A.logp = logp_dev; A.entropy = entropy_dev; A.B = B; A.D = D;
+  catanb::masked_categorical_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : ppo_fail(e, "catan_masked_categorical launch");
 }

@@ -109,3 +109,69 @@ def rows_to_actions(action_rows: torch.Tensor) -> List[torch.Tensor]:
     a = action_rows.long()
     return [a[:, h:h + 1] for h in range(7)] + [a[:, L.A_GIVE:L.A_GIVE + 4], a[:, L.A_RECV:L.A_RECV + 4]] + \
            [a[:, L.A_RES_A:L.A_RES_A + 1], a[:, L.A_RES_B:L.A_RES_B + 1], a[:, L.A_DISCARD:L.A_DISCARD + 1]]
+
+
+def masked_categorical(logits: torch.Tensor, mask: Optional[torch.Tensor] = None, actions: Optional[torch.Tensor] = None,
+                       deterministic: bool = False, uniforms: Optional[torch.Tensor] = None,
+                       generator: Optional[torch.Generator] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The tail of a reference action head in one launch (RL/distributions.py:11-40 ``Categorical.forward`` +
+    ``FixedCategorical.sample / mode / log_probs / entropy``): ``logits`` fp32 ``[B, D]``, ``mask`` fp32 ``[B, D]`` (0 = illegal) or
+    None.  Returns ``(actions [B, 1] int64, log_probs [B, 1], entropy [B])`` for the given ``actions`` (evaluate), the mode
+    (``deterministic``), or a sample drawn by inverse CDF from ``uniforms`` (default: ``torch.rand(B)`` of ``generator``).
+    Forward only (rollouts run under ``no_grad``); the PPO update keeps the torch distribution for its gradients."""
+    B, D = logits.shape
+    logits = logits.detach()
+    assert logits.dtype == torch.float32 and logits.is_cuda and logits.is_contiguous()
+    if mask is not None:
+        mask = mask.detach()
+        assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.shape == (B, D) and mask.device == logits.device
+    dev = logits.device
+    logp = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    entropy = torch.empty(B, dtype=torch.float32, device=dev)
+    given = out = None
+    if actions is not None:
+        given = actions.reshape(B).to(torch.int64).contiguous()
+    else:
+        out = torch.empty((B, 1), dtype=torch.int64, device=dev)
+        if not deterministic and uniforms is None:
+            uniforms = torch.rand(B, device=dev, generator=generator)
+        if deterministic:
+            uniforms = None
+    if uniforms is not None:
+        assert uniforms.dtype == torch.float32 and uniforms.is_contiguous() and uniforms.numel() == B
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(_lib.load().catan_masked_categorical(_p(logits), _p(mask), _p(given), _p(uniforms), B, D, _p(out), _p(logp), _p(entropy), stream))
+    return (given.view(B, 1) if out is None else out), logp, entropy
+
+
+class FusedCategorical:
+    """``FixedCategorical``'s surface (RL/distributions.py:11-23: ``sample / mode / log_probs / entropy``) on the fused kernel, for
+    the rollout path (no gradients): ``Categorical.forward`` can return ``FusedCategorical(x, mask)`` instead of
+    ``FixedCategorical(logits=x + torch.log(mask))`` when ``not torch.is_grad_enabled()``.  The first ``sample()`` / ``mode()``
+    computes action, log-prob and entropy in one launch; ``log_probs`` of that same action and ``entropy`` are then free."""
+
+    def __init__(self, logits: torch.Tensor, mask: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None):
+        self.logits = logits.detach().float().contiguous()
+        self.mask = None if mask is None else mask.detach().float().expand_as(self.logits).contiguous()
+        self.generator = generator
+        self._action = self._logp = self._entropy = None
+
+    def _run(self, **kw):
+        self._action, self._logp, self._entropy = masked_categorical(self.logits, self.mask, generator=self.generator, **kw)
+        return self._action
+
+    def sample(self) -> torch.Tensor:
+        return self._run()
+
+    def mode(self) -> torch.Tensor:
+        return self._run(deterministic=True)
+
+    def log_probs(self, actions: torch.Tensor) -> torch.Tensor:
+        if self._action is not None and (actions is self._action or torch.equal(actions.reshape(-1), self._action.reshape(-1))):
+            return self._logp
+        return masked_categorical(self.logits, self.mask, actions=actions)[1]
+
+    def entropy(self) -> torch.Tensor:
+        if self._entropy is None:
+            self._run(deterministic=True)
+        return self._entropy

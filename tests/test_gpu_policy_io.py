@@ -73,3 +73,74 @@ def test_policy_inputs_of_a_golden_row_and_action_round_trip():
     heads[7] = [heads[7][:, k:k + 1] for k in range(4)]
     heads[8] = [heads[8][:, k:k + 1] for k in range(4)]
     assert torch.equal(actions_to_rows(heads), a)
+
+
+def _reference_head(logits, mask):
+    """RL/distributions.py:11-40, restated: Categorical.forward + FixedCategorical"""
+    d = torch.distributions.Categorical(logits=logits if mask is None else logits + torch.log(mask))
+    p = d.probs.masked_fill(d.probs <= 0, 1)
+    return d, -1 * p.mul(p.log()).sum(-1)
+
+
+@pytest.mark.parametrize("D", [2, 5, 13, 54, 73, 200])
+def test_masked_categorical_matches_the_reference_distribution(D):
+    from settlers_of_catan_rl_b200.policy_io import masked_categorical
+    g = torch.Generator(device="cuda").manual_seed(D)
+    B = 4099
+    logits = (torch.randn(B, D, device="cuda", generator=g) * 3).contiguous()
+    mask = (torch.rand(B, D, device="cuda", generator=g) < 0.4).float()
+    mask[torch.arange(B), torch.randint(0, D, (B,), device="cuda", generator=g)] = 1.0     # at least one legal entry
+    for mk in (mask, None):
+        d, ent = _reference_head(logits, mk)
+        # mode (deterministic=True: FixedCategorical.mode)
+        a, lp, en = masked_categorical(logits, mk, deterministic=True)
+        assert torch.equal(a, d.probs.argmax(dim=-1, keepdim=True))
+        torch.testing.assert_close(lp.view(-1), d.log_prob(a.view(-1)), rtol=1e-5, atol=1e-5)     # tolerance: fp32 log-softmax
+        torch.testing.assert_close(en, ent, rtol=1e-5, atol=1e-5)
+        # evaluate: log-probs of given legal actions
+        given = torch.multinomial(d.probs, 1)
+        a2, lp2, en2 = masked_categorical(logits, mk, actions=given)
+        assert torch.equal(a2, given) and torch.equal(en2, en)
+        torch.testing.assert_close(lp2.view(-1), d.log_prob(given.view(-1)), rtol=1e-5, atol=1e-5)
+        # sample: always legal, log-prob of what was drawn, and u -> action is the inverse CDF
+        u = torch.rand(B, device="cuda", generator=g)
+        a3, lp3, _ = masked_categorical(logits, mk, uniforms=u)
+        if mk is not None:
+            assert bool((mk.gather(1, a3) == 1).all())
+        torch.testing.assert_close(lp3.view(-1), d.log_prob(a3.view(-1)), rtol=1e-5, atol=1e-5)
+        cdf = d.probs.double().cumsum(-1)
+        lo = torch.where(a3 > 0, cdf.gather(1, (a3 - 1).clamp(min=0)), torch.zeros_like(cdf[:, :1])).view(-1)
+        hi = cdf.gather(1, a3).view(-1)
+        assert bool(((u.double() >= lo - 1e-5) & (u.double() <= hi + 1e-5)).all())
+        assert bool((masked_categorical(logits, mk, uniforms=torch.zeros(B, device="cuda"))[0].view(-1) ==
+                     (d.probs > 0).float().argmax(dim=-1)).all())                              # u = 0 -> the first legal entry
+        top = masked_categorical(logits, mk, uniforms=torch.full((B,), 1.0 - 2 ** -24, device="cuda"))[0]
+        assert bool((d.probs.gather(1, top) > 0).all())
+
+
+def test_masked_categorical_sampling_frequencies():
+    from settlers_of_catan_rl_b200.policy_io import masked_categorical
+    D, B = 13, 400_000
+    logits = torch.tensor([0.3, -1.0, 2.0, 0.0, 0.5, -0.5, 1.0, 0.0, 0.0, -2.0, 0.7, 0.1, 0.2], device="cuda").repeat(B, 1).contiguous()
+    mask = torch.tensor([1, 0, 1, 1, 0, 1, 1, 0, 0, 1, 1, 0, 1], device="cuda", dtype=torch.float32).repeat(B, 1).contiguous()
+    a, _, _ = masked_categorical(logits, mask, generator=torch.Generator(device="cuda").manual_seed(1))
+    freq = torch.bincount(a.view(-1), minlength=D).double() / B
+    p = torch.softmax(logits[0] + torch.log(mask[0]), -1).double()
+    assert bool(((freq - p).abs() <= 5 * (p * (1 - p) / B).sqrt() + 1e-9).all())
+
+
+def test_fused_categorical_has_the_fixed_categorical_surface():
+    from settlers_of_catan_rl_b200.policy_io import FusedCategorical
+    g = torch.Generator(device="cuda").manual_seed(9)
+    logits = torch.randn(777, 54, device="cuda", generator=g)
+    mask = (torch.rand(777, 54, device="cuda", generator=g) < 0.5).float()
+    mask[:, 7] = 1.0
+    d, ent = _reference_head(logits, mask)
+    f = FusedCategorical(logits, mask, generator=g)
+    a = f.sample()
+    assert a.shape == (777, 1) and a.dtype == torch.int64 and bool((mask.gather(1, a) == 1).all())
+    torch.testing.assert_close(f.log_probs(a).view(-1), d.log_prob(a.view(-1)), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(f.entropy(), ent, rtol=1e-5, atol=1e-5)
+    other = torch.multinomial(d.probs, 1)
+    torch.testing.assert_close(f.log_probs(other).view(-1), d.log_prob(other.view(-1)), rtol=1e-5, atol=1e-5)
+    assert torch.equal(FusedCategorical(logits, mask).mode(), d.probs.argmax(dim=-1, keepdim=True))
