@@ -69,3 +69,24 @@ class SeatPolicies:
         return self.actions, self.logp
 
     __call__ = act
+
+
+def league_probabilities(num_policies: int, linear_num: int = 800, linear_prob: float = 0.5):
+    """Sampling weights over the stored earlier policies, oldest first (RL/ppo/update_opponent_policies.py:29-43
+    ``get_prob_dist``): half of the mass uniform, half rising linearly over the ``linear_num`` most recent snapshots."""
+    import numpy as np
+    p = np.full(num_policies, (1.0 - linear_prob) / num_policies, dtype=np.float64)
+    num_aux = min(linear_num, num_policies)
+    grad = (2.0 * linear_prob) / (num_aux + 1) / num_aux
+    p[num_policies - num_aux:] += np.arange(num_aux, dtype=np.float64) * grad
+    return p / p.sum()
+
+
+def sample_opponents(earlier_policies: Sequence, rng=None, count: int = 3) -> list:
+    """three earlier snapshots for seats 1-3 of a worker (update_opponent_policies.py:13-26): drawn with replacement from
+    ``league_probabilities``; seat 0 stays the learner.  ``rng``: a ``numpy.random.Generator`` / ``RandomState`` (default: the
+    global numpy state, as in the reference)."""
+    import numpy as np
+    p = league_probabilities(len(earlier_policies))
+    idx = (np.random if rng is None else rng).choice(len(earlier_policies), count, p=p)
+    return [earlier_policies[int(i)] for i in idx]
