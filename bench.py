@@ -317,8 +317,12 @@ def run_b200_arm(args):
     # streams (catan_step_host_async): while the host waits for one half's result, the other half's kernels and copies run.
     # This is how a host-side policy loop drives the library (the reference's sub-process manager also keeps several env
     # groups in flight, RL/ppo/vec_gather_experience.py); each half's step still depends on that half's previous result.
-    e2e_pipe, e2e_pipe_errs = e2e_double_buffered(n, e2e_steps * 10, min(1000, max(3, args.warmup) + args.steps), dev, args.seed, rank, world,
-                                                  args.e2e_groups, barrier)
+    e2e_pipe_error = None
+    try:
+        e2e_pipe, e2e_pipe_errs = e2e_double_buffered(n, e2e_steps * 10, min(1000, max(3, args.warmup) + args.steps), dev, args.seed, rank, world,
+                                                      max(1, args.e2e_groups), barrier)
+    except Exception as exc:  # reported, never hidden: the synchronous loop above then stands as e2e
+        e2e_pipe, e2e_pipe_errs, e2e_pipe_error = 0.0, -1, "%s: %s" % (type(exc).__name__, exc)
     h2d = n * L.ACTION_WORDS * 4
     d2h = n * (16 + L.INFO_STRIDE) + n * L.ACTION_WORDS * 4
     d2h_full = d2h + n * (L.OBS_STRIDE + L.MASK_STRIDE)
@@ -399,7 +403,7 @@ def run_b200_arm(args):
                 "call": "VecCatanEnv.step_host -> catan_step_host, one handle: pinned host actions in, reward+done/info rows out to "
                         "pinned host, synchronous; obs/masks stay in HBM for the GPU policy (d2h also counts the sampler's actions)"}
     e2e_db = {"value": e2e_pipe, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
-              "rejected_actions": e2e_pipe_errs,
+              "rejected_actions": e2e_pipe_errs, "error": e2e_pipe_error, "groups": max(1, args.e2e_groups),
               "call": "VecCatanEnv.step_host_async -> catan_step_host_async, double-buffered: the games split over %d handles on their own "
                       "streams, every step of every game still takes its actions from pinned host memory and returns reward+done/info "
                       "rows (and the sampler's next actions) to pinned host memory; the host waits for one group while the others run" % args.e2e_groups}
