@@ -163,7 +163,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # this build
 # ------------------------------------------------------------------------------------------------
-def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_groups=2, barrier=None):
+def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_groups=2, barrier=None, fused_sampler=True):
     import torch
     from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
     sizes = [n // n_groups + (1 if gi < n % n_groups else 0) for gi in range(n_groups)]     # sum = n
@@ -185,10 +185,15 @@ def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_grou
 
     def issue(g, step):
         with torch.cuda.stream(g["stream"]):
-            if step:
+            if not step:                                       # the first actions: sampled on the device, brought to the host
+                g["env"].sample_random(g["d_act"])
+                g["h_act"].copy_(g["d_act"], non_blocking=True)
+            elif fused_sampler:                                # H2D actions, step + next random-legal actions, D2H actions/reward/info
+                g["env"].step_sample_host_async(g["np"][0], g["np"][1], g["np"][2])
+            else:
                 g["env"].step_host_async(g["np"][0], None, None, g["np"][1], g["np"][2])
-            g["env"].sample_random(g["d_act"])                 # stand-in for the policy, as in e2e_tick
-            g["h_act"].copy_(g["d_act"], non_blocking=True)
+                g["env"].sample_random(g["d_act"])             # stand-in for the policy, as in e2e_tick
+                g["h_act"].copy_(g["d_act"], non_blocking=True)
 
     for g in groups:
         issue(g, False)
@@ -404,7 +409,7 @@ def run_b200_arm(args):
                         "pinned host, synchronous; obs/masks stay in HBM for the GPU policy (d2h also counts the sampler's actions)"}
     e2e_db = {"value": e2e_pipe, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
               "rejected_actions": e2e_pipe_errs, "error": e2e_pipe_error, "groups": max(1, args.e2e_groups),
-              "call": "VecCatanEnv.step_host_async -> catan_step_host_async, double-buffered: the games split over %d handles on their own "
+              "call": "VecCatanEnv.step_sample_host_async -> catan_step_sample_host_async (the random-legal policy fused into the step as in `value`), double-buffered: the games split over %d handles on their own "
                       "streams, every step of every game still takes its actions from pinned host memory and returns reward+done/info "
                       "rows (and the sampler's next actions) to pinned host memory; the host waits for one group while the others run" % args.e2e_groups}
     e2e_best, e2e_other = (e2e_db, e2e_sync) if e2e_pipe >= e2e_value else (e2e_sync, e2e_db)

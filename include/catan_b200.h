@@ -92,6 +92,9 @@ int catan_step_host(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_
  * the other half's kernels. */
 int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host,
                           float* reward_host, uint8_t* info_host, void* stream);
+/* catan_step_sample with host buffers, not synchronised (the env-only benchmark's random-legal policy, BASELINE.md §3, driven
+ * from the host): actions_io_host (pinned) is copied in, applied, and overwritten with every env's next random-legal action. */
+int catan_step_sample_host_async(catan_env_t* env, int32_t* actions_io_host, float* reward_host, uint8_t* info_host, void* stream);
 int catan_reset_host(catan_env_t* env, uint8_t* obs_host, uint8_t* masks_host, uint8_t* info_host, void* stream);
 
 /* EnvWrapper.save_state / restore_state (env/wrapper.py:711-721; game/game.py:1013-1205) as the

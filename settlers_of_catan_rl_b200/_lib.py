@@ -71,6 +71,7 @@ ABI = {
     "catan_step_sample": (C.c_int, [_vp, _vp, _vp]),
     "catan_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "catan_step_host_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "catan_step_sample_host_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "catan_reset_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "catan_export_state": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "catan_import_state": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),

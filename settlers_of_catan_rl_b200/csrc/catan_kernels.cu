@@ -855,6 +855,20 @@ int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t
   return copy_outputs_to_host(env, obs_host, masks_host, reward_host, info_host, s, false);
 }
 
+// catan_step_sample with host buffers, not synchronised: actions_io_host (pinned) is copied in, applied, and overwritten with
+// the next random-legal action of every env; reward / info rows as in catan_step_host_async.
+int catan_step_sample_host_async(catan_env_t* env, int32_t* actions_io_host, float* reward_host, uint8_t* info_host, void* stream) {
+  if (check_bound(env)) return -1;
+  if (!actions_io_host) return fail("actions_io_host is null");
+  if (device_guard(env)) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t bytes = sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(env->n);
+  CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_io_host, bytes, cudaMemcpyHostToDevice, s));
+  if (catan_step_sample(env, env->actions_stage, stream)) return -1;
+  CATAN_CUDA(cudaMemcpyAsync(actions_io_host, env->actions_stage, bytes, cudaMemcpyDeviceToHost, s));
+  return copy_outputs_to_host(env, nullptr, nullptr, reward_host, info_host, s, false);
+}
+
 int catan_step_host(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host, float* reward_host,
                     uint8_t* info_host, void* stream) {
   if (check_bound(env)) return -1;

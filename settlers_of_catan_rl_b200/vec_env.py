@@ -115,6 +115,15 @@ class VecCatanEnv:
         _lib.check(self.lib.catan_step_host_async(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
         self.kernel_launches += 6
 
+    def step_sample_host_async(self, actions_io: np.ndarray, reward: np.ndarray = None, info: np.ndarray = None) -> None:
+        """``step_sample`` with pinned host buffers, not synchronised: ``actions_io`` is applied and overwritten with the next
+        random-legal actions; valid once the current stream has been synchronised."""
+        def p(a):
+            return C.c_void_p(0 if a is None else a.ctypes.data)
+        assert actions_io.dtype == np.int32 and actions_io.flags.c_contiguous
+        _lib.check(self.lib.catan_step_sample_host_async(self._h, p(actions_io), p(reward), p(info), self._stream()))
+        self.kernel_launches += 6
+
     def reset_host(self, obs: np.ndarray = None, masks: np.ndarray = None, info: np.ndarray = None) -> None:
         def p(a):
             return C.c_void_p(0 if a is None else a.ctypes.data)

@@ -118,3 +118,29 @@ def test_async_host_step_equals_the_synchronous_one():
         for k in ("obs", "masks", "rew", "info"):
             assert torch.equal(bufs[0][k], bufs[1][k]), (tick, k)
     assert np.array_equal(a.export_state(), b.export_state())
+
+
+def test_async_host_step_with_the_fused_sampler():
+    """catan_step_sample_host_async == catan_step_host followed by catan_sample_random (actions, reward, info, state)"""
+    from settlers_of_catan_rl_b200 import VecCatanEnv
+    n = 500
+    a, b = VecCatanEnv(n, seed=33), VecCatanEnv(n, seed=33)
+    a.reset(); b.reset()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    ha, hb = pin((n, L.ACTION_WORDS), torch.int32), pin((n, L.ACTION_WORDS), torch.int32)
+    ra, rb, ia, ib = pin((n, 4), torch.float32), pin((n, 4), torch.float32), pin((n, L.INFO_STRIDE), torch.uint8), pin((n, L.INFO_STRIDE), torch.uint8)
+    first, first_b = a.sample_random(), b.sample_random()      # both envs draw decision 0 of the sampler stream
+    torch.cuda.synchronize()
+    assert torch.equal(first, first_b)
+    ha.copy_(first); hb.copy_(first_b)
+    side = torch.cuda.Stream()
+    for tick in range(150):
+        a.step_host(ha.numpy(), None, None, ra.numpy(), ia.numpy())
+        nxt = a.sample_random()
+        torch.cuda.synchronize()
+        ha.copy_(nxt)
+        with torch.cuda.stream(side):
+            b.step_sample_host_async(hb.numpy(), rb.numpy(), ib.numpy())
+        side.synchronize()
+        assert torch.equal(ha, hb) and torch.equal(ra, rb) and torch.equal(ia, ib), tick
+    assert np.array_equal(a.export_state(), b.export_state())
