@@ -11,19 +11,9 @@ import torch
 from oracle import ref_harness as H
 from oracle.policy_ref import rows_to_policy_inputs
 from settlers_of_catan_rl_b200 import layout as L
+from settlers_of_catan_rl_b200.policy_io import actions_to_rows, rows_to_actions   # pure tensor plumbing: runs on CPU tensors too
 
 pytestmark = pytest.mark.skipif(not H.reference_available(), reason="reference tree not present")
-
-
-def _actions_to_rows(actions):
-    cols = []
-    for a in actions:
-        if isinstance(a, list):
-            a = torch.cat([x.reshape(-1, 1) for x in a], dim=1)
-        cols.append(a.reshape(a.shape[0], -1))
-    row = torch.zeros((cols[0].shape[0], L.ACTION_WORDS), dtype=torch.int32)
-    row[:, :18] = torch.cat(cols, dim=1)
-    return row
 
 
 def test_reference_policy_reads_the_packed_rows_like_its_own_obs():
@@ -43,14 +33,17 @@ def test_reference_policy_reads_the_packed_rows_like_its_own_obs():
             if t % 7 == 0:   # the reference's own path: one env, its own conversions, its own sampling
                 v, acts, lp, _ = policy.act(policy.obs_to_torch(copy.deepcopy(obs)), None, None,
                                             policy.act_masks_to_torch(copy.deepcopy(masks)))
+                # the sampled heads go back to the env exactly as torch_act_to_np would hand them over (policy.py:192-199)
+                back = H.action_to_reference(actions_to_rows(acts)[0].numpy())
+                ref_np = policy.torch_act_to_np(copy.deepcopy(acts))
+                assert all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(back, ref_np))
                 obs_rows.append(o_row); mask_rows.append(m_row)
-                act_rows.append(_actions_to_rows(acts)); values.append(v.view(-1)); logps.append(lp.view(-1))
+                act_rows.append(actions_to_rows(acts)); values.append(v.view(-1)); logps.append(lp.view(-1))
             a = H.sample_action(m_row, o_row, samp.block(t))
             obs, _, done, _ = env.step(H.action_to_reference(a))
             if done:
                 obs = env.reset()
         assert len(obs_rows) == 100
-        from settlers_of_catan_rl_b200.policy_io import rows_to_actions
         bobs, bmasks = rows_to_policy_inputs(torch.from_numpy(np.stack(obs_rows)), torch.from_numpy(np.stack(mask_rows)))
         actions = rows_to_actions(torch.cat(act_rows))
         v2, lp2, _, _ = policy.evaluate_actions(bobs, None, None, actions, bmasks)
