@@ -55,3 +55,27 @@ def test_reference_policy_reads_the_packed_rows_like_its_own_obs():
             v1, lp1, _, _ = policy.evaluate_actions(o1, None, None, rows_to_actions(act_rows[i]), m1)
             torch.testing.assert_close(v1.view(-1), values[i], rtol=1e-5, atol=1e-5)
             torch.testing.assert_close(lp1.view(-1), logps[i], rtol=1e-5, atol=1e-5)
+
+
+def test_reference_policy_plays_the_reference_env_through_the_hand_off():
+    """the whole loop on the reference's own objects: env obs / masks -> packed rows -> decoded batch -> policy.act -> action
+    rows -> env.step, with validate_actions=True (an illegal action raises, wrapper.py:38-41)"""
+    R = H.import_reference()
+    from RL.models.build_agent_model import build_agent_model  # type: ignore
+    torch.manual_seed(1)
+    policy = build_agent_model(device="cpu")
+    policy.eval()
+    env = R["EnvWrapper"]()
+    with H.patched_rng(H.PhiloxStream(4, 0, 0)), torch.no_grad():
+        obs = env.reset()
+        types_seen = set()
+        for t in range(400):
+            o_row, m_row = H.obs_to_packed(obs), H.masks_to_packed(env.get_action_masks())
+            bobs, bmasks = rows_to_policy_inputs(torch.from_numpy(o_row[None]), torch.from_numpy(m_row[None]))
+            _, heads, _, _ = policy.act(bobs, None, None, bmasks)
+            row = actions_to_rows(heads)[0].numpy()
+            types_seen.add(int(row[L.A_TYPE]))
+            obs, _, done, _ = env.step(H.action_to_reference(row))
+            if done:
+                obs = env.reset()
+    assert len(types_seen) >= 6
