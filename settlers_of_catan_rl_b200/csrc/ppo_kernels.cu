@@ -145,6 +145,8 @@ __device__ __forceinline__ void store1(__nv_bfloat16* p, size_t i, float a) { p[
 // (8-byte for bf16 quads) vector that the warp writes contiguously.
 template <typename T>
 __global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constant__ PolicyInArgs A) {
+  __shared__ uint4 s_rows[32 * (CATAN_MASK_STRIDE / 16)];          // a tile of 32 mask rows
+  __shared__ uint2 s_col[CATAN_MASK_ENTRIES];                      // mask column -> (segment offset | dim << 16, division magic)
   const unsigned stride = gridDim.x * blockDim.x;
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned B = A.B;
@@ -197,33 +199,36 @@ __global__ void __launch_bounds__(256) policy_inputs_kernel(const __grid_constan
     }
   }
   if (A.masks != nullptr && A.head_masks != nullptr) {
-    // masks, head-major: head h owns output elements [off[h] * B, off[h + 1] * B), element (t * B + b) * dim + j of it is
-    // mask byte off[h] + t * dim + j of row b.  A thread decomposes its first element and walks on from there.
+    // masks, head-major: head h owns output elements [off[h] * B, off[h + 1] * B); a (head, type) segment s of `dim` entries at
+    // mask byte seg_off is, for 32 consecutive rows b0 .. b0 + 31, ONE contiguous run of 32 * dim output elements starting at
+    // seg_off * B + b0 * dim.  A block stages the 32 mask rows of a tile in shared memory (16-byte loads) and streams the 19
+    // runs out of it: consecutive threads write consecutive elements.
     T* dst = static_cast<T*>(A.head_masks);
-    const unsigned total = CATAN_MASK_ENTRIES * B;
-    for (unsigned o0 = tid * 4; o0 < total; o0 += stride * 4) {
-      const unsigned c = div_B(o0, A);
+    for (int c = threadIdx.x; c < CATAN_MASK_ENTRIES; c += blockDim.x) {
       int h = 0;
 #pragma unroll
-      for (int k = 1; k < 12; ++k) h += c >= static_cast<unsigned>(c_head_off[k]);
-      unsigned off = c_head_off[h], dim = c_head_dim[h];
-      const unsigned r = o0 - off * B, tb = div_magic(r, c_head_magic[h]);
-      unsigned j = r - tb * dim, t = div_B(tb, A), b = tb - t * B;
-      float v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (o0 + k >= total) continue;
-        v[k] = static_cast<float>(A.masks[src_row(b, A) * CATAN_MASK_STRIDE + off + t * dim + j]);
-        if (++j == dim) {
-          j = 0;
-          if (++b == B) {
-            b = 0; ++t;
-            if (off + t * dim >= static_cast<unsigned>(c_head_off[h + 1])) { ++h; off = c_head_off[h]; dim = c_head_dim[h]; t = 0; }
-          }
-        }
+      for (int k = 1; k < 12; ++k) h += c >= c_head_off[k];
+      const unsigned dim = c_head_dim[h], seg = c_head_off[h] + (c - c_head_off[h]) / dim * dim;
+      s_col[c] = make_uint2(seg | (dim << 16), ((1u << 20) + dim - 1) / dim);   // e / dim = (e * magic) >> 20 for e < 32 * 73
+    }
+    const unsigned tiles = (B + 31) / 32;
+    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const unsigned b0 = tile * 32, rows = min(32u, B - b0);
+      __syncthreads();                                             // the previous tile has been read (and s_col written)
+      for (unsigned q = threadIdx.x; q < rows * (CATAN_MASK_STRIDE / 16); q += blockDim.x) {
+        const unsigned r = q / (CATAN_MASK_STRIDE / 16), w = q - r * (CATAN_MASK_STRIDE / 16);
+        s_rows[q] = __ldcs(reinterpret_cast<const uint4*>(A.masks + src_row(b0 + r, A) * CATAN_MASK_STRIDE) + w);
       }
-      if (o0 + 3 < total) store4(dst, o0 >> 2, v);
-      else for (int k = 0; k < 4; ++k) if (o0 + k < total) store1(dst, o0 + k, v[k]);
+      __syncthreads();
+      const uint8_t* rows_b = reinterpret_cast<const uint8_t*>(s_rows);
+      for (unsigned p = threadIdx.x; p < rows * CATAN_MASK_ENTRIES; p += blockDim.x) {
+        const unsigned c = rows == 32 ? p >> 5 : p / rows;         // p = seg_off * rows + e: any column of the segment finds it
+        const uint2 sc = s_col[c];
+        const unsigned seg = sc.x & 0xffffu, dim = sc.x >> 16;
+        const unsigned e = p - seg * rows, bl = (e * sc.y) >> 20, j = e - bl * dim;
+        store1(dst, static_cast<size_t>(seg) * B + static_cast<size_t>(b0) * dim + e,
+               static_cast<float>(rows_b[bl * CATAN_MASK_STRIDE + seg + j]));
+      }
     }
   }
 }
