@@ -5,9 +5,13 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference's algorithm on host cores
 
 Workload (config.workload): 65 536 parallel 4-player games per GPU, random-legal policy, one "step" = one
-lock-step tick of every game = ONE fused launch (apply action -> auto-reset -> legal-action masks ->
-packed observation -> next random-legal action).  metric = env steps per second, whole job.
-Prints ONE JSON line on rank 0.  See DESIGN.md §measurement for how every field is obtained.
+lock-step tick of every game (apply action -> auto-reset -> legal-action masks -> packed observation -> next
+random-legal action).  metric = env steps per second, whole job.
+
+STEADY STATE, whatever --steps / --warmup are: every leg of every arm first advances its games `--preroll` ticks
+(default 1500) from their first reset, untimed, so that the timed window is ticks [preroll + warmup, preroll + warmup +
+steps) of games in every phase and not the opening of freshly reset games; `config.tick_window`
+records it.  Prints ONE JSON line on rank 0.  See DESIGN.md §6 for how every field is obtained.
 """
 from __future__ import annotations
 
@@ -48,7 +52,18 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--preroll", type=int, default=1500, help="untimed ticks every leg plays from the first reset before anything is timed")
+    ap.add_argument("--ref-envs-per-proc", type=int, default=0, help="reference arm: envs per worker process (0: sized from --steps)")
+    ap.add_argument("--no-python-reference", action="store_true", help="cpu_baseline / reference arm: the C port only")
     return ap.parse_args()
+
+
+def bench_config(args):
+    """`config` of the JSON line: identical keys and values in both arms"""
+    w = max(3, args.warmup)
+    return {"workload": WORKLOAD, "envs_per_gpu": args.envs, "seed": args.seed,
+            "tick_window": [args.preroll + w, args.preroll + w + args.steps],
+            "l2": "no explicit flush: one step streams >= 230 MB (records+obs+masks+actions) > 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -107,13 +122,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm on the host cores (C oracle port; the Python reference cannot travel)
+# CPU arm: the reference itself (oracle/_ref, Python, all host cores) and, beside it, the pinned C port of its algorithm
 # ------------------------------------------------------------------------------------------------
-def cpu_rollout_rate(seconds: float, n_envs: int = 4096, chunk: int = 25, seed: int = 0):
-    """time the oracle's sample->step->masks->obs loop on all host threads for ~`seconds`; returns (steps/s, threads, sample)"""
+def cpu_port_rate(seconds: float, preroll: int, n_envs: int = 4096, chunk: int = 25, seed: int = 0):
+    """the C oracle's sample->step->masks->obs loop on all host threads for ~`seconds`, from tick `preroll` on"""
     from oracle import oracle_lib as O
     v = O.OracleVec(n_envs, seed=seed, first_env_id=0)
-    v.run(chunk)                                   # reset + warm-up
+    v.run(0)
+    v.run(preroll)                                 # untimed: the same steady state as every other leg
     done_steps, t0 = 0, time.perf_counter()
     while True:
         v.run(chunk)
@@ -121,40 +137,72 @@ def cpu_rollout_rate(seconds: float, n_envs: int = 4096, chunk: int = 25, seed: 
         dt = time.perf_counter() - t0
         if dt >= seconds:
             break
-    return done_steps / dt, v.threads_used, "%d envs x %d ticks, %.1f s, C port of game.py+wrapper.py on %d host threads" % (
-        n_envs, done_steps // n_envs, dt, v.threads_used)
+    return {"value": done_steps / dt, "unit": UNIT, "cores": v.threads_used, "kind": "port",
+            "sample": "%d envs x %d ticks from tick %d, %.1f s, C port of game.py+wrapper.py (oracle/catan_oracle.c) on %d host threads" % (
+                n_envs, done_steps // n_envs, preroll, dt, v.threads_used)}
+
+
+def python_reference_rate(args, steps=None, seconds=15.0, envs_per_proc=8, warmup=0):
+    """the unmodified reference's EnvWrapper loop (oracle/ref_bench.py) on os.cpu_count() processes"""
+    from oracle import ref_bench
+    r = ref_bench.time_reference_env(envs_per_proc=envs_per_proc, preroll=args.preroll, warmup=warmup, steps=steps, seconds=seconds)
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"],
+            "per_core": r["per_core"], "seconds": r["seconds"], "env_steps": r["env_steps"]}
+
+
+def python_reference_available(args) -> bool:
+    if args.no_python_reference:
+        return False
+    try:
+        from oracle import ref_bench
+        return ref_bench.reference_available()
+    except Exception:
+        return False
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle_lib as O
-    # calibrate the per-step sample so that (steps + warmup) ticks finish in about a minute
-    rate, threads, _ = cpu_rollout_rate(2.0, n_envs=2048, chunk=10, seed=args.seed)
-    total_ticks = max(1, args.steps + args.warmup)
-    n_envs = int(max(64, min(args.envs, rate * 60.0 / total_ticks)))
-    n_envs = max(64, (n_envs // 64) * 64)
-    v = O.OracleVec(n_envs, seed=args.seed, first_env_id=0)
-    v.run(0)
-    for _ in range(args.warmup):
-        v.run(1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        v.run(1)
-    dt = time.perf_counter() - t0
-    value = n_envs * args.steps / dt
-    sample = "%d envs x %d ticks per timed run (one tick per step), all %d host threads" % (n_envs, args.steps, v.threads_used)
+    w = max(3, args.warmup)
+    port = None
+    if python_reference_available(args):
+        # a "step" = one tick of every env of every worker; envs per worker sized so that the timed region is ~10 s of
+        # host work when --steps is small, and the untimed pre-roll (1500 ticks of Python) stays near a minute
+        e = args.ref_envs_per_proc or int(max(8, min(64, 12000 // max(1, args.steps))))
+        base = python_reference_rate(args, steps=args.steps, envs_per_proc=e, warmup=w)
+        port = cpu_port_rate(min(args.cpu_seconds, 6.0), args.preroll, seed=args.seed)
+        dt = base["seconds"]
+    else:
+        from oracle import oracle_lib as O
+        rate = cpu_port_rate(2.0, 0, n_envs=2048, chunk=10, seed=args.seed)["value"]
+        total_ticks = max(1, args.steps + w + args.preroll)
+        n_envs = int(max(64, min(args.envs, rate * 60.0 / total_ticks)))
+        n_envs = max(64, (n_envs // 64) * 64)
+        v = O.OracleVec(n_envs, seed=args.seed, first_env_id=0)
+        v.run(0)
+        v.run(args.preroll)
+        for _ in range(w):
+            v.run(1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            v.run(1)
+        dt = time.perf_counter() - t0
+        base = {"value": n_envs * args.steps / dt, "unit": UNIT, "cores": v.threads_used, "kind": "port",
+                "sample": "%d envs x %d ticks per timed run (one tick per step), C port on all %d host threads" % (n_envs, args.steps, v.threads_used)}
+    value = base["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": w, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": n_envs,
-                   "note": "reference is pure Python and does not travel to the GPU box; this arm times the pinned C port of its "
-                           "algorithm (oracle/) on the host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": v.threads_used, "kind": "port", "sample": sample},
+        "config": bench_config(args),
+        "cpu_baseline": base,
+        "cpu_baseline_port": port,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "kind=reference: the UNMODIFIED Python reference (oracle/_ref, copied from the reference tree by oracle/build_ref.py) on "
+                "os.cpu_count() processes, a bounded sample of the workload (the per-step sample is in cpu_baseline.sample); "
+                "cpu_baseline_port: the pinned C restatement of the same algorithm on all host threads, for scale",
     }
     print(json.dumps(line))
     return 0
@@ -220,6 +268,11 @@ def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_grou
     return n * world * steps / float(te.item()), errs_e2e
 
 
+def _lib_record_bytes() -> int:
+    from settlers_of_catan_rl_b200 import _lib
+    return int(_lib.load().catan_record_bytes())
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -242,16 +295,24 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
 
     n = args.envs
+    rec_bytes = _lib_record_bytes()
     # games are numbered globally: rank r owns [r*n, (r+1)*n) — no data-path collective
     env = VecCatanEnv(n, device=dev, seed=args.seed, first_env_id=rank * n)
     env.reset()
     acts = env.sample_random()
-    for _ in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    # untimed pre-roll to the steady state: the games are in every phase by tick `preroll`.  The clock
+    # sampler (nvidia-smi every 100 ms) is started for the last CLOCK_LEAD ticks of it, runs through the timed region and a
+    # tail of CLOCK_TAIL further ticks of the same workload, so that it sees >= 1 s of this load even when --steps is small.
+    CLOCK_LEAD, CLOCK_TAIL = min(1000, args.preroll), 2000
+    for _ in range(args.preroll - CLOCK_LEAD):
         env.step_sample(acts)
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(CLOCK_LEAD + warm):
+        env.step_sample(acts)
     launches0 = env.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -262,14 +323,19 @@ def run_b200_arm(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = env.kernel_launches - launches0
+    for _ in range(CLOCK_TAIL):
+        env.step_sample(acts)
+    torch.cuda.synchronize()
     clock_info = clocks.stop() if rank == 0 else None
+    if clock_info is not None:
+        clock_info["window"] = "last %d pre-roll ticks + warm-up + the timed region + %d further ticks of the same workload" % (CLOCK_LEAD, CLOCK_TAIL)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     # per-kernel durations for the roofline: CUDA events recorded by the library around the two kernels of a step on this
     # stream (catan_set_timing), over `kernel_steps` further steps of the same games -- outside the timed region above
-    kernel_steps = min(200, args.steps)
+    kernel_steps = 200
     env.set_timing(True)
     for _ in range(kernel_steps):
         env.step_sample(acts)
@@ -324,7 +390,7 @@ def run_b200_arm(args):
     # groups in flight, RL/ppo/vec_gather_experience.py); each half's step still depends on that half's previous result.
     e2e_pipe_error = None
     try:
-        e2e_pipe, e2e_pipe_errs = e2e_double_buffered(n, e2e_steps * 10, min(1000, max(3, args.warmup) + args.steps), dev, args.seed, rank, world,
+        e2e_pipe, e2e_pipe_errs = e2e_double_buffered(n, e2e_steps * 10, args.preroll + warm, dev, args.seed, rank, world,
                                                       max(1, args.e2e_groups), barrier)
     except Exception as exc:  # reported, never hidden: the synchronous loop above then stands as e2e
         e2e_pipe, e2e_pipe_errs, e2e_pipe_error = 0.0, -1, "%s: %s" % (type(exc).__name__, exc)
@@ -399,10 +465,26 @@ def run_b200_arm(args):
             aux["policy_inputs_%s_N%d" % (pname, n)] = {"ms": pms, "GB/s": n * pbytes / pms / 1e6, "bytes_per_row": pbytes}
             del pin
 
-    cpu_baseline = None
+    # ---- cpu_baseline (rank 0, N=1 only): the UNMODIFIED reference on the box's host cores, the pinned C port beside it, and
+    # the reference's GAE + advantage-normalisation lines on CPU tensors beside aux.gae_* / aux.adv_norm_*
+    cpu_baseline = cpu_baseline_port = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, threads, sample = cpu_rollout_rate(args.cpu_seconds, seed=args.seed)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        cpu_baseline_port = cpu_port_rate(min(args.cpu_seconds, 8.0), args.preroll, seed=args.seed)
+        if python_reference_available(args):
+            try:
+                cpu_baseline = python_reference_rate(args, steps=None, seconds=args.cpu_seconds, envs_per_proc=8)
+            except Exception as exc:  # reported, never hidden: the port then stands as the baseline
+                cpu_baseline_port["python_reference_error"] = "%s: %s" % (type(exc).__name__, exc)
+        if cpu_baseline is None:
+            cpu_baseline, cpu_baseline_port = cpu_baseline_port, None
+        try:
+            from oracle import ref_bench
+            g = ref_bench.time_reference_gae(200, 131072, reps=1)
+            aux["gae_plus_adv_norm_cpu_reference_T200_N131072"] = g
+            if "gae_T200_N131072" in aux:
+                aux["gae_plus_adv_norm_T200_N131072_speedup_vs_cpu_reference"] = g["ms"] / (aux["gae_T200_N131072"]["ms"] + aux["adv_norm_T200_N131072"]["ms"])
+        except Exception as exc:
+            aux["gae_cpu_reference_error"] = "%s: %s" % (type(exc).__name__, exc)
 
     e2e_sync = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
                 "call": "VecCatanEnv.step_host -> catan_step_host, one handle: pinned host actions in, reward+done/info rows out to "
@@ -435,10 +517,9 @@ def run_b200_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "seed": args.seed,
-                       "l2": "no explicit flush: one step streams %.0f MB (records+obs+masks+actions) > 126 MB L2" % (
-                           n * (2 * 832 + L.OBS_STRIDE + L.MASK_STRIDE + 160 + 32) / 1e6),
-                       "games_finished_in_last_step": games_done, "rejected_actions": errs},
+            "config": bench_config(args),
+            "detail": {"games_finished_in_last_step": games_done, "rejected_actions": errs, "preroll_ticks": args.preroll,
+                       "streamed_MB_per_step": n * (2 * rec_bytes + L.OBS_STRIDE + L.MASK_STRIDE + 160 + 32) / 1e6},
             "clocks": clock_info,
             "e2e": e2e_best,
             "e2e_other": e2e_other,
@@ -446,7 +527,11 @@ def run_b200_arm(args):
                                      "steps": e2e_steps, "call": "same call with obs+masks rows also copied to pinned host (PCIe-bound)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "encode_kernel<MODE_STEP, SAMPLE> (obs + mask rows + sampler)",
+                         "traffic": traffic, "traffic_source": "profiles/traffic.json (one ncu --set full capture of this kernel, dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "obs_write_only": {"bytes_per_env_step": 1867, "achieved": 1867 * n / (per_launch_ms * 1e-3) / 1e9,
+                                            "frac": 1867 * n / (per_launch_ms * 1e-3) / 1e9 / peak,
+                                            "note": "north_star's obs-write roofline: the 1 867 obs bytes of every env step over the WHOLE step time"},
+                         "kernel": "encode_kernel<MODE_STEP, SAMPLE> (obs + mask rows + sampler)",
                          "algorithmic_bytes_per_launch": ENCODE_BYTES_PER_ENV_STEP * n, "peak_source": peak_src,
                          "kernel_ms": encode_ms, "timed_launches": timed_n,
                          "how": "CUDA events recorded by the library around the kernel on the launching stream (catan_set_timing)",
@@ -457,6 +542,7 @@ def run_b200_arm(args):
                                         "note": "6 launches on 2 streams: transition, encode | longest-road search, encode of "
                                                 "the searched games, copy-back, counter bookkeeping"}},
             "cpu_baseline": cpu_baseline,
+            "cpu_baseline_port": cpu_baseline_port,
             "aux": aux,
         }
         print(json.dumps(line))

@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE — drives the *real* reference (``/root/reference``) to pin the oracle.
 
 Only ``tests/`` and the fixture generator (``oracle/make_golden.py``) import this module.  It is
-never on the product path and it only works where ``/root/reference`` exists (this container, not
-the GPU box): the GPU tests replay the committed fixtures under ``tests/golden/`` instead.
+never on the product path.  It needs the reference tree: ``/root/reference`` in this container, or the
+git-ignored copy ``oracle/_ref/`` that ``oracle/build_ref.py`` makes and that travels to the GPU box; the GPU
+parity tests additionally replay the committed fixtures under ``tests/golden/``.
 
 What it does:
   * imports ``env.wrapper.EnvWrapper`` headless by stubbing ``ui.display`` / pygame / tkinter
@@ -30,7 +31,10 @@ sys.path.insert(0, os.path.dirname(_HERE))
 
 from settlers_of_catan_rl_b200 import layout as L  # noqa: E402
 
-REFERENCE_ROOT = os.environ.get("CATAN_REFERENCE_ROOT", "/root/reference")
+from oracle import build_ref as _build_ref  # noqa: E402
+
+#: the mounted reference where it exists (this container), else the copy oracle/build_ref.py made (the GPU box)
+REFERENCE_ROOT = os.environ.get("CATAN_REFERENCE_ROOT") or _build_ref.root() or "/root/reference"
 
 
 def reference_available() -> bool:
