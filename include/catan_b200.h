@@ -150,7 +150,7 @@ typedef struct catan_rollout {
   float* rewards;             /* [T][N]                                         process_batch.py:61-65 */
   float* tmasks;              /* [T+1][N] terminal masks                        process_batch.py:98-103 */
   int32_t* cursors;           /* [N][4]  lengths of the env's obs / action / reward / terminal-mask lists */
-  float* acc;                 /* [N][4]  running reward sums per player (game_manager.py:94-95) */
+  double* acc;                /* [N][4]  running reward sums per player, fp64 like the reference's Python floats (game_manager.py:94-95) */
   uint8_t* flags;             /* [N]     bit 0 = done_since_prev_turn (game_manager.py:77,134-136), bit 1 = last terminal mask */
   const uint8_t* active_pid;  /* [N]     the recorded seat's PlayerId (game_manager.py:26-27) */
   uint8_t* collecting;        /* [N] out (may be NULL): 1 while the env still needs observations -> catan_step_masked */

@@ -1,6 +1,9 @@
 """TEST INFRASTRUCTURE — line-by-line restatement of the reference's rollout collector for ONE env
 (RL/ppo/game_manager.py:34-150), driven by recorded tick events instead of live policies.
 
+PINNED: ``tests/test_rollout_vs_reference.py`` runs the reference's unchanged manager (oracle/manager_harness.py) and checks
+this restatement list for list over consecutive rollouts with games ending inside the window.
+
 The reference loop body (:78-136) is kept statement for statement; `tick()` is one iteration of the `while`
 loop for this env, `reset()` is GamesAndPoliciesManager.reset (:34-56), `after_rollouts()` is :142-150.
 """

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(128) rollout_store_kernel(const RolloutArgs A)
   if (e >= R.N) return;
   const int T = R.T, N = R.N;
   int32_t* cur = R.cursors + static_cast<size_t>(e) * 4;          // n_obs, n_act, n_rew, n_tm
-  float* acc = R.acc + static_cast<size_t>(e) * 4;
+  double* acc = R.acc + static_cast<size_t>(e) * 4;                // doubles: the reference sums Python floats (game_manager.py:94-95)
   const int active = R.active_pid[e];
   int n_obs = cur[0], n_act = cur[1], n_rew = cur[2], n_tm = cur[3];
   int flags = R.flags[e];                                          // bit 0: done_since_prev_turn, bit 1: last terminal mask
@@ -434,14 +434,14 @@ __global__ void __launch_bounds__(128) rollout_store_kernel(const RolloutArgs A)
       if (lane == 0 && n_tm > 0) R.tmasks[e] = (flags & 2) ? 1.0f : 0.0f;   // terminal_masks[-1], even when it lay beyond the buffer
       n_obs = n_obs > 0 ? 1 : 0; n_tm = n_tm > 0 ? 1 : 0; n_act = 0; n_rew = 0;
     }
-    if (lane < 4) acc[lane] = 0.0f;                                // game_manager.py:76-77: per-call locals
+    if (lane < 4) acc[lane] = 0.0;                                 // game_manager.py:76-77: per-call locals
     flags &= 2;                                                    // bit 1 = value of the last terminal mask, kept
   } else if ((A.stepped == nullptr || A.stepped[e]) && n_obs < T + 1) {
     const int pg = info[CATAN_INFO_ACTED], n_pg_pre = info[CATAN_INFO_ACTOR_PRE], n_pg = info[CATAN_INFO_ACTOR];
     const bool done = info[CATAN_INFO_DONE] != 0;
-    float a_acc = acc[active - 1] + A.env_reward[static_cast<size_t>(e) * 4 + active - 1];     // :94-95
+    double a_acc = acc[active - 1] + static_cast<double>(A.env_reward[static_cast<size_t>(e) * 4 + active - 1]);     // :94-95
     __syncwarp();
-    if (lane < 4) acc[lane] += A.env_reward[static_cast<size_t>(e) * 4 + lane];
+    if (lane < 4) acc[lane] += static_cast<double>(A.env_reward[static_cast<size_t>(e) * 4 + lane]);
     bool reward_updated = false;
     // The reference's lists may grow past what process_rollouts reads (T rows, T+1 for obs / terminal masks): e.g. the
     // terminal-mask list leads by one when the first observation of a rollout was not the active seat's.  Entries
@@ -453,21 +453,21 @@ __global__ void __launch_bounds__(128) rollout_store_kernel(const RolloutArgs A)
       n_act += 1;
     }
     if (n_pg_pre == active && n_act > 0 && !(flags & 1)) {         // :106-110
-      if (n_rew < T && lane == 0) R.rewards[static_cast<size_t>(n_rew) * N + e] = a_acc;
-      n_rew += 1; a_acc = 0.0f; reward_updated = true;
+      if (n_rew < T && lane == 0) R.rewards[static_cast<size_t>(n_rew) * N + e] = static_cast<float>(a_acc);
+      n_rew += 1; a_acc = 0.0; reward_updated = true;
       __syncwarp();
-      if (lane == 0) acc[active - 1] = 0.0f;
+      if (lane == 0) acc[active - 1] = 0.0;
     }
     if (done) {                                                    // :112-124
       if (n_tm <= T && lane == 0) R.tmasks[static_cast<size_t>(n_tm) * N + e] = 0.0f;
       n_tm += 1;
       flags &= ~3;
       if (!reward_updated) {
-        if (n_rew < T && lane == 0) R.rewards[static_cast<size_t>(n_rew) * N + e] = a_acc;
+        if (n_rew < T && lane == 0) R.rewards[static_cast<size_t>(n_rew) * N + e] = static_cast<float>(a_acc);
         n_rew += 1;
       }
       __syncwarp();
-      if (lane < 4) acc[lane] = 0.0f;
+      if (lane < 4) acc[lane] = 0.0;
     }
     if (n_pg == active) {                                          // :128-133
       if (!done && !(flags & 1)) {

@@ -64,7 +64,7 @@ class _GameView:
 class EnvWrapper(object):
     def __init__(self, interactive=False, max_actions_per_turn=None, max_proposed_trades_per_turn=4,
                  validate_actions=True, debug_mode=False, win_reward=500, dense_reward=False, policies=None,
-                 device="cuda:0", seed=0, env_id=None):
+                 device="cuda:0", seed=0, env_id=None, _engine=None):
         if interactive:
             raise NotImplementedError("the pygame UI is outside the hot path (SURVEY.md §2 row 16)")
         if env_id is None:
@@ -75,11 +75,16 @@ class EnvWrapper(object):
         self.validate_actions = validate_actions
         self.win_reward = win_reward
         self.dense_reward = dense_reward
-        self._vec = VecCatanEnv(
-            1, device=device, seed=seed, first_env_id=env_id, auto_reset=0,
+        cfg = dict(
+            auto_reset=0,
             max_actions_per_turn=-1 if max_actions_per_turn is None else int(max_actions_per_turn),
             max_proposed_trades_per_turn=-1 if max_proposed_trades_per_turn is None else int(max_proposed_trades_per_turn),
             validate_actions=int(bool(validate_actions)), dense_reward=int(bool(dense_reward)), win_reward=float(win_reward))
+        # `_engine` is a TEST hook: tests/host_emu compiles the product's game logic (csrc/catan_game.cuh) with g++ so that the
+        # reference's unchanged managers can be run over this adapter in the CPU-only container.  The product always runs the
+        # CUDA engine; there is no CPU path in the package.
+        self._vec = _engine(seed=seed, env_id=env_id, **cfg) if _engine is not None else VecCatanEnv(
+            1, device=device, seed=seed, first_env_id=env_id, **cfg)
         self._obs = np.zeros((1, L.OBS_STRIDE), np.uint8)
         self._masks = np.zeros((1, L.MASK_STRIDE), np.uint8)
         self._reward = np.zeros((1, 4), np.float32)
@@ -149,8 +154,7 @@ class EnvWrapper(object):
     def restore_state(self, state):
         self._started = True
         self._vec.import_state(state["state"][None, :])
-        self._obs[:] = self._vec.obs.cpu().numpy()
-        self._masks[:] = self._vec.masks.cpu().numpy()
+        self._obs[:], self._masks[:] = self._vec.rows_host()
         self._game = None
         self.curr_vps = dict(state["vps"])
         self.winner = state["winner"]

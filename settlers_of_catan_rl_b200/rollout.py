@@ -90,7 +90,7 @@ class RolloutStorage:
         self.rewards = torch.zeros((T, N), dtype=torch.float32, device=dev)
         self.tmasks = torch.ones((T + 1, N), dtype=torch.float32, device=dev)
         self.cursors = torch.zeros((N, 4), dtype=torch.int32, device=dev)
-        self.acc = torch.zeros((N, 4), dtype=torch.float32, device=dev)
+        self.acc = torch.zeros((N, 4), dtype=torch.float64, device=dev)
         self.flags = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.collecting = torch.ones(N, dtype=torch.uint8, device=dev)
         if active_pid is None:   # game_manager.py:24-27: a random seat per env is the recorded one

@@ -142,6 +142,10 @@ class VecCatanEnv:
         _lib.check(self.lib.catan_import_state(self._h, first, states.shape[0], C.c_void_p(states.ctypes.data)))
         self.kernel_launches += 1
 
+    def rows_host(self):
+        """(obs rows, mask rows) of all envs as numpy arrays (a D2H copy; used by the single-env adapter after an import)"""
+        return self.obs.cpu().numpy(), self.masks.cpu().numpy()
+
     def route_by_policy(self, policy_map: torch.Tensor, n_policies: int, active: Optional[torch.Tensor] = None):
         """game_manager.py:21-31 / :82-93 vectorised: ``policy_map`` uint8 [N,4] = policy index playing PlayerId p+1 in env n.
         Returns (counts int32 [K], lists int32 [K,N]): ``lists[k, :counts[k]]`` are the envs (ascending) whose next decision

@@ -148,3 +148,48 @@ def test_policy_routing_lists_match_the_reference_maps():
                 assert c == want.numel() and torch.equal(lists[k, :c], want), (tick, k)
                 total += c
             assert total == (n if act is None else int(active.sum()))
+
+
+def test_rollout_store_replays_the_reference_managers_tape():
+    """tests/golden/rollout_manager_tape.npz = the UNCHANGED reference ``GamesAndPoliciesManager`` (game_manager.py:34-150) over
+    the reference env with dense rewards, nine consecutive rollouts, recorded by oracle/make_rollout_golden.py.  The CUDA env
+    plays the same games from the recorded actions (shared Philox stream), ``catan_rollout_store`` collects, and every
+    buffer must equal what ``process_rollouts`` (process_batch.py:37-104) would stack from the manager's lists: obs / masks /
+    actions / log-probs / terminal masks bit for bit, rewards to fp32 rounding of the reference's double sums."""
+    import os
+    from settlers_of_catan_rl_b200 import VecCatanEnv, RolloutStorage
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollout_manager_tape.npz")))
+    T, N, R = int(g["T"]), g["active_pid"].shape[0], g["obs"].shape[0]
+    env = VecCatanEnv(N, seed=int(g["seed"]), first_env_id=int(g["first_env_id"]), dense_reward=1)
+    env.reset()
+    store = RolloutStorage(env, T, torch.from_numpy(g["active_pid"]))
+    tape_a = torch.from_numpy(g["tape_actions"]).to(env.device)           # [N, S, 20]
+    tape_lp = torch.from_numpy(g["tape_logp"]).to(env.device)
+    k = torch.zeros(N, dtype=torch.int64, device=env.device)                # next decision of every env
+    rows = torch.arange(N, device=env.device)
+    for r in range(R):
+        store.begin(fresh=(r == 0))
+        ticks = 0
+        while not store.finished():
+            ticks += 1
+            assert ticks < 20000
+            stepped = store.collecting.clone()
+            acts = tape_a[rows, k].contiguous()
+            logp = tape_lp[rows, k].contiguous()
+            env.step(acts, step_mask=stepped)
+            store.record(acts, logp, stepped)
+            k += stepped.long()
+        assert int(env.err_flags().any()) == 0
+        cur = store.cursors.cpu().numpy()
+        assert np.array_equal(cur, g["lengths"][r]), (r, cur, g["lengths"][r])
+        assert np.array_equal(store.obs.cpu().numpy(), g["obs"][r]), r
+        got_masks, got_act, got_lp = store.masks.cpu().numpy(), store.actions.cpu().numpy(), store.logp.cpu().numpy()
+        got_rew, got_tm = store.rewards.cpu().numpy(), store.tmasks.cpu().numpy()
+        for e in range(N):
+            n_obs, n_act, n_rew, n_tm = (int(x) for x in g["lengths"][r, e])
+            assert np.array_equal(got_masks[:min(n_act, T), e], g["masks"][r, :min(n_act, T), e]), (r, e)
+            assert np.array_equal(got_act[:min(n_act, T), e], g["actions"][r, :min(n_act, T), e]), (r, e)
+            assert np.array_equal(got_lp[:min(n_act, T), e], g["logp"][r, :min(n_act, T), e]), (r, e)
+            assert np.allclose(got_rew[:min(n_rew, T), e], g["rewards"][r, :min(n_rew, T), e], rtol=1e-6, atol=1e-6), (r, e)
+            assert np.array_equal(got_tm[:min(n_tm, T + 1), e], g["tmasks"][r, :min(n_tm, T + 1), e]), (r, e)
+    assert np.array_equal(k.cpu().numpy(), g["tape_len"]), "every recorded decision was consumed, and no more"
