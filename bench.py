@@ -46,6 +46,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--config", choices=["env", "ppo16k", "ppo131k", "ppo8x"], default="env",
+                    help="env: BASELINE configs[1] (the headline, default); ppo16k / ppo131k / ppo8x: BASELINE configs[2] / [3] / [4], "
+                         "whole PPO self-play cycles (rollouts + 10 epochs x 64 minibatches), --steps = cycles timed (default 1)")
+    ap.add_argument("--ppo-envs", type=int, default=0, help="PPO configs: envs per GPU (0: the BASELINE config's)")
+    ap.add_argument("--ppo-micro-batch", type=int, default=51200)
+    ap.add_argument("--checkpoint", default="", help="PPO configs: a reference state_dict to start from (default: seeded random init)")
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU, help="games per GPU (default: the BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--e2e-groups", type=int, default=6, help="handles (env groups) kept in flight by the double-buffered e2e loop")
@@ -551,8 +557,96 @@ def run_b200_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------
+# PPO self-play configs (BASELINE configs[2..4]): env steps/s AND PPO updates/s over whole run_update cycles
+# ------------------------------------------------------------------------------------------------
+PPO_CONFIGS = {
+    "ppo16k": dict(envs=16384, dtype="float32", workload="PPO self-play, repo default policy net (1 928 995 parameters, fp32), 16384 envs, 1xB200 (BASELINE configs[2])"),
+    "ppo131k": dict(envs=131072, dtype="bfloat16", workload="PPO self-play, 131072 envs, bf16 policy (autocast), 1xB200, GAE + advantage-norm kernels (BASELINE configs[3])"),
+    "ppo8x": dict(envs=65536, dtype="bfloat16", workload="PPO self-play, 65536 envs per GPU (524288 over 8), bf16 policy, NCCL all-reduce of the flat gradient bucket (BASELINE configs[4])"),
+}
+
+
+def run_ppo_arm(args):
+    import torch
+    import torch.distributed as dist
+    from settlers_of_catan_rl_b200 import SelfPlayTrainer, PPOConfig, CatanPolicy
+
+    pc = PPO_CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.ppo_envs or pc["envs"]
+    dtype = getattr(torch, pc["dtype"])
+    torch.manual_seed(args.seed)
+    policy = CatanPolicy()
+    if args.checkpoint:
+        policy.load_reference_state_dict(torch.load(args.checkpoint, map_location="cpu", weights_only=False))
+    cfg = PPOConfig(dtype=dtype, micro_batch=args.ppo_micro_batch)
+    tr = SelfPlayTrainer(n, policy, cfg, device=dev, seed=args.seed, first_env_id=rank * n, group=True if world > 1 else None)
+    cycles = args.steps if args.steps != 2000 else 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up, untimed: graph capture + one whole rollout (games leave the opening), and two optimiser steps whose effect is undone
+    t0 = time.perf_counter()
+    tr.collect()
+    tr.warmup_update()
+    warm_s = time.perf_counter() - t0
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    outs = [tr.run_update() for _ in range(cycles)]
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    steps = torch.tensor([float(sum(o["env_steps"] for o in outs))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(steps, op=dist.ReduceOp.SUM)
+    clock_info = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        sec = float(ms.item()) * 1e-3
+        o = outs[-1]
+        opt_steps = sum(x["optimiser_steps"] for x in outs)
+        line = {
+            "metric": METRIC, "value": float(steps.item()) / sec, "unit": UNIT, "n_gpus": world, "steps": cycles, "warmup": 1,
+            "ms_per_step": 1e3 * sec / cycles, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if dtype == torch.bfloat16 else "fp32", "data": "synthetic (seeded random-init policy weights; games generated by the engine)",
+            "config": {"workload": pc["workload"], "envs_per_gpu": n, "seed": args.seed, "num_steps": cfg.num_steps, "ppo_epoch": cfg.ppo_epoch,
+                       "num_mini_batch": cfg.num_mini_batch, "micro_batch": tr.micro, "step": "one run_update cycle (robust_train.py:95-156): rollouts until every env "
+                       "holds 200 decisions of its recorded seat, then 10 epochs x (value pass over 201 x N obs + GAE + advantage norm + 64 minibatch steps)"},
+            "ppo": {"updates_per_sec": cycles / sec, "optimiser_steps_per_sec": opt_steps / sec, "recorded_decisions_per_sec": cycles * tr.T * n * world / sec,
+                    "collect_ms": o["collect_ms"], "update_ms": o["update_ms"], "ticks_per_rollout": o["ticks"], "env_steps_per_rollout_per_gpu": o["env_steps"],
+                    "rollout_env_steps_per_sec": o["env_steps"] * world / (o["collect_ms"] * 1e-3), "value_loss": o["value_loss"], "action_loss": o["action_loss"],
+                    "entropy": o["entropy"], "games_finished_in_rollout": o["games_finished"], "warmup_s": warm_s,
+                    "grad_allreduce": None if world == 1 else "flat fp32 bucket of %d bytes, one NCCL all-reduce (AVG) per optimiser step; advantage statistics: 24 B per epoch" % (tr.flat_grad.numel() * 4)},
+            "clocks": clock_info,
+            "gpu_launches": None,
+            "e2e": None,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.config != "env" and args.impl == "b200":
+        return run_ppo_arm(args)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)

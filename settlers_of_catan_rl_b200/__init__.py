@@ -7,7 +7,8 @@ lazily; there is no CPU implementation.
 """
 from . import layout  # noqa: F401
 
-__all__ = ["layout", "VecCatanEnv", "EnvWrapper", "gae", "normalise_advantages", "RolloutStorage", "PolicyInputs", "SeatPolicies"]
+__all__ = ["layout", "VecCatanEnv", "EnvWrapper", "gae", "normalise_advantages", "RolloutStorage", "PolicyInputs", "SeatPolicies",
+           "CatanPolicy", "SelfPlayTrainer", "PPOConfig"]
 
 
 def __getattr__(name):
@@ -26,4 +27,10 @@ def __getattr__(name):
     if name == "SeatPolicies":
         from .self_play import SeatPolicies
         return SeatPolicies
+    if name == "CatanPolicy":
+        from .policy_net import CatanPolicy
+        return CatanPolicy
+    if name in ("SelfPlayTrainer", "PPOConfig"):
+        from . import ppo
+        return getattr(ppo, name)
     raise AttributeError(name)

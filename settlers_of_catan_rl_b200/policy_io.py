@@ -89,6 +89,9 @@ class PolicyInputs:
 def actions_to_rows(actions: Sequence, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The 12 sampled heads of ``policy.act`` (``[B, 1]`` long tensors; heads 7 / 8 a list of four of them, or ``[B, 4]``) ->
     int32 ``[B, 20]`` action rows (catan_layout.h; policy.py:192-199 + wrapper.py:114-166 read them in this order)."""
+    if isinstance(actions, torch.Tensor):                  # already action rows (CatanPolicy.act)
+        assert actions.dim() == 2 and actions.shape[1] == L.ACTION_WORDS
+        return actions.to(torch.int32)
     cols = []
     for h in range(12):
         a = actions[h]
