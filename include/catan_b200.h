@@ -203,6 +203,21 @@ int catan_masked_categorical(const float* logits_dev, const float* mask_dev, con
                              const float* uniforms_dev, int B, int D, int64_t* actions_dev, float* logp_dev,
                              float* entropy_dev, void* stream);
 
+/* ---- the two small-dimension pieces of the policy network that the library kernels handle badly at rollout batch sizes ------
+ * (the network itself stays PyTorch; these are autograd functions on its side, settlers_of_catan_rl_b200/policy_ops.py)
+ * catan_tile_attention_*: the tile encoder's self-attention (RL/models/tile_encoder.py:43-57, multi_headed_attention.py:28-39):
+ *   qkv fp32 [B][19][192] (q | k | v, 4 heads of 16) -> y fp32 [B][19][64] = concat_h softmax(q k^T / 4) v; the backward takes
+ *   dy and returns dqkv.  16-byte aligned, contiguous.
+ * catan_ln_small_*: LayerNorm over a last dimension dim <= 64 (tile_encoder.py:38, :75-76; player_modules.py:29-33) of `rows`
+ *   contiguous fp32 rows; stats [rows][2] = (mean, 1 / std) is written by the forward (may be NULL) and read by the backward,
+ *   which ACCUMULATES into dweight / dbias (zero them first). */
+int catan_tile_attention_fwd(const float* qkv_dev, float* y_dev, int B, void* stream);
+int catan_tile_attention_bwd(const float* qkv_dev, const float* dy_dev, float* dqkv_dev, int B, void* stream);
+int catan_ln_small_fwd(const float* x_dev, const float* weight_dev, const float* bias_dev, float* y_dev, float* stats_dev, long long rows,
+                       int dim, float eps, void* stream);
+int catan_ln_small_bwd(const float* x_dev, const float* weight_dev, const float* stats_dev, const float* dy_dev, float* dx_dev,
+                       float* dweight_dev, float* dbias_dev, long long rows, int dim, void* stream);
+
 /* ---- minibatch generator (RL/ppo/process_batch.py:169-200, generator_standard) --------------------
  * The reference draws a random permutation of the T*N (time, env) pairs, cuts it into num_mini_batch index lists and, for
  * each, indexes every CPU buffer key by key and copies the pieces to the device.  Here the rollout buffers are already in

@@ -86,6 +86,10 @@ ABI = {
     "catan_policy_inputs": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "catan_masked_categorical": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "catan_minibatch_gather": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "catan_tile_attention_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "catan_tile_attention_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "catan_ln_small_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_float, _vp]),
+    "catan_ln_small_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, C.c_int, _vp]),
 }
 
 _lib = None

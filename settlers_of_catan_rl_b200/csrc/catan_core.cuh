@@ -64,13 +64,16 @@ static_assert(sizeof(Topo) == 1008, "Topo must stay a multiple of 16 bytes");
    {0, 0, 0, 0, 0, 0}}
 
 // ------------------------------------------------------------------------------------------------
-// packed per-game record: 832 bytes.  In HBM 32 records are interleaved into one chunk (catan_game.cuh: GameView).
+// packed per-game record: 832 bytes (the card lists are 4-bit codes: 208 -> 104 bytes, which pays for the production cache).  In HBM 32 records are interleaved into one chunk (catan_game.cuh: GameView).
 // Field meaning == catan_state_t (catan_layout.h).
 // ------------------------------------------------------------------------------------------------
 struct alignas(16) GameRec {
   int16_t est_min[4][3][5];   // opponent_min_res[observer][label][r]        (player.py:38-43)
   int16_t est_max[4][3][5];
   int16_t vis[4][5];          // visible_resources (unbounded growth through trades -> 16 bit)
+  uint16_t prod[4][13];       // engine-private cache of the observation's production table (wrapper.py:595-610): 4-bit counts,
+                              // entry j = slot * 10 + number slot in the obs order at bits 4 * (j & 3) of prod[p][j >> 2]; kept
+                              // current by the transition (a settlement adds 1, a city one more per adjacent tile)
   uint32_t rng_ctr;           // game-stream Philox draw counter
   uint32_t decision_ctr;      // sampler-stream decision index
   uint32_t episode_steps;     // env steps since the last reset
@@ -95,8 +98,8 @@ struct alignas(16) GameRec {
   uint8_t cur_longest_path[4];
   uint8_t has_path_key[4];
   uint8_t cur_army[4];
-  uint8_t hidden[4][25];
-  uint8_t played[4][25];
+  uint8_t hidden[4][13];      // ordered card lists, two cards per byte (card i at bits 4 * (i & 1) of byte i >> 1; unused = 0)
+  uint8_t played[4][13];
   uint8_t bank[5];
   uint8_t deck_n;
   uint8_t deck[25];
@@ -117,7 +120,7 @@ struct alignas(16) GameRec {
   uint8_t winner;
   uint8_t lr_dirty[4];        // engine-private (not part of the canonical state): an opponent built next to this player's
                               // roads since cur_longest_path was measured -> the incremental update is not allowed
-  uint8_t pad_[9];
+  uint8_t pad_[1];
 };
 static_assert(sizeof(GameRec) == 832, "GameRec layout changed: keep it a multiple of 16 bytes and update DESIGN.md");
 
@@ -369,7 +372,10 @@ static inline void rec_to_state(const GameRec& g, catan_state_t& s) {
     }
     s.vp[p] = g.vp[p]; s.harbours[p] = g.harbours[p];
     s.n_hidden[p] = g.n_hidden[p]; s.n_played[p] = g.n_played[p];
-    for (int i = 0; i < 25; ++i) { s.hidden[p][i] = g.hidden[p][i]; s.played[p][i] = g.played[p][i]; }
+    for (int i = 0; i < 25; ++i) {
+      s.hidden[p][i] = i < g.n_hidden[p] ? (g.hidden[p][i >> 1] >> (4 * (i & 1))) & 15 : 0;
+      s.played[p][i] = i < g.n_played[p] ? (g.played[p][i >> 1] >> (4 * (i & 1))) & 15 : 0;
+    }
     s.settlements_left[p] = g.settlements_left[p]; s.cities_left[p] = g.cities_left[p];
     s.init_settlements[p] = g.init_settlements[p]; s.init_roads[p] = g.init_roads[p];
     s.second_corner[p] = g.second_corner[p];
@@ -395,6 +401,24 @@ static inline void rec_to_state(const GameRec& g, catan_state_t& s) {
   s.rng_ctr_lo = static_cast<int16_t>(g.rng_ctr & 0xFFFF); s.rng_ctr_hi = static_cast<int16_t>(g.rng_ctr >> 16);
 }
 
+// obs slot of resource index r (BRICK..WHEAT) in the order Wood, Brick, Wheat, Ore, Sheep (wrapper.py:550), and the number slot of
+// a token (2-6 -> 0-4, 8-12 -> 5-9; wrapper.py:600-604)
+#define CATAN_OBS_RES_SLOT(r_) ((0x24301 >> (4 * (r_))) & 7)
+#define CATAN_OBS_NUM_SLOT(v_) ((v_) <= 6 ? (v_) - 2 : (v_) - 3)
+// the production cache from scratch (host side: catan_import_state)
+static inline void rebuild_prod(GameRec& g) {
+  static const Topo T = CATAN_TOPO_INITIALIZER;
+  memset(g.prod, 0, sizeof(g.prod));
+  for (int t = 0; t < 19; ++t) {
+    if (g.tile_res[t] == 0 || g.tile_val[t] == 7) continue;
+    const int j = CATAN_OBS_RES_SLOT(g.tile_res[t] - 1) * 10 + CATAN_OBS_NUM_SLOT(g.tile_val[t]);
+    for (int k = 0; k < 6; ++k) {
+      const int b = g.corner[T.tile_corners[t][k]];
+      if (b) g.prod[(b >> 2) - 1][j >> 2] = static_cast<uint16_t>(g.prod[(b >> 2) - 1][j >> 2] + ((b & 3) << (4 * (j & 3))));
+    }
+  }
+}
+
 static inline void state_to_rec(const catan_state_t& s, GameRec& g) {
   const uint32_t dec = g.decision_ctr, steps = g.episode_steps;
   memset(&g, 0, sizeof(g));
@@ -413,7 +437,10 @@ static inline void state_to_rec(const catan_state_t& s, GameRec& g) {
     }
     g.vp[p] = static_cast<int8_t>(s.vp[p]); g.harbours[p] = static_cast<uint8_t>(s.harbours[p]);
     g.n_hidden[p] = static_cast<uint8_t>(s.n_hidden[p]); g.n_played[p] = static_cast<uint8_t>(s.n_played[p]);
-    for (int i = 0; i < 25; ++i) { g.hidden[p][i] = static_cast<uint8_t>(s.hidden[p][i]); g.played[p][i] = static_cast<uint8_t>(s.played[p][i]); }
+    for (int i = 0; i < 25; ++i) {                              // (entries beyond the list length stay zero: the encoder relies on it)
+      if (i < s.n_hidden[p]) g.hidden[p][i >> 1] |= static_cast<uint8_t>((s.hidden[p][i] & 15) << (4 * (i & 1)));
+      if (i < s.n_played[p]) g.played[p][i >> 1] |= static_cast<uint8_t>((s.played[p][i] & 15) << (4 * (i & 1)));
+    }
     g.settlements_left[p] = static_cast<uint8_t>(s.settlements_left[p]); g.cities_left[p] = static_cast<uint8_t>(s.cities_left[p]);
     g.init_settlements[p] = static_cast<uint8_t>(s.init_settlements[p]); g.init_roads[p] = static_cast<uint8_t>(s.init_roads[p]);
     g.second_corner[p] = static_cast<int8_t>(s.second_corner[p]);
@@ -444,6 +471,7 @@ static inline void state_to_rec(const catan_state_t& s, GameRec& g) {
   for (int c = 0; c < 5; ++c) g.bought[c] = static_cast<uint8_t>(s.bought[c]);
   g.winner = static_cast<uint8_t>(s.winner);
   for (int p = 0; p < 4; ++p) g.lr_dirty[p] = 1;   // nothing is known about how cur_longest_path relates to the imported board
+  rebuild_prod(g);
   g.rng_ctr = static_cast<uint32_t>(static_cast<uint16_t>(s.rng_ctr_lo)) | (static_cast<uint32_t>(static_cast<uint16_t>(s.rng_ctr_hi)) << 16);
 }
 

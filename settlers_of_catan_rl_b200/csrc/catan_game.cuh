@@ -17,6 +17,7 @@
 #pragma once
 
 #include <stddef.h>
+#include <type_traits>
 
 #include "catan_core.cuh"
 
@@ -46,7 +47,7 @@ struct GameView {
 #define CATAN_F1(T, name) CATAN_MFN T& name(int i) const { return at<T>(offsetof(GameRec, name), i); }
 #define CATAN_F2(T, name, B) CATAN_MFN T& name(int i, int j) const { return at<T>(offsetof(GameRec, name), i * (B) + j); }
 #define CATAN_F3(T, name, B, C_) CATAN_MFN T& name(int i, int j, int k) const { return at<T>(offsetof(GameRec, name), (i * (B) + j) * (C_) + k); }
-  CATAN_F3(int16_t, est_min, 3, 5) CATAN_F3(int16_t, est_max, 3, 5) CATAN_F2(int16_t, vis, 5)
+  CATAN_F3(int16_t, est_min, 3, 5) CATAN_F3(int16_t, est_max, 3, 5) CATAN_F2(int16_t, vis, 5) CATAN_F2(uint16_t, prod, 13)
   CATAN_F0(uint32_t, rng_ctr) CATAN_F0(uint32_t, decision_ctr) CATAN_F0(uint32_t, episode_steps)
   CATAN_F0(uint16_t, actions_this_turn) CATAN_F0(uint16_t, turn)
   CATAN_F1(uint8_t, corner) CATAN_F1(uint8_t, edge) CATAN_F1(uint8_t, tile_res) CATAN_F1(uint8_t, tile_val)
@@ -54,7 +55,7 @@ struct GameView {
   CATAN_F1(uint8_t, harbours) CATAN_F1(uint8_t, n_hidden) CATAN_F1(uint8_t, n_played) CATAN_F1(uint8_t, settlements_left)
   CATAN_F1(uint8_t, cities_left) CATAN_F1(uint8_t, init_settlements) CATAN_F1(uint8_t, init_roads) CATAN_F1(int8_t, second_corner)
   CATAN_F1(uint8_t, cur_longest_path) CATAN_F1(uint8_t, has_path_key) CATAN_F1(uint8_t, cur_army)
-  CATAN_F2(uint8_t, hidden, 25) CATAN_F2(uint8_t, played, 25) CATAN_F1(uint8_t, bank) CATAN_F0(uint8_t, deck_n) CATAN_F1(uint8_t, deck)
+  CATAN_F2(uint8_t, hidden, 13) CATAN_F2(uint8_t, played, 13) CATAN_F1(uint8_t, bank) CATAN_F0(uint8_t, deck_n) CATAN_F1(uint8_t, deck)
   CATAN_F1(uint8_t, player_order) CATAN_F0(uint8_t, player_order_id) CATAN_F0(uint8_t, players_go)
   CATAN_F0(uint8_t, lr_holder) CATAN_F0(uint8_t, lr_count) CATAN_F0(uint8_t, la_holder) CATAN_F0(uint8_t, la_count)
   CATAN_F0(uint8_t, initial_phase) CATAN_F0(uint8_t, dice_rolled) CATAN_F0(uint8_t, played_dev) CATAN_F0(uint8_t, must_use_dev)
@@ -79,8 +80,8 @@ CATAN_FN GameView game_view(uint8_t* recs, size_t i) {
 
 // host side: one game between a chunked buffer and a plain GameRec (catan_export_state / catan_import_state)
 static inline void chunk_get(const uint8_t* chunk, int lane, int W, GameRec& out) {
-  // 1-, 2- and 4-byte fields interleave in units of their own size; GameRec's layout: int16 [0,280), uint32 [280,292),
-  // uint16 [292,296), bytes from 296 on
+  // 1-, 2- and 4-byte fields interleave in units of their own size; GameRec's layout: 16-bit [0,384), uint32 [384,396),
+  // uint16 [396,400), bytes from 400 on
   uint8_t* o = reinterpret_cast<uint8_t*>(&out);
   for (size_t off = 0; off < sizeof(GameRec);) {
     const size_t sz = off < offsetof(GameRec, rng_ctr) ? 2 : (off < offsetof(GameRec, actions_this_turn) ? 4 : (off < offsetof(GameRec, corner) ? 2 : 1));
@@ -96,8 +97,8 @@ static inline void chunk_put(uint8_t* chunk, int lane, int W, const GameRec& in)
     off += sz;
   }
 }
-static_assert(offsetof(GameRec, est_min) == 0 && offsetof(GameRec, rng_ctr) == 280 && offsetof(GameRec, actions_this_turn) == 292 &&
-              offsetof(GameRec, corner) == 296, "chunk_get/chunk_put assume this field order");
+static_assert(offsetof(GameRec, est_min) == 0 && offsetof(GameRec, rng_ctr) == 384 && offsetof(GameRec, actions_this_turn) == 396 &&
+              offsetof(GameRec, corner) == 400, "chunk_get/chunk_put assume this field order");
 
 // OR over the lanes of a group (host build: one lane)
 #ifdef CATAN_DEVICE
@@ -197,20 +198,43 @@ CATAN_FN int t_best_exchange_rate(const GameView& g, int pid, int r) {   // wrap
   const int h = g.harbours(pid - 1);
   return (h >> (r + 1)) & 1 ? 2 : ((h & 1) ? 3 : 4);
 }
+// the ordered card lists hold two cards per byte
+CATAN_FN int t_hidden_at(const GameView& g, int p, int i) { return (g.hidden(p, i >> 1) >> (4 * (i & 1))) & 15; }
+CATAN_FN int t_played_at(const GameView& g, int p, int i) { return (g.played(p, i >> 1) >> (4 * (i & 1))) & 15; }
+CATAN_FN void t_hidden_set(const GameView& g, int p, int i, int card) {
+  uint8_t& b = g.hidden(p, i >> 1);
+  b = static_cast<uint8_t>((b & ~(15u << (4 * (i & 1)))) | (static_cast<uint32_t>(card) << (4 * (i & 1))));
+}
+CATAN_FN void t_played_set(const GameView& g, int p, int i, int card) {
+  uint8_t& b = g.played(p, i >> 1);
+  b = static_cast<uint8_t>((b & ~(15u << (4 * (i & 1)))) | (static_cast<uint32_t>(card) << (4 * (i & 1))));
+}
 // number of cards of every kind in a player's hidden list, 6 bits per kind
 CATAN_FN uint32_t t_hidden_counts(const GameView& g, int p) {
   uint32_t k = 0;
   const int n = g.n_hidden(p);
   CATAN_NO_UNROLL
-  for (int i = 0; i < n; ++i) k += 1u << (6 * g.hidden(p, i));
+  for (int i = 0; i < n; ++i) k += 1u << (6 * t_hidden_at(g, p, i));
   return k;
 }
 CATAN_FN int t_count_played(const GameView& g, int p, int card) {
   int k = 0;
   const int n = g.n_played(p);
   CATAN_NO_UNROLL
-  for (int i = 0; i < n; ++i) k += g.played(p, i) == card;
+  for (int i = 0; i < n; ++i) k += t_played_at(g, p, i) == card;
   return k;
+}
+// the production cache (GameRec::prod): `w` more production for player index p from every tile around corner c
+CATAN_FN void t_prod_add(const GameView& g, const Topo& T, int p, int c, int w) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int tl = T.corner_tiles[c][k];
+    if (tl < 0) continue;
+    const int tr = g.tile_res(tl), val = g.tile_val(tl);
+    if (tr == 0 || val == 7) continue;
+    const int j = CATAN_OBS_RES_SLOT(tr - 1) * 10 + CATAN_OBS_NUM_SLOT(val);
+    g.prod(p, j >> 2) = static_cast<uint16_t>(g.prod(p, j >> 2) + (w << (4 * (j & 3))));
+  }
 }
 
 CATAN_FN uint32_t t_rng_next(TCx& cx) {   // next word of the game stream
@@ -500,6 +524,7 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp, const Act& t) {
       const bool initial = g.initial_phase();
       if (!initial) { t_pay(g, p, WHEAT, 1); t_pay(g, p, SHEEP, 1); t_pay(g, p, WOOD, 1); t_pay(g, p, BRICK, 1); }
       g.corner(c) = static_cast<uint8_t>((pid << 2) | 1);
+      t_prod_add(g, T, p, c, 1);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {                                  // the corner now cuts the other players' roads through it
         const int e = T.corner_neigh_edge[c][k];
@@ -569,6 +594,7 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp, const Act& t) {
     case CATAN_ACT_UPGRADE_CITY: {                                   // game.py:598-604, :240-251
       t_pay(g, p, WHEAT, 2); t_pay(g, p, ORE, 3);
       g.corner(t.corner) = static_cast<uint8_t>((pid << 2) | 2);
+      t_prod_add(g, T, p, t.corner, 1);
       g.vp(p) += 1; g.cities_left(p) -= 1; g.settlements_left(p) += 1;
       EstReq& q = t_post_est(cx, tmp, pid, 0);
       est_set(q, ORE, -3); est_set(q, WHEAT, -2);
@@ -635,14 +661,14 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp, const Act& t) {
     case CATAN_ACT_PLAY_DEV: {                                       // game.py:653-693
       const int n = g.n_hidden(p);
       int at = 0;
-      while (at < n && g.hidden(p, at) != t.card) ++at;
+      while (at < n && t_hidden_at(g, p, at) != t.card) ++at;
       if (at < n) {                                                  // (always true for a validated action)
-        for (int i = at; i + 1 < n; ++i) g.hidden(p, i) = g.hidden(p, i + 1);
-        g.hidden(p, n - 1) = 0;
+        for (int i = at; i + 1 < n; ++i) t_hidden_set(g, p, i, t_hidden_at(g, p, i + 1));
+        t_hidden_set(g, p, n - 1, 0);
         g.n_hidden(p) = static_cast<uint8_t>(n - 1);
       }
       const int np = g.n_played(p);
-      if (np < 25) { g.played(p, np) = static_cast<uint8_t>(t.card); g.n_played(p) = static_cast<uint8_t>(np + 1); }
+      if (np < 25) { t_played_set(g, p, np, t.card); g.n_played(p) = static_cast<uint8_t>(np + 1); }
       g.played_dev() = 1;
       if (t.card == CATAN_DEV_VP) g.vp(p) += 1;
       else if (t.card == CATAN_DEV_KNIGHT) { g.can_move_robber() = 1; t_update_largest_army(g); }
@@ -680,7 +706,7 @@ CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp, const Act& t) {
       if (dn > 0 && nh < 25) {                                       // (always true for a validated action)
         const int card = g.deck(dn - 1);                             // deque.pop(): right end
         g.deck(dn - 1) = 0; g.deck_n() = static_cast<uint8_t>(dn - 1);
-        g.hidden(p, nh) = static_cast<uint8_t>(card); g.n_hidden(p) = static_cast<uint8_t>(nh + 1);
+        t_hidden_set(g, p, nh, card); g.n_hidden(p) = static_cast<uint8_t>(nh + 1);
         g.bought(card) += 1;
       }
       break;
@@ -1659,185 +1685,173 @@ static_assert(CATAN_A_TYPE == 0 && CATAN_A_CORNER == 1 && CATAN_A_EDGE == 2 && C
 // ------------------------------------------------------------------------------------------------
 // observation (wrapper.py:52-83, :491-524, :526-709).
 //
-// A thread produces its row front to back through a small sliding window in shared memory (RowWriter): features are
-// scattered as bytes into the window, and every completed 16-byte piece leaves as one vector store.  The window of
-// thread t is word-interleaved with the other threads of the block (word w at ring[w * NT + t]), so every access of a
-// warp is bank-conflict free whatever the per-thread byte positions are.
+// A row is cut into CATAN_OBS_PARTS 16-byte aligned parts and every part is produced by ONE thread in registers, without
+// any scratch memory: almost every byte of a row is 0 or 1, so a part is first built as a BIT IMAGE (bit i = byte i of the
+// part) by a handful of shifts at compile-time positions, the few count-valued bytes (production table, road / army lengths,
+// card lists, meta) are placed into a word image at compile-time offsets, and each 16-byte piece then leaves as
+// spread(16 bits) | count words in one streaming vector store.  (Round 1 scattered bytes through a 128-byte shared-memory
+// window per thread: 46 % of the encode kernel's instructions and 20 KB of shared memory per block.)
 // ------------------------------------------------------------------------------------------------
-#define CATAN_RING_BYTES 128
-// A row can be produced by several threads: each owns a 16-byte aligned range [lo, hi) of it, walks the features that
-// intersect its range and drops the bytes outside (a feature straddling a cut is evaluated on both sides).
-template <int NT>
-struct RowWriter {
-  uint32_t* ring;      // this thread's word 0
-  uint8_t* row;        // destination row (16-byte aligned)
-  int flushed;         // everything in [lo, flushed) has been written (multiple of 16)
-  int lo, hi;          // range of the row this writer owns (multiples of 16)
-  CATAN_MFN uint8_t* byte_ptr(int p) const {
-    return reinterpret_cast<uint8_t*>(ring + ((p & (CATAN_RING_BYTES - 1)) >> 2) * NT) + (p & 3);
-  }
-  CATAN_MFN void init(uint32_t* r, uint8_t* dst, int lo_, int hi_) {
-    ring = r; row = dst; flushed = lo_; lo = lo_; hi = hi_;
-#pragma unroll
-    for (int w = 0; w < CATAN_RING_BYTES / 4; ++w) ring[w * NT] = 0;
-  }
-  CATAN_MFN bool owns(int p) const { return p >= lo && p < hi; }
-  CATAN_MFN bool overlaps(int a, int b) const { return a < hi && b > lo; }   // [a, b) intersects [lo, hi)
-  CATAN_MFN void put(int p, int v) const { if (owns(p)) *byte_ptr(p) = static_cast<uint8_t>(v); }
-  CATAN_MFN void add(int p, int v) const { if (owns(p)) { uint8_t* q = byte_ptr(p); *q = static_cast<uint8_t>(*q + v); } }
-  // write out (and clear) every complete 16-byte piece below `upto`; afterwards positions < upto + 112 are writable
-  CATAN_MFN void flush_to(int upto) {
-    struct alignas(16) V16 { uint32_t a, b, c, d; };
-    if (upto > hi) upto = hi;
-    CATAN_NO_UNROLL
-    while (flushed + 16 <= upto) {
-      uint32_t* q = ring + ((flushed & (CATAN_RING_BYTES - 1)) >> 2) * NT;
-      const V16 v = {q[0], q[NT], q[2 * NT], q[3 * NT]};
-#ifdef CATAN_DEVICE
-      __stcs(reinterpret_cast<uint4*>(row + flushed), make_uint4(v.a, v.b, v.c, v.d));   // streamed: rows are not re-read here
-#else
-      *reinterpret_cast<V16*>(row + flushed) = v;
-#endif
-      q[0] = 0; q[NT] = 0; q[2 * NT] = 0; q[3 * NT] = 0;
-      flushed += 16;
-    }
-  }
-};
-
 CATAN_FN int t_bucket8(int n) { return n < 5 ? n : (n < 8 ? 5 : (n < 11 ? 6 : 7)); }                        // wrapper.py:554-561
 CATAN_FN int t_bucket7(int n) { return n <= 2 ? n : (n <= 5 ? 3 : (n <= 7 ? 4 : (n <= 10 ? 5 : 6))); }       // wrapper.py:662-671
+// 4 nibbles -> the 4 bytes of a word
+CATAN_FN uint32_t nib4(uint32_t x) { x = (x | (x << 8)) & 0x00FF00FFu; return (x | (x << 4)) & 0x0F0F0F0Fu; }
 
-// bytes [lo, hi) of the observation row of one game (lo, hi multiples of 16); the whole row is [0, CATAN_OBS_STRIDE)
-template <int NT>
-CATAN_FN_NOINLINE void t_encode_obs(const TCx& cx, uint32_t* ring, uint8_t* row, int lo, int hi) {
+template <int I, int N, class F>
+CATAN_FN void static_for(F&& f) {
+  if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+
+// a part of up to 160 bytes: bit image (w0: bytes 0-63, w1: 64-127, w2: 128-159) + count bytes as words
+struct PartImg {
+  uint64_t w0, w1, w2;
+  uint32_t pw[40];
+};
+// OR a word of 4 count bytes whose first byte lies at byte offset O of the part (compile time; bytes outside [0, 4 * NW) drop)
+template <int O, int NW>
+CATAN_FN void pw_put(uint32_t (&pw)[40], uint32_t v) {
+  constexpr int idx = O >= 0 ? O / 4 : -((3 - O) / 4), s = O - idx * 4;
+  if constexpr (s == 0) {
+    if constexpr (idx >= 0 && idx < NW) pw[idx] |= v;
+  } else {
+    if constexpr (idx >= 0 && idx < NW) pw[idx] |= v << (8 * s);
+    if constexpr (idx + 1 >= 0 && idx + 1 < NW) pw[idx + 1] |= v >> (32 - 8 * s);
+  }
+}
+// OR a 160-bit block image (b0, b1, b2), shifted by SH bits (compile time, -8 < SH < 64), into the part image
+template <int SH>
+CATAN_FN void img_or(PartImg& P, uint64_t b0, uint64_t b1, uint64_t b2) {
+  if constexpr (SH == 0) { P.w0 |= b0; P.w1 |= b1; P.w2 |= b2; }
+  else if constexpr (SH > 0) { P.w0 |= b0 << SH; P.w1 |= (b1 << SH) | (b0 >> (64 - SH)); P.w2 |= (b2 << SH) | (b1 >> (64 - SH)); }
+  else { P.w0 |= (b0 >> -SH) | (b1 << (64 + SH)); P.w1 |= (b1 >> -SH) | (b2 << (64 + SH)); P.w2 |= b2 >> -SH; }
+}
+// the pieces [0, NP) of a part -> row + lo
+template <int NP>
+CATAN_FN void img_store(const PartImg& P, uint8_t* dst) {
+  struct alignas(16) V16 { uint32_t a, b, c, d; };
+  static_for<0, NP>([&](auto I) {
+    constexpr int i = decltype(I)::value;
+    const uint64_t w = i < 4 ? P.w0 : (i < 8 ? P.w1 : P.w2);
+    const uint32_t b16 = static_cast<uint32_t>(w >> (16 * (i & 3))) & 0xffffu;
+    const V16 v = {spread4(b16 & 15u) | P.pw[4 * i], spread4((b16 >> 4) & 15u) | P.pw[4 * i + 1], spread4((b16 >> 8) & 15u) | P.pw[4 * i + 2],
+                   spread4(b16 >> 12) | P.pw[4 * i + 3]};
+#ifdef CATAN_DEVICE
+    __stcs(reinterpret_cast<uint4*>(dst + 16 * i), make_uint4(v.a, v.b, v.c, v.d));    // streamed: rows are not re-read here
+#else
+    *reinterpret_cast<V16*>(dst + 16 * i) = v;
+#endif
+  });
+}
+
+// the production table of player index tp (GameRec::prod, 50 x 4 bits) as 50 count bytes starting at byte offset O of the part
+template <int O>
+CATAN_FN void t_put_production(const GameView& g, int tp, PartImg& P) {
+  static_for<0, 13>([&](auto K) {
+    constexpr int k = decltype(K)::value;
+    uint32_t e = nib4(g.prod(tp, k));
+    if constexpr (k == 12) e &= 0x0000ffffu;                        // entries 48, 49
+    pw_put<O + 4 * k, 40>(P.pw, e);
+  });
+}
+
+struct ObsCtx { int actor, ap, aseat, lr_holder, la_holder; uint32_t relpack; };
+CATAN_FN ObsCtx t_obs_ctx(const TCx& cx) {
   const GameView& g = cx.g;
-  const Topo& T = *cx.T;
-  RowWriter<NT> W;
-  W.init(ring, row, lo, hi);
-  const int actor = t_current_actor(g), ap = actor - 1;
-  const int aseat = seat_of(cx.s, actor);
-  // REL(pid) = block of PlayerId pid seen from the actor (0 self, 1 next, ...), PID_AT(rel) = PlayerId rel seats after the actor
-  uint32_t relpack = 0;
+  ObsCtx C;
+  C.actor = t_current_actor(g); C.ap = C.actor - 1; C.aseat = seat_of(cx.s, C.actor);
+  C.lr_holder = g.lr_holder(); C.la_holder = g.la_holder();
+  C.relpack = 0;
 #pragma unroll
-  for (int p = 1; p <= 4; ++p) relpack |= static_cast<uint32_t>((seat_of(cx.s, p) - aseat + 4) & 3) << (2 * p);
-#define CATAN_REL(pid_) ((relpack >> (2 * (pid_))) & 3u)
-#define CATAN_PID_AT(rel_) pid_at_seat(cx.s, aseat + (rel_))
-  // ---- [0, 18): proposed trade (wrapper.py:61-69, Q15) and the actor's hand (wrapper.py:70-71)
-  if (W.overlaps(0, CATAN_OBS_TILES)) {
-    if (g.trade_proposer()) {
-      const int ng = g.n_give(), nr = g.n_recv();
-      for (int k = 0; k < ng; ++k) W.put(CATAN_OBS_PROPOSED_TRADE + g.give(k), 1);
-      for (int k = 0; k < nr; ++k) W.put(CATAN_OBS_PROPOSED_TRADE + g.recv(k) + 5, 1);
-    }
-#pragma unroll
-    for (int r = 0; r < 5; ++r) W.put(CATAN_OBS_CURRENT_RES + 1 + r, g.res(ap, r));
+  for (int p = 1; p <= 4; ++p) C.relpack |= static_cast<uint32_t>((seat_of(cx.s, p) - C.aseat + 4) & 3) << (2 * p);
+  return C;
+}
+
+// road / army / harbour entries shared by both block kinds (wrapper.py:613-637): returns the bits [holder?, -, holder?, -, h0..h5]
+// relative to the "longest road" entry and places the two count bytes at part offsets O + 1 and O + 3
+template <int O>
+CATAN_FN uint32_t t_road_army_harbours(const GameView& g, const ObsCtx& C, int target, PartImg& P) {
+  const int tp = target - 1;
+  uint32_t bits = 0, len = 0;
+  if (C.lr_holder) {                                                 // Q9
+    if (C.lr_holder == target) { bits |= 1u; len = g.lr_count(); }
+    else if (g.has_path_key(tp)) len = g.cur_longest_path(tp);
   }
-  // ---- tiles (wrapper.py:491-524)
-  if (W.overlaps(CATAN_OBS_TILES, CATAN_OBS_CUR_MAIN)) {
-    const int robber = g.robber_tile();
-    CATAN_NO_UNROLL
-    for (int t = 0; t < 19; ++t) {
-      const int base = CATAN_OBS_TILES + t * CATAN_OBS_TILE_DIM;
-      if (!W.overlaps(base, base + CATAN_OBS_TILE_DIM)) continue;
-      uint32_t b[6];
+  if (C.la_holder == target) bits |= 4u;                             // Q10
+  pw_put<O + 1, 40>(P.pw, len);
+  pw_put<O + 3, 40>(P.pw, static_cast<uint32_t>(g.cur_army(tp)));
+  return bits | (static_cast<uint32_t>(g.harbours(tp) & 63u) << 4);
+}
+
+// the acting player's block (152 bytes, wrapper.py:526-562, :587-637, :657-686), its first byte at part offset ST
+template <int ST>
+CATAN_FN void t_current_block(const TCx& cx, const ObsCtx& C, PartImg& P) {
+  const GameView& g = cx.g;
+  uint64_t b0 = 0, b1 = 0, b2 = 0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) b[k] = g.corner(T.tile_corners[t][k]);   // loads first, scatter afterwards
-      const int val = g.tile_val(t), tres = g.tile_res(t);
-      W.flush_to(base);
-      if (robber == t) W.put(base, 1);
-      W.put(base + 1 + val - 2, 1);
-      W.put(base + 12 + tres, 1);
+  for (int r = 0; r < 5; ++r) b0 |= 1ull << (CATAN_OBS_RES_SLOT(r) * 8 + t_bucket8(g.res(C.ap, r)));       // [0, 40)
+  const int vps = g.vp(C.ap);
+  b0 |= 1ull << (40 + (vps < 10 ? vps : 9));                                                              // [40, 50)
+  t_put_production<ST + 50>(g, C.ap, P);                                                                  // [50, 100)
+  b1 |= static_cast<uint64_t>(t_road_army_harbours<ST + 100>(g, C, C.actor, P)) << (100 - 64);            // [100, 110)
+  uint64_t bank = 0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const int cf = base + 18 + k * 7;
-        W.put(cf + (b[k] & 3), 1);                                   // none / settlement / city
-        if (b[k]) W.put(cf + 3 + CATAN_REL(b[k] >> 2), 1);           // owner relative to the actor
-      }
-    }
+  for (int r = 0; r < 5; ++r) bank |= 1ull << (CATAN_OBS_RES_SLOT(r) * 7 + t_bucket7(g.bank(r)));         // [110, 145)
+  bank |= 1ull << (35 + t_bucket7(g.deck_n()));                                                           // [145, 152)
+  b1 |= bank << (110 - 64);
+  b2 |= bank >> (128 - 110);
+  img_or<ST>(P, b0, b1, b2);
+}
+
+// an opponent's block (159 bytes, wrapper.py:563-637, :688-695), REL = 1..3 seats after the actor, first byte at part offset ST
+template <int REL, int ST>
+CATAN_FN void t_other_block(const TCx& cx, const ObsCtx& C, PartImg& P) {
+  const GameView& g = cx.g;
+  const int target = pid_at_seat(cx.s, C.aseat + REL), tp = target - 1;
+  uint64_t b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int slot = CATAN_OBS_RES_SLOT(r);
+    b0 |= 1ull << (slot * 8 + t_bucket8(g.est_min(C.ap, REL - 1, r)));                                    // [0, 40)
+    const int mx = 40 + slot * 8 + t_bucket8(g.est_max(C.ap, REL - 1, r));                                // [40, 80)
+    if (slot < 3) b0 |= 1ull << mx; else b1 |= 1ull << (mx - 64);
   }
-  // ---- player blocks (wrapper.py:526-709)
-  if (W.overlaps(CATAN_OBS_CUR_MAIN, CATAN_OBS_DEV_LISTS)) {
-    const int lr_holder = g.lr_holder(), la_holder = g.la_holder();
-    CATAN_NO_UNROLL
-    for (int rel = 0; rel < 4; ++rel) {
-      const int m = rel == 0 ? CATAN_OBS_CUR_MAIN : CATAN_OBS_OTHER_MAIN + (rel - 1) * CATAN_OBS_OTHER_MAIN_DIM;
-      if (!W.overlaps(m, m + (rel == 0 ? CATAN_OBS_CUR_MAIN_DIM : CATAN_OBS_OTHER_MAIN_DIM))) continue;
-      const int target = CATAN_PID_AT(rel), tp = target - 1;
-      const int c = m + (rel == 0 ? 40 : 80);                        // vp 10 | production 50 | road 2 | army 2 | harbours 6
-      W.flush_to(m);
-      if (rel == 0) {
-#pragma unroll
-        for (int r = 0; r < 5; ++r) W.put(m + ((0x24301 >> (4 * r)) & 7) * 8 + t_bucket8(g.res(ap, r)), 1);   // wrapper.py:550-562
-      } else {
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {                                // wrapper.py:563-585
-          const int slot = (0x24301 >> (4 * r)) & 7;
-          W.put(m + slot * 8 + t_bucket8(g.est_min(ap, rel - 1, r)), 1);
-          W.put(m + 40 + slot * 8 + t_bucket8(g.est_max(ap, rel - 1, r)), 1);
-        }
-        W.flush_to(c);
-      }
-      const int vps = g.vp(tp);
-      W.put(c + (vps < 10 ? vps : 9), 1);                            // wrapper.py:587-593
-      if (W.overlaps(c + 10, c + 60)) {                              // production table (wrapper.py:595-610)
-        CATAN_NO_UNROLL
-        for (int t = 0; t < 19; ++t) {
-          uint32_t b[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) b[k] = g.corner(T.tile_corners[t][k]);
-          const int val = g.tile_val(t), tres = g.tile_res(t);
-          uint32_t cnt = 0;                                          // settlement 1, city 2 for every building of `target`
-#pragma unroll
-          for (int k = 0; k < 6; ++k) cnt += (b[k] >> 2) == static_cast<uint32_t>(target) ? (b[k] & 3u) : 0u;
-          // slot of resource index r in the obs order Wood,Brick,Wheat,Ore,Sheep (wrapper.py:550): BRICK->1 WOOD->0 ORE->3 SHEEP->4 WHEAT->2
-          if (cnt && val != 7) W.add(c + 10 + ((0x24301 >> (4 * (tres - 1))) & 7) * 10 + (val <= 6 ? val - 2 : val - 3), cnt);
-        }
-      }
-      if (rel == 0) W.flush_to(c + 60);
-      if (lr_holder) {                                               // wrapper.py:613-620 (Q9)
-        if (lr_holder == target) { W.put(c + 60, 1); W.put(c + 61, g.lr_count()); }
-        else if (g.has_path_key(tp)) W.put(c + 61, g.cur_longest_path(tp));
-      }
-      if (la_holder == target) W.put(c + 62, 1);                     // wrapper.py:623-627 (Q10)
-      W.put(c + 63, g.cur_army(tp));
-      const int hb = g.harbours(tp);
-#pragma unroll
-      for (int b = 0; b < 6; ++b) W.put(c + 64 + b, (hb >> b) & 1);  // wrapper.py:632-637
-      if (rel == 0) {
-#pragma unroll
-        for (int r = 0; r < 5; ++r) W.put(m + 110 + ((0x24301 >> (4 * r)) & 7) * 7 + t_bucket7(g.bank(r)), 1);   // wrapper.py:657-672
-        W.put(m + 145 + t_bucket7(g.deck_n()), 1);                   // wrapper.py:674-686
-      } else {
-        W.put(m + 150 + rel - 1, 1);                                 // wrapper.py:532-541
-        const int nh = g.n_hidden(tp);
-        W.put(m + 153 + (nh <= 4 ? nh : 5), 1);                      // wrapper.py:690-695
-      }
-    }
-  }
-  // ---- development-card lists (wrapper.py:642-655) and the meta bytes
-  if (W.overlaps(CATAN_OBS_DEV_LISTS, CATAN_OBS_STRIDE)) {
-    int n_list[5];
-    CATAN_NO_UNROLL
-    for (int li = 0; li < 5; ++li) {
-      const int lb = CATAN_OBS_DEV_LISTS + li * CATAN_OBS_DEV_PAD;
-      W.flush_to(lb);
-      const int tp = (li < 2 ? actor : CATAN_PID_AT(li - 1)) - 1;
-      const int n = li == 1 ? g.n_hidden(tp) : g.n_played(tp);
-      n_list[li] = n;
-      if (li == 1) { for (int j = 0; j < n; ++j) W.put(lb + j, g.hidden(tp, j) + 1); }
-      else { for (int j = 0; j < n; ++j) W.put(lb + j, g.played(tp, j) + 1); }
-    }
-    W.flush_to(CATAN_OBS_META);
-    W.put(CATAN_OBS_META, actor);
-    W.put(CATAN_OBS_META + 1, n_list[0]);
-    W.put(CATAN_OBS_META + 2, n_list[1]);
-    W.put(CATAN_OBS_META + 3, n_list[2]);
-    W.put(CATAN_OBS_META + 4, n_list[3]);
-    W.put(CATAN_OBS_META + 5, n_list[4]);
-  }
-  W.flush_to(hi);
-#undef CATAN_REL
-#undef CATAN_PID_AT
+  const int vps = g.vp(tp);
+  b1 |= 1ull << (80 - 64 + (vps < 10 ? vps : 9));                                                         // [80, 90)
+  t_put_production<ST + 90>(g, tp, P);                                                                    // [90, 140)
+  uint64_t tail = t_road_army_harbours<ST + 140>(g, C, target, P);                                        // [140, 150)
+  tail |= 1ull << (10 + REL - 1);                                                                         // [150, 153) wrapper.py:532-541
+  const int nh = g.n_hidden(tp);
+  tail |= 1ull << (13 + (nh <= 4 ? nh : 5));                                                              // [153, 159) wrapper.py:690-695
+  b2 |= tail << (140 - 128);
+  img_or<ST>(P, b0, b1, b2);
+}
+// the first bytes of the NEXT opponent's block that fall into this part (its min-estimate one-hot of the slot-0 resource, Wood)
+template <int REL, int ST>
+CATAN_FN void t_other_block_head(const TCx& cx, const ObsCtx& C, PartImg& P) {
+  const int b = t_bucket8(cx.g.est_min(C.ap, REL - 1, WOOD));
+  if (ST + b < 160) P.w2 |= 1ull << (ST + b - 128);
+}
+
+// word k (cards 4k .. 4k+3) of a card list as obs bytes: card + 1, 0 beyond the list (wrapper.py:642-655)
+CATAN_FN uint32_t t_list_word(uint32_t nibbles16, int n, int k) {
+  const uint32_t valid = n >= 32 ? ~0u : ((1u << n) - 1u);
+  return nib4(nibbles16) + spread4((valid >> (4 * k)) & 15u);
+}
+// the card list LI (0: actor played, 1: actor hidden, 2..4: opponents' played), its first byte at part offset O; words [K0, K1)
+template <int LI, int O, int K0, int K1>
+CATAN_FN int t_put_list(const TCx& cx, const ObsCtx& C, PartImg& P) {
+  const GameView& g = cx.g;
+  const int tp = (LI < 2 ? C.actor : pid_at_seat(cx.s, C.aseat + LI - 1)) - 1;
+  const int n = LI == 1 ? g.n_hidden(tp) : g.n_played(tp);
+  static_for<K0, K1>([&](auto K) {
+    constexpr int k = decltype(K)::value;
+    uint32_t x = LI == 1 ? g.hidden(tp, 2 * k) : g.played(tp, 2 * k);
+    if constexpr (k < 6) x |= static_cast<uint32_t>(LI == 1 ? g.hidden(tp, 2 * k + 1) : g.played(tp, 2 * k + 1)) << 8;
+    uint32_t e = t_list_word(x, n, k);
+    if constexpr (k == 6) e &= 0xffu;                               // card 24 is the last one
+    pw_put<O + 4 * k, 40>(P.pw, e);
+  });
+  return n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1917,18 +1931,70 @@ static_assert(CATAN_OBS_PROPOSED_TRADE == 0 && CATAN_OBS_CURRENT_RES == 12 && CA
               "t_encode_obs_tiles packs the header by hand");
 
 // The cuts used by the device encoder: CATAN_OBS_PARTS threads share one row.  Parts 0 .. CATAN_OBS_TILE_PARTS-1 lie in
-// the header + tile region (t_encode_obs_tiles), the others go through the window (t_encode_obs).
+// the header + tile region (t_encode_obs_tiles); parts 4-7 hold one player block each (plus the few bytes of its neighbours
+// that share its first / last 16-byte piece), part 8 the card lists and the meta bytes.
 #define CATAN_OBS_PARTS 9
 #define CATAN_OBS_TILE_PARTS 4
 #define CATAN_OBS_TILE_END 1152
-CATAN_FN int t_obs_part_lo(int part) {   // four tile parts, one part per player block (cut at the nearest 16-byte piece), lists + meta
+CATAN_FN int t_obs_part_lo(int part) {
   return part == 0 ? 0 : part == 1 ? 304 : part == 2 ? 592 : part == 3 ? 880 : part == 4 ? CATAN_OBS_TILE_END : part == 5 ? 1312 :
          part == 6 ? 1472 : part == 7 ? 1632 : part == 8 ? 1792 : CATAN_OBS_STRIDE;
 }
-template <int NT>
-CATAN_FN void t_encode_obs_part(const TCx& cx, uint32_t* ring, uint8_t* row, int part) {
+CATAN_FN void t_encode_obs_players(const TCx& cx, uint8_t* row, int part) {
+  const ObsCtx C = t_obs_ctx(cx);
+  PartImg P = {};
+  constexpr int OTH = CATAN_OBS_OTHER_MAIN, OD = CATAN_OBS_OTHER_MAIN_DIM, LISTS = CATAN_OBS_DEV_LISTS, PAD = CATAN_OBS_DEV_PAD;
+  switch (part) {
+    case 4: {                                                        // [1152, 1312): tail of tile 18, the actor's block, 2 bytes of the next
+      constexpr int lo = 1152;
+      P.w0 = t_tile_bits(cx.g, *cx.T, 18, cx.g.robber_tile(), C.relpack) >> (lo - (CATAN_OBS_TILES + 18 * CATAN_OBS_TILE_DIM));
+      t_current_block<CATAN_OBS_CUR_MAIN - lo>(cx, C, P);
+      t_other_block_head<1, OTH - lo>(cx, C, P);
+      img_store<10>(P, row + lo);
+      break;
+    }
+    case 5: {
+      constexpr int lo = 1312;
+      t_other_block<1, OTH - lo>(cx, C, P);
+      t_other_block_head<2, OTH + OD - lo>(cx, C, P);
+      img_store<10>(P, row + lo);
+      break;
+    }
+    case 6: {
+      constexpr int lo = 1472;
+      t_other_block<2, OTH + OD - lo>(cx, C, P);
+      t_other_block_head<3, OTH + 2 * OD - lo>(cx, C, P);
+      img_store<10>(P, row + lo);
+      break;
+    }
+    case 7: {                                                        // ... and the first 5 cards of the actor's played list
+      constexpr int lo = 1632;
+      t_other_block<3, OTH + 2 * OD - lo>(cx, C, P);
+      t_put_list<0, LISTS - lo, 0, 2>(cx, C, P);
+      img_store<10>(P, row + lo);
+      break;
+    }
+    default: {                                                       // [1792, 1920): the card lists and the meta bytes
+      constexpr int lo = 1792;
+      const int n0 = t_put_list<0, LISTS - lo, 1, 7>(cx, C, P);
+      const int n1 = t_put_list<1, LISTS + PAD - lo, 0, 7>(cx, C, P);
+      const int n2 = t_put_list<2, LISTS + 2 * PAD - lo, 0, 7>(cx, C, P);
+      const int n3 = t_put_list<3, LISTS + 3 * PAD - lo, 0, 7>(cx, C, P);
+      const int n4 = t_put_list<4, LISTS + 4 * PAD - lo, 0, 7>(cx, C, P);
+      P.pw[(CATAN_OBS_META - lo) / 4] = static_cast<uint32_t>(C.actor) | (static_cast<uint32_t>(n0) << 8) | (static_cast<uint32_t>(n1) << 16) |
+                                        (static_cast<uint32_t>(n2) << 24);
+      P.pw[(CATAN_OBS_META - lo) / 4 + 1] = static_cast<uint32_t>(n3) | (static_cast<uint32_t>(n4) << 8);
+      img_store<8>(P, row + lo);
+      break;
+    }
+  }
+}
+static_assert(CATAN_OBS_CUR_MAIN == 1158 && CATAN_OBS_OTHER_MAIN == 1310 && CATAN_OBS_OTHER_MAIN_DIM == 159 && CATAN_OBS_DEV_LISTS == 1787 &&
+              CATAN_OBS_META == 1912 && CATAN_OBS_STRIDE == 1920 && CATAN_OBS_DEV_PAD == 25, "the part cuts assume this row layout");
+
+CATAN_FN void t_encode_obs_part(const TCx& cx, uint8_t* row, int part) {
   if (part < CATAN_OBS_TILE_PARTS) t_encode_obs_tiles(cx, row, t_obs_part_lo(part), t_obs_part_lo(part + 1));
-  else t_encode_obs<NT>(cx, ring, row, t_obs_part_lo(part), t_obs_part_lo(part + 1));
+  else t_encode_obs_players(cx, row, part);
 }
 
 }  // namespace catanb

@@ -41,6 +41,16 @@ namespace catanb {
 
 __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 
+// -DCATAN_PROFILE_PHASES (profiles/phase_profile.py only): cycles from block start to a few markers, summed over the blocks
+#ifdef CATAN_PROFILE_PHASES
+__device__ unsigned long long d_phase[64];     // [2 * k] = sum of cycles, [2 * k + 1] = count
+#define CATAN_MARK(k_) do { if ((threadIdx.x & 31) == 0) { atomicAdd(&d_phase[2 * (k_)], static_cast<unsigned long long>(clock64() - t_block0)); atomicAdd(&d_phase[2 * (k_) + 1], 1ull); } } while (0)
+#define CATAN_MARK_BEGIN() const long long t_block0 = clock64()
+#else
+#define CATAN_MARK(k_) ((void)0)
+#define CATAN_MARK_BEGIN() ((void)0)
+#endif
+
 // ---- launch shapes ------------------------------------------------------------------------------
 constexpr int kTransWarps = 4;              // transition_kernel: warps per chunk of 32 games ...
 constexpr int kLrBatch = 2;                 // incremental longest road: games walked at a time per rule warp
@@ -171,6 +181,7 @@ struct alignas(128) TransSmem {      // <= 31.4 KB so that 7 blocks fit an SM: 2
 __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_constant__ EnvParams P) {
   __shared__ TransSmem S;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  CATAN_MARK_BEGIN();
   const int base = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32;
   uint8_t* const home = P.recs + static_cast<size_t>(base >> 5) * CATAN_CHUNK_BYTES;
   if (tid == 0) { mbar_init(&S.mbar); chunk_to_shared(S.chunk, home, &S.mbar); S.n_follow = 0; }   // in flight while the topology is staged
@@ -181,6 +192,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   }
   __syncthreads();
   chunk_wait(&S.mbar, 0);
+  if (warp == 0) CATAN_MARK(0);
   // kRuleWarps warps share the 32 games (game gl = warp * 32 / kRuleWarps + lane, lanes above that idle): the rule code is
   // one big switch over 13 action types, and a warp pays for every type that occurs among ITS games
   constexpr int kPerWarp = 32 / kRuleWarps;
@@ -208,6 +220,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     pos = __shfl_sync(0xffffffffu, pos, 0);
     if (follow) S.follow_list[pos + __popc(fb & ((1u << lane) - 1u))] = static_cast<uint8_t>(gl);
     if (lane < kPerWarp) S.slot[gl] = -1;
+    CATAN_MARK(1);
   }
   __syncthreads();
   if (warp < kRuleWarps) {
@@ -256,6 +269,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     if (mine)
       P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
                   (static_cast<uint32_t>(tmp.roll_info) << 24) | (slow ? 0x80000000u : 0u);
+    CATAN_MARK(2);
   } else {
     const int nf = S.n_follow;
     for (int j = warp - kRuleWarps; j < nf; j += kTransWarps - kRuleWarps) {
@@ -263,6 +277,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
       g.base = S.chunk; g.lane = S.follow_list[j];
       t_followups_group(g, S.topo, S.tmp[g.lane], lane, 32);
     }
+    CATAN_MARK(3);
   }
   chunk_written();
   __syncthreads();
@@ -271,6 +286,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     if (slot >= 0) copy_game(GameView{S.chunk, b}, game_view(P.stage, static_cast<size_t>(slot)), lane);
   }
   if (tid == 0) chunk_to_global(home, S.chunk);                      // (frozen games go back unchanged)
+  if (warp == 0) CATAN_MARK(4);
 }
 
 // ---- 2. longest road ----------------------------------------------------------------------------
@@ -374,12 +390,10 @@ __global__ void lr_finish_kernel(LrCtl* c) {
 // row each (t_obs_part_lo): the header + tile pieces as bit sets expanded in registers, the player blocks and card
 // lists through a 128-byte window per thread.  A block's latency is what bounds the kernel (a warp issues one instruction
 // every ~40 cycles), hence the many narrow parts.
-constexpr int kObsRingThreads = (CATAN_OBS_PARTS - CATAN_OBS_TILE_PARTS) * 32;   // the tile parts build their pieces in registers
 struct alignas(128) EncSmem {
   uint8_t chunk[CATAN_CHUNK_BYTES];                                 // the 32 games of this block (see chunk_to_shared)
   uint64_t mbar;
   GameSmem topo;
-  uint32_t ring[(CATAN_RING_BYTES / 4) * kObsRingThreads];          // RowWriter windows, word-interleaved over those threads
   uint32_t wbuf[CATAN_RESET_WORDS];                                 // reset: pre-drawn Philox words (warp 0)
   uint8_t arr[96];                                                  // reset: shuffle arrays (warp 0)
   Scan scan[32];                                                    // board scan of game b (valid where scan_need has bit b)
@@ -395,6 +409,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
   extern __shared__ __align__(128) uint8_t enc_smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(enc_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  CATAN_MARK_BEGIN();
   const int list_count = LISTED ? P.lr_ctl->slow_count : 0;
   if (LISTED && static_cast<int>(blockIdx.x) * 32 >= list_count) return;
 #define CATAN_ENC_HOME(l0_) ((LISTED ? P.stage : P.recs) + static_cast<size_t>((LISTED ? (l0_) : (P.range_first & ~31) + (l0_)) >> 5) * CATAN_CHUNK_BYTES)
@@ -421,6 +436,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
     if (tid == 0 && l0 != static_cast<int>(blockIdx.x) * 32) chunk_to_shared(S.chunk, home, &S.mbar);
     chunk_wait(&S.mbar, phase);
     phase ^= 1;
+    if (!LISTED && warp == 0) CATAN_MARK(8);
     const GameView hv = GameView{home, lane};
 #define CATAN_VIEW_OF(b_) GameView{S.chunk, (b_)}
     TCx cx;
@@ -458,6 +474,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
         for (int p = 0; p < 4; ++p) hv.curr_vps(p) = cx.g.curr_vps(p);
       }
     }
+    if (!LISTED && warp == 0) CATAN_MARK(9);
     __syncthreads();                                                 // the games are final: every warp may read them now
     if (valid) cx.s = load_seats(cx.g);
     MaskBits m;
@@ -469,6 +486,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
       const unsigned nb = __ballot_sync(0xffffffffu, need_scan);
       S.scan_pid[lane] = static_cast<uint8_t>(cx.g.players_go());
       if (lane == 0) S.scan_need = nb;
+      if (!LISTED) CATAN_MARK(10);
     }
     __syncthreads();
     // the board scans (54 corners, 72 edges, 19 tiles) of the games that are in a placement phase: one WARP per game, one
@@ -484,6 +502,7 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
       }
     }
     __syncthreads();
+    if (!LISTED && warp == 0) CATAN_MARK(11);
     if (warp == 0) {
       if (valid) {
         if (pl.post) t_masks_post(cx, m, pl, S.scan[lane]);
@@ -503,8 +522,9 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
         }
       }
     } else if (valid) {
-      t_encode_obs_part<kObsRingThreads>(cx, S.ring + (tid - 32 * (1 + CATAN_OBS_TILE_PARTS)), P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE, warp - 1);
+      t_encode_obs_part(cx, P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE, warp - 1);
     }
+    if (!LISTED) { if (warp == 0) CATAN_MARK(12); else if (warp <= CATAN_OBS_TILE_PARTS) CATAN_MARK(13); else CATAN_MARK(14); }
     if (LISTED) __syncthreads();                                     // warp 0's reset scratch is reused by the next 32 games
 #undef CATAN_VIEW_OF
   }
@@ -974,6 +994,14 @@ int catan_read_timing(catan_env_t* env, double* out_host) {
   out_host[0] = static_cast<double>(env->t_n); out_host[1] = env->t_ms[0]; out_host[2] = env->t_ms[1];
   return 0;
 }
+
+#ifdef CATAN_PROFILE_PHASES
+int catan_debug_read_phases(unsigned long long* out64_host, int clear) {
+  if (cudaMemcpyFromSymbol(out64_host, catanb::d_phase, sizeof(unsigned long long) * 64) != cudaSuccess) return fail("catan_debug_read_phases");
+  if (clear) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(catanb::d_phase, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 int catan_read_err_flags(catan_env_t* env, uint32_t* flags_host, int clear) {
   if (!env || !flags_host) return fail("null argument");

@@ -45,6 +45,18 @@ def _ortho(m: nn.Linear, gain: float = math.sqrt(2)) -> nn.Linear:
     return m
 
 
+def _layer_norm_small(x: torch.Tensor, norm: nn.LayerNorm) -> torch.Tensor:
+    """LayerNorm over a short last dimension (16 / 25 / 64) of a tensor with very many rows.  ``F.layer_norm`` launches one block
+    per row, which at a few dozen elements per row runs at a few percent of the memory bandwidth (profiles/r2_notes.md: 31-40 % of
+    a rollout tick); moments by a vectorised reduction + elementwise ops are several times faster and the same function."""
+    if x.is_cuda:                                           # one fused launch (csrc/policy_kernels.cu), with its own backward
+        from .policy_ops import layer_norm_small
+        return layer_norm_small(x, norm.weight, norm.bias, norm.eps)
+    x = x.float()
+    var, mean = torch.var_mean(x, dim=-1, unbiased=False, keepdim=True)
+    return (x - mean) * torch.rsqrt(var + norm.eps) * norm.weight.float() + norm.bias.float()
+
+
 class _MHA(nn.Module):
     """multi_headed_attention.py:11-54; ``key_mask`` [B, L] bool = keys that may be attended"""
 
@@ -58,7 +70,11 @@ class _MHA(nn.Module):
         B, S, D = x.shape
         w = torch.cat([n.weight for n in self.qkv_nets], dim=0)
         b = torch.cat([n.bias for n in self.qkv_nets], dim=0)
-        qkv = F.linear(x, w, b).view(B, S, 3, self.heads, self.hd).permute(2, 0, 3, 1, 4)      # one GEMM for q, k, v
+        qkv = F.linear(x, w, b)                                                                 # one GEMM for q, k, v
+        if x.is_cuda and key_mask is None and (S, D, self.heads) == (19, 64, 4):
+            from .policy_ops import tile_attention              # 19 tokens x 4 heads of 16: the library kernels tile 64 x 64
+            return self.out_proj_net(tile_attention(qkv))
+        qkv = qkv.view(B, S, 3, self.heads, self.hd).permute(2, 0, 3, 1, 4)
         am = None if key_mask is None else key_mask.view(B, 1, 1, S)
         y = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=am)
         return self.out_proj_net(y.transpose(1, 2).reshape(B, S, D))
@@ -89,8 +105,8 @@ class _EncoderLayer(nn.Module):
         self.pointwise_net = _FFN(dim, 2)
 
     def forward(self, x):
-        x = x + self.multi_headed_attention(self.sublayers[0].norm(x))
-        return x + self.pointwise_net(self.sublayers[1].norm(x))
+        x = x + self.multi_headed_attention(_layer_norm_small(x, self.sublayers[0].norm))
+        return x + self.pointwise_net(_layer_norm_small(x, self.sublayers[1].norm))
 
 
 class _TileEncoder(nn.Module):
@@ -104,10 +120,10 @@ class _TileEncoder(nn.Module):
         self.out_proj = _ortho(nn.Linear(dim, out_dim))
 
     def forward(self, tiles):                       # [B, 19, 60]
-        x = F.relu(self.norm_2(self.first_layer(tiles)))
+        x = F.relu(_layer_norm_small(self.first_layer(tiles), self.norm_2))
         for layer in self.encoder_layers:
             x = layer(x)
-        return F.relu(self.norm(self.out_proj(x)).reshape(tiles.shape[0], -1))
+        return F.relu(_layer_norm_small(self.out_proj(x), self.norm).reshape(tiles.shape[0], -1))
 
 
 class _CurrentPlayer(nn.Module):
@@ -145,14 +161,38 @@ class _Observation(nn.Module):
         self.final_layer = _ortho(nn.Linear(19 * 25 + 4 * 128, TRUNK))
         self.norm = nn.LayerNorm(TRUNK)
 
-    def _cards(self, cards: torch.Tensor, mha: _MHA):
-        """padded card lists [R, 25] -> per position attention output [R, 25, 16] and the valid-position mask.  The reference
-        takes a list's length as the number of non-zero entries, at least 1 (player_modules.py:53-55): an empty list is the
-        single padding token."""
-        n = (cards != 0).sum(dim=-1).clamp_(min=1)
-        valid = torch.arange(cards.shape[1], device=cards.device).unsqueeze(0) < n.unsqueeze(1)
-        e = self.dev_card_embedding(cards)
-        return mha(e, valid), valid
+    def _card_lists(self, cards: torch.Tensor, mha: _MHA, norms) -> torch.Tensor:
+        """``cards`` [G, B, 25] (G lists per sample, zero-padded card codes) -> [G, B, 16]: what the reference computes as embedding ->
+        masked self-attention over the list -> LayerNorm (``norms[g]``) -> zero the padding -> sum over the positions
+        (player_modules.py:49-84), WITHOUT materialising the sequence.  There is no positional term, so the attention output of a
+        position depends only on its own card kind and on how many cards of each kind the list holds: with counts c[k] of the six
+        token kinds (an empty list is one padding token, :53-55), the softmax weight of kind k for a query of kind a is
+        c[k] exp(s[a, k]) / sum_k' c[k'] exp(s[a, k']) with the 6 x 6 score table s of the embedding, and the pooled output is
+        sum_a c[a] LayerNorm(out_proj(attention[a])).  Two GEMMs with K = 6 replace the [B, 25, 16] sequence tensors; the result
+        is the same function (sums re-associated)."""
+        with torch.autocast(device_type=cards.device.type, enabled=False):      # a few K = 6 products: kept in fp32
+            return self._card_lists_fp32(cards, mha, norms)
+
+    def _card_lists_fp32(self, cards: torch.Tensor, mha: _MHA, norms) -> torch.Tensor:
+        G, B, S = cards.shape
+        kinds = torch.arange(1, 6, device=cards.device)
+        c = (cards.unsqueeze(-1) == kinds).sum(dim=2).to(torch.float32)                         # [G, B, 5]
+        c = torch.cat(((c.sum(-1, keepdim=True) == 0).to(torch.float32), c), dim=-1)              # kind 0: the single padding token
+        H, hd = mha.heads, mha.hd
+        e = self.dev_card_embedding.weight.float()                                                # [6, 16]
+        q, k, v = (F.linear(e, n.weight.float(), n.bias.float()).view(6, H, hd).transpose(0, 1) for n in mha.qkv_nets)   # [H, 6, hd]
+        sc = torch.matmul(q, k.transpose(1, 2)) / math.sqrt(hd)                                   # [H, a, k]
+        p = torch.exp(sc - sc.amax(dim=-1, keepdim=True))
+        m_num = (p.unsqueeze(-1) * v.unsqueeze(1)).permute(2, 0, 1, 3).reshape(6, H * 6 * hd)     # [k, (h, a, d)]
+        m_den = p.permute(2, 0, 1).reshape(6, H * 6)                                              # [k, (h, a)]
+        cf = c.view(G * B, 6)
+        att = (cf @ m_num).view(-1, H, 6, hd) / (cf @ m_den).view(-1, H, 6, 1)                    # [GB, H, a, hd]
+        att = att.permute(0, 2, 1, 3).reshape(G, B, 6, H * hd)
+        out = F.linear(att, mha.out_proj_net.weight.float(), mha.out_proj_net.bias.float())      # [G, B, 6, 16]
+        pooled = []
+        for g in range(G):
+            pooled.append((_layer_norm_small(out[g], norms[g]) * c[g].unsqueeze(-1)).sum(dim=1))
+        return torch.stack(pooled, dim=0)
 
     def forward(self, obs: Dict[str, torch.Tensor]) -> torch.Tensor:
         B = obs["current_player_main"].shape[0]
@@ -160,13 +200,10 @@ class _Observation(nn.Module):
         tiles = self.tile_encoder(obs["tile_representations"])
         # played cards of all four players through the shared attention in one batch; each module has its own LayerNorm
         played = torch.stack([obs["current_player_played_dev"], obs["next_player_played_dev"], obs["next_next_player_played_dev"],
-                              obs["next_next_next_player_played_dev"]], dim=0).reshape(4 * B, -1)
-        rep, valid = self._cards(played, self.played_card_mha)
-        rep, valid = rep.view(4, B, *rep.shape[1:]), valid.view(4, B, -1, 1)
-        cur_played = (cur.norm(rep[0]) * valid[0]).sum(dim=1)
-        oth_played = (oth.norm(rep[1:]) * valid[1:]).sum(dim=2)                                   # [3, B, 16]
-        hrep, hvalid = self._cards(obs["current_player_hidden_dev"], self.hidden_card_mha)
-        cur_hidden = (cur.norm(hrep) * hvalid.unsqueeze(-1)).sum(dim=1)
+                              obs["next_next_next_player_played_dev"]], dim=0)
+        pooled = self._card_lists(played, self.played_card_mha, (cur.norm, oth.norm, oth.norm, oth.norm))
+        cur_played, oth_played = pooled[0], pooled[1:]
+        cur_hidden = self._card_lists(obs["current_player_hidden_dev"].unsqueeze(0), self.hidden_card_mha, (cur.norm,))[0]
         cur_hidden = F.relu(cur.norm_2(cur.proj_hidden_dev_card(cur_hidden)))
         cur_played = F.relu(cur.norm_3(cur.proj_played_dev_card(cur_played)))
         cur_main = F.relu(cur.norm_1(cur.main_input_layer_1(obs["current_player_main"])))

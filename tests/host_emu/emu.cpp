@@ -17,7 +17,6 @@ struct EmuEnv {
   alignas(16) uint8_t obs[CATAN_OBS_STRIDE];
   alignas(16) uint8_t mask[CATAN_MASK_STRIDE];
   alignas(16) uint8_t scratch[CATAN_LP_SCRATCH_BYTES + 16];
-  uint32_t ring[CATAN_RING_BYTES / 4];
   uint32_t wbuf[CATAN_RESET_WORDS];
   uint8_t arr[96];
   catan_config_t cfg;
@@ -45,7 +44,7 @@ static void encode(EmuEnv* e) {
   t_flatten_masks(m, F);
   t_store_mask_row(F, e->mask);
   // the row is produced in the same pieces as on the device (one thread per piece there)
-  for (int part = 0; part < CATAN_OBS_PARTS; ++part) t_encode_obs_part<1>(cx, e->ring, e->obs, part);
+  for (int part = 0; part < CATAN_OBS_PARTS; ++part) t_encode_obs_part(cx, e->obs, part);
 }
 
 extern "C" {

@@ -174,8 +174,9 @@ def test_rollout_store_replays_the_reference_managers_tape():
             ticks += 1
             assert ticks < 20000
             stepped = store.collecting.clone()
-            acts = tape_a[rows, k].contiguous()
-            logp = tape_lp[rows, k].contiguous()
+            kk = k.clamp(max=tape_a.shape[1] - 1)                       # (an env that has consumed its tape is frozen from here on)
+            acts = tape_a[rows, kk].contiguous()
+            logp = tape_lp[rows, kk].contiguous()
             env.step(acts, step_mask=stepped)
             store.record(acts, logp, stepped)
             k += stepped.long()
