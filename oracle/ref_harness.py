@@ -129,7 +129,7 @@ class patched_rng:
         self.stream = stream
 
     def __enter__(self):
-        self._saved = (np.random.shuffle, np.random.randint, _py_random.choice)
+        self._saved = (np.random.shuffle, np.random.randint, _py_random.choice, _py_random.shuffle)
         s = self.stream
 
         def _shuffle(x):
@@ -145,10 +145,11 @@ class patched_rng:
         np.random.shuffle = _shuffle
         np.random.randint = _randint
         _py_random.choice = _choice
+        _py_random.shuffle = _shuffle            # game.py:1250,1255 (randomise_uncertainty): the same Fisher-Yates
         return self
 
     def __exit__(self, *exc):
-        np.random.shuffle, np.random.randint, _py_random.choice = self._saved
+        np.random.shuffle, np.random.randint, _py_random.choice, _py_random.shuffle = self._saved
         return False
 
 

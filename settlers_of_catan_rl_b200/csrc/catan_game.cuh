@@ -925,6 +925,87 @@ CATAN_FN void t_step_scalar(TCx& cx, const int32_t* a, StepTmp& tmp) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Game.randomise_uncertainty (game.py:1207-1282; forward search, RL/forward_search_policy/worker.py:42-58): re-deal everything
+// the controlling player `c` cannot see, consistently with what it knows.  (1) the deck and the opponents' hidden cards are
+// pooled, shuffled and dealt back (players in dict order Blue, Red, Orange, White; cards popped from the right end);
+// (2) every opponent's hand is set to c's MINIMUM belief, and the cards that are then unaccounted for (19 per resource minus
+// bank, c's hand and the minima) are dealt one by one, in shuffled order, to the first opponent -- in a freshly shuffled player
+// order -- that still has room (hand total below its true total) and whose MAXIMUM belief allows one more card of that
+// resource; attempts repeat until every resource adds up to 19 (:1262-1272), which is also the reference's closing assert
+// (:1276-1282).  One thread per game; draws come from the game stream in the reference's call order.  Returns the number of
+// attempts, or 0 when `max_attempts` were not enough (the reference would loop forever on beliefs that admit no deal).
+// ------------------------------------------------------------------------------------------------
+CATAN_FN void t_rng_shuffle(TCx& cx, uint8_t* a, int n) {            // Fisher-Yates as pinned in catan_layout.h
+  for (int i = n - 1; i > 0; --i) {
+    const int j = t_rng_bounded(cx, i + 1);
+    const uint8_t x = a[i]; a[i] = a[j]; a[j] = x;
+  }
+}
+CATAN_FN_NOINLINE int t_randomise_uncertainty(TCx& cx, int c, int max_attempts) {
+  const GameView& g = cx.g;
+  const int dict_order[4] = {BLUE, RED, ORANGE, WHITE};              // game.py:17-22
+  const int res_order[5] = {SHEEP, BRICK, ORE, WHEAT, WOOD};         // game.py:1231
+  uint8_t pool[25];
+  int n = g.deck_n();
+  for (int i = 0; i < n; ++i) pool[i] = g.deck(i);
+  for (int k = 0; k < 4; ++k) {
+    const int q = dict_order[k];
+    if (q == c) continue;
+    const int nh = g.n_hidden(q - 1);
+    for (int i = 0; i < nh; ++i) pool[n++] = static_cast<uint8_t>(t_hidden_at(g, q - 1, i));
+  }
+  t_rng_shuffle(cx, pool, n);
+  for (int k = 0; k < 4; ++k) {
+    const int q = dict_order[k];
+    if (q == c) continue;
+    const int nh = g.n_hidden(q - 1);
+    for (int i = 0; i < nh; ++i) t_hidden_set(g, q - 1, i, pool[--n]);
+  }
+  for (int i = 0; i < 25; ++i) g.deck(i) = i < n ? pool[i] : 0;      // (n is the deck's length again)
+  int before[4], unacc[5];
+  for (int p = 0; p < 4; ++p) before[p] = t_hand_total(g, p + 1);
+  for (int k = 0; k < 5; ++k) {
+    const int r = res_order[k];
+    int acc = g.bank(r);
+    for (int q = 1; q <= 4; ++q) {
+      if (q != c) {
+        const int d = g.est_min(c - 1, label_of(cx.s, c, q), r);
+        acc += d;
+        g.res(q - 1, r) = static_cast<uint8_t>(d);
+      } else {
+        acc += g.res(q - 1, r);
+      }
+    }
+    unacc[k] = 19 - acc;
+  }
+  uint8_t list[96], prop[4][5];
+  for (int attempt = 1; attempt <= max_attempts; ++attempt) {
+    for (int p = 0; p < 4; ++p) for (int r = 0; r < 5; ++r) prop[p][r] = g.res(p, r);
+    int len = 0;
+    for (int k = 0; k < 5; ++k) for (int j = 0; j < unacc[k] && len < 96; ++j) list[len++] = static_cast<uint8_t>(res_order[k]);
+    t_rng_shuffle(cx, list, len);
+    while (len > 0) {
+      const int r = list[--len];
+      uint8_t keys[4] = {BLUE, RED, ORANGE, WHITE};
+      t_rng_shuffle(cx, keys, 4);
+      for (int k = 0; k < 4; ++k) {
+        const int q = keys[k];
+        if (q == c) continue;
+        const int tot = prop[q - 1][0] + prop[q - 1][1] + prop[q - 1][2] + prop[q - 1][3] + prop[q - 1][4];
+        if (tot < before[q - 1] && g.est_max(c - 1, label_of(cx.s, c, q), r) > prop[q - 1][r]) { prop[q - 1][r] += 1; break; }
+      }
+    }
+    bool ok = true;
+    for (int r = 0; r < 5; ++r) ok &= prop[0][r] + prop[1][r] + prop[2][r] + prop[3][r] + g.bank(r) == 19;
+    if (ok) {
+      for (int p = 0; p < 4; ++p) for (int r = 0; r < 5; ++r) g.res(p, r) = prop[p][r];
+      return attempt;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // longest road (game.py:843-919): adjacency masks from a view; the search itself is catan_core.cuh's lp_round
 // ------------------------------------------------------------------------------------------------
 CATAN_FN void t_lp_build_adj(const GameView& g, const Topo& T, int pid, uint64_t* adj, int lane, int nlanes) {
@@ -1219,34 +1300,49 @@ CATAN_FN_NOINLINE bool t_step_finish(TCx& cx, const StepTmp& tmp, float* reward_
 // `nl` lanes (a warp on the device, one lane in the host build).  The game stream is counter based, so the lanes first
 // compute the next CATAN_RESET_WORDS draws in parallel; lane 0 then runs the (inherently serial) Fisher-Yates shuffles
 // over small arrays in `arr` and only falls back to computing single draws when the 6/8 rejection loop of board.py:80-81
-// needed more than that.  wbuf: CATAN_RESET_WORDS words, arr: 96 bytes, both private to the group (shared memory).
+// needed more than that.  wbuf: CATAN_RESET_WORDS words, arr: 128 bytes, both private to the group (shared memory).
 // info_patch (may be null): info row of the step that ended the previous game; gets the new actor and RESET = 1.
 // ------------------------------------------------------------------------------------------------
-#define CATAN_RESET_WORDS 256
-#define CATAN_PER_GROUP19 ((19 + CATAN_W - 1) / CATAN_W)   // tiles per lane of a group
-struct ResetRng {
-  const uint32_t* wbuf;
-  uint32_t d_base, d;
-  uint64_t seed, env_id;
-};
-CATAN_FN uint32_t reset_rng_next(ResetRng& R) {
-  const uint32_t d = R.d++;
-  const uint32_t i = d - R.d_base;
-  if (i < CATAN_RESET_WORDS) return R.wbuf[i];
+#define CATAN_RESET_WORDS 512
+#if defined(CATAN_PROFILE_PHASES) && defined(CATAN_DEVICE)
+__device__ unsigned long long d_phase[64];     // [2 * k] = sum of cycles, [2 * k + 1] = count (see catan_kernels.cu)
+#define CATAN_RESET_T(k_) do { const long long t_now = clock64(); atomicAdd(&d_phase[k_], static_cast<unsigned long long>(t_now - t_mark)); t_mark = t_now; } while (0)
+#define CATAN_RESET_T0() long long t_mark = clock64()
+#else
+#define CATAN_RESET_T(k_) ((void)0)
+#define CATAN_RESET_T0() ((void)0)
+#endif
+// One Fisher-Yates shuffle of a[0..n) with the draws d0, d0 + 1, ... of the game stream (catan_layout.h): the lanes turn the n - 1
+// draws into swap partners in parallel (js), lane 0 then only swaps bytes.  (Round 2 measured ~700 cycles per swap when the one
+// lane also fetched the draw and reduced it: a reset took 57 us on average and 350 us at worst, and a step waits for the slowest
+// of the ~43 resets of a tick.)
+CATAN_FN uint32_t reset_word(const uint32_t* wbuf, uint32_t d_base, uint32_t d, uint64_t seed, uint64_t env_id) {
+  const uint32_t i = d - d_base;
+  if (i < CATAN_RESET_WORDS) return wbuf[i];
   uint32_t w[4];
-  philox4x32(d >> 2, CATAN_STREAM_GAME, static_cast<uint32_t>(R.env_id), static_cast<uint32_t>(R.env_id >> 32),
-             static_cast<uint32_t>(R.seed), static_cast<uint32_t>(R.seed >> 32), w);
+  philox4x32(d >> 2, CATAN_STREAM_GAME, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32), static_cast<uint32_t>(seed),
+             static_cast<uint32_t>(seed >> 32), w);
   return w[d & 3];
 }
-CATAN_FN void reset_shuffle(ResetRng& R, uint8_t* a, int n) {
-  for (int i = n - 1; i >= 1; --i) {
-    const int j = static_cast<int>(mulhi32(reset_rng_next(R), static_cast<uint32_t>(i + 1)));
-    const uint8_t t = a[i]; a[i] = a[j]; a[j] = t;
-  }
-}
+#define CATAN_RESET_SHUFFLE(a_, n_)                                                                                        \
+  do {                                                                                                                     \
+    for (int k_ = lane; k_ < (n_) - 1; k_ += nl)                                                                           \
+      js[k_] = static_cast<uint8_t>(mulhi32(reset_word(wbuf, d_base, d + static_cast<uint32_t>(k_), seed, env_id), static_cast<uint32_t>((n_) - k_))); \
+    CATAN_GROUP_SYNC();                                                                                                    \
+    if (lane == 0)                                                                                                         \
+      for (int k_ = 0; k_ < (n_) - 1; ++k_) {                                                                              \
+        const int i_ = (n_) - 1 - k_, j_ = js[k_];                                                                         \
+        const uint8_t x_ = (a_)[i_], y_ = (a_)[j_];                                                                        \
+        (a_)[i_] = y_; (a_)[j_] = x_;                                                                                      \
+      }                                                                                                                    \
+    d += static_cast<uint32_t>((n_) - 1);                                                                                  \
+    CATAN_GROUP_SYNC();                                                                                                    \
+  } while (0)
+
 CATAN_FN_NOINLINE void reset_game_group(const GameView& g, const Topo& T, uint64_t seed, uint64_t env_id, uint32_t* wbuf, uint8_t* arr,
                                         int lane, int nl, uint8_t* info_patch) {
   const uint32_t rng = g.rng_ctr(), dec = g.decision_ctr();
+  CATAN_RESET_T0();
   CATAN_GROUP_SYNC();
   // clear the record field-size wise (16- and 32-bit fields interleave in units of their own size); the two stream counters survive
   for (int k = lane; k < static_cast<int>(offsetof(GameRec, rng_ctr) / 2); k += nl) g.at<int16_t>(0, k) = 0;
@@ -1256,66 +1352,65 @@ CATAN_FN_NOINLINE void reset_game_group(const GameView& g, const Topo& T, uint64
   for (int b = lane; b < CATAN_RESET_WORDS / 4; b += nl)
     philox4x32((d_base >> 2) + b, CATAN_STREAM_GAME, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32),
                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), wbuf + 4 * b);
-  CATAN_GROUP_SYNC();
   uint8_t* terrain = arr;            // 19
-  uint8_t* numbers = arr + 19;       // 18
-  uint8_t* harb = arr + 37;          // 9
-  uint8_t* order = arr + 46;         // 4
-  uint8_t* deck = arr + 50;          // 25
-  uint8_t* vals = arr + 75;          // 19: number token of every tile under the current number order
-  ResetRng R = {wbuf, d_base, rng, seed, env_id};                    // (only lane 0 draws)
-  if (lane == 0) {
-    for (int i = 0; i < 19; ++i) terrain[i] = static_cast<uint8_t>(T.terrain_to_place[i]);
-    reset_shuffle(R, terrain, 19);                                   // board.py:71-72
-    for (int i = 0; i < 18; ++i) numbers[i] = static_cast<uint8_t>(T.default_number_order[i]);
-    reset_shuffle(R, numbers, 18);                                   // board.py:79
+  uint8_t* numbers = arr + 19;       // 18 + 1 (entry 18: the desert's "token", 7)
+  uint8_t* harb = arr + 38;          // 9
+  uint8_t* order = arr + 47;         // 4
+  uint8_t* deck = arr + 51;          // 25
+  uint8_t* tok = arr + 76;           // 19: index of tile t's number token (the desert: 18)
+  uint8_t* js = arr + 96;            // 32: swap partners of the shuffle in progress
+  for (int i = lane; i < 19; i += nl) terrain[i] = static_cast<uint8_t>(T.terrain_to_place[i]);
+  for (int i = lane; i < 18; i += nl) numbers[i] = static_cast<uint8_t>(T.default_number_order[i]);
+  for (int i = lane; i < 9; i += nl) harb[i] = static_cast<uint8_t>(i);
+  for (int i = lane; i < 25; i += nl) deck[i] = static_cast<uint8_t>(T.deck_init[i]);
+  if (lane == 0) { order[0] = WHITE; order[1] = BLUE; order[2] = ORANGE; order[3] = RED; numbers[18] = 7; }   // (numbers[18]: the desert's "token")
+  uint32_t d = rng;                                                  // next draw of the game stream (the same in every lane)
+  CATAN_GROUP_SYNC();
+  CATAN_RESET_T(56);                                                  // clear + pre-drawn words
+  CATAN_RESET_SHUFFLE(terrain, 19);                                  // board.py:71-72
+  CATAN_RESET_SHUFFLE(numbers, 18);                                  // board.py:79
+  // tile t takes the token at its rank in the placement order, not counting the desert (board.py:88-100)
+  for (int t = lane; t < 19; t += nl) {
+    int rank = 0, desert_rank = 0;
+    for (int i = 0; i < 19; ++i) {
+      const int pt = T.number_placement[i];
+      if (pt == t) rank = i;
+      if (terrain[pt] == 0) desert_rank = i;
+    }
+    tok[t] = static_cast<uint8_t>(rank == desert_rank ? 18 : rank - (desert_rank < rank ? 1 : 0));
   }
   CATAN_GROUP_SYNC();
-  // board.py:80-81: reshuffle until no 6 / 8 touch (board.py:50-65).  The check is one lane per tile; tile t takes the
-  // token at its rank in the placement order, not counting the desert (board.py:88-100).
-  int my_rank[CATAN_PER_GROUP19], desert_rank = 0;
-  for (int i = 0; i < 19; ++i) if (terrain[T.number_placement[i]] == 0) desert_rank = i;
-  for (int q = 0, t = lane; t < 19; t += nl, ++q) {
-    int r = 0;
-    for (int i = 0; i < 19; ++i) if (T.number_placement[i] == t) r = i;
-    my_rank[q] = r;
-  }
+  CATAN_RESET_T(57);                                                  // terrain + first number shuffle
+  // board.py:80-81: reshuffle until no 6 / 8 touch (board.py:50-65); the check is one lane per tile
   for (;;) {
-    for (int q = 0, t = lane; t < 19; t += nl, ++q)
-      vals[t] = my_rank[q] == desert_rank ? 7 : numbers[my_rank[q] - (desert_rank < my_rank[q] ? 1 : 0)];
-    CATAN_GROUP_SYNC();
+    uint32_t m68 = 0;
+    for (int t = lane; t < 19; t += nl) { const int v = numbers[tok[t]]; if (v == 6 || v == 8) m68 |= 1u << t; }
+    m68 = group_or32(m68);
     uint32_t bad = 0;
     for (int t = lane; t < 19; t += nl) {
-      if (vals[t] != 6 && vals[t] != 8) continue;
-      for (int k = 0; k < 6; ++k) {
-        const int nb = T.tile_neigh[t][k];
-        if (nb >= 0 && (vals[nb] == 6 || vals[nb] == 8)) bad = 1;
-      }
+      if (!((m68 >> t) & 1u)) continue;
+      for (int k = 0; k < 6; ++k) { const int nb = T.tile_neigh[t][k]; if (nb >= 0 && ((m68 >> nb) & 1u)) bad = 1; }
     }
-    bad = group_or32(bad);
-    if (!bad) break;
-    if (lane == 0) reset_shuffle(R, numbers, 18);
-    CATAN_GROUP_SYNC();
+    if (!group_or32(bad)) break;
+    CATAN_RESET_SHUFFLE(numbers, 18);
+#if defined(CATAN_PROFILE_PHASES) && defined(CATAN_DEVICE)
+    if (lane == 0) atomicAdd(&d_phase[60], 1ull);
+#endif
   }
-  if (lane == 0) {
-    for (int i = 0; i < 9; ++i) harb[i] = static_cast<uint8_t>(i);
-    reset_shuffle(R, harb, 9);                                       // board.py:83-84
-    order[0] = WHITE; order[1] = BLUE; order[2] = ORANGE; order[3] = RED;
-    reset_shuffle(R, order, 4);                                      // game.py:41-42
-    for (int i = 0; i < 25; ++i) deck[i] = static_cast<uint8_t>(T.deck_init[i]);
-    reset_shuffle(R, deck, 25);                                      // game.py:75-78
-    g.rng_ctr() = R.d;
-    g.decision_ctr() = dec;
-  }
-  CATAN_GROUP_SYNC();
+  CATAN_RESET_T(58);                                                  // the 6 / 8 rejection loop
+  CATAN_RESET_SHUFFLE(harb, 9);                                      // board.py:83-84
+  CATAN_RESET_SHUFFLE(order, 4);                                     // game.py:41-42
+  CATAN_RESET_SHUFFLE(deck, 25);                                     // game.py:75-78
   for (int t = lane; t < 19; t += nl) {                              // board.py:88-100
     g.tile_res(t) = terrain[t];
-    g.tile_val(t) = vals[t];
+    g.tile_val(t) = numbers[tok[t]];
     if (terrain[t] == 0) g.robber_tile() = static_cast<uint8_t>(t);
   }
   for (int i = lane; i < 25; i += nl) g.deck(i) = deck[i];
   for (int i = lane; i < 9; i += nl) g.harbour_perm(i) = harb[i];
   if (lane == 0) {
+    g.rng_ctr() = d;
+    g.decision_ctr() = dec;
     for (int i = 0; i < 4; ++i) g.player_order(i) = order[i];
     g.players_go() = order[0];
     for (int r = 0; r < 5; ++r) g.bank(r) = 19;                      // game.py:48-54
@@ -1323,6 +1418,7 @@ CATAN_FN_NOINLINE void reset_game_group(const GameView& g, const Topo& T, uint64
     g.deck_n() = 25;
     g.initial_phase() = 1;
     if (info_patch) { info_patch[CATAN_INFO_ACTOR] = order[0]; info_patch[CATAN_INFO_RESET] = 1; }
+    CATAN_RESET_T(59);                                                // the other shuffles + write-out
   }
   CATAN_GROUP_SYNC();
 }

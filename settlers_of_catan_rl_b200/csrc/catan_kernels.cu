@@ -43,7 +43,7 @@ __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 
 // -DCATAN_PROFILE_PHASES (profiles/phase_profile.py only): cycles from block start to a few markers, summed over the blocks
 #ifdef CATAN_PROFILE_PHASES
-__device__ unsigned long long d_phase[64];     // [2 * k] = sum of cycles, [2 * k + 1] = count
+// (d_phase is defined in catan_game.cuh, where the reset is instrumented as well)
 #define CATAN_MARK(k_) do { if ((threadIdx.x & 31) == 0) { atomicAdd(&d_phase[2 * (k_)], static_cast<unsigned long long>(clock64() - t_block0)); atomicAdd(&d_phase[2 * (k_) + 1], 1ull); } } while (0)
 #define CATAN_MARK_BEGIN() const long long t_block0 = clock64()
 #else
@@ -54,10 +54,12 @@ __device__ unsigned long long d_phase[64];     // [2 * k] = sum of cycles, [2 * 
 // ---- launch shapes ------------------------------------------------------------------------------
 constexpr int kTransWarps = 4;              // transition_kernel: warps per chunk of 32 games ...
 constexpr int kLrBatch = 2;                 // incremental longest road: games walked at a time per rule warp
-constexpr int kRuleWarps = 1;               // ... of which this many run the rules; the others the follow-ups (2 x 16 games measured: +5 % time)
 constexpr int kTransThreads = kTransWarps * 32;
-constexpr int kEncWarps = 1 + CATAN_OBS_PARTS;   // encode_kernel: finish/masks/sampler warp + one warp per piece of the obs row
+constexpr int kRowWarps = CATAN_OBS_TILE_PARTS;  // encode_kernel: warps that write observation rows (a tile part and a player part each) ...
+constexpr int kEncWarps = 2 * kRowWarps;         // ... and as many that share the per-game scalar work (done / reward, masks, sampler)
 constexpr int kEncThreads = kEncWarps * 32;
+constexpr int kMaskWarps = kEncWarps - kRowWarps;
+static_assert(CATAN_OBS_PARTS == 2 * CATAN_OBS_TILE_PARTS + 1, "row warp r writes tile part r and player part r; the last one also the lists");
 constexpr int kCopyThreads = 128;           // lr_copy_back_kernel: one warp per game
 constexpr int kLrSlowThreads = 512;         // lr_slow_kernel: one block per update that needs a search
 constexpr int kLrSlowBlocksPerSM = 2;
@@ -67,7 +69,8 @@ enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
 struct LrCtl {                // per-step queue counters; lr_finish_kernel banks them into the totals and clears them
   int32_t count, slow_count;  // longest-road updates of this step; those that went to lr_slow_kernel (= length of its queue)
-  unsigned long long total, slow_total;   // the same, summed over all earlier steps
+  int32_t rs_count, pad_;     // games that ended in this step and are reset on their own stream (= length of rs_queue)
+  unsigned long long total, slow_total, rs_total;   // the same, summed over all earlier steps
   unsigned long long dbg[6];  // lr_slow_kernel diagnostics: cycles sum / max, walk steps sum / max per search; full enumerations; tasks
 };
 
@@ -89,6 +92,13 @@ struct EnvParams {
   uint32_t* side;              // [n] transition -> encode: err | acted_pid << 8 | act_type << 16 | roll << 24 | longest-road update pending << 31
   uint64_t* lr_slow_queue;     // [n] updates that need a search: env index | PlayerId << 32 | edge or corner << 40 | CATAN_LR_* << 48 | acting PlayerId << 56
   LrCtl* lr_ctl;               // queue lengths of this step
+  uint64_t* rs_queue;          // [n] env index of the games that ended in this step (auto-reset): they are finished, reset and encoded on
+  uint8_t* stage_rs;           //     staging copies by their own launch, so that the slow, serial reset never holds up a block of 32 games
+  // what a LISTED encode / copy-back launch works on: one of the two queues
+  const uint64_t* list_queue;
+  uint8_t* list_stage;
+  const int32_t* list_count;
+  int list_group;              // games of the queue per block (a power of two <= 32)
 };
 
 struct GameSmem {
@@ -157,10 +167,10 @@ __device__ __forceinline__ void copy_game(const GameView& src, const GameView& d
   if (lane < 2) dst.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane) = v;
 }
 __global__ void __launch_bounds__(kCopyThreads) lr_copy_back_kernel(const __grid_constant__ EnvParams P) {
-  const int count = P.lr_ctl->slow_count;
+  const int count = *P.list_count;
   const int lane = threadIdx.x & 31, warps = static_cast<int>(gridDim.x) * (kCopyThreads / 32);
   for (int j = static_cast<int>(blockIdx.x) * (kCopyThreads / 32) + (threadIdx.x >> 5); j < count; j += warps)
-    copy_game(game_view(P.stage, static_cast<size_t>(j)), game_view(P.recs, static_cast<uint32_t>(P.lr_slow_queue[j])), lane);
+    copy_game(game_view(P.list_stage, static_cast<size_t>(j)), game_view(P.recs, static_cast<uint32_t>(P.list_queue[j])), lane);
 }
 
 // ---- 1. transition ------------------------------------------------------------------------------
@@ -174,6 +184,7 @@ struct alignas(128) TransSmem {      // <= 31.4 KB so that 7 blocks fit an SM: 2
   StepTmp tmp[32];
   int32_t n_follow;
   int32_t slot[32];          // staging slot of a game that goes to lr_slow_kernel, else -1
+  uint8_t order[kTransWarps][32];   // the chunk's games sorted by action type (one copy per warp: no barrier needed)
   uint64_t und[kLrBatch][54];   // incremental longest road: neighbour tables of the games being walked
   uint8_t follow_list[32];
 };
@@ -190,28 +201,48 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     int4* dst = reinterpret_cast<int4*>(&S.topo);
     for (int k = tid; k < static_cast<int>(sizeof(Topo) / 16); k += kTransThreads) dst[k] = src[k];
   }
+  // order of the chunk's games by action type (frozen / out-of-range games last), computed by every warp for itself
+  const int ig = base + lane;
+  const bool live = ig >= P.range_first && ig < P.range_first + P.range_count && !(P.env_mask != nullptr && P.env_mask[ig] == 0);
+  int n_live;
+  {
+    int key = 14;
+    if (live) { const int ty = P.actions[static_cast<size_t>(ig) * CATAN_ACTION_WORDS + CATAN_A_TYPE]; key = (ty < 0 || ty > 12) ? 13 : ty; }
+    int pos = 0, cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 15; ++t) {
+      const unsigned b = __ballot_sync(0xffffffffu, key == t);
+      if (key == t) pos = cnt + __popc(b & ((1u << lane) - 1u));
+      if (t == 13) n_live = cnt + __popc(b);
+      cnt += __popc(b);
+    }
+    S.order[warp][pos] = static_cast<uint8_t>(lane);
+    if (warp == 0) {
+      S.slot[lane] = -1;
+      if (!live) { S.tmp[lane].lr_pid = 0; S.tmp[lane].err = 0; S.tmp[lane].follow = 0; }
+    }
+  }
   __syncthreads();
   chunk_wait(&S.mbar, 0);
   if (warp == 0) CATAN_MARK(0);
-  // kRuleWarps warps share the 32 games (game gl = warp * 32 / kRuleWarps + lane, lanes above that idle): the rule code is
-  // one big switch over 13 action types, and a warp pays for every type that occurs among ITS games
-  constexpr int kPerWarp = 32 / kRuleWarps;
-  const int gl = warp * kPerWarp + (lane & (kPerWarp - 1));          // game of this thread inside the chunk (rule warps)
+  // The rule code is one big switch over 13 action types, and a warp pays for every type that occurs among ITS games: with one
+  // game per lane of one warp the 32 games of a chunk took 22 us of a 38 us block (profiles/r2_notes.md).  The games were
+  // therefore sorted by action type above (S.order), and each of the four warps takes eight consecutive games of that order:
+  // mostly one or two types per warp, and the four warps run side by side.
+  const int slot8 = warp * 8 + lane;
+  const bool mine = lane < 8 && slot8 < n_live;
+  const int gl = mine ? S.order[warp][slot8] : 0;                    // game of this thread inside the chunk
   const int i = base + gl;
-  const bool mine = warp < kRuleWarps && lane < kPerWarp && i >= P.range_first && i < P.range_first + P.range_count &&
-                    !(P.env_mask != nullptr && P.env_mask[i] == 0);
   TCx cx;
   cx.g.base = S.chunk; cx.g.lane = gl;
   cx.T = &S.topo; cx.X = nullptr; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);   // (X: masks only)
-  bool lr = false;
-  if (warp < kRuleWarps) {
+  {
     bool follow = false;
     if (mine) {
       cx.s = load_seats(cx.g);
       StepTmp& tmp = S.tmp[gl];
       t_step_scalar(cx, P.actions + static_cast<size_t>(i) * CATAN_ACTION_WORDS, tmp);
       if (tmp.err) P.err_flags[i] |= 1u << tmp.err;
-      lr = !tmp.err && tmp.lr_pid;
       follow = tmp.follow != 0;
     }
     const unsigned fb = __ballot_sync(0xffffffffu, follow);
@@ -219,15 +250,18 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
     if (lane == 0 && fb) pos = atomicAdd(&S.n_follow, __popc(fb));
     pos = __shfl_sync(0xffffffffu, pos, 0);
     if (follow) S.follow_list[pos + __popc(fb & ((1u << lane) - 1u))] = static_cast<uint8_t>(gl);
-    if (lane < kPerWarp) S.slot[gl] = -1;
     CATAN_MARK(1);
   }
   __syncthreads();
-  if (warp < kRuleWarps) {
+  if (warp == 0) {
+    // (game = lane from here on)
+    cx.g.lane = lane;
+    const int i = base + lane;
+    const bool lr = live && !S.tmp[lane].err && S.tmp[lane].lr_pid;
     // longest road (game.py:843-919), one thread per update: the incremental rule settles ~93 % of them on the spot; a
     // game that needs a search goes to the queue of lr_slow_kernel.  (Independent of the follow-ups: those touch hands,
     // bank and beliefs only.)
-    const StepTmp& tmp = S.tmp[gl];
+    const StepTmp& tmp = S.tmp[lane];
     const unsigned lb = __ballot_sync(0xffffffffu, lr);
     // Two games at a time: the warp gathers the road / blocked-corner bit sets (one lane per corner / edge) and the
     // neighbour table of the player's road graph (one lane per corner) into shared memory, then the two owning lanes walk.
@@ -241,7 +275,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
         const int b = __ffs(static_cast<int>(mm)) - 1;
         mm &= mm - 1;
         const uint32_t pid = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp.lr_pid), b);
-        const GameView gb = GameView{S.chunk, warp * kPerWarp + b};
+        const GameView gb = GameView{S.chunk, b};
         const uint32_t c0 = gb.corner(lane), c1 = lane + 32 < 54 ? gb.corner(lane + 32) : 0u;
         const uint32_t k0 = __ballot_sync(0xffffffffu, c0 != 0 && (c0 >> 2) != pid), k1 = __ballot_sync(0xffffffffu, c1 != 0 && (c1 >> 2) != pid);
         const uint32_t e0 = __ballot_sync(0xffffffffu, gb.edge(lane) == pid), e1 = __ballot_sync(0xffffffffu, gb.edge(lane + 32) == pid);
@@ -263,16 +297,28 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
       const int slot = atomicAdd(&P.lr_ctl->slow_count, 1);
       P.lr_slow_queue[slot] = static_cast<uint64_t>(static_cast<uint32_t>(i)) | (static_cast<uint64_t>(tmp.lr_pid) << 32) | (static_cast<uint64_t>(tmp.lr_loc) << 40) |
                               (static_cast<uint64_t>(tmp.lr_kind) << 48) | (static_cast<uint64_t>(tmp.acted_pid) << 56);
-      S.slot[gl] = slot;
+      S.slot[lane] = slot;
     }
     if (lane == 0 && lb) atomicAdd(&P.lr_ctl->count, __popc(lb));
-    if (mine)
+    // A game that ends with this step is reset by the encode (wrapper.py:30-34 after done): a handful of serial shuffles with a
+    // rejection loop, 60-300 us for ONE lane while the other 319 threads of an encode block wait -- the ~40 such blocks per step
+    // were the stragglers that set the encode kernel's duration (profiles/r2_notes.md).  The points are final here (follow-ups do
+    // not touch them), so these games leave the main path like the searched ones and go to the reset queue.
+    bool ends = false;
+    if (live && !slow && !tmp.err && P.cfg.auto_reset)
+      ends = cx.g.vp(0) >= 10 || cx.g.vp(1) >= 10 || cx.g.vp(2) >= 10 || cx.g.vp(3) >= 10;
+    if (ends) {
+      const int slot = atomicAdd(&P.lr_ctl->rs_count, 1);
+      P.rs_queue[slot] = static_cast<uint64_t>(static_cast<uint32_t>(i));
+      S.slot[lane] = -2 - slot;
+    }
+    if (live)
       P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
-                  (static_cast<uint32_t>(tmp.roll_info) << 24) | (slow ? 0x80000000u : 0u);
+                  (static_cast<uint32_t>(tmp.roll_info) << 24) | ((slow || ends) ? 0x80000000u : 0u);
     CATAN_MARK(2);
   } else {
     const int nf = S.n_follow;
-    for (int j = warp - kRuleWarps; j < nf; j += kTransWarps - kRuleWarps) {
+    for (int j = warp - 1; j < nf; j += kTransWarps - 1) {
       GameView g;
       g.base = S.chunk; g.lane = S.follow_list[j];
       t_followups_group(g, S.topo, S.tmp[g.lane], lane, 32);
@@ -284,6 +330,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   for (int b = warp; b < 32; b += kTransWarps) {                     // games that wait for a search: also into their staging slot
     const int slot = S.slot[b];
     if (slot >= 0) copy_game(GameView{S.chunk, b}, game_view(P.stage, static_cast<size_t>(slot)), lane);
+    else if (slot <= -2) copy_game(GameView{S.chunk, b}, game_view(P.stage_rs, static_cast<size_t>(-2 - slot)), lane);
   }
   if (tid == 0) chunk_to_global(home, S.chunk);                      // (frozen games go back unchanged)
   if (warp == 0) CATAN_MARK(4);
@@ -383,6 +430,10 @@ __global__ void lr_finish_kernel(LrCtl* c) {
   c->total += static_cast<unsigned long long>(c->count); c->slow_total += static_cast<unsigned long long>(c->slow_count);
   c->count = 0; c->slow_count = 0;
 }
+__global__ void rs_finish_kernel(LrCtl* c) {   // the same for the reset queue, last launch of its stream
+  c->rs_total += static_cast<unsigned long long>(c->rs_count);
+  c->rs_count = 0;
+}
 
 // ---- 3. finish + masks + sampler + observation --------------------------------------------------
 // One block per chunk of 32 games, one game per lane in every warp.  Warp 0: done / reward / info (+ auto-reset), then
@@ -395,36 +446,43 @@ struct alignas(128) EncSmem {
   uint64_t mbar;
   GameSmem topo;
   uint32_t wbuf[CATAN_RESET_WORDS];                                 // reset: pre-drawn Philox words (warp 0)
-  uint8_t arr[96];                                                  // reset: shuffle arrays (warp 0)
+  alignas(4) uint8_t arr[128];                                       // reset: scratch (warp 0)
   Scan scan[32];                                                    // board scan of game b (valid where scan_need has bit b)
-  uint32_t scan_need;
+  uint32_t scan_need, reset_need;
+  int32_t scan_pid_done;                                            // (profiling build: warps that finished)
   uint8_t scan_pid[32];
 };
 
 // LISTED = false: block b takes chunk b of the env range; in a step, games whose longest-road update is still pending
 // (side bit 31) are left out.  LISTED = true: those games, 32 per block iteration in queue order, on their staging
 // copies once the searches have finished (second stream, see launch_step).
+#ifndef CATAN_ENC_MIN_BLOCKS
+#define CATAN_ENC_MIN_BLOCKS 4   // (5 blocks per SM at 48 registers measured 2 % slower than 4 at 56)
+#endif
 template <int MODE, bool SAMPLE, bool LISTED>
-__global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_constant__ EnvParams P) {
+__global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kernel(const __grid_constant__ EnvParams P) {
   extern __shared__ __align__(128) uint8_t enc_smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(enc_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   CATAN_MARK_BEGIN();
-  const int list_count = LISTED ? P.lr_ctl->slow_count : 0;
-  if (LISTED && static_cast<int>(blockIdx.x) * 32 >= list_count) return;
-#define CATAN_ENC_HOME(l0_) ((LISTED ? P.stage : P.recs) + static_cast<size_t>((LISTED ? (l0_) : (P.range_first & ~31) + (l0_)) >> 5) * CATAN_CHUNK_BYTES)
+  const int list_count = LISTED ? *P.list_count : 0;
+  const int G = LISTED ? P.list_group : 32;                          // games per block iteration: LISTED blocks take a WINDOW of a staging chunk
+  if (LISTED && static_cast<int>(blockIdx.x) * G >= list_count) return;
+#define CATAN_ENC_HOME(l0_) ((LISTED ? P.list_stage : P.recs) + static_cast<size_t>((LISTED ? (l0_) : (P.range_first & ~31) + (l0_)) >> 5) * CATAN_CHUNK_BYTES)
   if (tid == 0) {                                                    // the first chunk is on its way while the topology is staged
+    S.reset_need = 0; S.scan_need = 0; S.scan_pid_done = 0;          // (made visible by the barrier of stage_topology)
     mbar_init(&S.mbar);
-    chunk_to_shared(S.chunk, CATAN_ENC_HOME(static_cast<int>(blockIdx.x) * 32), &S.mbar);
+    chunk_to_shared(S.chunk, CATAN_ENC_HOME((static_cast<int>(blockIdx.x) * G) & ~31), &S.mbar);
   }
   stage_topology(S.topo, tid, kEncThreads);
   uint32_t phase = 0;
-  for (int l0 = static_cast<int>(blockIdx.x) * 32; LISTED ? l0 < list_count : l0 == static_cast<int>(blockIdx.x) * 32; l0 += static_cast<int>(gridDim.x) * 32) {
+  for (int w0 = static_cast<int>(blockIdx.x) * G; LISTED ? w0 < list_count : w0 == static_cast<int>(blockIdx.x) * G; w0 += static_cast<int>(gridDim.x) * G) {
+    const int l0 = w0 & ~31;                                         // first queue slot / game of the chunk
     int i;
     bool valid;
     if (LISTED) {
-      valid = l0 + lane < list_count;
-      i = valid ? static_cast<int>(static_cast<uint32_t>(P.lr_slow_queue[l0 + lane])) : 0;
+      valid = l0 + lane >= w0 && l0 + lane < w0 + G && l0 + lane < list_count;
+      i = valid ? static_cast<int>(static_cast<uint32_t>(P.list_queue[l0 + lane])) : 0;
     } else {
       i = (P.range_first & ~31) + l0 + lane;
       valid = i >= P.range_first && i < P.range_first + P.range_count && !(MODE != MODE_REFRESH && P.env_mask != nullptr && P.env_mask[i] == 0);
@@ -433,99 +491,172 @@ __global__ void __launch_bounds__(kEncThreads, 4) encode_kernel(const __grid_con
     // the chunk of these 32 games (home records, or the staging copies) -> shared memory; lane b of every warp works on
     // game b of it.  What the block changes goes home explicitly: the games of the other stream must not be touched.
     uint8_t* const home = CATAN_ENC_HOME(l0);
-    if (tid == 0 && l0 != static_cast<int>(blockIdx.x) * 32) chunk_to_shared(S.chunk, home, &S.mbar);
+    if (tid == 0 && w0 != static_cast<int>(blockIdx.x) * G) chunk_to_shared(S.chunk, home, &S.mbar);
     chunk_wait(&S.mbar, phase);
     phase ^= 1;
     if (!LISTED && warp == 0) CATAN_MARK(8);
-    const GameView hv = GameView{home, lane};
 #define CATAN_VIEW_OF(b_) GameView{S.chunk, (b_)}
-    TCx cx;
-    cx.g = CATAN_VIEW_OF(lane);
-    cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
-    uint8_t* info = P.info + static_cast<size_t>(i) * CATAN_INFO_STRIDE;
-    if (warp == 0 && MODE != MODE_REFRESH) {
-      bool need_reset = false;
-      if (MODE == MODE_STEP) {
-        if (valid) {
-          cx.s = load_seats(cx.g);
-          const uint32_t sd = P.side[i];
-          StepTmp tmp;
-          tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
-          tmp.roll_info = static_cast<uint8_t>((sd >> 24) & 0x7f);
-          need_reset = t_step_finish(cx, tmp, P.reward + static_cast<size_t>(i) * 4, info);
-        }
-      } else {
-        need_reset = valid;
-      }
-      // Board.reset + Game.reset are a handful of serial shuffles: the warp does them game by game (lanes pre-draw the
-      // Philox words in parallel).  Rare in a step (a game ends every ~1500 steps), everything in catan_reset.
-      unsigned rb = __ballot_sync(0xffffffffu, need_reset);
-      while (rb) {
-        const int b = __ffs(static_cast<int>(rb)) - 1;
-        rb &= rb - 1;
-        const int e = __shfl_sync(0xffffffffu, i, b);
-        reset_game_group(CATAN_VIEW_OF(b), S.topo.topo, P.seed, P.first_env_id + static_cast<uint64_t>(e), S.wbuf, S.arr,
-                         lane, 32, MODE == MODE_STEP ? P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE : nullptr);
-        copy_game(CATAN_VIEW_OF(b), GameView{home, b}, lane);        // the whole new game goes home
-      }
-      if (MODE == MODE_STEP && valid) {                              // what done / reward changed (wrapper.py:85-112)
-        hv.episode_steps() = cx.g.episode_steps(); hv.winner() = cx.g.winner();
+    // Roles (kMaskWarps + kRowWarps warps).
+    //   mask warps 0 .. kMaskWarps-1: the per-game scalar work -- done / reward / info, the legal-action masks, the sampler.  It is a
+    //     long dependent chain per game, and when ONE warp did it for all 32 games it was the block's long pole (34 us of a ~40 us
+    //     block, profiles/r2_notes.md); mask warp q takes the games g with g % kMaskWarps == q in its lanes g / kMaskWarps.
+    //   row warps: lane b works on game b; row warp r writes tile part r of the observation row and then player part r (the last
+    //     one also the card lists).
+    // In a step launch no game of the main path is ever reset (the transition sent those to the reset queue), and nothing the
+    // observation reads is changed by done / reward: the row warps then start at once and the mask warps synchronise among
+    // themselves (named barrier 1).  Every other launch (reset, refresh, the two queues) keeps the block-wide barriers.
+    constexpr bool kDecoupled = MODE == MODE_STEP && !LISTED;
+    const bool mask_warp = warp < kMaskWarps;
+    const int mq = warp;                                             // index among the mask warps
+    const int gm = lane * kMaskWarps + mq;                           // game of this thread in its mask role
+    const bool m_lane = mask_warp && gm < 32;
+    const int im = __shfl_sync(0xffffffffu, i, gm & 31);
+    const bool vm = __shfl_sync(0xffffffffu, static_cast<int>(valid), gm & 31) != 0 && m_lane;
+#define CATAN_MASK_SYNC() do { if (kDecoupled) asm volatile("bar.sync 1, %0;" :: "n"(kMaskWarps * 32) : "memory"); else __syncthreads(); } while (0)
+    if (mask_warp || !kDecoupled) {
+      TCx mx;                                                        // context of the mask role
+      mx.g = CATAN_VIEW_OF(gm & 31);
+      mx.T = &S.topo.topo; mx.X = &S.topo.topox; mx.cfg = &P.cfg; mx.seed = P.seed; mx.env_id = P.first_env_id + static_cast<uint64_t>(im);
+      const GameView hv = GameView{home, gm & 31};
+      uint8_t* info = P.info + static_cast<size_t>(im) * CATAN_INFO_STRIDE;
+      if (mask_warp && MODE != MODE_REFRESH) {
+        bool need_reset = false;
+        if (MODE == MODE_STEP) {
+          if (vm) {
+            mx.s = load_seats(mx.g);
+            const uint32_t sd = P.side[im];
+            StepTmp tmp;
+            tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
+            tmp.roll_info = static_cast<uint8_t>((sd >> 24) & 0x7f);
+            need_reset = t_step_finish(mx, tmp, P.reward + static_cast<size_t>(im) * 4, info);
+            hv.episode_steps() = mx.g.episode_steps(); hv.winner() = mx.g.winner();   // what done / reward changed (wrapper.py:85-112)
 #pragma unroll
-        for (int p = 0; p < 4; ++p) hv.curr_vps(p) = cx.g.curr_vps(p);
+            for (int p = 0; p < 4; ++p) hv.curr_vps(p) = mx.g.curr_vps(p);
+          }
+        } else {
+          need_reset = vm;
+        }
+        if (need_reset && !kDecoupled) atomicOr(&S.reset_need, 1u << gm);
       }
-    }
-    if (!LISTED && warp == 0) CATAN_MARK(9);
-    __syncthreads();                                                 // the games are final: every warp may read them now
-    if (valid) cx.s = load_seats(cx.g);
-    MaskBits m;
-    MaskPlan pl;
-    pl.post = 0;
-    if (warp == 0) {
-      if (MODE != MODE_STEP && valid) t_write_info_fresh(cx.g, info, MODE == MODE_RESET);
-      const bool need_scan = valid && t_masks_pre(cx, m, pl);
-      const unsigned nb = __ballot_sync(0xffffffffu, need_scan);
-      S.scan_pid[lane] = static_cast<uint8_t>(cx.g.players_go());
-      if (lane == 0) S.scan_need = nb;
-      if (!LISTED) CATAN_MARK(10);
-    }
-    __syncthreads();
-    // the board scans (54 corners, 72 edges, 19 tiles) of the games that are in a placement phase: one WARP per game, one
-    // lane per corner / edge, all warps of the block take their share
-    {
-      unsigned nb = S.scan_need;
-      for (int k = 0; nb; ++k) {
-        const int b = __ffs(static_cast<int>(nb)) - 1;
-        nb &= nb - 1;
-        if (k % kEncWarps != warp) continue;
-        const Scan r = t_scan_group(CATAN_VIEW_OF(b), S.topo.topo, S.topo.topox, S.scan_pid[b], lane, 32);
-        if (lane == 0) S.scan[b] = r;
+      if (!LISTED && warp == 0) CATAN_MARK(9);
+      if (!kDecoupled) {
+        __syncthreads();
+        if (MODE != MODE_REFRESH && S.reset_need) {                  // (block-uniform)
+          // Board.reset + Game.reset: warp 0 does them game by game (the lanes share the shuffles' draws and the 6 / 8 check)
+          if (warp == 0) {
+            unsigned rb = S.reset_need;
+#ifdef CATAN_PROFILE_PHASES
+            const long long t_reset0 = clock64();
+#endif
+            while (rb) {
+              const int b = __ffs(static_cast<int>(rb)) - 1;
+              rb &= rb - 1;
+              const int e = __shfl_sync(0xffffffffu, i, b);
+              reset_game_group(CATAN_VIEW_OF(b), S.topo.topo, P.seed, P.first_env_id + static_cast<uint64_t>(e), S.wbuf, S.arr,
+                               lane, 32, MODE == MODE_STEP ? P.info + static_cast<size_t>(e) * CATAN_INFO_STRIDE : nullptr);
+              copy_game(CATAN_VIEW_OF(b), GameView{home, b}, lane);  // the whole new game goes home
+            }
+#ifdef CATAN_PROFILE_PHASES
+            if (lane == 0 && MODE == MODE_STEP) {
+              const unsigned long long d = static_cast<unsigned long long>(clock64() - t_reset0);
+              atomicAdd(&d_phase[32], d); atomicAdd(&d_phase[33], 1ull); atomicMax(&d_phase[48], d);
+              atomicAdd(&d_phase[50 + (d < 20000 ? 0 : d < 40000 ? 1 : d < 80000 ? 2 : d < 160000 ? 3 : d < 320000 ? 4 : 5)], 1ull);
+            }
+#endif
+          }
+          __syncthreads();
+        }
       }
-    }
-    __syncthreads();
-    if (!LISTED && warp == 0) CATAN_MARK(11);
-    if (warp == 0) {
-      if (valid) {
-        if (pl.post) t_masks_post(cx, m, pl, S.scan[lane]);
+      // (the games are final)
+      if (mask_warp) {
+        MaskBits m;
+        MaskPlan pl;
+        pl.post = 0;
+        if (vm) mx.s = load_seats(mx.g);
+        if (MODE != MODE_STEP && vm) t_write_info_fresh(mx.g, info, MODE == MODE_RESET);
+        const bool need_scan = vm && t_masks_pre(mx, m, pl);
+        if (m_lane) S.scan_pid[gm] = static_cast<uint8_t>(mx.g.players_go());
+        if (need_scan) atomicOr(&S.scan_need, 1u << gm);
+        if (!LISTED && warp == 0) CATAN_MARK(10);
+        CATAN_MASK_SYNC();
+        // the board scans (54 corners, 72 edges, 19 tiles) of the games that are in a placement phase: one WARP per game, one
+        // lane per corner / edge; the mask warps (in a step) or all warps take their share
         {
-          MaskFlat F;
-          t_flatten_masks(m, F);
-          t_store_mask_row(F, P.masks + static_cast<size_t>(i) * CATAN_MASK_STRIDE);
+          unsigned nb = S.scan_need;
+          for (int k = 0; nb; ++k) {
+            const int b = __ffs(static_cast<int>(nb)) - 1;
+            nb &= nb - 1;
+            if (k % (kDecoupled ? kMaskWarps : kEncWarps) != warp) continue;
+            const Scan r = t_scan_group(CATAN_VIEW_OF(b), S.topo.topo, S.topo.topox, S.scan_pid[b], lane, 32);
+            if (lane == 0) S.scan[b] = r;
+          }
         }
-        if (SAMPLE) {
-          const int ap = t_current_actor(cx.g) - 1;
-          uint32_t hand = 0;
+        CATAN_MASK_SYNC();
+        if (!LISTED && warp == 0) CATAN_MARK(11);
+        if (vm) {
+          if (pl.post) t_masks_post(mx, m, pl, S.scan[gm]);
+          {
+            MaskFlat F;
+            t_flatten_masks(m, F);
+            t_store_mask_row(F, P.masks + static_cast<size_t>(im) * CATAN_MASK_STRIDE);
+          }
+          if (SAMPLE) {
+            const int ap = t_current_actor(mx.g) - 1;
+            uint32_t hand = 0;
 #pragma unroll
-          for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(cx.g.res(ap, r) != 0) << r;
-          const uint32_t decision = cx.g.decision_ctr();
-          hv.decision_ctr() = decision + 1;
-          t_sample_action(m, hand, P.seed, cx.env_id, decision, P.actions_out + static_cast<size_t>(i) * CATAN_ACTION_WORDS);
+            for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(mx.g.res(ap, r) != 0) << r;
+            const uint32_t decision = mx.g.decision_ctr();
+            hv.decision_ctr() = decision + 1;
+            t_sample_action(m, hand, P.seed, mx.env_id, decision, P.actions_out + static_cast<size_t>(im) * CATAN_ACTION_WORDS);
+          }
         }
+        if (!LISTED) CATAN_MARK(12);
+      } else {                                                       // row warps of a launch with block-wide barriers: their share of the scans
+        __syncthreads();
+        {
+          unsigned nb = S.scan_need;
+          for (int k = 0; nb; ++k) {
+            const int b = __ffs(static_cast<int>(nb)) - 1;
+            nb &= nb - 1;
+            if (k % kEncWarps != warp) continue;
+            const Scan r = t_scan_group(CATAN_VIEW_OF(b), S.topo.topo, S.topo.topox, S.scan_pid[b], lane, 32);
+            if (lane == 0) S.scan[b] = r;
+          }
+        }
+        __syncthreads();
       }
-    } else if (valid) {
-      t_encode_obs_part(cx, P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE, warp - 1);
     }
-    if (!LISTED) { if (warp == 0) CATAN_MARK(12); else if (warp <= CATAN_OBS_TILE_PARTS) CATAN_MARK(13); else CATAN_MARK(14); }
-    if (LISTED) __syncthreads();                                     // warp 0's reset scratch is reused by the next 32 games
+    if (!mask_warp) {
+      TCx cx;
+      cx.g = CATAN_VIEW_OF(lane);
+      cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
+      if (valid) {
+        cx.s = load_seats(cx.g);
+        const int r = warp - kMaskWarps;                             // tile part r, then player part r (the last row warp: the lists too)
+        uint8_t* row = P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE;
+        t_encode_obs_part(cx, row, r);
+        if (!LISTED) CATAN_MARK(13);
+        t_encode_obs_part(cx, row, CATAN_OBS_TILE_PARTS + r);
+        if (r == kRowWarps - 1) t_encode_obs_part(cx, row, CATAN_OBS_PARTS - 1);
+      }
+      if (!LISTED) CATAN_MARK(14);
+    }
+#undef CATAN_MASK_SYNC
+#ifdef CATAN_PROFILE_PHASES
+    if (!LISTED) {                                                   // the last warp of the block to get here: the block's duration
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) last = atomicAdd(&S.scan_pid_done, 1) == kEncWarps - 1;
+      if (last) { CATAN_MARK(15); const unsigned long long d = static_cast<unsigned long long>(clock64() - t_block0); atomicMax(&d_phase[40], d);
+                  atomicAdd(&d_phase[42 + (d < 30000 ? 0 : d < 60000 ? 1 : d < 90000 ? 2 : d < 120000 ? 3 : d < 200000 ? 4 : 5)], 1ull);
+                  if (S.reset_need) atomicAdd(&d_phase[41], 1ull); }
+    }
+#endif
+    if (LISTED) {                                                    // the scratch and the flags are reused by the next 32 games
+      __syncthreads();
+      if (tid == 0) { S.reset_need = 0; S.scan_need = 0; }
+      __syncthreads();
+    }
 #undef CATAN_VIEW_OF
   }
 #undef CATAN_ENC_HOME
@@ -573,6 +704,8 @@ struct catan_env {
   uint32_t* err_flags = nullptr;
   uint32_t* side = nullptr;
   uint64_t* lr_slow_queue = nullptr;
+  uint64_t* rs_queue = nullptr;       // games that ended in the step (auto-reset): env indices
+  uint8_t* stage_rs = nullptr;        // their staging chunks
   catanb::LrCtl* lr_ctl = nullptr;
   int32_t* actions_stage = nullptr;   // device staging for catan_step_host
   uint8_t* obs = nullptr;
@@ -581,7 +714,8 @@ struct catan_env {
   uint8_t* info = nullptr;
   int lr_grid = 0;
   cudaStream_t lr_stream = nullptr;   // high-priority stream of the longest-road updates (overlaps the encode kernel)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t rs_stream = nullptr;   // high-priority stream of the games that are reset (likewise)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_rs = nullptr;
   // catan_set_timing: CUDA events around the two kernels on the caller's stream, a ring of kTimedSteps steps
   bool timing = false;
   cudaEvent_t tev[32][3] = {};
@@ -602,6 +736,7 @@ static EnvParams make_params(const catan_env* env) {
   P.recs = env->recs; P.stage = env->stage; P.n_envs = env->n; P.seed = env->seed; P.first_env_id = env->first_env_id; P.cfg = env->cfg;
   P.obs = env->obs; P.masks = env->masks; P.reward = env->reward; P.info = env->info; P.err_flags = env->err_flags;
   P.side = env->side; P.lr_slow_queue = env->lr_slow_queue; P.lr_ctl = env->lr_ctl;
+  P.rs_queue = env->rs_queue; P.stage_rs = env->stage_rs;
   return P;
 }
 
@@ -667,18 +802,35 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   if (tev) CATAN_CUDA(cudaEventRecord(tev[1], stream));
   CATAN_CUDA(cudaEventRecord(env->ev_fork, stream));
   CATAN_CUDA(cudaStreamWaitEvent(env->lr_stream, env->ev_fork, 0));
-  catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), env->lr_stream>>>(P);
-  CATAN_CUDA(cudaGetLastError());
-  catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count / 2, catanb::kEncThreads, sizeof(catanb::EncSmem), env->lr_stream>>>(P);
-  CATAN_CUDA(cudaGetLastError());
-  catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->lr_stream>>>(P);
-  CATAN_CUDA(cudaGetLastError());
-  catanb::lr_finish_kernel<<<1, 1, 0, env->lr_stream>>>(env->lr_ctl);
-  CATAN_CUDA(cudaGetLastError());
-  CATAN_CUDA(cudaEventRecord(env->ev_join, env->lr_stream));
+  CATAN_CUDA(cudaStreamWaitEvent(env->rs_stream, env->ev_fork, 0));
+  {   // the searched games: search -> encode on the staging copies (8 games of the queue per block) -> home
+    EnvParams L = P;
+    L.list_queue = env->lr_slow_queue; L.list_stage = env->stage; L.list_count = &env->lr_ctl->slow_count; L.list_group = 8;
+    catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), env->lr_stream>>>(L);
+    CATAN_CUDA(cudaGetLastError());
+    catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count, catanb::kEncThreads, sizeof(catanb::EncSmem), env->lr_stream>>>(L);
+    CATAN_CUDA(cudaGetLastError());
+    catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->lr_stream>>>(L);
+    CATAN_CUDA(cudaGetLastError());
+    catanb::lr_finish_kernel<<<1, 1, 0, env->lr_stream>>>(env->lr_ctl);
+    CATAN_CUDA(cudaGetLastError());
+    CATAN_CUDA(cudaEventRecord(env->ev_join, env->lr_stream));
+  }
+  {   // the games that ended: done / reward -> reset -> encode of the new game, ONE game per block (the reset is serial)
+    EnvParams L = P;
+    L.list_queue = env->rs_queue; L.list_stage = env->stage_rs; L.list_count = &env->lr_ctl->rs_count; L.list_group = 1;
+    catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count * 2, catanb::kEncThreads, sizeof(catanb::EncSmem), env->rs_stream>>>(L);
+    CATAN_CUDA(cudaGetLastError());
+    catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->rs_stream>>>(L);
+    CATAN_CUDA(cudaGetLastError());
+    catanb::rs_finish_kernel<<<1, 1, 0, env->rs_stream>>>(env->lr_ctl);
+    CATAN_CUDA(cudaGetLastError());
+    CATAN_CUDA(cudaEventRecord(env->ev_join_rs, env->rs_stream));
+  }
   if (launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream)) return -1;
   if (tev) CATAN_CUDA(cudaEventRecord(tev[2], stream));
   CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join, 0));
+  CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join_rs, 0));
   return 0;
 }
 
@@ -690,10 +842,13 @@ static int check_bound(const catan_env* env) {
 
 static void free_env(catan_env* env) {
   if (env->lr_stream) cudaStreamDestroy(env->lr_stream);
+  if (env->rs_stream) cudaStreamDestroy(env->rs_stream);
   if (env->ev_fork) cudaEventDestroy(env->ev_fork);
   if (env->ev_join) cudaEventDestroy(env->ev_join);
+  if (env->ev_join_rs) cudaEventDestroy(env->ev_join_rs);
   for (auto& slot : env->tev) for (cudaEvent_t ev : slot) if (ev) cudaEventDestroy(ev);
   cudaFree(env->recs); cudaFree(env->stage); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_slow_queue); cudaFree(env->lr_ctl);
+  cudaFree(env->rs_queue); cudaFree(env->stage_rs);
   cudaFree(env->actions_stage);
   delete env;
 }
@@ -755,6 +910,9 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   if (e == cudaSuccess) e = cudaMalloc(&env->side, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMemset(env->side, 0, sizeof(uint32_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&env->lr_slow_queue, sizeof(uint64_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&env->rs_queue, sizeof(uint64_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&env->stage_rs, env->rec_bytes);
+  if (e == cudaSuccess) e = cudaMemset(env->stage_rs, 0, env->rec_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&env->lr_ctl, sizeof(catanb::LrCtl));
   if (e == cudaSuccess) e = cudaMemset(env->lr_ctl, 0, sizeof(catanb::LrCtl));
   if (e == cudaSuccess) e = cudaMalloc(&env->actions_stage, sizeof(int32_t) * CATAN_ACTION_WORDS * n);
@@ -762,9 +920,11 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
     int lo = 0, hi = 0;                                  // (greatest priority is the numerically lowest value)
     e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&env->lr_stream, cudaStreamNonBlocking, hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&env->rs_stream, cudaStreamNonBlocking, hi);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join_rs, cudaEventDisableTiming);
   {
     const int enc_bytes = static_cast<int>(sizeof(catanb::EncSmem));   // > 48 KB: opt in, per instantiation
     if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
@@ -773,6 +933,9 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
     if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_RESET, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_REFRESH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
+    // (more than four blocks per SM only fit with the largest shared-memory carve-out)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::transition_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::lr_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::LrSmem)));

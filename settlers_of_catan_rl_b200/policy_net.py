@@ -204,13 +204,13 @@ class _Observation(nn.Module):
         pooled = self._card_lists(played, self.played_card_mha, (cur.norm, oth.norm, oth.norm, oth.norm))
         cur_played, oth_played = pooled[0], pooled[1:]
         cur_hidden = self._card_lists(obs["current_player_hidden_dev"].unsqueeze(0), self.hidden_card_mha, (cur.norm,))[0]
-        cur_hidden = F.relu(cur.norm_2(cur.proj_hidden_dev_card(cur_hidden)))
-        cur_played = F.relu(cur.norm_3(cur.proj_played_dev_card(cur_played)))
+        cur_hidden = F.relu(_layer_norm_small(cur.proj_hidden_dev_card(cur_hidden), cur.norm_2))
+        cur_played = F.relu(_layer_norm_small(cur.proj_played_dev_card(cur_played), cur.norm_3))
         cur_main = F.relu(cur.norm_1(cur.main_input_layer_1(obs["current_player_main"])))
         cur_out = F.relu(cur.norm_4(cur.final_linear_layer(torch.cat((cur_main, cur_played, cur_hidden), dim=-1))))
         oth_main = torch.stack([obs["next_player_main"], obs["next_next_player_main"], obs["next_next_next_player_main"]], dim=0)
         oth_main = F.relu(oth.norm_1(oth.main_input_layer_1(oth_main)))
-        oth_played = F.relu(oth.norm_2(oth.proj_played_dev_card(oth_played)))
+        oth_played = F.relu(_layer_norm_small(oth.proj_played_dev_card(oth_played), oth.norm_2))
         oth_out = F.relu(oth.norm_3(oth.final_linear_layer(torch.cat((oth_main, oth_played), dim=-1))))     # [3, B, 128]
         final = torch.cat((tiles, cur_out, oth_out[0], oth_out[1], oth_out[2]), dim=-1)
         return F.relu(self.norm(self.final_layer(final)))

@@ -17,6 +17,11 @@ import torch
 from . import _lib, layout as L
 
 
+#: launches of one step: transition, encode (caller's stream) | longest-road search, encode of the searched games, copy-back, counter
+#: bookkeeping (library stream 1) | encode of the games that ended and were reset, copy-back, counter bookkeeping (library stream 2)
+LAUNCHES_PER_STEP = 9
+
+
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -76,7 +81,7 @@ class VecCatanEnv:
         if step_mask is not None:
             assert step_mask.dtype == torch.uint8 and step_mask.is_cuda and step_mask.numel() == self.n_envs
         _lib.check(self.lib.catan_step_masked(self._h, _ptr(actions), _ptr(step_mask), self._stream()))
-        self.kernel_launches += 6                      # transition, encode | lr_slow, encode (listed), copy-back, lr_finish
+        self.kernel_launches += LAUNCHES_PER_STEP
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
     def sample_random(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -90,7 +95,7 @@ class VecCatanEnv:
         """One call (six launches on two streams, the sampler fused into the last): apply ``actions_io`` and overwrite it with the next random-legal actions."""
         assert actions_io.dtype == torch.int32 and actions_io.is_cuda and actions_io.is_contiguous()
         _lib.check(self.lib.catan_step_sample(self._h, _ptr(actions_io), self._stream()))
-        self.kernel_launches += 6
+        self.kernel_launches += LAUNCHES_PER_STEP
         return self.obs, self.reward, self.info[:, L.INFO_DONE], self.info
 
     def get_action_masks(self) -> torch.Tensor:
@@ -103,7 +108,7 @@ class VecCatanEnv:
             return C.c_void_p(0 if a is None else a.ctypes.data)
         assert actions.dtype == np.int32 and actions.flags.c_contiguous
         _lib.check(self.lib.catan_step_host(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
-        self.kernel_launches += 6
+        self.kernel_launches += LAUNCHES_PER_STEP
 
     def step_host_async(self, actions: np.ndarray, obs: np.ndarray = None, masks: np.ndarray = None, reward: np.ndarray = None,
                         info: np.ndarray = None) -> None:
@@ -113,7 +118,7 @@ class VecCatanEnv:
             return C.c_void_p(0 if a is None else a.ctypes.data)
         assert actions.dtype == np.int32 and actions.flags.c_contiguous
         _lib.check(self.lib.catan_step_host_async(self._h, p(actions), p(obs), p(masks), p(reward), p(info), self._stream()))
-        self.kernel_launches += 6
+        self.kernel_launches += LAUNCHES_PER_STEP
 
     def step_sample_host_async(self, actions_io: np.ndarray, reward: np.ndarray = None, info: np.ndarray = None) -> None:
         """``step_sample`` with pinned host buffers, not synchronised: ``actions_io`` is applied and overwritten with the next
@@ -122,7 +127,7 @@ class VecCatanEnv:
             return C.c_void_p(0 if a is None else a.ctypes.data)
         assert actions_io.dtype == np.int32 and actions_io.flags.c_contiguous
         _lib.check(self.lib.catan_step_sample_host_async(self._h, p(actions_io), p(reward), p(info), self._stream()))
-        self.kernel_launches += 6
+        self.kernel_launches += LAUNCHES_PER_STEP
 
     def reset_host(self, obs: np.ndarray = None, masks: np.ndarray = None, info: np.ndarray = None) -> None:
         def p(a):

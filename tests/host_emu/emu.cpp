@@ -18,7 +18,7 @@ struct EmuEnv {
   alignas(16) uint8_t mask[CATAN_MASK_STRIDE];
   alignas(16) uint8_t scratch[CATAN_LP_SCRATCH_BYTES + 16];
   uint32_t wbuf[CATAN_RESET_WORDS];
-  uint8_t arr[96];
+  alignas(4) uint8_t arr[128];
   catan_config_t cfg;
   uint64_t seed, env_id;
 };
@@ -114,6 +114,12 @@ void emu_export_state(EmuEnv* e, int16_t* out) { rec_to_state(e->g, *reinterpret
 void emu_import_state(EmuEnv* e, const int16_t* in) {
   state_to_rec(*reinterpret_cast<const catan_state_t*>(in), e->g);
   encode(e);
+}
+int emu_randomise_uncertainty(EmuEnv* e, int controlling_pid, int max_attempts) {
+  TCx cx = make_ctx(e);
+  const int n = t_randomise_uncertainty(cx, controlling_pid, max_attempts);
+  encode(e);
+  return n;
 }
 int emu_longest_path(EmuEnv* e, int pid) { TCx cx = make_ctx(e); return t_longest_path(cx.g, h_topo, pid, e->scratch, 0); }
 int emu_rec_bytes(void) { return static_cast<int>(sizeof(GameRec)); }

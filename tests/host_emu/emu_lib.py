@@ -55,6 +55,8 @@ def lib(flavor="default"):
         l.emu_masks.restype = C.POINTER(C.c_uint8)
         l.emu_export_state.argtypes = [C.c_void_p, C.POINTER(C.c_int16)]
         l.emu_import_state.argtypes = [C.c_void_p, C.POINTER(C.c_int16)]
+        l.emu_randomise_uncertainty.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        l.emu_randomise_uncertainty.restype = C.c_int
         l.emu_longest_path.argtypes = [C.c_void_p, C.c_int]
         l.emu_longest_path.restype = C.c_int
         _libs[flavor] = l
@@ -103,6 +105,9 @@ class EmuEnv:
         a = np.zeros(L.ACTION_WORDS, dtype=np.int32)
         self.l.emu_sample(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)))
         return a
+
+    def randomise_uncertainty(self, controlling_pid, max_attempts=100000):
+        return self.l.emu_randomise_uncertainty(self.h, int(controlling_pid), int(max_attempts))
 
     def longest_path(self, pid):
         return self.l.emu_longest_path(self.h, pid)

@@ -76,5 +76,10 @@ def test_policy_on_cuda_matches_policy_on_cpu():
     (vg.mean() + lpg.mean() + eg).backward()
     vc, lpc, ec = cpu.evaluate_actions(obs_c, masks_c, rows.cpu())
     (vc.mean() + lpc.mean() + ec).backward()
+    checked = 0
     for (n, p), (_, q) in zip(pol.named_parameters(), cpu.named_parameters()):
-        torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-3, atol=2e-5, msg=lambda m, n=n: n + ": " + m)
+        assert (p.grad is None) == (q.grad is None), n               # (the value normaliser's constants take no gradient)
+        if p.grad is not None:
+            torch.testing.assert_close(p.grad.cpu(), q.grad, rtol=2e-3, atol=2e-5, msg=lambda m, n=n: n + ": " + m)
+            checked += 1
+    assert checked > 150
