@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--preroll", type=int, default=1500, help="untimed ticks every leg plays from the first reset before anything is timed")
     ap.add_argument("--ref-envs-per-proc", type=int, default=0, help="reference arm: envs per worker process (0: sized from --steps)")
     ap.add_argument("--no-python-reference", action="store_true", help="cpu_baseline / reference arm: the C port only")
+    ap.add_argument("--no-graphs", action="store_true", help="issue every launch of a step directly instead of replaying its CUDA graph")
     return ap.parse_args()
 
 
@@ -217,7 +218,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # this build
 # ------------------------------------------------------------------------------------------------
-def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_groups=2, barrier=None, fused_sampler=True):
+def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_groups=2, barrier=None, fused_sampler=True, graphs=True):
     import torch
     from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
     sizes = [n // n_groups + (1 if gi < n % n_groups else 0) for gi in range(n_groups)]     # sum = n
@@ -225,6 +226,7 @@ def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_grou
     for gi in range(n_groups):
         half = sizes[gi]
         e = VecCatanEnv(half, device=dev, seed=seed, first_env_id=rank * n + sum(sizes[:gi]))
+        e.set_graphs(graphs)
         e.reset()
         a = e.sample_random()
         for _ in range(warm_ticks):
@@ -304,6 +306,7 @@ def run_b200_arm(args):
     rec_bytes = _lib_record_bytes()
     # games are numbered globally: rank r owns [r*n, (r+1)*n) — no data-path collective
     env = VecCatanEnv(n, device=dev, seed=args.seed, first_env_id=rank * n)
+    env.set_graphs(not args.no_graphs)             # one cudaGraphLaunch per step instead of ~20 driver calls (the same launches)
     env.reset()
     acts = env.sample_random()
     warm = max(3, args.warmup)
@@ -397,7 +400,7 @@ def run_b200_arm(args):
     e2e_pipe_error = None
     try:
         e2e_pipe, e2e_pipe_errs = e2e_double_buffered(n, e2e_steps * 10, args.preroll + warm, dev, args.seed, rank, world,
-                                                      max(1, args.e2e_groups), barrier)
+                                                      max(1, args.e2e_groups), barrier, graphs=not args.no_graphs)
     except Exception as exc:  # reported, never hidden: the synchronous loop above then stands as e2e
         e2e_pipe, e2e_pipe_errs, e2e_pipe_error = 0.0, -1, "%s: %s" % (type(exc).__name__, exc)
     h2d = n * L.ACTION_WORDS * 4
@@ -545,8 +548,8 @@ def run_b200_arm(args):
                                                "achieved": TRANSITION_BYTES_PER_ENV_STEP * n / (transition_ms * 1e-3) / 1e9},
                          "whole_step": {"ms": per_launch_ms, "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * n,
                                         "achieved": step_achieved, "frac": step_achieved / peak,
-                                        "note": "6 launches on 2 streams: transition, encode | longest-road search, encode of "
-                                                "the searched games, copy-back, counter bookkeeping"}},
+                                        "note": "9 launches on 3 streams, replayed as one CUDA graph: transition, encode | longest-road search, encode of the "
+                                                "searched games, copy-back, counters | encode (done / reset / new game) of the games that ended, copy-back, counters"}},
             "cpu_baseline": cpu_baseline,
             "cpu_baseline_port": cpu_baseline_port,
             "aux": aux,

@@ -203,6 +203,20 @@ int catan_masked_categorical(const float* logits_dev, const float* mask_dev, con
                              const float* uniforms_dev, int B, int D, int64_t* actions_dev, float* logp_dev,
                              float* entropy_dev, void* stream);
 
+/* Game.randomise_uncertainty (game/game.py:1207-1282; consumer RL/forward_search_policy/worker.py:42-58): for every env n with
+ * controlling_pid_dev[n] in 1..4, re-deal what that player cannot see (the deck + the opponents' hidden cards; the opponents' hands
+ * between its minimum and maximum beliefs) until every resource adds up to 19 again; 0 leaves the env alone.  Draws come from the
+ * game stream in the reference's order, so a reference game under the shared Philox stream is re-dealt identically.  The bound
+ * observation / mask rows are refreshed.  An env whose beliefs admit no deal within max_attempts (the reference would loop forever)
+ * gets bit CATAN_ERR_NO_DEAL in its sticky error word; its hands are then left at the minimum beliefs. */
+/* CUDA-graph replay of the step calls: with enable != 0, catan_step / catan_step_masked / catan_step_sample and the two *_host_async
+ * calls capture their work (9 launches on three streams, event calls, copies) ONCE per distinct set of buffer pointers and replay it
+ * with one cudaGraphLaunch on the caller's stream afterwards.  Off by default; a call made while the caller's stream is itself being
+ * captured (e.g. inside torch.cuda.graph) is issued directly and becomes part of that graph.  Host buffers must be pinned. */
+int catan_set_graphs(catan_env_t* env, int enable);
+
+int catan_randomise_uncertainty(catan_env_t* env, const uint8_t* controlling_pid_dev, int max_attempts, void* stream);
+
 /* ---- the two small-dimension pieces of the policy network that the library kernels handle badly at rollout batch sizes ------
  * (the network itself stays PyTorch; these are autograd functions on its side, settlers_of_catan_rl_b200/policy_ops.py)
  * catan_tile_attention_*: the tile encoder's self-attention (RL/models/tile_encoder.py:43-57, multi_headed_attention.py:28-39):

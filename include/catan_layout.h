@@ -113,7 +113,8 @@ enum { CATAN_RES_BRICK = 0, CATAN_RES_WOOD = 1, CATAN_RES_ORE = 2, CATAN_RES_SHE
 enum {
   CATAN_ERR_NONE = 0, CATAN_ERR_BAD_TYPE = 1, CATAN_ERR_PHASE = 2, CATAN_ERR_CANNOT_AFFORD = 3,
   CATAN_ERR_BAD_LOCATION = 4, CATAN_ERR_BAD_CARD = 5, CATAN_ERR_BAD_RESOURCE = 6, CATAN_ERR_BAD_TARGET = 7,
-  CATAN_ERR_BAD_HEAD_VALUE = 8
+  CATAN_ERR_BAD_HEAD_VALUE = 8,
+  CATAN_ERR_NO_DEAL = 9       /* catan_randomise_uncertainty: the controlling player's beliefs admit no consistent deal */
 };
 
 /* ---- canonical unpacked game state (== Game.save_current_state, game/game.py:1013-1091, plus the

@@ -662,6 +662,21 @@ __global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kern
 #undef CATAN_ENC_HOME
 }
 
+// Game.randomise_uncertainty (game.py:1207-1282) for every env whose byte in `controlling` is a PlayerId: one thread per game on
+// the home records (a few hundred draws and byte moves per game; this is the forward-search hook, not the step path).  A game whose
+// beliefs admit no consistent deal within max_attempts gets bit CATAN_ERR_NO_DEAL in its sticky error word.
+__global__ void __launch_bounds__(128) randomise_kernel(const __grid_constant__ EnvParams P, const uint8_t* controlling, int max_attempts) {
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= P.n_envs) return;
+  const int c = controlling[e];
+  if (c < WHITE || c > RED) return;
+  TCx cx;
+  cx.g = game_view(P.recs, static_cast<size_t>(e));
+  cx.T = &d_topo; cx.X = nullptr; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(e);
+  cx.s = load_seats(cx.g);
+  if (t_randomise_uncertainty(cx, c, max_attempts) == 0) P.err_flags[e] |= 1u << CATAN_ERR_NO_DEAL;
+}
+
 // stand-alone sampler: one thread per env, reads the bound mask / obs rows back from global memory
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(uint8_t* recs, int n_envs, uint64_t seed, uint64_t first_env_id,
                                                                 const uint8_t* masks, const uint8_t* obs, int32_t* actions_out) {
@@ -717,6 +732,12 @@ struct catan_env {
   cudaStream_t rs_stream = nullptr;   // high-priority stream of the games that are reset (likewise)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_rs = nullptr;
   // catan_set_timing: CUDA events around the two kernels on the caller's stream, a ring of kTimedSteps steps
+  // catan_set_graphs: every distinct step call (entry point + buffer pointers) is captured once into a CUDA graph on an internal
+  // stream and replayed on the caller's stream afterwards: one driver call per step instead of ~20 (9 launches, 6 event calls, copies)
+  bool use_graphs = false;
+  cudaStream_t capture_stream = nullptr;
+  struct StepGraph { int kind; const void* p[4]; cudaGraphExec_t exec; };
+  std::vector<StepGraph> graphs;
   bool timing = false;
   cudaEvent_t tev[32][3] = {};
   unsigned long long timed = 0;        // steps recorded since timing was switched on
@@ -834,6 +855,42 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   return 0;
 }
 
+static void drop_graphs(catan_env* env) {
+  for (auto& g : env->graphs) cudaGraphExecDestroy(g.exec);
+  env->graphs.clear();
+}
+
+// Replay (capturing it first if need be) the work `record(capture stream)` issues, keyed by (kind, p0..p3).  Returns 1 when the
+// caller has to issue the work directly (graphs off, timing hooks on, or a capture is already in progress on its stream).
+template <class Record>
+static int replay_step_graph(catan_env* env, int kind, const void* p0, const void* p1, const void* p2, const void* p3, cudaStream_t stream,
+                             Record record) {
+  if (!env->use_graphs || env->timing) return 1;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) { cudaGetLastError(); return 1; }
+  if (st != cudaStreamCaptureStatusNone) return 1;                   // (the caller is building its own graph: become part of it)
+  for (auto& g : env->graphs)
+    if (g.kind == kind && g.p[0] == p0 && g.p[1] == p1 && g.p[2] == p2 && g.p[3] == p3) {
+      CATAN_CUDA(cudaGraphLaunch(g.exec, stream));
+      return 0;
+    }
+  if (!env->capture_stream) CATAN_CUDA(cudaStreamCreateWithFlags(&env->capture_stream, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  CATAN_CUDA(cudaStreamBeginCapture(env->capture_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = record(env->capture_stream);
+  cudaError_t e = cudaStreamEndCapture(env->capture_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+  if (env->graphs.size() >= 64) drop_graphs(env);                    // (callers use a handful of buffer sets)
+  env->graphs.push_back({kind, {p0, p1, p2, p3}, exec});
+  CATAN_CUDA(cudaGraphLaunch(exec, stream));
+  return 0;
+}
+
 static int check_bound(const catan_env* env) {
   if (!env) return fail("null handle");
   if (!env->obs || !env->masks || !env->reward || !env->info) return fail("catan_bind has not been called");
@@ -841,6 +898,8 @@ static int check_bound(const catan_env* env) {
 }
 
 static void free_env(catan_env* env) {
+  drop_graphs(env);
+  if (env->capture_stream) cudaStreamDestroy(env->capture_stream);
   if (env->lr_stream) cudaStreamDestroy(env->lr_stream);
   if (env->rs_stream) cudaStreamDestroy(env->rs_stream);
   if (env->ev_fork) cudaEventDestroy(env->ev_fork);
@@ -958,6 +1017,7 @@ int catan_num_envs(const catan_env_t* env) { return env ? env->n : 0; }
 int catan_set_config(catan_env_t* env, const catan_config_t* cfg) {
   if (!env || !cfg) return fail("null argument");
   env->cfg = *cfg;
+  drop_graphs(env);                                                  // (the config is baked into the captured launches)
   return 0;
 }
 
@@ -968,6 +1028,7 @@ int catan_bind(catan_env_t* env, uint8_t* obs_dev, uint8_t* masks_dev, float* re
        reinterpret_cast<uintptr_t>(info_dev)) & 15)
     return fail("output buffers must be 16-byte aligned");
   env->obs = obs_dev; env->masks = masks_dev; env->reward = reward_dev; env->info = info_dev;
+  drop_graphs(env);
   return 0;
 }
 
@@ -988,7 +1049,9 @@ int catan_step_masked(catan_env_t* env, const int32_t* actions_dev, const uint8_
   EnvParams P = make_params(env);
   P.actions = actions_dev;
   P.env_mask = step_mask_dev;
-  return launch_step<false>(env, P, static_cast<cudaStream_t>(stream));
+  const int g = replay_step_graph(env, 1, actions_dev, step_mask_dev, nullptr, nullptr, static_cast<cudaStream_t>(stream),
+                                  [&](cudaStream_t s) { return launch_step<false>(env, P, s); });
+  return g <= 0 ? g : launch_step<false>(env, P, static_cast<cudaStream_t>(stream));
 }
 
 int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream) {
@@ -998,7 +1061,9 @@ int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream) {
   EnvParams P = make_params(env);
   P.actions = actions_io_dev;
   P.actions_out = actions_io_dev;
-  return launch_step<true>(env, P, static_cast<cudaStream_t>(stream));
+  const int g = replay_step_graph(env, 2, actions_io_dev, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream),
+                                  [&](cudaStream_t s) { return launch_step<true>(env, P, s); });
+  return g <= 0 ? g : launch_step<true>(env, P, static_cast<cudaStream_t>(stream));
 }
 
 int catan_sample_random(catan_env_t* env, int32_t* actions_out_dev, void* stream) {
@@ -1031,11 +1096,18 @@ int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t
   if (check_bound(env)) return -1;
   if (!actions_host) return fail("actions_host is null");
   if (device_guard(env)) return -1;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_host, sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(env->n),
-                             cudaMemcpyHostToDevice, s));
-  if (catan_step(env, env->actions_stage, stream)) return -1;
-  return copy_outputs_to_host(env, obs_host, masks_host, reward_host, info_host, s, false);
+  auto issue = [&](cudaStream_t s) -> int {
+    CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_host, sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(env->n),
+                               cudaMemcpyHostToDevice, s));
+    EnvParams P = make_params(env);
+    P.actions = env->actions_stage;
+    if (launch_step<false>(env, P, s)) return -1;
+    return copy_outputs_to_host(env, obs_host, masks_host, reward_host, info_host, s, false);
+  };
+  // (the graph is keyed by the host pointers: pinned buffers that the caller reuses every tick)
+  const void* k3 = obs_host ? static_cast<const void*>(obs_host) : static_cast<const void*>(masks_host);
+  const int g = replay_step_graph(env, 3, actions_host, reward_host, info_host, k3, static_cast<cudaStream_t>(stream), issue);
+  return g <= 0 ? g : issue(static_cast<cudaStream_t>(stream));
 }
 
 // catan_step_sample with host buffers, not synchronised: actions_io_host (pinned) is copied in, applied, and overwritten with
@@ -1044,12 +1116,18 @@ int catan_step_sample_host_async(catan_env_t* env, int32_t* actions_io_host, flo
   if (check_bound(env)) return -1;
   if (!actions_io_host) return fail("actions_io_host is null");
   if (device_guard(env)) return -1;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t bytes = sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(env->n);
-  CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_io_host, bytes, cudaMemcpyHostToDevice, s));
-  if (catan_step_sample(env, env->actions_stage, stream)) return -1;
-  CATAN_CUDA(cudaMemcpyAsync(actions_io_host, env->actions_stage, bytes, cudaMemcpyDeviceToHost, s));
-  return copy_outputs_to_host(env, nullptr, nullptr, reward_host, info_host, s, false);
+  auto issue = [&](cudaStream_t s) -> int {
+    CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_io_host, bytes, cudaMemcpyHostToDevice, s));
+    EnvParams P = make_params(env);
+    P.actions = env->actions_stage;
+    P.actions_out = env->actions_stage;
+    if (launch_step<true>(env, P, s)) return -1;
+    CATAN_CUDA(cudaMemcpyAsync(actions_io_host, env->actions_stage, bytes, cudaMemcpyDeviceToHost, s));
+    return copy_outputs_to_host(env, nullptr, nullptr, reward_host, info_host, s, false);
+  };
+  const int g = replay_step_graph(env, 4, actions_io_host, reward_host, info_host, nullptr, static_cast<cudaStream_t>(stream), issue);
+  return g <= 0 ? g : issue(static_cast<cudaStream_t>(stream));
 }
 
 int catan_step_host(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host, float* reward_host,
@@ -1126,6 +1204,17 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
   return 0;
 }
 
+int catan_randomise_uncertainty(catan_env_t* env, const uint8_t* controlling_pid_dev, int max_attempts, void* stream) {
+  if (check_bound(env)) return -1;
+  if (!controlling_pid_dev || max_attempts <= 0) return fail("catan_randomise_uncertainty: bad argument");
+  if (device_guard(env)) return -1;
+  EnvParams P = make_params(env);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  catanb::randomise_kernel<<<(env->n + 127) / 128, 128, 0, s>>>(P, controlling_pid_dev, max_attempts);
+  CATAN_CUDA(cudaGetLastError());
+  return launch_encode<catanb::MODE_REFRESH, false>(env, P, 0, env->n, s);   // observations / masks of the re-dealt games
+}
+
 int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
   if (!env || !out_host) return fail("null argument");
   if (device_guard(env)) return -1;
@@ -1135,6 +1224,14 @@ int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
   out_host[0] = last.total; out_host[1] = last.slow_total;
   out_host[2] = last.dbg[4]; out_host[3] = last.dbg[5];
   for (int i = 0; i < 4; ++i) out_host[4 + i] = last.dbg[i];
+  return 0;
+}
+
+int catan_set_graphs(catan_env_t* env, int enable) {
+  if (!env) return fail("null handle");
+  if (device_guard(env)) return -1;
+  env->use_graphs = enable != 0;
+  if (!enable) { CATAN_CUDA(cudaDeviceSynchronize()); drop_graphs(env); }
   return 0;
 }
 

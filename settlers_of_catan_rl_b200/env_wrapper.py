@@ -37,7 +37,8 @@ class _GameView:
     """the handful of ``env.game.*`` attributes the reference's managers read (game_manager.py:152-159,
     evaluation/evaluation_manager.py:86-88)"""
 
-    def __init__(self, st):
+    def __init__(self, st, owner=None):
+        self._owner = owner
         self.players_need_to_discard = bool(st["need_discard"])
         self.players_to_discard = [PlayerId(int(x)) for x in st["discard_queue"][: int(st["n_discard"])]]
         self.must_respond_to_trade = bool(st["must_respond"])
@@ -59,6 +60,10 @@ class _GameView:
         self.turn = int(st["turn"])
         self.die_1, self.die_2 = int(st["die1"]) or None, int(st["die2"]) or None
         self.victory_points = {PlayerId(p + 1): int(st["vp"][p]) for p in range(4)}
+
+    def randomise_uncertainty(self, controlling_player_id):
+        """game/game.py:1207-1282, as the forward-search worker calls it (RL/forward_search_policy/worker.py:44)"""
+        self._owner._randomise_uncertainty(int(controlling_player_id))
 
 
 class EnvWrapper(object):
@@ -114,7 +119,7 @@ class EnvWrapper(object):
     def game(self):
         self._ensure_started()
         if self._game is None:
-            self._game = _GameView(self._vec.export_state().view(L.STATE_DTYPE)[0, 0])
+            self._game = _GameView(self._vec.export_state().view(L.STATE_DTYPE)[0, 0], self)
         return self._game
 
     # ---- EnvWrapper API
@@ -158,6 +163,11 @@ class EnvWrapper(object):
         self._game = None
         self.curr_vps = dict(state["vps"])
         self.winner = state["winner"]
+
+    def _randomise_uncertainty(self, pid: int) -> None:
+        self._vec.randomise_uncertainty(pid)
+        self._obs[:], self._masks[:] = self._vec.rows_host()
+        self._game = None
 
     def render(self):
         raise NotImplementedError("rendering is outside the hot path (SURVEY.md §2 row 16)")

@@ -147,6 +147,15 @@ class VecCatanEnv:
         _lib.check(self.lib.catan_import_state(self._h, first, states.shape[0], C.c_void_p(states.ctypes.data)))
         self.kernel_launches += 1
 
+    def randomise_uncertainty(self, controlling_pid, max_attempts: int = 10000) -> None:
+        """Game.randomise_uncertainty (game/game.py:1207-1282) for every env: ``controlling_pid`` = a PlayerId for all envs, or a uint8
+        CUDA tensor [N] (0 = leave that env alone).  Obs / mask rows are refreshed; envs without a consistent deal get error bit 9."""
+        if not torch.is_tensor(controlling_pid):
+            controlling_pid = torch.full((self.n_envs,), int(controlling_pid), dtype=torch.uint8, device=self.device)
+        assert controlling_pid.dtype == torch.uint8 and controlling_pid.is_cuda and controlling_pid.numel() == self.n_envs
+        _lib.check(self.lib.catan_randomise_uncertainty(self._h, _ptr(controlling_pid), int(max_attempts), self._stream()))
+        self.kernel_launches += 2
+
     def rows_host(self):
         """(obs rows, mask rows) of all envs as numpy arrays (a D2H copy; used by the single-env adapter after an import)"""
         return self.obs.cpu().numpy(), self.masks.cpu().numpy()
@@ -170,6 +179,10 @@ class VecCatanEnv:
         out = np.zeros(8, dtype=np.uint64)
         _lib.check(self.lib.catan_read_lr_stats(self._h, C.c_void_p(out.ctypes.data)))
         return out
+
+    def set_graphs(self, enable: bool) -> None:
+        """replay every distinct step call as one CUDA graph (catan_set_graphs): pass the same tensors / pinned buffers every tick"""
+        _lib.check(self.lib.catan_set_graphs(self._h, int(enable)))
 
     def set_timing(self, enable: bool) -> None:
         """CUDA events around the transition and encode kernels of every following step (catan_set_timing)"""

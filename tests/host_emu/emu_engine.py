@@ -46,6 +46,9 @@ class EmuEngine:
     def rows_host(self):
         return self.e.obs()[None, :], self.e.masks()[None, :]
 
+    def randomise_uncertainty(self, pid, max_attempts=10000):
+        self.e.randomise_uncertainty(int(pid), int(max_attempts))
+
     def set_reward_annealing_factor(self, factor):
         self.config.reward_annealing_factor = float(factor)
         self.e.l.emu_set_config(self.e.h, C.byref(self.config))

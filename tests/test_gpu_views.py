@@ -144,3 +144,87 @@ def test_async_host_step_with_the_fused_sampler():
         side.synchronize()
         assert torch.equal(ha, hb) and torch.equal(ra, rb) and torch.equal(ia, ib), tick
     assert np.array_equal(a.export_state(), b.export_state())
+
+
+def test_cuda_randomise_uncertainty_matches_the_game_core_and_conserves():
+    """catan_randomise_uncertainty (game.py:1207-1282) on the device == the same game logic compiled for the host (which
+    tests/test_randomise_uncertainty.py pins against the reference), game by game incl. the draw counters; and at scale the
+    re-dealt games keep 19 cards per resource and the controlling player's hand and hidden cards."""
+    import numpy as np
+    from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
+    from tests.host_emu.emu_lib import EmuEnv
+    n = 4096
+    env = VecCatanEnv(n, seed=12, first_env_id=77)
+    env.reset()
+    a = env.sample_random()
+    for _ in range(700):
+        env.step_sample(a)
+    before = env.export_state()
+    ctrl = torch.from_numpy((np.arange(n) % 5).astype(np.uint8)).cuda()          # 0 = untouched
+    env.err_flags(clear=True)
+    env.randomise_uncertainty(ctrl, max_attempts=300)
+    after = env.export_state()
+    flags = env.err_flags()
+    sb, sa = before.view(L.STATE_DTYPE)[:, 0], after.view(L.STATE_DTYPE)[:, 0]
+    c = ctrl.cpu().numpy()
+    ok = (flags >> 9) & 1 == 0
+    assert ok.mean() > 0.5
+    untouched = c == 0
+    assert np.array_equal(before[untouched], after[untouched])
+    dealt = ok & ~untouched & (sb["initial_phase"] == 0)
+    assert np.array_equal((sa["res"].sum(axis=1) + sa["bank"])[dealt], np.full((int(dealt.sum()), 5), 19))
+    # (hand SIZES are kept only when the controlling player's minimum beliefs do not overestimate a hand -- the reference has no
+    # such guarantee either, its closing assert is the per-resource sum, game.py:1276-1282)
+    assert (sa["res"].sum(axis=2)[dealt] == sb["res"].sum(axis=2)[dealt]).mean() > 0.9
+    idx = np.nonzero(dealt)[0]
+    assert np.array_equal(sa["res"][idx, c[idx] - 1], sb["res"][idx, c[idx] - 1])
+    assert np.array_equal(sa["hidden"][idx, c[idx] - 1], sb["hidden"][idx, c[idx] - 1])
+    assert np.array_equal(sa["n_hidden"], sb["n_hidden"]) and np.array_equal(sa["deck_n"], sb["deck_n"])
+    # game by game against the host build of the same logic
+    for e in list(idx[:40]) + list(np.nonzero(~ok & ~untouched)[0][:5]):
+        emu = EmuEnv(seed=12, env_id=77 + int(e), auto_reset=0)
+        emu.import_state(before[e])
+        emu.randomise_uncertainty(int(c[e]), 300)
+        assert np.array_equal(emu.state(), after[e]), e
+    # the bound rows were refreshed
+    o = env.obs.cpu().numpy()
+    e = int(idx[0])
+    emu = EmuEnv(seed=12, env_id=77 + e, auto_reset=0)
+    emu.import_state(after[e])
+    assert np.array_equal(emu.obs(), o[e])
+
+
+def test_library_graph_replay_is_the_same_step():
+    """catan_set_graphs: the captured-and-replayed step (device-resident and pinned-host variants) == the directly issued one"""
+    import numpy as np
+    from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
+    n = 3000
+    a_env, b_env = VecCatanEnv(n, seed=5), VecCatanEnv(n, seed=5)
+    b_env.set_graphs(True)
+    for e in (a_env, b_env):
+        e.reset()
+    acts_a, acts_b = a_env.sample_random(), b_env.sample_random()
+    for t in range(300):
+        a_env.step_sample(acts_a)
+        b_env.step_sample(acts_b)
+    assert torch.equal(a_env.obs, b_env.obs) and torch.equal(a_env.masks, b_env.masks) and torch.equal(acts_a, acts_b)
+    assert np.array_equal(a_env.export_state(), b_env.export_state())
+    # masked step with explicit actions, and a config change (drops the captured graphs)
+    mask = (torch.arange(n, device="cuda") % 3 != 0).to(torch.uint8)
+    b_env.set_reward_annealing_factor(0.5); a_env.set_reward_annealing_factor(0.5)
+    for t in range(20):
+        a_env.step(acts_a, step_mask=mask); a_env.sample_random(acts_a)
+        b_env.step(acts_b, step_mask=mask); b_env.sample_random(acts_b)
+    assert torch.equal(a_env.obs, b_env.obs) and torch.equal(a_env.reward, b_env.reward)
+    # pinned host buffers: H2D actions, step + sampler, D2H actions / reward / info in one replayed graph
+    h_act = [torch.empty((n, L.ACTION_WORDS), dtype=torch.int32).pin_memory() for _ in range(2)]
+    h_rew = [torch.empty((n, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_info = [torch.empty((n, L.INFO_STRIDE), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for k, (e, acts) in enumerate(((a_env, acts_a), (b_env, acts_b))):
+        h_act[k].copy_(acts)
+    for t in range(30):
+        for k, e in enumerate((a_env, b_env)):
+            e.step_sample_host_async(h_act[k].numpy(), h_rew[k].numpy(), h_info[k].numpy())
+        torch.cuda.synchronize()
+        assert torch.equal(h_act[0], h_act[1]) and torch.equal(h_rew[0], h_rew[1]) and torch.equal(h_info[0], h_info[1]), t
+    assert int(a_env.err_flags().any()) == 0 and int(b_env.err_flags().any()) == 0
