@@ -11,6 +11,7 @@
 // game/components/{board,corner,edge,player}.py, env/wrapper.py (EnvWrapper).  See SURVEY.md §8a.
 #pragma once
 
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -26,7 +27,14 @@
 #define CATAN_FN_NOINLINE __device__ __noinline__
 #define CATAN_NO_UNROLL _Pragma("unroll 1")
 #define CATAN_LANES 32
+// The phase functions take their game through a pointer the compiler cannot trace back to the kernel's shared memory: without a
+// hint every access to the staged chunk and topology is a generic LD / ST (L1TEX address check, "long scoreboard" stalls) instead
+// of LDS / STS.  A function that only ever runs on staged data says so.
+#define CATAN_IN_SMEM(p_) __builtin_assume(__isShared(p_))
+#define CATAN_IN_LOCAL(p_) __builtin_assume(__isLocal(p_))     // (a caller's stack object passed by reference)
 #else
+#define CATAN_IN_SMEM(p_) ((void)0)
+#define CATAN_IN_LOCAL(p_) ((void)0)
 #define CATAN_FN static inline
 #define CATAN_FN_NOINLINE static
 #define CATAN_NO_UNROLL
@@ -68,22 +76,20 @@ static_assert(sizeof(Topo) == 1008, "Topo must stay a multiple of 16 bytes");
 // Field meaning == catan_state_t (catan_layout.h).
 // ------------------------------------------------------------------------------------------------
 struct alignas(16) GameRec {
+  // ---- cold, 16 bit: the belief tables and the production cache (follow-up passes, observation)
   int16_t est_min[4][3][5];   // opponent_min_res[observer][label][r]        (player.py:38-43)
   int16_t est_max[4][3][5];
-  int16_t vis[4][5];          // visible_resources (unbounded growth through trades -> 16 bit)
   uint16_t prod[4][13];       // engine-private cache of the observation's production table (wrapper.py:595-610): 4-bit counts,
                               // entry j = slot * 10 + number slot in the obs order at bits 4 * (j & 3) of prod[p][j >> 2]; kept
                               // current by the transition (a settlement adds 1, a city one more per adjacent tile)
+  // ---- HOT [CATAN_HOT_BEGIN, CATAN_HOT_END): what the rules of almost every action read and write.  The transition kernel stages
+  // only this part of a chunk in shared memory (6 KB instead of 26 KB) and touches the cold parts in place.
+  int16_t vis[4][5];          // visible_resources (unbounded growth through trades -> 16 bit)
   uint32_t rng_ctr;           // game-stream Philox draw counter
   uint32_t decision_ctr;      // sampler-stream decision index
   uint32_t episode_steps;     // env steps since the last reset
   uint16_t actions_this_turn;
   uint16_t turn;
-  uint8_t corner[54];         // (owner PlayerId << 2) | type (0 none, 1 settlement, 2 city)
-  uint8_t edge[72];           // road owner PlayerId, 0 none
-  uint8_t tile_res[19];
-  uint8_t tile_val[19];
-  uint8_t harbour_perm[9];
   uint8_t robber_tile;
   uint8_t res[4][5];
   int8_t vp[4];
@@ -98,11 +104,8 @@ struct alignas(16) GameRec {
   uint8_t cur_longest_path[4];
   uint8_t has_path_key[4];
   uint8_t cur_army[4];
-  uint8_t hidden[4][13];      // ordered card lists, two cards per byte (card i at bits 4 * (i & 1) of byte i >> 1; unused = 0)
-  uint8_t played[4][13];
   uint8_t bank[5];
   uint8_t deck_n;
-  uint8_t deck[25];
   uint8_t player_order[4];
   uint8_t player_order_id, players_go;
   uint8_t lr_holder, lr_count, la_holder, la_count;
@@ -120,9 +123,21 @@ struct alignas(16) GameRec {
   uint8_t winner;
   uint8_t lr_dirty[4];        // engine-private (not part of the canonical state): an opponent built next to this player's
                               // roads since cur_longest_path was measured -> the incremental update is not allowed
+  // ---- cold, bytes: the board and the card lists (placements, dice payout, development cards, observation)
+  uint8_t corner[54];         // (owner PlayerId << 2) | type (0 none, 1 settlement, 2 city)
+  uint8_t edge[72];           // road owner PlayerId, 0 none
+  uint8_t tile_res[19];
+  uint8_t tile_val[19];
+  uint8_t harbour_perm[9];
+  uint8_t hidden[4][13];      // ordered card lists, two cards per byte (card i at bits 4 * (i & 1) of byte i >> 1; unused = 0)
+  uint8_t played[4][13];
+  uint8_t deck[25];
   uint8_t pad_[1];
 };
+#define CATAN_HOT_BEGIN 344   /* offsetof(GameRec, vis) */
+#define CATAN_HOT_END 529     /* offsetof(GameRec, corner) */
 static_assert(sizeof(GameRec) == 832, "GameRec layout changed: keep it a multiple of 16 bytes and update DESIGN.md");
+static_assert(offsetof(GameRec, vis) == CATAN_HOT_BEGIN && offsetof(GameRec, corner) == CATAN_HOT_END && CATAN_HOT_BEGIN % 8 == 0, "the hot range of a record");
 
 // translated action (wrapper.py:114-166)
 struct Act {

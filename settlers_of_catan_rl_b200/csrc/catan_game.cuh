@@ -36,12 +36,25 @@ namespace catanb {
 // view of one game inside a lane-interleaved chunk.  Field names / meaning == GameRec (catan_core.cuh).
 // ------------------------------------------------------------------------------------------------
 struct GameView {
-  uint8_t* base;   // chunk base
+  uint8_t* base;   // where the HOT fields start (record offset CATAN_HOT_BEGIN of the chunk; the range ends at CATAN_HOT_END) ...
   int lane;        // game index inside the chunk
+  uint8_t* cold;   // ... and the chunk base, for all the other fields.  One chunk (base == cold + CATAN_HOT_BEGIN * CATAN_W) except in
+                   // the transition kernel, which stages only the hot part of a chunk in shared memory and leaves the rest in place.
+  GameView() = default;
+  CATAN_MFN GameView(uint8_t* chunk, int l) : base(chunk + static_cast<size_t>(CATAN_HOT_BEGIN) * CATAN_W), lane(l), cold(chunk) {}
+  CATAN_MFN GameView(uint8_t* hot, int l, uint8_t* chunk) : base(hot), lane(l), cold(chunk) {}
+  // field at record offset `off` (a compile-time constant at every call site: the choice of the pointer folds away), element k
   template <class T>
   CATAN_MFN T& at(int off, int k) const {
-    return *reinterpret_cast<T*>(base + (static_cast<size_t>(off) + static_cast<size_t>(k) * sizeof(T)) * CATAN_W +
+    const bool h = off >= CATAN_HOT_BEGIN && off < CATAN_HOT_END;
+    return *reinterpret_cast<T*>((h ? base : cold) + (static_cast<size_t>(h ? off - CATAN_HOT_BEGIN : off) + static_cast<size_t>(k) * sizeof(T)) * CATAN_W +
                                  static_cast<size_t>(lane) * sizeof(T));
+  }
+  // raw access by the record offset of the ELEMENT (copies, clears): the pointer is chosen at run time
+  template <class T>
+  CATAN_MFN T& raw(int byte_off) const {
+    const bool h = byte_off >= CATAN_HOT_BEGIN && byte_off < CATAN_HOT_END;
+    return *reinterpret_cast<T*>((h ? base : cold) + static_cast<size_t>(h ? byte_off - CATAN_HOT_BEGIN : byte_off) * CATAN_W + static_cast<size_t>(lane) * sizeof(T));
   }
 #define CATAN_F0(T, name) CATAN_MFN T& name() const { return at<T>(offsetof(GameRec, name), 0); }
 #define CATAN_F1(T, name) CATAN_MFN T& name(int i) const { return at<T>(offsetof(GameRec, name), i); }
@@ -72,10 +85,7 @@ struct GameView {
 
 // view of game `i` of a record array stored as lane-interleaved chunks
 CATAN_FN GameView game_view(uint8_t* recs, size_t i) {
-  GameView g;
-  g.base = recs + (i / CATAN_W) * CATAN_CHUNK_BYTES;
-  g.lane = static_cast<int>(i % CATAN_W);
-  return g;
+  return GameView(recs + (i / CATAN_W) * CATAN_CHUNK_BYTES, static_cast<int>(i % CATAN_W));
 }
 
 // host side: one game between a chunked buffer and a plain GameRec (catan_export_state / catan_import_state)
@@ -84,7 +94,7 @@ static inline void chunk_get(const uint8_t* chunk, int lane, int W, GameRec& out
   // uint16 [396,400), bytes from 400 on
   uint8_t* o = reinterpret_cast<uint8_t*>(&out);
   for (size_t off = 0; off < sizeof(GameRec);) {
-    const size_t sz = off < offsetof(GameRec, rng_ctr) ? 2 : (off < offsetof(GameRec, actions_this_turn) ? 4 : (off < offsetof(GameRec, corner) ? 2 : 1));
+    const size_t sz = off < offsetof(GameRec, rng_ctr) ? 2 : (off < offsetof(GameRec, actions_this_turn) ? 4 : (off < offsetof(GameRec, robber_tile) ? 2 : 1));
     memcpy(o + off, chunk + off * W + static_cast<size_t>(lane) * sz, sz);
     off += sz;
   }
@@ -92,13 +102,13 @@ static inline void chunk_get(const uint8_t* chunk, int lane, int W, GameRec& out
 static inline void chunk_put(uint8_t* chunk, int lane, int W, const GameRec& in) {
   const uint8_t* o = reinterpret_cast<const uint8_t*>(&in);
   for (size_t off = 0; off < sizeof(GameRec);) {
-    const size_t sz = off < offsetof(GameRec, rng_ctr) ? 2 : (off < offsetof(GameRec, actions_this_turn) ? 4 : (off < offsetof(GameRec, corner) ? 2 : 1));
+    const size_t sz = off < offsetof(GameRec, rng_ctr) ? 2 : (off < offsetof(GameRec, actions_this_turn) ? 4 : (off < offsetof(GameRec, robber_tile) ? 2 : 1));
     memcpy(chunk + off * W + static_cast<size_t>(lane) * sz, o + off, sz);
     off += sz;
   }
 }
 static_assert(offsetof(GameRec, est_min) == 0 && offsetof(GameRec, rng_ctr) == 384 && offsetof(GameRec, actions_this_turn) == 396 &&
-              offsetof(GameRec, corner) == 400, "chunk_get/chunk_put assume this field order");
+              offsetof(GameRec, robber_tile) == 400, "chunk_get/chunk_put assume this field order");
 
 // OR over the lanes of a group (host build: one lane)
 #ifdef CATAN_DEVICE
@@ -168,6 +178,13 @@ struct TCx {
   uint64_t seed, env_id;
   Seats s;
 };
+// address-space hints (CATAN_IN_SMEM).  ENCODE: functions that only the encode kernels call -- the whole chunk and both topology
+// tables are staged.  RULES: functions that only the transition kernel calls -- the hot range of the chunk and the topology are
+// staged, the cold fields may be at home in global memory (transition_kernel<DIRECT>).
+#define CATAN_STAGED_ENCODE_G(g_) do { CATAN_IN_SMEM((g_).base); CATAN_IN_SMEM((g_).cold); } while (0)
+#define CATAN_STAGED_ENCODE(cx_) do { CATAN_STAGED_ENCODE_G((cx_).g); CATAN_IN_SMEM((cx_).T); CATAN_IN_SMEM((cx_).X); } while (0)
+#define CATAN_STAGED_RULES_G(g_) CATAN_IN_SMEM((g_).base)
+#define CATAN_STAGED_RULES(cx_) do { CATAN_STAGED_RULES_G((cx_).g); CATAN_IN_SMEM((cx_).T); } while (0)
 
 enum { CATAN_LR_ROAD = 0, CATAN_LR_SETTLE = 1 };
 // what apply_action leaves for the follow-up passes of the same step
@@ -250,7 +267,9 @@ CATAN_FN int t_rng_bounded(TCx& cx, int n) { return static_cast<int>(mulhi32(t_r
 // ------------------------------------------------------------------------------------------------
 // placement predicates for ONE location (corner.py:24-39, edge.py:23-42); the mask encoder uses bit boards instead
 // ------------------------------------------------------------------------------------------------
-CATAN_FN_NOINLINE bool t_can_place_settlement(const GameView& g, const Topo& T, int c, int pid, bool initial) {
+CATAN_FN_NOINLINE bool t_can_place_settlement(const GameView& g_, const Topo& T, int c, int pid, bool initial) {
+  const GameView g = g_;
+  CATAN_STAGED_RULES_G(g); CATAN_IN_SMEM(&T);
   if (g.corner(c)) return false;
   bool own_road = false;
 #pragma unroll
@@ -263,7 +282,9 @@ CATAN_FN_NOINLINE bool t_can_place_settlement(const GameView& g, const Topo& T, 
   return initial || own_road;
 }
 
-CATAN_FN_NOINLINE bool t_can_place_road(const GameView& g, const Topo& T, int e, int pid, bool after_second, int second_corner) {
+CATAN_FN_NOINLINE bool t_can_place_road(const GameView& g_, const Topo& T, int e, int pid, bool after_second, int second_corner) {
+  const GameView g = g_;
+  CATAN_STAGED_RULES_G(g); CATAN_IN_SMEM(&T);
   if (g.edge(e)) return false;
   const int c1 = T.edge_corners[e][0], c2 = T.edge_corners[e][1];
   if (after_second) return c1 == second_corner || c2 == second_corner;
@@ -282,7 +303,10 @@ CATAN_FN_NOINLINE bool t_can_place_road(const GameView& g, const Topo& T, int e,
 // ------------------------------------------------------------------------------------------------
 // translate (wrapper.py:114-166, :414-486) and validate (game.py:264-525)
 // ------------------------------------------------------------------------------------------------
-CATAN_FN_NOINLINE int t_translate_action(const TCx& cx, const int32_t* a, Act& t) {
+CATAN_FN_NOINLINE int t_translate_action(const TCx& cx_, const int32_t* a, Act& t) {
+  TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
+  CATAN_IN_LOCAL(&t);
+  CATAN_STAGED_RULES(cx);
   const GameView& g = cx.g;
   memset(&t, 0, sizeof(Act));
   const int type = a[CATAN_A_TYPE], pg = g.players_go();
@@ -372,7 +396,10 @@ CATAN_FN_NOINLINE int t_translate_action(const TCx& cx, const int32_t* a, Act& t
   }
 }
 
-CATAN_FN_NOINLINE int t_validate_action(const TCx& cx, const Act& t) {
+CATAN_FN_NOINLINE int t_validate_action(const TCx& cx_, const Act& t) {
+  TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
+  CATAN_IN_LOCAL(&t);
+  CATAN_STAGED_RULES(cx);
   const GameView& g = cx.g;
   const Topo& T = *cx.T;
   const int pid = g.players_go(), p = pid - 1;
@@ -494,7 +521,9 @@ CATAN_FN void t_advance_seat(const GameView& g, bool left) {   // game.py:253-26
   g.players_go() = g.player_order(id);
 }
 
-CATAN_FN_NOINLINE void t_update_largest_army(const GameView& g) {   // game.py:817-841
+CATAN_FN_NOINLINE void t_update_largest_army(const GameView& g_) {   // game.py:817-841
+  const GameView g = g_;
+  CATAN_STAGED_RULES_G(g);
   int max_count = 0, cp = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -514,7 +543,10 @@ CATAN_FN_NOINLINE void t_update_largest_army(const GameView& g) {   // game.py:8
   }
 }
 
-CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx, StepTmp& tmp, const Act& t) {
+CATAN_FN_NOINLINE void t_apply_scalar(TCx& cx_, StepTmp& tmp, const Act& t) {
+  TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
+  CATAN_IN_LOCAL(&t); CATAN_IN_SMEM(&tmp);
+  CATAN_STAGED_RULES(cx);
   const GameView& g = cx.g;
   const Topo& T = *cx.T;
   const int pid = g.players_go(), p = pid - 1;
@@ -894,7 +926,10 @@ CATAN_FN void t_est_special_group(const GameView& g, Seats s, const StepTmp& tmp
   }
 }
 
-CATAN_FN_NOINLINE void t_followups_group(const GameView& g, const Topo& T, StepTmp& tmp, int lane, int nl) {
+CATAN_FN_NOINLINE void t_followups_group(const GameView& g_, const Topo& T, StepTmp& tmp, int lane, int nl) {
+  const GameView g = g_;
+  CATAN_IN_SMEM(&tmp);
+  CATAN_STAGED_RULES_G(g); CATAN_IN_SMEM(&T);
   const int special = tmp.dice_roll ? EST_SPECIAL_DICE : tmp.est_special;   // (nobody writes tmp's flags here: the lanes only read them)
   if (tmp.dice_roll) t_dice_payout_group(g, T, tmp, lane, nl);
   for (int qi = 0; qi < tmp.n_est; ++qi) {
@@ -1178,8 +1213,10 @@ CATAN_FN uint64_t t_road_nb(const Topo& T, const RoadBits& R, int x) {
 }
 // pre (may be null): the player's RoadBits, when the caller has already gathered them (the transition kernel does, one
 // lane per corner / edge); und (may be null): likewise the table of t_road_nb() for all 54 corners
-CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int kind, int loc, int placer, const RoadBits* pre = nullptr,
+CATAN_FN_NOINLINE int t_lr_fast(const GameView& g_, const Topo& T, int pid, int kind, int loc, int placer, const RoadBits* pre = nullptr,
                                 const uint64_t* und = nullptr) {
+  const GameView g = g_;
+  CATAN_STAGED_RULES_G(g); CATAN_IN_SMEM(&T);
   const int holder = g.lr_holder();
   const int old = holder == pid ? g.lr_count() : (g.has_path_key(pid - 1) ? g.cur_longest_path(pid - 1) : 0);
   if (kind == CATAN_LR_SETTLE) {                                     // pid == holder (game.py:552-553): its length is always current
@@ -1245,7 +1282,10 @@ CATAN_FN_NOINLINE int t_lr_fast(const GameView& g, const Topo& T, int pid, int k
 // done / reward / info (wrapper.py:85-112).  Returns true when the game ended and must be reset (cfg.auto_reset); the
 // reset itself is done by reset_game_group(), which then patches the two info bytes that describe the new game.
 // ------------------------------------------------------------------------------------------------
-CATAN_FN_NOINLINE bool t_step_finish(TCx& cx, const StepTmp& tmp, float* reward_out, uint8_t* info_out) {
+CATAN_FN_NOINLINE bool t_step_finish(TCx& cx_, const StepTmp& tmp, float* reward_out, uint8_t* info_out) {
+  TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
+  CATAN_IN_LOCAL(&tmp);
+  CATAN_STAGED_ENCODE(cx);
   const GameView& g = cx.g;
   struct alignas(16) V16 { uint32_t w[4]; };
   struct alignas(16) F4 { float v[4]; };
@@ -1345,9 +1385,9 @@ CATAN_FN_NOINLINE void reset_game_group(const GameView& g, const Topo& T, uint64
   CATAN_RESET_T0();
   CATAN_GROUP_SYNC();
   // clear the record field-size wise (16- and 32-bit fields interleave in units of their own size); the two stream counters survive
-  for (int k = lane; k < static_cast<int>(offsetof(GameRec, rng_ctr) / 2); k += nl) g.at<int16_t>(0, k) = 0;
+  for (int k = lane; k < static_cast<int>(offsetof(GameRec, rng_ctr) / 2); k += nl) g.raw<int16_t>(2 * k) = 0;
   if (lane == 0) { g.episode_steps() = 0; g.actions_this_turn() = 0; g.turn() = 0; }
-  for (int k = static_cast<int>(offsetof(GameRec, corner)) + lane; k < static_cast<int>(sizeof(GameRec)); k += nl) g.at<uint8_t>(k, 0) = 0;
+  for (int k = static_cast<int>(offsetof(GameRec, robber_tile)) + lane; k < static_cast<int>(sizeof(GameRec)); k += nl) g.raw<uint8_t>(k) = 0;
   const uint32_t d_base = rng & ~3u;
   for (int b = lane; b < CATAN_RESET_WORDS / 4; b += nl)
     philox4x32((d_base >> 2) + b, CATAN_STREAM_GAME, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32),
@@ -1461,7 +1501,9 @@ struct Scan {
   uint32_t road_hi, e_any_hi;   // edges 64..71
   uint32_t tile_bld;         // tiles with any building on a corner (wrapper.py:308-320, Q1)
 };
-CATAN_FN_NOINLINE Scan t_scan_group(const GameView& g, const Topo& T, const TopoX& X, int pid, int lane, int nl, bool solo = false) {
+CATAN_FN_NOINLINE Scan t_scan_group(const GameView& g_, const Topo& T, const TopoX& X, int pid, int lane, int nl, bool solo = false) {
+  const GameView g = g_;
+  CATAN_STAGED_ENCODE_G(g); CATAN_IN_SMEM(&T); CATAN_IN_SMEM(&X);
   uint64_t bld = 0, mine = 0, ms = 0;
   for (int c = lane; c < 54; c += nl) {
     const uint32_t b = g.corner(c);
@@ -1531,7 +1573,10 @@ CATAN_FN void t_mask_play_dev(const GameView& g, int p, MaskBits& m) {   // wrap
 // The masks of one game in two halves around the placement scan: t_masks_pre() handles the phases that need no board
 // scan and returns true when t_scan_group() must run for this game (PlayerId = players_go) before t_masks_post().
 struct MaskPlan { uint8_t post, initial, rb, capped, init_settle, want_settle, want_city, want_road, want_tiles; };   // post: t_masks_post() must run
-CATAN_FN_NOINLINE bool t_masks_pre(const TCx& cx, MaskBits& m, MaskPlan& pl) {
+CATAN_FN_NOINLINE bool t_masks_pre(const TCx& cx_, MaskBits& m, MaskPlan& pl) {
+  TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
+  CATAN_IN_LOCAL(&m); CATAN_IN_LOCAL(&pl);
+  CATAN_STAGED_ENCODE(cx);
   const GameView& g = cx.g;
   const Topo& T = *cx.T;
   m.type = 0; m.settle = CATAN_ALL54; m.city = CATAN_ALL54; m.edge_lo = ~0ull; m.edge_hi = 0x1ffu; m.tile = (1u << 19) - 1u;
@@ -1593,7 +1638,10 @@ CATAN_FN_NOINLINE bool t_masks_pre(const TCx& cx, MaskBits& m, MaskPlan& pl) {
   return want_settle || want_city || want_road || want_tiles;
 }
 
-CATAN_FN_NOINLINE void t_masks_post(const TCx& cx, MaskBits& m, const MaskPlan& pl, const Scan& sc) {
+CATAN_FN_NOINLINE void t_masks_post(const TCx& cx_, MaskBits& m, const MaskPlan& pl, const Scan& sc) {
+  TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
+  CATAN_IN_LOCAL(&m); CATAN_IN_LOCAL(&pl); CATAN_IN_SMEM(&sc);
+  CATAN_STAGED_ENCODE(cx);
   const GameView& g = cx.g;
   const int pid = g.players_go(), p = pid - 1;
   const bool initial = pl.initial, rb = pl.rb;
@@ -1737,6 +1785,7 @@ CATAN_FN int pick64(uint64_t m, uint32_t w) { return pick96(static_cast<uint32_t
 
 // hand_bits: bit r set iff the acting player holds resource r (== obs current_resources[1..5] != 0, wrapper.py:70-71)
 CATAN_FN_NOINLINE void t_sample_action(const MaskBits& m, uint32_t hand_bits, uint64_t seed, uint64_t env_id, uint32_t decision, int32_t* out) {
+  CATAN_IN_LOCAL(&m);
   uint32_t w[4];
   philox4x32(decision, CATAN_STREAM_SAMPLER, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32),
              static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), w);
@@ -1971,7 +2020,9 @@ CATAN_FN uint64_t t_tile_bits(const GameView& g, const Topo& T, int t, int robbe
   return static_cast<uint64_t>(w0) | (static_cast<uint64_t>(w1) << 32);
 }
 
-CATAN_FN_NOINLINE void t_encode_obs_tiles(const TCx& cx, uint8_t* row, int lo, int hi) {
+CATAN_FN_NOINLINE void t_encode_obs_tiles(const TCx& cx_, uint8_t* row, int lo, int hi) {
+  TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
+  CATAN_STAGED_ENCODE(cx);
   const GameView& g = cx.g;
   const Topo& T = *cx.T;
   const int actor = t_current_actor(g), ap = actor - 1, aseat = seat_of(cx.s, actor), robber = g.robber_tile();

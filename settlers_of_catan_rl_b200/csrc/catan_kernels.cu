@@ -125,10 +125,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar) {           // by one t
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 // by one thread: start the copy of a chunk into shared memory; everybody then waits with chunk_wait(bar, phase)
-__device__ __forceinline__ void chunk_to_shared(uint8_t* dst, const uint8_t* chunk, uint64_t* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(static_cast<uint32_t>(CATAN_CHUNK_BYTES)) : "memory");
+__device__ __forceinline__ void bulk_to_shared(uint8_t* dst, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(chunk), "r"(static_cast<uint32_t>(CATAN_CHUNK_BYTES)), "r"(smem_u32(bar)) : "memory");
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void chunk_to_shared(uint8_t* dst, const uint8_t* chunk, uint64_t* bar) {
+  bulk_to_shared(dst, chunk, static_cast<uint32_t>(CATAN_CHUNK_BYTES), bar);
 }
 __device__ __forceinline__ void chunk_wait(uint64_t* bar, uint32_t phase) {
   uint32_t ok;
@@ -139,32 +142,32 @@ __device__ __forceinline__ void chunk_wait(uint64_t* bar, uint32_t phase) {
 }
 // every thread that wrote to the staged chunk: chunk_written(), then a block barrier; then ONE thread: chunk_to_global()
 __device__ __forceinline__ void chunk_written() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void chunk_to_global(uint8_t* chunk, const uint8_t* src) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               :: "l"(chunk), "r"(smem_u32(src)), "r"(static_cast<uint32_t>(CATAN_CHUNK_BYTES)) : "memory");
+__device__ __forceinline__ void bulk_to_global(uint8_t* dst, const uint8_t* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the block may exit (and its shared memory go) after this
 }
+__device__ __forceinline__ void chunk_to_global(uint8_t* chunk, const uint8_t* src) { bulk_to_global(chunk, src, static_cast<uint32_t>(CATAN_CHUNK_BYTES)); }
 
 // The games that need a search are scattered over the chunks: every field access of a warp that works on 32 of them
 // would touch 32 sectors.  The transition therefore copies them (one warp per game) into staging chunks in queue order;
 // they are searched and encoded there with the ordinary coalesced code and copied back.
 __device__ __forceinline__ void copy_game(const GameView& src, const GameView& dst, int lane) {
-  constexpr int n16 = static_cast<int>(offsetof(GameRec, rng_ctr) / 2), b0 = static_cast<int>(offsetof(GameRec, corner)), nb = static_cast<int>(sizeof(GameRec)) - b0;
+  constexpr int n16 = static_cast<int>(offsetof(GameRec, rng_ctr) / 2), b0 = static_cast<int>(offsetof(GameRec, robber_tile)), nb = static_cast<int>(sizeof(GameRec)) - b0;
   int16_t h[(n16 + 31) / 32];
   uint8_t c[(nb + 31) / 32];
 #pragma unroll
-  for (int q = 0; q < (n16 + 31) / 32; ++q) if (lane + 32 * q < n16) h[q] = src.at<int16_t>(0, lane + 32 * q);    // all loads first
+  for (int q = 0; q < (n16 + 31) / 32; ++q) if (lane + 32 * q < n16) h[q] = src.raw<int16_t>(2 * (lane + 32 * q));    // all loads first
 #pragma unroll
-  for (int q = 0; q < (nb + 31) / 32; ++q) if (lane + 32 * q < nb) c[q] = src.at<uint8_t>(b0 + lane + 32 * q, 0);
-  const uint32_t w = lane < 3 ? src.at<uint32_t>(offsetof(GameRec, rng_ctr), lane) : 0u;
-  const uint16_t v = lane < 2 ? src.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane) : 0;
+  for (int q = 0; q < (nb + 31) / 32; ++q) if (lane + 32 * q < nb) c[q] = src.raw<uint8_t>(b0 + lane + 32 * q);
+  const uint32_t w = lane < 3 ? src.raw<uint32_t>(static_cast<int>(offsetof(GameRec, rng_ctr)) + 4 * lane) : 0u;
+  const uint16_t v = lane < 2 ? src.raw<uint16_t>(static_cast<int>(offsetof(GameRec, actions_this_turn)) + 2 * lane) : 0;
 #pragma unroll
-  for (int q = 0; q < (n16 + 31) / 32; ++q) if (lane + 32 * q < n16) dst.at<int16_t>(0, lane + 32 * q) = h[q];
+  for (int q = 0; q < (n16 + 31) / 32; ++q) if (lane + 32 * q < n16) dst.raw<int16_t>(2 * (lane + 32 * q)) = h[q];
 #pragma unroll
-  for (int q = 0; q < (nb + 31) / 32; ++q) if (lane + 32 * q < nb) dst.at<uint8_t>(b0 + lane + 32 * q, 0) = c[q];
-  if (lane < 3) dst.at<uint32_t>(offsetof(GameRec, rng_ctr), lane) = w;
-  if (lane < 2) dst.at<uint16_t>(offsetof(GameRec, actions_this_turn), lane) = v;
+  for (int q = 0; q < (nb + 31) / 32; ++q) if (lane + 32 * q < nb) dst.raw<uint8_t>(b0 + lane + 32 * q) = c[q];
+  if (lane < 3) dst.raw<uint32_t>(static_cast<int>(offsetof(GameRec, rng_ctr)) + 4 * lane) = w;
+  if (lane < 2) dst.raw<uint16_t>(static_cast<int>(offsetof(GameRec, actions_this_turn)) + 2 * lane) = v;
 }
 __global__ void __launch_bounds__(kCopyThreads) lr_copy_back_kernel(const __grid_constant__ EnvParams P) {
   const int count = *P.list_count;
@@ -177,8 +180,10 @@ __global__ void __launch_bounds__(kCopyThreads) lr_copy_back_kernel(const __grid
 // One block per chunk of 32 games.  Warp 0 runs the scalar part of apply_action, one game per lane; the data-parallel
 // follow-ups it posts (dice payout over 19 tiles x 6 corners, belief updates over 60 entries) are then executed by all
 // warps of the block, one warp per game and one lane per item.
-struct alignas(128) TransSmem {      // <= 31.4 KB so that 7 blocks fit an SM: 2048 chunks are then two waves instead of three
-  uint8_t chunk[CATAN_CHUNK_BYTES];
+constexpr uint32_t kHotBytes = (CATAN_HOT_END - CATAN_HOT_BEGIN) * 32;     // 5 920 of the 26 624 bytes of a chunk
+template <bool DIRECT>
+struct alignas(128) TransSmem {
+  uint8_t chunk[DIRECT ? ((kHotBytes + 127) / 128) * 128 : CATAN_CHUNK_BYTES];   // DIRECT: only the hot range of the chunk is staged
   uint64_t mbar;
   alignas(16) Topo topo;
   StepTmp tmp[32];
@@ -189,13 +194,30 @@ struct alignas(128) TransSmem {      // <= 31.4 KB so that 7 blocks fit an SM: 2
   uint8_t follow_list[32];
 };
 
-__global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_constant__ EnvParams P) {
-  __shared__ TransSmem S;
+// DIRECT = false stages the whole chunk in shared memory (TMA in, TMA out).  DIRECT = true stages only its HOT range (GameRec: flags,
+// hands, bank, points, counters -- 185 of the 832 bytes of a record, what the rules of every action read and write) and touches the
+// rest (board, beliefs, card lists) in place through L1 / L2: the rules use a small, data-dependent part of those, and with 11 KB
+// instead of 32 KB of shared memory per block twice as many chunks are in flight per SM.
+#ifndef CATAN_TRANS_DIRECT_BLOCKS
+#define CATAN_TRANS_DIRECT_BLOCKS 16
+#endif
+template <bool DIRECT>
+__global__ void __launch_bounds__(kTransThreads, DIRECT ? CATAN_TRANS_DIRECT_BLOCKS : 7) transition_kernel(const __grid_constant__ EnvParams P) {
+  __shared__ TransSmem<DIRECT> S;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   CATAN_MARK_BEGIN();
   const int base = (P.range_first & ~31) + static_cast<int>(blockIdx.x) * 32;
   uint8_t* const home = P.recs + static_cast<size_t>(base >> 5) * CATAN_CHUNK_BYTES;
-  if (tid == 0) { mbar_init(&S.mbar); chunk_to_shared(S.chunk, home, &S.mbar); S.n_follow = 0; }   // in flight while the topology is staged
+  // view of game b of this chunk: hot fields in the staged copy, the others in the staged copy too (whole chunk) or at home (DIRECT)
+  uint8_t* const hot = DIRECT ? S.chunk : S.chunk + static_cast<size_t>(CATAN_HOT_BEGIN) * 32;
+  uint8_t* const coldp = DIRECT ? home : S.chunk;
+#define CATAN_TVIEW(b_) GameView(hot, (b_), coldp)
+  if (tid == 0) {                                                    // in flight while the topology is staged
+    mbar_init(&S.mbar);
+    if (DIRECT) bulk_to_shared(S.chunk, home + static_cast<size_t>(CATAN_HOT_BEGIN) * 32, kHotBytes, &S.mbar);
+    else chunk_to_shared(S.chunk, home, &S.mbar);
+    S.n_follow = 0;
+  }
   {
     const int4* src = reinterpret_cast<const int4*>(&d_topo);
     int4* dst = reinterpret_cast<int4*>(&S.topo);
@@ -234,7 +256,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   const int gl = mine ? S.order[warp][slot8] : 0;                    // game of this thread inside the chunk
   const int i = base + gl;
   TCx cx;
-  cx.g.base = S.chunk; cx.g.lane = gl;
+  cx.g = CATAN_TVIEW(gl);
   cx.T = &S.topo; cx.X = nullptr; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);   // (X: masks only)
   {
     bool follow = false;
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   __syncthreads();
   if (warp == 0) {
     // (game = lane from here on)
-    cx.g.lane = lane;
+    cx.g = CATAN_TVIEW(lane);
     const int i = base + lane;
     const bool lr = live && !S.tmp[lane].err && S.tmp[lane].lr_pid;
     // longest road (game.py:843-919), one thread per update: the incremental rule settles ~93 % of them on the spot; a
@@ -275,7 +297,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
         const int b = __ffs(static_cast<int>(mm)) - 1;
         mm &= mm - 1;
         const uint32_t pid = __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp.lr_pid), b);
-        const GameView gb = GameView{S.chunk, b};
+        const GameView gb = CATAN_TVIEW(b);
         const uint32_t c0 = gb.corner(lane), c1 = lane + 32 < 54 ? gb.corner(lane + 32) : 0u;
         const uint32_t k0 = __ballot_sync(0xffffffffu, c0 != 0 && (c0 >> 2) != pid), k1 = __ballot_sync(0xffffffffu, c1 != 0 && (c1 >> 2) != pid);
         const uint32_t e0 = __ballot_sync(0xffffffffu, gb.edge(lane) == pid), e1 = __ballot_sync(0xffffffffu, gb.edge(lane + 32) == pid);
@@ -319,8 +341,7 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   } else {
     const int nf = S.n_follow;
     for (int j = warp - 1; j < nf; j += kTransWarps - 1) {
-      GameView g;
-      g.base = S.chunk; g.lane = S.follow_list[j];
+      const GameView g = CATAN_TVIEW(S.follow_list[j]);
       t_followups_group(g, S.topo, S.tmp[g.lane], lane, 32);
     }
     CATAN_MARK(3);
@@ -329,10 +350,14 @@ __global__ void __launch_bounds__(kTransThreads) transition_kernel(const __grid_
   __syncthreads();
   for (int b = warp; b < 32; b += kTransWarps) {                     // games that wait for a search: also into their staging slot
     const int slot = S.slot[b];
-    if (slot >= 0) copy_game(GameView{S.chunk, b}, game_view(P.stage, static_cast<size_t>(slot)), lane);
-    else if (slot <= -2) copy_game(GameView{S.chunk, b}, game_view(P.stage_rs, static_cast<size_t>(-2 - slot)), lane);
+    if (slot >= 0) copy_game(CATAN_TVIEW(b), game_view(P.stage, static_cast<size_t>(slot)), lane);
+    else if (slot <= -2) copy_game(CATAN_TVIEW(b), game_view(P.stage_rs, static_cast<size_t>(-2 - slot)), lane);
   }
-  if (tid == 0) chunk_to_global(home, S.chunk);                      // (frozen games go back unchanged)
+  if (tid == 0) {                                                    // (frozen games go back unchanged)
+    if (DIRECT) bulk_to_global(home + static_cast<size_t>(CATAN_HOT_BEGIN) * 32, S.chunk, kHotBytes);
+    else chunk_to_global(home, S.chunk);
+  }
+#undef CATAN_TVIEW
   if (warp == 0) CATAN_MARK(4);
 }
 
@@ -445,13 +470,24 @@ struct alignas(128) EncSmem {
   uint8_t chunk[CATAN_CHUNK_BYTES];                                 // the 32 games of this block (see chunk_to_shared)
   uint64_t mbar;
   GameSmem topo;
-  uint32_t wbuf[CATAN_RESET_WORDS];                                 // reset: pre-drawn Philox words (warp 0)
-  alignas(4) uint8_t arr[128];                                       // reset: scratch (warp 0)
-  Scan scan[32];                                                    // board scan of game b (valid where scan_need has bit b)
   uint32_t scan_need, reset_need;
   int32_t scan_pid_done;                                            // (profiling build: warps that finished)
+  // ---- a ROLE_ROWS block needs nothing below
+  Scan scan[32];                                                    // board scan of game b (valid where scan_need has bit b)
   uint8_t scan_pid[32];
+  // ---- a ROLE_MASKS block of a step (no resets on the main path) needs nothing below
+  uint32_t wbuf[CATAN_RESET_WORDS];                                 // reset: pre-drawn Philox words (warp 0)
+  alignas(4) uint8_t arr[128];                                       // reset: scratch (warp 0)
 };
+// A step's main encode is TWO launches of 4-warp blocks, because both halves are instruction-fetch bound (no_inst was the first or
+// second stall reason of the active warps, profiles/r2_notes.md: the code of a block runs once per chunk, with little reuse) and
+// neither waits for the other: ROLE_ROWS writes the observation rows, ROLE_MASKS does done / reward / info, masks and sampler.
+// Each then has half the code, half the registers per block and 7 blocks per SM.  Every other launch (reset, refresh, the two
+// queues) is ROLE_BOTH: 8 warps with block-wide barriers.
+enum { ROLE_BOTH = 0, ROLE_MASKS = 1, ROLE_ROWS = 2 };
+constexpr size_t enc_smem_bytes(int role) {
+  return role == ROLE_ROWS ? offsetof(EncSmem, scan) : role == ROLE_MASKS ? offsetof(EncSmem, wbuf) : sizeof(EncSmem);
+}
 
 // LISTED = false: block b takes chunk b of the env range; in a step, games whose longest-road update is still pending
 // (side bit 31) are left out.  LISTED = true: those games, 32 per block iteration in queue order, on their staging
@@ -459,8 +495,11 @@ struct alignas(128) EncSmem {
 #ifndef CATAN_ENC_MIN_BLOCKS
 #define CATAN_ENC_MIN_BLOCKS 4   // (5 blocks per SM at 48 registers measured 2 % slower than 4 at 56)
 #endif
-template <int MODE, bool SAMPLE, bool LISTED>
-__global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kernel(const __grid_constant__ EnvParams P) {
+template <int MODE, bool SAMPLE, bool LISTED, int ROLE>
+__global__ void __launch_bounds__(ROLE == ROLE_BOTH ? kEncThreads : kEncThreads / 2, ROLE == ROLE_BOTH ? CATAN_ENC_MIN_BLOCKS : 7)
+encode_kernel(const __grid_constant__ EnvParams P) {
+  static_assert(ROLE == ROLE_BOTH || (MODE == MODE_STEP && !LISTED), "the split roles are for the main path of a step");
+  constexpr int kThreads = ROLE == ROLE_BOTH ? kEncThreads : kEncThreads / 2, kWarps = kThreads / 32;
   extern __shared__ __align__(128) uint8_t enc_smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(enc_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -474,7 +513,7 @@ __global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kern
     mbar_init(&S.mbar);
     chunk_to_shared(S.chunk, CATAN_ENC_HOME((static_cast<int>(blockIdx.x) * G) & ~31), &S.mbar);
   }
-  stage_topology(S.topo, tid, kEncThreads);
+  stage_topology(S.topo, tid, kThreads);
   uint32_t phase = 0;
   for (int w0 = static_cast<int>(blockIdx.x) * G; LISTED ? w0 < list_count : w0 == static_cast<int>(blockIdx.x) * G; w0 += static_cast<int>(gridDim.x) * G) {
     const int l0 = w0 & ~31;                                         // first queue slot / game of the chunk
@@ -506,14 +545,14 @@ __global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kern
     // observation reads is changed by done / reward: the row warps then start at once and the mask warps synchronise among
     // themselves (named barrier 1).  Every other launch (reset, refresh, the two queues) keeps the block-wide barriers.
     constexpr bool kDecoupled = MODE == MODE_STEP && !LISTED;
-    const bool mask_warp = warp < kMaskWarps;
+    const bool mask_warp = ROLE == ROLE_MASKS || (ROLE == ROLE_BOTH && warp < kMaskWarps);
     const int mq = warp;                                             // index among the mask warps
     const int gm = lane * kMaskWarps + mq;                           // game of this thread in its mask role
     const bool m_lane = mask_warp && gm < 32;
     const int im = __shfl_sync(0xffffffffu, i, gm & 31);
     const bool vm = __shfl_sync(0xffffffffu, static_cast<int>(valid), gm & 31) != 0 && m_lane;
-#define CATAN_MASK_SYNC() do { if (kDecoupled) asm volatile("bar.sync 1, %0;" :: "n"(kMaskWarps * 32) : "memory"); else __syncthreads(); } while (0)
-    if (mask_warp || !kDecoupled) {
+#define CATAN_MASK_SYNC() do { if (kDecoupled && ROLE == ROLE_BOTH) asm volatile("bar.sync 1, %0;" :: "n"(kMaskWarps * 32) : "memory"); else __syncthreads(); } while (0)
+    if (ROLE != ROLE_ROWS && (mask_warp || !kDecoupled)) {
       TCx mx;                                                        // context of the mask role
       mx.g = CATAN_VIEW_OF(gm & 31);
       mx.T = &S.topo.topo; mx.X = &S.topo.topox; mx.cfg = &P.cfg; mx.seed = P.seed; mx.env_id = P.first_env_id + static_cast<uint64_t>(im);
@@ -586,7 +625,7 @@ __global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kern
           for (int k = 0; nb; ++k) {
             const int b = __ffs(static_cast<int>(nb)) - 1;
             nb &= nb - 1;
-            if (k % (kDecoupled ? kMaskWarps : kEncWarps) != warp) continue;
+            if (k % (kDecoupled ? kMaskWarps : kWarps) != warp) continue;
             const Scan r = t_scan_group(CATAN_VIEW_OF(b), S.topo.topo, S.topo.topox, S.scan_pid[b], lane, 32);
             if (lane == 0) S.scan[b] = r;
           }
@@ -618,7 +657,7 @@ __global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kern
           for (int k = 0; nb; ++k) {
             const int b = __ffs(static_cast<int>(nb)) - 1;
             nb &= nb - 1;
-            if (k % kEncWarps != warp) continue;
+            if (k % kWarps != warp) continue;
             const Scan r = t_scan_group(CATAN_VIEW_OF(b), S.topo.topo, S.topo.topox, S.scan_pid[b], lane, 32);
             if (lane == 0) S.scan[b] = r;
           }
@@ -626,13 +665,13 @@ __global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kern
         __syncthreads();
       }
     }
-    if (!mask_warp) {
+    if (ROLE != ROLE_MASKS && !mask_warp) {
       TCx cx;
       cx.g = CATAN_VIEW_OF(lane);
       cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
       if (valid) {
         cx.s = load_seats(cx.g);
-        const int r = warp - kMaskWarps;                             // tile part r, then player part r (the last row warp: the lists too)
+        const int r = ROLE == ROLE_ROWS ? warp : warp - kMaskWarps;  // tile part r, then player part r (the last row warp: the lists too)
         uint8_t* row = P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE;
         t_encode_obs_part(cx, row, r);
         if (!LISTED) CATAN_MARK(13);
@@ -646,7 +685,7 @@ __global__ void __launch_bounds__(kEncThreads, CATAN_ENC_MIN_BLOCKS) encode_kern
     if (!LISTED) {                                                   // the last warp of the block to get here: the block's duration
       __syncwarp();
       int last = 0;
-      if (lane == 0) last = atomicAdd(&S.scan_pid_done, 1) == kEncWarps - 1;
+      if (lane == 0) last = atomicAdd(&S.scan_pid_done, 1) == kWarps - 1;
       if (last) { CATAN_MARK(15); const unsigned long long d = static_cast<unsigned long long>(clock64() - t_block0); atomicMax(&d_phase[40], d);
                   atomicAdd(&d_phase[42 + (d < 30000 ? 0 : d < 60000 ? 1 : d < 90000 ? 2 : d < 120000 ? 3 : d < 200000 ? 4 : 5)], 1ull);
                   if (S.reset_need) atomicAdd(&d_phase[41], 1ull); }
@@ -734,6 +773,7 @@ struct catan_env {
   // catan_set_timing: CUDA events around the two kernels on the caller's stream, a ring of kTimedSteps steps
   // catan_set_graphs: every distinct step call (entry point + buffer pointers) is captured once into a CUDA graph on an internal
   // stream and replayed on the caller's stream afterwards: one driver call per step instead of ~20 (9 launches, 6 event calls, copies)
+  bool trans_direct = true;           // transition_kernel<DIRECT> (see there)
   bool use_graphs = false;
   cudaStream_t capture_stream = nullptr;
   struct StepGraph { int kind; const void* p[4]; cudaGraphExec_t exec; };
@@ -791,8 +831,15 @@ template <int MODE, bool SAMPLE>
 static int launch_encode(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
   P.range_first = first; P.range_count = count;
   if (count <= 0) return 0;
-  CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<MODE, SAMPLE, false>, game_blocks(first, count), catanb::kEncThreads,
-                                       sizeof(catanb::EncSmem), stream, P));
+  if constexpr (MODE == catanb::MODE_STEP) {                         // rows, then masks + sampler: two launches of 4-warp blocks
+    CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, false, catanb::ROLE_ROWS>, game_blocks(first, count),
+                                         catanb::kEncThreads / 2, catanb::enc_smem_bytes(catanb::ROLE_ROWS), stream, P));
+    CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, false, catanb::ROLE_MASKS>, game_blocks(first, count),
+                                         catanb::kEncThreads / 2, catanb::enc_smem_bytes(catanb::ROLE_MASKS), stream, P));
+  } else {
+    CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<MODE, false, false, catanb::ROLE_BOTH>,
+                                         game_blocks(first, count), catanb::kEncThreads, sizeof(catanb::EncSmem), stream, P));
+  }
   return 0;
 }
 
@@ -819,7 +866,8 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
     env->timed += 1;
     CATAN_CUDA(cudaEventRecord(tev[0], stream));
   }
-  CATAN_CUDA(launch_with_record_window(env, catanb::transition_kernel, game_blocks(0, env->n), catanb::kTransThreads, 0, stream, P));
+  if (env->trans_direct) CATAN_CUDA(launch_with_record_window(env, catanb::transition_kernel<true>, game_blocks(0, env->n), catanb::kTransThreads, 0, stream, P));
+  else CATAN_CUDA(launch_with_record_window(env, catanb::transition_kernel<false>, game_blocks(0, env->n), catanb::kTransThreads, 0, stream, P));
   if (tev) CATAN_CUDA(cudaEventRecord(tev[1], stream));
   CATAN_CUDA(cudaEventRecord(env->ev_fork, stream));
   CATAN_CUDA(cudaStreamWaitEvent(env->lr_stream, env->ev_fork, 0));
@@ -829,7 +877,7 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
     L.list_queue = env->lr_slow_queue; L.list_stage = env->stage; L.list_count = &env->lr_ctl->slow_count; L.list_group = 8;
     catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), env->lr_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
-    catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count, catanb::kEncThreads, sizeof(catanb::EncSmem), env->lr_stream>>>(L);
+    catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true, catanb::ROLE_BOTH><<<env->sm_count, catanb::kEncThreads, sizeof(catanb::EncSmem), env->lr_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
     catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->lr_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
@@ -840,7 +888,7 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   {   // the games that ended: done / reward -> reset -> encode of the new game, ONE game per block (the reset is serial)
     EnvParams L = P;
     L.list_queue = env->rs_queue; L.list_stage = env->stage_rs; L.list_count = &env->lr_ctl->rs_count; L.list_group = 1;
-    catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true><<<env->sm_count * 2, catanb::kEncThreads, sizeof(catanb::EncSmem), env->rs_stream>>>(L);
+    catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true, catanb::ROLE_BOTH><<<env->sm_count * 2, catanb::kEncThreads, sizeof(catanb::EncSmem), env->rs_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
     catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->rs_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
@@ -986,17 +1034,22 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join_rs, cudaEventDisableTiming);
   {
     const int enc_bytes = static_cast<int>(sizeof(catanb::EncSmem));   // > 48 KB: opt in, per instantiation
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_RESET, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_REFRESH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_bytes);
-    // (more than four blocks per SM only fit with the largest shared-memory carve-out)
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::encode_kernel<catanb::MODE_STEP, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    using namespace catanb;
+#define CATAN_ENC_ATTR(K_, BYTES_)                                                                                         \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(BYTES_)); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, false, false, ROLE_ROWS>), enc_smem_bytes(ROLE_ROWS))
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, true, false, ROLE_ROWS>), enc_smem_bytes(ROLE_ROWS))
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, false, false, ROLE_MASKS>), enc_smem_bytes(ROLE_MASKS))
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, true, false, ROLE_MASKS>), enc_smem_bytes(ROLE_MASKS))
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, false, true, ROLE_BOTH>), enc_bytes)
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, true, true, ROLE_BOTH>), enc_bytes)
+    CATAN_ENC_ATTR((encode_kernel<MODE_RESET, false, false, ROLE_BOTH>), enc_bytes)
+    CATAN_ENC_ATTR((encode_kernel<MODE_REFRESH, false, false, ROLE_BOTH>), enc_bytes)
+#undef CATAN_ENC_ATTR
   }
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::transition_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::transition_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  env->trans_direct = !(getenv("CATAN_TRANS_DIRECT") != nullptr && atoi(getenv("CATAN_TRANS_DIRECT")) == 0);   // (0: stage whole chunks)
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::lr_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::LrSmem)));
   if (e != cudaSuccess) {
     free_env(env);

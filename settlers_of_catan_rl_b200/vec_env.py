@@ -17,9 +17,9 @@ import torch
 from . import _lib, layout as L
 
 
-#: launches of one step: transition, encode (caller's stream) | longest-road search, encode of the searched games, copy-back, counter
+#: launches of one step: transition, encode of the rows, encode of the masks + sampler (caller's stream) | longest-road search, encode of the searched games, copy-back, counter
 #: bookkeeping (library stream 1) | encode of the games that ended and were reset, copy-back, counter bookkeeping (library stream 2)
-LAUNCHES_PER_STEP = 9
+LAUNCHES_PER_STEP = 10
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:

@@ -26,7 +26,7 @@ struct EmuEnv {
 static TCx make_ctx(EmuEnv* e) {
   if (!h_topox_ready) { build_topox(h_topo, h_topox, 0, 1); h_topox_ready = true; }
   TCx cx;
-  cx.g.base = reinterpret_cast<uint8_t*>(&e->g); cx.g.lane = 0;
+  cx.g = GameView(reinterpret_cast<uint8_t*>(&e->g), 0);
   cx.T = &h_topo; cx.X = &h_topox; cx.cfg = &e->cfg; cx.seed = e->seed; cx.env_id = e->env_id;
   cx.s = load_seats(cx.g);
   return cx;
