@@ -37,6 +37,8 @@ ALGO_BYTES_PER_ENV_STEP = 3552
 # and writes the obs row, the mask row and the next action row
 TRANSITION_BYTES_PER_ENV_STEP = 80 + 640 + 640
 ENCODE_BYTES_PER_ENV_STEP = 640 + 1867 + 325 + 80
+ROWS_BYTES_PER_ENV_STEP = 640 + 1867            # the observation-rows launch: record in, obs row out
+MASKS_BYTES_PER_ENV_STEP = 640 + 325 + 80         # the masks + sampler launch: record in, mask row + next action out
 WORKLOAD = "65536 parallel envs per GPU, random-legal policy, fused step+auto-reset+masks+obs+sample (BASELINE configs[1])"
 
 
@@ -219,60 +221,41 @@ def run_reference_arm(args):
 # this build
 # ------------------------------------------------------------------------------------------------
 def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_groups=2, barrier=None, fused_sampler=True, graphs=True):
+    """The games split over n_groups handles kept in flight from the host (HostEnvGroups: own stream and pinned buffers each).  One
+    library call per round (catan_step_sample_host_groups) waits for each group's previous result, reads its done flags on the host
+    and issues its next step from its pinned actions."""
     import torch
     from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
+    from settlers_of_catan_rl_b200.vec_env import HostEnvGroups
     sizes = [n // n_groups + (1 if gi < n % n_groups else 0) for gi in range(n_groups)]     # sum = n
-    groups = []
+    envs = []
     for gi in range(n_groups):
-        half = sizes[gi]
-        e = VecCatanEnv(half, device=dev, seed=seed, first_env_id=rank * n + sum(sizes[:gi]))
+        e = VecCatanEnv(sizes[gi], device=dev, seed=seed, first_env_id=rank * n + sum(sizes[:gi]))
         e.set_graphs(graphs)
         e.reset()
         a = e.sample_random()
         for _ in range(warm_ticks):
             e.step_sample(a)
-        g = {"env": e, "stream": torch.cuda.Stream(device=dev), "d_act": a,
-             "h_act": torch.empty((half, L.ACTION_WORDS), dtype=torch.int32).pin_memory(),
-             "h_rew": torch.empty((half, 4), dtype=torch.float32).pin_memory(),
-             "h_info": torch.empty((half, L.INFO_STRIDE), dtype=torch.uint8).pin_memory()}
-        g["np"] = (g["h_act"].numpy(), g["h_rew"].numpy(), g["h_info"].numpy())
-        groups.append(g)
+        envs.append(e)
     torch.cuda.synchronize()
-
-    def issue(g, step):
-        with torch.cuda.stream(g["stream"]):
-            if not step:                                       # the first actions: sampled on the device, brought to the host
-                g["env"].sample_random(g["d_act"])
-                g["h_act"].copy_(g["d_act"], non_blocking=True)
-            elif fused_sampler:                                # H2D actions, step + next random-legal actions, D2H actions/reward/info
-                g["env"].step_sample_host_async(g["np"][0], g["np"][1], g["np"][2])
-            else:
-                g["env"].step_host_async(g["np"][0], None, None, g["np"][1], g["np"][2])
-                g["env"].sample_random(g["d_act"])             # stand-in for the policy, as in e2e_tick
-                g["h_act"].copy_(g["d_act"], non_blocking=True)
-
-    for g in groups:
-        issue(g, False)
-    done_rows = 0
-    t0 = 0.0
-    for it in range(3 + steps):
-        if it == 3:
-            if barrier is not None:
-                barrier()
-            t0 = time.perf_counter()
-        for g in groups:
-            g["stream"].synchronize()                          # this half's result (and next actions) are on the host
-            done_rows += int(g["np"][2][0, L.INFO_DONE])       # touch the result
-            issue(g, True)
+    groups = HostEnvGroups(envs)
+    groups.prime()
+    groups.synchronize()
+    groups.pump(3)
+    if barrier is not None:
+        barrier()
+    t0 = time.perf_counter()
+    for it in range(steps):
+        groups.pump(1)                                         # (Python gets every round's results: one ctypes call per tick)
+    groups.synchronize()
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    launches_e2e = sum(g["env"].kernel_launches for g in groups)
-    errs_e2e = int(sum(int(g["env"].err_flags().any()) for g in groups))
-    for g in groups:
-        g["env"].close()
+    errs_e2e = int(sum(int(e.err_flags().any()) for e in envs))
+    for e in envs:
+        e.close()
     return n * world * steps / float(te.item()), errs_e2e
 
 
@@ -348,7 +331,7 @@ def run_b200_arm(args):
     env.set_timing(True)
     for _ in range(kernel_steps):
         env.step_sample(acts)
-    timed_n, transition_ms, encode_ms = env.read_timing()
+    timed_n, transition_ms, encode_ms, rows_ms = env.read_timing(detail=True)
     env.set_timing(False)
     games_done = int(env.info[:, L.INFO_DONE].sum().item())  # touch the result
     errs = int(env.err_flags().any())
@@ -500,7 +483,7 @@ def run_b200_arm(args):
                         "pinned host, synchronous; obs/masks stay in HBM for the GPU policy (d2h also counts the sampler's actions)"}
     e2e_db = {"value": e2e_pipe, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
               "rejected_actions": e2e_pipe_errs, "error": e2e_pipe_error, "groups": max(1, args.e2e_groups),
-              "call": "VecCatanEnv.step_sample_host_async -> catan_step_sample_host_async (the random-legal policy fused into the step as in `value`), double-buffered: the games split over %d handles on their own "
+              "call": "HostEnvGroups.pump -> catan_step_sample_host_groups -> catan_step_sample_host_async per handle (the random-legal policy fused into the step as in `value`), pipelined: the games split over %d handles on their own "
                       "streams, every step of every game still takes its actions from pinned host memory and returns reward+done/info "
                       "rows (and the sampler's next actions) to pinned host memory; the host waits for one group while the others run" % args.e2e_groups}
     e2e_best, e2e_other = (e2e_db, e2e_sync) if e2e_pipe >= e2e_value else (e2e_sync, e2e_db)
@@ -511,14 +494,15 @@ def run_b200_arm(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         per_launch_ms = ms_max / args.steps
-        # dominant kernel = encode_kernel (obs + mask rows): its algorithmic bytes per env step over its own duration
-        achieved = ENCODE_BYTES_PER_ENV_STEP * n / (encode_ms * 1e-3) / 1e9
+        # dominant kernel = the observation-rows launch of the encode: its algorithmic bytes per env step over its own duration
+        achieved = ROWS_BYTES_PER_ENV_STEP * n / (rows_ms * 1e-3) / 1e9
+        masks_ms = encode_ms - rows_ms
         step_achieved = ALGO_BYTES_PER_ENV_STEP * n / (per_launch_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("encode_kernel_dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get("encode_rows_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
         value = n * world * args.steps / (ms_max * 1e-3)
@@ -540,16 +524,23 @@ def run_b200_arm(args):
                          "obs_write_only": {"bytes_per_env_step": 1867, "achieved": 1867 * n / (per_launch_ms * 1e-3) / 1e9,
                                             "frac": 1867 * n / (per_launch_ms * 1e-3) / 1e9 / peak,
                                             "note": "north_star's obs-write roofline: the 1 867 obs bytes of every env step over the WHOLE step time"},
-                         "kernel": "encode_kernel<MODE_STEP, SAMPLE> (obs + mask rows + sampler)",
-                         "algorithmic_bytes_per_launch": ENCODE_BYTES_PER_ENV_STEP * n, "peak_source": peak_src,
-                         "kernel_ms": encode_ms, "timed_launches": timed_n,
-                         "how": "CUDA events recorded by the library around the kernel on the launching stream (catan_set_timing)",
+                         "kernel": "encode_kernel<MODE_STEP, SAMPLE, ROLE_ROWS> (the observation rows: 640 B of record in, 1 867 B out per env step)",
+                         "algorithmic_bytes_per_launch": ROWS_BYTES_PER_ENV_STEP * n, "peak_source": peak_src,
+                         "kernel_ms": rows_ms, "timed_launches": timed_n,
+                         "how": "CUDA events recorded by the library around each kernel on the launching stream (catan_set_timing: the rows launch "
+                                "then runs in front of the masks launch on the caller's stream; in production it runs beside it on a library stream)",
+                         "encode_masks_kernel": {"ms": masks_ms, "algorithmic_bytes_per_launch": MASKS_BYTES_PER_ENV_STEP * n,
+                                                 "achieved": MASKS_BYTES_PER_ENV_STEP * n / (masks_ms * 1e-3) / 1e9},
+                         "encode_both_launches": {"ms": encode_ms, "algorithmic_bytes_per_launch": ENCODE_BYTES_PER_ENV_STEP * n,
+                                                  "achieved": ENCODE_BYTES_PER_ENV_STEP * n / (encode_ms * 1e-3) / 1e9,
+                                                  "frac": ENCODE_BYTES_PER_ENV_STEP * n / (encode_ms * 1e-3) / 1e9 / peak},
                          "transition_kernel": {"ms": transition_ms, "algorithmic_bytes_per_launch": TRANSITION_BYTES_PER_ENV_STEP * n,
                                                "achieved": TRANSITION_BYTES_PER_ENV_STEP * n / (transition_ms * 1e-3) / 1e9},
                          "whole_step": {"ms": per_launch_ms, "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * n,
                                         "achieved": step_achieved, "frac": step_achieved / peak,
-                                        "note": "9 launches on 3 streams, replayed as one CUDA graph: transition, encode | longest-road search, encode of the "
-                                                "searched games, copy-back, counters | encode (done / reset / new game) of the games that ended, copy-back, counters"}},
+                                        "note": "10 launches on 4 streams, replayed as one CUDA graph: transition, masks + sampler | observation rows | longest-road "
+                                                "search, encode of the searched games, copy-back, counters | encode (done / reset / new game) of the games that "
+                                                "ended, copy-back, counters"}},
             "cpu_baseline": cpu_baseline,
             "cpu_baseline_port": cpu_baseline_port,
             "aux": aux,

@@ -96,6 +96,14 @@ int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t
  * from the host): actions_io_host (pinned) is copied in, applied, and overwritten with every env's next random-legal action. */
 int catan_step_sample_host_async(catan_env_t* env, int32_t* actions_io_host, float* reward_host, uint8_t* info_host, void* stream);
 int catan_reset_host(catan_env_t* env, uint8_t* obs_host, uint8_t* masks_host, uint8_t* info_host, void* stream);
+/* One round of the host loop that keeps several env groups (handles) in flight -- the sub-process manager's pipelining,
+ * RL/ppo/vec_gather_experience.py, without a Python round trip per group: for g = 0 .. n_groups-1, wait for group g's previous
+ * step (cudaStreamSynchronize(streams[g])): its reward / info rows and next actions are then in its pinned host buffers; count the
+ * `done` flags of its info rows into *done_seen (may be NULL; this is the host's read of the result); issue its next
+ * catan_step_sample_host_async on streams[g].  Repeated `rounds` times.  The buffers of group g hold its last ISSUED step's
+ * result once streams[g] has been synchronised by the caller. */
+int catan_step_sample_host_groups(catan_env_t* const* envs, int n_groups, int32_t* const* actions_io_host, float* const* reward_host,
+                                  uint8_t* const* info_host, void* const* streams, int rounds, long long* done_seen);
 
 /* EnvWrapper.save_state / restore_state (env/wrapper.py:711-721; game/game.py:1013-1205) as the
  * canonical int16 state (catan_state_t) of `count` envs starting at `first`.  Host buffers;
@@ -114,8 +122,10 @@ int catan_read_err_flags(catan_env_t* env, uint32_t* flags_host, int clear);
 int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host);
 
 /* Device-side timing of a step's two kernels on the caller's stream (CUDA events recorded by catan_step*): enable,
- * step, then read out_host[0] = steps timed, [1] = summed ms of transition_kernel, [2] = summed ms of encode_kernel
- * (with the longest-road stream running beside it, as in production).  bench.py's roofline uses it.  Synchronous. */
+ * step, then read out_host[0] = steps timed, [1] = summed ms of transition_kernel, [2] = summed ms of the two encode launches
+ * (observation rows, then masks + sampler; with the longest-road / reset streams running beside them, as in production),
+ * [3] = summed ms of the rows launch alone.  While the hooks are on, the rows launch runs on the caller's stream in front of the
+ * masks launch instead of beside it.  bench.py's roofline uses it.  Synchronous.  out_host: 4 doubles. */
 int catan_set_timing(catan_env_t* env, int enable);
 int catan_read_timing(catan_env_t* env, double* out_host);
 

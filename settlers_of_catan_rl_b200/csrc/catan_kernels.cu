@@ -769,7 +769,8 @@ struct catan_env {
   int lr_grid = 0;
   cudaStream_t lr_stream = nullptr;   // high-priority stream of the longest-road updates (overlaps the encode kernel)
   cudaStream_t rs_stream = nullptr;   // high-priority stream of the games that are reset (likewise)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_rs = nullptr;
+  cudaStream_t rows_stream = nullptr; // the observation rows of a step: beside the masks + sampler launch (neither reads what the other writes)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_rs = nullptr, ev_join_rows = nullptr;
   // catan_set_timing: CUDA events around the two kernels on the caller's stream, a ring of kTimedSteps steps
   // catan_set_graphs: every distinct step call (entry point + buffer pointers) is captured once into a CUDA graph on an internal
   // stream and replayed on the caller's stream afterwards: one driver call per step instead of ~20 (9 launches, 6 event calls, copies)
@@ -779,9 +780,9 @@ struct catan_env {
   struct StepGraph { int kind; const void* p[4]; cudaGraphExec_t exec; };
   std::vector<StepGraph> graphs;
   bool timing = false;
-  cudaEvent_t tev[32][3] = {};
+  cudaEvent_t tev[32][4] = {};        // [0] transition [1] rows [3] masks + sampler [2]
   unsigned long long timed = 0;        // steps recorded since timing was switched on
-  double t_ms[2] = {0.0, 0.0};         // transition, encode: summed over the steps already retired from the ring
+  double t_ms[3] = {0.0, 0.0, 0.0};    // transition, encode (rows + masks), rows alone: summed over the steps already retired from the ring
   unsigned long long t_n = 0;
 };
 
@@ -828,14 +829,22 @@ static cudaError_t launch_with_record_window(const catan_env* env, Kernel kernel
 }
 
 template <int MODE, bool SAMPLE>
-static int launch_encode(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream) {
+static int launch_encode(catan_env* env, EnvParams P, int first, int count, cudaStream_t stream, cudaEvent_t* tev = nullptr) {
   P.range_first = first; P.range_count = count;
   if (count <= 0) return 0;
-  if constexpr (MODE == catanb::MODE_STEP) {                         // rows, then masks + sampler: two launches of 4-warp blocks
+  if constexpr (MODE == catanb::MODE_STEP) {
+    // Two launches of 4-warp blocks, side by side: the observation rows on the library's rows stream (forked at ev_fork, joined by
+    // the caller), masks + sampler on the caller's stream.  With the timing hooks on they run one after the other on the caller's
+    // stream, an event between them, so that each is measured alone.
+    cudaStream_t rs = tev ? stream : env->rows_stream;
+    if (!tev) CATAN_CUDA(cudaStreamWaitEvent(rs, env->ev_fork, 0));
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, false, catanb::ROLE_ROWS>, game_blocks(first, count),
-                                         catanb::kEncThreads / 2, catanb::enc_smem_bytes(catanb::ROLE_ROWS), stream, P));
+                                         catanb::kEncThreads / 2, catanb::enc_smem_bytes(catanb::ROLE_ROWS), rs, P));
+    if (tev) CATAN_CUDA(cudaEventRecord(tev[3], stream));
+    else CATAN_CUDA(cudaEventRecord(env->ev_join_rows, rs));
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, false, catanb::ROLE_MASKS>, game_blocks(first, count),
                                          catanb::kEncThreads / 2, catanb::enc_smem_bytes(catanb::ROLE_MASKS), stream, P));
+    if (!tev) CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join_rows, 0));
   } else {
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<MODE, false, false, catanb::ROLE_BOTH>,
                                          game_blocks(first, count), catanb::kEncThreads, sizeof(catanb::EncSmem), stream, P));
@@ -848,11 +857,12 @@ static int launch_encode(catan_env* env, EnvParams P, int first, int count, cuda
 // updates and the encode of exactly those games.  The searches are latency-bound (a few hundred dependent walk steps
 // per update) and would otherwise sit between the two big kernels with the machine idle.
 static int retire_timed_step(catan_env* env, cudaEvent_t* ev) {     // one ring slot -> the sums (waits for that step)
-  float a = 0.f, b = 0.f;
+  float a = 0.f, b = 0.f, c = 0.f;
   CATAN_CUDA(cudaEventSynchronize(ev[2]));
   CATAN_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
   CATAN_CUDA(cudaEventElapsedTime(&b, ev[1], ev[2]));
-  env->t_ms[0] += a; env->t_ms[1] += b; env->t_n += 1;
+  CATAN_CUDA(cudaEventElapsedTime(&c, ev[1], ev[3]));
+  env->t_ms[0] += a; env->t_ms[1] += b; env->t_ms[2] += c; env->t_n += 1;
   return 0;
 }
 
@@ -896,7 +906,7 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
     CATAN_CUDA(cudaGetLastError());
     CATAN_CUDA(cudaEventRecord(env->ev_join_rs, env->rs_stream));
   }
-  if (launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream)) return -1;
+  if (launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream, tev)) return -1;
   if (tev) CATAN_CUDA(cudaEventRecord(tev[2], stream));
   CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join, 0));
   CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join_rs, 0));
@@ -950,9 +960,11 @@ static void free_env(catan_env* env) {
   if (env->capture_stream) cudaStreamDestroy(env->capture_stream);
   if (env->lr_stream) cudaStreamDestroy(env->lr_stream);
   if (env->rs_stream) cudaStreamDestroy(env->rs_stream);
+  if (env->rows_stream) cudaStreamDestroy(env->rows_stream);
   if (env->ev_fork) cudaEventDestroy(env->ev_fork);
   if (env->ev_join) cudaEventDestroy(env->ev_join);
   if (env->ev_join_rs) cudaEventDestroy(env->ev_join_rs);
+  if (env->ev_join_rows) cudaEventDestroy(env->ev_join_rows);
   for (auto& slot : env->tev) for (cudaEvent_t ev : slot) if (ev) cudaEventDestroy(ev);
   cudaFree(env->recs); cudaFree(env->stage); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_slow_queue); cudaFree(env->lr_ctl);
   cudaFree(env->rs_queue); cudaFree(env->stage_rs);
@@ -1028,10 +1040,12 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
     e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&env->lr_stream, cudaStreamNonBlocking, hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&env->rs_stream, cudaStreamNonBlocking, hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&env->rows_stream, cudaStreamNonBlocking, lo);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join_rs, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join_rows, cudaEventDisableTiming);
   {
     const int enc_bytes = static_cast<int>(sizeof(catanb::EncSmem));   // > 48 KB: opt in, per instantiation
     using namespace catanb;
@@ -1183,6 +1197,26 @@ int catan_step_sample_host_async(catan_env_t* env, int32_t* actions_io_host, flo
   return g <= 0 ? g : issue(static_cast<cudaStream_t>(stream));
 }
 
+int catan_step_sample_host_groups(catan_env_t* const* envs, int n_groups, int32_t* const* actions_io_host, float* const* reward_host,
+                                  uint8_t* const* info_host, void* const* streams, int rounds, long long* done_seen) {
+  if (!envs || !actions_io_host || !reward_host || !info_host || !streams || n_groups <= 0 || rounds < 0) return fail("catan_step_sample_host_groups: bad argument");
+  long long seen = 0;
+  for (int r = 0; r < rounds; ++r) {
+    for (int g = 0; g < n_groups; ++g) {
+      if (check_bound(envs[g]) || device_guard(envs[g])) return -1;
+      CATAN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(streams[g])));
+      if (info_host[g]) {
+        const uint8_t* info = info_host[g];
+        const int n = envs[g]->n;
+        for (int i = 0; i < n; ++i) seen += info[static_cast<size_t>(i) * CATAN_INFO_STRIDE + CATAN_INFO_DONE];
+      }
+      if (catan_step_sample_host_async(envs[g], actions_io_host[g], reward_host[g], info_host[g], streams[g])) return -1;
+    }
+  }
+  if (done_seen) *done_seen += seen;
+  return 0;
+}
+
 int catan_step_host(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_host, uint8_t* masks_host, float* reward_host,
                     uint8_t* info_host, void* stream) {
   if (check_bound(env)) return -1;
@@ -1294,7 +1328,7 @@ int catan_set_timing(catan_env_t* env, int enable) {
   CATAN_CUDA(cudaDeviceSynchronize());
   if (enable)
     for (auto& slot : env->tev) for (cudaEvent_t& ev : slot) if (!ev) CATAN_CUDA(cudaEventCreate(&ev));
-  env->timing = enable != 0; env->timed = 0; env->t_ms[0] = env->t_ms[1] = 0.0; env->t_n = 0;
+  env->timing = enable != 0; env->timed = 0; env->t_ms[0] = env->t_ms[1] = env->t_ms[2] = 0.0; env->t_n = 0;
   return 0;
 }
 
@@ -1304,7 +1338,7 @@ int catan_read_timing(catan_env_t* env, double* out_host) {
   const unsigned long long pending = env->timed < 32 ? env->timed : 32;
   for (unsigned long long k = env->timed - pending; k < env->timed; ++k) if (retire_timed_step(env, env->tev[k % 32])) return -1;
   env->timed = 0;                                                    // (the ring is empty again)
-  out_host[0] = static_cast<double>(env->t_n); out_host[1] = env->t_ms[0]; out_host[2] = env->t_ms[1];
+  out_host[0] = static_cast<double>(env->t_n); out_host[1] = env->t_ms[0]; out_host[2] = env->t_ms[1]; out_host[3] = env->t_ms[2];
   return 0;
 }
 

@@ -17,7 +17,7 @@ import torch
 from . import _lib, layout as L
 
 
-#: launches of one step: transition, encode of the rows, encode of the masks + sampler (caller's stream) | longest-road search, encode of the searched games, copy-back, counter
+#: launches of one step: transition, encode of the masks + sampler (caller's stream) | encode of the rows (library stream 0) | longest-road search, encode of the searched games, copy-back, counter
 #: bookkeeping (library stream 1) | encode of the games that ended and were reset, copy-back, counter bookkeeping (library stream 2)
 LAUNCHES_PER_STEP = 10
 
@@ -188,12 +188,13 @@ class VecCatanEnv:
         """CUDA events around the transition and encode kernels of every following step (catan_set_timing)"""
         _lib.check(self.lib.catan_set_timing(self._h, int(enable)))
 
-    def read_timing(self):
-        """(steps timed, average ms of transition_kernel, average ms of encode_kernel) since set_timing(True)"""
-        out = np.zeros(3, dtype=np.float64)
+    def read_timing(self, detail: bool = False):
+        """(steps timed, average ms of transition_kernel, average ms of the two encode launches) since set_timing(True);
+        ``detail``: a fourth entry, the average ms of the observation-rows launch alone"""
+        out = np.zeros(4, dtype=np.float64)
         _lib.check(self.lib.catan_read_timing(self._h, C.c_void_p(out.ctypes.data)))
         n = max(1.0, out[0])
-        return int(out[0]), out[1] / n, out[2] / n
+        return (int(out[0]), out[1] / n, out[2] / n) + ((out[3] / n,) if detail else ())
 
     def err_flags(self, clear: bool = False) -> np.ndarray:
         out = np.zeros(self.n_envs, dtype=np.uint32)
@@ -236,3 +237,47 @@ class VecCatanEnv:
     def mask_views(self):
         """List of 12 uint8 views shaped like EnvWrapper.get_action_masks() with a leading env dim."""
         return [self.masks[:, off:off + int(np.prod(shape))].view(self.n_envs, *shape) for off, shape in L.MASK_HEADS]
+
+
+class HostEnvGroups:
+    """Several ``VecCatanEnv`` handles kept in flight from the host, each on its own stream with its own pinned host buffers
+    (the sub-process manager's pipelining, RL/ppo/vec_gather_experience.py: while the host looks at one group's result, the other
+    groups' kernels and PCIe copies run).  ``pump()`` is ONE library call per round (``catan_step_sample_host_groups``): for every
+    group in turn it waits for the group's previous step, reads the ``done`` flags of its info rows, and issues its next step from
+    the actions in ``actions[g]`` (pinned; overwritten with the next random-legal actions, as ``step_sample_host_async``)."""
+
+    def __init__(self, envs):
+        self.envs = list(envs)
+        G = len(self.envs)
+        dev = self.envs[0].device
+        self.lib = self.envs[0].lib
+        self.streams = [torch.cuda.Stream(device=e.device) for e in self.envs]
+        self.actions = [torch.empty((e.n_envs, L.ACTION_WORDS), dtype=torch.int32).pin_memory() for e in self.envs]
+        self.reward = [torch.empty((e.n_envs, 4), dtype=torch.float32).pin_memory() for e in self.envs]
+        self.info = [torch.zeros((e.n_envs, L.INFO_STRIDE), dtype=torch.uint8).pin_memory() for e in self.envs]
+        arr = C.c_void_p * G
+        self._envs = arr(*[e._h.value for e in self.envs])
+        self._act = arr(*[t.data_ptr() for t in self.actions])
+        self._rew = arr(*[t.data_ptr() for t in self.reward])
+        self._info = arr(*[t.data_ptr() for t in self.info])
+        self._streams = arr(*[s.cuda_stream for s in self.streams])
+        self.done_seen = C.c_longlong(0)
+        self.device = dev
+
+    def prime(self) -> None:
+        """the first actions of every group: sampled on the device, brought to the host"""
+        for e, s, a in zip(self.envs, self.streams, self.actions):
+            with torch.cuda.stream(s):
+                d = e.sample_random()
+                a.copy_(d, non_blocking=True)
+                d.record_stream(s)
+
+    def pump(self, rounds: int = 1) -> None:
+        _lib.check(self.lib.catan_step_sample_host_groups(self._envs, len(self.envs), self._act, self._rew, self._info, self._streams,
+                                                          int(rounds), C.byref(self.done_seen)))
+        for e in self.envs:
+            e.kernel_launches += LAUNCHES_PER_STEP * int(rounds)
+
+    def synchronize(self) -> None:
+        for s in self.streams:
+            s.synchronize()

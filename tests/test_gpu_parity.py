@@ -91,6 +91,10 @@ def test_cuda_auto_reset_matches_reference_reset():
     (4096, 1500, 100, {}),
     (1000, 600, 50, dict(dense_reward=1, reward_annealing_factor=0.5, max_proposed_trades_per_turn=-1)),
     (333, 400, 57, dict(max_actions_per_turn=4)),
+    # soak: the BASELINE size (65 536 envs) through 2 200 ticks, and 4 096 envs through 10 000 ticks (about eight games per env: long
+    # games, u16 turn counters, full card lists, every reset path), with unlimited trade proposals in the long one
+    (65536, 2200, 200, {}),
+    (4096, 10000, 500, dict(max_proposed_trades_per_turn=-1)),
 ])
 def test_cuda_matches_oracle_at_scale(n_envs, steps, chunk, cfg):
     """same (seed, env ids), same pinned sampler: kernel (fused step+sample) vs the C oracle on host threads"""

@@ -229,3 +229,41 @@ def test_library_graph_replay_is_the_same_step():
         torch.cuda.synchronize()
         assert torch.equal(h_act[0], h_act[1]) and torch.equal(h_rew[0], h_rew[1]) and torch.equal(h_info[0], h_info[1]), t
     assert int(a_env.err_flags().any()) == 0 and int(b_env.err_flags().any()) == 0
+
+
+def test_host_env_groups_pump_is_the_per_handle_loop():
+    """catan_step_sample_host_groups (one library call per round over several handles in flight) == the same handles stepped one
+    by one with catan_step_sample_host_async: actions, reward, info rows, final state; the done flags it read add up"""
+    import numpy as np
+    from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
+    from settlers_of_catan_rl_b200.vec_env import HostEnvGroups
+    sizes, seed = [700, 650, 697], 9
+    def make():
+        envs = [VecCatanEnv(m, seed=seed, first_env_id=sum(sizes[:k])) for k, m in enumerate(sizes)]
+        for e in envs:
+            e.set_graphs(True)
+            e.reset()
+        return envs
+    a_envs, b_envs = make(), make()
+    groups = HostEnvGroups(a_envs)
+    groups.prime()
+    h = [(torch.empty((m, L.ACTION_WORDS), dtype=torch.int32).pin_memory(), torch.empty((m, 4), dtype=torch.float32).pin_memory(),
+          torch.zeros((m, L.INFO_STRIDE), dtype=torch.uint8).pin_memory()) for m in sizes]
+    for e, (ha, _, _) in zip(b_envs, h):
+        ha.copy_(e.sample_random())
+    torch.cuda.synchronize()
+    done_b = 0
+    for r in range(12):
+        groups.pump(50)
+        for _ in range(50):
+            for e, (ha, hr, hi) in zip(b_envs, h):
+                done_b += int(hi[:, L.INFO_DONE].sum())                 # (the previous step's rows, as the pump reads them)
+                e.step_sample_host_async(ha.numpy(), hr.numpy(), hi.numpy())
+                torch.cuda.synchronize()
+        groups.synchronize()
+        for k in range(len(sizes)):
+            assert torch.equal(groups.actions[k], h[k][0]) and torch.equal(groups.reward[k], h[k][1]) and torch.equal(groups.info[k], h[k][2]), (r, k)
+    assert groups.done_seen.value == done_b and done_b > 0
+    for ea, eb in zip(a_envs, b_envs):
+        assert np.array_equal(ea.export_state(), eb.export_state())
+        assert not ea.err_flags().any()
