@@ -125,7 +125,9 @@ int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host);
  * step, then read out_host[0] = steps timed, [1] = summed ms of transition_kernel, [2] = summed ms of the two encode launches
  * (observation rows, then masks + sampler; with the longest-road / reset streams running beside them, as in production),
  * [3] = summed ms of the rows launch alone.  While the hooks are on, the rows launch runs on the caller's stream in front of the
- * masks launch instead of beside it.  bench.py's roofline uses it.  Synchronous.  out_host: 4 doubles. */
+ * masks launch instead of beside it.  bench.py's roofline uses it.  Synchronous.  out_host: 9 doubles; [4..8] = summed ms, from
+ * the end of the transition, until the search stream starts its search / of the search / of the rest of that stream (encode of the
+ * searched games, copy-back) / until the reset stream is done / until the last of the step's streams is done. */
 int catan_set_timing(catan_env_t* env, int enable);
 int catan_read_timing(catan_env_t* env, double* out_host);
 

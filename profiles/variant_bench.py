@@ -17,3 +17,4 @@ env.set_timing(True)
 for _ in range(200): env.step_sample(a)
 _, tr, en, rows = env.read_timing(detail=True)
 print("%s: %.4f ms/step  transition %.4f  encode %.4f (rows %.4f, masks %.4f)  errs %d" % (os.environ.get("CATAN_B200_LIB", "default"), e0.elapsed_time(e1) / ticks, tr, en, rows, en - rows, int(env.err_flags().any())))
+print("   streams (ms from the end of the transition):", {k: round(v, 4) for k, v in env.stream_timing.items()})

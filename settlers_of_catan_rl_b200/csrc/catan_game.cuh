@@ -1282,7 +1282,7 @@ CATAN_FN_NOINLINE int t_lr_fast(const GameView& g_, const Topo& T, int pid, int 
 // done / reward / info (wrapper.py:85-112).  Returns true when the game ended and must be reset (cfg.auto_reset); the
 // reset itself is done by reset_game_group(), which then patches the two info bytes that describe the new game.
 // ------------------------------------------------------------------------------------------------
-CATAN_FN_NOINLINE bool t_step_finish(TCx& cx_, const StepTmp& tmp, float* reward_out, uint8_t* info_out) {
+CATAN_FN bool t_step_finish_inl(TCx& cx_, const StepTmp& tmp, float* reward_out, uint8_t* info_out) {
   TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
   CATAN_IN_LOCAL(&tmp);
   CATAN_STAGED_ENCODE(cx);
@@ -1334,6 +1334,7 @@ CATAN_FN_NOINLINE bool t_step_finish(TCx& cx_, const StepTmp& tmp, float* reward
   *reinterpret_cast<V16*>(info_out) = info;
   return done && cx.cfg->auto_reset;
 }
+CATAN_FN_NOINLINE bool t_step_finish(TCx& cx, const StepTmp& tmp, float* reward_out, uint8_t* info_out) { CATAN_IN_LOCAL(&tmp); return t_step_finish_inl(cx, tmp, reward_out, info_out); }
 
 // ------------------------------------------------------------------------------------------------
 // reset: Board.reset (board.py:67-167) + Game.reset (game.py:39-136) + EnvWrapper.reset (wrapper.py:30-34), by a GROUP of
@@ -1573,7 +1574,7 @@ CATAN_FN void t_mask_play_dev(const GameView& g, int p, MaskBits& m) {   // wrap
 // The masks of one game in two halves around the placement scan: t_masks_pre() handles the phases that need no board
 // scan and returns true when t_scan_group() must run for this game (PlayerId = players_go) before t_masks_post().
 struct MaskPlan { uint8_t post, initial, rb, capped, init_settle, want_settle, want_city, want_road, want_tiles; };   // post: t_masks_post() must run
-CATAN_FN_NOINLINE bool t_masks_pre(const TCx& cx_, MaskBits& m, MaskPlan& pl) {
+CATAN_FN bool t_masks_pre_inl(const TCx& cx_, MaskBits& m, MaskPlan& pl) {
   TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
   CATAN_IN_LOCAL(&m); CATAN_IN_LOCAL(&pl);
   CATAN_STAGED_ENCODE(cx);
@@ -1637,8 +1638,9 @@ CATAN_FN_NOINLINE bool t_masks_pre(const TCx& cx_, MaskBits& m, MaskPlan& pl) {
   pl.want_settle = want_settle; pl.want_city = want_city; pl.want_road = want_road; pl.want_tiles = want_tiles;
   return want_settle || want_city || want_road || want_tiles;
 }
+CATAN_FN_NOINLINE bool t_masks_pre(const TCx& cx, MaskBits& m, MaskPlan& pl) { CATAN_IN_LOCAL(&m); CATAN_IN_LOCAL(&pl); return t_masks_pre_inl(cx, m, pl); }
 
-CATAN_FN_NOINLINE void t_masks_post(const TCx& cx_, MaskBits& m, const MaskPlan& pl, const Scan& sc) {
+CATAN_FN void t_masks_post_inl(const TCx& cx_, MaskBits& m, const MaskPlan& pl, const Scan& sc) {
   TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
   CATAN_IN_LOCAL(&m); CATAN_IN_LOCAL(&pl); CATAN_IN_SMEM(&sc);
   CATAN_STAGED_ENCODE(cx);
@@ -1696,6 +1698,7 @@ CATAN_FN_NOINLINE void t_masks_post(const TCx& cx_, MaskBits& m, const MaskPlan&
     if (g.can_move_robber()) m.type |= 1u << CATAN_ACT_MOVE_ROBBER;
   }
 }
+CATAN_FN_NOINLINE void t_masks_post(const TCx& cx, MaskBits& m, const MaskPlan& pl, const Scan& sc) { CATAN_IN_LOCAL(&m); CATAN_IN_LOCAL(&pl); t_masks_post_inl(cx, m, pl, sc); }
 
 // the 325 mask entries as one bit string (bit i = entry i of the packed row, catan_layout.h)
 struct MaskFlat { uint32_t w[11]; };
@@ -1784,8 +1787,7 @@ CATAN_FN int pick32(uint32_t m, uint32_t w) { return pick96(m, 0u, 0u, w); }
 CATAN_FN int pick64(uint64_t m, uint32_t w) { return pick96(static_cast<uint32_t>(m), static_cast<uint32_t>(m >> 32), 0u, w); }
 
 // hand_bits: bit r set iff the acting player holds resource r (== obs current_resources[1..5] != 0, wrapper.py:70-71)
-CATAN_FN_NOINLINE void t_sample_action(const MaskBits& m, uint32_t hand_bits, uint64_t seed, uint64_t env_id, uint32_t decision, int32_t* out) {
-  CATAN_IN_LOCAL(&m);
+CATAN_FN void t_sample_action_inl(const MaskBits& m, uint32_t hand_bits, uint64_t seed, uint64_t env_id, uint32_t decision, int32_t* out) {
   uint32_t w[4];
   philox4x32(decision, CATAN_STREAM_SAMPLER, static_cast<uint32_t>(env_id), static_cast<uint32_t>(env_id >> 32),
              static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), w);
@@ -1823,6 +1825,7 @@ CATAN_FN_NOINLINE void t_sample_action(const MaskBits& m, uint32_t hand_bits, ui
   const I4 r0 = {t, corner, edge, tile}, r1 = {card, accept, player, give}, r2 = {0, 0, 0, recv}, r3 = {0, 0, 0, res_a}, r4 = {res_b, discard, 0, 0};
   o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4;
 }
+CATAN_FN_NOINLINE void t_sample_action(const MaskBits& m, uint32_t hand_bits, uint64_t seed, uint64_t env_id, uint32_t decision, int32_t* out) { CATAN_IN_LOCAL(&m); t_sample_action_inl(m, hand_bits, seed, env_id, decision, out); }
 static_assert(CATAN_A_TYPE == 0 && CATAN_A_CORNER == 1 && CATAN_A_EDGE == 2 && CATAN_A_TILE == 3 && CATAN_A_CARD == 4 && CATAN_A_ACCEPT == 5 &&
               CATAN_A_PLAYER == 6 && CATAN_A_GIVE == 7 && CATAN_A_RECV == 11 && CATAN_A_RES_A == 15 && CATAN_A_RES_B == 16 &&
               CATAN_A_DISCARD == 17 && CATAN_ACTION_WORDS == 20, "t_sample_action packs the action row by hand");
@@ -2020,7 +2023,7 @@ CATAN_FN uint64_t t_tile_bits(const GameView& g, const Topo& T, int t, int robbe
   return static_cast<uint64_t>(w0) | (static_cast<uint64_t>(w1) << 32);
 }
 
-CATAN_FN_NOINLINE void t_encode_obs_tiles(const TCx& cx_, uint8_t* row, int lo, int hi) {
+CATAN_FN void t_encode_obs_tiles_inl(const TCx& cx_, uint8_t* row, int lo, int hi) {
   TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
   CATAN_STAGED_ENCODE(cx);
   const GameView& g = cx.g;
@@ -2074,6 +2077,9 @@ CATAN_FN_NOINLINE void t_encode_obs_tiles(const TCx& cx_, uint8_t* row, int lo, 
     pos += 16;
   }
 }
+// (the called form: the kernels that hold several phases keep their code small; the rows launch of a step inlines it -- a call
+// forces the context through local memory, which misses the small L1 these kernels leave beside their shared memory)
+CATAN_FN_NOINLINE void t_encode_obs_tiles(const TCx& cx, uint8_t* row, int lo, int hi) { t_encode_obs_tiles_inl(cx, row, lo, hi); }
 static_assert(CATAN_OBS_PROPOSED_TRADE == 0 && CATAN_OBS_CURRENT_RES == 12 && CATAN_OBS_TILES == 18 && CATAN_OBS_TILE_DIM == 60,
               "t_encode_obs_tiles packs the header by hand");
 

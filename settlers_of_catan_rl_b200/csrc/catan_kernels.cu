@@ -59,6 +59,35 @@ constexpr int kRowWarps = CATAN_OBS_TILE_PARTS;  // encode_kernel: warps that wr
 constexpr int kEncWarps = 2 * kRowWarps;         // ... and as many that share the per-game scalar work (done / reward, masks, sampler)
 constexpr int kEncThreads = kEncWarps * 32;
 constexpr int kMaskWarps = kEncWarps - kRowWarps;
+// the rows launch of a step (ROLE_ROWS): its own number of warps, each with a balanced share of the row's 120 16-byte pieces
+#ifndef CATAN_ROWS_WARPS
+#define CATAN_ROWS_WARPS 4
+#endif
+#ifndef CATAN_ROWS_BLOCKS
+#define CATAN_ROWS_BLOCKS 7
+#endif
+constexpr int kRowsWarps = CATAN_ROWS_WARPS, kRowsThreads = kRowsWarps * 32;
+constexpr int kMasksThreads = kMaskWarps * 32;
+static_assert(kRowsWarps >= 4 && kRowsWarps <= 8, "warps 0-3 of the rows launch own the four player blocks");
+// Warp w of the rows launch writes the player part 4 + w (w < 4: 10 pieces) or the card lists (w == min(4, kRowsWarps - 1): 8 pieces) and the
+// tile pieces [rows_tile_lo(w), rows_tile_lo(w + 1)) of the 72 pieces of the header + tile region, so that every warp has about
+// 120 / kRowsWarps pieces.
+__host__ __device__ constexpr int rows_fixed_pieces(int w) { return (w < 4 ? 10 : 0) + (w == (kRowsWarps > 4 ? 4 : 3) ? 8 : 0); }
+__host__ __device__ constexpr int rows_tile_lo(int w) {
+  // greedy: hand out the 72 tile pieces one by one to the warp with the fewest pieces so far (ties: the highest warp)
+  int have[12] = {0};
+  for (int k = 0; k < kRowsWarps; ++k) have[k] = rows_fixed_pieces(k);
+  int tiles[12] = {0};
+  for (int n = 0; n < 72; ++n) {
+    int best = kRowsWarps - 1;
+    for (int k = kRowsWarps - 1; k >= 0; --k) if (have[k] < have[best]) best = k;
+    have[best] += 1; tiles[best] += 1;
+  }
+  int lo = 0;
+  for (int k = 0; k < w; ++k) lo += tiles[k];
+  return lo;
+}
+static_assert(rows_tile_lo(0) == 0 && rows_tile_lo(kRowsWarps) == 72, "the tile pieces are covered exactly once");
 static_assert(CATAN_OBS_PARTS == 2 * CATAN_OBS_TILE_PARTS + 1, "row warp r writes tile part r and player part r; the last one also the lists");
 constexpr int kCopyThreads = 128;           // lr_copy_back_kernel: one warp per game
 constexpr int kLrSlowThreads = 512;         // lr_slow_kernel: one block per update that needs a search
@@ -496,10 +525,11 @@ constexpr size_t enc_smem_bytes(int role) {
 #define CATAN_ENC_MIN_BLOCKS 4   // (5 blocks per SM at 48 registers measured 2 % slower than 4 at 56)
 #endif
 template <int MODE, bool SAMPLE, bool LISTED, int ROLE>
-__global__ void __launch_bounds__(ROLE == ROLE_BOTH ? kEncThreads : kEncThreads / 2, ROLE == ROLE_BOTH ? CATAN_ENC_MIN_BLOCKS : 7)
+__global__ void __launch_bounds__(ROLE == ROLE_BOTH ? kEncThreads : ROLE == ROLE_ROWS ? kRowsThreads : kMasksThreads,
+                                  ROLE == ROLE_BOTH ? CATAN_ENC_MIN_BLOCKS : ROLE == ROLE_ROWS ? CATAN_ROWS_BLOCKS : 7)
 encode_kernel(const __grid_constant__ EnvParams P) {
   static_assert(ROLE == ROLE_BOTH || (MODE == MODE_STEP && !LISTED), "the split roles are for the main path of a step");
-  constexpr int kThreads = ROLE == ROLE_BOTH ? kEncThreads : kEncThreads / 2, kWarps = kThreads / 32;
+  constexpr int kThreads = ROLE == ROLE_BOTH ? kEncThreads : ROLE == ROLE_ROWS ? kRowsThreads : kMasksThreads, kWarps = kThreads / 32;
   extern __shared__ __align__(128) uint8_t enc_smem_raw[];
   EncSmem& S = *reinterpret_cast<EncSmem*>(enc_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -567,7 +597,8 @@ encode_kernel(const __grid_constant__ EnvParams P) {
             StepTmp tmp;
             tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
             tmp.roll_info = static_cast<uint8_t>((sd >> 24) & 0x7f);
-            need_reset = t_step_finish(mx, tmp, P.reward + static_cast<size_t>(im) * 4, info);
+            need_reset = (ROLE == ROLE_MASKS) ? t_step_finish_inl(mx, tmp, P.reward + static_cast<size_t>(im) * 4, info)
+                                              : t_step_finish(mx, tmp, P.reward + static_cast<size_t>(im) * 4, info);
             hv.episode_steps() = mx.g.episode_steps(); hv.winner() = mx.g.winner();   // what done / reward changed (wrapper.py:85-112)
 #pragma unroll
             for (int p = 0; p < 4; ++p) hv.curr_vps(p) = mx.g.curr_vps(p);
@@ -613,7 +644,7 @@ encode_kernel(const __grid_constant__ EnvParams P) {
         pl.post = 0;
         if (vm) mx.s = load_seats(mx.g);
         if (MODE != MODE_STEP && vm) t_write_info_fresh(mx.g, info, MODE == MODE_RESET);
-        const bool need_scan = vm && t_masks_pre(mx, m, pl);
+        const bool need_scan = vm && ((ROLE == ROLE_MASKS) ? t_masks_pre_inl(mx, m, pl) : t_masks_pre(mx, m, pl));
         if (m_lane) S.scan_pid[gm] = static_cast<uint8_t>(mx.g.players_go());
         if (need_scan) atomicOr(&S.scan_need, 1u << gm);
         if (!LISTED && warp == 0) CATAN_MARK(10);
@@ -633,7 +664,7 @@ encode_kernel(const __grid_constant__ EnvParams P) {
         CATAN_MASK_SYNC();
         if (!LISTED && warp == 0) CATAN_MARK(11);
         if (vm) {
-          if (pl.post) t_masks_post(mx, m, pl, S.scan[gm]);
+          if (pl.post) { if (ROLE == ROLE_MASKS) t_masks_post_inl(mx, m, pl, S.scan[gm]); else t_masks_post(mx, m, pl, S.scan[gm]); }
           {
             MaskFlat F;
             t_flatten_masks(m, F);
@@ -646,7 +677,8 @@ encode_kernel(const __grid_constant__ EnvParams P) {
             for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(mx.g.res(ap, r) != 0) << r;
             const uint32_t decision = mx.g.decision_ctr();
             hv.decision_ctr() = decision + 1;
-            t_sample_action(m, hand, P.seed, mx.env_id, decision, P.actions_out + static_cast<size_t>(im) * CATAN_ACTION_WORDS);
+            if (ROLE == ROLE_MASKS) t_sample_action_inl(m, hand, P.seed, mx.env_id, decision, P.actions_out + static_cast<size_t>(im) * CATAN_ACTION_WORDS);
+            else t_sample_action(m, hand, P.seed, mx.env_id, decision, P.actions_out + static_cast<size_t>(im) * CATAN_ACTION_WORDS);
           }
         }
         if (!LISTED) CATAN_MARK(12);
@@ -671,12 +703,22 @@ encode_kernel(const __grid_constant__ EnvParams P) {
       cx.T = &S.topo.topo; cx.X = &S.topo.topox; cx.cfg = &P.cfg; cx.seed = P.seed; cx.env_id = P.first_env_id + static_cast<uint64_t>(i);
       if (valid) {
         cx.s = load_seats(cx.g);
-        const int r = ROLE == ROLE_ROWS ? warp : warp - kMaskWarps;  // tile part r, then player part r (the last row warp: the lists too)
         uint8_t* row = P.obs + static_cast<size_t>(i) * CATAN_OBS_STRIDE;
-        t_encode_obs_part(cx, row, r);
-        if (!LISTED) CATAN_MARK(13);
-        t_encode_obs_part(cx, row, CATAN_OBS_TILE_PARTS + r);
-        if (r == kRowWarps - 1) t_encode_obs_part(cx, row, CATAN_OBS_PARTS - 1);
+        if constexpr (ROLE == ROLE_ROWS) {                           // a balanced share of the row's pieces (rows_tile_lo)
+          int lo = 0, hi = 0;
+#pragma unroll
+          for (int w = 0; w < kRowsWarps; ++w) if (w == warp) { lo = 16 * rows_tile_lo(w); hi = 16 * rows_tile_lo(w + 1); }
+          if (hi > lo) t_encode_obs_tiles_inl(cx, row, lo, hi);
+          CATAN_MARK(13);
+          if (warp < 4) t_encode_obs_part(cx, row, CATAN_OBS_TILE_PARTS + warp);
+          if (warp == (kRowsWarps > 4 ? 4 : 3)) t_encode_obs_part(cx, row, CATAN_OBS_PARTS - 1);
+        } else {
+          const int r = warp - kMaskWarps;                           // tile part r, then player part r (the last row warp: the lists too)
+          t_encode_obs_part(cx, row, r);
+          if (!LISTED) CATAN_MARK(13);
+          t_encode_obs_part(cx, row, CATAN_OBS_TILE_PARTS + r);
+          if (r == kRowWarps - 1) t_encode_obs_part(cx, row, CATAN_OBS_PARTS - 1);
+        }
       }
       if (!LISTED) CATAN_MARK(14);
     }
@@ -775,14 +817,16 @@ struct catan_env {
   // catan_set_graphs: every distinct step call (entry point + buffer pointers) is captured once into a CUDA graph on an internal
   // stream and replayed on the caller's stream afterwards: one driver call per step instead of ~20 (9 launches, 6 event calls, copies)
   bool trans_direct = true;           // transition_kernel<DIRECT> (see there)
+  bool rows_beside = false;           // the rows launch of a step on the library's rows stream, beside the masks launch
   bool use_graphs = false;
   cudaStream_t capture_stream = nullptr;
   struct StepGraph { int kind; const void* p[4]; cudaGraphExec_t exec; };
   std::vector<StepGraph> graphs;
   bool timing = false;
-  cudaEvent_t tev[32][4] = {};        // [0] transition [1] rows [3] masks + sampler [2]
+  cudaEvent_t tev[32][8] = {};        // [0] transition [1] rows [3] masks + sampler [2]; search stream: [1] wait [4] search [5] rest [6]; reset stream: .. [7]
   unsigned long long timed = 0;        // steps recorded since timing was switched on
-  double t_ms[3] = {0.0, 0.0, 0.0};    // transition, encode (rows + masks), rows alone: summed over the steps already retired from the ring
+  double t_ms[8] = {};                 // transition, encode (rows + masks), rows alone, [3] fork -> search starts, [4] search, [5] the rest of
+                                       // the search stream, [6] fork -> end of the reset stream, [7] fork -> the step's last join: summed over the steps already retired from the ring
   unsigned long long t_n = 0;
 };
 
@@ -836,15 +880,15 @@ static int launch_encode(catan_env* env, EnvParams P, int first, int count, cuda
     // Two launches of 4-warp blocks, side by side: the observation rows on the library's rows stream (forked at ev_fork, joined by
     // the caller), masks + sampler on the caller's stream.  With the timing hooks on they run one after the other on the caller's
     // stream, an event between them, so that each is measured alone.
-    cudaStream_t rs = tev ? stream : env->rows_stream;
-    if (!tev) CATAN_CUDA(cudaStreamWaitEvent(rs, env->ev_fork, 0));
+    cudaStream_t rs = (tev || !env->rows_beside) ? stream : env->rows_stream;
+    if (rs != stream) CATAN_CUDA(cudaStreamWaitEvent(rs, env->ev_fork, 0));
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, false, catanb::ROLE_ROWS>, game_blocks(first, count),
-                                         catanb::kEncThreads / 2, catanb::enc_smem_bytes(catanb::ROLE_ROWS), rs, P));
+                                         catanb::kRowsThreads, catanb::enc_smem_bytes(catanb::ROLE_ROWS), rs, P));
     if (tev) CATAN_CUDA(cudaEventRecord(tev[3], stream));
-    else CATAN_CUDA(cudaEventRecord(env->ev_join_rows, rs));
+    if (rs != stream) CATAN_CUDA(cudaEventRecord(env->ev_join_rows, rs));
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, false, catanb::ROLE_MASKS>, game_blocks(first, count),
-                                         catanb::kEncThreads / 2, catanb::enc_smem_bytes(catanb::ROLE_MASKS), stream, P));
-    if (!tev) CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join_rows, 0));
+                                         catanb::kMasksThreads, catanb::enc_smem_bytes(catanb::ROLE_MASKS), stream, P));
+    if (rs != stream) CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join_rows, 0));
   } else {
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<MODE, false, false, catanb::ROLE_BOTH>,
                                          game_blocks(first, count), catanb::kEncThreads, sizeof(catanb::EncSmem), stream, P));
@@ -863,6 +907,15 @@ static int retire_timed_step(catan_env* env, cudaEvent_t* ev) {     // one ring 
   CATAN_CUDA(cudaEventElapsedTime(&b, ev[1], ev[2]));
   CATAN_CUDA(cudaEventElapsedTime(&c, ev[1], ev[3]));
   env->t_ms[0] += a; env->t_ms[1] += b; env->t_ms[2] += c; env->t_n += 1;
+  CATAN_CUDA(cudaEventSynchronize(ev[6]));
+  CATAN_CUDA(cudaEventSynchronize(ev[7]));
+  float d = 0.f;
+  CATAN_CUDA(cudaEventElapsedTime(&d, ev[1], ev[4])); env->t_ms[3] += d;
+  CATAN_CUDA(cudaEventElapsedTime(&d, ev[4], ev[5])); env->t_ms[4] += d;
+  CATAN_CUDA(cudaEventElapsedTime(&d, ev[5], ev[6])); env->t_ms[5] += d;
+  CATAN_CUDA(cudaEventElapsedTime(&d, ev[1], ev[7])); env->t_ms[6] += d;
+  { float e6 = 0.f, e7 = 0.f; CATAN_CUDA(cudaEventElapsedTime(&e6, ev[1], ev[6])); CATAN_CUDA(cudaEventElapsedTime(&e7, ev[1], ev[7]));
+    env->t_ms[7] += fmaxf(fmaxf(e6, e7), b); }
   return 0;
 }
 
@@ -885,14 +938,17 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   {   // the searched games: search -> encode on the staging copies (8 games of the queue per block) -> home
     EnvParams L = P;
     L.list_queue = env->lr_slow_queue; L.list_stage = env->stage; L.list_count = &env->lr_ctl->slow_count; L.list_group = 8;
+    if (tev) CATAN_CUDA(cudaEventRecord(tev[4], env->lr_stream));
     catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), env->lr_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
+    if (tev) CATAN_CUDA(cudaEventRecord(tev[5], env->lr_stream));
     catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true, catanb::ROLE_BOTH><<<env->sm_count, catanb::kEncThreads, sizeof(catanb::EncSmem), env->lr_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
     catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->lr_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
     catanb::lr_finish_kernel<<<1, 1, 0, env->lr_stream>>>(env->lr_ctl);
     CATAN_CUDA(cudaGetLastError());
+    if (tev) CATAN_CUDA(cudaEventRecord(tev[6], env->lr_stream));
     CATAN_CUDA(cudaEventRecord(env->ev_join, env->lr_stream));
   }
   {   // the games that ended: done / reward -> reset -> encode of the new game, ONE game per block (the reset is serial)
@@ -904,6 +960,7 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
     CATAN_CUDA(cudaGetLastError());
     catanb::rs_finish_kernel<<<1, 1, 0, env->rs_stream>>>(env->lr_ctl);
     CATAN_CUDA(cudaGetLastError());
+    if (tev) CATAN_CUDA(cudaEventRecord(tev[7], env->rs_stream));
     CATAN_CUDA(cudaEventRecord(env->ev_join_rs, env->rs_stream));
   }
   if (launch_encode<catanb::MODE_STEP, SAMPLE>(env, P, 0, env->n, stream, tev)) return -1;
@@ -1063,6 +1120,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
 #undef CATAN_ENC_ATTR
   }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::transition_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  env->rows_beside = getenv("CATAN_ROWS_BESIDE") != nullptr && atoi(getenv("CATAN_ROWS_BESIDE")) != 0;   // (measured: 0.300 ms per step beside, 0.279 in front)
   env->trans_direct = !(getenv("CATAN_TRANS_DIRECT") != nullptr && atoi(getenv("CATAN_TRANS_DIRECT")) == 0);   // (0: stage whole chunks)
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::lr_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::LrSmem)));
   if (e != cudaSuccess) {
@@ -1328,7 +1386,7 @@ int catan_set_timing(catan_env_t* env, int enable) {
   CATAN_CUDA(cudaDeviceSynchronize());
   if (enable)
     for (auto& slot : env->tev) for (cudaEvent_t& ev : slot) if (!ev) CATAN_CUDA(cudaEventCreate(&ev));
-  env->timing = enable != 0; env->timed = 0; env->t_ms[0] = env->t_ms[1] = env->t_ms[2] = 0.0; env->t_n = 0;
+  env->timing = enable != 0; env->timed = 0; for (double& x : env->t_ms) x = 0.0; env->t_n = 0;
   return 0;
 }
 
@@ -1339,6 +1397,7 @@ int catan_read_timing(catan_env_t* env, double* out_host) {
   for (unsigned long long k = env->timed - pending; k < env->timed; ++k) if (retire_timed_step(env, env->tev[k % 32])) return -1;
   env->timed = 0;                                                    // (the ring is empty again)
   out_host[0] = static_cast<double>(env->t_n); out_host[1] = env->t_ms[0]; out_host[2] = env->t_ms[1]; out_host[3] = env->t_ms[2];
+  for (int k = 3; k < 8; ++k) out_host[1 + k] = env->t_ms[k];
   return 0;
 }
 

@@ -191,9 +191,11 @@ class VecCatanEnv:
     def read_timing(self, detail: bool = False):
         """(steps timed, average ms of transition_kernel, average ms of the two encode launches) since set_timing(True);
         ``detail``: a fourth entry, the average ms of the observation-rows launch alone"""
-        out = np.zeros(4, dtype=np.float64)
+        out = np.zeros(9, dtype=np.float64)
         _lib.check(self.lib.catan_read_timing(self._h, C.c_void_p(out.ctypes.data)))
         n = max(1.0, out[0])
+        self.stream_timing = {"search_wait": out[4] / n, "search": out[5] / n, "search_rest": out[6] / n, "reset_stream": out[7] / n,
+                              "after_transition": out[8] / n}     # (average ms per step, see catan_read_timing)
         return (int(out[0]), out[1] / n, out[2] / n) + ((out[3] / n,) if detail else ())
 
     def err_flags(self, clear: bool = False) -> np.ndarray:

@@ -186,7 +186,8 @@ def test_cuda_randomise_uncertainty_matches_the_game_core_and_conserves():
         emu = EmuEnv(seed=12, env_id=77 + int(e), auto_reset=0)
         emu.import_state(before[e])
         emu.randomise_uncertainty(int(c[e]), 300)
-        assert np.array_equal(emu.state(), after[e]), e
+        from tests.common import state_diff
+        assert np.array_equal(emu.state(), after[e]), (e, int(c[e]), state_diff(emu.state(), after[e])[:8])
     # the bound rows were refreshed
     o = env.obs.cpu().numpy()
     e = int(idx[0])
