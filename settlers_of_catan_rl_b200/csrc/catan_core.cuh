@@ -196,6 +196,20 @@ CATAN_FN_NOINLINE void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+// word `idx` of the same block, returned in a register: a caller that wants ONE word has no output array on its stack (the
+// address of such an array, handed to the called function, defeats the compiler's stack-slot lifetime analysis -- on the device
+// Game.randomise_uncertainty's hand totals were overwritten by the four words)
+CATAN_FN_NOINLINE uint32_t philox4x32_word(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, int idx) {
+  CATAN_NO_UNROLL
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return idx == 0 ? c0 : idx == 1 ? c1 : idx == 2 ? c2 : c3;
+}
 
 
 // ------------------------------------------------------------------------------------------------

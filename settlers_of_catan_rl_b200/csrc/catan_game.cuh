@@ -257,10 +257,8 @@ CATAN_FN void t_prod_add(const GameView& g, const Topo& T, int p, int c, int w) 
 CATAN_FN uint32_t t_rng_next(TCx& cx) {   // next word of the game stream
   const uint32_t d = cx.g.rng_ctr();
   cx.g.rng_ctr() = d + 1;
-  uint32_t w[4];
-  philox4x32(d >> 2, CATAN_STREAM_GAME, static_cast<uint32_t>(cx.env_id), static_cast<uint32_t>(cx.env_id >> 32),
-             static_cast<uint32_t>(cx.seed), static_cast<uint32_t>(cx.seed >> 32), w);
-  return w[d & 3];
+  return philox4x32_word(d >> 2, CATAN_STREAM_GAME, static_cast<uint32_t>(cx.env_id), static_cast<uint32_t>(cx.env_id >> 32),
+                         static_cast<uint32_t>(cx.seed), static_cast<uint32_t>(cx.seed >> 32), static_cast<int>(d & 3));
 }
 CATAN_FN int t_rng_bounded(TCx& cx, int n) { return static_cast<int>(mulhi32(t_rng_next(cx), static_cast<uint32_t>(n))); }
 
@@ -1014,6 +1012,14 @@ CATAN_FN_NOINLINE int t_randomise_uncertainty(TCx& cx, int c, int max_attempts) 
     unacc[k] = 19 - acc;
   }
   uint8_t list[96], prop[4][5];
+#ifdef CATAN_DEBUG_RANDOMISE
+  if (cx.env_id == CATAN_DEBUG_RANDOMISE) {
+    printf("DBG c %d before %d %d %d %d unacc %d %d %d %d %d ctr %u\n", c, before[0], before[1], before[2], before[3], unacc[0], unacc[1], unacc[2], unacc[3], unacc[4], (unsigned)g.rng_ctr());
+    for (int q = 1; q <= 4; ++q) if (q != c) printf("DBG q %d label %d min %d %d %d %d %d max %d %d %d %d %d\n", q, label_of(cx.s, c, q),
+      (int)g.est_min(c - 1, label_of(cx.s, c, q), 0), (int)g.est_min(c - 1, label_of(cx.s, c, q), 1), (int)g.est_min(c - 1, label_of(cx.s, c, q), 2), (int)g.est_min(c - 1, label_of(cx.s, c, q), 3), (int)g.est_min(c - 1, label_of(cx.s, c, q), 4),
+      (int)g.est_max(c - 1, label_of(cx.s, c, q), 0), (int)g.est_max(c - 1, label_of(cx.s, c, q), 1), (int)g.est_max(c - 1, label_of(cx.s, c, q), 2), (int)g.est_max(c - 1, label_of(cx.s, c, q), 3), (int)g.est_max(c - 1, label_of(cx.s, c, q), 4));
+  }
+#endif
   for (int attempt = 1; attempt <= max_attempts; ++attempt) {
     for (int p = 0; p < 4; ++p) for (int r = 0; r < 5; ++r) prop[p][r] = g.res(p, r);
     int len = 0;
@@ -1027,6 +1033,9 @@ CATAN_FN_NOINLINE int t_randomise_uncertainty(TCx& cx, int c, int max_attempts) 
         const int q = keys[k];
         if (q == c) continue;
         const int tot = prop[q - 1][0] + prop[q - 1][1] + prop[q - 1][2] + prop[q - 1][3] + prop[q - 1][4];
+#ifdef CATAN_DEBUG_RANDOMISE
+        if (cx.env_id == CATAN_DEBUG_RANDOMISE) printf("DBG att %d len %d r %d k %d q %d tot %d before %d max %d prop %d\n", attempt, len, r, k, q, tot, before[q - 1], (int)g.est_max(c - 1, label_of(cx.s, c, q), r), (int)prop[q - 1][r]);
+#endif
         if (tot < before[q - 1] && g.est_max(c - 1, label_of(cx.s, c, q), r) > prop[q - 1][r]) { prop[q - 1][r] += 1; break; }
       }
     }
