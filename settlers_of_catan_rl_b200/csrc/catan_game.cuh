@@ -1882,21 +1882,42 @@ CATAN_FN void img_or(PartImg& P, uint64_t b0, uint64_t b1, uint64_t b2) {
   else if constexpr (SH > 0) { P.w0 |= b0 << SH; P.w1 |= (b1 << SH) | (b0 >> (64 - SH)); P.w2 |= (b2 << SH) | (b1 >> (64 - SH)); }
   else { P.w0 |= (b0 >> -SH) | (b1 << (64 + SH)); P.w1 |= (b1 >> -SH) | (b2 << (64 + SH)); P.w2 |= b2 >> -SH; }
 }
-// the pieces [0, NP) of a part -> row + lo
-template <int NP>
-CATAN_FN void img_store(const PartImg& P, uint8_t* dst) {
-  struct alignas(16) V16 { uint32_t a, b, c, d; };
-  static_for<0, NP>([&](auto I) {
-    constexpr int i = decltype(I)::value;
-    const uint64_t w = i < 4 ? P.w0 : (i < 8 ? P.w1 : P.w2);
-    const uint32_t b16 = static_cast<uint32_t>(w >> (16 * (i & 3))) & 0xffffu;
-    const V16 v = {spread4(b16 & 15u) | P.pw[4 * i], spread4((b16 >> 4) & 15u) | P.pw[4 * i + 1], spread4((b16 >> 8) & 15u) | P.pw[4 * i + 2],
-                   spread4(b16 >> 12) | P.pw[4 * i + 3]};
+// two adjacent 16-byte pieces of a row (dst 32-byte aligned) in ONE store: every lane of a row warp writes to its own row, so a
+// store instruction costs one L1 wavefront per lane whatever its width -- the 256-bit form halves the wavefronts per byte
+struct alignas(16) ObsPiece { uint32_t a, b, c, d; };
+// WIDE: the 256-bit form (rows launch of a step only).  In a CALLED function nvcc 12.9 lowered the same statement to a 32-bit store
+// of the first word (caught by the golden replay), so every other path writes the pair as two 128-bit stores.
+template <bool WIDE>
+CATAN_FN void obs_store32(uint8_t* dst, const ObsPiece& x, const ObsPiece& y) {
 #ifdef CATAN_DEVICE
-    __stcs(reinterpret_cast<uint4*>(dst + 16 * i), make_uint4(v.a, v.b, v.c, v.d));    // streamed: rows are not re-read here
+  if constexpr (WIDE) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(dst), "r"(x.a), "r"(x.b), "r"(x.c), "r"(x.d),
+                 "r"(y.a), "r"(y.b), "r"(y.c), "r"(y.d) : "memory");                      // streamed: rows are not re-read here
+  } else {
+    __stcs(reinterpret_cast<uint4*>(dst), make_uint4(x.a, x.b, x.c, x.d));
+    __stcs(reinterpret_cast<uint4*>(dst + 16), make_uint4(y.a, y.b, y.c, y.d));
+  }
 #else
-    *reinterpret_cast<V16*>(dst + 16 * i) = v;
+  *reinterpret_cast<ObsPiece*>(dst) = x;
+  *reinterpret_cast<ObsPiece*>(dst + 16) = y;
 #endif
+}
+// the pieces [0, NP) of a part -> row + lo (NP even, the part 32-byte aligned)
+template <int NP, bool WIDE>
+CATAN_FN void img_store(const PartImg& P, uint8_t* dst) {
+  static_assert(NP % 2 == 0, "pieces leave in pairs");
+  static_for<0, NP / 2>([&](auto I) {
+    constexpr int i0 = 2 * decltype(I)::value;
+    ObsPiece v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = i0 + h;
+      const uint64_t w = i < 4 ? P.w0 : (i < 8 ? P.w1 : P.w2);
+      const uint32_t b16 = static_cast<uint32_t>(w >> (16 * (i & 3))) & 0xffffu;
+      v[h] = ObsPiece{spread4(b16 & 15u) | P.pw[4 * i], spread4((b16 >> 4) & 15u) | P.pw[4 * i + 1], spread4((b16 >> 8) & 15u) | P.pw[4 * i + 2],
+                      spread4(b16 >> 12) | P.pw[4 * i + 3]};
+    }
+    obs_store32<WIDE>(dst + 16 * i0, v[0], v[1]);
   });
 }
 
@@ -2032,6 +2053,7 @@ CATAN_FN uint64_t t_tile_bits(const GameView& g, const Topo& T, int t, int robbe
   return static_cast<uint64_t>(w0) | (static_cast<uint64_t>(w1) << 32);
 }
 
+template <bool WIDE>
 CATAN_FN void t_encode_obs_tiles_inl(const TCx& cx_, uint8_t* row, int lo, int hi) {
   TCx cx = cx_;   // (a private copy: the address-space hints below then hold for every access, whatever the stores in between)
   CATAN_STAGED_ENCODE(cx);
@@ -2061,47 +2083,44 @@ CATAN_FN void t_encode_obs_tiles_inl(const TCx& cx_, uint8_t* row, int lo, int h
     fill = CATAN_OBS_TILE_DIM - skip;
     ++t;
   }
-  struct alignas(16) V16 { uint32_t a, b, c, d; };
+  // (lo and hi are multiples of 32: two 16-byte pieces per iteration, one 32-byte store)
   CATAN_NO_UNROLL
   while (pos < hi) {
-    if (fill < 16) {                                                 // (t < 19 here: the region ends inside tile 18)
+    if (fill < 32) {                                                 // (t < 19 here: the region ends inside tile 18)
       const uint64_t m = t_tile_bits(g, T, t, robber, relpack);
       ++t;
       acc_lo |= m << fill;
       acc_hi = fill > 4 ? m >> (64 - fill) : 0ull;
       fill += CATAN_OBS_TILE_DIM;
     }
-    const uint32_t b16 = static_cast<uint32_t>(acc_lo) & 0xffffu;
-    V16 v = {spread4(b16 & 15u), spread4((b16 >> 4) & 15u), spread4((b16 >> 8) & 15u), spread4(b16 >> 12)};
-    if (pos == 0) v.d |= hand012;                                    // bytes 13..15 = CATAN_OBS_CURRENT_RES + 1 + r
-    if (pos == 16) v.a |= hand34;                                    // bytes 16, 17
-#ifdef CATAN_DEVICE
-    __stcs(reinterpret_cast<uint4*>(row + pos), make_uint4(v.a, v.b, v.c, v.d));
-#else
-    *reinterpret_cast<V16*>(row + pos) = v;
-#endif
-    acc_lo = (acc_lo >> 16) | (acc_hi << 48);
-    acc_hi >>= 16;
-    fill -= 16;
-    pos += 16;
+    const uint32_t b32 = static_cast<uint32_t>(acc_lo);
+    ObsPiece v0 = {spread4(b32 & 15u), spread4((b32 >> 4) & 15u), spread4((b32 >> 8) & 15u), spread4((b32 >> 12) & 15u)};
+    ObsPiece v1 = {spread4((b32 >> 16) & 15u), spread4((b32 >> 20) & 15u), spread4((b32 >> 24) & 15u), spread4(b32 >> 28)};
+    if (pos == 0) { v0.d |= hand012; v1.a |= hand34; }               // bytes 13..15 = CATAN_OBS_CURRENT_RES + 1 + r, then bytes 16, 17
+    obs_store32<WIDE>(row + pos, v0, v1);
+    acc_lo = (acc_lo >> 32) | (acc_hi << 32);
+    acc_hi >>= 32;
+    fill -= 32;
+    pos += 32;
   }
 }
 // (the called form: the kernels that hold several phases keep their code small; the rows launch of a step inlines it -- a call
 // forces the context through local memory, which misses the small L1 these kernels leave beside their shared memory)
-CATAN_FN_NOINLINE void t_encode_obs_tiles(const TCx& cx, uint8_t* row, int lo, int hi) { t_encode_obs_tiles_inl(cx, row, lo, hi); }
+CATAN_FN_NOINLINE void t_encode_obs_tiles(const TCx& cx, uint8_t* row, int lo, int hi) { t_encode_obs_tiles_inl<false>(cx, row, lo, hi); }
 static_assert(CATAN_OBS_PROPOSED_TRADE == 0 && CATAN_OBS_CURRENT_RES == 12 && CATAN_OBS_TILES == 18 && CATAN_OBS_TILE_DIM == 60,
               "t_encode_obs_tiles packs the header by hand");
 
-// The cuts used by the device encoder: CATAN_OBS_PARTS threads share one row.  Parts 0 .. CATAN_OBS_TILE_PARTS-1 lie in
+// The cuts used by the device encoder (multiples of 32 bytes: obs_store32): CATAN_OBS_PARTS threads share one row.  Parts 0 .. CATAN_OBS_TILE_PARTS-1 lie in
 // the header + tile region (t_encode_obs_tiles); parts 4-7 hold one player block each (plus the few bytes of its neighbours
 // that share its first / last 16-byte piece), part 8 the card lists and the meta bytes.
 #define CATAN_OBS_PARTS 9
 #define CATAN_OBS_TILE_PARTS 4
 #define CATAN_OBS_TILE_END 1152
 CATAN_FN int t_obs_part_lo(int part) {
-  return part == 0 ? 0 : part == 1 ? 304 : part == 2 ? 592 : part == 3 ? 880 : part == 4 ? CATAN_OBS_TILE_END : part == 5 ? 1312 :
+  return part == 0 ? 0 : part == 1 ? 288 : part == 2 ? 576 : part == 3 ? 864 : part == 4 ? CATAN_OBS_TILE_END : part == 5 ? 1312 :
          part == 6 ? 1472 : part == 7 ? 1632 : part == 8 ? 1792 : CATAN_OBS_STRIDE;
 }
+template <bool WIDE>
 CATAN_FN void t_encode_obs_players(const TCx& cx, uint8_t* row, int part) {
   const ObsCtx C = t_obs_ctx(cx);
   PartImg P = {};
@@ -2112,28 +2131,28 @@ CATAN_FN void t_encode_obs_players(const TCx& cx, uint8_t* row, int part) {
       P.w0 = t_tile_bits(cx.g, *cx.T, 18, cx.g.robber_tile(), C.relpack) >> (lo - (CATAN_OBS_TILES + 18 * CATAN_OBS_TILE_DIM));
       t_current_block<CATAN_OBS_CUR_MAIN - lo>(cx, C, P);
       t_other_block_head<1, OTH - lo>(cx, C, P);
-      img_store<10>(P, row + lo);
+      img_store<10, WIDE>(P, row + lo);
       break;
     }
     case 5: {
       constexpr int lo = 1312;
       t_other_block<1, OTH - lo>(cx, C, P);
       t_other_block_head<2, OTH + OD - lo>(cx, C, P);
-      img_store<10>(P, row + lo);
+      img_store<10, WIDE>(P, row + lo);
       break;
     }
     case 6: {
       constexpr int lo = 1472;
       t_other_block<2, OTH + OD - lo>(cx, C, P);
       t_other_block_head<3, OTH + 2 * OD - lo>(cx, C, P);
-      img_store<10>(P, row + lo);
+      img_store<10, WIDE>(P, row + lo);
       break;
     }
     case 7: {                                                        // ... and the first 5 cards of the actor's played list
       constexpr int lo = 1632;
       t_other_block<3, OTH + 2 * OD - lo>(cx, C, P);
       t_put_list<0, LISTS - lo, 0, 2>(cx, C, P);
-      img_store<10>(P, row + lo);
+      img_store<10, WIDE>(P, row + lo);
       break;
     }
     default: {                                                       // [1792, 1920): the card lists and the meta bytes
@@ -2146,7 +2165,7 @@ CATAN_FN void t_encode_obs_players(const TCx& cx, uint8_t* row, int part) {
       P.pw[(CATAN_OBS_META - lo) / 4] = static_cast<uint32_t>(C.actor) | (static_cast<uint32_t>(n0) << 8) | (static_cast<uint32_t>(n1) << 16) |
                                         (static_cast<uint32_t>(n2) << 24);
       P.pw[(CATAN_OBS_META - lo) / 4 + 1] = static_cast<uint32_t>(n3) | (static_cast<uint32_t>(n4) << 8);
-      img_store<8>(P, row + lo);
+      img_store<8, WIDE>(P, row + lo);
       break;
     }
   }
@@ -2154,9 +2173,10 @@ CATAN_FN void t_encode_obs_players(const TCx& cx, uint8_t* row, int part) {
 static_assert(CATAN_OBS_CUR_MAIN == 1158 && CATAN_OBS_OTHER_MAIN == 1310 && CATAN_OBS_OTHER_MAIN_DIM == 159 && CATAN_OBS_DEV_LISTS == 1787 &&
               CATAN_OBS_META == 1912 && CATAN_OBS_STRIDE == 1920 && CATAN_OBS_DEV_PAD == 25, "the part cuts assume this row layout");
 
+template <bool WIDE = false>
 CATAN_FN void t_encode_obs_part(const TCx& cx, uint8_t* row, int part) {
   if (part < CATAN_OBS_TILE_PARTS) t_encode_obs_tiles(cx, row, t_obs_part_lo(part), t_obs_part_lo(part + 1));
-  else t_encode_obs_players(cx, row, part);
+  else t_encode_obs_players<WIDE>(cx, row, part);
 }
 
 }  // namespace catanb

@@ -59,7 +59,7 @@ constexpr int kRowWarps = CATAN_OBS_TILE_PARTS;  // encode_kernel: warps that wr
 constexpr int kEncWarps = 2 * kRowWarps;         // ... and as many that share the per-game scalar work (done / reward, masks, sampler)
 constexpr int kEncThreads = kEncWarps * 32;
 constexpr int kMaskWarps = kEncWarps - kRowWarps;
-// the rows launch of a step (ROLE_ROWS): its own number of warps, each with a balanced share of the row's 120 16-byte pieces
+// the rows launch of a step (ROLE_ROWS): its own number of warps, each with a balanced share of the row's 60 32-byte pairs of pieces
 #ifndef CATAN_ROWS_WARPS
 #define CATAN_ROWS_WARPS 4
 #endif
@@ -69,16 +69,16 @@ constexpr int kMaskWarps = kEncWarps - kRowWarps;
 constexpr int kRowsWarps = CATAN_ROWS_WARPS, kRowsThreads = kRowsWarps * 32;
 constexpr int kMasksThreads = kMaskWarps * 32;
 static_assert(kRowsWarps >= 4 && kRowsWarps <= 8, "warps 0-3 of the rows launch own the four player blocks");
-// Warp w of the rows launch writes the player part 4 + w (w < 4: 10 pieces) or the card lists (w == min(4, kRowsWarps - 1): 8 pieces) and the
-// tile pieces [rows_tile_lo(w), rows_tile_lo(w + 1)) of the 72 pieces of the header + tile region, so that every warp has about
-// 120 / kRowsWarps pieces.
-__host__ __device__ constexpr int rows_fixed_pieces(int w) { return (w < 4 ? 10 : 0) + (w == (kRowsWarps > 4 ? 4 : 3) ? 8 : 0); }
+// Warp w of the rows launch writes the player part 4 + w (w < 4: five 32-byte pairs of pieces) or the card lists (w == min(4, kRowsWarps - 1):
+// four pairs) and the pairs [rows_tile_lo(w), rows_tile_lo(w + 1)) of the 36 pairs of the header + tile region, so that every warp
+// has about 60 / kRowsWarps pairs.
+__host__ __device__ constexpr int rows_fixed_pairs(int w) { return (w < 4 ? 5 : 0) + (w == (kRowsWarps > 4 ? 4 : 3) ? 4 : 0); }
 __host__ __device__ constexpr int rows_tile_lo(int w) {
-  // greedy: hand out the 72 tile pieces one by one to the warp with the fewest pieces so far (ties: the highest warp)
+  // greedy: hand out the 36 tile pairs one by one to the warp with the fewest pairs so far (ties: the highest warp)
   int have[12] = {0};
-  for (int k = 0; k < kRowsWarps; ++k) have[k] = rows_fixed_pieces(k);
+  for (int k = 0; k < kRowsWarps; ++k) have[k] = rows_fixed_pairs(k);
   int tiles[12] = {0};
-  for (int n = 0; n < 72; ++n) {
+  for (int n = 0; n < 36; ++n) {
     int best = kRowsWarps - 1;
     for (int k = kRowsWarps - 1; k >= 0; --k) if (have[k] < have[best]) best = k;
     have[best] += 1; tiles[best] += 1;
@@ -87,7 +87,7 @@ __host__ __device__ constexpr int rows_tile_lo(int w) {
   for (int k = 0; k < w; ++k) lo += tiles[k];
   return lo;
 }
-static_assert(rows_tile_lo(0) == 0 && rows_tile_lo(kRowsWarps) == 72, "the tile pieces are covered exactly once");
+static_assert(rows_tile_lo(0) == 0 && rows_tile_lo(kRowsWarps) == 36, "the tile pairs are covered exactly once");
 static_assert(CATAN_OBS_PARTS == 2 * CATAN_OBS_TILE_PARTS + 1, "row warp r writes tile part r and player part r; the last one also the lists");
 constexpr int kCopyThreads = 128;           // lr_copy_back_kernel: one warp per game
 constexpr int kLrSlowThreads = 512;         // lr_slow_kernel: one block per update that needs a search
@@ -707,11 +707,11 @@ encode_kernel(const __grid_constant__ EnvParams P) {
         if constexpr (ROLE == ROLE_ROWS) {                           // a balanced share of the row's pieces (rows_tile_lo)
           int lo = 0, hi = 0;
 #pragma unroll
-          for (int w = 0; w < kRowsWarps; ++w) if (w == warp) { lo = 16 * rows_tile_lo(w); hi = 16 * rows_tile_lo(w + 1); }
-          if (hi > lo) t_encode_obs_tiles_inl(cx, row, lo, hi);
+          for (int w = 0; w < kRowsWarps; ++w) if (w == warp) { lo = 32 * rows_tile_lo(w); hi = 32 * rows_tile_lo(w + 1); }
+          if (hi > lo) t_encode_obs_tiles_inl<true>(cx, row, lo, hi);
           CATAN_MARK(13);
-          if (warp < 4) t_encode_obs_part(cx, row, CATAN_OBS_TILE_PARTS + warp);
-          if (warp == (kRowsWarps > 4 ? 4 : 3)) t_encode_obs_part(cx, row, CATAN_OBS_PARTS - 1);
+          if (warp < 4) t_encode_obs_part<true>(cx, row, CATAN_OBS_TILE_PARTS + warp);
+          if (warp == (kRowsWarps > 4 ? 4 : 3)) t_encode_obs_part<true>(cx, row, CATAN_OBS_PARTS - 1);
         } else {
           const int r = warp - kMaskWarps;                           // tile part r, then player part r (the last row warp: the lists too)
           t_encode_obs_part(cx, row, r);
