@@ -538,9 +538,8 @@ def run_b200_arm(args):
                                                "achieved": TRANSITION_BYTES_PER_ENV_STEP * n / (transition_ms * 1e-3) / 1e9},
                          "whole_step": {"ms": per_launch_ms, "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * n,
                                         "achieved": step_achieved, "frac": step_achieved / peak,
-                                        "note": "10 launches on 4 streams, replayed as one CUDA graph: transition, masks + sampler | observation rows | longest-road "
-                                                "search, encode of the searched games, copy-back, counters | encode (done / reset / new game) of the games that "
-                                                "ended, copy-back, counters"}},
+                                        "note": "6 launches on 3 streams, replayed as one CUDA graph: transition, observation rows, masks + sampler | longest-road "
+                                                "search, encode of the searched games | encode (done / reset / new game) of the games that ended"}},
             "cpu_baseline": cpu_baseline,
             "cpu_baseline_port": cpu_baseline_port,
             "aux": aux,

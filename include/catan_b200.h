@@ -120,6 +120,9 @@ int catan_read_err_flags(catan_env_t* env, uint32_t* flags_host, int clear);
  * enumerations (stored length not trusted); [3] = search tasks created; [4], [5] = GPU cycles per search, sum and max;
  * [6], [7] = walk steps per search, sum and max.  Synchronous. */
 int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host);
+/* Three log2 histograms of 24 bins each (bin b counts values in [2^b, 2^(b+1))), since construction: GPU cycles of a block-wide
+ * search, walk steps of a search, GPU cycles of the LONGEST search of a step (what the step waits for).  out_host: 72 words.  Synchronous. */
+int catan_read_lr_histograms(catan_env_t* env, unsigned long long* out_host);
 
 /* Device-side timing of a step's two kernels on the caller's stream (CUDA events recorded by catan_step*): enable,
  * step, then read out_host[0] = steps timed, [1] = summed ms of transition_kernel, [2] = summed ms of the two encode launches
@@ -222,7 +225,7 @@ int catan_masked_categorical(const float* logits_dev, const float* mask_dev, con
  * observation / mask rows are refreshed.  An env whose beliefs admit no deal within max_attempts (the reference would loop forever)
  * gets bit CATAN_ERR_NO_DEAL in its sticky error word; its hands are then left at the minimum beliefs. */
 /* CUDA-graph replay of the step calls: with enable != 0, catan_step / catan_step_masked / catan_step_sample and the two *_host_async
- * calls capture their work (9 launches on three streams, event calls, copies) ONCE per distinct set of buffer pointers and replay it
+ * calls capture their work (6 launches on three streams, event calls, copies) ONCE per distinct set of buffer pointers and replay it
  * with one cudaGraphLaunch on the caller's stream afterwards.  Off by default; a call made while the caller's stream is itself being
  * captured (e.g. inside torch.cuda.graph) is issued directly and becomes part of that graph.  Host buffers must be pinned. */
 int catan_set_graphs(catan_env_t* env, int enable);

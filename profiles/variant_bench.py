@@ -18,3 +18,6 @@ for _ in range(200): env.step_sample(a)
 _, tr, en, rows = env.read_timing(detail=True)
 print("%s: %.4f ms/step  transition %.4f  encode %.4f (rows %.4f, masks %.4f)  errs %d" % (os.environ.get("CATAN_B200_LIB", "default"), e0.elapsed_time(e1) / ticks, tr, en, rows, en - rows, int(env.err_flags().any())))
 print("   streams (ms from the end of the transition):", {k: round(v, 4) for k, v in env.stream_timing.items()})
+h = env.lr_histograms()
+for name, row in zip(("cycles per search", "walk steps per search", "cycles of a step's longest search"), h):
+    print("   log2 histogram,", name + ":", {int(b): int(c) for b, c in enumerate(row) if c})

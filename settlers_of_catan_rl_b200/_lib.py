@@ -79,6 +79,7 @@ ABI = {
     "catan_read_err_flags": (C.c_int, [_vp, _vp, C.c_int]),
     "catan_randomise_uncertainty": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "catan_read_lr_stats": (C.c_int, [_vp, _vp]),
+    "catan_read_lr_histograms": (C.c_int, [_vp, _vp]),
     "catan_set_graphs": (C.c_int, [_vp, C.c_int]),
     "catan_set_timing": (C.c_int, [_vp, C.c_int]),
     "catan_read_timing": (C.c_int, [_vp, _vp]),

@@ -21,7 +21,8 @@
 //                        length cannot be trusted, the reference's full enumeration (game.py:843-862) -- as a pool of
 //                        16-byte subtree tasks that the lanes drain and re-split without barriers (lp_pool).
 //   encode_kernel<LISTED> the same encode for the queued games, on their staging chunks
-//   lr_copy_back_kernel  staging -> home records (+ lr_finish_kernel: one thread banks and clears the queue counters)
+//                        (each block copies its games from the staging chunk to their home records at the end, and the last
+//                        block of the launch banks and clears the queue counters: queue_block_done)
 //
 // Why the search is not inside a thread-per-game kernel: its cost varies by four orders of magnitude between games and
 // would stall 31 other games per unit of imbalance; why it runs on a second stream: it is latency-bound (a few hundred
@@ -89,18 +90,20 @@ __host__ __device__ constexpr int rows_tile_lo(int w) {
 }
 static_assert(rows_tile_lo(0) == 0 && rows_tile_lo(kRowsWarps) == 36, "the tile pairs are covered exactly once");
 static_assert(CATAN_OBS_PARTS == 2 * CATAN_OBS_TILE_PARTS + 1, "row warp r writes tile part r and player part r; the last one also the lists");
-constexpr int kCopyThreads = 128;           // lr_copy_back_kernel: one warp per game
 constexpr int kLrSlowThreads = 512;         // lr_slow_kernel: one block per update that needs a search
 constexpr int kLrSlowBlocksPerSM = 2;
 constexpr int kSampleThreads = 128;         // stand-alone sampler kernel
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_REFRESH = 2 };
 
-struct LrCtl {                // per-step queue counters; lr_finish_kernel banks them into the totals and clears them
+struct LrCtl {                // per-step queue counters; queue_finish() banks them into the totals and clears them
   int32_t count, slow_count;  // longest-road updates of this step; those that went to lr_slow_kernel (= length of its queue)
   int32_t rs_count, pad_;     // games that ended in this step and are reset on their own stream (= length of rs_queue)
+  int32_t blocks_done[2];     // blocks of the two queues' encode launches that are through: the last one banks and clears its queue's counters
   unsigned long long total, slow_total, rs_total;   // the same, summed over all earlier steps
   unsigned long long dbg[6];  // lr_slow_kernel diagnostics: cycles sum / max, walk steps sum / max per search; full enumerations; tasks
+  unsigned long long hist[3][24];   // log2 histograms: cycles of a search, walk steps of a search, cycles of the LONGEST search of a step
+  unsigned long long step_max;      // (longest search of the current step; banked into hist[2] by queue_finish)
 };
 
 struct EnvParams {
@@ -109,6 +112,7 @@ struct EnvParams {
   int n_envs;
   uint64_t seed, first_env_id;
   catan_config_t cfg;
+  int list_kind;               // LISTED encode: 0 = the searched games (lr queue), 1 = the games that ended (reset queue)
   const int32_t* actions;      // transition input
   int32_t* actions_out;        // fused sampler output (may alias `actions`), or nullptr
   uint8_t* obs;
@@ -197,12 +201,6 @@ __device__ __forceinline__ void copy_game(const GameView& src, const GameView& d
   for (int q = 0; q < (nb + 31) / 32; ++q) if (lane + 32 * q < nb) dst.raw<uint8_t>(b0 + lane + 32 * q) = c[q];
   if (lane < 3) dst.raw<uint32_t>(static_cast<int>(offsetof(GameRec, rng_ctr)) + 4 * lane) = w;
   if (lane < 2) dst.raw<uint16_t>(static_cast<int>(offsetof(GameRec, actions_this_turn)) + 2 * lane) = v;
-}
-__global__ void __launch_bounds__(kCopyThreads) lr_copy_back_kernel(const __grid_constant__ EnvParams P) {
-  const int count = *P.list_count;
-  const int lane = threadIdx.x & 31, warps = static_cast<int>(gridDim.x) * (kCopyThreads / 32);
-  for (int j = static_cast<int>(blockIdx.x) * (kCopyThreads / 32) + (threadIdx.x >> 5); j < count; j += warps)
-    copy_game(game_view(P.list_stage, static_cast<size_t>(j)), game_view(P.recs, static_cast<uint32_t>(P.list_queue[j])), lane);
 }
 
 // ---- 1. transition ------------------------------------------------------------------------------
@@ -474,19 +472,35 @@ __global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_co
       atomicAdd(&P.lr_ctl->dbg[0], dt); atomicMax(&P.lr_ctl->dbg[1], dt);
       atomicAdd(&P.lr_ctl->dbg[2], static_cast<unsigned long long>(S.steps)); atomicMax(&P.lr_ctl->dbg[3], static_cast<unsigned long long>(S.steps));
       if (was_full) atomicAdd(&P.lr_ctl->dbg[4], 1ull);
+      atomicAdd(&P.lr_ctl->hist[0][min(23, 63 - __clzll(static_cast<long long>(dt | 1ull)))], 1ull);
+      atomicAdd(&P.lr_ctl->hist[1][min(23, 31 - __clz(S.steps | 1))], 1ull);
+      atomicMax(&P.lr_ctl->step_max, dt);
       atomicAdd(&P.lr_ctl->dbg[5], static_cast<unsigned long long>(S.tasks));
     }
   }
 }
 
-// last launch of a step on the library's stream: every consumer of the queue counters has run
-__global__ void lr_finish_kernel(LrCtl* c) {
-  c->total += static_cast<unsigned long long>(c->count); c->slow_total += static_cast<unsigned long long>(c->slow_count);
-  c->count = 0; c->slow_count = 0;
+// by the LAST block of a queue's encode launch (every consumer of the queue counters has run): bank and clear them
+__device__ __forceinline__ void queue_finish(LrCtl* c, int kind) {
+  if (kind == 0) {
+    c->total += static_cast<unsigned long long>(c->count); c->slow_total += static_cast<unsigned long long>(c->slow_count);
+    c->count = 0; c->slow_count = 0;
+    if (c->step_max) { c->hist[2][min(23, 63 - __clzll(static_cast<long long>(c->step_max)))] += 1ull; c->step_max = 0ull; }
+  } else {
+    c->rs_total += static_cast<unsigned long long>(c->rs_count);
+    c->rs_count = 0;
+  }
 }
-__global__ void rs_finish_kernel(LrCtl* c) {   // the same for the reset queue, last launch of its stream
-  c->rs_total += static_cast<unsigned long long>(c->rs_count);
-  c->rs_count = 0;
+__device__ __forceinline__ void queue_block_done(LrCtl* c, int kind, int tid) {   // all threads of a block of a LISTED encode launch, at its end
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&c->blocks_done[kind], 1) == static_cast<int>(gridDim.x) - 1) {
+      __threadfence();
+      queue_finish(c, kind);
+      c->blocks_done[kind] = 0;
+    }
+  }
 }
 
 // ---- 3. finish + masks + sampler + observation --------------------------------------------------
@@ -536,7 +550,7 @@ encode_kernel(const __grid_constant__ EnvParams P) {
   CATAN_MARK_BEGIN();
   const int list_count = LISTED ? *P.list_count : 0;
   const int G = LISTED ? P.list_group : 32;                          // games per block iteration: LISTED blocks take a WINDOW of a staging chunk
-  if (LISTED && static_cast<int>(blockIdx.x) * G >= list_count) return;
+  if (LISTED && static_cast<int>(blockIdx.x) * G >= list_count) { queue_block_done(P.lr_ctl, P.list_kind, tid); return; }
 #define CATAN_ENC_HOME(l0_) ((LISTED ? P.list_stage : P.recs) + static_cast<size_t>((LISTED ? (l0_) : (P.range_first & ~31) + (l0_)) >> 5) * CATAN_CHUNK_BYTES)
   if (tid == 0) {                                                    // the first chunk is on its way while the topology is staged
     S.reset_need = 0; S.scan_need = 0; S.scan_pid_done = 0;          // (made visible by the barrier of stage_topology)
@@ -597,7 +611,7 @@ encode_kernel(const __grid_constant__ EnvParams P) {
             StepTmp tmp;
             tmp.err = static_cast<uint8_t>(sd); tmp.acted_pid = static_cast<uint8_t>(sd >> 8); tmp.act_type = static_cast<uint8_t>(sd >> 16);
             tmp.roll_info = static_cast<uint8_t>((sd >> 24) & 0x7f);
-            need_reset = (ROLE == ROLE_MASKS) ? t_step_finish_inl(mx, tmp, P.reward + static_cast<size_t>(im) * 4, info)
+            need_reset = (ROLE == ROLE_MASKS || LISTED) ? t_step_finish_inl(mx, tmp, P.reward + static_cast<size_t>(im) * 4, info)
                                               : t_step_finish(mx, tmp, P.reward + static_cast<size_t>(im) * 4, info);
             hv.episode_steps() = mx.g.episode_steps(); hv.winner() = mx.g.winner();   // what done / reward changed (wrapper.py:85-112)
 #pragma unroll
@@ -644,7 +658,7 @@ encode_kernel(const __grid_constant__ EnvParams P) {
         pl.post = 0;
         if (vm) mx.s = load_seats(mx.g);
         if (MODE != MODE_STEP && vm) t_write_info_fresh(mx.g, info, MODE == MODE_RESET);
-        const bool need_scan = vm && ((ROLE == ROLE_MASKS) ? t_masks_pre_inl(mx, m, pl) : t_masks_pre(mx, m, pl));
+        const bool need_scan = vm && ((ROLE == ROLE_MASKS || LISTED) ? t_masks_pre_inl(mx, m, pl) : t_masks_pre(mx, m, pl));
         if (m_lane) S.scan_pid[gm] = static_cast<uint8_t>(mx.g.players_go());
         if (need_scan) atomicOr(&S.scan_need, 1u << gm);
         if (!LISTED && warp == 0) CATAN_MARK(10);
@@ -664,7 +678,7 @@ encode_kernel(const __grid_constant__ EnvParams P) {
         CATAN_MASK_SYNC();
         if (!LISTED && warp == 0) CATAN_MARK(11);
         if (vm) {
-          if (pl.post) { if (ROLE == ROLE_MASKS) t_masks_post_inl(mx, m, pl, S.scan[gm]); else t_masks_post(mx, m, pl, S.scan[gm]); }
+          if (pl.post) { if (ROLE == ROLE_MASKS || LISTED) t_masks_post_inl(mx, m, pl, S.scan[gm]); else t_masks_post(mx, m, pl, S.scan[gm]); }
           {
             MaskFlat F;
             t_flatten_masks(m, F);
@@ -677,7 +691,7 @@ encode_kernel(const __grid_constant__ EnvParams P) {
             for (int r = 0; r < 5; ++r) hand |= static_cast<uint32_t>(mx.g.res(ap, r) != 0) << r;
             const uint32_t decision = mx.g.decision_ctr();
             hv.decision_ctr() = decision + 1;
-            if (ROLE == ROLE_MASKS) t_sample_action_inl(m, hand, P.seed, mx.env_id, decision, P.actions_out + static_cast<size_t>(im) * CATAN_ACTION_WORDS);
+            if (ROLE == ROLE_MASKS || LISTED) t_sample_action_inl(m, hand, P.seed, mx.env_id, decision, P.actions_out + static_cast<size_t>(im) * CATAN_ACTION_WORDS);
             else t_sample_action(m, hand, P.seed, mx.env_id, decision, P.actions_out + static_cast<size_t>(im) * CATAN_ACTION_WORDS);
           }
         }
@@ -714,7 +728,8 @@ encode_kernel(const __grid_constant__ EnvParams P) {
           if (warp == (kRowsWarps > 4 ? 4 : 3)) t_encode_obs_part<true>(cx, row, CATAN_OBS_PARTS - 1);
         } else {
           const int r = warp - kMaskWarps;                           // tile part r, then player part r (the last row warp: the lists too)
-          t_encode_obs_part(cx, row, r);
+          if (LISTED) t_encode_obs_tiles_inl<false>(cx, row, t_obs_part_lo(r), t_obs_part_lo(r + 1));   // (few blocks, latency matters: inlined)
+          else t_encode_obs_part(cx, row, r);
           if (!LISTED) CATAN_MARK(13);
           t_encode_obs_part(cx, row, CATAN_OBS_TILE_PARTS + r);
           if (r == kRowWarps - 1) t_encode_obs_part(cx, row, CATAN_OBS_PARTS - 1);
@@ -733,14 +748,19 @@ encode_kernel(const __grid_constant__ EnvParams P) {
                   if (S.reset_need) atomicAdd(&d_phase[41], 1ull); }
     }
 #endif
-    if (LISTED) {                                                    // the scratch and the flags are reused by the next 32 games
-      __syncthreads();
-      if (tid == 0) { S.reset_need = 0; S.scan_need = 0; }
+    if (LISTED) {
+      __syncthreads();                                               // the block's changes to the staging copies are all written
+      for (int b = warp; b < 32; b += kWarps) {                      // staging -> home records, one warp per game
+        const int vb = __shfl_sync(0xffffffffu, static_cast<int>(valid), b), ib = __shfl_sync(0xffffffffu, i, b);
+        if (vb) copy_game(GameView{home, b}, game_view(P.recs, static_cast<size_t>(ib)), lane);
+      }
+      if (tid == 0) { S.reset_need = 0; S.scan_need = 0; }           // the scratch and the flags are reused by the next 32 games
       __syncthreads();
     }
 #undef CATAN_VIEW_OF
   }
 #undef CATAN_ENC_HOME
+  if (LISTED) queue_block_done(P.lr_ctl, P.list_kind, tid);
 }
 
 // Game.randomise_uncertainty (game.py:1207-1282) for every env whose byte in `controlling` is a PlayerId: one thread per game on
@@ -937,28 +957,20 @@ static int launch_step(catan_env* env, EnvParams P, cudaStream_t stream) {
   CATAN_CUDA(cudaStreamWaitEvent(env->rs_stream, env->ev_fork, 0));
   {   // the searched games: search -> encode on the staging copies (8 games of the queue per block) -> home
     EnvParams L = P;
-    L.list_queue = env->lr_slow_queue; L.list_stage = env->stage; L.list_count = &env->lr_ctl->slow_count; L.list_group = 8;
+    L.list_queue = env->lr_slow_queue; L.list_stage = env->stage; L.list_count = &env->lr_ctl->slow_count; L.list_group = 8; L.list_kind = 0;
     if (tev) CATAN_CUDA(cudaEventRecord(tev[4], env->lr_stream));
     catanb::lr_slow_kernel<<<env->lr_grid, catanb::kLrSlowThreads, sizeof(catanb::LrSmem), env->lr_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
     if (tev) CATAN_CUDA(cudaEventRecord(tev[5], env->lr_stream));
     catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true, catanb::ROLE_BOTH><<<env->sm_count, catanb::kEncThreads, sizeof(catanb::EncSmem), env->lr_stream>>>(L);
     CATAN_CUDA(cudaGetLastError());
-    catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->lr_stream>>>(L);
-    CATAN_CUDA(cudaGetLastError());
-    catanb::lr_finish_kernel<<<1, 1, 0, env->lr_stream>>>(env->lr_ctl);
-    CATAN_CUDA(cudaGetLastError());
     if (tev) CATAN_CUDA(cudaEventRecord(tev[6], env->lr_stream));
     CATAN_CUDA(cudaEventRecord(env->ev_join, env->lr_stream));
   }
   {   // the games that ended: done / reward -> reset -> encode of the new game, ONE game per block (the reset is serial)
     EnvParams L = P;
-    L.list_queue = env->rs_queue; L.list_stage = env->stage_rs; L.list_count = &env->lr_ctl->rs_count; L.list_group = 1;
+    L.list_queue = env->rs_queue; L.list_stage = env->stage_rs; L.list_count = &env->lr_ctl->rs_count; L.list_group = 1; L.list_kind = 1;
     catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, true, catanb::ROLE_BOTH><<<env->sm_count * 2, catanb::kEncThreads, sizeof(catanb::EncSmem), env->rs_stream>>>(L);
-    CATAN_CUDA(cudaGetLastError());
-    catanb::lr_copy_back_kernel<<<env->sm_count, catanb::kCopyThreads, 0, env->rs_stream>>>(L);
-    CATAN_CUDA(cudaGetLastError());
-    catanb::rs_finish_kernel<<<1, 1, 0, env->rs_stream>>>(env->lr_ctl);
     CATAN_CUDA(cudaGetLastError());
     if (tev) CATAN_CUDA(cudaEventRecord(tev[7], env->rs_stream));
     CATAN_CUDA(cudaEventRecord(env->ev_join_rs, env->rs_stream));
@@ -1369,6 +1381,16 @@ int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
   out_host[0] = last.total; out_host[1] = last.slow_total;
   out_host[2] = last.dbg[4]; out_host[3] = last.dbg[5];
   for (int i = 0; i < 4; ++i) out_host[4 + i] = last.dbg[i];
+  return 0;
+}
+
+int catan_read_lr_histograms(catan_env_t* env, unsigned long long* out_host) {
+  if (!env || !out_host) return fail("null argument");
+  if (device_guard(env)) return -1;
+  catanb::LrCtl last;
+  CATAN_CUDA(cudaDeviceSynchronize());
+  CATAN_CUDA(cudaMemcpy(&last, env->lr_ctl, sizeof(last), cudaMemcpyDeviceToHost));
+  memcpy(out_host, last.hist, sizeof(last.hist));
   return 0;
 }
 

@@ -17,9 +17,9 @@ import torch
 from . import _lib, layout as L
 
 
-#: launches of one step: transition, encode of the masks + sampler (caller's stream) | encode of the rows (library stream 0) | longest-road search, encode of the searched games, copy-back, counter
-#: bookkeeping (library stream 1) | encode of the games that ended and were reset, copy-back, counter bookkeeping (library stream 2)
-LAUNCHES_PER_STEP = 10
+#: launches of one step: transition, encode of the rows, encode of the masks + sampler (caller's stream) | longest-road search, encode of the
+#: searched games (library stream 1) | encode of the games that ended and were reset (library stream 2)
+LAUNCHES_PER_STEP = 6
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -178,6 +178,12 @@ class VecCatanEnv:
         walk steps sum, max] since construction"""
         out = np.zeros(8, dtype=np.uint64)
         _lib.check(self.lib.catan_read_lr_stats(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def lr_histograms(self) -> np.ndarray:
+        """catan_read_lr_histograms: [3, 24] log2 histograms (cycles per search, walk steps per search, cycles of a step's longest search)"""
+        out = np.zeros((3, 24), dtype=np.uint64)
+        _lib.check(self.lib.catan_read_lr_histograms(self._h, C.c_void_p(out.ctypes.data)))
         return out
 
     def set_graphs(self, enable: bool) -> None:
