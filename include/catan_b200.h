@@ -213,7 +213,9 @@ int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* mask_rows_de
  *   inverse CDF of uniforms_dev[b] in [0, 1)   when uniforms_dev != NULL (sample; never an illegal entry),
  *   the first maximum                          otherwise (mode, deterministic=True).
  * logp_dev[b] = log p(action), entropy_dev[b] (may be NULL) = -sum p log p over p > 0.  Forward only: the PPO update, which
- * differentiates through log_probs and entropy, keeps the reference's torch distribution. */
+ * differentiates through log_probs and entropy, keeps the reference's torch distribution.
+ * The mask is BINARY: an entry != 0 keeps its logit (the reference adds log(mask), RL/distributions.py:36-38, which is the same
+ * for the 0 / 1 masks EnvWrapper.get_action_masks produces); a given action outside [0, D) yields log-prob -inf. */
 int catan_masked_categorical(const float* logits_dev, const float* mask_dev, const int64_t* given_actions_dev,
                              const float* uniforms_dev, int B, int D, int64_t* actions_dev, float* logp_dev,
                              float* entropy_dev, void* stream);

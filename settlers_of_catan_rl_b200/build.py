@@ -12,7 +12,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SO = os.path.join(CSRC, "libcatan_b200.so")
 SOURCES = ("catan_kernels.cu", "ppo_kernels.cu", "policy_kernels.cu")
-HEADERS = ("catan_core.cuh", "catan_game.cuh", os.path.join("..", "..", "include", "catan_b200.h"),
+HEADERS = ("catan_core.cuh", "catan_game.cuh", "device_scope.cuh", os.path.join("..", "..", "include", "catan_b200.h"),
            os.path.join("..", "..", "include", "catan_layout.h"), os.path.join("..", "..", "include", "catan_topology.h"))
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-shared", "-cudart", "static"]

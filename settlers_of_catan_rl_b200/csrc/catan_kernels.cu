@@ -29,6 +29,8 @@
 // dependent walk steps) and touches 0.3 % of the games, so it hides completely behind the encode of the others.
 #include <cuda_runtime.h>
 
+#include "device_scope.cuh"
+
 #include <cstddef>
 #include <cstdlib>
 #include <new>
@@ -850,12 +852,10 @@ struct catan_env {
   unsigned long long t_n = 0;
 };
 
-static int device_guard(const catan_env* env) {
-  int cur = -1;
-  CATAN_CUDA(cudaGetDevice(&cur));
-  if (cur != env->device) CATAN_CUDA(cudaSetDevice(env->device));
-  return 0;
-}
+// the handle's device for the rest of the calling function; the caller's current device comes back when it returns
+#define CATAN_ON_DEVICE_OF(env_)                                              \
+  catanb::DeviceScope device_scope_;                                          \
+  if (device_scope_.enter((env_)->device)) return fail("cannot make the handle's device current")
 
 static EnvParams make_params(const catan_env* env) {
   EnvParams P{};
@@ -1071,7 +1071,8 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) return fail("no CUDA device available: this library has no CPU path");
   if (device < 0 || device >= count) return fail("bad device index");
-  CATAN_CUDA(cudaSetDevice(device));
+  catanb::DeviceScope device_scope_;                                 // (the caller's current device comes back on return)
+  if (device_scope_.enter(device)) return fail("cannot make the device current");
   catan_env* env = new (std::nothrow) catan_env();
   if (!env) return fail("out of host memory");
   env->n = n_envs; env->device = device; env->seed = seed; env->first_env_id = first_env_id;
@@ -1171,7 +1172,7 @@ int catan_bind(catan_env_t* env, uint8_t* obs_dev, uint8_t* masks_dev, float* re
 
 int catan_reset(catan_env_t* env, const uint8_t* reset_mask_dev, void* stream) {
   if (check_bound(env)) return -1;
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   EnvParams P = make_params(env);
   P.env_mask = reset_mask_dev;
   return launch_encode<catanb::MODE_RESET, false>(env, P, 0, env->n, static_cast<cudaStream_t>(stream));
@@ -1182,7 +1183,7 @@ int catan_step(catan_env_t* env, const int32_t* actions_dev, void* stream) { ret
 int catan_step_masked(catan_env_t* env, const int32_t* actions_dev, const uint8_t* step_mask_dev, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_dev) return fail("actions_dev is null");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   EnvParams P = make_params(env);
   P.actions = actions_dev;
   P.env_mask = step_mask_dev;
@@ -1194,7 +1195,7 @@ int catan_step_masked(catan_env_t* env, const int32_t* actions_dev, const uint8_
 int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_io_dev) return fail("actions_io_dev is null");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   EnvParams P = make_params(env);
   P.actions = actions_io_dev;
   P.actions_out = actions_io_dev;
@@ -1206,7 +1207,7 @@ int catan_step_sample(catan_env_t* env, int32_t* actions_io_dev, void* stream) {
 int catan_sample_random(catan_env_t* env, int32_t* actions_out_dev, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_out_dev) return fail("actions_out_dev is null");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   const int blocks = (env->n + catanb::kSampleThreads - 1) / catanb::kSampleThreads;
   catanb::sample_kernel<<<blocks, catanb::kSampleThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       env->recs, env->n, env->seed, env->first_env_id, env->masks, env->obs, actions_out_dev);
@@ -1232,7 +1233,7 @@ int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t
                           uint8_t* info_host, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_host) return fail("actions_host is null");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   auto issue = [&](cudaStream_t s) -> int {
     CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_host, sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(env->n),
                                cudaMemcpyHostToDevice, s));
@@ -1252,7 +1253,7 @@ int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t
 int catan_step_sample_host_async(catan_env_t* env, int32_t* actions_io_host, float* reward_host, uint8_t* info_host, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_io_host) return fail("actions_io_host is null");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   const size_t bytes = sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(env->n);
   auto issue = [&](cudaStream_t s) -> int {
     CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_io_host, bytes, cudaMemcpyHostToDevice, s));
@@ -1273,8 +1274,11 @@ int catan_step_sample_host_groups(catan_env_t* const* envs, int n_groups, int32_
   long long seen = 0;
   for (int r = 0; r < rounds; ++r) {
     for (int g = 0; g < n_groups; ++g) {
-      if (check_bound(envs[g]) || device_guard(envs[g])) return -1;
-      CATAN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(streams[g])));
+      if (check_bound(envs[g])) return -1;
+      {
+        CATAN_ON_DEVICE_OF(envs[g]);
+        CATAN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(streams[g])));
+      }
       if (info_host[g]) {
         const uint8_t* info = info_host[g];
         const int n = envs[g]->n;
@@ -1291,7 +1295,7 @@ int catan_step_host(catan_env_t* env, const int32_t* actions_host, uint8_t* obs_
                     uint8_t* info_host, void* stream) {
   if (check_bound(env)) return -1;
   if (!actions_host) return fail("actions_host is null");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CATAN_CUDA(cudaMemcpyAsync(env->actions_stage, actions_host, sizeof(int32_t) * CATAN_ACTION_WORDS * static_cast<size_t>(env->n),
                              cudaMemcpyHostToDevice, s));
@@ -1316,7 +1320,7 @@ int catan_export_state(catan_env_t* env, int first, int count, int16_t* states_h
   if (!env || !states_host) return fail("null argument");
   if (first < 0 || count < 0 || first + count > env->n) return fail("env range out of bounds");
   if (count == 0) return 0;
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   size_t off, bytes;
   if (chunk_range(env, first, count, off, bytes)) return -1;
   std::vector<uint8_t> tmp(bytes);
@@ -1338,7 +1342,7 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
   if (!states_host) return fail("null argument");
   if (first < 0 || count < 0 || first + count > env->n) return fail("env range out of bounds");
   if (count == 0) return 0;
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   size_t off, bytes;
   if (chunk_range(env, first, count, off, bytes)) return -1;
   std::vector<uint8_t> tmp(bytes);
@@ -1364,7 +1368,7 @@ int catan_import_state(catan_env_t* env, int first, int count, const int16_t* st
 int catan_randomise_uncertainty(catan_env_t* env, const uint8_t* controlling_pid_dev, int max_attempts, void* stream) {
   if (check_bound(env)) return -1;
   if (!controlling_pid_dev || max_attempts <= 0) return fail("catan_randomise_uncertainty: bad argument");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   EnvParams P = make_params(env);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   catanb::randomise_kernel<<<(env->n + 127) / 128, 128, 0, s>>>(P, controlling_pid_dev, max_attempts);
@@ -1374,7 +1378,7 @@ int catan_randomise_uncertainty(catan_env_t* env, const uint8_t* controlling_pid
 
 int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
   if (!env || !out_host) return fail("null argument");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   catanb::LrCtl last;
   CATAN_CUDA(cudaDeviceSynchronize());
   CATAN_CUDA(cudaMemcpy(&last, env->lr_ctl, sizeof(last), cudaMemcpyDeviceToHost));
@@ -1386,7 +1390,7 @@ int catan_read_lr_stats(catan_env_t* env, unsigned long long* out_host) {
 
 int catan_read_lr_histograms(catan_env_t* env, unsigned long long* out_host) {
   if (!env || !out_host) return fail("null argument");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   catanb::LrCtl last;
   CATAN_CUDA(cudaDeviceSynchronize());
   CATAN_CUDA(cudaMemcpy(&last, env->lr_ctl, sizeof(last), cudaMemcpyDeviceToHost));
@@ -1396,7 +1400,7 @@ int catan_read_lr_histograms(catan_env_t* env, unsigned long long* out_host) {
 
 int catan_set_graphs(catan_env_t* env, int enable) {
   if (!env) return fail("null handle");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   env->use_graphs = enable != 0;
   if (!enable) { CATAN_CUDA(cudaDeviceSynchronize()); drop_graphs(env); }
   return 0;
@@ -1404,7 +1408,7 @@ int catan_set_graphs(catan_env_t* env, int enable) {
 
 int catan_set_timing(catan_env_t* env, int enable) {
   if (!env) return fail("null handle");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   CATAN_CUDA(cudaDeviceSynchronize());
   if (enable)
     for (auto& slot : env->tev) for (cudaEvent_t& ev : slot) if (!ev) CATAN_CUDA(cudaEventCreate(&ev));
@@ -1414,7 +1418,7 @@ int catan_set_timing(catan_env_t* env, int enable) {
 
 int catan_read_timing(catan_env_t* env, double* out_host) {
   if (!env || !out_host) return fail("null argument");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   const unsigned long long pending = env->timed < 32 ? env->timed : 32;
   for (unsigned long long k = env->timed - pending; k < env->timed; ++k) if (retire_timed_step(env, env->tev[k % 32])) return -1;
   env->timed = 0;                                                    // (the ring is empty again)
@@ -1433,7 +1437,7 @@ int catan_debug_read_phases(unsigned long long* out64_host, int clear) {
 
 int catan_read_err_flags(catan_env_t* env, uint32_t* flags_host, int clear) {
   if (!env || !flags_host) return fail("null argument");
-  if (device_guard(env)) return -1;
+  CATAN_ON_DEVICE_OF(env);
   CATAN_CUDA(cudaDeviceSynchronize());
   CATAN_CUDA(cudaMemcpy(flags_host, env->err_flags, sizeof(uint32_t) * static_cast<size_t>(env->n), cudaMemcpyDeviceToHost));
   if (clear) CATAN_CUDA(cudaMemset(env->err_flags, 0, sizeof(uint32_t) * static_cast<size_t>(env->n)));

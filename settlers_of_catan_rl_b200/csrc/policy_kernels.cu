@@ -13,6 +13,8 @@
 // torch.  The PyTorch side (settlers_of_catan_rl_b200/policy_ops.py) wraps them as autograd functions.
 #include <cuda_runtime.h>
 
+#include "device_scope.cuh"
+
 #include <stdint.h>
 #include <cstdio>
 
@@ -266,6 +268,8 @@ static int pol_fail(cudaError_t e, const char* what) {
 extern "C" int catan_tile_attention_fwd(const float* qkv_dev, float* y_dev, int B, void* stream) {
   if (!qkv_dev || !y_dev || B <= 0) return pol_fail(cudaErrorInvalidValue, "catan_tile_attention_fwd: bad argument");
   if ((reinterpret_cast<uintptr_t>(qkv_dev) | reinterpret_cast<uintptr_t>(y_dev)) & 15) return pol_fail(cudaErrorInvalidValue, "catan_tile_attention_fwd: buffers must be 16-byte aligned");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(qkv_dev, static_cast<cudaStream_t>(stream))) return pol_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   cudaError_t e0 = cudaFuncSetAttribute(catanb::tile_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::AttSmemF)));
   if (e0 != cudaSuccess) return pol_fail(e0, "catan_tile_attention_fwd");
   const int blocks = (B + catanb::kAttSamples - 1) / catanb::kAttSamples;
@@ -278,6 +282,8 @@ extern "C" int catan_tile_attention_bwd(const float* qkv_dev, const float* dy_de
   if (!qkv_dev || !dy_dev || !dqkv_dev || B <= 0) return pol_fail(cudaErrorInvalidValue, "catan_tile_attention_bwd: bad argument");
   if ((reinterpret_cast<uintptr_t>(qkv_dev) | reinterpret_cast<uintptr_t>(dy_dev) | reinterpret_cast<uintptr_t>(dqkv_dev)) & 15)
     return pol_fail(cudaErrorInvalidValue, "catan_tile_attention_bwd: buffers must be 16-byte aligned");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(qkv_dev, static_cast<cudaStream_t>(stream))) return pol_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   cudaError_t e = cudaFuncSetAttribute(catanb::tile_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::AttSmemB)));
   if (e != cudaSuccess) return pol_fail(e, "catan_tile_attention_bwd");
   const int blocks = (B + catanb::kAttSamplesB - 1) / catanb::kAttSamplesB;
@@ -306,6 +312,8 @@ static int launch_ln_bwd(const float* x, const float* w, const float* stats, con
 extern "C" int catan_ln_small_fwd(const float* x_dev, const float* weight_dev, const float* bias_dev, float* y_dev, float* stats_dev, long long rows,
                                   int dim, float eps, void* stream) {
   if (!x_dev || !weight_dev || !bias_dev || !y_dev || rows <= 0 || dim <= 0 || dim > 64) return pol_fail(cudaErrorInvalidValue, "catan_ln_small_fwd: bad argument (dim <= 64)");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(x_dev, static_cast<cudaStream_t>(stream))) return pol_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dim <= 16) launch_ln_fwd<4>(x_dev, weight_dev, bias_dev, y_dev, stats_dev, rows, dim, eps, s);
   else if (dim <= 32) launch_ln_fwd<8>(x_dev, weight_dev, bias_dev, y_dev, stats_dev, rows, dim, eps, s);
@@ -318,6 +326,8 @@ extern "C" int catan_ln_small_bwd(const float* x_dev, const float* weight_dev, c
                                   float* dweight_dev, float* dbias_dev, long long rows, int dim, void* stream) {
   if (!x_dev || !weight_dev || !stats_dev || !dy_dev || !dx_dev || !dweight_dev || !dbias_dev || rows <= 0 || dim <= 0 || dim > 64)
     return pol_fail(cudaErrorInvalidValue, "catan_ln_small_bwd: bad argument (dim <= 64)");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(x_dev, static_cast<cudaStream_t>(stream))) return pol_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dim <= 16) launch_ln_bwd<4>(x_dev, weight_dev, stats_dev, dy_dev, dx_dev, dweight_dev, dbias_dev, rows, dim, s);
   else if (dim <= 32) launch_ln_bwd<8>(x_dev, weight_dev, stats_dev, dy_dev, dx_dev, dweight_dev, dbias_dev, rows, dim, s);

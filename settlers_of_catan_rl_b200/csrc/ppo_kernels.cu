@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "device_scope.cuh"
+
 #include <string>
 
 #include "../../include/catan_b200.h"
@@ -333,6 +335,8 @@ extern "C" {
 int catan_gae(const float* rewards_dev, const float* values_dev, const float* masks_dev, int T, int N, double gamma,
               double gae_lambda, float* returns_dev, float* advantages_dev, void* stream) {
   if (!rewards_dev || !values_dev || !masks_dev || !returns_dev || !advantages_dev || T <= 0 || N <= 0) return ppo_fail(cudaErrorInvalidValue, "catan_gae: bad argument");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(rewards_dev, static_cast<cudaStream_t>(stream))) return ppo_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   const int threads = 256, blocks = (N + threads - 1) / threads;
   // torch multiplies fp32 tensors by Python doubles rounded to fp32; gamma*lambda is formed in double first
   catanb::gae_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -354,6 +358,9 @@ static int stream_grid(long long count) {
 
 int catan_adv_stats(const float* advantages_dev, long long count, double* stats_dev, void* stream) {
   if (!advantages_dev || !stats_dev || count <= 1) return ppo_fail(cudaErrorInvalidValue, "catan_adv_stats: bad argument");
+  if (reinterpret_cast<uintptr_t>(advantages_dev) & 15) return ppo_fail(cudaErrorInvalidValue, "catan_adv_stats: advantages must be 16-byte aligned");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(advantages_dev, static_cast<cudaStream_t>(stream))) return ppo_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(stats_dev, 0, 3 * sizeof(double), s);
   if (e != cudaSuccess) return ppo_fail(e, "catan_adv_stats memset");
@@ -364,6 +371,9 @@ int catan_adv_stats(const float* advantages_dev, long long count, double* stats_
 
 int catan_adv_apply(float* advantages_dev, long long count, const double* stats_dev, double eps, void* stream) {
   if (!advantages_dev || !stats_dev || count <= 1) return ppo_fail(cudaErrorInvalidValue, "catan_adv_apply: bad argument");
+  if (reinterpret_cast<uintptr_t>(advantages_dev) & 15) return ppo_fail(cudaErrorInvalidValue, "catan_adv_apply: advantages must be 16-byte aligned");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(advantages_dev, static_cast<cudaStream_t>(stream))) return ppo_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   catanb::adv_apply_kernel<<<stream_grid(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(advantages_dev, count, stats_dev,
                                                                                            static_cast<float>(eps));
   cudaError_t e = cudaGetLastError();
@@ -588,6 +598,8 @@ extern "C" int catan_rollout_store(const catan_rollout_t* rollout, const uint8_t
   if (!rollout || !env_obs_dev || !env_masks_dev || !env_info_dev || rollout->N <= 0 || rollout->T <= 0)
     return ppo_fail(cudaErrorInvalidValue, "catan_rollout_store: bad argument");
   if (!begin && (!env_reward_dev || !actions_dev || !logp_dev)) return ppo_fail(cudaErrorInvalidValue, "catan_rollout_store: bad argument");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(env_obs_dev, static_cast<cudaStream_t>(stream))) return ppo_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   catanb::RolloutArgs A;
   A.r = *rollout;
   A.env_obs = env_obs_dev; A.env_masks = env_masks_dev; A.env_reward = env_reward_dev; A.env_info = env_info_dev;
@@ -607,6 +619,8 @@ extern "C" int catan_minibatch_gather(const catan_rollout_t* rollout, const floa
     return ppo_fail(cudaErrorInvalidValue, "catan_minibatch_gather: null output buffer");
   if ((reinterpret_cast<uintptr_t>(out->obs) | reinterpret_cast<uintptr_t>(out->masks) | reinterpret_cast<uintptr_t>(out->actions)) & 15)
     return ppo_fail(cudaErrorInvalidValue, "catan_minibatch_gather: row buffers must be 16-byte aligned");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(values_dev, static_cast<cudaStream_t>(stream))) return ppo_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   catanb::GatherArgs A;
   A.r = *rollout; A.values = values_dev; A.returns = returns_dev; A.advantages = advantages_dev; A.indices = indices_dev; A.out = *out; A.B = B;
   catanb::minibatch_gather_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
@@ -618,6 +632,8 @@ extern "C" int catan_route_by_policy(const uint8_t* env_info_dev, const uint8_t*
                                      int n_policies, int32_t* counts_dev, int32_t* lists_dev, void* stream) {
   if (!env_info_dev || !policy_map_dev || !counts_dev || !lists_dev || N <= 0 || n_policies <= 0 || n_policies > 255)
     return ppo_fail(cudaErrorInvalidValue, "catan_route_by_policy: bad argument");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(env_info_dev, static_cast<cudaStream_t>(stream))) return ppo_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   catanb::RouteArgs A;
   A.info = env_info_dev; A.policy_map = policy_map_dev; A.active = active_dev; A.counts = counts_dev; A.lists = lists_dev; A.N = N;
   catanb::route_kernel<<<n_policies, 1024, 0, static_cast<cudaStream_t>(stream)>>>(A);
@@ -630,6 +646,8 @@ extern "C" int catan_policy_inputs(const uint8_t* obs_rows_dev, const uint8_t* m
   if (!obs_rows_dev || !features_dev || !lists_dev || B <= 0 || B > (1 << 22) || (dtype != CATAN_DTYPE_F32 && dtype != CATAN_DTYPE_BF16) ||
       (mask_rows_dev == nullptr) != (head_masks_dev == nullptr))
     return ppo_fail(cudaErrorInvalidValue, "catan_policy_inputs: bad argument");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(obs_rows_dev, static_cast<cudaStream_t>(stream))) return ppo_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   catanb::PolicyInArgs A;
   A.obs = obs_rows_dev; A.masks = mask_rows_dev; A.index = row_index_dev; A.features = features_dev; A.lists = reinterpret_cast<long long*>(lists_dev);
   A.head_masks = head_masks_dev; A.B = static_cast<unsigned>(B);
@@ -648,6 +666,8 @@ extern "C" int catan_masked_categorical(const float* logits_dev, const float* ma
                                         float* entropy_dev, void* stream) {
   if (!logits_dev || !logp_dev || B <= 0 || D <= 0 || (given_actions_dev == nullptr && actions_dev == nullptr))
     return ppo_fail(cudaErrorInvalidValue, "catan_masked_categorical: bad argument");
+  catanb::DeviceScope device_scope_;                                 // the kernel runs where its buffers live; the caller's device comes back
+  if (device_scope_.enter_for(logits_dev, static_cast<cudaStream_t>(stream))) return ppo_fail(cudaErrorInvalidDevice, "cannot make the device of the buffers current");
   catanb::CategoricalArgs A;
   A.logits = logits_dev; A.mask = mask_dev; A.given = reinterpret_cast<const long long*>(given_actions_dev); A.uniform = uniforms_dev;
   A.action = reinterpret_cast<long long*>(actions_dev); A.logp = logp_dev; A.entropy = entropy_dev; A.B = B; A.D = D;

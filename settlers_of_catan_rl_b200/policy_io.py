@@ -64,7 +64,8 @@ class PolicyInputs:
         return self._views(B, mask_rows is not None)
 
     def _views(self, B: int, with_masks: bool):
-        """the views of a batch size are built once: a call costs one launch, not two dozen tensor constructions"""
+        """the views of a batch size are built once: a call costs one launch, not two dozen tensor constructions.  The returned
+        tensors are VIEWS of this object's buffers: the next call overwrites them (clone what must outlive it)."""
         hit = self._view_cache.get((B, with_masks))
         if hit is not None:
             return hit
@@ -81,8 +82,9 @@ class PolicyInputs:
             for h, (off, shape) in enumerate(L.MASK_HEADS):
                 flat = self.head_masks[off * B:(off + int(np.prod(shape))) * B]
                 masks.append(flat.view(shape[0], B, shape[1]) if h in TYPE_CONDITIONAL_HEADS else flat.view(B, shape[0]))
-        if len(self._view_cache) < 64:
-            self._view_cache[(B, with_masks)] = (obs, masks)
+        if len(self._view_cache) >= 64:                                # (per-policy batch sizes change every tick: keep the newest)
+            self._view_cache.pop(next(iter(self._view_cache)))
+        self._view_cache[(B, with_masks)] = (obs, masks)
         return obs, masks
 
 
@@ -170,7 +172,7 @@ class FusedCategorical:
         return self._run(deterministic=True)
 
     def log_probs(self, actions: torch.Tensor) -> torch.Tensor:
-        if self._action is not None and (actions is self._action or torch.equal(actions.reshape(-1), self._action.reshape(-1))):
+        if self._action is not None and actions is self._action:      # (identity only: a value comparison would be a host sync)
             return self._logp
         return masked_categorical(self.logits, self.mask, actions=actions)[1]
 

@@ -27,6 +27,8 @@ def _check_f32_cuda(*ts: torch.Tensor) -> None:
     for t in ts:
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise _lib.CatanError("rollout kernels take contiguous fp32 CUDA tensors (no CPU path)")
+        if t.data_ptr() % 16:
+            raise _lib.CatanError("rollout kernels read 16-byte vectors: pass tensors whose storage offset keeps them 16-byte aligned")
 
 
 def gae(rewards: torch.Tensor, values: torch.Tensor, masks: torch.Tensor, gamma: float = 0.999, gae_lambda: float = 0.95,
