@@ -274,7 +274,10 @@ CATAN_FN int32_t vload_i32(const int32_t* p) { return *reinterpret_cast<const vo
 CATAN_FN uint32_t vload_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 CATAN_FN void vstore_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 CATAN_FN void group_fence() { __threadfence_block(); }
-CATAN_FN void group_idle() { __nanosleep(200); }
+#ifndef CATAN_LP_IDLE_NS
+#define CATAN_LP_IDLE_NS 200
+#endif
+CATAN_FN void group_idle() { __nanosleep(CATAN_LP_IDLE_NS); }
 #else
 CATAN_FN int32_t vload_i32(const int32_t* p) { return *p; }
 CATAN_FN uint32_t vload_u32(const uint32_t* p) { return *p; }

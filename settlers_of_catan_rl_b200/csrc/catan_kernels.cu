@@ -434,7 +434,10 @@ __device__ __forceinline__ int block_through_edge(LrSmem& S, const GameView& g, 
   return through;
 }
 
-__global__ void __launch_bounds__(kLrSlowThreads) lr_slow_kernel(const __grid_constant__ EnvParams P) {
+#ifndef CATAN_LR_MIN_BLOCKS
+#define CATAN_LR_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(kLrSlowThreads, CATAN_LR_MIN_BLOCKS) lr_slow_kernel(const __grid_constant__ EnvParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   LrSmem& S = *reinterpret_cast<LrSmem*>(smem_raw);
   const int tid = threadIdx.x;
