@@ -220,7 +220,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # this build
 # ------------------------------------------------------------------------------------------------
-def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_groups=2, barrier=None, fused_sampler=True, graphs=True):
+def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_groups=2, barrier=None, fused_sampler=True, graphs=True, packed=True):
     """The games split over n_groups handles kept in flight from the host (HostEnvGroups: own stream and pinned buffers each).  One
     library call per round (catan_step_sample_host_groups) waits for each group's previous result, reads its done flags on the host
     and issues its next step from its pinned actions."""
@@ -238,7 +238,7 @@ def e2e_double_buffered(n, steps, warm_ticks, dev, seed, rank=0, world=1, n_grou
             e.step_sample(a)
         envs.append(e)
     torch.cuda.synchronize()
-    groups = HostEnvGroups(envs)
+    groups = HostEnvGroups(envs, packed_actions=packed)
     groups.prime()
     groups.synchronize()
     groups.pump(3)
@@ -481,9 +481,10 @@ def run_b200_arm(args):
     e2e_sync = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
                 "call": "VecCatanEnv.step_host -> catan_step_host, one handle: pinned host actions in, reward+done/info rows out to "
                         "pinned host, synchronous; obs/masks stay in HBM for the GPU policy (d2h also counts the sampler's actions)"}
-    e2e_db = {"value": e2e_pipe, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps * 10,
+    e2e_db = {"value": e2e_pipe, "unit": UNIT, "h2d_bytes_per_step": n * L.ACTION_WORDS, "d2h_bytes_per_step": n * (16 + L.INFO_STRIDE) + n * L.ACTION_WORDS,
+              "steps": e2e_steps * 10, "action_rows": "uint8 [N, 20] on the host side (catan_step_sample_host_async_u8: one byte per word, expanded on the device)",
               "rejected_actions": e2e_pipe_errs, "error": e2e_pipe_error, "groups": max(1, args.e2e_groups),
-              "call": "HostEnvGroups.pump -> catan_step_sample_host_groups -> catan_step_sample_host_async per handle (the random-legal policy fused into the step as in `value`), pipelined: the games split over %d handles on their own "
+              "call": "HostEnvGroups.pump -> catan_step_sample_host_groups -> catan_step_sample_host_async_u8 per handle (the random-legal policy fused into the step as in `value`), pipelined: the games split over %d handles on their own "
                       "streams, every step of every game still takes its actions from pinned host memory and returns reward+done/info "
                       "rows (and the sampler's next actions) to pinned host memory; the host waits for one group while the others run" % args.e2e_groups}
     e2e_best, e2e_other = (e2e_db, e2e_sync) if e2e_pipe >= e2e_value else (e2e_sync, e2e_db)

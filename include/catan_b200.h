@@ -96,14 +96,22 @@ int catan_step_host_async(catan_env_t* env, const int32_t* actions_host, uint8_t
  * from the host): actions_io_host (pinned) is copied in, applied, and overwritten with every env's next random-legal action. */
 int catan_step_sample_host_async(catan_env_t* env, int32_t* actions_io_host, float* reward_host, uint8_t* info_host, void* stream);
 int catan_reset_host(catan_env_t* env, uint8_t* obs_host, uint8_t* masks_host, uint8_t* info_host, void* stream);
+/* The same call with the COMPACT host transport of action rows: one byte per word (uint8 [N, 20]; 255 stands for -1; every field of
+ * an action row -- type, corner, edge, tile, card, player, resources -- is below 128).  A host-driven loop moves 80 + 112 bytes per
+ * env step over PCIe with int32 rows and 20 + 52 with these; on an 8-GPU box the host's DMA bandwidth is what bounds such loops. */
+int catan_step_sample_host_async_u8(catan_env_t* env, uint8_t* actions_io_host_u8, float* reward_host, uint8_t* info_host, void* stream);
 /* One round of the host loop that keeps several env groups (handles) in flight -- the sub-process manager's pipelining,
  * RL/ppo/vec_gather_experience.py, without a Python round trip per group: for g = 0 .. n_groups-1, wait for group g's previous
  * step (cudaStreamSynchronize(streams[g])): its reward / info rows and next actions are then in its pinned host buffers; count the
  * `done` flags of its info rows into *done_seen (may be NULL; this is the host's read of the result); issue its next
- * catan_step_sample_host_async on streams[g].  Repeated `rounds` times.  The buffers of group g hold its last ISSUED step's
- * result once streams[g] has been synchronised by the caller. */
-int catan_step_sample_host_groups(catan_env_t* const* envs, int n_groups, int32_t* const* actions_io_host, float* const* reward_host,
-                                  uint8_t* const* info_host, void* const* streams, int rounds, long long* done_seen);
+ * catan_step_sample_host_async (action_format CATAN_ACTIONS_I32: int32 rows) or catan_step_sample_host_async_u8 (CATAN_ACTIONS_U8)
+ * on streams[g].  Repeated `rounds` times.  The buffers of group g hold its last ISSUED step's result once streams[g] has been
+ * synchronised by the caller. */
+#define CATAN_ACTIONS_I32 0
+#define CATAN_ACTIONS_U8 1
+int catan_step_sample_host_groups(catan_env_t* const* envs, int n_groups, void* const* actions_io_host, int action_format,
+                                  float* const* reward_host, uint8_t* const* info_host, void* const* streams, int rounds,
+                                  long long* done_seen);
 
 /* EnvWrapper.save_state / restore_state (env/wrapper.py:711-721; game/game.py:1013-1205) as the
  * canonical int16 state (catan_state_t) of `count` envs starting at `first`.  Host buffers;

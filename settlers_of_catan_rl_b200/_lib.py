@@ -73,7 +73,8 @@ ABI = {
     "catan_step_host_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "catan_step_sample_host_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "catan_reset_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
-    "catan_step_sample_host_groups": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_longlong)]),
+    "catan_step_sample_host_async_u8": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "catan_step_sample_host_groups": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_longlong)]),
     "catan_export_state": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "catan_import_state": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "catan_read_err_flags": (C.c_int, [_vp, _vp, C.c_int]),

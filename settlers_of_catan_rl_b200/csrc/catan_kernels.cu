@@ -783,6 +783,21 @@ __global__ void __launch_bounds__(128) randomise_kernel(const __grid_constant__ 
   if (t_randomise_uncertainty(cx, c, max_attempts) == 0) P.err_flags[e] |= 1u << CATAN_ERR_NO_DEAL;
 }
 
+// the compact host transport of action rows (catan_step_sample_host_async_u8): one byte per word, 255 = -1
+__global__ void __launch_bounds__(256) actions_unpack_kernel(const uint8_t* __restrict__ in, int32_t* __restrict__ out, int n_words) {
+  const int k = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (k >= n_words) return;                                          // (n_words is a multiple of 4: 20 words per env)
+  const uchar4 b = *reinterpret_cast<const uchar4*>(in + k);
+  *reinterpret_cast<int4*>(out + k) = make_int4(b.x == 255 ? -1 : b.x, b.y == 255 ? -1 : b.y, b.z == 255 ? -1 : b.z, b.w == 255 ? -1 : b.w);
+}
+__global__ void __launch_bounds__(256) actions_pack_kernel(const int32_t* __restrict__ in, uint8_t* __restrict__ out, int n_words) {
+  const int k = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (k >= n_words) return;
+  const int4 v = *reinterpret_cast<const int4*>(in + k);
+  auto pk = [](int x) { return static_cast<unsigned char>(x < 0 ? 255 : (x > 254 ? 254 : x)); };
+  *reinterpret_cast<uchar4*>(out + k) = make_uchar4(pk(v.x), pk(v.y), pk(v.z), pk(v.w));
+}
+
 // stand-alone sampler: one thread per env, reads the bound mask / obs rows back from global memory
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(uint8_t* recs, int n_envs, uint64_t seed, uint64_t first_env_id,
                                                                 const uint8_t* masks, const uint8_t* obs, int32_t* actions_out) {
@@ -829,6 +844,7 @@ struct catan_env {
   uint8_t* stage_rs = nullptr;        // their staging chunks
   catanb::LrCtl* lr_ctl = nullptr;
   int32_t* actions_stage = nullptr;   // device staging for catan_step_host
+  uint8_t* actions_u8_stage = nullptr;   // device staging of the one-byte-per-word host transport (allocated on first use)
   uint8_t* obs = nullptr;
   uint8_t* masks = nullptr;
   float* reward = nullptr;
@@ -1040,7 +1056,7 @@ static void free_env(catan_env* env) {
   for (auto& slot : env->tev) for (cudaEvent_t ev : slot) if (ev) cudaEventDestroy(ev);
   cudaFree(env->recs); cudaFree(env->stage); cudaFree(env->err_flags); cudaFree(env->side); cudaFree(env->lr_slow_queue); cudaFree(env->lr_ctl);
   cudaFree(env->rs_queue); cudaFree(env->stage_rs);
-  cudaFree(env->actions_stage);
+  cudaFree(env->actions_stage); cudaFree(env->actions_u8_stage);
   delete env;
 }
 
@@ -1271,8 +1287,33 @@ int catan_step_sample_host_async(catan_env_t* env, int32_t* actions_io_host, flo
   return g <= 0 ? g : issue(static_cast<cudaStream_t>(stream));
 }
 
-int catan_step_sample_host_groups(catan_env_t* const* envs, int n_groups, int32_t* const* actions_io_host, float* const* reward_host,
+int catan_step_sample_host_async_u8(catan_env_t* env, uint8_t* actions_io_host_u8, float* reward_host, uint8_t* info_host, void* stream) {
+  if (check_bound(env)) return -1;
+  if (!actions_io_host_u8) return fail("actions_io_host_u8 is null");
+  CATAN_ON_DEVICE_OF(env);
+  const int n_words = CATAN_ACTION_WORDS * env->n;
+  static_assert(CATAN_ACTION_WORDS % 4 == 0, "the pack / unpack kernels move four words per thread");
+  if (!env->actions_u8_stage) CATAN_CUDA(cudaMalloc(&env->actions_u8_stage, static_cast<size_t>(n_words)));
+  auto issue = [&](cudaStream_t s) -> int {
+    CATAN_CUDA(cudaMemcpyAsync(env->actions_u8_stage, actions_io_host_u8, static_cast<size_t>(n_words), cudaMemcpyHostToDevice, s));
+    catanb::actions_unpack_kernel<<<(n_words / 4 + 255) / 256, 256, 0, s>>>(env->actions_u8_stage, env->actions_stage, n_words);
+    CATAN_CUDA(cudaGetLastError());
+    EnvParams P = make_params(env);
+    P.actions = env->actions_stage;
+    P.actions_out = env->actions_stage;
+    if (launch_step<true>(env, P, s)) return -1;
+    catanb::actions_pack_kernel<<<(n_words / 4 + 255) / 256, 256, 0, s>>>(env->actions_stage, env->actions_u8_stage, n_words);
+    CATAN_CUDA(cudaGetLastError());
+    CATAN_CUDA(cudaMemcpyAsync(actions_io_host_u8, env->actions_u8_stage, static_cast<size_t>(n_words), cudaMemcpyDeviceToHost, s));
+    return copy_outputs_to_host(env, nullptr, nullptr, reward_host, info_host, s, false);
+  };
+  const int g = replay_step_graph(env, 5, actions_io_host_u8, reward_host, info_host, nullptr, static_cast<cudaStream_t>(stream), issue);
+  return g <= 0 ? g : issue(static_cast<cudaStream_t>(stream));
+}
+
+int catan_step_sample_host_groups(catan_env_t* const* envs, int n_groups, void* const* actions_io_host, int action_format, float* const* reward_host,
                                   uint8_t* const* info_host, void* const* streams, int rounds, long long* done_seen) {
+  if (action_format != CATAN_ACTIONS_I32 && action_format != CATAN_ACTIONS_U8) return fail("catan_step_sample_host_groups: bad action format");
   if (!envs || !actions_io_host || !reward_host || !info_host || !streams || n_groups <= 0 || rounds < 0) return fail("catan_step_sample_host_groups: bad argument");
   long long seen = 0;
   for (int r = 0; r < rounds; ++r) {
@@ -1287,7 +1328,9 @@ int catan_step_sample_host_groups(catan_env_t* const* envs, int n_groups, int32_
         const int n = envs[g]->n;
         for (int i = 0; i < n; ++i) seen += info[static_cast<size_t>(i) * CATAN_INFO_STRIDE + CATAN_INFO_DONE];
       }
-      if (catan_step_sample_host_async(envs[g], actions_io_host[g], reward_host[g], info_host[g], streams[g])) return -1;
+      if (action_format == CATAN_ACTIONS_U8 ? catan_step_sample_host_async_u8(envs[g], static_cast<uint8_t*>(actions_io_host[g]), reward_host[g], info_host[g], streams[g])
+                                            : catan_step_sample_host_async(envs[g], static_cast<int32_t*>(actions_io_host[g]), reward_host[g], info_host[g], streams[g]))
+        return -1;
     }
   }
   if (done_seen) *done_seen += seen;

@@ -122,12 +122,14 @@ class VecCatanEnv:
 
     def step_sample_host_async(self, actions_io: np.ndarray, reward: np.ndarray = None, info: np.ndarray = None) -> None:
         """``step_sample`` with pinned host buffers, not synchronised: ``actions_io`` is applied and overwritten with the next
-        random-legal actions; valid once the current stream has been synchronised."""
+        random-legal actions; valid once the current stream has been synchronised.  int32 rows, or uint8 rows (one byte per
+        word, 255 = -1: the compact transport, catan_step_sample_host_async_u8)."""
         def p(a):
             return C.c_void_p(0 if a is None else a.ctypes.data)
-        assert actions_io.dtype == np.int32 and actions_io.flags.c_contiguous
-        _lib.check(self.lib.catan_step_sample_host_async(self._h, p(actions_io), p(reward), p(info), self._stream()))
-        self.kernel_launches += LAUNCHES_PER_STEP
+        assert actions_io.dtype in (np.int32, np.uint8) and actions_io.flags.c_contiguous
+        fn = self.lib.catan_step_sample_host_async if actions_io.dtype == np.int32 else self.lib.catan_step_sample_host_async_u8
+        _lib.check(fn(self._h, p(actions_io), p(reward), p(info), self._stream()))
+        self.kernel_launches += LAUNCHES_PER_STEP + (2 if actions_io.dtype == np.uint8 else 0)
 
     def reset_host(self, obs: np.ndarray = None, masks: np.ndarray = None, info: np.ndarray = None) -> None:
         def p(a):
@@ -254,13 +256,14 @@ class HostEnvGroups:
     group in turn it waits for the group's previous step, reads the ``done`` flags of its info rows, and issues its next step from
     the actions in ``actions[g]`` (pinned; overwritten with the next random-legal actions, as ``step_sample_host_async``)."""
 
-    def __init__(self, envs):
+    def __init__(self, envs, packed_actions: bool = False):
         self.envs = list(envs)
+        self.packed = bool(packed_actions)      # the one-byte-per-word host transport of action rows (catan_step_sample_host_async_u8)
         G = len(self.envs)
         dev = self.envs[0].device
         self.lib = self.envs[0].lib
         self.streams = [torch.cuda.Stream(device=e.device) for e in self.envs]
-        self.actions = [torch.empty((e.n_envs, L.ACTION_WORDS), dtype=torch.int32).pin_memory() for e in self.envs]
+        self.actions = [torch.empty((e.n_envs, L.ACTION_WORDS), dtype=torch.uint8 if self.packed else torch.int32).pin_memory() for e in self.envs]
         self.reward = [torch.empty((e.n_envs, 4), dtype=torch.float32).pin_memory() for e in self.envs]
         self.info = [torch.zeros((e.n_envs, L.INFO_STRIDE), dtype=torch.uint8).pin_memory() for e in self.envs]
         arr = C.c_void_p * G
@@ -277,14 +280,15 @@ class HostEnvGroups:
         for e, s, a in zip(self.envs, self.streams, self.actions):
             with torch.cuda.stream(s):
                 d = e.sample_random()
+                if self.packed:
+                    d = torch.where(d < 0, torch.full_like(d, 255), d).to(torch.uint8)
                 a.copy_(d, non_blocking=True)
-                d.record_stream(s)
 
     def pump(self, rounds: int = 1) -> None:
-        _lib.check(self.lib.catan_step_sample_host_groups(self._envs, len(self.envs), self._act, self._rew, self._info, self._streams,
-                                                          int(rounds), C.byref(self.done_seen)))
+        _lib.check(self.lib.catan_step_sample_host_groups(self._envs, len(self.envs), self._act, 1 if self.packed else 0, self._rew, self._info,
+                                                          self._streams, int(rounds), C.byref(self.done_seen)))
         for e in self.envs:
-            e.kernel_launches += LAUNCHES_PER_STEP * int(rounds)
+            e.kernel_launches += (LAUNCHES_PER_STEP + (2 if self.packed else 0)) * int(rounds)   # (+ unpack / pack of the byte rows)
 
     def synchronize(self) -> None:
         for s in self.streams:

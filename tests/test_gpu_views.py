@@ -232,9 +232,11 @@ def test_library_graph_replay_is_the_same_step():
     assert int(a_env.err_flags().any()) == 0 and int(b_env.err_flags().any()) == 0
 
 
-def test_host_env_groups_pump_is_the_per_handle_loop():
+@pytest.mark.parametrize("packed", [False, True])
+def test_host_env_groups_pump_is_the_per_handle_loop(packed):
     """catan_step_sample_host_groups (one library call per round over several handles in flight) == the same handles stepped one
-    by one with catan_step_sample_host_async: actions, reward, info rows, final state; the done flags it read add up"""
+    by one with catan_step_sample_host_async: actions, reward, info rows, final state; the done flags it read add up.  packed: the
+    groups move their action rows as one byte per word (catan_step_sample_host_async_u8), the per-handle loop as int32"""
     import numpy as np
     from settlers_of_catan_rl_b200 import VecCatanEnv, layout as L
     from settlers_of_catan_rl_b200.vec_env import HostEnvGroups
@@ -246,7 +248,7 @@ def test_host_env_groups_pump_is_the_per_handle_loop():
             e.reset()
         return envs
     a_envs, b_envs = make(), make()
-    groups = HostEnvGroups(a_envs)
+    groups = HostEnvGroups(a_envs, packed_actions=packed)
     groups.prime()
     h = [(torch.empty((m, L.ACTION_WORDS), dtype=torch.int32).pin_memory(), torch.empty((m, 4), dtype=torch.float32).pin_memory(),
           torch.zeros((m, L.INFO_STRIDE), dtype=torch.uint8).pin_memory()) for m in sizes]
@@ -263,7 +265,11 @@ def test_host_env_groups_pump_is_the_per_handle_loop():
                 torch.cuda.synchronize()
         groups.synchronize()
         for k in range(len(sizes)):
-            assert torch.equal(groups.actions[k], h[k][0]) and torch.equal(groups.reward[k], h[k][1]) and torch.equal(groups.info[k], h[k][2]), (r, k)
+            want = h[k][0]
+            if packed:
+                assert int(want.max()) < 255
+                want = torch.where(want < 0, torch.full_like(want, 255), want).to(torch.uint8)
+            assert torch.equal(groups.actions[k], want) and torch.equal(groups.reward[k], h[k][1]) and torch.equal(groups.info[k], h[k][2]), (r, k)
     assert groups.done_seen.value == done_b and done_b > 0
     for ea, eb in zip(a_envs, b_envs):
         assert np.array_equal(ea.export_state(), eb.export_state())
