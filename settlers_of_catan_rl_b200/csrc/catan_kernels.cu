@@ -1,32 +1,35 @@
 // catan_kernels.cu — sm_100a kernels + C ABI of the vectorised Catan engine (see include/catan_b200.h).
 //
-// One env step is six launches on two streams (catan_game.cuh holds the game logic; records are lane-interleaved
-// chunks of 32 games, and every kernel below works on whole chunks with one game per lane):
+// One env step is six launches on three streams, replayed as one CUDA graph (catan_game.cuh holds the game logic; records are
+// lane-interleaved chunks of 32 games, and every kernel below works on whole chunks with one game per lane):
 //
 //   caller's stream
-//   transition_kernel    one block per chunk, staged in shared memory.  Warp 0: ONE THREAD PER GAME for translate +
-//                        validate + the scalar part of apply_action, then the incremental longest-road update of the
-//                        games that placed a road / settlement (t_lr_fast: ~93 % are settled by two tiny walks).  The
-//                        other warps: the data-parallel follow-ups (dice payout, belief updates), one warp per game and
-//                        one lane per item.  A game whose longest road needs a real search is queued and copied into a
-//                        staging chunk.
-//   encode_kernel        one block per chunk: warp 0 does done / reward / info (+ auto-reset), the legal-action masks as
-//                        bit sets and the fused random-legal sampler; nine more warps produce one piece of the packed
-//                        observation row each (tile pieces as bit sets expanded in registers, player blocks and card
-//                        lists through a 128-byte window per thread).  The board scans behind the placement masks are
-//                        shared by all ten warps, one warp per game that needs one.  Queued games are left out.
+//   transition_kernel    one block per chunk, the HOT range of the chunk staged in shared memory (TMA bulk copy).  The games are
+//                        sorted by action type and the four warps take eight each: translate + validate + the scalar part of
+//                        apply_action, ONE THREAD PER GAME.  Then warp 0: the incremental longest-road update of the games that
+//                        placed a road / settlement (t_lr_fast: ~93 % are settled by two tiny walks); the other warps: the
+//                        data-parallel follow-ups (dice payout, belief updates), one warp per game and one lane per item.  A
+//                        game whose longest road needs a real search, or that ended, is queued and copied into a staging chunk.
+//   encode_kernel<ROLE_ROWS>   one block of four warps per chunk: the packed observation rows, built as bit images in registers
+//                        and written as 256-bit streaming stores.  Queued games are left out.
+//   encode_kernel<ROLE_MASKS>  one block of four warps per chunk: done / reward / info, the legal-action masks as bit sets (the
+//                        board scans behind the placement masks one warp per game that needs one) and the fused random-legal sampler.
 //
-//   library's high-priority stream (forked after the transition, joined at the end of the step)
+//   library's high-priority stream 1 (forked after the transition, joined at the end of the step)
 //   lr_slow_kernel       one 512-thread block per queued update: the paths through the new road -- or, when the stored
 //                        length cannot be trusted, the reference's full enumeration (game.py:843-862) -- as a pool of
 //                        16-byte subtree tasks that the lanes drain and re-split without barriers (lp_pool).
-//   encode_kernel<LISTED> the same encode for the queued games, on their staging chunks
-//                        (each block copies its games from the staging chunk to their home records at the end, and the last
-//                        block of the launch banks and clears the queue counters: queue_block_done)
+//   encode_kernel<LISTED> the whole encode (eight warps) for the searched games, on their staging chunks; each block copies its
+//                        games home at the end, and the last block of the launch banks and clears the queue counters.
+//
+//   library's high-priority stream 2
+//   encode_kernel<LISTED> the same for the games that ended in this step: done / reward, Board.reset + Game.reset (serial per
+//                        game, hence off the main path), rows and masks of the new game; one game per block.
 //
 // Why the search is not inside a thread-per-game kernel: its cost varies by four orders of magnitude between games and
-// would stall 31 other games per unit of imbalance; why it runs on a second stream: it is latency-bound (a few hundred
-// dependent walk steps) and touches 0.3 % of the games, so it hides completely behind the encode of the others.
+// would stall 31 other games per unit of imbalance; why it runs on its own stream: it is latency-bound (a few hundred
+// dependent walk steps) and touches 0.3 % of the games.  (Since round 2 it no longer hides behind the encode of the others:
+// profiles/r2_notes.md.)
 #include <cuda_runtime.h>
 
 #include "device_scope.cuh"

@@ -1,7 +1,7 @@
 """Python mirror of ``include/catan_layout.h``: packed observation / mask / action / state layouts.
 
 The numbers here are the contract between the CUDA kernels and the PyTorch side; a CPU test
-(`tests/test_layout.py`) checks every constant against the values the built library reports.
+(`tests/test_abi.py`) checks every constant against the values the built library reports.
 
 Reference citations: observation pieces ``env/wrapper.py:52-83, :491-709``; mask heads
 ``env/wrapper.py:168-185``; action heads ``env/wrapper.py:114-166``; state ``game/game.py:1013-1091``.
