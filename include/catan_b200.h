@@ -55,7 +55,8 @@ int catan_num_envs(const catan_env_t* env);
 int catan_set_config(catan_env_t* env, const catan_config_t* cfg);
 
 /* Output buffers (device): obs uint8[n][CATAN_OBS_STRIDE], masks uint8[n][CATAN_MASK_STRIDE],
- * reward float[n][4] (by player index), info uint8[n][CATAN_INFO_STRIDE].  16-byte aligned. */
+ * reward float[n][4] (by player index), info uint8[n][CATAN_INFO_STRIDE].  16-byte aligned; obs 32-byte aligned (its rows are
+ * written with 256-bit stores). */
 int catan_bind(catan_env_t* env, uint8_t* obs_dev, uint8_t* masks_dev, float* reward_dev, uint8_t* info_dev);
 
 /* EnvWrapper.reset (env/wrapper.py:30-34) for every env (reset_mask_dev == NULL) or for envs whose

@@ -1187,6 +1187,7 @@ int catan_bind(catan_env_t* env, uint8_t* obs_dev, uint8_t* masks_dev, float* re
   if ((reinterpret_cast<uintptr_t>(obs_dev) | reinterpret_cast<uintptr_t>(masks_dev) | reinterpret_cast<uintptr_t>(reward_dev) |
        reinterpret_cast<uintptr_t>(info_dev)) & 15)
     return fail("output buffers must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(obs_dev) & 31) return fail("the observation buffer must be 32-byte aligned (rows are written with 256-bit stores)");
   env->obs = obs_dev; env->masks = masks_dev; env->reward = reward_dev; env->info = info_dev;
   drop_graphs(env);
   return 0;
