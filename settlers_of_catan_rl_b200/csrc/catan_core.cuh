@@ -363,6 +363,27 @@ CATAN_FN_NOINLINE void lp_pool(const uint64_t* adj, const uint64_t* adjb, int sw
 #undef CATAN_LP_CAND
 }
 
+// One round of the level-synchronous opening (CATAN_LP_RUN): the lane consumes task `idx` of the ring and appends one task per
+// untried neighbour (the cursors: ctl[0] first live task, ctl[1] write cursor; barriers between rounds are the caller's).
+CATAN_FN void lp_open_level(const uint64_t* adj, const uint64_t* adjb, int sw, int32_t* ctl, LpTask* ring, int ring_mask, int idx,
+                            int& lbest, int& steps) {
+  const LpTask tk = ring[idx & ring_mask];
+  const uint64_t vis = tk.visited;
+  uint64_t c = ((sw >= 0 && !((vis >> (sw < 0 ? 0 : sw)) & 1ull)) ? adjb[tk.node] : adj[tk.node]) & ~vis;
+  ++steps;
+  if (lbest < tk.depth) lbest = tk.depth;
+  if (!c) return;
+  int need = 0;
+  for (uint64_t t = c; t; t &= t - 1) ++need;
+  int w = fetch_add_i32(&ctl[1], need);
+  for (; c; c &= c - 1, ++w) {
+    const int t = ctz64(c);
+    LpTask& nt = ring[w & ring_mask];
+    nt.visited = vis | (1ull << t); nt.node = static_cast<uint8_t>(t); nt.depth = static_cast<uint8_t>(tk.depth + 1);
+    nt.seq = static_cast<uint32_t>(w) + 1u;
+  }
+}
+
 // Driver shared by the group-local and the block-cooperative callers: SYNC_ is the barrier of the participating threads,
 // leader_ is true for exactly one of them.  The leader seeds the pool: one task per corner with an outgoing arc
 // (start_ < 0), or the single corner start_.  lanes_ = number of participating threads (>= 1; the ring holds at least
@@ -373,14 +394,45 @@ CATAN_FN_NOINLINE void lp_pool(const uint64_t* adj, const uint64_t* adjb, int sw
     SYNC_;                                                                                                                 \
     if (leader_) {                                                                                                         \
       int n_ = 0;                                                                                                          \
-      for (int v_ = 0; v_ < 54; ++v_) {                                                                                    \
-        if ((start_) >= 0 ? v_ != (start_) : (adj_)[v_] == 0ull) continue;                                                 \
+      for (int v_ = (start_) >= 0 ? (start_) : 0; v_ < ((start_) >= 0 ? (start_) + 1 : 54); ++v_) {                        \
+        if ((start_) < 0 && (adj_)[v_] == 0ull) continue;                                                                  \
         LpTask& tk_ = (ring_)[n_];                                                                                         \
         tk_.visited = 1ull << v_; tk_.node = static_cast<uint8_t>(v_); tk_.depth = 0; tk_.seq = static_cast<uint32_t>(++n_); \
       }                                                                                                                    \
       (ctl_)[0] = 0; (ctl_)[1] = n_; (ctl_)[2] = n_; (ctl_)[3] = 0;                                                                    \
     }                                                                                                                      \
     SYNC_;                                                                                                                 \
+    /* Level-synchronous opening (>= 32 lanes): as long as the frontier of the search tree fits the lanes, every lane unfolds ONE */ \
+    /* open subtree by one level per round (lp_open_level) -- a deep, narrow tree (a chain of roads: 64-256 walk steps at ~200   */ \
+    /* cycles each for one walking lane) is finished in `depth` rounds, and a bushy one reaches the pool with a task for every   */ \
+    /* lane instead of growing there one hand-over at a time (profiles/r2_notes.md).  While the frontier fits ONE warp the       */ \
+    /* rounds are that warp's alone (a warp barrier costs a fifth of a block barrier); then the whole group joins.               */ \
+    if ((lanes_) >= 32) {                                                                                                  \
+      int lbest_ = 0, steps_ = 0;                                                                                          \
+      if ((plane_) < 32) {                                                                                                 \
+        for (int round_ = 0; round_ < 64; ++round_) {                                                                      \
+          const int lo_ = vload_i32(&(ctl_)[0]), hi_ = vload_i32(&(ctl_)[1]), nf_ = hi_ - lo_;                             \
+          wsync();                                                                                                         \
+          if (nf_ == 0 || nf_ > 32 || 4 * nf_ > (cap_) - 64) break;                                                        \
+          if ((plane_) < nf_) lp_open_level(adj_, adjb_, sw_, ctl_, ring_, (cap_) - 1, lo_ + (plane_), lbest_, steps_);    \
+          if (leader_) (ctl_)[0] = hi_;                                                                                    \
+          wsync();                                                                                                         \
+        }                                                                                                                  \
+      }                                                                                                                    \
+      SYNC_;                                                                                                               \
+      for (int round_ = 0; round_ < 64; ++round_) {                                                                        \
+        const int lo_ = vload_i32(&(ctl_)[0]), hi_ = vload_i32(&(ctl_)[1]), nf_ = hi_ - lo_;                               \
+        SYNC_;                                               /* everybody has read the cursors of this round */            \
+        if (nf_ == 0 || nf_ > (lanes_) || 4 * nf_ > (cap_) - 64) break;                                                    \
+        if ((plane_) < nf_) lp_open_level(adj_, adjb_, sw_, ctl_, ring_, (cap_) - 1, lo_ + (plane_), lbest_, steps_);      \
+        if (leader_) (ctl_)[0] = hi_;                        /* this level is consumed */                                  \
+        SYNC_;                                               /* the next level and the cursors are visible */              \
+      }                                                                                                                    \
+      if (lbest_) smax_i32(best_, lbest_);                                                                                 \
+      if (steps_) fetch_add_i32(&(ctl_)[3], steps_);                                                                       \
+      if (leader_) (ctl_)[2] = vload_i32(&(ctl_)[1]) - vload_i32(&(ctl_)[0]);   /* what is left for the pool */             \
+      SYNC_;                                                                                                               \
+    }                                                                                                                      \
     lp_pool(adj_, adjb_, sw_, ctl_, best_, path_, lanes_, plane_, ring_, (cap_) - 1, (lanes_) < 4 ? 2 : (lanes_) / 2);   \
     SYNC_;                                                                                                                 \
   } while (0)

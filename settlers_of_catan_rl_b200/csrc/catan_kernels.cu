@@ -459,6 +459,15 @@ __global__ void __launch_bounds__(kLrSlowThreads, CATAN_LR_MIN_BLOCKS) lr_slow_k
     const long long t_start = clock64();
     bool was_full = true;
     if (tid == 0) { S.steps = 0; S.tasks = 0; }
+    // The search reads a few dozen fields of the game one after the other (adjacency build, stored lengths, t_lr_apply), each a
+    // round trip to L2 on the staging chunk: 8-33 us of a typical search were this latency.  All threads touch the record's bytes
+    // once, side by side, so that those reads hit L1.
+    {
+      unsigned acc = 0;
+      for (int k = tid; k < static_cast<int>(sizeof(GameRec)); k += kLrSlowThreads) acc += g.raw<uint8_t>(k & ~0) ;
+      if (acc == 0xffffffffu) S.tasks = -1;                          // (keeps the loads)
+    }
+    __syncthreads();
     if (kind == CATAN_LR_ROAD && loc != 0xff && !g.lr_dirty(pid - 1)) {
       was_full = false;
       // the stored length is exact: only the paths through the new road can beat it
