@@ -391,17 +391,17 @@ CATAN_FN void lp_open_level(const uint64_t* adj, const uint64_t* adjb, int sw, i
 #define CATAN_LP_RUN(adj_, adjb_, sw_, start_, ctl_, best_, path_, lanes_, plane_, ring_, cap_, leader_, SYNC_)            \
   do {                                                                                                                     \
     for (int v_ = (plane_); v_ < (cap_); v_ += (lanes_)) (ring_)[v_].seq = 0u;   /* no task of an earlier search is valid */ \
+    if (leader_) { (ctl_)[0] = 0; (ctl_)[1] = 0; (ctl_)[2] = 0; (ctl_)[3] = 0; }                                           \
     SYNC_;                                                                                                                 \
-    if (leader_) {                                                                                                         \
-      int n_ = 0;                                                                                                          \
-      for (int v_ = (start_) >= 0 ? (start_) : 0; v_ < ((start_) >= 0 ? (start_) + 1 : 54); ++v_) {                        \
-        if ((start_) < 0 && (adj_)[v_] == 0ull) continue;                                                                  \
-        LpTask& tk_ = (ring_)[n_];                                                                                         \
-        tk_.visited = 1ull << v_; tk_.node = static_cast<uint8_t>(v_); tk_.depth = 0; tk_.seq = static_cast<uint32_t>(++n_); \
-      }                                                                                                                    \
-      (ctl_)[0] = 0; (ctl_)[1] = n_; (ctl_)[2] = n_; (ctl_)[3] = 0;                                                                    \
+    /* the seeds: the single corner start_, or (every lane its share of the corners) each corner with an outgoing arc */   \
+    for (int v_ = (start_) >= 0 ? ((leader_) ? (start_) : 54) : (plane_); v_ < 54; v_ += (start_) >= 0 ? 54 : (lanes_)) {  \
+      if ((start_) < 0 && (adj_)[v_] == 0ull) continue;                                                                    \
+      const int n_ = fetch_add_i32(&(ctl_)[1], 1);                                                                         \
+      LpTask& tk_ = (ring_)[n_];                                                                                           \
+      tk_.visited = 1ull << v_; tk_.node = static_cast<uint8_t>(v_); tk_.depth = 0; tk_.seq = static_cast<uint32_t>(n_) + 1u; \
     }                                                                                                                      \
     SYNC_;                                                                                                                 \
+    if ((lanes_) < 32) { if (leader_) (ctl_)[2] = (ctl_)[1]; SYNC_; }                                                      \
     /* Level-synchronous opening (>= 32 lanes): as long as the frontier of the search tree fits the lanes, every lane unfolds ONE */ \
     /* open subtree by one level per round (lp_open_level) -- a deep, narrow tree (a chain of roads: 64-256 walk steps at ~200   */ \
     /* cycles each for one walking lane) is finished in `depth` rounds, and a bushy one reaches the pool with a task for every   */ \
