@@ -105,6 +105,7 @@ struct LrCtl {                // per-step queue counters; queue_finish() banks t
   int32_t count, slow_count;  // longest-road updates of this step; those that went to lr_slow_kernel (= length of its queue)
   int32_t rs_count, pad_;     // games that ended in this step and are reset on their own stream (= length of rs_queue)
   int32_t blocks_done[2];     // blocks of the two queues' encode launches that are through: the last one banks and clears its queue's counters
+  int32_t search_claim, pad2_;   // next unclaimed entry of the search queue (lr_slow_kernel's blocks take the searches one by one)
   unsigned long long total, slow_total, rs_total;   // the same, summed over all earlier steps
   unsigned long long dbg[6];  // lr_slow_kernel diagnostics: cycles sum / max, walk steps sum / max per search; full enumerations; tasks
   unsigned long long hist[3][24];   // log2 histograms: cycles of a search, walk steps of a search, cycles of the LONGEST search of a step
@@ -407,6 +408,7 @@ struct alignas(16) LrSmem {
   int32_t best[4];
   int32_t ctl[CATAN_LP_CTL_WORDS];
   int32_t steps, tasks;      // diagnostics: walk steps and tasks of the current update
+  int32_t job;               // the queue entry this block works on
 };
 
 __device__ __forceinline__ int block_longest_path(LrSmem& S, const GameView& g, int pid, int tid) {
@@ -452,7 +454,14 @@ __global__ void __launch_bounds__(kLrSlowThreads, CATAN_LR_MIN_BLOCKS) lr_slow_k
     for (int i = tid; i < static_cast<int>(sizeof(Topo) / 16); i += kLrSlowThreads) dst[i] = src[i];
   }
   __syncthreads();
-  for (int j = static_cast<int>(blockIdx.x); j < count; j += static_cast<int>(gridDim.x)) {
+  // A steady-state step queues about as many searches as there are resident blocks (~290 of 296) and their lengths differ by an
+  // order of magnitude: the blocks CLAIM the searches one by one instead of striding over the queue.
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.job = atomicAdd(&P.lr_ctl->search_claim, 1);
+    __syncthreads();
+    const int j = S.job;
+    if (j >= count) break;
     const uint64_t en = P.lr_slow_queue[j];
     const GameView g = game_view(P.stage, static_cast<size_t>(j));
     const int pid = static_cast<int>((en >> 32) & 0xff), loc = static_cast<int>((en >> 40) & 0xff), kind = static_cast<int>((en >> 48) & 0xff);
@@ -501,7 +510,7 @@ __global__ void __launch_bounds__(kLrSlowThreads, CATAN_LR_MIN_BLOCKS) lr_slow_k
 __device__ __forceinline__ void queue_finish(LrCtl* c, int kind) {
   if (kind == 0) {
     c->total += static_cast<unsigned long long>(c->count); c->slow_total += static_cast<unsigned long long>(c->slow_count);
-    c->count = 0; c->slow_count = 0;
+    c->count = 0; c->slow_count = 0; c->search_claim = 0;
     if (c->step_max) { c->hist[2][min(23, 63 - __clzll(static_cast<long long>(c->step_max)))] += 1ull; c->step_max = 0ull; }
   } else {
     c->rs_total += static_cast<unsigned long long>(c->rs_count);
@@ -870,6 +879,7 @@ struct catan_env {
   // catan_set_graphs: every distinct step call (entry point + buffer pointers) is captured once into a CUDA graph on an internal
   // stream and replayed on the caller's stream afterwards: one driver call per step instead of ~20 (9 launches, 6 event calls, copies)
   bool trans_direct = true;           // transition_kernel<DIRECT> (see there)
+  size_t enc_pad_bytes = 0;           // extra dynamic shared memory of the rows / masks launches: caps their blocks per SM (room for the search blocks)
   bool rows_beside = false;           // the rows launch of a step on the library's rows stream, beside the masks launch
   bool use_graphs = false;
   cudaStream_t capture_stream = nullptr;
@@ -934,11 +944,11 @@ static int launch_encode(catan_env* env, EnvParams P, int first, int count, cuda
     cudaStream_t rs = (tev || !env->rows_beside) ? stream : env->rows_stream;
     if (rs != stream) CATAN_CUDA(cudaStreamWaitEvent(rs, env->ev_fork, 0));
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, false, catanb::ROLE_ROWS>, game_blocks(first, count),
-                                         catanb::kRowsThreads, catanb::enc_smem_bytes(catanb::ROLE_ROWS), rs, P));
+                                         catanb::kRowsThreads, catanb::enc_smem_bytes(catanb::ROLE_ROWS) + env->enc_pad_bytes, rs, P));
     if (tev) CATAN_CUDA(cudaEventRecord(tev[3], stream));
     if (rs != stream) CATAN_CUDA(cudaEventRecord(env->ev_join_rows, rs));
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<catanb::MODE_STEP, SAMPLE, false, catanb::ROLE_MASKS>, game_blocks(first, count),
-                                         catanb::kMasksThreads, catanb::enc_smem_bytes(catanb::ROLE_MASKS), stream, P));
+                                         catanb::kMasksThreads, catanb::enc_smem_bytes(catanb::ROLE_MASKS) + env->enc_pad_bytes, stream, P));
     if (rs != stream) CATAN_CUDA(cudaStreamWaitEvent(stream, env->ev_join_rows, 0));
   } else {
     CATAN_CUDA(launch_with_record_window(env, catanb::encode_kernel<MODE, false, false, catanb::ROLE_BOTH>,
@@ -1153,10 +1163,10 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
 #define CATAN_ENC_ATTR(K_, BYTES_)                                                                                         \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(BYTES_)); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, false, false, ROLE_ROWS>), enc_smem_bytes(ROLE_ROWS))
-    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, true, false, ROLE_ROWS>), enc_smem_bytes(ROLE_ROWS))
-    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, false, false, ROLE_MASKS>), enc_smem_bytes(ROLE_MASKS))
-    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, true, false, ROLE_MASKS>), enc_smem_bytes(ROLE_MASKS))
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, false, false, ROLE_ROWS>), enc_smem_bytes(ROLE_ROWS) + 32768)
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, true, false, ROLE_ROWS>), enc_smem_bytes(ROLE_ROWS) + 32768)
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, false, false, ROLE_MASKS>), enc_smem_bytes(ROLE_MASKS) + 32768)
+    CATAN_ENC_ATTR((encode_kernel<MODE_STEP, true, false, ROLE_MASKS>), enc_smem_bytes(ROLE_MASKS) + 32768)
     CATAN_ENC_ATTR((encode_kernel<MODE_STEP, false, true, ROLE_BOTH>), enc_bytes)
     CATAN_ENC_ATTR((encode_kernel<MODE_STEP, true, true, ROLE_BOTH>), enc_bytes)
     CATAN_ENC_ATTR((encode_kernel<MODE_RESET, false, false, ROLE_BOTH>), enc_bytes)
@@ -1164,6 +1174,7 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
 #undef CATAN_ENC_ATTR
   }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::transition_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  env->enc_pad_bytes = getenv("CATAN_ENC_PAD_KB") ? static_cast<size_t>(atoi(getenv("CATAN_ENC_PAD_KB"))) * 1024 : 0;
   env->rows_beside = getenv("CATAN_ROWS_BESIDE") != nullptr && atoi(getenv("CATAN_ROWS_BESIDE")) != 0;   // (measured: 0.300 ms per step beside, 0.279 in front)
   env->trans_direct = !(getenv("CATAN_TRANS_DIRECT") != nullptr && atoi(getenv("CATAN_TRANS_DIRECT")) == 0);   // (0: stage whole chunks)
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::lr_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(catanb::LrSmem)));
