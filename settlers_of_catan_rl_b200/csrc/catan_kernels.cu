@@ -1174,6 +1174,10 @@ int catan_create(int n_envs, int device, uint64_t seed, uint64_t first_env_id, c
 #undef CATAN_ENC_ATTR
   }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::transition_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // DIRECT: 16 blocks x 11.4 KB = 182 KB of shared memory per SM; the rest of the 256 KB is L1 for the cold fields touched in place
+  // and for the stack of the rule functions
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(catanb::transition_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 getenv("CATAN_TRANS_CARVEOUT") ? atoi(getenv("CATAN_TRANS_CARVEOUT")) : 80);
   env->enc_pad_bytes = getenv("CATAN_ENC_PAD_KB") ? static_cast<size_t>(atoi(getenv("CATAN_ENC_PAD_KB"))) * 1024 : 0;
   env->rows_beside = getenv("CATAN_ROWS_BESIDE") != nullptr && atoi(getenv("CATAN_ROWS_BESIDE")) != 0;   // (measured: 0.300 ms per step beside, 0.279 in front)
   env->trans_direct = !(getenv("CATAN_TRANS_DIRECT") != nullptr && atoi(getenv("CATAN_TRANS_DIRECT")) == 0);   // (0: stage whole chunks)
