@@ -59,7 +59,10 @@ __device__ const Topo d_topo = CATAN_TOPO_INITIALIZER;
 
 // ---- launch shapes ------------------------------------------------------------------------------
 constexpr int kTransWarps = 4;              // transition_kernel: warps per chunk of 32 games ...
-constexpr int kLrBatch = 2;                 // incremental longest road: games walked at a time per rule warp
+#ifndef CATAN_LR_BATCH
+#define CATAN_LR_BATCH 6
+#endif
+constexpr int kLrBatch = CATAN_LR_BATCH;                 // incremental longest road: games walked at a time per rule warp
 constexpr int kTransThreads = kTransWarps * 32;
 constexpr int kRowWarps = CATAN_OBS_TILE_PARTS;  // encode_kernel: warps that write observation rows (a tile part and a player part each) ...
 constexpr int kEncWarps = 2 * kRowWarps;         // ... and as many that share the per-game scalar work (done / reward, masks, sampler)
