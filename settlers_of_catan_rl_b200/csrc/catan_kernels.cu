@@ -228,6 +228,7 @@ struct alignas(128) TransSmem {
   uint8_t order[kTransWarps][32];   // the chunk's games sorted by action type (one copy per warp: no barrier needed)
   uint64_t und[kLrBatch][54];   // incremental longest road: neighbour tables of the games being walked
   uint8_t follow_list[32];
+  int follow_claim;           // next unclaimed entry of follow_list
 };
 
 // DIRECT = false stages the whole chunk in shared memory (TMA in, TMA out).  DIRECT = true stages only its HOT range (GameRec: flags,
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kTransThreads, DIRECT ? CATAN_TRANS_DIRECT_BLO
     mbar_init(&S.mbar);
     if (DIRECT) bulk_to_shared(S.chunk, home + static_cast<size_t>(CATAN_HOT_BEGIN) * 32, kHotBytes, &S.mbar);
     else chunk_to_shared(S.chunk, home, &S.mbar);
-    S.n_follow = 0;
+    S.n_follow = 0; S.follow_claim = 0;
   }
   {
     const int4* src = reinterpret_cast<const int4*>(&d_topo);
@@ -374,13 +375,20 @@ __global__ void __launch_bounds__(kTransThreads, DIRECT ? CATAN_TRANS_DIRECT_BLO
       P.side[i] = static_cast<uint32_t>(tmp.err) | (static_cast<uint32_t>(tmp.acted_pid) << 8) | (static_cast<uint32_t>(tmp.act_type) << 16) |
                   (static_cast<uint32_t>(tmp.roll_info) << 24) | ((slow || ends) ? 0x80000000u : 0u);
     CATAN_MARK(2);
-  } else {
+  }
+  {
+    // the follow-ups of the chunk's games, one warp per game: every warp claims the next one (warp 0 joins when its longest-road
+    // updates are done; the slowest warp of the slowest block is what the kernel waits for)
     const int nf = S.n_follow;
-    for (int j = warp - 1; j < nf; j += kTransWarps - 1) {
+    for (;;) {
+      int j = 0;
+      if (lane == 0) j = atomicAdd(&S.follow_claim, 1);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= nf) break;
       const GameView g = CATAN_TVIEW(S.follow_list[j]);
       t_followups_group(g, S.topo, S.tmp[g.lane], lane, 32);
     }
-    CATAN_MARK(3);
+    if (warp != 0) CATAN_MARK(3);
   }
   chunk_written();
   __syncthreads();
