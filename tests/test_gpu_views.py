@@ -70,6 +70,31 @@ def test_step_timing_hooks():
     assert a.read_timing()[0] == 0
 
 
+def test_search_diagnostics_add_up():
+    """catan_read_lr_stats / catan_read_lr_histograms / the per-stream timing of catan_read_timing: every search is counted once
+    in each of the two per-search histograms, a step contributes at most one entry to the longest-search histogram, and the
+    rows launch is part of the encode time"""
+    from settlers_of_catan_rl_b200 import VecCatanEnv
+    env = VecCatanEnv(4096, seed=4)
+    env.reset()
+    acts = env.sample_random()
+    steps = 600
+    for _ in range(steps):
+        env.step_sample(acts)
+    st, h = env.lr_stats(), env.lr_histograms()
+    assert st[0] > 0 and 0 < st[1] <= st[0]                     # updates, of which searched by a block
+    assert int(h[0].sum()) == int(st[1]) and int(h[1].sum()) == int(st[1])
+    assert 0 < int(h[2].sum()) <= steps
+    env.set_timing(True)
+    for _ in range(40):
+        env.step_sample(acts)
+    n, t_ms, e_ms, rows_ms = env.read_timing(detail=True)
+    env.set_timing(False)
+    assert n == 40 and 0.0 < rows_ms < e_ms
+    assert set(env.stream_timing) == {"search_wait", "search", "search_rest", "reset_stream", "after_transition"}
+    assert env.stream_timing["after_transition"] >= e_ms - 1e-6
+
+
 def test_a_step_can_be_captured_in_a_cuda_graph():
     """the six launches of a step (two streams, forked and joined with events) are capturable: replaying the graph advances
     the games exactly like direct calls"""
