@@ -92,7 +92,7 @@ class VecCatanEnv:
         return out
 
     def step_sample(self, actions_io: torch.Tensor):
-        """One call (six launches on two streams, the sampler fused into the last): apply ``actions_io`` and overwrite it with the next random-legal actions."""
+        """One call (six launches on three streams, replayed as one CUDA graph with set_graphs; the sampler fused into the masks launch): apply ``actions_io`` and overwrite it with the next random-legal actions."""
         assert actions_io.dtype == torch.int32 and actions_io.is_cuda and actions_io.is_contiguous()
         _lib.check(self.lib.catan_step_sample(self._h, _ptr(actions_io), self._stream()))
         self.kernel_launches += LAUNCHES_PER_STEP
